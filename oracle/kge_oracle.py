@@ -1,0 +1,574 @@
+"""CPU restatement of the KGE-Keras triple-scoring hot path (TEST INFRASTRUCTURE, see oracle/__init__.py).
+
+Every function cites the reference lines it follows (paths relative to /root/reference).
+Two precisions are offered everywhere: `np.float32` mirrors the reference op by op (TF computes in
+fp32, NumPy broadcasting == TF broadcasting), `np.float64` is the "truth" the fp32 numbers are
+judged against.
+
+Parity status: the TF-dependent functions here are "parity unpinned" (no reference golden vectors
+exist and TF is not installable here); the NumPy functions are pinned by tests/golden/ (made by
+running the reference's own code through oracle/ref_ast.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# score kinds -- numeric values are shared with include/kgeb200.h (kgeb_score_kind)
+DISTMULT, TRANSE_L1, TRANSE_L2, COMPLEX, HOLE = 0, 1, 2, 3, 4
+SCORE_KINDS = {"DistMult": DISTMULT, "TransE_L1": TRANSE_L1, "TransE_L2": TRANSE_L2,
+               "ComplEx": COMPLEX, "HolE": HOLE}
+
+# loss kinds -- shared with kgeb_loss_kind
+POINTWISE_HINGE, POINTWISE_LOGISTIC, POINTWISE_SQUARE, PAIRWISE_HINGE, PAIRWISE_LOGISTIC, PAIRWISE_SQUARE = range(6)
+LOSS_NAMES = {  # utils.py:321-330 (spelling "wize" is the reference's)
+    "pointwize_hinge": POINTWISE_HINGE, "pointwize_logistic": POINTWISE_LOGISTIC,
+    "pointwize_square_loss": POINTWISE_SQUARE, "pairwize_hinge": PAIRWISE_HINGE,
+    "pairwize_logistic": PAIRWISE_LOGISTIC, "pairwize_square_loss": PAIRWISE_SQUARE,
+}
+# pair modes -- shared with kgeb_pair_mode
+PAIRED, ALLPAIRS = 0, 1
+# optimizers -- shared with kgeb_opt_kind
+OPT_SGD, OPT_ADAGRAD, OPT_LAZY_ADAM, OPT_ADAM_DENSE = range(4)
+# corruption modes of the Philox sampler -- shared with kgeb_corrupt_mode
+CORRUPT_BOTH, CORRUPT_HEAD, CORRUPT_TAIL, CORRUPT_EITHER = range(4)
+
+EPSILON = 1e-6  # utils.py:12
+
+
+# --------------------------------------------------------------------------------------------
+# tables
+# --------------------------------------------------------------------------------------------
+def glorot_uniform(rng: np.random.Generator, rows: int, cols: int, dtype=np.float32):
+    """models.py:87-88 GlorotUniform: U(+-sqrt(6/(fan_in+fan_out))) with fan = (rows, cols)."""
+    lim = np.sqrt(6.0 / (rows + cols))
+    return rng.uniform(-lim, lim, size=(rows, cols)).astype(dtype)
+
+
+def dyadic_table(rng: np.random.Generator, rows: int, cols: int, lo=-4, hi=4, denom=4.0):
+    """Small dyadic rationals k/denom: every product/sum the score functions form is exact in
+    fp32 (and in bf16 x bf16 -> fp32), so scores and ranks are independent of summation order."""
+    return (rng.integers(lo, hi + 1, size=(rows, cols)) / denom).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------------
+# score functions  (models.py:134-237)
+# --------------------------------------------------------------------------------------------
+def gather(E, R, idx):
+    """EmbeddingModel.call, models.py:140-150: s,p,o = unstack(inputs,axis=1); Embedding lookups."""
+    idx = np.asarray(idx).astype(np.int64)
+    return E[idx[:, 0]], R[idx[:, 1]], E[idx[:, 2]]
+
+
+def circular_correlation_fft(a, b):
+    """HolE.func, models.py:231-234: real(ifft(conj(fft(a)) * fft(b))) in complex64 (or complex128)."""
+    ctype = np.complex64 if a.dtype == np.float32 else np.complex128
+    fa = np.fft.fft(a.astype(ctype), axis=-1)
+    fb = np.fft.fft(b.astype(ctype), axis=-1)
+    return np.real(np.fft.ifft(np.conj(fa) * fb, axis=-1)).astype(a.dtype)
+
+
+def circular_correlation_direct(a, b):
+    """x_k = sum_i a_i b_{(i+k) mod d}  (equals the FFT form)."""
+    d = a.shape[-1]
+    out = np.zeros_like(a)
+    for k in range(d):
+        out[..., k] = np.sum(a * np.roll(b, -k, axis=-1), axis=-1)
+    return out
+
+
+def score(kind, s, p, o, gamma=12.0, hole_fft=True):
+    """func(s,p,o) of the four hot-path models; dtype follows the inputs.
+
+    DistMult models.py:171-172, TransE 186-190, ComplEx 212-222, HolE 231-237."""
+    dt = s.dtype
+    if kind == DISTMULT:
+        return np.sum(s * p * o, axis=-1)
+    if kind in (TRANSE_L1, TRANSE_L2):
+        r = s + p - o
+        n = np.sum(np.abs(r), axis=-1) if kind == TRANSE_L1 else np.sqrt(np.sum(r * r, axis=-1))
+        if gamma > 0:  # models.py:187-190
+            return (dt.type(gamma) - n).astype(dt)
+        return n
+    if kind == COMPLEX:
+        d = s.shape[-1] // 2
+        sr, si = s[..., :d], s[..., d:]
+        pr, pi = p[..., :d], p[..., d:]
+        orr, oi = o[..., :d], o[..., d:]
+        s1 = sr * pr * orr
+        s2 = pr * si * oi
+        s3 = pi * sr * oi
+        s4 = pi * si * orr
+        return np.sum(s1 + s2 + s3 - s4, axis=-1)
+    if kind == HOLE:
+        x = circular_correlation_fft(s, o) if hole_fft else circular_correlation_direct(s, o)
+        return np.sum(p * x, axis=-1)
+    raise KeyError(kind)
+
+
+def score_triples(kind, E, R, idx, gamma=12.0, dtype=np.float32, hole_fft=True):
+    """EmbeddingModel.call with dp inactive (models.py:134-162): (B,3) ids -> (B,) scores."""
+    s, p, o = gather(E.astype(dtype), R.astype(dtype), idx)
+    return score(kind, s, p, o, gamma, hole_fft)
+
+
+def score_abs_terms(kind, E, R, idx, gamma=12.0):
+    """sum of |terms| entering each score, fp64: the scale an fp32 summation error is relative to."""
+    s, p, o = gather(E.astype(np.float64), R.astype(np.float64), idx)
+    if kind == DISTMULT:
+        return np.sum(np.abs(s * p * o), axis=-1)
+    if kind in (TRANSE_L1, TRANSE_L2):
+        return np.abs(gamma) + np.sum(np.abs(s) + np.abs(p) + np.abs(o), axis=-1)
+    if kind == COMPLEX:
+        d = s.shape[-1] // 2
+        a = np.abs(s[..., :d]) + np.abs(s[..., d:])
+        b = np.abs(p[..., :d]) + np.abs(p[..., d:])
+        c = np.abs(o[..., :d]) + np.abs(o[..., d:])
+        return np.sum(a * b * c, axis=-1)
+    if kind == HOLE:
+        return np.sum(np.abs(p), axis=-1) * np.sqrt(np.sum(s * s, -1) * np.sum(o * o, -1)) + \
+            np.sum(np.abs(p) * circular_correlation_direct(np.abs(s), np.abs(o)), axis=-1)
+    raise KeyError(kind)
+
+
+def score_grads(kind, s, p, o, gamma=12.0):
+    """Analytic d score / d (s, p, o); checked against torch autograd in tests."""
+    if kind == DISTMULT:
+        return p * o, s * o, s * p
+    if kind in (TRANSE_L1, TRANSE_L2):
+        r = s + p - o
+        if kind == TRANSE_L1:
+            g = np.sign(r)
+        else:
+            g = r / np.sqrt(np.sum(r * r, axis=-1, keepdims=True))
+        sg = -1.0 if gamma > 0 else 1.0
+        g = (sg * g).astype(s.dtype)
+        return g, g, -g
+    if kind == COMPLEX:
+        d = s.shape[-1] // 2
+        sr, si = s[..., :d], s[..., d:]
+        pr, pi = p[..., :d], p[..., d:]
+        orr, oi = o[..., :d], o[..., d:]
+        ds = np.concatenate([pr * orr + pi * oi, pr * oi - pi * orr], axis=-1)
+        dp = np.concatenate([sr * orr + si * oi, sr * oi - si * orr], axis=-1)
+        do = np.concatenate([sr * pr - pi * si, pr * si + pi * sr], axis=-1)
+        return ds, dp, do
+    if kind == HOLE:
+        d = s.shape[-1]
+        dp = circular_correlation_direct(s, o)           # dp_k = sum_i s_i o_{i+k}
+        ds = np.zeros_like(s)
+        do = np.zeros_like(o)
+        for k in range(d):
+            ds += p[..., k:k + 1] * np.roll(o, -k, axis=-1)   # ds_i = sum_k p_k o_{i+k}
+            do += p[..., k:k + 1] * np.roll(s, k, axis=-1)    # do_j = sum_k p_k s_{j-k}
+        return ds, dp, do
+    raise KeyError(kind)
+
+
+# --------------------------------------------------------------------------------------------
+# losses  (utils.py:288-319) -- NumPy broadcasting == TF broadcasting
+# --------------------------------------------------------------------------------------------
+def _c(dt):
+    # EPSILON+1 is a Python float added to an fp32 tensor -> fp32(1.000001) = 1.00000095367431640625
+    return dt.type(EPSILON + 1)
+
+
+def pointwize_hinge(true, false, margin=1, negative_samples=1, reduce_mean=True):
+    """utils.py:288-289"""
+    dt = true.dtype
+    return np.mean(np.maximum(dt.type(margin) - true, 0)) + np.mean(np.maximum(dt.type(margin) + false, 0))
+
+
+def pointwize_logistic(true, false, margin=1, negative_samples=1, reduce_mean=True):
+    """utils.py:291-292"""
+    c = _c(true.dtype)
+    with np.errstate(over="ignore"):
+        return np.mean(np.log(c + np.exp(-true))) + np.mean(np.log(c + np.exp(false)))
+
+
+def pointwize_square_loss(true, false, margin=1, negative_samples=1, reduce_mean=True):
+    """utils.py:294-295"""
+    dt = true.dtype
+    return np.mean(np.square(dt.type(margin) - true)) + np.mean(np.square(dt.type(margin) + false))
+
+
+def pointwize_cross_entropy(true, false, margin=1, negative_samples=1, reduce_mean=True):
+    """utils.py:297-298; Keras binary_crossentropy on raw scores (third-party, recalled: clip to
+    [1e-7, 1-1e-7], -(y log(p+eps) + (1-y) log(1-p+eps)), mean over the last axis)."""
+    dt = true.dtype
+    eps = dt.type(1e-7)
+
+    def bce(y, pred):
+        pred = np.clip(pred, eps, dt.type(1) - eps)
+        return np.mean(-(y * np.log(pred + eps) + (1 - y) * np.log(1 - pred + eps)), axis=-1)
+    return bce(dt.type(1), true) + bce(dt.type(0), false)
+
+
+def pairwize_hinge(true, false, margin=1, negative_samples=1, reduce_mean=True):
+    """utils.py:300-305"""
+    false = np.reshape(false, (-1, negative_samples))
+    tmp = np.maximum(true.dtype.type(margin) + false - true, 0)
+    return np.mean(tmp) if reduce_mean else tmp
+
+
+def pairwize_logistic(true, false, margin=0, negative_samples=1, reduce_mean=True):
+    """utils.py:307-312"""
+    false = np.reshape(false, (-1, negative_samples))
+    with np.errstate(over="ignore"):
+        tmp = np.log(_c(true.dtype) + np.exp(false - true))
+    return np.mean(tmp) if reduce_mean else tmp
+
+
+def pairwize_square_loss(true, false, margin=0, negative_samples=1, reduce_mean=True):
+    """utils.py:314-319 (sign as written in the reference)"""
+    false = np.reshape(false, (-1, negative_samples))
+    tmp = -np.square(false - true)
+    return np.mean(tmp) if reduce_mean else tmp
+
+
+def loss_function_lookup(name):
+    """utils.py:321-330"""
+    return {
+        "pointwize_hinge": pointwize_hinge,
+        "pointwize_logistic": pointwize_logistic,
+        "pointwize_cross_entropy": pointwize_cross_entropy,
+        "pointwize_square_loss": pointwize_square_loss,
+        "pairwize_hinge": pairwize_hinge,
+        "pairwize_logistic": pairwize_logistic,
+        "pairwize_square_loss": pairwize_square_loss,
+    }[name]
+
+
+def loss_and_coefs(loss_kind, pair_mode, t, f, K, margin):
+    """Loss value and dL/dt (B,), dL/df (Bf,) in the dtype of t.
+
+    PAIRED   : true is (B,1), false (B*K,) -> (B,K)            
+    ALLPAIRS : true is (m,), false (m',) reshaped (m',1): the harness' (m',m) broadcast, tests.py:81
+    pointwise kinds ignore pair_mode."""
+    dt = t.dtype
+    M = dt.type(margin)
+    c = _c(dt)
+    B, Bf = t.shape[0], f.shape[0]
+    with np.errstate(over="ignore", invalid="ignore"):
+        if loss_kind == POINTWISE_HINGE:
+            L = np.mean(np.maximum(M - t, 0)) + np.mean(np.maximum(M + f, 0))
+            return L, -(M - t > 0).astype(dt) / B, (M + f > 0).astype(dt) / Bf
+        if loss_kind == POINTWISE_LOGISTIC:
+            et, ef = np.exp(-t), np.exp(f)
+            L = np.mean(np.log(c + et)) + np.mean(np.log(c + ef))
+            return L, -(et / (c + et)) / B, (ef / (c + ef)) / Bf
+        if loss_kind == POINTWISE_SQUARE:
+            L = np.mean(np.square(M - t)) + np.mean(np.square(M + f))
+            return L, -2 * (M - t) / B, 2 * (M + f) / Bf
+        if pair_mode == PAIRED:
+            F = f.reshape(B, K)
+            T = t.reshape(B, 1)
+        else:
+            F = f.reshape(Bf, 1)
+            T = t.reshape(1, B)
+        X = F - T
+        cnt = dt.type(X.size)
+        if loss_kind == PAIRWISE_HINGE:
+            A = (M + X > 0).astype(dt)
+            L = np.mean(np.maximum(M + X, 0))
+        elif loss_kind == PAIRWISE_LOGISTIC:
+            ex = np.exp(X)
+            A = ex / (c + ex)
+            L = np.mean(np.log(c + ex))
+        elif loss_kind == PAIRWISE_SQUARE:
+            A = -2 * X
+            L = np.mean(-np.square(X))
+        else:
+            raise KeyError(loss_kind)
+        if pair_mode == PAIRED:
+            return L, -A.sum(axis=1) / cnt, (A / cnt).reshape(-1)
+        return L, -A.sum(axis=0) / cnt, A.sum(axis=1) / cnt
+
+
+# --------------------------------------------------------------------------------------------
+# backward + optimizer (third-party Keras/TF semantics, recalled)
+# --------------------------------------------------------------------------------------------
+def dense_grads(kind, E, R, idx, dscore, gamma=12.0, dtype=np.float64):
+    """IndexedSlices -> dense: sum of dscore_m * dscore/drow over every reference to a row."""
+    s, p, o = gather(E.astype(dtype), R.astype(dtype), idx)
+    ds, dp, do = score_grads(kind, s, p, o, gamma)
+    w = np.asarray(dscore, dtype=dtype)[:, None]
+    gE = np.zeros(E.shape, dtype)
+    gR = np.zeros(R.shape, dtype)
+    idx = np.asarray(idx).astype(np.int64)
+    np.add.at(gE, idx[:, 0], w * ds)
+    np.add.at(gE, idx[:, 2], w * do)
+    np.add.at(gR, idx[:, 1], w * dp)
+    tE = np.zeros(E.shape[0], bool)
+    tR = np.zeros(R.shape[0], bool)
+    tE[idx[:, 0]] = True
+    tE[idx[:, 2]] = True
+    tR[idx[:, 1]] = True
+    return gE, gR, tE, tR
+
+
+def opt_update(opt_kind, P, G, touched, state, lr, step, b1=0.9, b2=0.999, eps=1e-7):
+    """One optimizer step on a table, in the dtype of P.  state = (m, v) for Adam, (acc,) for Adagrad.
+
+    SGD: p -= lr g.  Adagrad (Keras: initial accumulator 0.1): acc += g^2; p -= lr g/(sqrt(acc)+eps).
+    Adam (Keras OptimizerV2): lr_t = lr sqrt(1-b2^t)/(1-b1^t); m = b1 m+(1-b1) g; v = b2 v+(1-b2) g^2;
+    p -= lr_t m/(sqrt(v)+eps).  LAZY_ADAM applies it to touched rows only; ADAM_DENSE to every row with
+    g = 0 for untouched ones (what Keras' sparse apply does: dense decay of m and v)."""
+    dt = P.dtype
+    P = P.copy()
+    state = [x.copy() for x in state]
+    rows = np.ones(P.shape[0], bool) if opt_kind == OPT_ADAM_DENSE else np.asarray(touched, bool)
+    g = np.where(np.asarray(touched, bool)[:, None], G, 0).astype(dt)[rows]
+    if opt_kind == OPT_SGD:
+        P[rows] -= dt.type(lr) * g
+    elif opt_kind == OPT_ADAGRAD:
+        acc = state[0]
+        acc[rows] += g * g
+        P[rows] -= dt.type(lr) * g / (np.sqrt(acc[rows]) + dt.type(eps))
+    else:
+        m, v = state
+        lr_t = dt.type(lr * np.sqrt(1.0 - b2 ** step) / (1.0 - b1 ** step))
+        m[rows] = dt.type(b1) * m[rows] + dt.type(1 - b1) * g
+        v[rows] = dt.type(b2) * v[rows] + dt.type(1 - b2) * g * g
+        P[rows] -= lr_t * m[rows] / (np.sqrt(v[rows]) + dt.type(eps))
+    return P, state
+
+
+def train_step(kind, loss_kind, pair_mode, E, R, pos, neg, K, margin, gamma, opt_kind, state_E, state_R,
+               lr, step, dtype=np.float64):
+    """One full step of the harness' loop (tests.py:72-87,130-134) with dp=0, regularization=0:
+    scores -> loss -> gradients (dedup by id) -> optimizer.  Returns dict."""
+    E = E.astype(dtype)
+    R = R.astype(dtype)
+    t = score_triples(kind, E, R, pos, gamma, dtype, hole_fft=False)
+    f = score_triples(kind, E, R, neg, gamma, dtype, hole_fft=False)
+    L, dt_, df_ = loss_and_coefs(loss_kind, pair_mode, t, f, K, margin)
+    idx = np.concatenate([np.asarray(pos), np.asarray(neg)], axis=0)
+    gE, gR, tE, tR = dense_grads(kind, E, R, idx, np.concatenate([dt_, df_]), gamma, dtype)
+    E2, sE = opt_update(opt_kind, E, gE, tE, [x.astype(dtype) for x in state_E], lr, step)
+    R2, sR = opt_update(opt_kind, R, gR, tR, [x.astype(dtype) for x in state_R], lr, step)
+    return dict(loss=L, pos_scores=t, neg_scores=f, dpos=dt_, dneg=df_, gE=gE, gR=gR, touched_E=tE,
+                touched_R=tR, E=E2, R=R2, state_E=sE, state_R=sR)
+
+
+# --------------------------------------------------------------------------------------------
+# Philox4x32-10 counter-based sampler (new in the B200 build; the host restatement pins the kernel)
+# --------------------------------------------------------------------------------------------
+_PH_M0, _PH_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+_PH_W0, _PH_W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
+_U32 = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(ctr, key):
+    """ctr: (...,4) uint32, key: (...,2) uint32 -> (...,4) uint32.  Random123 Philox4x32-10."""
+    c = [np.asarray(ctr[..., i], dtype=np.uint32).copy() for i in range(4)]
+    k0 = np.asarray(key[..., 0], dtype=np.uint32).copy()
+    k1 = np.asarray(key[..., 1], dtype=np.uint32).copy()
+    with np.errstate(over="ignore"):
+        for r in range(10):
+            p0 = _PH_M0 * c[0].astype(np.uint64)
+            p1 = _PH_M1 * c[2].astype(np.uint64)
+            hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), (p0 & _U32).astype(np.uint32)
+            hi1, lo1 = (p1 >> np.uint64(32)).astype(np.uint32), (p1 & _U32).astype(np.uint32)
+            c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+            if r < 9:
+                k0 = (k0 + _PH_W0).astype(np.uint32)
+                k1 = (k1 + _PH_W1).astype(np.uint32)
+    return np.stack(c, axis=-1)
+
+
+def philox_negatives(pos, N, K, seed, offset, mode=CORRUPT_BOTH):
+    """Negatives exactly as the CUDA sampler draws them (kgeb_negatives / fused train step).
+
+    For positive i and j < K, g = i*K + j: (x,y,z,w) = Philox(ctr=(g_lo, g_hi, off_lo, off_hi), key=seed);
+    head' = (x*N)>>32, tail' = (y*N)>>32; BOTH replaces both (reference behaviour, utils.py:117-120),
+    HEAD/TAIL one side, EITHER picks the side from the top bit of z (1 -> head).  Relation is kept."""
+    pos = np.asarray(pos, dtype=np.int64)
+    B = pos.shape[0]
+    g = np.arange(B * K, dtype=np.uint64)
+    ctr = np.stack([(g & _U32), (g >> np.uint64(32)),
+                    np.full_like(g, np.uint64(offset) & _U32), np.full_like(g, np.uint64(offset) >> np.uint64(32))],
+                   axis=-1).astype(np.uint32)
+    key = np.empty((B * K, 2), np.uint32)
+    key[:, 0] = np.uint64(seed) & _U32
+    key[:, 1] = np.uint64(seed) >> np.uint64(32)
+    r = philox4x32_10(ctr, key).astype(np.uint64)
+    nh = ((r[:, 0] * np.uint64(N)) >> np.uint64(32)).astype(np.int64)
+    nt = ((r[:, 1] * np.uint64(N)) >> np.uint64(32)).astype(np.int64)
+    head_side = (r[:, 2] >> np.uint64(31)).astype(bool)
+    rep = np.repeat(pos, K, axis=0)
+    out = rep.copy()
+    if mode == CORRUPT_BOTH:
+        out[:, 0], out[:, 2] = nh, nt
+    elif mode == CORRUPT_HEAD:
+        out[:, 0] = nh
+    elif mode == CORRUPT_TAIL:
+        out[:, 2] = nt
+    else:
+        out[:, 0] = np.where(head_side, nh, rep[:, 0])
+        out[:, 2] = np.where(head_side, rep[:, 2], nt)
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# reference-style host negatives (utils.py:114-147) -- restated; pinned by tests/golden/negatives_ref.npz
+# --------------------------------------------------------------------------------------------
+def generate_negative(kg, N, negative=2, check_kg=False, corrupt_head=True, corrupt_tail=True):
+    """utils.py:114-121: both s and o uniform in [0,N) (fs drawn first in full, then fo); relation
+    repeated `negative` times consecutively; output (negative*len(kg), 3, 1); flags ignored."""
+    assert corrupt_head or corrupt_tail
+    R = np.repeat(np.asarray([p for _, p, _ in kg]).reshape((-1, 1)), negative, axis=0)
+    fs = np.random.randint(0, N, size=(negative * len(kg), 1))
+    fo = np.random.randint(0, N, size=(negative * len(kg), 1))
+    return np.stack([fs, R, fo], axis=1)
+
+
+def oversample_data(kgs):
+    """utils.py:123-147 without the unused x/y branch: each list resampled WITH replacement to the
+    longest length via random.choices, then squeezed."""
+    from random import choices
+    kgs = [list(kg) for kg in kgs]
+    m = max(map(len, kgs))
+    return [np.squeeze(np.asarray(choices(kg, k=m))) for kg in kgs]
+
+
+# --------------------------------------------------------------------------------------------
+# filtered ranking (utils.py:165-264)
+# --------------------------------------------------------------------------------------------
+def build_filters(filtering_triples):
+    """utils.py:201-205"""
+    from collections import defaultdict
+    filter_h, filter_t = defaultdict(set), defaultdict(set)
+    for s, p, o in filtering_triples:
+        filter_h[(p, o)].add(s)
+        filter_t[(s, p)].add(o)
+    return filter_h, filter_t
+
+
+def all_entity_scores(kind, E, R, triples, side, gamma=12.0, dtype=np.float32, hole_fft=False):
+    """(Q,N) matrix: score of every candidate entity in the `side` slot of each test triple, computed
+    exactly like call() would on the (C+1,3) candidate array of gen_tail_data/gen_head_data."""
+    triples = np.asarray(triples, dtype=np.int64)
+    N = E.shape[0]
+    out = np.empty((len(triples), N), dtype)
+    cand = np.arange(N, dtype=np.int64)
+    for qi, (s, p, o) in enumerate(triples):
+        idx = np.empty((N, 3), np.int64)
+        idx[:, 0] = cand if side == "head" else s
+        idx[:, 1] = p
+        idx[:, 2] = cand if side == "tail" else o
+        out[qi] = score_triples(kind, E, R, idx, gamma, dtype, hole_fft)
+    return out
+
+
+def ranks_from_scores(scores, triples, side, filters):
+    """rank = 1 + #{c not in F u {target} : score_c > score_target}  (utils.py:211-215).
+    `filters` is the dict of sets from build_filters for this side."""
+    triples = np.asarray(triples, dtype=np.int64)
+    ranks = np.empty(len(triples), np.int64)
+    for qi, (s, p, o) in enumerate(triples):
+        tgt = o if side == "tail" else s
+        key = (s, p) if side == "tail" else (p, o)
+        keep = np.ones(scores.shape[1], bool)
+        fl = list(filters.get(key, ()))
+        if fl:
+            keep[np.asarray(fl, dtype=np.int64)] = False
+        keep[tgt] = False
+        ranks[qi] = 1 + int(np.count_nonzero(scores[qi][keep] > scores[qi][tgt]))
+    return ranks
+
+
+def metrics_from_ranks(tail_ranks, head_ranks):
+    """utils.py:216-262: the 15-key dict; denominators len(test_data); combined = (tail+head)/2."""
+    def side(r):
+        r = np.asarray(r, dtype=np.int64)
+        n = float(len(r))
+        return (np.count_nonzero(r <= 1) / n, np.count_nonzero(r <= 3) / n, np.count_nonzero(r <= 10) / n,
+                np.mean(r), np.mean([1 / m for m in r]))
+    t1, t3, t10, tmr, tmrr = side(tail_ranks)
+    h1, h3, h10, hmr, hmrr = side(head_ranks)
+    return {'tail_hits@1': t1, 'tail_hits@3': t3, 'tail_hits@10': t10, 'tail_mr': tmr, 'tail_mrr': tmrr,
+            'head_hits@1': h1, 'head_hits@3': h3, 'head_hits@10': h10, 'head_mr': hmr, 'head_mrr': hmrr,
+            'hits@1': (t1 + h1) / 2, 'hits@3': (t3 + h3) / 2, 'hits@10': (t10 + h10) / 2,
+            'mr': (tmr + hmr) / 2, 'mrr': (tmrr + hmrr) / 2}
+
+
+def validate(kind, E, R, test_data, filtering_triples, gamma=12.0, dtype=np.float32, chunk=256):
+    """Vectorised restatement of validate (utils.py:199-264) for the four hot-path models."""
+    filter_h, filter_t = build_filters(filtering_triples)
+    test = np.asarray(test_data, dtype=np.int64)
+    tr, hr = [], []
+    for i in range(0, len(test), chunk):
+        part = test[i:i + chunk]
+        tr.append(ranks_from_scores(all_entity_scores(kind, E, R, part, "tail", gamma, dtype), part, "tail", filter_t))
+        hr.append(ranks_from_scores(all_entity_scores(kind, E, R, part, "head", gamma, dtype), part, "head", filter_h))
+    tr, hr = np.concatenate(tr), np.concatenate(hr)
+    return metrics_from_ranks(tr, hr), tr, hr
+
+
+# --------------------------------------------------------------------------------------------
+# 1-N query vectors and the sequential-k arithmetic of the CUDA-core rank kernel
+# --------------------------------------------------------------------------------------------
+def query_vectors(kind, E, R, triples, side, dtype=np.float32):
+    """Per-query vector q such that score(candidate c) = op(q, E[c]):
+    DistMult tail s*p / head p*o; ComplEx tail [sr pr - si pi | si pr + sr pi], head
+    [pr or + pi oi | pr oi - pi or]; HolE tail q_j = sum_i s_i p_{(j-i)}, head q_i = sum_k p_k o_{(i+k)};
+    TransE tail a = s+p (dist |a - e|), head: (p, o) kept separately so (e+p)-o keeps the reference's order."""
+    triples = np.asarray(triples, dtype=np.int64)
+    s, p, o = gather(E.astype(dtype), R.astype(dtype), triples)
+    if kind == DISTMULT:
+        return s * p if side == "tail" else p * o
+    if kind == COMPLEX:
+        d = s.shape[-1] // 2
+        sr, si, pr, pi, orr, oi = s[:, :d], s[:, d:], p[:, :d], p[:, d:], o[:, :d], o[:, d:]
+        if side == "tail":
+            return np.concatenate([sr * pr - si * pi, si * pr + sr * pi], axis=1)
+        return np.concatenate([pr * orr + pi * oi, pr * oi - pi * orr], axis=1)
+    if kind == HOLE:
+        d = s.shape[-1]
+        q = np.zeros_like(s)
+        if side == "tail":
+            for i in range(d):   # q_j = sum_i s_i p_{(j-i) mod d}, sequential in i
+                q = q + s[:, i:i + 1] * np.roll(p, i, axis=1)
+        else:
+            for k in range(d):   # q_i = sum_k p_k o_{(i+k) mod d}, sequential in k
+                q = q + p[:, k:k + 1] * np.roll(o, -k, axis=1)
+        return q
+    if kind in (TRANSE_L1, TRANSE_L2):
+        return s + p if side == "tail" else np.concatenate([p, o], axis=1)
+    raise KeyError(kind)
+
+
+def seqk_scores(kind, q, Erows, side, gamma=12.0):
+    """Scores op(q, e) accumulated sequentially over k in fp32 with separate multiply and add roundings --
+    bit-for-bit what kgeb_rank_1n's CUDA-core kernels compute (they use __fmul_rn/__fadd_rn, no FMA)."""
+    q = q.astype(np.float32)
+    Er = Erows.astype(np.float32)
+    Q, Nn, W = q.shape[0], Er.shape[0], Er.shape[1]
+    acc = np.zeros((Q, Nn), np.float32)
+    if kind in (DISTMULT, COMPLEX, HOLE):
+        for k in range(W):
+            acc = acc + q[:, k:k + 1] * Er[None, :, k]
+        return acc
+    for k in range(W):
+        if side == "tail":
+            r = q[:, k:k + 1] - Er[None, :, k]
+        else:
+            r = (Er[None, :, k] + q[:, k:k + 1]) - q[:, W + k:W + k + 1]
+        acc = acc + (np.abs(r) if kind == TRANSE_L1 else r * r)
+    if kind == TRANSE_L2:
+        acc = np.sqrt(acc)
+    return (np.float32(gamma) - acc) if gamma > 0 else acc
+
+
+def filter_csr(triples, side, filters):
+    """Sorted per-query filter lists in CSR form (offsets int64[Q+1], ids int32[nnz]); target removed."""
+    triples = np.asarray(triples, dtype=np.int64)
+    offs = np.zeros(len(triples) + 1, np.int64)
+    ids = []
+    for qi, (s, p, o) in enumerate(triples):
+        key = (s, p) if side == "tail" else (p, o)
+        tgt = o if side == "tail" else s
+        fl = sorted(int(x) for x in filters.get(key, ()) if int(x) != tgt)
+        ids.extend(fl)
+        offs[qi + 1] = len(ids)
+    return offs, np.asarray(ids, dtype=np.int32)
