@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the B200 triple-scoring hot path on BASELINE.json's metric.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...)
+
+Workload (config.workload): BASELINE.json configs[1] -- TransE-L1, dim 200, WN18RR shape (40 943 entities, 11 relations),
+synthetic Glorot tables and uniform synthetic triples.  One "step" = one fused train step over B positives
+with K in-kernel Philox negatives each: gather -> score -> pairwise hinge -> gradient scatter -> LazyAdam on touched rows.
+`value` = train triples/s incl. negatives, B*(1+K)/t_step, inputs resident in HBM, CUDA-event timed per step with an L2
+flush between steps (the 33 MB table + Adam state fit the 126 MB L2, so without the flush every step would be L2-hot).
+`e2e` = the same step through the public API with HOST index buffers (pinned H2D of the batch, D2H of the loss) in the
+timed region.  `eval` = filtered 1-N ranking queries/s (tail+head), entity rows sharded over the ranks, integer partial
+counts all-reduced over NCCL.  Training on this shape is "replicas only" at N > 1 (tables fit one GPU).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "kge-keras_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+WORKLOAD = dict(name="C2 TransE-L1 dim=200 WN18RR-shape (N=40943, R=11)", N=40943, R=11, d=200, gamma=12.0, K=10,
+                margin=1.0, test_triples=3134)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return dict(hbm_gbs=float(p["hbm_gbs"]), bf16_tflops=float(p["bf16_tflops"]), source="MEASURED_PEAKS.json (measured)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="B200_PROFILING.md fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.err = index, [], set(), False, None, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                     "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.002)
+        except Exception as e:  # NVML missing: report it, never fake numbers
+            self.err = repr(e)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "error": self.err}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def glorot(rng, rows, cols):
+    lim = np.sqrt(6.0 / (rows + cols))
+    return rng.uniform(-lim, lim, size=(rows, cols)).astype(np.float32)
+
+
+def synth_filter_csr(rng, Q, N, lam):
+    """Poisson(lam) known-true ids per query, sorted, unique (WN18RR tail mean 5.4, head 23.5)."""
+    lens = rng.poisson(lam, Q)
+    offs = np.zeros(Q + 1, np.int64)
+    offs[1:] = np.cumsum(lens)
+    ids = np.empty(offs[-1], np.int32)
+    for q in range(Q):
+        ids[offs[q]:offs[q + 1]] = np.sort(rng.choice(N, lens[q], replace=False))
+    return offs, ids
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the CPU port of the reference step (TensorFlow is not installable here), all host threads."""
+    if rank != 0:
+        return
+    from oracle import cpu_port, kge_oracle as ko
+    import torch
+    w = WORKLOAD
+    rng = np.random.default_rng(0)
+    E, R = glorot(rng, w["N"], w["d"]), glorot(rng, w["R"], w["d"])
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    r = cpu_port.time_train(ko.TRANSE_L1, E, R, args.batch, w["K"], w["gamma"], steps=args.steps, warmup=max(1, min(args.warmup, 2)),
+                            threads=threads, budget_s=120.0)
+    line = {
+        "impl": "reference", "metric": "train_triples_per_s", "value": r["triples_per_s"], "unit": "triples/s",
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["name"], "batch_positives": args.batch, "negatives_per_positive": w["K"],
+                   "loss": "pairwize_hinge (paired)", "optimizer": "lazy sparse Adam (torch.optim.SparseAdam)"},
+        "cpu_baseline": {"value": r["triples_per_s"], "unit": "triples/s", "cores": r["threads"], "kind": "port",
+                         "sample": f"{r['steps']} full steps of the same workload (PyTorch-CPU fp32 restatement; TensorFlow not installable)"},
+        "e2e": {"value": r["triples_per_s"], "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16384, help="positives per step")
+    ap.add_argument("--corrupt", default="both", choices=["both", "head", "tail", "either"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eval-steps", type=int, default=10)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from KGEkeras import _abi as abi
+    from KGEkeras._engine import Engine
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = WORKLOAD
+    N, R, d, K, B = w["N"], w["R"], w["d"], w["K"], args.batch
+    corrupt = {"both": abi.CORRUPT_BOTH, "head": abi.CORRUPT_HEAD, "tail": abi.CORRUPT_TAIL, "either": abi.CORRUPT_EITHER}[args.corrupt]
+    rng = np.random.default_rng(0)  # same tables on every rank (replicated), different batches per rank
+    E0, R0 = glorot(rng, N, d), glorot(rng, R, d)
+    eng = Engine(abi.TRANSE_L1, N, R, d, d, gamma=w["gamma"], E=E0, R=R0)
+    brng = np.random.default_rng(1000 + rank)
+    steps, warm = args.steps, max(args.warmup, 3)
+    nb = steps + warm
+    host_batches = torch.from_numpy(np.stack([brng.integers(0, N, (nb, B)), brng.integers(0, R, (nb, B)),
+                                              brng.integers(0, N, (nb, B))], axis=2).astype(np.int32)).pin_memory()
+    dev_batches = host_batches.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    step_kw = dict(K=K, loss_kind=abi.PAIRWISE_HINGE, pair_mode=abi.PAIRED, margin=w["margin"], corrupt_mode=corrupt, seed=1234 + rank)
+    opt_kw = dict(opt_kind=abi.LAZY_ADAM, lr=1e-3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # untimed diagnostic: unique rows touched by one step (for the algorithmic-bytes figure)
+    res = eng.forward_backward(dev_batches[0], None, want_neg=True, offset=0, **step_kw, opt_kind=abi.LAZY_ADAM)
+    U_E, U_R = int(eng.tE.sum().item()), int(eng.tR.sum().item())
+    eng.apply_optimizer(**opt_kw)
+
+    for i in range(warm):
+        flush.zero_()
+        eng.train_step(dev_batches[i], None, offset=i, **step_kw, **opt_kw)
+    # ---- timed: K steps, device-resident inputs, per-step CUDA events, L2 flushed between steps ----------------------
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = eng.launches
+    t_wall0 = time.perf_counter()
+    for i in range(steps):
+        flush.zero_()
+        ev[i][0].record()
+        eng.forward_backward(dev_batches[warm + i], None, offset=warm + i, **step_kw, opt_kind=abi.LAZY_ADAM)
+        ev[i][1].record()
+        eng.apply_optimizer(**opt_kw)
+        ev[i][2].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = eng.launches - l0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    t_fb = np.array([e[0].elapsed_time(e[1]) for e in ev])
+    t_op = np.array([e[1].elapsed_time(e[2]) for e in ev])
+    t_step_ms = float((t_fb + t_op).sum())
+    tt = torch.tensor([t_step_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_total_ms = float(tt.item())
+    value = world * steps * B * (1 + K) / (t_total_ms * 1e-3)
+
+    # ---- e2e: host index buffers, H2D + step + D2H(loss) timed per step on the host clock ---------------------------
+    e2e_t = 0.0
+    n_e2e = min(steps, 50)
+    for i in range(3 + n_e2e):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        batch = host_batches[(warm + i) % nb].to(dev, non_blocking=True)
+        r = eng.train_step(batch, None, offset=10_000 + i, **step_kw, **opt_kw)
+        loss_val = r["loss"].item()
+        if i >= 3:
+            e2e_t += time.perf_counter() - t0
+    te = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_e2e * B * (1 + K) / float(te.item())
+
+    # ---- filtered 1-N evaluation: rows sharded over ranks, integer counts all-reduced ------------------------------
+    erng = np.random.default_rng(7)
+    nt = w["test_triples"]
+    tri = np.stack([erng.integers(0, N, nt), erng.integers(0, R, nt), erng.integers(0, N, nt)], axis=1).astype(np.int32)
+    csr_t, csr_h = synth_filter_csr(erng, nt, N, 5.4), synth_filter_csr(erng, nt, N, 23.5)
+    per = -(-N // world)
+    rr = (rank * per, min(N, (rank + 1) * per))
+    tri_d = torch.from_numpy(tri).to(dev)
+    csr_t = tuple(torch.from_numpy(a).to(dev) for a in csr_t)
+    csr_h = tuple(torch.from_numpy(a).to(dev) for a in csr_h)
+    eval_ms = []
+    l1 = eng.launches
+    for i in range(3 + args.eval_steps):
+        flush.zero_()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ct = eng.rank_counts(tri_d, abi.SIDE_TAIL, csr_t[0], csr_t[1], row_range=rr)
+        ch = eng.rank_counts(tri_d, abi.SIDE_HEAD, csr_h[0], csr_h[1], row_range=rr)
+        if world > 1:
+            both = torch.cat([ct, ch])
+            dist.all_reduce(both)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            eval_ms.append(e0.elapsed_time(e1))
+    eval_launches = (eng.launches - l1) // (3 + args.eval_steps)
+    tev = torch.tensor([float(np.sum(eval_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tev, op=dist.ReduceOp.MAX)
+    eval_qps = args.eval_steps * 2 * nt / (float(tev.item()) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    # algorithmic bytes: fused fwd+bwd kernel reads each unique touched row once and writes its gradient once
+    # -> 8 B/element + 12 B of ids per positive; the optimizer reads g,p,m,v and writes p,m,v,g(=0) -> 32 B/element.
+    bytes_fb = 8.0 * (d * U_E + d * U_R) + 12.0 * B
+    bytes_op = 32.0 * (d * U_E + d * U_R)
+    bytes_step = (4 + 24) * (d * U_E + d * U_R) + 12.0 * B  # compulsory bytes of the whole step
+    fb_ms, op_ms = float(t_fb.mean()), float(t_op.mean())
+    dom = ("k_train_fwd_bwd", bytes_fb, fb_ms) if fb_ms >= op_ms else ("k_opt_update (E and R)", bytes_op, op_ms)
+    ach = dom[1] / (dom[2] * 1e-3) / 1e9
+    ach_step = bytes_step / ((fb_ms + op_ms) * 1e-3) / 1e9
+    # gather traffic the kernel actually asks the memory system for (no reuse): 2 entity rows read + 2 written per triple
+    gather_bytes = B * (1 + K) * (4 * d * 4.0) + B * (2 * d * 4.0)
+    line = {
+        "metric": "train_triples_per_s", "value": value, "unit": "triples/s", "n_gpus": world, "steps": steps, "warmup": warm,
+        "ms_per_step": t_total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["name"], "batch_positives": B, "negatives_per_positive": K, "corruption": args.corrupt,
+                   "loss": "pairwize_hinge (paired)", "optimizer": "LazyAdam (touched rows)", "negatives": "in-kernel Philox4x32-10",
+                   "l2": "flushed between steps (256 MiB write); table+state 98 MB < 126 MB L2",
+                   "multi_gpu": "replicas only for training; eval rows sharded + NCCL all-reduce of int32 counts",
+                   "unique_entity_rows_per_step": U_E, "unique_relation_rows_per_step": U_R},
+        "e2e": {"value": e2e_value, "unit": "triples/s", "h2d_bytes_per_step": int(B * 3 * 4), "d2h_bytes_per_step": 4,
+                "steps": n_e2e, "api": "Engine.train_step(host int32 batch) -> loss.item()"},
+        "gpu_launches": int(launches),
+        "kernel_ms": {"k_train_fwd_bwd": fb_ms, "k_opt_update_x2": op_ms, "wall_ms_per_step_incl_flush": 1e3 * t_wall / steps},
+        "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                     "note": "algorithmic = compulsory bytes with perfect on-chip reuse of the %d unique rows; the kernel's "
+                             "no-reuse gather+scatter request volume is %.0f MB/launch (L2-resident table)" % (U_E, gather_bytes / 1e6)},
+        "roofline_step": {"bound": "hbm", "achieved": ach_step, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_step / pk["hbm_gbs"],
+                          "bytes_step": bytes_step, "formula": "(4+24)*(We*U_E+Wr*U_R)+12*B (SURVEY 8d, Adam)"},
+        "eval": {"metric": "filtered_eval_queries_per_s", "value": eval_qps, "unit": "queries/s", "queries_per_pass": 2 * nt,
+                 "ms_per_pass": float(np.mean(eval_ms)), "passes": args.eval_steps, "scaling": "strong",
+                 "gpu_launches_per_pass": int(eval_launches),
+                 "fp32_alu_tflops": (2 * d * nt * N + 3 * d * nt * N) * 1.0 / (float(np.mean(eval_ms)) * 1e-3) / 1e12},
+        "clocks": sampler.summary(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_port, kge_oracle as ko
+        cb = cpu_port.time_train(ko.TRANSE_L1, E0, R0, B, K, w["gamma"], steps=6, warmup=1, threads=os.cpu_count(), budget_s=20.0)
+        ce = cpu_port.time_eval(ko.TRANSE_L1, E0, R0, tri, [tuple(int(x) for x in r) for r in tri[:2000]], w["gamma"],
+                                max_queries=48, budget_s=10.0)
+        line["cpu_baseline"] = {"value": cb["triples_per_s"], "unit": "triples/s", "cores": cb["threads"], "kind": "port",
+                                "sample": f"{cb['steps']} full steps (B={B}, K={K}) of the PyTorch-CPU fp32 restatement; TensorFlow not installable",
+                                "eval_queries_per_s": ce["queries_per_s"], "eval_sample": f"{ce['queries']} queries, NumPy restatement of validate, 1 process"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,148 @@
+/* kgeb200.h -- C ABI of libkgeb200.so: the B200 (sm_100a) triple-scoring hot path of KGE-Keras.
+ *
+ * The reference (NIVA-Knowledge-Graph/KGE-Keras, paths below relative to its root) has NO native/FFI seam:
+ * its library layer calls stock Keras/TF ops.  This header is therefore the seam a maintainer would add
+ * under the unchanged Python signatures; each entry point cites the reference code
+ * whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch / TF types; every pointer named `const float* E`, `idx`, ... is a DEVICE pointer owned
+ *     by the caller (the host framework owns the parameter tables, so get_weights()/init_entities keep working);
+ *   - every call enqueues on the caller's `stream` (a cudaStream_t passed as void*) and returns without
+ *     synchronising; nothing allocates after kgeb_create;
+ *   - return value 0 = ok, negative = kgeb_status; kgeb_last_error() gives the text; nothing throws;
+ *   - a context is bound to one device and one model shape; contexts are independent, a single context is
+ *     not thread-safe;
+ *   - tables are row-major fp32, row stride `ld` floats (ld >= width).  The vectorised kernels need
+ *     ld % 4 == 0 and 16-byte aligned base pointers; anything else returns KGEB_ERR_ALIGNMENT (never a slow
+ *     silent path);
+ *   - ids are int32 [m,3] row-major (s, p, o) as in EmbeddingModel.call (KGEkeras/models.py:140).
+ */
+#ifndef KGEB200_H
+#define KGEB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KGEB_VERSION 100 /* 0.1.0 */
+#if defined(__GNUC__)
+#define KGEB_API __attribute__((visibility("default")))
+#else
+#define KGEB_API
+#endif
+
+typedef struct kgeb_ctx kgeb_ctx;
+typedef void* kgeb_stream; /* cudaStream_t */
+
+typedef enum {
+  KGEB_OK = 0,
+  KGEB_ERR_INVALID = -1,   /* bad argument (null pointer, negative size, unknown enum) */
+  KGEB_ERR_CUDA = -2,      /* a CUDA runtime call failed; text in kgeb_last_error */
+  KGEB_ERR_ALIGNMENT = -3, /* pointer / stride not usable by the vectorised kernels */
+  KGEB_ERR_UNSUPPORTED = -4, /* valid but not implemented combination (e.g. row wider than the kernels handle) */
+  KGEB_ERR_WORKSPACE = -5  /* caller workspace too small */
+} kgeb_status;
+
+/* score functions: DistMult models.py:171-172, TransE 186-190 (norm=1|2), ComplEx 212-222, HolE 231-237 */
+typedef enum { KGEB_DISTMULT = 0, KGEB_TRANSE_L1 = 1, KGEB_TRANSE_L2 = 2, KGEB_COMPLEX = 3, KGEB_HOLE = 4 } kgeb_score_kind;
+
+/* losses utils.py:288-319 (pointwize_cross_entropy is composed on the host from kernel scores) */
+typedef enum {
+  KGEB_POINTWISE_HINGE = 0, KGEB_POINTWISE_LOGISTIC = 1, KGEB_POINTWISE_SQUARE = 2,
+  KGEB_PAIRWISE_HINGE = 3, KGEB_PAIRWISE_LOGISTIC = 4, KGEB_PAIRWISE_SQUARE = 5
+} kgeb_loss_kind;
+
+/* how pairwise losses pair true with false scores:
+ * PAIRED   true (B,1) vs false (B,K)            -- the per-positive pairwise loss
+ * ALLPAIRS true (m,)  vs false (m',1) -> (m',m) -- what tests.py:81 computes through broadcasting */
+typedef enum { KGEB_PAIRED = 0, KGEB_ALLPAIRS = 1 } kgeb_pair_mode;
+
+/* optimizers (tests.py:86 uses Keras 'adam'); ADAM_DENSE = Keras OptimizerV2 sparse-apply semantics
+ * (m, v decayed on every row), LAZY_ADAM = touched rows only */
+typedef enum { KGEB_SGD = 0, KGEB_ADAGRAD = 1, KGEB_LAZY_ADAM = 2, KGEB_ADAM_DENSE = 3 } kgeb_opt_kind;
+
+/* which slot(s) the Philox sampler corrupts; BOTH is what utils.py:117-120 does */
+typedef enum { KGEB_CORRUPT_BOTH = 0, KGEB_CORRUPT_HEAD = 1, KGEB_CORRUPT_TAIL = 2, KGEB_CORRUPT_EITHER = 3 } kgeb_corrupt_mode;
+
+typedef enum { KGEB_SIDE_TAIL = 0, KGEB_SIDE_HEAD = 1 } kgeb_side;
+
+/* ---- lifecycle -------------------------------------------------------------------------------------------- */
+KGEB_API int kgeb_version(void);
+
+/* One context per (device, model).  we/wr = STORED row widths in floats (ComplEx: 2*dim), ldE/ldR = row strides.
+ * Replaces EmbeddingModel.__init__'s table allocation contract, models.py:84-112 (tables stay caller-owned). */
+KGEB_API int kgeb_create(kgeb_ctx** out, int device, int64_t num_entities, int64_t num_relations, int we, int wr, int ldE,
+                int ldR, int score_kind, float gamma);
+KGEB_API int kgeb_destroy(kgeb_ctx* ctx);
+/* Text of the last error on this context (ctx may be NULL: last error of a failed kgeb_create). */
+KGEB_API const char* kgeb_last_error(const kgeb_ctx* ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+KGEB_API int64_t kgeb_launch_count(const kgeb_ctx* ctx);
+KGEB_API int kgeb_num_sms(const kgeb_ctx* ctx);
+
+/* ---- scoring: EmbeddingModel.call + func, models.py:134-162 (dropout inactive) ---------------------------- */
+/* scores[m] = func(E[idx[:,0]], R[idx[:,1]], E[idx[:,2]]) */
+KGEB_API int kgeb_score_fwd(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* idx, int64_t m, float* scores,
+                   kgeb_stream stream);
+/* Registered-gradient half of score_fwd: gE/gR += dscore[m] * d score / d row, touched flags set to 1.
+ * Replaces TF autodiff through Embedding (IndexedSlices) for this path, SURVEY 8a row a19. */
+KGEB_API int kgeb_score_bwd(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* idx, int64_t m, const float* dscore,
+                   float* gE, float* gR, uint8_t* touchedE, uint8_t* touchedR, kgeb_stream stream);
+
+/* ---- negatives: generate_negative utils.py:114-121 re-done as a counter-based device sampler -------------- */
+/* neg[(i*K+j),:] = corrupt(pos[i]) with Philox4x32-10(counter=(i*K+j, offset), key=seed); relation kept. */
+KGEB_API int kgeb_negatives(kgeb_ctx* ctx, const int32_t* pos, int64_t B, int K, uint64_t seed, uint64_t offset,
+                   int corrupt_mode, int32_t* neg, kgeb_stream stream);
+
+/* ---- losses on score vectors: utils.py:288-319 ------------------------------------------------------------ */
+/* loss[0] = loss_weight * L(t, f); dt[B], df[Bf] = loss_weight * dL/dt, dL/df (either may be NULL).
+ * Bf must be B*K for PAIRED pairwise kinds. */
+KGEB_API int kgeb_loss_fwd_bwd(kgeb_ctx* ctx, const float* t, int64_t B, const float* f, int64_t Bf, int K, int loss_kind,
+                      int pair_mode, float margin, float loss_weight, float* loss, float* dt, float* df,
+                      kgeb_stream stream);
+
+/* ---- fused train step forward + gradient (K1): gather, negatives, score, loss, gradient scatter ----------- */
+/* One pass over B positives, each with K negatives: negatives come from `neg` ([B*K,3], index-driven parity
+ * mode) or, when neg == NULL, from the Philox sampler above.  PAIRED pairing for pairwise losses.
+ * Outputs: loss[0]; optional pos_scores[B], neg_scores[B*K], neg_out[B*K,3]; gradients are ADDED into gE/gR
+ * (dense, same shape/stride as the tables) and touched flags set.  HolE and ALLPAIRS are served by the
+ * unfused sequence score_fwd -> loss_fwd_bwd -> score_bwd. */
+KGEB_API int kgeb_train_fwd_bwd(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* pos, int64_t B,
+                       const int32_t* neg, int K, int loss_kind, float margin, float loss_weight, int corrupt_mode,
+                       uint64_t seed, uint64_t offset, float* loss, float* pos_scores, float* neg_scores,
+                       int32_t* neg_out, float* gE, float* gR, uint8_t* touchedE, uint8_t* touchedR,
+                       kgeb_stream stream);
+
+/* ---- sparse optimizer (K2 second half): applies the update to touched rows, zeroes G and the flags -------- */
+/* P, G: [rows, ld]; state0/state1: Adam m,v (or Adagrad accumulator in state0; unused -> NULL). step >= 1. */
+KGEB_API int kgeb_opt_update(kgeb_ctx* ctx, float* P, float* G, uint8_t* touched, int64_t rows, int width, int ld,
+                    float* state0, float* state1, int opt_kind, float lr, float beta1, float beta2, float eps,
+                    int64_t step, kgeb_stream stream);
+
+/* ---- 1-N filtered ranking: validate / gen_tail_data / gen_head_data, utils.py:165-264 --------------------- */
+/* Width in floats of one query vector for `side` (we, or 2*we for TransE head queries). */
+KGEB_API int kgeb_query_width(const kgeb_ctx* ctx, int side);
+/* qvec[q,:] for the queries whose source entity row lies in [row_offset, row_offset+n_rows) of the logical
+ * table (E_shard points at row `row_offset`); other rows of qvec are left untouched (zero them first; with a
+ * row-sharded table all-reduce(sum) qvec afterwards: exactly one rank contributes each row). */
+KGEB_API int kgeb_query_prep(kgeb_ctx* ctx, const float* E_shard, int64_t row_offset, int64_t n_rows, const float* R,
+                    const int32_t* triples, int64_t Q, int side, float* qvec, kgeb_stream stream);
+/* tscore[q] = score of the query's own target entity, computed with the SAME arithmetic as the candidates
+ * (so a candidate that ties the target is never counted).  Written only for targets inside the shard. */
+KGEB_API int kgeb_target_scores(kgeb_ctx* ctx, const float* E_shard, int64_t row_offset, int64_t n_rows, const float* qvec,
+                       const int32_t* triples, int64_t Q, int side, float* tscore, kgeb_stream stream);
+/* counts[q] += #{c in shard, c not in filter(q), c != target(q) : score(q,c) > tscore[q]}   (rank = 1 + sum over
+ * shards).  filt_offsets int64[Q+1] / filt_ids int32[nnz] = CSR of known-true ids per query (may be
+ * NULL/NULL).  Integer partial counts: summing them over any row partition gives bit-identical ranks. */
+KGEB_API int kgeb_rank_1n(kgeb_ctx* ctx, const float* E_shard, int64_t row_offset, int64_t n_rows, const float* qvec,
+                 const float* tscore, const int32_t* triples, int64_t Q, int side, const int64_t* filt_offsets,
+                 const int32_t* filt_ids, int32_t* counts, kgeb_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGEB200_H */

@@ -1,0 +1,76 @@
+"""ctypes binding of libkgeb200.so (include/kgeb200.h).  No CPU fallback: if the library is missing or cannot be
+loaded this module raises, and every non-zero status from the C ABI becomes a KgebError carrying kgeb_last_error()."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+# enum values of include/kgeb200.h
+DISTMULT, TRANSE_L1, TRANSE_L2, COMPLEX, HOLE = range(5)
+POINTWISE_HINGE, POINTWISE_LOGISTIC, POINTWISE_SQUARE, PAIRWISE_HINGE, PAIRWISE_LOGISTIC, PAIRWISE_SQUARE = range(6)
+PAIRED, ALLPAIRS = 0, 1
+SGD, ADAGRAD, LAZY_ADAM, ADAM_DENSE = range(4)
+CORRUPT_BOTH, CORRUPT_HEAD, CORRUPT_TAIL, CORRUPT_EITHER = range(4)
+SIDE_TAIL, SIDE_HEAD = 0, 1
+
+LOSS_KINDS = {  # reference names, utils.py:321-330
+    "pointwize_hinge": POINTWISE_HINGE, "pointwize_logistic": POINTWISE_LOGISTIC,
+    "pointwize_square_loss": POINTWISE_SQUARE, "pairwize_hinge": PAIRWISE_HINGE,
+    "pairwize_logistic": PAIRWISE_LOGISTIC, "pairwize_square_loss": PAIRWISE_SQUARE,
+}
+OPT_KINDS = {"sgd": SGD, "adagrad": ADAGRAD, "lazy_adam": LAZY_ADAM, "adam": ADAM_DENSE}
+STATUS = {0: "OK", -1: "INVALID", -2: "CUDA", -3: "ALIGNMENT", -4: "UNSUPPORTED", -5: "WORKSPACE"}
+
+LIB_PATH = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "lib", "libkgeb200.so"))
+
+
+class KgebError(RuntimeError):
+    def __init__(self, status, text):
+        super().__init__(f"libkgeb200: {STATUS.get(status, status)}: {text}")
+        self.status = status
+
+
+_p, _i, _i64, _u64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float
+
+# name -> (restype, argtypes); mirrors include/kgeb200.h one to one
+PROTOTYPES = {
+    "kgeb_version": (_i, []),
+    "kgeb_create": (_i, [C.POINTER(_p), _i, _i64, _i64, _i, _i, _i, _i, _i, _f]),
+    "kgeb_destroy": (_i, [_p]),
+    "kgeb_last_error": (C.c_char_p, [_p]),
+    "kgeb_launch_count": (_i64, [_p]),
+    "kgeb_num_sms": (_i, [_p]),
+    "kgeb_score_fwd": (_i, [_p, _p, _p, _p, _i64, _p, _p]),
+    "kgeb_score_bwd": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p]),
+    "kgeb_negatives": (_i, [_p, _p, _i64, _i, _u64, _u64, _i, _p, _p]),
+    "kgeb_loss_fwd_bwd": (_i, [_p, _p, _i64, _p, _i64, _i, _i, _i, _f, _f, _p, _p, _p, _p]),
+    "kgeb_train_fwd_bwd": (_i, [_p, _p, _p, _p, _i64, _p, _i, _i, _f, _f, _i, _u64, _u64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "kgeb_opt_update": (_i, [_p, _p, _p, _p, _i64, _i, _i, _p, _p, _i, _f, _f, _f, _f, _i64, _p]),
+    "kgeb_query_width": (_i, [_p, _i]),
+    "kgeb_query_prep": (_i, [_p, _p, _i64, _i64, _p, _p, _i64, _i, _p, _p]),
+    "kgeb_target_scores": (_i, [_p, _p, _i64, _i64, _p, _p, _i64, _i, _p, _p]),
+    "kgeb_rank_1n": (_i, [_p, _p, _i64, _i64, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library (loaded once).  Raises ImportError with the build hint if it is not there."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              f"or `make -C kge-keras_b200/csrc` (there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)  # AttributeError here = header / library mismatch
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(status, ctx=None):
+    if status != 0:
+        msg = lib().kgeb_last_error(ctx)
+        raise KgebError(status, msg.decode() if msg else "")

@@ -1,0 +1,224 @@
+"""Device-side state of one embedding model and the calls into libkgeb200.
+
+PyTorch is used for device memory, streams and (elsewhere) torch.distributed only; every number comes out of the
+hand-written sm_100a kernels behind the C ABI.  There is no CPU path: constructing an Engine without CUDA raises."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _abi as abi
+
+
+def _ptr(t):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def as_idx(x, device):
+    """(m,3) ids in any int/float dtype (the harness feeds float32 ids, tests.py:72-73) -> int32 device tensor."""
+    if isinstance(x, torch.Tensor):
+        t = x.to(device=device, non_blocking=True)
+    else:
+        a = np.asarray(x)
+        if a.ndim == 3 and a.shape[-1] == 1:  # generate_negative returns (n,3,1), utils.py:120
+            a = a[..., 0]
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(device=device, non_blocking=True)
+    if t.dim() == 3 and t.shape[-1] == 1:
+        t = t[..., 0]
+    if t.dim() != 2 or t.shape[1] != 3:
+        raise ValueError(f"expected triples of shape (batch, 3), got {tuple(t.shape)}")
+    return t.to(torch.int32).contiguous()
+
+
+class Engine:
+    """Tables + gradient/optimizer buffers of one model on one GPU, bound to a kgeb context."""
+
+    def __init__(self, kind, num_entities, num_relations, we, wr, gamma=12.0, device=None, E=None, R=None, rng=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("KGEkeras (B200 build) needs a CUDA device: there is no CPU fallback")
+        self.lib = abi.lib()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.kind, self.N, self.R_, self.we, self.wr, self.gamma = kind, int(num_entities), int(num_relations), int(we), int(wr), float(gamma)
+        # zero-padded columns are neutral for DistMult/TransE, so odd widths are padded to the 128-bit granule
+        pad_ok = kind in (abi.DISTMULT, abi.TRANSE_L1, abi.TRANSE_L2)
+        self.we_k = (self.we + 3) // 4 * 4 if pad_ok else self.we
+        self.wr_k = (self.wr + 3) // 4 * 4 if pad_ok else self.wr
+        rng = rng or np.random.default_rng()
+        self.E = self._table(E, self.N, self.we, self.we_k, rng)
+        self.Rel = self._table(R, self.R_, self.wr, self.wr_k, rng)
+        h = C.c_void_p()
+        abi.check(self.lib.kgeb_create(C.byref(h), self.device.index or 0, self.N, self.R_, self.we_k, self.wr_k,
+                                       self.we_k, self.wr_k, kind, self.gamma))
+        self.ctx = h
+        self.gE = self.gR = self.tE = self.tR = None
+        self.opt_state = None
+        self.step = 0
+        self._loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+    def _table(self, init, rows, w, wk, rng):
+        if init is None:  # GlorotUniform, models.py:87-88
+            lim = float(np.sqrt(6.0 / (rows + w)))
+            init = rng.uniform(-lim, lim, size=(rows, w)).astype(np.float32)
+        a = torch.as_tensor(np.asarray(init, dtype=np.float32)) if not isinstance(init, torch.Tensor) else init.detach().to(torch.float32).cpu()
+        if tuple(a.shape) != (rows, w):
+            raise ValueError(f"initial weights have shape {tuple(a.shape)}, expected {(rows, w)}")
+        t = torch.zeros(rows, wk, dtype=torch.float32, device=self.device)
+        t[:, :w] = a.to(self.device)
+        return t
+
+    def __del__(self):
+        try:
+            if getattr(self, "ctx", None):
+                self.lib.kgeb_destroy(self.ctx)
+                self.ctx = None
+        except Exception:
+            pass
+
+    # ---- bookkeeping --------------------------------------------------------------------------------------------
+    @property
+    def launches(self):
+        return int(self.lib.kgeb_launch_count(self.ctx))
+
+    def _check(self, rc):
+        abi.check(rc, self.ctx)
+
+    def _ensure_train_buffers(self, opt_kind):
+        if self.gE is None:
+            self.gE, self.gR = torch.zeros_like(self.E), torch.zeros_like(self.Rel)
+            self.tE = torch.zeros(self.N, dtype=torch.uint8, device=self.device)
+            self.tR = torch.zeros(self.R_, dtype=torch.uint8, device=self.device)
+        if self.opt_state is None or self.opt_state[0] != opt_kind:
+            if opt_kind == abi.SGD:
+                st = (None, None, None, None)
+            elif opt_kind == abi.ADAGRAD:  # Keras Adagrad: initial_accumulator_value = 0.1
+                st = (torch.full_like(self.E, 0.1), None, torch.full_like(self.Rel, 0.1), None)
+            else:
+                st = (torch.zeros_like(self.E), torch.zeros_like(self.E), torch.zeros_like(self.Rel), torch.zeros_like(self.Rel))
+            self.opt_state = (opt_kind,) + st
+            self.step = 0
+
+    # ---- scoring ------------------------------------------------------------------------------------------------
+    def score(self, idx, out=None):
+        idx = as_idx(idx, self.device)
+        m = idx.shape[0]
+        out = torch.empty(m, dtype=torch.float32, device=self.device) if out is None else out
+        self._check(self.lib.kgeb_score_fwd(self.ctx, _ptr(self.E), _ptr(self.Rel), _ptr(idx), m, _ptr(out), _stream()))
+        return out
+
+    def score_bwd(self, idx, dscore):
+        idx = as_idx(idx, self.device)
+        self._ensure_train_buffers(self.opt_state[0] if self.opt_state else abi.SGD)
+        dscore = dscore.to(device=self.device, dtype=torch.float32).contiguous()
+        self._check(self.lib.kgeb_score_bwd(self.ctx, _ptr(self.E), _ptr(self.Rel), _ptr(idx), idx.shape[0], _ptr(dscore),
+                                            _ptr(self.gE), _ptr(self.gR), _ptr(self.tE), _ptr(self.tR), _stream()))
+
+    def negatives(self, pos, K, seed, offset, corrupt_mode=abi.CORRUPT_BOTH):
+        pos = as_idx(pos, self.device)
+        neg = torch.empty(pos.shape[0] * K, 3, dtype=torch.int32, device=self.device)
+        self._check(self.lib.kgeb_negatives(self.ctx, _ptr(pos), pos.shape[0], K, seed, offset, corrupt_mode, _ptr(neg), _stream()))
+        return neg
+
+    def loss(self, t, f, K, loss_kind, pair_mode, margin, loss_weight=1.0, want_grads=True):
+        t = t.to(device=self.device, dtype=torch.float32).contiguous().view(-1)
+        f = f.to(device=self.device, dtype=torch.float32).contiguous().view(-1)
+        out = torch.empty(1, dtype=torch.float32, device=self.device)
+        dt = torch.empty_like(t) if want_grads else None
+        df = torch.empty_like(f) if want_grads else None
+        self._check(self.lib.kgeb_loss_fwd_bwd(self.ctx, _ptr(t), t.numel(), _ptr(f), f.numel(), K, loss_kind, pair_mode,
+                                               margin, loss_weight, _ptr(out), _ptr(dt), _ptr(df), _stream()))
+        return out, dt, df
+
+    # ---- training -----------------------------------------------------------------------------------------------
+    def forward_backward(self, pos, neg=None, K=1, loss_kind=abi.PAIRWISE_HINGE, pair_mode=abi.PAIRED, margin=1.0,
+                         loss_weight=1.0, corrupt_mode=abi.CORRUPT_BOTH, seed=0, offset=0, want_scores=False,
+                         want_neg=False, force_unfused=False, opt_kind=abi.ADAM_DENSE):
+        """Scores, loss and gradient scatter of one batch (no parameter update).  Returns a dict of device tensors."""
+        pos = as_idx(pos, self.device)
+        B = pos.shape[0]
+        if neg is not None:
+            neg = as_idx(neg, self.device)
+            if pair_mode == abi.PAIRED or loss_kind < abi.PAIRWISE_HINGE:
+                if neg.shape[0] % B != 0 and loss_kind >= abi.PAIRWISE_HINGE:
+                    raise ValueError("PAIRED pairwise loss needs len(neg) to be a multiple of len(pos)")
+                if neg.shape[0] % B == 0:
+                    K = neg.shape[0] // B
+        self._ensure_train_buffers(opt_kind)
+        pairwise = loss_kind >= abi.PAIRWISE_HINGE
+        fused = (not force_unfused and self.kind != abi.HOLE and not (pairwise and pair_mode == abi.ALLPAIRS)
+                 and (neg is None or neg.shape[0] == B * K))
+        res = {}
+        if fused:
+            ps = torch.empty(B, dtype=torch.float32, device=self.device) if want_scores else None
+            ns = torch.empty(B * K, dtype=torch.float32, device=self.device) if want_scores else None
+            no = torch.empty(B * K, 3, dtype=torch.int32, device=self.device) if (want_neg and neg is None) else None
+            self._check(self.lib.kgeb_train_fwd_bwd(
+                self.ctx, _ptr(self.E), _ptr(self.Rel), _ptr(pos), B, _ptr(neg), K, loss_kind, margin, loss_weight,
+                corrupt_mode, seed, offset, _ptr(self._loss), _ptr(ps), _ptr(ns), _ptr(no), _ptr(self.gE), _ptr(self.gR),
+                _ptr(self.tE), _ptr(self.tR), _stream()))
+            res.update(loss=self._loss, pos_scores=ps, neg_scores=ns, neg=neg if neg is not None else no)
+        else:
+            if neg is None:
+                neg = self.negatives(pos, K, seed, offset, corrupt_mode)
+            t, f = self.score(pos), self.score(neg)
+            loss, dt, df = self.loss(t, f, K, loss_kind, pair_mode, margin, loss_weight)
+            self.score_bwd(pos, dt)
+            self.score_bwd(neg, df)
+            res.update(loss=loss, pos_scores=t, neg_scores=f, neg=neg)
+        return res
+
+    def apply_optimizer(self, opt_kind=abi.ADAM_DENSE, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7):
+        self._ensure_train_buffers(opt_kind)
+        self.step += 1
+        _, m_e, v_e, m_r, v_r = self.opt_state
+        self._check(self.lib.kgeb_opt_update(self.ctx, _ptr(self.E), _ptr(self.gE), _ptr(self.tE), self.N, self.we_k, self.we_k,
+                                             _ptr(m_e), _ptr(v_e), opt_kind, lr, beta1, beta2, eps, self.step, _stream()))
+        self._check(self.lib.kgeb_opt_update(self.ctx, _ptr(self.Rel), _ptr(self.gR), _ptr(self.tR), self.R_, self.wr_k, self.wr_k,
+                                             _ptr(m_r), _ptr(v_r), opt_kind, lr, beta1, beta2, eps, self.step, _stream()))
+
+    def train_step(self, pos, neg=None, opt_kind=abi.ADAM_DENSE, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7, **kw):
+        res = self.forward_backward(pos, neg, opt_kind=opt_kind, **kw)
+        self.apply_optimizer(opt_kind, lr, beta1, beta2, eps)
+        return res
+
+    # ---- 1-N filtered ranking -----------------------------------------------------------------------------------
+    def rank_counts(self, triples, side, filt_offsets=None, filt_ids=None, row_range=None, counts=None):
+        """int32 partial counts #{c in rows, c not filtered : score > target score} for every query.
+        row_range=(r0, r1) restricts the candidates to a row shard of the (replicated) table."""
+        tri = as_idx(triples, self.device)
+        Q = tri.shape[0]
+        qw = self.lib.kgeb_query_width(self.ctx, side)
+        qvec = torch.zeros(Q, qw, dtype=torch.float32, device=self.device)
+        tscore = torch.zeros(Q, dtype=torch.float32, device=self.device)
+        counts = torch.zeros(Q, dtype=torch.int32, device=self.device) if counts is None else counts
+        st = _stream()
+        self._check(self.lib.kgeb_query_prep(self.ctx, _ptr(self.E), 0, self.N, _ptr(self.Rel), _ptr(tri), Q, side, _ptr(qvec), st))
+        self._check(self.lib.kgeb_target_scores(self.ctx, _ptr(self.E), 0, self.N, _ptr(qvec), _ptr(tri), Q, side, _ptr(tscore), st))
+        r0, r1 = (0, self.N) if row_range is None else row_range
+        fo = fi = None
+        if filt_offsets is not None:
+            fo = (filt_offsets if isinstance(filt_offsets, torch.Tensor) else torch.as_tensor(np.asarray(filt_offsets, dtype=np.int64))).to(self.device, torch.int64).contiguous()
+            fi = (filt_ids if isinstance(filt_ids, torch.Tensor) else torch.as_tensor(np.asarray(filt_ids, dtype=np.int32))).to(self.device, torch.int32).contiguous()
+            if fi.numel() == 0:
+                fo = fi = None
+        if r1 > r0:
+            e_shard = C.c_void_p(self.E.data_ptr() + r0 * self.we_k * 4)
+            self._check(self.lib.kgeb_rank_1n(self.ctx, e_shard, r0, r1 - r0, _ptr(qvec), _ptr(tscore), _ptr(tri), Q, side,
+                                              _ptr(fo), _ptr(fi), _ptr(counts), st))
+        self._keep = (qvec, tscore, tri, fo, fi)  # keep alive until the stream has consumed them
+        return counts
+
+    # ---- weights ------------------------------------------------------------------------------------------------
+    def get_tables(self):
+        return self.E[:, :self.we].cpu().numpy(), self.Rel[:, :self.wr].cpu().numpy()
+
+    def set_tables(self, E=None, R=None):
+        if E is not None:
+            self.E[:, :self.we] = torch.as_tensor(np.asarray(E, dtype=np.float32)).to(self.device)
+        if R is not None:
+            self.Rel[:, :self.wr] = torch.as_tensor(np.asarray(R, dtype=np.float32)).to(self.device)

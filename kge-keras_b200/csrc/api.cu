@@ -1,0 +1,60 @@
+// api.cu -- context lifecycle of libkgeb200 (see include/kgeb200.h).
+#include "common.cuh"
+#include <new>
+
+char g_kgeb_create_err[512] = "";
+
+extern "C" int kgeb_version(void) { return KGEB_VERSION; }
+
+extern "C" int kgeb_create(kgeb_ctx** out, int device, int64_t num_entities, int64_t num_relations, int we, int wr, int ldE,
+                           int ldR, int score_kind, float gamma) {
+  if (!out) return kgeb_fail(nullptr, KGEB_ERR_INVALID, "%s", "kgeb_create: out is null");
+  *out = nullptr;
+  if (num_entities <= 0 || num_relations <= 0 || we <= 0 || wr <= 0 || ldE < we || ldR < wr)
+    return kgeb_fail(nullptr, KGEB_ERR_INVALID, "%s", "kgeb_create: bad table shape");
+  if (num_entities > 0x7fffffffLL || num_relations > 0x7fffffffLL)
+    return kgeb_fail(nullptr, KGEB_ERR_INVALID, "%s", "kgeb_create: ids are int32");
+  if (score_kind < KGEB_DISTMULT || score_kind > KGEB_HOLE)
+    return kgeb_fail(nullptr, KGEB_ERR_INVALID, "%s", "kgeb_create: unknown score kind");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return kgeb_fail(nullptr, KGEB_ERR_CUDA, "kgeb_create: no CUDA device (%s)", e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return kgeb_fail(nullptr, KGEB_ERR_INVALID, "%s", "kgeb_create: bad device index");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return kgeb_fail(nullptr, KGEB_ERR_CUDA, "kgeb_create: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return kgeb_fail(nullptr, KGEB_ERR_UNSUPPORTED, "%s: built for sm_100a only, device is sm_%lld%lld", "kgeb_create", prop.major, prop.minor);
+  if ((e = cudaSetDevice(device)) != cudaSuccess)
+    return kgeb_fail(nullptr, KGEB_ERR_CUDA, "kgeb_create: %s", cudaGetErrorString(e));
+  kgeb_ctx* c = new (std::nothrow) kgeb_ctx();
+  if (!c) return kgeb_fail(nullptr, KGEB_ERR_INVALID, "%s", "kgeb_create: out of host memory");
+  memset(c, 0, sizeof(*c));
+  c->device = device; c->N = num_entities; c->R = num_relations; c->we = we; c->wr = wr; c->ldE = ldE; c->ldR = ldR;
+  c->kind = score_kind; c->gamma = gamma; c->num_sms = prop.multiProcessorCount;
+  if ((e = cudaMalloc(&c->d_partials, sizeof(double) * 2 * KGEB_MAX_PARTIAL_BLOCKS)) != cudaSuccess ||
+      (e = cudaMalloc(&c->d_ticket, sizeof(unsigned int))) != cudaSuccess ||
+      (e = cudaMemset(c->d_ticket, 0, sizeof(unsigned int))) != cudaSuccess) {
+    kgeb_fail(nullptr, KGEB_ERR_CUDA, "kgeb_create: %s", cudaGetErrorString(e));
+    if (c->d_partials) cudaFree(c->d_partials);
+    if (c->d_ticket) cudaFree(c->d_ticket);
+    delete c;
+    return KGEB_ERR_CUDA;
+  }
+  *out = c;
+  return KGEB_OK;
+}
+
+extern "C" int kgeb_destroy(kgeb_ctx* ctx) {
+  if (!ctx) return KGEB_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (ctx->d_partials) cudaFree(ctx->d_partials);
+  if (ctx->d_ticket) cudaFree(ctx->d_ticket);
+  delete ctx;
+  return KGEB_OK;
+}
+
+extern "C" const char* kgeb_last_error(const kgeb_ctx* ctx) { return ctx ? ctx->err : g_kgeb_create_err; }
+extern "C" int64_t kgeb_launch_count(const kgeb_ctx* ctx) { return ctx ? ctx->launches : -1; }
+extern "C" int kgeb_num_sms(const kgeb_ctx* ctx) { return ctx ? ctx->num_sms : KGEB_ERR_INVALID; }

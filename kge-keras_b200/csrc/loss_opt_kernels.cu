@@ -1,0 +1,243 @@
+// loss_opt_kernels.cu -- losses on score vectors (utils.py:288-319) with their derivatives, and the touched-row
+// optimizer (K2 second half; Keras Adam/Adagrad/SGD semantics).
+#include "common.cuh"
+#include <math.h>
+
+namespace {
+
+// -------- pointwise: L = mean_i g(t_i) + mean_j h(f_j) ---------------------------------------------------
+__global__ void __launch_bounds__(KGEB_THREADS) k_loss_pointwise(const float* __restrict__ t, int64_t B,
+                                                                 const float* __restrict__ f, int64_t Bf, int kind,
+                                                                 float margin, float w, float* loss, float* dt, float* df,
+                                                                 double* partials, unsigned int* ticket) {
+  double lp = 0.0, ln = 0.0;
+  const float sP = (float)((double)w / (double)B), sN = (float)((double)w / (double)Bf);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B + Bf; i += stride) {
+    float val, der;
+    if (i < B) {
+      pointwise_terms(kind, margin, __ldg(t + i), true, val, der);
+      lp += (double)val;
+      if (dt) dt[i] = der * sP;
+    } else {
+      pointwise_terms(kind, margin, __ldg(f + (i - B)), false, val, der);
+      ln += (double)val;
+      if (df) df[i - B] = der * sN;
+    }
+  }
+  block_finalize_loss(lp, ln, partials, ticket, (double)w / (double)B, (double)w / (double)Bf, loss);
+}
+
+// -------- pairwise PAIRED: X_ij = f_{iK+j} - t_i -----------------------------------------------------------
+__global__ void __launch_bounds__(KGEB_THREADS) k_loss_paired(const float* __restrict__ t, int64_t B,
+                                                              const float* __restrict__ f, int K, int kind, float margin,
+                                                              float w, float* loss, float* dt, float* df, double* partials,
+                                                              unsigned int* ticket) {
+  double ln = 0.0;
+  const float sN = (float)((double)w / ((double)B * (double)K));
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += stride) {
+    const float ti = __ldg(t + i);
+    float cpos = 0.f;
+    for (int j = 0; j < K; ++j) {
+      float val, A;
+      pairwise_terms(kind, margin, __ldg(f + i * K + j) - ti, val, A);
+      ln += (double)val;
+      const float c = A * sN;
+      if (df) df[i * K + j] = c;
+      cpos -= c;
+    }
+    if (dt) dt[i] = cpos;
+  }
+  block_finalize_loss(0.0, ln, partials, ticket, 0.0, (double)w / ((double)B * (double)K), loss);
+}
+
+// -------- pairwise ALLPAIRS: X_ji = f_j - t_i over the full (Bf x B) grid (tests.py:81 broadcast) --------------
+// blockIdx.z == 0: a thread owns one t_i and walks a slice of f (accumulates loss and dt_i);
+// blockIdx.z == 1: a thread owns one f_j and walks a slice of t (accumulates df_j).  Partial sums meet in
+// float atomics on dt/df (zeroed by the host wrapper first).
+#define AP_TILE 256
+__global__ void __launch_bounds__(AP_TILE) k_loss_allpairs(const float* __restrict__ t, int64_t B, const float* __restrict__ f,
+                                                           int64_t Bf, int kind, float margin, float w, float* dt, float* df,
+                                                           double* loss_acc) {
+  __shared__ float tile[AP_TILE];
+  const bool own_t = blockIdx.z == 0;
+  const float* own = own_t ? t : f;
+  const float* oth = own_t ? f : t;
+  const int64_t n_own = own_t ? B : Bf, n_oth = own_t ? Bf : B;
+  const int64_t nblk_own = (n_own + AP_TILE - 1) / AP_TILE;
+  if ((int64_t)blockIdx.x >= nblk_own) return;
+  const int64_t i = (int64_t)blockIdx.x * AP_TILE + threadIdx.x;
+  const float mine = i < n_own ? __ldg(own + i) : 0.f;
+  // slice of the other vector handled by this blockIdx.y
+  const int64_t per = ((n_oth + gridDim.y - 1) / gridDim.y + AP_TILE - 1) / AP_TILE * AP_TILE;
+  const int64_t j0 = (int64_t)blockIdx.y * per;
+  const int64_t j1 = j0 + per < n_oth ? j0 + per : n_oth;
+  float accA = 0.f;
+  double accL = 0.0;
+  for (int64_t base = j0; base < j1; base += AP_TILE) {
+    __syncthreads();
+    const int64_t jj = base + threadIdx.x;
+    tile[threadIdx.x] = jj < j1 ? __ldg(oth + jj) : 0.f;
+    __syncthreads();
+    const int lim = (int)((j1 - base) < AP_TILE ? (j1 - base) : AP_TILE);
+    float l32 = 0.f;
+    for (int k = 0; k < lim; ++k) {
+      float val, A;
+      const float x = own_t ? tile[k] - mine : mine - tile[k];
+      pairwise_terms(kind, margin, x, val, A);
+      accA += A;
+      l32 += val;
+    }
+    accL += (double)l32;
+  }
+  const double cnt = (double)B * (double)Bf;
+  const float sc = (float)((double)w / cnt);
+  if (i < n_own) {
+    if (own_t) { if (dt) atomicAdd(dt + i, -accA * sc); }
+    else       { if (df) atomicAdd(df + i, accA * sc); }
+  }
+  if (own_t) {
+    if (i >= n_own) accL = 0.0;
+    accL = warp_sum_d(accL);
+    if ((threadIdx.x & 31) == 0) atomicAdd(loss_acc, accL);
+  }
+}
+__global__ void k_loss_allpairs_finish(const double* loss_acc, double scale, float* loss) { loss[0] = (float)(loss_acc[0] * scale); }
+
+// -------- optimizer: a warp scans 32 row flags at a time, then updates the touched rows cooperatively -----------
+struct OptArgs {
+  float* P; float* G; uint8_t* touched; int64_t rows; int w4; int ld4; float* s0; float* s1;
+  int kind; float lr, b1, b2, eps, lr_t;
+  int win;  // rows scanned per warp trip (1..32): small when most rows are touched so the work spreads over all SMs
+};
+
+__device__ __forceinline__ void opt_elem(int kind, float g, float& p, float& m, float& v, const OptArgs& a) {
+  if (kind == KGEB_SGD) {
+    p -= a.lr * g;
+  } else if (kind == KGEB_ADAGRAD) {
+    m += g * g;
+    p -= a.lr * g / (sqrtf(m) + a.eps);
+  } else {
+    m = a.b1 * m + (1.f - a.b1) * g;
+    v = a.b2 * v + (1.f - a.b2) * g * g;
+    p -= a.lr_t * m / (sqrtf(v) + a.eps);
+  }
+}
+
+__global__ void __launch_bounds__(KGEB_THREADS) k_opt_update(OptArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * KGEB_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int64_t nw = (int64_t)gridDim.x * KGEB_WARPS_PER_BLOCK;
+  const bool dense = a.kind == KGEB_ADAM_DENSE;
+  float4* P4 = reinterpret_cast<float4*>(a.P);
+  float4* G4 = reinterpret_cast<float4*>(a.G);
+  float4* M4 = reinterpret_cast<float4*>(a.s0);
+  float4* V4 = reinterpret_cast<float4*>(a.s1);
+  for (int64_t base = warp * a.win; base < a.rows; base += nw * a.win) {
+    const int64_t r = base + lane;
+    const bool inwin = lane < a.win && r < a.rows;
+    const bool flag = inwin && (a.touched[r] != 0);
+    const bool work = inwin && (dense || flag);
+    unsigned mask = __ballot_sync(0xffffffffu, work);
+    const unsigned tmask = __ballot_sync(0xffffffffu, flag);
+    while (mask) {
+      const int b = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int64_t row = base + b;
+      const bool was_touched = (tmask >> b) & 1u;
+      for (int c = lane; c < a.w4; c += 32) {
+        const int64_t off = row * a.ld4 + c;
+        float4 g = was_touched ? G4[off] : f4zero();
+        float4 p = P4[off];
+        float4 m = f4zero(), v = f4zero();
+        if (a.kind != KGEB_SGD) m = M4[off];
+        if (a.kind >= KGEB_LAZY_ADAM) v = V4[off];
+        opt_elem(a.kind, g.x, p.x, m.x, v.x, a);
+        opt_elem(a.kind, g.y, p.y, m.y, v.y, a);
+        opt_elem(a.kind, g.z, p.z, m.z, v.z, a);
+        opt_elem(a.kind, g.w, p.w, m.w, v.w, a);
+        P4[off] = p;
+        if (a.kind != KGEB_SGD) M4[off] = m;
+        if (a.kind >= KGEB_LAZY_ADAM) V4[off] = v;
+        if (was_touched) G4[off] = f4zero();
+      }
+      if (was_touched && lane == 0) a.touched[row] = 0;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int kgeb_loss_fwd_bwd(kgeb_ctx* ctx, const float* t, int64_t B, const float* f, int64_t Bf, int K, int loss_kind,
+                                 int pair_mode, float margin, float loss_weight, float* loss, float* dt, float* df,
+                                 kgeb_stream stream) {
+  if (!ctx) return KGEB_ERR_INVALID;
+  KGEB_REQUIRE(ctx, t && f && loss && B > 0 && Bf > 0, KGEB_ERR_INVALID, "loss_fwd_bwd: bad arguments");
+  KGEB_REQUIRE(ctx, loss_kind >= 0 && loss_kind <= KGEB_PAIRWISE_SQUARE, KGEB_ERR_INVALID, "unknown loss kind");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cap = ctx->num_sms * 4 < KGEB_MAX_PARTIAL_BLOCKS ? ctx->num_sms * 4 : KGEB_MAX_PARTIAL_BLOCKS;
+  if (loss_kind < KGEB_PAIRWISE_HINGE) {
+    int64_t blocks = (B + Bf + KGEB_THREADS - 1) / KGEB_THREADS;
+    if (blocks > cap) blocks = cap;
+    k_loss_pointwise<<<(int)blocks, KGEB_THREADS, 0, st>>>(t, B, f, Bf, loss_kind, margin, loss_weight, loss, dt, df,
+                                                           ctx->d_partials, ctx->d_ticket);
+    KGEB_LAUNCH_OK(ctx);
+    return KGEB_OK;
+  }
+  if (pair_mode == KGEB_PAIRED) {
+    KGEB_REQUIRE(ctx, K > 0 && Bf == B * (int64_t)K, KGEB_ERR_INVALID, "PAIRED needs len(false) == len(true) * K");
+    int64_t blocks = (B + KGEB_THREADS - 1) / KGEB_THREADS;
+    if (blocks > cap) blocks = cap;
+    k_loss_paired<<<(int)blocks, KGEB_THREADS, 0, st>>>(t, B, f, K, loss_kind, margin, loss_weight, loss, dt, df,
+                                                        ctx->d_partials, ctx->d_ticket);
+    KGEB_LAUNCH_OK(ctx);
+    return KGEB_OK;
+  }
+  KGEB_REQUIRE(ctx, pair_mode == KGEB_ALLPAIRS, KGEB_ERR_INVALID, "unknown pair mode");
+  if (dt) KGEB_CUDA_OK(ctx, cudaMemsetAsync(dt, 0, (size_t)B * sizeof(float), st));
+  if (df) KGEB_CUDA_OK(ctx, cudaMemsetAsync(df, 0, (size_t)Bf * sizeof(float), st));
+  double* loss_acc = ctx->d_partials;  // slot 0 doubles as the ALLPAIRS accumulator
+  KGEB_CUDA_OK(ctx, cudaMemsetAsync(loss_acc, 0, sizeof(double), st));
+  const int64_t nb = ((B > Bf ? B : Bf) + AP_TILE - 1) / AP_TILE;
+  int slices = (int)((int64_t)ctx->num_sms * 8 / (2 * nb));
+  if (slices < 1) slices = 1;
+  if (slices > 256) slices = 256;
+  dim3 grid((unsigned)nb, (unsigned)slices, 2);
+  k_loss_allpairs<<<grid, AP_TILE, 0, st>>>(t, B, f, Bf, loss_kind, margin, loss_weight, dt, df, loss_acc);
+  KGEB_LAUNCH_OK(ctx);
+  k_loss_allpairs_finish<<<1, 1, 0, st>>>(loss_acc, (double)loss_weight / ((double)B * (double)Bf), loss);
+  KGEB_LAUNCH_OK(ctx);
+  return KGEB_OK;
+}
+
+extern "C" int kgeb_opt_update(kgeb_ctx* ctx, float* P, float* G, uint8_t* touched, int64_t rows, int width, int ld,
+                               float* state0, float* state1, int opt_kind, float lr, float beta1, float beta2, float eps,
+                               int64_t step, kgeb_stream stream) {
+  if (!ctx) return KGEB_ERR_INVALID;
+  KGEB_REQUIRE(ctx, P && G && touched && rows >= 0 && width > 0 && ld >= width, KGEB_ERR_INVALID, "opt_update: bad arguments");
+  KGEB_REQUIRE(ctx, opt_kind >= KGEB_SGD && opt_kind <= KGEB_ADAM_DENSE, KGEB_ERR_INVALID, "unknown optimizer");
+  KGEB_REQUIRE(ctx, opt_kind == KGEB_SGD || state0, KGEB_ERR_INVALID, "optimizer state0 missing");
+  KGEB_REQUIRE(ctx, opt_kind < KGEB_LAZY_ADAM || (state1 && step >= 1), KGEB_ERR_INVALID, "Adam needs state1 and step >= 1");
+  KGEB_REQUIRE(ctx, width % 4 == 0 && ld % 4 == 0 && kgeb_aligned16(P) && kgeb_aligned16(G) &&
+                        (!state0 || kgeb_aligned16(state0)) && (!state1 || kgeb_aligned16(state1)),
+               KGEB_ERR_ALIGNMENT, "opt_update needs width, ld multiples of 4 floats and 16-byte aligned buffers");
+  if (rows == 0) return KGEB_OK;
+  OptArgs a;
+  a.P = P; a.G = G; a.touched = touched; a.rows = rows; a.w4 = width / 4; a.ld4 = ld / 4; a.s0 = state0; a.s1 = state1;
+  a.kind = opt_kind; a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps;
+  a.lr_t = lr;
+  if (opt_kind >= KGEB_LAZY_ADAM) {
+    const double t = (double)step;
+    a.lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, t)) / (1.0 - pow((double)beta1, t)));
+  }
+  // window: ~32 warps per SM worth of windows when the table is small, 32 rows per trip when it is huge
+  int64_t win = rows / ((int64_t)ctx->num_sms * 32);
+  a.win = win >= 32 ? 32 : (win >= 16 ? 16 : (win >= 8 ? 8 : (win >= 4 ? 4 : (win >= 2 ? 2 : 1))));
+  int64_t blocks = (rows + (int64_t)a.win * KGEB_WARPS_PER_BLOCK - 1) / ((int64_t)a.win * KGEB_WARPS_PER_BLOCK);
+  const int64_t cap = (int64_t)ctx->num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  k_opt_update<<<(int)blocks, KGEB_THREADS, 0, (cudaStream_t)stream>>>(a);
+  KGEB_LAUNCH_OK(ctx);
+  return KGEB_OK;
+}

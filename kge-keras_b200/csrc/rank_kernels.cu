@@ -1,0 +1,318 @@
+// rank_kernels.cu -- 1-N filtered ranking (validate / gen_tail_data / gen_head_data, utils.py:165-264) without ever
+// materialising the Q x N score matrix: a register-tiled CUDA-core kernel scores a 64-query x 64-entity tile, compares
+// against the query's target score in registers and keeps only integer counts.
+//
+//   rank(q) = 1 + #{c not in filter(q) u {target(q)} : score(q,c) > score(q,target)}          
+//
+// Arithmetic contract (what makes the integer counts reproducible and tie-consistent): every score -- candidate,
+// target, filtered candidate -- is accumulated SEQUENTIALLY over k = 0..W-1 in fp32 with separately rounded multiply
+// and add (__fmul_rn/__fadd_rn, no FMA), so the three code paths below give bit-identical scores for the same (q,c)
+// and oracle.kge_oracle.seqk_scores reproduces them on the CPU.  The filter is applied as a correction pass:
+// counts -= #{c in filter(q) : score(q,c) > target}.
+#include "common.cuh"
+
+namespace {
+
+enum { OP_DOT = 0, OP_L1_TAIL = 1, OP_L1_HEAD = 2, OP_L2_TAIL = 3, OP_L2_HEAD = 4 };
+
+// one term of the sequential accumulation; a = qvec[k] (a2 = qvec[W+k] for head TransE), e = E[c][k]
+template <int OP>
+__device__ __forceinline__ float seq_term(float acc, float a, float a2, float e) {
+  if (OP == OP_DOT) return __fadd_rn(acc, __fmul_rn(a, e));
+  float r;
+  if (OP == OP_L1_TAIL || OP == OP_L2_TAIL) r = __fsub_rn(a, e);
+  else r = __fsub_rn(__fadd_rn(e, a), a2);
+  if (OP == OP_L1_TAIL || OP == OP_L1_HEAD) return __fadd_rn(acc, fabsf(r));
+  return __fadd_rn(acc, __fmul_rn(r, r));
+}
+template <int OP>
+__device__ __forceinline__ float seq_finish(float acc, float gamma) {
+  if (OP == OP_DOT) return acc;
+  if (OP == OP_L2_TAIL || OP == OP_L2_HEAD) acc = __fsqrt_rn(acc);
+  return gamma > 0.f ? __fsub_rn(gamma, acc) : acc;
+}
+template <int OP>
+__device__ __forceinline__ float seq_score(const float* __restrict__ q, const float* __restrict__ e, int W, float gamma) {
+  float acc = 0.f;
+  for (int k = 0; k < W; ++k) acc = seq_term<OP>(acc, q[k], (OP == OP_L1_HEAD || OP == OP_L2_HEAD) ? q[W + k] : 0.f, e[k]);
+  return seq_finish<OP>(acc, gamma);
+}
+__device__ __forceinline__ float seq_score_dyn(int op, const float* q, const float* e, int W, float gamma) {
+  switch (op) {
+    case OP_DOT: return seq_score<OP_DOT>(q, e, W, gamma);
+    case OP_L1_TAIL: return seq_score<OP_L1_TAIL>(q, e, W, gamma);
+    case OP_L1_HEAD: return seq_score<OP_L1_HEAD>(q, e, W, gamma);
+    case OP_L2_TAIL: return seq_score<OP_L2_TAIL>(q, e, W, gamma);
+    default: return seq_score<OP_L2_HEAD>(q, e, W, gamma);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// query vectors; one thread per output element
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_query_prep(int kind, int side, const float* __restrict__ Es, int64_t row_offset, int64_t n_rows, int ldE,
+                             const float* __restrict__ R, int ldR, int W, const int32_t* __restrict__ triples, int64_t Q,
+                             int qw, float* __restrict__ qvec) {
+  const int64_t total = Q * (int64_t)qw;
+  for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = x / qw;
+    const int k = (int)(x - q * qw);
+    const int64_t src = side == KGEB_SIDE_TAIL ? triples[3 * q] : triples[3 * q + 2];
+    if (src < row_offset || src >= row_offset + n_rows) continue;  // another shard owns this query's source row
+    const float* e = Es + (src - row_offset) * (int64_t)ldE;   // s (tail queries) or o (head queries)
+    const float* p = R + (int64_t)triples[3 * q + 1] * ldR;
+    float out;
+    if (kind == KGEB_DISTMULT) {
+      out = side == KGEB_SIDE_TAIL ? __fmul_rn(e[k], p[k]) : __fmul_rn(p[k], e[k]);
+    } else if (kind == KGEB_COMPLEX) {
+      const int d = W / 2;
+      const int j = k < d ? k : k - d;
+      const float er = e[j], ei = e[d + j], pr = p[j], pi = p[d + j];
+      if (side == KGEB_SIDE_TAIL)  // e = s:  [sr pr - si pi | si pr + sr pi]
+        out = k < d ? __fsub_rn(__fmul_rn(er, pr), __fmul_rn(ei, pi)) : __fadd_rn(__fmul_rn(ei, pr), __fmul_rn(er, pi));
+      else                         // e = o:  [pr or + pi oi | pr oi - pi or]
+        out = k < d ? __fadd_rn(__fmul_rn(pr, er), __fmul_rn(pi, ei)) : __fsub_rn(__fmul_rn(pr, ei), __fmul_rn(pi, er));
+    } else if (kind == KGEB_HOLE) {
+      float acc = 0.f;
+      if (side == KGEB_SIDE_TAIL) {  // q_j = sum_i s_i p_{(j-i) mod d}
+        int jj = k;
+        for (int i = 0; i < W; ++i) {
+          acc = __fadd_rn(acc, __fmul_rn(e[i], p[jj]));
+          if (--jj < 0) jj = W - 1;
+        }
+      } else {                        // q_i = sum_k p_k o_{(i+k) mod d}
+        int jj = k;
+        for (int i = 0; i < W; ++i) {
+          acc = __fadd_rn(acc, __fmul_rn(p[i], e[jj]));
+          if (++jj == W) jj = 0;
+        }
+      }
+      out = acc;
+    } else {  // TransE: tail a = s + p; head keeps [p | o] so (e + p) - o follows the reference's order
+      if (side == KGEB_SIDE_TAIL) out = __fadd_rn(e[k], p[k]);
+      else out = k < W ? p[k] : e[k - W];
+    }
+    qvec[x] = out;
+  }
+}
+
+__global__ void k_target_scores(int op, const float* __restrict__ Es, int64_t row_offset, int64_t n_rows, int ldE, int W,
+                                const float* __restrict__ qvec, int qw, const int32_t* __restrict__ triples, int64_t Q,
+                                int side, float gamma, float* __restrict__ tscore) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t tgt = side == KGEB_SIDE_TAIL ? triples[3 * q + 2] : triples[3 * q];
+    if (tgt < row_offset || tgt >= row_offset + n_rows) continue;
+    tscore[q] = seq_score_dyn(op, qvec + q * (int64_t)qw, Es + (tgt - row_offset) * (int64_t)ldE, W, gamma);
+  }
+}
+
+// filter correction: one thread per CSR entry
+__global__ void k_filter_correct(int op, const float* __restrict__ Es, int64_t row_offset, int64_t n_rows, int ldE, int W,
+                                 const float* __restrict__ qvec, int qw, const float* __restrict__ tscore,
+                                 const int32_t* __restrict__ triples, int64_t Q, int side, float gamma,
+                                 const int64_t* __restrict__ offs, const int32_t* __restrict__ ids, int32_t* counts) {
+  const int64_t nnz = offs[Q];
+  for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < nnz; x += (int64_t)gridDim.x * blockDim.x) {
+    int64_t lo = 0, hi = Q;  // largest q with offs[q] <= x
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (offs[mid] <= x) lo = mid; else hi = mid;
+    }
+    const int64_t q = lo;
+    const int64_t c = ids[x];
+    const int64_t tgt = side == KGEB_SIDE_TAIL ? triples[3 * q + 2] : triples[3 * q];
+    if (c == tgt || c < row_offset || c >= row_offset + n_rows) continue;
+    const float sc = seq_score_dyn(op, qvec + q * (int64_t)qw, Es + (c - row_offset) * (int64_t)ldE, W, gamma);
+    if (sc > tscore[q]) atomicSub(counts + q, 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the tile kernel: CTA = 64 queries x (a strided set of 64-entity tiles); thread = 4 x 4 micro-tile
+// ---------------------------------------------------------------------------------------------------
+constexpr int BQ = 64, BN = 64, BK = 32, LDS_STRIDE = 68;
+
+template <int OP>
+__global__ void __launch_bounds__(256) k_rank_tile(const float* __restrict__ Es, int64_t n_rows, int ldE, int W,
+                                                   const float* __restrict__ qvec, int qw, const float* __restrict__ tscore,
+                                                   int64_t Q, float gamma, int32_t* counts) {
+  constexpr bool HEAD = (OP == OP_L1_HEAD || OP == OP_L2_HEAD);
+  __shared__ __align__(16) float As[BK][LDS_STRIDE];
+  __shared__ __align__(16) float As2[HEAD ? BK : 1][LDS_STRIDE];
+  __shared__ __align__(16) float Bs[BK][LDS_STRIDE];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t q0 = (int64_t)blockIdx.x * BQ;
+  const int64_t ntiles = (n_rows + BN - 1) / BN;
+  // loader mapping: 8 float4 per 32-float k-chunk row, 32 rows per pass, 2 passes
+  const int lr = tid >> 3, lk4 = tid & 7;
+  const int nkc = (W + BK - 1) / BK;
+
+  float tq[4];
+  int cnt[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t q = q0 + ty * 4 + i;
+    tq[i] = q < Q ? __ldg(tscore + q) : 0.f;
+  }
+
+  for (int64_t tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
+    const int64_t n0 = tile * BN;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    float4 ra[2], ra2[2], rb[2];
+    auto gload = [&](int kc) {
+      const int k = kc * BK + lk4 * 4;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int64_t q = q0 + lr + 32 * h;
+        const int64_t n = n0 + lr + 32 * h;
+        const bool kin = k < W;
+        ra[h] = (kin && q < Q) ? ldg4(reinterpret_cast<const float4*>(qvec + q * (int64_t)qw + k)) : f4zero();
+        if (HEAD) ra2[h] = (kin && q < Q) ? ldg4(reinterpret_cast<const float4*>(qvec + q * (int64_t)qw + W + k)) : f4zero();
+        rb[h] = (kin && n < n_rows) ? ldg4(reinterpret_cast<const float4*>(Es + n * (int64_t)ldE + k)) : f4zero();
+      }
+    };
+    auto sstore = [&]() {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = lr + 32 * h, kk = lk4 * 4;
+        As[kk + 0][r] = ra[h].x; As[kk + 1][r] = ra[h].y; As[kk + 2][r] = ra[h].z; As[kk + 3][r] = ra[h].w;
+        if (HEAD) { As2[kk + 0][r] = ra2[h].x; As2[kk + 1][r] = ra2[h].y; As2[kk + 2][r] = ra2[h].z; As2[kk + 3][r] = ra2[h].w; }
+        Bs[kk + 0][r] = rb[h].x; Bs[kk + 1][r] = rb[h].y; Bs[kk + 2][r] = rb[h].z; Bs[kk + 3][r] = rb[h].w;
+      }
+    };
+
+    gload(0);
+    for (int kc = 0; kc < nkc; ++kc) {
+      __syncthreads();  // previous chunk fully consumed
+      sstore();
+      __syncthreads();
+      if (kc + 1 < nkc) gload(kc + 1);  // in flight while this chunk is computed
+      const int klim = (W - kc * BK) < BK ? (W - kc * BK) : BK;
+#pragma unroll 4
+      for (int k = 0; k < klim; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        float4 a2 = f4zero();
+        if (HEAD) a2 = *reinterpret_cast<const float4*>(&As2[k][ty * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w}, a2v[4] = {a2.x, a2.y, a2.z, a2.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = seq_term<OP>(acc[i][j], av[i], a2v[i], bv[j]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t n = n0 + tx * 4 + j;
+        const float sc = seq_finish<OP>(acc[i][j], gamma);
+        cnt[i] += (n < n_rows && sc > tq[i]) ? 1 : 0;
+      }
+  }
+  // the 16 tx lanes of one ty live in one half-warp: butterfly inside 16 lanes, then one integer atomic per query
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int c = cnt[i];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    const int64_t q = q0 + ty * 4 + i;
+    if (tx == 0 && q < Q && c != 0) atomicAdd(counts + q, c);
+  }
+}
+
+int grid1d(const kgeb_ctx* ctx, int64_t n, int threads) {
+  int64_t b = (n + threads - 1) / threads;
+  const int64_t cap = (int64_t)ctx->num_sms * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+int host_op_for(int kind, int side) {
+  if (kind == KGEB_TRANSE_L1) return side == KGEB_SIDE_TAIL ? OP_L1_TAIL : OP_L1_HEAD;
+  if (kind == KGEB_TRANSE_L2) return side == KGEB_SIDE_TAIL ? OP_L2_TAIL : OP_L2_HEAD;
+  return OP_DOT;
+}
+
+}  // namespace
+
+extern "C" int kgeb_query_width(const kgeb_ctx* ctx, int side) {
+  if (!ctx) return KGEB_ERR_INVALID;
+  const bool transe = ctx->kind == KGEB_TRANSE_L1 || ctx->kind == KGEB_TRANSE_L2;
+  return (transe && side == KGEB_SIDE_HEAD) ? 2 * ctx->we : ctx->we;
+}
+
+extern "C" int kgeb_query_prep(kgeb_ctx* ctx, const float* E_shard, int64_t row_offset, int64_t n_rows, const float* R,
+                               const int32_t* triples, int64_t Q, int side, float* qvec, kgeb_stream stream) {
+  if (!ctx) return KGEB_ERR_INVALID;
+  KGEB_REQUIRE(ctx, E_shard && R && triples && qvec && Q >= 0 && n_rows >= 0 && row_offset >= 0, KGEB_ERR_INVALID,
+               "query_prep: bad arguments");
+  KGEB_REQUIRE(ctx, side == KGEB_SIDE_TAIL || side == KGEB_SIDE_HEAD, KGEB_ERR_INVALID, "unknown side");
+  KGEB_REQUIRE(ctx, ctx->we == ctx->wr, KGEB_ERR_UNSUPPORTED, "1-N ranking needs e_dim == r_dim");
+  if (Q == 0) return KGEB_OK;
+  const int qw = kgeb_query_width(ctx, side);
+  k_query_prep<<<grid1d(ctx, Q * (int64_t)qw, 256), 256, 0, (cudaStream_t)stream>>>(
+      ctx->kind, side, E_shard, row_offset, n_rows, ctx->ldE, R, ctx->ldR, ctx->we, triples, Q, qw, qvec);
+  KGEB_LAUNCH_OK(ctx);
+  return KGEB_OK;
+}
+
+extern "C" int kgeb_target_scores(kgeb_ctx* ctx, const float* E_shard, int64_t row_offset, int64_t n_rows, const float* qvec,
+                                  const int32_t* triples, int64_t Q, int side, float* tscore, kgeb_stream stream) {
+  if (!ctx) return KGEB_ERR_INVALID;
+  KGEB_REQUIRE(ctx, E_shard && qvec && triples && tscore && Q >= 0, KGEB_ERR_INVALID, "target_scores: bad arguments");
+  if (Q == 0) return KGEB_OK;
+  const int qw = kgeb_query_width(ctx, side);
+  k_target_scores<<<grid1d(ctx, Q, 128), 128, 0, (cudaStream_t)stream>>>(host_op_for(ctx->kind, side), E_shard, row_offset,
+                                                                         n_rows, ctx->ldE, ctx->we, qvec, qw, triples, Q,
+                                                                         side, ctx->gamma, tscore);
+  KGEB_LAUNCH_OK(ctx);
+  return KGEB_OK;
+}
+
+extern "C" int kgeb_rank_1n(kgeb_ctx* ctx, const float* E_shard, int64_t row_offset, int64_t n_rows, const float* qvec,
+                            const float* tscore, const int32_t* triples, int64_t Q, int side, const int64_t* filt_offsets,
+                            const int32_t* filt_ids, int32_t* counts, kgeb_stream stream) {
+  if (!ctx) return KGEB_ERR_INVALID;
+  KGEB_REQUIRE(ctx, E_shard && qvec && tscore && triples && counts && Q >= 0 && n_rows >= 0, KGEB_ERR_INVALID,
+               "rank_1n: bad arguments");
+  KGEB_REQUIRE(ctx, (filt_offsets == nullptr) == (filt_ids == nullptr), KGEB_ERR_INVALID, "filter CSR: give both arrays or neither");
+  KGEB_REQUIRE(ctx, ctx->we % 4 == 0 && ctx->ldE % 4 == 0 && kgeb_aligned16(E_shard) && kgeb_aligned16(qvec),
+               KGEB_ERR_ALIGNMENT, "rank_1n needs width, stride multiples of 4 floats and 16-byte aligned pointers");
+  if (Q == 0 || n_rows == 0) return KGEB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int qw = kgeb_query_width(ctx, side);
+  const int op = host_op_for(ctx->kind, side);
+  const int64_t qtiles = (Q + BQ - 1) / BQ;
+  const int64_t ntiles = (n_rows + BN - 1) / BN;
+  // split the entity range so the grid covers ~4 CTAs per SM; each CTA keeps its counts in registers across its tiles
+  int64_t split = ((int64_t)ctx->num_sms * 4 + qtiles - 1) / qtiles;
+  if (split > ntiles) split = ntiles;
+  if (split < 1) split = 1;
+  if (split > 65535) split = 65535;
+  dim3 grid((unsigned)qtiles, (unsigned)split);
+#define KGEB_RANK_LAUNCH(OPV) \
+  k_rank_tile<OPV><<<grid, 256, 0, st>>>(E_shard, n_rows, ctx->ldE, ctx->we, qvec, qw, tscore, Q, ctx->gamma, counts)
+  switch (op) {
+    case OP_DOT: KGEB_RANK_LAUNCH(OP_DOT); break;
+    case OP_L1_TAIL: KGEB_RANK_LAUNCH(OP_L1_TAIL); break;
+    case OP_L1_HEAD: KGEB_RANK_LAUNCH(OP_L1_HEAD); break;
+    case OP_L2_TAIL: KGEB_RANK_LAUNCH(OP_L2_TAIL); break;
+    default: KGEB_RANK_LAUNCH(OP_L2_HEAD); break;
+  }
+  KGEB_LAUNCH_OK(ctx);
+  if (filt_offsets) {
+    // nnz is on the device; size the grid from Q (lists are short) -- the kernel grid-strides over nnz
+    k_filter_correct<<<grid1d(ctx, Q * 8, 128), 128, 0, st>>>(op, E_shard, row_offset, n_rows, ctx->ldE, ctx->we, qvec, qw,
+                                                              tscore, triples, Q, side, ctx->gamma, filt_offsets, filt_ids,
+                                                              counts);
+    KGEB_LAUNCH_OK(ctx);
+  }
+  return KGEB_OK;
+}

@@ -125,8 +125,7 @@ def score_abs_terms(kind, E, R, idx, gamma=12.0):
         c = np.abs(o[..., :d]) + np.abs(o[..., d:])
         return np.sum(a * b * c, axis=-1)
     if kind == HOLE:
-        return np.sum(np.abs(p), axis=-1) * np.sqrt(np.sum(s * s, -1) * np.sum(o * o, -1)) + \
-            np.sum(np.abs(p) * circular_correlation_direct(np.abs(s), np.abs(o)), axis=-1)
+        return np.sum(np.abs(p) * circular_correlation_direct(np.abs(s), np.abs(o)), axis=-1)
     raise KeyError(kind)
 
 
@@ -334,7 +333,7 @@ def opt_update(opt_kind, P, G, touched, state, lr, step, b1=0.9, b2=0.999, eps=1
 
 
 def train_step(kind, loss_kind, pair_mode, E, R, pos, neg, K, margin, gamma, opt_kind, state_E, state_R,
-               lr, step, dtype=np.float64):
+               lr, step, dtype=np.float64, b1=0.9, b2=0.999, eps=1e-7):
     """One full step of the harness' loop (tests.py:72-87,130-134) with dp=0, regularization=0:
     scores -> loss -> gradients (dedup by id) -> optimizer.  Returns dict."""
     E = E.astype(dtype)
@@ -344,8 +343,8 @@ def train_step(kind, loss_kind, pair_mode, E, R, pos, neg, K, margin, gamma, opt
     L, dt_, df_ = loss_and_coefs(loss_kind, pair_mode, t, f, K, margin)
     idx = np.concatenate([np.asarray(pos), np.asarray(neg)], axis=0)
     gE, gR, tE, tR = dense_grads(kind, E, R, idx, np.concatenate([dt_, df_]), gamma, dtype)
-    E2, sE = opt_update(opt_kind, E, gE, tE, [x.astype(dtype) for x in state_E], lr, step)
-    R2, sR = opt_update(opt_kind, R, gR, tR, [x.astype(dtype) for x in state_R], lr, step)
+    E2, sE = opt_update(opt_kind, E, gE, tE, [x.astype(dtype) for x in state_E], lr, step, b1, b2, eps)
+    R2, sR = opt_update(opt_kind, R, gR, tR, [x.astype(dtype) for x in state_R], lr, step, b1, b2, eps)
     return dict(loss=L, pos_scores=t, neg_scores=f, dpos=dt_, dneg=df_, gE=gE, gR=gR, touched_E=tE,
                 touched_R=tR, E=E2, R=R2, state_E=sE, state_R=sR)
 

@@ -1,0 +1,315 @@
+"""GPU parity tests: the C-ABI kernels (through KGEkeras._engine, i.e. ctypes -> libkgeb200.so) against the CPU oracle.
+
+Bars (stated here, as the task demands):
+  * integer / index work (Philox negatives, filtered rank counts): bit-exact;
+  * scores on dyadic tables (every product and sum exact in fp32): bit-exact, any summation order;
+  * fp32 scores / losses / gradients on real-valued tables: |gpu - fp64 truth| <= 1e-5 * (sum of |terms|), i.e. 1e-5
+    relative to the magnitude the rounding error scales with (a plain relative bound is meaningless for sums that cancel);
+  * rank kernel scores on real-valued tables: bit-exact against the sequential-k fp32 emulation in the oracle.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kge_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+KINDS = [ko.DISTMULT, ko.TRANSE_L1, ko.TRANSE_L2, ko.COMPLEX, ko.HOLE]
+KNAME = {ko.DISTMULT: "DistMult", ko.TRANSE_L1: "TransE_L1", ko.TRANSE_L2: "TransE_L2", ko.COMPLEX: "ComplEx", ko.HOLE: "HolE"}
+RTOL = 1e-5
+
+
+def width(kind, d):
+    return 2 * d if kind == ko.COMPLEX else d
+
+
+def make_engine(kind, N, R, d, seed=0, dyadic=False, gamma=12.0, scale=1.0):
+    from KGEkeras._engine import Engine
+    rng = np.random.default_rng(seed)
+    W = width(kind, d)
+    if dyadic:
+        E, Rm = ko.dyadic_table(rng, N, W), ko.dyadic_table(rng, R, W)
+    else:
+        E, Rm = ko.glorot_uniform(rng, N, W) * scale, ko.glorot_uniform(rng, R, W) * scale
+    return Engine(kind, N, R, W, W, gamma, E=E, R=Rm), E, Rm
+
+
+def rand_triples(rng, n, N, R):
+    return np.stack([rng.integers(0, N, n), rng.integers(0, R, n), rng.integers(0, N, n)], axis=1).astype(np.int32)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("d", [4, 100, 200, 256, 320])
+def test_score_fwd_dyadic_exact(kind, d):
+    if kind == ko.HOLE and d > 256:
+        pytest.skip("HolE O(d^2) oracle is slow")
+    eng, E, Rm = make_engine(kind, 300, 11, d, seed=d, dyadic=True)
+    rng = np.random.default_rng(1)
+    idx = rand_triples(rng, 777, 300, 11)
+    idx[:5, 2] = idx[:5, 0]  # self loops
+    got = eng.score(idx).cpu().numpy()
+    # fp32 op-by-op oracle: on dyadic tables every intermediate is exact, so any summation order gives these bits
+    want = ko.score_triples(kind, E, Rm, idx, 12.0, np.float32, hole_fft=False)
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("d", [8, 100, 200])
+def test_score_fwd_real(kind, d):
+    eng, E, Rm = make_engine(kind, 500, 7, d, seed=3 + d, scale=3.0)
+    rng = np.random.default_rng(2)
+    idx = rand_triples(rng, 1000, 500, 7)
+    got = eng.score(idx).cpu().numpy().astype(np.float64)
+    want = ko.score_triples(kind, E, Rm, idx, 12.0, np.float64, hole_fft=False)
+    bound = RTOL * ko.score_abs_terms(kind, E, Rm, idx, 12.0)
+    assert np.all(np.abs(got - want) <= bound), float(np.max(np.abs(got - want) / bound))
+    # and the fp32 op-by-op restatement of the reference sits inside the same band
+    ref32 = ko.score_triples(kind, E, Rm, idx, 12.0, np.float32).astype(np.float64)
+    assert np.all(np.abs(ref32 - want) <= bound)
+
+
+def test_score_empty_and_errors():
+    from KGEkeras import _abi as abi
+    from KGEkeras._engine import Engine
+    eng, _, _ = make_engine(ko.DISTMULT, 10, 3, 8)
+    assert eng.score(np.zeros((0, 3), np.int32)).numel() == 0
+    with pytest.raises(ValueError):
+        eng.score(np.zeros((4, 2), np.int32))
+    with pytest.raises(abi.KgebError):  # ComplEx needs dim % 4 == 0: reported, never a silent slow path
+        Engine(ko.COMPLEX, 10, 3, 12, 12).score(np.zeros((1, 3), np.int32))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("d", [8, 100])
+def test_score_bwd(kind, d):
+    N, R, M = 200, 5, 900
+    eng, E, Rm = make_engine(kind, N, R, d, seed=11, scale=3.0)
+    rng = np.random.default_rng(5)
+    idx = rand_triples(rng, M, N, R)
+    idx[:4, 2] = idx[:4, 0]
+    dscore = rng.normal(size=M).astype(np.float32)
+    dscore[10:20] = 0.0
+    eng.score_bwd(idx, torch.from_numpy(dscore))
+    gE, gR, tE, tR = ko.dense_grads(kind, E, Rm, idx, dscore, 12.0)
+    got_gE = eng.gE.cpu().numpy()[:, :E.shape[1]].astype(np.float64)
+    got_gR = eng.gR.cpu().numpy()[:, :Rm.shape[1]].astype(np.float64)
+    gs = max(np.max(np.abs(gE)), np.max(np.abs(gR)))
+    np.testing.assert_allclose(got_gE, gE, rtol=1e-4, atol=1e-5 * gs)
+    np.testing.assert_allclose(got_gR, gR, rtol=1e-4, atol=1e-5 * gs)
+    np.testing.assert_array_equal(eng.tE.cpu().numpy().astype(bool), tE)
+    np.testing.assert_array_equal(eng.tR.cpu().numpy().astype(bool), tR)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [ko.CORRUPT_BOTH, ko.CORRUPT_HEAD, ko.CORRUPT_TAIL, ko.CORRUPT_EITHER])
+def test_philox_negatives_bit_exact(mode):
+    N = 40943
+    eng, _, _ = make_engine(ko.DISTMULT, N, 11, 4)
+    rng = np.random.default_rng(9)
+    pos = rand_triples(rng, 1000, N, 11)
+    for seed, offset, K in [(0, 0, 1), (12345678901234567, 3, 10), (2 ** 63 + 5, 2 ** 40 + 1, 7)]:
+        got = eng.negatives(pos, K, seed, offset, mode).cpu().numpy()
+        want = ko.philox_negatives(pos, N, K, seed, offset, mode)
+        np.testing.assert_array_equal(got, want.astype(np.int32))
+
+
+@pytest.mark.parametrize("lname", list(ko.LOSS_NAMES))
+@pytest.mark.parametrize("pm", [ko.PAIRED, ko.ALLPAIRS])
+def test_loss_fwd_bwd(lname, pm):
+    lk = ko.LOSS_NAMES[lname]
+    eng, _, _ = make_engine(ko.DISTMULT, 10, 3, 4)
+    rng = np.random.default_rng(lk * 2 + pm)
+    B, K = 300, 7
+    t = rng.normal(size=B).astype(np.float32) * 2
+    f = rng.normal(size=B * K).astype(np.float32) * 2
+    loss, dt, df = eng.loss(torch.from_numpy(t), torch.from_numpy(f), K, lk, pm, 1.0, 1.0)
+    L, wdt, wdf = ko.loss_and_coefs(lk, pm, t.astype(np.float64), f.astype(np.float64), K, 1.0)
+    assert abs(float(loss.item()) - L) <= 2e-6 * max(1.0, abs(L))
+    np.testing.assert_allclose(dt.cpu().numpy(), wdt, rtol=2e-5, atol=2e-7 * np.max(np.abs(wdt)))
+    np.testing.assert_allclose(df.cpu().numpy(), wdf, rtol=2e-5, atol=2e-7 * np.max(np.abs(wdf)))
+    # the reference function itself (restated) gives the same value
+    ref = ko.loss_function_lookup(lname)
+    if pm == ko.PAIRED:
+        Lref = ref(t.reshape(-1, 1) if lk >= ko.PAIRWISE_HINGE else t, f, 1.0, K)
+    else:
+        Lref = ref(t, f, 1.0, 1)
+    assert abs(float(Lref) - L) <= 1e-5 * max(1.0, abs(L))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def _state(kind_opt, E, Rm):
+    if kind_opt == ko.OPT_SGD:
+        return [], []
+    if kind_opt == ko.OPT_ADAGRAD:
+        return [np.full_like(E, 0.1)], [np.full_like(Rm, 0.1)]
+    return [np.zeros_like(E), np.zeros_like(E)], [np.zeros_like(Rm), np.zeros_like(Rm)]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("lname,pm", [("pairwize_hinge", ko.PAIRED), ("pairwize_logistic", ko.PAIRED),
+                                      ("pointwize_logistic", ko.PAIRED), ("pointwize_hinge", ko.PAIRED),
+                                      ("pairwize_hinge", ko.ALLPAIRS), ("pairwize_square_loss", ko.PAIRED),
+                                      ("pointwize_square_loss", ko.PAIRED)])
+@pytest.mark.parametrize("opt", [ko.OPT_LAZY_ADAM, ko.OPT_ADAM_DENSE, ko.OPT_ADAGRAD, ko.OPT_SGD])
+def test_train_step_index_driven(kind, lname, pm, opt):
+    if opt in (ko.OPT_ADAGRAD, ko.OPT_SGD) and lname not in ("pairwize_hinge",):
+        pytest.skip("optimizer variants are exercised on one loss")
+    lk = ko.LOSS_NAMES[lname]
+    N, R, d, B, K = 120, 6, 16, 64, 5
+    eng, E, Rm = make_engine(kind, N, R, d, seed=21, scale=4.0, gamma=2.0)
+    rng = np.random.default_rng(31)
+    pos = rand_triples(rng, B, N, R)
+    neg = ko.philox_negatives(pos, N, K, 7, 0, ko.CORRUPT_EITHER).astype(np.int32)
+    neg[::3, 1] = (neg[::3, 1] + 1) % R  # index-driven negatives may carry any relation
+    lr = 0.05
+    sE, sR = _state(opt, E, Rm)
+    # eps = 1e-3 keeps Adam's m/(sqrt(v)+eps) well conditioned for gradients that cancel to ~0 (the fp32 atomics'
+    # summation order is free); the default eps = 1e-7 is covered with exact inputs in test_opt_update_exact_inputs
+    want = ko.train_step(kind, lk, pm, E, Rm, pos, neg, K, 1.0, 2.0, opt, sE, sR, lr, 1, np.float64, eps=1e-3)
+    res = eng.forward_backward(pos, neg, K=K, loss_kind=lk, pair_mode=pm, margin=1.0, want_scores=True, opt_kind=opt)
+    W = E.shape[1]
+    gE = eng.gE.cpu().numpy()[:, :W].astype(np.float64)
+    gR = eng.gR.cpu().numpy()[:, :W].astype(np.float64)
+    L = float(res["loss"].item())
+    assert abs(L - want["loss"]) <= 1e-5 * max(1.0, abs(want["loss"])), (L, want["loss"])
+    tol_s = RTOL * ko.score_abs_terms(kind, E, Rm, pos, 2.0)
+    assert np.all(np.abs(res["pos_scores"].cpu().numpy() - want["pos_scores"]) <= tol_s)
+    gs = max(np.max(np.abs(want["gE"])), np.max(np.abs(want["gR"])))
+    np.testing.assert_allclose(gE, want["gE"], rtol=1e-4, atol=1e-5 * gs)
+    np.testing.assert_allclose(gR, want["gR"], rtol=1e-4, atol=1e-5 * gs)
+    eng.apply_optimizer(opt, lr=lr, eps=1e-3)
+    E1, R1 = eng.get_tables()
+    np.testing.assert_allclose(E1, want["E"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(R1, want["R"], rtol=1e-4, atol=2e-5)
+    # gradient buffers and flags are handed back clean
+    assert float(eng.gE.abs().max()) == 0.0 and float(eng.gR.abs().max()) == 0.0
+    assert int(eng.tE.sum()) == 0 and int(eng.tR.sum()) == 0
+
+
+@pytest.mark.parametrize("kind", [ko.DISTMULT, ko.TRANSE_L1, ko.COMPLEX])
+@pytest.mark.parametrize("mode", [ko.CORRUPT_BOTH, ko.CORRUPT_EITHER])
+def test_train_step_philox_equals_index_driven(kind, mode):
+    """In-kernel Philox negatives == the host restatement, and the fused pass on them == the unfused sequence."""
+    N, R, d, B, K = 500, 4, 100, 256, 10
+    eng, E, Rm = make_engine(kind, N, R, d, seed=5, scale=3.0)
+    rng = np.random.default_rng(6)
+    pos = rand_triples(rng, B, N, R)
+    lk = ko.PAIRWISE_HINGE
+    res = eng.forward_backward(pos, None, K=K, loss_kind=lk, margin=1.0, corrupt_mode=mode, seed=99, offset=4,
+                               want_scores=True, want_neg=True)
+    neg_want = ko.philox_negatives(pos, N, K, 99, 4, mode).astype(np.int32)
+    np.testing.assert_array_equal(res["neg"].cpu().numpy(), neg_want)
+    g1 = eng.gE.clone(), eng.gR.clone()
+    L1 = float(res["loss"].item())
+    eng.gE.zero_(); eng.gR.zero_(); eng.tE.zero_(); eng.tR.zero_()
+    res2 = eng.forward_backward(pos, neg_want, K=K, loss_kind=lk, margin=1.0, force_unfused=True)
+    assert abs(L1 - float(res2["loss"].item())) <= 1e-6 * max(1.0, abs(L1))
+    gs = float(g1[0].abs().max())
+    assert float((g1[0] - eng.gE).abs().max()) <= 1e-5 * gs
+    assert float((g1[1] - eng.gR).abs().max()) <= 1e-5 * max(gs, float(g1[1].abs().max()))
+
+
+def test_multi_step_training_reduces_loss_and_tracks_oracle():
+    """20 LazyAdam steps on a fixed batch: loss decreases and the table stays within fp32 drift of the fp64 oracle."""
+    kind, N, R, d, B, K = ko.DISTMULT, 80, 4, 16, 128, 4
+    eng, E, Rm = make_engine(kind, N, R, d, seed=8, scale=2.0)
+    rng = np.random.default_rng(8)
+    pos = rand_triples(rng, B, N, R)
+    neg = ko.philox_negatives(pos, N, K, 1, 0, ko.CORRUPT_BOTH).astype(np.int32)
+    E64, R64 = E.astype(np.float64), Rm.astype(np.float64)
+    sE, sR = _state(ko.OPT_LAZY_ADAM, E64, R64)
+    losses = []
+    for step in range(1, 21):
+        res = eng.train_step(pos, neg, opt_kind=ko.OPT_LAZY_ADAM, lr=0.01, eps=1e-4, K=K, loss_kind=ko.PAIRWISE_LOGISTIC, margin=0.0)
+        losses.append(float(res["loss"].item()))
+        w = ko.train_step(kind, ko.PAIRWISE_LOGISTIC, ko.PAIRED, E64, R64, pos, neg, K, 0.0, 12.0, ko.OPT_LAZY_ADAM,
+                          sE, sR, 0.01, step, np.float64, eps=1e-4)
+        assert abs(losses[-1] - w["loss"]) <= 1e-4 * abs(w["loss"])
+        E64, R64, sE, sR = w["E"], w["R"], w["state_E"], w["state_R"]
+    assert losses[-1] < losses[0]
+    E1, R1 = eng.get_tables()
+    np.testing.assert_allclose(E1, E64, rtol=1e-3, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def _rank_case(kind, N, R, d, Q, seed, dyadic):
+    eng, E, Rm = make_engine(kind, N, R, d, seed=seed, dyadic=dyadic, scale=3.0)
+    rng = np.random.default_rng(seed + 1)
+    tri = rand_triples(rng, Q, N, R)
+    known = rand_triples(rng, 4 * Q, N, R)
+    known[:Q, :2] = tri[:, :2]   # some known-true triples share (s,p) / (p,o) with the queries
+    known[Q:2 * Q, 1:] = tri[:, 1:]
+    fh, ft = ko.build_filters([tuple(int(x) for x in r) for r in known])
+    return eng, E, Rm, tri, fh, ft
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("side", ["tail", "head"])
+@pytest.mark.parametrize("d,N,Q", [(8, 130, 70), (100, 1000, 257), (36, 64, 64)])
+def test_rank_counts_bit_exact_real_valued(kind, side, d, N, Q):
+    eng, E, Rm, tri, fh, ft = _rank_case(kind, N, 5, d, Q, seed=17 + d, dyadic=False)
+    filt = ft if side == "tail" else fh
+    offs, ids = ko.filter_csr(tri, side, filt)
+    sd = 0 if side == "tail" else 1
+    counts = eng.rank_counts(tri, sd, offs, ids).cpu().numpy()
+    qv = ko.query_vectors(kind, E, Rm, tri, side)
+    sc = ko.seqk_scores(kind, qv, E, side, 12.0)
+    want = ko.ranks_from_scores(sc, tri, side, filt) - 1
+    np.testing.assert_array_equal(counts, want.astype(np.int32))
+    # near-tie-aware agreement with the fp64 truth: ranks may differ only where fp64 scores are within the fp32 band
+    sc64 = ko.all_entity_scores(kind, E, Rm, tri, side, 12.0, np.float64)
+    r64 = ko.ranks_from_scores(sc64, tri, side, filt)
+    diff = np.nonzero(r64 - 1 != counts)[0]
+    for qi in diff:
+        tgt = tri[qi, 2] if side == "tail" else tri[qi, 0]
+        gap = np.sort(np.abs(sc64[qi] - sc64[qi, tgt]))[1:1 + abs(int(r64[qi] - 1 - counts[qi]))]
+        assert np.all(gap <= 1e-4 * max(1.0, np.max(np.abs(sc64[qi])))), (qi, gap)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("side", ["tail", "head"])
+def test_rank_counts_dyadic_exact_with_ties(kind, side):
+    eng, E, Rm, tri, fh, ft = _rank_case(kind, 700, 5, 12, 200, seed=3, dyadic=True)
+    filt = ft if side == "tail" else fh
+    offs, ids = ko.filter_csr(tri, side, filt)
+    counts = eng.rank_counts(tri, 0 if side == "tail" else 1, offs, ids).cpu().numpy()
+    sc = ko.all_entity_scores(kind, E, Rm, tri, side, 12.0, np.float32)   # exact on dyadic tables
+    want = ko.ranks_from_scores(sc, tri, side, filt) - 1
+    np.testing.assert_array_equal(counts, want.astype(np.int32))
+
+
+@pytest.mark.parametrize("opt", [ko.OPT_SGD, ko.OPT_ADAGRAD, ko.OPT_LAZY_ADAM, ko.OPT_ADAM_DENSE])
+def test_opt_update_exact_inputs(opt):
+    """Optimizer kernel alone, fed the same fp32 gradient as the oracle, Keras default eps = 1e-7, 3 steps."""
+    N, W = 333, 24
+    eng, E, Rm = make_engine(ko.DISTMULT, N, 4, W, seed=2)
+    eng._ensure_train_buffers(opt)
+    rng = np.random.default_rng(12)
+    P = E.astype(np.float64)
+    st = [x.astype(np.float64) for x in _state(opt, E, Rm)[0]]
+    for step in range(1, 4):
+        touched = rng.random(N) < 0.3
+        G = (rng.normal(size=(N, W)) * touched[:, None]).astype(np.float32)
+        eng.gE.copy_(torch.from_numpy(G))
+        eng.tE.copy_(torch.from_numpy(touched.astype(np.uint8)))
+        eng.apply_optimizer(opt, lr=0.01)
+        P, st = ko.opt_update(opt, P, G.astype(np.float64), touched, st, 0.01, step)
+        np.testing.assert_allclose(eng.E.cpu().numpy(), P, rtol=2e-5, atol=1e-6)
+        assert float(eng.gE.abs().max()) == 0.0 and int(eng.tE.sum()) == 0
+
+
+def test_rank_shards_sum_to_whole():
+    """Integer partial counts over any row partition add up to the single-shard result (the multi-GPU contract)."""
+    kind = ko.TRANSE_L1
+    eng, E, Rm, tri, fh, ft = _rank_case(kind, 1000, 5, 20, 150, seed=4, dyadic=False)
+    offs, ids = ko.filter_csr(tri, "tail", ft)
+    whole = eng.rank_counts(tri, 0, offs, ids).cpu().numpy()
+    for G in (2, 3, 8):
+        per = -(-1000 // G)
+        acc = np.zeros_like(whole)
+        for g in range(G):
+            r0, r1 = g * per, min(1000, (g + 1) * per)
+            acc += eng.rank_counts(tri, 0, offs, ids, row_range=(r0, r1)).cpu().numpy()
+        np.testing.assert_array_equal(acc, whole)
