@@ -453,7 +453,9 @@ int grid_for(const kgeb_ctx* ctx, int64_t warps_needed, int blocks_per_sm) {
 extern "C" int kgeb_score_fwd(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* idx, int64_t m, float* scores,
                               kgeb_stream stream) {
   if (!ctx) return KGEB_ERR_INVALID;
-  KGEB_REQUIRE(ctx, idx && scores && m >= 0, KGEB_ERR_INVALID, "score_fwd: bad arguments");
+  KGEB_REQUIRE(ctx, m >= 0, KGEB_ERR_INVALID, "score_fwd: negative batch");
+  if (m == 0) return KGEB_OK;  /* empty batch: nothing to read, pointers may be null */
+  KGEB_REQUIRE(ctx, idx && scores, KGEB_ERR_INVALID, "score_fwd: bad arguments");
   if (int rc = check_tables(ctx, E, R)) return rc;
   if (m == 0) return KGEB_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -478,7 +480,9 @@ extern "C" int kgeb_score_bwd(kgeb_ctx* ctx, const float* E, const float* R, con
                               const float* dscore, float* gE, float* gR, uint8_t* touchedE, uint8_t* touchedR,
                               kgeb_stream stream) {
   if (!ctx) return KGEB_ERR_INVALID;
-  KGEB_REQUIRE(ctx, idx && dscore && gE && gR && touchedE && touchedR && m >= 0, KGEB_ERR_INVALID, "score_bwd: bad arguments");
+  KGEB_REQUIRE(ctx, m >= 0, KGEB_ERR_INVALID, "score_bwd: negative batch");
+  if (m == 0) return KGEB_OK;
+  KGEB_REQUIRE(ctx, idx && dscore && gE && gR && touchedE && touchedR, KGEB_ERR_INVALID, "score_bwd: bad arguments");
   if (int rc = check_tables(ctx, E, R)) return rc;
   KGEB_REQUIRE(ctx, ctx->kind == KGEB_HOLE || (kgeb_aligned16(gE) && kgeb_aligned16(gR)), KGEB_ERR_ALIGNMENT,
                "gradient buffers must be 16-byte aligned");
