@@ -6,6 +6,7 @@
 // Reference arithmetic replaced: EmbeddingModel.call models.py:134-162, DistMult.func 171-172, TransE.func 186-190,
 // ComplEx.func 212-222, HolE.func 231-237, losses utils.py:288-319, negatives utils.py:114-121.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -302,6 +303,222 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_train_fwd_bwd(TrainArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// fused train forward + gradient, shared-memory ring version (the default path).
+//
+// The register version above is latency bound (profiles/r01_v1_summary.md: 8.9 warps stalled on global loads per
+// issued instruction, L2 15 % busy).  Here every gathered row travels global -> shared memory as ONE bulk async copy
+// (cp.async.bulk, SASS UBLKCP) that completes on an mbarrier, and each warp owns a private ring of D stages
+// (one stage = the rows of one negative), so D negatives per warp are in flight without costing registers.  The warp is
+// its own producer and consumer: no block-level synchronisation exists in the main loop.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "KGEB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra KGEB_DONE;\n\t"
+      "bra KGEB_WAIT;\n\t"
+      "KGEB_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+template <int KIND, int NC>
+__device__ __forceinline__ void load_frag_smem(Frag<KIND, NC>& f, const float* row, RowGeom g, int lane) {
+  const float4* r4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int c = lane + 32 * i;
+    const bool ok = c < g.nch;
+    f.v[i] = ok ? r4[c] : f4zero();
+    if (KIND == COMPLEX) f.v[NC + i] = ok ? r4[g.half4 + c] : f4zero();
+  }
+}
+
+template <int KIND, int NC>
+__global__ void __launch_bounds__(KGEB_THREADS) k_train_ring(TrainArgs a, int D, int RB) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const size_t region = (size_t)(3 + 3 * D) * RB;
+  unsigned char* base = smem_raw + (size_t)w * region;
+  float* posS = reinterpret_cast<float*>(base);
+  float* posP = reinterpret_cast<float*>(base + RB);
+  float* posO = reinterpret_cast<float*>(base + 2 * (size_t)RB);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)KGEB_WARPS_PER_BLOCK * region) + w * (D + 1);
+  if (lane == 0)
+    for (int i = 0; i <= D; ++i) mbar_init(bars + i, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  const ScoreArgs& sc = a.sc;
+  const int64_t nw = (int64_t)gridDim.x * KGEB_WARPS_PER_BLOCK;
+  const bool pairwise = a.loss_kind >= KGEB_PAIRWISE_HINGE;
+  const double cntP = (double)a.B, cntN = (double)a.B * (double)a.K;
+  const float scaleP = (float)((double)a.loss_weight / cntP), scaleN = (float)((double)a.loss_weight / cntN);
+  const int K = a.K;
+  double lp = 0.0, ln = 0.0;
+  uint32_t phases = 0;  // bit 0: positive barrier, bit 1+s: stage s
+
+  for (int64_t g = (int64_t)blockIdx.x * KGEB_WARPS_PER_BLOCK + w; g < a.B; g += nw) {
+    const int s = __ldg(a.pos + 3 * g), p = __ldg(a.pos + 3 * g + 1), o = __ldg(a.pos + 3 * g + 2);
+    __syncwarp();  // every lane is done reading the previous group's buffers
+    if (lane == 0) {
+      mbar_expect_tx(bars, 3u * RB);
+      bulk_g2s(posS, sc.E + (int64_t)s * sc.ldE, RB, bars);
+      bulk_g2s(posP, sc.R + (int64_t)p * sc.ldR, RB, bars);
+      bulk_g2s(posO, sc.E + (int64_t)o * sc.ldE, RB, bars);
+    }
+    // ids of this group's negatives: lane l owns negative (chunk*32 + l), drawn by Philox or read from the caller's
+    // index tensor.  Two chunks are held (cur, ahead) because issue() runs up to D <= 32 negatives ahead of consumption.
+    auto compute_chunk = [&](int chunk, int& ns, int& np, int& no) {
+      const int j = chunk * 32 + lane;
+      ns = s; np = p; no = o;
+      if (j < K) {
+        const int64_t gi = g * (int64_t)K + j;
+        if (a.neg) {
+          ns = __ldg(a.neg + 3 * gi); np = __ldg(a.neg + 3 * gi + 1); no = __ldg(a.neg + 3 * gi + 2);
+        } else {
+          philox_corrupt(s, o, (uint64_t)gi, a.seed, a.offset, a.N, a.corrupt_mode, ns, no);
+        }
+        if (a.neg_out) { a.neg_out[3 * gi] = ns; a.neg_out[3 * gi + 1] = np; a.neg_out[3 * gi + 2] = no; }
+        a.tE[ns] = 1; a.tE[no] = 1; a.tR[np] = 1;
+      }
+    };
+    int cur_chunk = 0, my_ns, my_np, my_no, ah_ns = s, ah_np = p, ah_no = o;
+    compute_chunk(0, my_ns, my_np, my_no);
+    if (K > 32) compute_chunk(1, ah_ns, ah_np, ah_no);
+    auto ids_of = [&](int j, int& ns, int& np, int& no) {
+      const bool in_cur = (j >> 5) == cur_chunk;  // warp-uniform; otherwise j lies in chunk cur_chunk + 1
+      const int l = j & 31;
+      ns = __shfl_sync(0xffffffffu, in_cur ? my_ns : ah_ns, l);
+      np = __shfl_sync(0xffffffffu, in_cur ? my_np : ah_np, l);
+      no = __shfl_sync(0xffffffffu, in_cur ? my_no : ah_no, l);
+    };
+    // issue the rows of negative j into stage j % D (rows shared with the positive are not copied again)
+    auto issue = [&](int j) {
+      int ns, np, no;
+      ids_of(j, ns, np, no);
+      if (lane == 0) {
+        const int st = j % D;
+        unsigned char* sb = base + (size_t)(3 + 3 * st) * RB;
+        const uint32_t nrows = (ns != s) + (np != p) + (no != o);
+        if (nrows) {
+          mbar_expect_tx(bars + 1 + st, nrows * (uint32_t)RB);
+          if (ns != s) bulk_g2s(sb, sc.E + (int64_t)ns * sc.ldE, RB, bars + 1 + st);
+          if (np != p) bulk_g2s(sb + RB, sc.R + (int64_t)np * sc.ldR, RB, bars + 1 + st);
+          if (no != o) bulk_g2s(sb + 2 * (size_t)RB, sc.E + (int64_t)no * sc.ldE, RB, bars + 1 + st);
+        }
+      }
+    };
+    const int prime = K < D ? K : D;
+    for (int j = 0; j < prime; ++j) issue(j);
+
+    // positive score
+    mbar_wait(bars, phases & 1u);
+    phases ^= 1u;
+    float tsum, t;
+    {
+      Frag<KIND, NC> S, P, O;
+      load_frag_smem(S, posS, sc.ge, lane);
+      load_frag_smem(P, posP, sc.gr, lane);
+      load_frag_smem(O, posO, sc.ge, lane);
+      tsum = warp_sum(score_partial(S, P, O));
+      t = score_finish<KIND>(tsum, sc.gamma);
+    }
+    if (lane == 0) {
+      if (a.pos_scores) a.pos_scores[g] = t;
+      a.tE[s] = 1; a.tE[o] = 1; a.tR[p] = 1;
+    }
+    float cpos = 0.f;
+    if (!pairwise) {
+      float val, der;
+      pointwise_terms(a.loss_kind, a.margin, t, true, val, der);
+      lp += (double)val;
+      cpos = der * scaleP;
+    }
+    Frag<KIND, NC> AS, AP, AO;
+    zero_frag(AS); zero_frag(AP); zero_frag(AO);
+    bool usedS = false, usedP = false, usedO = false;
+
+    for (int j = 0; j < K; ++j) {
+      if ((j & 31) == 0 && j > 0) {  // crossed into the "ahead" chunk: rotate, then draw the chunk after it
+        cur_chunk = j >> 5; my_ns = ah_ns; my_np = ah_np; my_no = ah_no;
+        if ((cur_chunk + 1) * 32 < K) compute_chunk(cur_chunk + 1, ah_ns, ah_np, ah_no);
+      }
+      int ns, np, no;
+      ids_of(j, ns, np, no);
+      const int st = j % D;
+      const unsigned char* sb = base + (size_t)(3 + 3 * st) * RB;
+      if ((ns != s) | (np != p) | (no != o)) {
+        mbar_wait(bars + 1 + st, (phases >> (1 + st)) & 1u);
+        phases ^= 1u << (1 + st);
+      }
+      const float* rS = ns != s ? reinterpret_cast<const float*>(sb) : posS;
+      const float* rP = np != p ? reinterpret_cast<const float*>(sb + RB) : posP;
+      const float* rO = no != o ? reinterpret_cast<const float*>(sb + 2 * (size_t)RB) : posO;
+      Frag<KIND, NC> Sn, Pn, On;
+      load_frag_smem(Sn, rS, sc.ge, lane);
+      load_frag_smem(Pn, rP, sc.gr, lane);
+      load_frag_smem(On, rO, sc.ge, lane);
+      const float fsum = warp_sum(score_partial(Sn, Pn, On));
+      // the butterfly consumed every lane's loads of this stage, so the stage can be refilled for negative j + D
+      if (j + D < K) issue(j + D);
+      const float f = score_finish<KIND>(fsum, sc.gamma);
+      float cneg;
+      if (pairwise) {
+        float val, A;
+        pairwise_terms(a.loss_kind, a.margin, f - t, val, A);
+        ln += (double)val;
+        cneg = A * scaleN;
+        cpos -= cneg;
+      } else {
+        float val, der;
+        pointwise_terms(a.loss_kind, a.margin, f, false, val, der);
+        ln += (double)val;
+        cneg = der * scaleN;
+      }
+      if (lane == 0 && a.neg_scores) a.neg_scores[g * (int64_t)K + j] = f;
+      if (cneg != 0.f) {
+        Frag<KIND, NC> GS, GP, GO;
+        score_grads(Sn, Pn, On, cneg, fsum, sc.gamma, GS, GP, GO);
+        if (ns != s) red_frag(a.gE, ns, sc.ldE, sc.ge, lane, GS); else { add_frag(AS, GS); usedS = true; }
+        if (np != p) red_frag(a.gR, np, sc.ldR, sc.gr, lane, GP); else { add_frag(AP, GP); usedP = true; }
+        if (no != o) red_frag(a.gE, no, sc.ldE, sc.ge, lane, GO); else { add_frag(AO, GO); usedO = true; }
+      }
+    }
+    if (cpos != 0.f) {
+      Frag<KIND, NC> S, P, O, GS, GP, GO;
+      load_frag_smem(S, posS, sc.ge, lane);
+      load_frag_smem(P, posP, sc.gr, lane);
+      load_frag_smem(O, posO, sc.ge, lane);
+      score_grads(S, P, O, cpos, tsum, sc.gamma, GS, GP, GO);
+      add_frag(AS, GS); add_frag(AP, GP); add_frag(AO, GO);
+      usedS = usedP = usedO = true;
+    }
+    if (usedS) red_frag(a.gE, s, sc.ldE, sc.ge, lane, AS);
+    if (usedP) red_frag(a.gR, p, sc.ldR, sc.gr, lane, AP);
+    if (usedO) red_frag(a.gE, o, sc.ldE, sc.ge, lane, AO);
+  }
+  if (lane != 0) { lp = 0.0; ln = 0.0; }
+  const double wgt = (double)a.loss_weight;
+  block_finalize_loss(lp, ln, a.partials, a.ticket, pairwise ? 0.0 : wgt / cntP, wgt / cntN, a.loss);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // HolE: f = sum_k p_k sum_i s_i o_{(i+k) mod d}; rows staged in shared memory, O(d^2/32) per lane
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void hole_stage(float* dst, const float* __restrict__ src, int d, int lane) {
@@ -431,20 +648,20 @@ int grid_for(const kgeb_ctx* ctx, int64_t warps_needed, int blocks_per_sm) {
 
 // NC (chunks per lane) is a compile-time constant so rows live in registers: widths up to 512 floats
 // (ComplEx: dim up to 256) are covered; wider rows are reported, never silently slow-pathed.
-#define KGEB_DISPATCH_NC(NCV, CALL)                                       \
+#define KGEB_DISPATCH_NC(NCV, ...)                                        \
   switch (NCV) {                                                          \
-    case 1: { constexpr int NC = 1; CALL; } break;                        \
-    case 2: { constexpr int NC = 2; CALL; } break;                        \
-    case 3: { constexpr int NC = 3; CALL; } break;                        \
-    case 4: { constexpr int NC = 4; CALL; } break;                        \
+    case 1: { constexpr int NC = 1; __VA_ARGS__; } break;                 \
+    case 2: { constexpr int NC = 2; __VA_ARGS__; } break;                 \
+    case 3: { constexpr int NC = 3; __VA_ARGS__; } break;                 \
+    case 4: { constexpr int NC = 4; __VA_ARGS__; } break;                 \
     default: return kgeb_fail(ctx, KGEB_ERR_UNSUPPORTED, "row too wide for the register-resident kernels (max 512 floats; ComplEx dim 256)"); \
   }
-#define KGEB_DISPATCH_KIND(KINDV, CALL)                                              \
-  switch (KINDV) {                                                                   \
-    case KGEB_DISTMULT: { constexpr int KIND = KGEB_DISTMULT; CALL; } break;         \
-    case KGEB_TRANSE_L1: { constexpr int KIND = KGEB_TRANSE_L1; CALL; } break;       \
-    case KGEB_TRANSE_L2: { constexpr int KIND = KGEB_TRANSE_L2; CALL; } break;       \
-    case KGEB_COMPLEX: { constexpr int KIND = KGEB_COMPLEX; CALL; } break;           \
+#define KGEB_DISPATCH_KIND(KINDV, ...)                                                   \
+  switch (KINDV) {                                                                       \
+    case KGEB_DISTMULT: { constexpr int KIND = KGEB_DISTMULT; __VA_ARGS__; } break;      \
+    case KGEB_TRANSE_L1: { constexpr int KIND = KGEB_TRANSE_L1; __VA_ARGS__; } break;    \
+    case KGEB_TRANSE_L2: { constexpr int KIND = KGEB_TRANSE_L2; __VA_ARGS__; } break;    \
+    case KGEB_COMPLEX: { constexpr int KIND = KGEB_COMPLEX; __VA_ARGS__; } break;        \
     default: return kgeb_fail(ctx, KGEB_ERR_INVALID, "unknown score kind");          \
   }
 
@@ -540,10 +757,28 @@ extern "C" int kgeb_train_fwd_bwd(kgeb_ctx* ctx, const float* E, const float* R,
   a.corrupt_mode = corrupt_mode; a.seed = seed; a.offset = offset; a.N = (uint32_t)ctx->N;
   a.loss = loss; a.pos_scores = pos_scores; a.neg_scores = neg_scores; a.neg_out = neg_out;
   a.gE = gE; a.gR = gR; a.tE = touchedE; a.tR = touchedR; a.partials = ctx->d_partials; a.ticket = ctx->d_ticket;
-  int grid = grid_for(ctx, B, 4);
-  if (grid > KGEB_MAX_PARTIAL_BLOCKS) grid = KGEB_MAX_PARTIAL_BLOCKS;
   cudaStream_t st = (cudaStream_t)stream;
-  KGEB_DISPATCH_KIND(ctx->kind, KGEB_DISPATCH_NC(nc, (k_train_fwd_bwd<KIND, NC><<<grid, KGEB_THREADS, 0, st>>>(a))));
+  // shared-memory ring version: D stages of 3 rows per warp + the positive's 3 rows; 2 CTAs/SM when it fits
+  const int RB = ctx->we * (int)sizeof(float);
+  auto stages_for = [&](size_t budget) { return (int)(((long long)(budget / KGEB_WARPS_PER_BLOCK) - 3LL * RB) / (3LL * RB)); };
+  int ctas = 2, D = stages_for(112 * 1024);
+  if (D < 2) { ctas = 1; D = stages_for(224 * 1024); }
+  if (D > 8) D = 8;
+  const char* force = getenv("KGEB_TRAIN_KERNEL");
+  const bool use_ring = D >= 1 && !(force && strcmp(force, "reg") == 0);
+  if (use_ring) {
+    const size_t smem = (size_t)KGEB_WARPS_PER_BLOCK * (3 + 3 * D) * RB + (size_t)KGEB_WARPS_PER_BLOCK * (D + 1) * sizeof(uint64_t);
+    int grid = grid_for(ctx, B, ctas);
+    if (grid > KGEB_MAX_PARTIAL_BLOCKS) grid = KGEB_MAX_PARTIAL_BLOCKS;
+    KGEB_DISPATCH_KIND(ctx->kind, KGEB_DISPATCH_NC(nc, {
+      KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_train_ring<KIND, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_train_ring<KIND, NC><<<grid, KGEB_THREADS, smem, st>>>(a, D, RB);
+    }));
+  } else {
+    int grid = grid_for(ctx, B, 4);
+    if (grid > KGEB_MAX_PARTIAL_BLOCKS) grid = KGEB_MAX_PARTIAL_BLOCKS;
+    KGEB_DISPATCH_KIND(ctx->kind, KGEB_DISPATCH_NC(nc, (k_train_fwd_bwd<KIND, NC><<<grid, KGEB_THREADS, 0, st>>>(a))));
+  }
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
 }
