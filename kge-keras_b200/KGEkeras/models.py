@@ -1,0 +1,413 @@
+"""Host-side mirror of KGEkeras/models.py (reference): same class names, constructor keywords, `call` / `func` /
+`fit` / `evaluate` / `predict` entry points -- but no TensorFlow underneath.  Every score, loss, gradient and update
+is computed by libkgeb200's sm_100a kernels through KGEkeras._engine; there is no CPU fallback.
+
+Reference lines mirrored: EmbeddingModel.__init__ models.py:14-129, call 134-162, DistMult 164-172, TransE 175-190,
+ComplEx 203-222, HolE 224-237; sibling classes 192-200, 239-489 keep their constructors (their score kernels are the
+"next" rows of SURVEY 8f and raise NotImplementedError when scored).
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+from . import _abi as abi
+
+
+class Dropout:
+    """Stands in for keras.layers.Dropout(dp) (models.py:122): only the rate is kept."""
+
+    def __init__(self, rate):
+        self.rate = float(rate)
+
+
+class EmbeddingTable:
+    """Stands in for keras.layers.Embedding (models.py:89-112): owns nothing, views a table of the model's Engine."""
+
+    def __init__(self, model, which, input_dim, output_dim, name):
+        self._model, self._which = model, which
+        self.input_dim, self.output_dim, self.name = input_dim, output_dim, name
+        self.trainable = True
+
+    def get_weights(self):
+        E, R = self._model._engine_().get_tables()
+        return [E if self._which == "E" else R]
+
+    def set_weights(self, weights):
+        (w,) = weights
+        if self._which == "E":
+            self._model._engine_().set_tables(E=w)
+        else:
+            self._model._engine_().set_tables(R=w)
+
+    @property
+    def embeddings(self):
+        eng = self._model._engine_()
+        return eng.E[:, :eng.we] if self._which == "E" else eng.Rel[:, :eng.wr]
+
+    def __call__(self, ids):
+        import torch
+        ids = torch.as_tensor(np.asarray(ids)).to(self.embeddings.device).long()
+        return self.embeddings[ids]
+
+
+class History:
+    def __init__(self):
+        self.history = {}
+        self.epoch = []
+
+
+class _OptimizerSpec:
+    """Accepts what Keras' compile accepts for this path: a name or an object with Keras-style attributes."""
+
+    def __init__(self, opt):
+        name = opt if isinstance(opt, str) else type(opt).__name__
+        name = name.lower()
+        cfg = dict(learning_rate=None, beta_1=0.9, beta_2=0.999, epsilon=1e-7)
+        if not isinstance(opt, str):
+            for k in list(cfg):
+                if hasattr(opt, k):
+                    cfg[k] = float(getattr(opt, k))
+            if cfg["learning_rate"] is None and hasattr(opt, "lr"):
+                cfg["learning_rate"] = float(opt.lr)
+        if name not in abi.OPT_KINDS:
+            raise ValueError(f"optimizer {name!r} is not served by the B200 hot path (have {sorted(abi.OPT_KINDS)})")
+        self.kind = abi.OPT_KINDS[name]
+        # Keras defaults: Adam 1e-3, Adagrad 1e-3 (TF2), SGD 1e-2
+        self.lr = cfg["learning_rate"] if cfg["learning_rate"] is not None else (1e-2 if name == "sgd" else 1e-3)
+        self.beta1, self.beta2, self.eps = cfg["beta_1"], cfg["beta_2"], cfg["epsilon"]
+
+
+class EmbeddingModel:
+    """Base class (models.py:13-162).  Constructor signature identical to the reference's; `negative_samples`,
+    `batch_size` and `loss_function`, which the reference accepts and drops, drive `fit` here."""
+
+    _score_kind = None  # set by the four hot-path subclasses
+    _e_mult, _r_mult = 1, 1
+
+    def __init__(self,
+                 e_dim,
+                 r_dim,
+                 num_entities,
+                 num_relations,
+                 negative_samples=2,
+                 batch_size=16,
+                 loss_function='pointwize_hinge',
+                 dp=0.2,
+                 margin=1,
+                 loss_weight=1,
+                 regularization=0.0,
+                 literal_activation=None,
+                 literals=None,
+                 use_batch_norm=False,
+                 entity_embedding_args=None,
+                 relational_embedding_args=None,
+                 init_entities=None,
+                 init_relations=None,
+                 name='embedding_model',
+                 **kwargs):
+        self.regularization = regularization
+        self.num_entities = num_entities
+        self.num_relations = num_relations
+        self.name = name
+        self.entity_embedding = EmbeddingTable(self, "E", num_entities, e_dim, name + '_entity_embedding')
+        self.relational_embedding = EmbeddingTable(self, "R", num_relations, r_dim, name + '_relational_embedding')
+        if literal_activation:
+            raise NotImplementedError("the literal branch (models.py:114-120,152-158) is outside the B200 hot path (SURVEY 8f #4)")
+        self.dp = Dropout(dp)
+        self.e_dim = e_dim
+        self.r_dim = r_dim
+        self.margin = margin
+        self.loss_weight = loss_weight
+        self.negative_samples = negative_samples
+        self.batch_size = batch_size
+        self.loss_function = loss_function
+        self._init_E, self._init_R = init_entities, init_relations
+        self._eng = None
+        self._opt = _OptimizerSpec('adam')
+        self._seed, self._step_counter = int(np.random.randint(0, 2 ** 31 - 1)), 0
+        self.pair_mode = 'paired'          # 'allpairs' reproduces the (m,m) broadcast of the reference harness (tests.py:81)
+        self.corrupt = 'both'              # reference behaviour (utils.py:117-120); 'head' | 'tail' | 'either' honour the flags
+        self.stop_training = False
+        self.__dict__.update(kwargs)       # models.py:129: unknown keywords become attributes
+
+    # ---- engine ------------------------------------------------------------------------------------------------
+    def _gamma_(self):
+        return float(getattr(self, "gamma", 12.0))
+
+    def _kind_(self):
+        if self._score_kind is None:
+            raise NotImplementedError(f"{type(self).__name__}: score kernel not built yet (SURVEY 8f next rows); "
+                                      f"DistMult, TransE, ComplEx and HolE are served")
+        return self._score_kind
+
+    def _engine_(self):
+        if self._eng is None:
+            from ._engine import Engine
+            self._eng = Engine(self._kind_(), self.num_entities, self.num_relations, self.e_dim, self.r_dim,
+                               gamma=self._gamma_(), E=self._init_E, R=self._init_R)
+            self._init_E = self._init_R = None
+        return self._eng
+
+    def get_config(self):
+        return self.__dict__
+
+    # ---- forward -----------------------------------------------------------------------------------------------
+    def call(self, inputs, training=False):
+        """inputs: (batch, 3) ids (int or the harness' float32) -> (batch,) scores as a CUDA torch tensor."""
+        return self._engine_().score(inputs)
+
+    __call__ = call
+
+    def func(self, s, p, o, training=False):
+        """Score of already-gathered rows (the per-model hook of the reference).  Runs the same kernel on a scratch
+        engine whose tables are the given rows."""
+        import torch
+        from ._engine import Engine
+        s, p, o = (torch.as_tensor(np.asarray(x.detach().cpu() if hasattr(x, "detach") else x), dtype=torch.float32) for x in (s, p, o))
+        n = s.shape[0]
+        eng = Engine(self._kind_(), 2 * n, n, s.shape[1], p.shape[1], gamma=self._gamma_(), E=torch.cat([s, o]).numpy(), R=p.numpy())
+        idx = np.stack([np.arange(n), np.arange(n), n + np.arange(n)], axis=1).astype(np.int32)
+        return eng.score(idx)
+
+    def predict(self, x, batch_size=32, verbose=0, **kwargs):
+        """Keras Model.predict: numpy (n,) scores.  The whole input is scored in one launch (batch_size is accepted)."""
+        return self._engine_().score(x).cpu().numpy()
+
+    # ---- training ----------------------------------------------------------------------------------------------
+    def compile(self, optimizer='adam', loss=None, **kwargs):
+        self._opt = _OptimizerSpec(optimizer)
+        if isinstance(loss, str):
+            self.loss_function = loss
+
+    def _loss_kind(self):
+        if self.loss_function not in abi.LOSS_KINDS:
+            raise KeyError(self.loss_function)  # same exception as loss_function_lookup (utils.py:321-330)
+        return abi.LOSS_KINDS[self.loss_function]
+
+    def _step_kwargs(self):
+        if self.regularization != 0.0:
+            raise NotImplementedError("l3 regularisation (models.py:10-11) makes the gradient dense; not on the B200 path yet")
+        if self.dp.rate > 0 and not getattr(self, "_warned_dp", False):
+            warnings.warn(f"dropout dp={self.dp.rate} is not applied by the B200 kernels yet; training runs with dp=0")
+            self._warned_dp = True
+        return dict(loss_kind=self._loss_kind(), margin=float(self.margin if self.margin is not None else 1), loss_weight=float(self.loss_weight),
+                    pair_mode={'paired': abi.PAIRED, 'allpairs': abi.ALLPAIRS}[self.pair_mode],
+                    corrupt_mode={'both': abi.CORRUPT_BOTH, 'head': abi.CORRUPT_HEAD, 'tail': abi.CORRUPT_TAIL,
+                                  'either': abi.CORRUPT_EITHER}[self.corrupt])
+
+    @staticmethod
+    def _split_xy(x):
+        """([pos, neg], y) | [pos, neg] | pos  ->  (pos, neg or None)"""
+        if isinstance(x, tuple) and len(x) == 2 and (x[1] is None or np.ndim(x[1]) <= 1) and isinstance(x[0], (list, tuple)):
+            x = x[0]
+        if isinstance(x, (list, tuple)) and len(x) == 2 and np.ndim(x[0]) >= 2:
+            return x[0], x[1]
+        return x, None
+
+    def train_on_batch(self, x, y=None, **kwargs):
+        pos, neg = self._split_xy(x)
+        o = self._opt
+        self._step_counter += 1
+        res = self._engine_().train_step(pos, neg, opt_kind=o.kind, lr=o.lr, beta1=o.beta1, beta2=o.beta2, eps=o.eps,
+                                         K=int(self.negative_samples), seed=self._seed, offset=self._step_counter,
+                                         **self._step_kwargs())
+        return res["loss"]
+
+    def test_on_batch(self, x, y=None, **kwargs):
+        pos, neg = self._split_xy(x)
+        eng = self._engine_()
+        kw = self._step_kwargs()
+        if neg is None:
+            neg = eng.negatives(pos, int(self.negative_samples), self._seed, 2 ** 40 + self._step_counter, kw["corrupt_mode"])
+        t, f = eng.score(pos), eng.score(neg)
+        K = max(1, f.numel() // max(1, t.numel()))
+        loss, _, _ = eng.loss(t, f, K, kw["loss_kind"], kw["pair_mode"], kw["margin"], kw["loss_weight"], want_grads=False)
+        return loss
+
+    def fit(self, x=None, y=None, batch_size=None, epochs=1, verbose=1, callbacks=None, validation_data=None, shuffle=True,
+            steps_per_epoch=None, **kwargs):
+        """Keras-style fit.  x is a Sequence like the harness' DataGenerator (tests.py:29-61, yielding ([pos, neg], None)),
+        a [pos, neg] pair of (m,3) arrays, or a (n,3) array of positives (negatives then come from the in-kernel Philox
+        sampler, `negative_samples` per positive)."""
+        hist = History()
+        callbacks = list(callbacks or [])
+        for cb in callbacks:
+            if hasattr(cb, "set_model"):
+                cb.set_model(self)
+            else:
+                cb.model = self
+            if hasattr(cb, "on_train_begin"):
+                cb.on_train_begin({})
+        bs = int(batch_size or self.batch_size)
+        is_seq = hasattr(x, "__getitem__") and hasattr(x, "__len__") and not isinstance(x, (list, tuple, np.ndarray)) and not hasattr(x, "shape")
+        logs = {}
+        for epoch in range(epochs):
+            losses = []
+            if is_seq:
+                nb = len(x) if steps_per_epoch is None else min(len(x), steps_per_epoch)
+                for b in range(nb):
+                    losses.append(self.train_on_batch(x[b]))
+                if hasattr(x, "on_epoch_end"):
+                    x.on_epoch_end()
+            else:
+                pos, neg = self._split_xy(x)
+                pos = np.asarray(pos)
+                n = len(pos)
+                order = np.random.permutation(n) if shuffle else np.arange(n)
+                nb = (n + bs - 1) // bs if steps_per_epoch is None else steps_per_epoch
+                per = None if neg is None else len(np.asarray(neg)) // n
+                for b in range(nb):
+                    sel = order[b * bs:(b + 1) * bs]
+                    if len(sel) == 0:
+                        break
+                    if neg is None:
+                        losses.append(self.train_on_batch(pos[sel]))
+                    else:
+                        nsel = (sel[:, None] * per + np.arange(per)[None, :]).reshape(-1)
+                        losses.append(self.train_on_batch([pos[sel], np.asarray(neg)[nsel]]))
+            logs = {"loss": float(np.mean([float(l.item()) for l in losses])) if losses else float("nan")}
+            if validation_data is not None:
+                logs["val_loss"] = float(self.evaluate(validation_data, verbose=0))
+            for cb in callbacks:
+                if hasattr(cb, "on_epoch_end"):
+                    cb.on_epoch_end(epoch, logs)
+            hist.epoch.append(epoch)
+            for k, v in logs.items():
+                hist.history.setdefault(k, []).append(v)
+            if verbose:
+                print(f"Epoch {epoch + 1}/{epochs} - " + " - ".join(f"{k}: {v:.4f}" for k, v in logs.items()))
+            if self.stop_training:
+                break
+        for cb in callbacks:
+            if hasattr(cb, "on_train_end"):
+                cb.on_train_end(logs)
+        return hist
+
+    def evaluate(self, x=None, y=None, batch_size=None, verbose=1, **kwargs):
+        """Mean loss over x (same input forms as fit), no parameter update."""
+        is_seq = hasattr(x, "__getitem__") and hasattr(x, "__len__") and not isinstance(x, (list, tuple, np.ndarray)) and not hasattr(x, "shape")
+        if is_seq:
+            vals = [float(self.test_on_batch(x[b]).item()) for b in range(len(x))]
+            return float(np.mean(vals)) if vals else float("nan")
+        return float(self.test_on_batch(x).item())
+
+    # ---- weights -----------------------------------------------------------------------------------------------
+    def get_weights(self):
+        E, R = self._engine_().get_tables()
+        return [E, R]
+
+    def set_weights(self, weights):
+        E, R = weights
+        self._engine_().set_tables(E, R)
+
+
+class DistMult(EmbeddingModel):
+    _score_kind = abi.DISTMULT
+
+    def __init__(self, name='DistMult', **kwargs):
+        """DistMult (models.py:164-172): sum(s*p*o)."""
+        super(DistMult, self).__init__(name=name, **kwargs)
+
+
+class TransE(EmbeddingModel):
+    def __init__(self, name='TransE', norm=1, gamma=12, **kwargs):
+        """TransE (models.py:175-190): gamma - ||s+p-o||_norm (bare norm if gamma <= 0)."""
+        super(TransE, self).__init__(name=name, **kwargs)
+        self.gamma = gamma
+        self.norm = norm
+
+    def _kind_(self):
+        if self.norm == 1:
+            return abi.TRANSE_L1
+        if self.norm == 2:
+            return abi.TRANSE_L2
+        raise NotImplementedError(f"TransE norm={self.norm!r}: the kernels serve ord 1 and 2")
+
+
+class ComplEx(EmbeddingModel):
+    _score_kind = abi.COMPLEX
+
+    def __init__(self, name='ComplEx', **kwargs):
+        """ComplEx (models.py:203-222): rows are [re | im]; like the reference, e_dim / r_dim must be passed by keyword
+        and are doubled."""
+        kwargs['e_dim'] = 2 * kwargs['e_dim']
+        kwargs['r_dim'] = 2 * kwargs['r_dim']
+        super(ComplEx, self).__init__(name=name, **kwargs)
+
+
+class HolE(EmbeddingModel):
+    _score_kind = abi.HOLE
+
+    def __init__(self, name='HolE', **kwargs):
+        """HolE (models.py:224-237): sum_k p_k (s (*) o)_k, circular correlation."""
+        super(HolE, self).__init__(name=name, **kwargs)
+
+
+# ---- sibling classes: constructors kept (same keywords, same width multipliers), score kernels are SURVEY 8f "next" ----
+class CosinE(EmbeddingModel):
+    def __init__(self, name='CosinE', **kwargs):
+        super(CosinE, self).__init__(name=name, **kwargs)
+
+    def func(self, s, p, o, training=False):
+        # the reference calls an undefined name here (models.py:200); the defect is kept, not papered over
+        raise NameError("name 'cosine_similarity' is not defined")
+
+
+class ModE(EmbeddingModel):
+    def __init__(self, gamma=12, norm=2, name='ModE', **kwargs):
+        kwargs['e_dim'] = 2 * kwargs['e_dim']
+        kwargs['r_dim'] = 3 * kwargs['r_dim']
+        super(ModE, self).__init__(name=name, **kwargs)
+        self.norm = norm
+        self.gamma = gamma  # the reference reads self.gamma without assigning it (models.py:415); fixed here
+
+
+class HAKE(EmbeddingModel):
+    def __init__(self, epsilon=2, gamma=12, phase_weight=0.5, mod_weight=1, name='HAKE', **kwargs):
+        kwargs['e_dim'] = 2 * kwargs['e_dim']
+        kwargs['r_dim'] = 3 * kwargs['r_dim']
+        super(HAKE, self).__init__(name=name, **kwargs)
+        self.gamma, self.epsilon, self.phase_weight, self.mod_weight = gamma, epsilon, phase_weight, mod_weight
+        self.pi = np.pi
+        self.embedding_range = (self.gamma + self.epsilon) / self.e_dim / 2
+
+
+class RotatE(EmbeddingModel):
+    def __init__(self, gamma=12, norm=2, epsilon=2, name='RotatE', **kwargs):
+        kwargs['e_dim'] = 2 * kwargs['e_dim']
+        kwargs['r_dim'] = kwargs['r_dim']
+        super(RotatE, self).__init__(name=name, **kwargs)
+        self.gamma, self.epsilon, self.norm = gamma, epsilon, norm
+        self.pi = np.pi
+        self.embedding_range = (self.gamma + self.epsilon) / self.e_dim / 2
+
+
+class pRotatE(EmbeddingModel):
+    def __init__(self, gamma=12, epsilon=2, modulus=0.5, name='pRotatE', **kwargs):
+        kwargs['e_dim'] = 2 * kwargs['e_dim']
+        kwargs['r_dim'] = 2 * kwargs['r_dim']
+        super(pRotatE, self).__init__(name=name, **kwargs)
+        self.gamma, self.epsilon = gamma, epsilon
+        self.pi = np.pi
+        self.embedding_range = (self.gamma + self.epsilon) / self.e_dim / 2
+        self.modulus = modulus * self.embedding_range
+
+
+class _ConvOutOfScope(EmbeddingModel):
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError(f"{type(self).__name__} is a dense conv net (models.py:239-360), outside the "
+                                  f"gather/score/scatter hot path this build accelerates (SURVEY 2 #4)")
+
+
+class ConvE(_ConvOutOfScope):
+    pass
+
+
+class ConvR(_ConvOutOfScope):
+    pass
+
+
+class ConvKB(_ConvOutOfScope):
+    pass

@@ -80,18 +80,23 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 }
 
 // One corrupted triple: g = i*K + j is the global negative index.  Mirrors oracle.kge_oracle.philox_negatives.
+// head_side reports which slot was replaced in the one-sided modes (true = head).
 __device__ __forceinline__ void philox_corrupt(int s, int o, uint64_t g, uint64_t seed, uint64_t offset, uint32_t N,
-                                               int mode, int& ns, int& no) {
+                                               int mode, int& ns, int& no, bool& head_side) {
   const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)),
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   const int nh = (int)(((unsigned long long)r.x * N) >> 32);
   const int nt = (int)(((unsigned long long)r.y * N) >> 32);
-  const bool head_side = (r.z >> 31) != 0;
+  head_side = mode == KGEB_CORRUPT_HEAD || (mode == KGEB_CORRUPT_EITHER && (r.z >> 31) != 0);
   ns = s; no = o;
   if (mode == KGEB_CORRUPT_BOTH) { ns = nh; no = nt; }
-  else if (mode == KGEB_CORRUPT_HEAD) ns = nh;
-  else if (mode == KGEB_CORRUPT_TAIL) no = nt;
-  else { if (head_side) ns = nh; else no = nt; }
+  else if (head_side) ns = nh;
+  else no = nt;
+}
+__device__ __forceinline__ void philox_corrupt(int s, int o, uint64_t g, uint64_t seed, uint64_t offset, uint32_t N,
+                                               int mode, int& ns, int& no) {
+  bool hs;
+  philox_corrupt(s, o, g, seed, offset, N, mode, ns, no, hs);
 }
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }

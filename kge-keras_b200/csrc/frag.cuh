@@ -1,0 +1,219 @@
+// frag.cuh -- register row fragments and the score / gradient arithmetic shared by the scoring and training kernels.
+#pragma once
+#include "common.cuh"
+#include <stdlib.h>
+
+namespace {
+
+constexpr int DISTMULT = KGEB_DISTMULT, TRANSE_L1 = KGEB_TRANSE_L1, TRANSE_L2 = KGEB_TRANSE_L2, COMPLEX = KGEB_COMPLEX;
+
+// Row fragment: NC chunks per lane (ComplEx: NC chunks of the real half followed by NC of the imaginary half).
+template <int KIND, int NC>
+struct Frag {
+  static constexpr int NT = (KIND == COMPLEX) ? 2 * NC : NC;
+  float4 v[NT];
+};
+
+struct RowGeom {
+  int nch;   // 128-bit chunks per (half-)row handled by the lane loop: width/4, or (width/2)/4 for ComplEx
+  int half4; // ComplEx: offset of the imaginary half in float4 units; otherwise 0
+};
+
+template <int KIND, int NC>
+__device__ __forceinline__ void load_frag(Frag<KIND, NC>& f, const float* __restrict__ table, int64_t row, int ld,
+                                          RowGeom g, int lane) {
+  const float4* r4 = reinterpret_cast<const float4*>(table + row * (int64_t)ld);
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int c = lane + 32 * i;
+    const bool ok = c < g.nch;
+    f.v[i] = ok ? ldg4(r4 + c) : f4zero();
+    if (KIND == COMPLEX) f.v[NC + i] = ok ? ldg4(r4 + g.half4 + c) : f4zero();
+  }
+}
+
+template <int KIND, int NC>
+__device__ __forceinline__ void zero_frag(Frag<KIND, NC>& f) {
+#pragma unroll
+  for (int i = 0; i < Frag<KIND, NC>::NT; ++i) f.v[i] = f4zero();
+}
+template <int KIND, int NC>
+__device__ __forceinline__ void add_frag(Frag<KIND, NC>& a, const Frag<KIND, NC>& b) {
+#pragma unroll
+  for (int i = 0; i < Frag<KIND, NC>::NT; ++i) {
+    a.v[i].x += b.v[i].x; a.v[i].y += b.v[i].y; a.v[i].z += b.v[i].z; a.v[i].w += b.v[i].w;
+  }
+}
+
+template <int KIND, int NC>
+__device__ __forceinline__ void red_frag(float* __restrict__ table, int64_t row, int ld, RowGeom g, int lane,
+                                         const Frag<KIND, NC>& f) {
+  float* r = table + row * (int64_t)ld;
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int c = lane + 32 * i;
+    if (c < g.nch) {
+      red_add4(r + 4 * c, f.v[i]);
+      if (KIND == COMPLEX) red_add4(r + 4 * (g.half4 + c), f.v[NC + i]);
+    }
+  }
+}
+
+#define KGEB_FOR4(...)                    \
+  {                                       \
+    { constexpr int _e = 0; __VA_ARGS__ } \
+    { constexpr int _e = 1; __VA_ARGS__ } \
+    { constexpr int _e = 2; __VA_ARGS__ } \
+    { constexpr int _e = 3; __VA_ARGS__ } \
+  }
+__device__ __forceinline__ float& comp(float4& v, int e) { return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w)); }
+__device__ __forceinline__ float comp(const float4& v, int e) { return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w)); }
+
+// lane-partial of the score sum; products are rounded like the reference's elementwise ops (no FMA contraction
+// of s*p*o), the accumulation order is lane-strided + butterfly.
+template <int KIND, int NC>
+__device__ __forceinline__ float score_partial(const Frag<KIND, NC>& s, const Frag<KIND, NC>& p, const Frag<KIND, NC>& o) {
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    KGEB_FOR4({
+      if (KIND == DISTMULT) {
+        acc += __fmul_rn(__fmul_rn(comp(s.v[i], _e), comp(p.v[i], _e)), comp(o.v[i], _e));
+      } else if (KIND == TRANSE_L1) {
+        acc += fabsf(__fsub_rn(__fadd_rn(comp(s.v[i], _e), comp(p.v[i], _e)), comp(o.v[i], _e)));
+      } else if (KIND == TRANSE_L2) {
+        const float r = __fsub_rn(__fadd_rn(comp(s.v[i], _e), comp(p.v[i], _e)), comp(o.v[i], _e));
+        acc += __fmul_rn(r, r);
+      } else {
+        const float sr = comp(s.v[i], _e), si = comp(s.v[NC + i], _e);
+        const float pr = comp(p.v[i], _e), pi = comp(p.v[NC + i], _e);
+        const float orr = comp(o.v[i], _e), oi = comp(o.v[NC + i], _e);
+        const float s1 = __fmul_rn(__fmul_rn(sr, pr), orr);
+        const float s2 = __fmul_rn(__fmul_rn(pr, si), oi);
+        const float s3 = __fmul_rn(__fmul_rn(pi, sr), oi);
+        const float s4 = __fmul_rn(__fmul_rn(pi, si), orr);
+        acc += __fsub_rn(__fadd_rn(__fadd_rn(s1, s2), s3), s4);
+      }
+    })
+  }
+  return acc;
+}
+
+template <int KIND>
+__device__ __forceinline__ float score_finish(float sum, float gamma) {
+  if (KIND == TRANSE_L1) return gamma > 0.f ? gamma - sum : sum;
+  if (KIND == TRANSE_L2) { const float n = sqrtf(sum); return gamma > 0.f ? gamma - n : n; }
+  return sum;
+}
+
+// gradient fragments of coef * score wrt the three rows.  `sum` is the un-finished score sum (needed by L2).
+template <int KIND, int NC>
+__device__ __forceinline__ void score_grads(const Frag<KIND, NC>& s, const Frag<KIND, NC>& p, const Frag<KIND, NC>& o,
+                                            float coef, float sum, float gamma, Frag<KIND, NC>& gs, Frag<KIND, NC>& gp,
+                                            Frag<KIND, NC>& go) {
+  float k = coef;
+  if (KIND == TRANSE_L1 || KIND == TRANSE_L2) {
+    k = gamma > 0.f ? -coef : coef;
+    if (KIND == TRANSE_L2) { const float n = sqrtf(sum); k = n > 0.f ? k / n : 0.f; }  // TF gives NaN at r == 0; we give 0
+  }
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    KGEB_FOR4({
+      if (KIND == DISTMULT) {
+        const float a = comp(s.v[i], _e), b = comp(p.v[i], _e), c = comp(o.v[i], _e);
+        comp(gs.v[i], _e) = k * (b * c);
+        comp(gp.v[i], _e) = k * (a * c);
+        comp(go.v[i], _e) = k * (a * b);
+      } else if (KIND == TRANSE_L1 || KIND == TRANSE_L2) {
+        const float r = __fsub_rn(__fadd_rn(comp(s.v[i], _e), comp(p.v[i], _e)), comp(o.v[i], _e));
+        const float g = (KIND == TRANSE_L1) ? (r > 0.f ? k : (r < 0.f ? -k : 0.f)) : k * r;
+        comp(gs.v[i], _e) = g;
+        comp(gp.v[i], _e) = g;
+        comp(go.v[i], _e) = -g;
+      } else {
+        const float sr = comp(s.v[i], _e), si = comp(s.v[NC + i], _e);
+        const float pr = comp(p.v[i], _e), pi = comp(p.v[NC + i], _e);
+        const float orr = comp(o.v[i], _e), oi = comp(o.v[NC + i], _e);
+        comp(gs.v[i], _e) = k * (pr * orr + pi * oi);
+        comp(gs.v[NC + i], _e) = k * (pr * oi - pi * orr);
+        comp(gp.v[i], _e) = k * (sr * orr + si * oi);
+        comp(gp.v[NC + i], _e) = k * (sr * oi - si * orr);
+        comp(go.v[i], _e) = k * (sr * pr - pi * si);
+        comp(go.v[NC + i], _e) = k * (pr * si + pi * sr);
+      }
+    })
+  }
+}
+
+struct ScoreArgs {
+  const float* E; const float* R; int ldE, ldR; RowGeom ge, gr; float gamma;
+};
+
+struct TrainArgs {
+  ScoreArgs sc;
+  const int32_t* pos; int64_t B; const int32_t* neg; int K;
+  int loss_kind; float margin; float loss_weight; int corrupt_mode; uint64_t seed, offset; uint32_t N;
+  float* loss; float* pos_scores; float* neg_scores; int32_t* neg_out;
+  float* gE; float* gR; uint8_t* tE; uint8_t* tR;
+  double* partials; unsigned int* ticket;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// host-side dispatch
+// ---------------------------------------------------------------------------------------------------
+int check_tables(kgeb_ctx* ctx, const void* E, const void* R) {
+  KGEB_REQUIRE(ctx, E && R, KGEB_ERR_INVALID, "null table pointer");
+  if (ctx->kind == KGEB_HOLE) return KGEB_OK;
+  KGEB_REQUIRE(ctx, kgeb_aligned16(E) && kgeb_aligned16(R), KGEB_ERR_ALIGNMENT, "table pointers must be 16-byte aligned");
+  KGEB_REQUIRE(ctx, ctx->ldE % 4 == 0 && ctx->ldR % 4 == 0, KGEB_ERR_ALIGNMENT, "row strides must be multiples of 4 floats");
+  KGEB_REQUIRE(ctx, ctx->we == ctx->wr, KGEB_ERR_UNSUPPORTED, "entity and relation widths must match for this score kind");
+  if (ctx->kind == KGEB_COMPLEX) {
+    KGEB_REQUIRE(ctx, ctx->we % 8 == 0, KGEB_ERR_ALIGNMENT, "ComplEx needs dim % 4 == 0 (stored width % 8 == 0)");
+  } else {
+    KGEB_REQUIRE(ctx, ctx->we % 4 == 0, KGEB_ERR_ALIGNMENT, "row width must be a multiple of 4 floats");
+  }
+  return KGEB_OK;
+}
+
+ScoreArgs make_score_args(const kgeb_ctx* ctx, const float* E, const float* R, int* nc_out) {
+  ScoreArgs a;
+  a.E = E; a.R = R; a.ldE = ctx->ldE; a.ldR = ctx->ldR; a.gamma = ctx->gamma;
+  if (ctx->kind == KGEB_COMPLEX) {
+    a.ge.nch = ctx->we / 8; a.ge.half4 = ctx->we / 8;
+  } else {
+    a.ge.nch = ctx->we / 4; a.ge.half4 = 0;
+  }
+  a.gr = a.ge;
+  *nc_out = (a.ge.nch + 31) / 32;
+  return a;
+}
+
+int grid_for(const kgeb_ctx* ctx, int64_t warps_needed, int blocks_per_sm) {
+  int64_t blocks = (warps_needed + KGEB_WARPS_PER_BLOCK - 1) / KGEB_WARPS_PER_BLOCK;
+  const int64_t cap = (int64_t)ctx->num_sms * blocks_per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// NC (chunks per lane) is a compile-time constant so rows live in registers: widths up to 512 floats
+// (ComplEx: dim up to 256) are covered; wider rows are reported, never silently slow-pathed.
+#define KGEB_DISPATCH_NC(NCV, ...)                                        \
+  switch (NCV) {                                                          \
+    case 1: { constexpr int NC = 1; __VA_ARGS__; } break;                 \
+    case 2: { constexpr int NC = 2; __VA_ARGS__; } break;                 \
+    case 3: { constexpr int NC = 3; __VA_ARGS__; } break;                 \
+    case 4: { constexpr int NC = 4; __VA_ARGS__; } break;                 \
+    default: return kgeb_fail(ctx, KGEB_ERR_UNSUPPORTED, "row too wide for the register-resident kernels (max 512 floats; ComplEx dim 256)"); \
+  }
+#define KGEB_DISPATCH_KIND(KINDV, ...)                                                   \
+  switch (KINDV) {                                                                       \
+    case KGEB_DISTMULT: { constexpr int KIND = KGEB_DISTMULT; __VA_ARGS__; } break;      \
+    case KGEB_TRANSE_L1: { constexpr int KIND = KGEB_TRANSE_L1; __VA_ARGS__; } break;    \
+    case KGEB_TRANSE_L2: { constexpr int KIND = KGEB_TRANSE_L2; __VA_ARGS__; } break;    \
+    case KGEB_COMPLEX: { constexpr int KIND = KGEB_COMPLEX; __VA_ARGS__; } break;        \
+    default: return kgeb_fail(ctx, KGEB_ERR_INVALID, "unknown score kind");          \
+  }
+
+
+}  // namespace

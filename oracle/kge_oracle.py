@@ -168,7 +168,8 @@ def score_grads(kind, s, p, o, gamma=12.0):
 # --------------------------------------------------------------------------------------------
 def _c(dt):
     # EPSILON+1 is a Python float added to an fp32 tensor -> fp32(1.000001) = 1.00000095367431640625
-    return dt.type(EPSILON + 1)
+    # (the fp64 "truth" uses the same fp32-rounded constant: it is the reference's constant, not an error to judge)
+    return dt.type(np.float32(EPSILON + 1))
 
 
 def pointwize_hinge(true, false, margin=1, negative_samples=1, reduce_mean=True):

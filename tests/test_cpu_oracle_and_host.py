@@ -1,0 +1,288 @@
+"""CPU suite (-m "not gpu"): the oracle against the golden vectors made from the reference's own code, the host-side
+mirror's data-preparation logic, the C-ABI library's symbols, and the world_size-2 (gloo) shard/merge logic.
+No CUDA compute is called here."""
+import ctypes
+import json
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+from oracle import kge_oracle as ko
+from oracle import ref_ast
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+GOLD = os.path.join(ROOT, "tests", "golden")
+KINDS = {"DistMult": ko.DISTMULT, "TransE_L1": ko.TRANSE_L1, "TransE_L2": ko.TRANSE_L2, "ComplEx": ko.COMPLEX, "HolE": ko.HOLE}
+
+
+def load_dataset(name):
+    d = np.load(os.path.join(GOLD, "datasets", name + ".npz"))
+    return dict(N=int(d["num_entities"]), R=int(d["num_relations"]), train=d["train"], valid=d["valid"], test=d["test"])
+
+
+def golden_tables(kind, N, R, d, seed, dyadic):
+    rng = np.random.default_rng(seed)
+    W = 2 * d if kind == ko.COMPLEX else d
+    if dyadic:
+        return ko.dyadic_table(rng, N, W), ko.dyadic_table(rng, R, W)
+    return ko.glorot_uniform(rng, N, W), ko.glorot_uniform(rng, R, W)
+
+
+# ---- Philox ---------------------------------------------------------------------------------------------------
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    kat = [([0, 0, 0, 0], [0, 0], "6627e8d5 e169c58d bc57ac4c 9b00dbd8"),
+           ([0xffffffff] * 4, [0xffffffff] * 2, "408f276d 41c83b0e a20bc7c6 6d5451fd"),
+           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0], "d16cfe09 94fdcceb 5001e420 24126ea1")]
+    for c, k, want in kat:
+        r = ko.philox4x32_10(np.array([c], dtype=np.uint32), np.array([k], dtype=np.uint32))[0]
+        assert " ".join("%08x" % x for x in r) == want
+
+
+def test_philox_negatives_properties():
+    pos = np.stack([np.arange(50), np.arange(50) % 7, np.arange(50)[::-1]], 1)
+    for mode in range(4):
+        neg = ko.philox_negatives(pos, 1000, 6, 42, 3, mode)
+        assert neg.shape == (300, 3) and neg.min() >= 0 and neg[:, [0, 2]].max() < 1000
+        np.testing.assert_array_equal(neg[:, 1], np.repeat(pos[:, 1], 6))
+        rep = np.repeat(pos, 6, axis=0)
+        if mode == ko.CORRUPT_HEAD:
+            np.testing.assert_array_equal(neg[:, 2], rep[:, 2])
+        if mode == ko.CORRUPT_TAIL:
+            np.testing.assert_array_equal(neg[:, 0], rep[:, 0])
+        if mode == ko.CORRUPT_EITHER:
+            assert np.all((neg[:, 0] == rep[:, 0]) | (neg[:, 2] == rep[:, 2]))
+    assert not np.array_equal(ko.philox_negatives(pos, 1000, 6, 42, 3, 0), ko.philox_negatives(pos, 1000, 6, 42, 4, 0))
+
+
+# ---- oracle vs golden fixtures made by the reference's own code --------------------------------------------------
+def test_oracle_negatives_match_reference_golden():
+    g = np.load(os.path.join(GOLD, "negatives_ref.npz"))
+    for ci in range(4):
+        B, N, K, seed = (int(x) for x in g[f"c{ci}_params"])
+        kg = g[f"c{ci}_kg"]
+        np.random.seed(seed)
+        random.seed(seed)
+        neg = ko.generate_negative(kg, N, K)
+        X = ko.oversample_data([kg, neg])
+        np.testing.assert_array_equal(neg, g[f"c{ci}_neg"])
+        np.testing.assert_array_equal(X[0], g[f"c{ci}_pos_over"])
+        np.testing.assert_array_equal(X[1], g[f"c{ci}_neg_over"])
+
+
+def test_host_mirror_negatives_match_reference_golden():
+    """KGEkeras.utils (the shipped host code) consumes np.random / random exactly like the reference."""
+    from KGEkeras import utils as ku
+    g = np.load(os.path.join(GOLD, "negatives_ref.npz"))
+    for ci in range(4):
+        B, N, K, seed = (int(x) for x in g[f"c{ci}_params"])
+        kg = g[f"c{ci}_kg"]
+        np.random.seed(seed)
+        random.seed(seed)
+        neg = ku.generate_negative(kg, N=N, negative=K)
+        X = ku.oversample_data(kgs=[kg, neg])
+        assert neg.shape == (K * B, 3, 1)
+        np.testing.assert_array_equal(neg, g[f"c{ci}_neg"])
+        np.testing.assert_array_equal(X[0], g[f"c{ci}_pos_over"])
+        np.testing.assert_array_equal(X[1], g[f"c{ci}_neg_over"])
+    with pytest.raises(AssertionError):
+        ku.generate_negative(kg, N, corrupt_head=False, corrupt_tail=False)
+
+
+with open(os.path.join(GOLD, "validate_ref.json")) as _fh:
+    VALIDATE_META = json.load(_fh)
+
+
+@pytest.mark.parametrize("key", [k for k in VALIDATE_META if k.split("/")[0] in ("kinship", "nations", "UMLS") and k.split("/")[1] in ("DistMult", "TransE_L1", "ComplEx")])
+def test_oracle_validate_matches_reference_golden(key):
+    meta = VALIDATE_META[key]
+    arrs = np.load(os.path.join(GOLD, "validate_ref.npz"))
+    ds = load_dataset(meta["dataset"])
+    kind = KINDS[meta["kind"]]
+    E, Rm = golden_tables(kind, ds["N"], ds["R"], meta["d"], meta["seed"], meta["dyadic"])
+    test = ds["test"][:meta["ntest"]]
+    filt = np.concatenate([ds["train"], ds["valid"]])
+    m, tr, hr = ko.validate(kind, E, Rm, test, filt, meta["gamma"], np.float32)
+    n = meta["n_ref_per_query"]
+    np.testing.assert_array_equal(tr[:n], arrs[key + "/ref_tail_ranks"])   # ranks produced by the reference's validate
+    np.testing.assert_array_equal(hr[:n], arrs[key + "/ref_head_ranks"])
+    np.testing.assert_array_equal(tr, arrs[key + "/tail_ranks"])
+    for k, v in meta["metrics"].items():                                   # the reference's own 15-key dict
+        assert abs(m[k] - v) <= 2e-6 * max(1.0, abs(v)), k
+
+
+@pytest.mark.skipif(not ref_ast.available(), reason="/root/reference not mounted (GPU box)")
+def test_live_reference_functions_agree_with_mirror():
+    from KGEkeras import utils as ku
+    ref = ref_ast.load()
+    ds = load_dataset("nations")
+    test = [tuple(int(x) for x in r) for r in ds["test"][:20]]
+    filt = [tuple(int(x) for x in r) for r in np.concatenate([ds["train"], ds["valid"]])]
+    fh, ft = ko.build_filters(filt)
+    for a, b in zip(ref["gen_tail_data"](test, ds["N"], 32, ft), ku.gen_tail_data(test, ds["N"], 32, ft)):
+        np.testing.assert_array_equal(a, b)
+    for a, b in zip(ref["gen_head_data"](test, ds["N"], 32, fh), ku.gen_head_data(test, ds["N"], 32, fh)):
+        np.testing.assert_array_equal(a, b)
+    with pytest.raises(ValueError):   # target inside its own filter set: both crash the same way
+        list(ref["gen_tail_data"](test[:1], ds["N"], 32, {(test[0][0], test[0][1]): {test[0][2]}}))
+    with pytest.raises(ValueError):
+        list(ku.gen_tail_data(test[:1], ds["N"], 32, {(test[0][0], test[0][1]): {test[0][2]}}))
+    sc = [("a", 0.5), ("b", 0.9), ("c", 0.5), ("d", 0.1)]
+    for t in "abcd":
+        assert ref["mrr"](t, sc) == ku.mrr(t, sc) and ref["hits"](t, sc, 2) == ku.hits(t, sc, 2)
+    path = "/root/reference/data/nations/valid.txt"
+    assert ref["load_kg"](path) == ku.load_kg(path)
+    random.seed(5)
+    a = ref["pad"]([(1, 2, 3), (4, 5, 6), (7, 8, 9)], 4)
+    random.seed(5)
+    b = ku.pad([(1, 2, 3), (4, 5, 6), (7, 8, 9)], 4)
+    np.testing.assert_array_equal(a, b)
+
+
+def test_score_kat_frozen():
+    g = np.load(os.path.join(GOLD, "score_kat.npz"))
+    for kname, kind in KINDS.items():
+        E, Rm, pos, neg = g[f"{kname}/E"], g[f"{kname}/R"], g[f"{kname}/pos"], g[f"{kname}/neg"]
+        np.testing.assert_allclose(ko.score_triples(kind, E, Rm, pos, 12.0, np.float64, hole_fft=False), g[f"{kname}/score64"], rtol=1e-13)
+        np.testing.assert_allclose(ko.score_triples(kind, E, Rm, pos, 12.0, np.float32), g[f"{kname}/score32"], rtol=2e-6, atol=1e-6)
+        # fp32 op-by-op restatement vs fp64 truth: 1e-5 of the magnitude that enters the sum
+        bound = 1e-5 * ko.score_abs_terms(kind, E, Rm, pos, 12.0)
+        assert np.all(np.abs(g[f"{kname}/score32"].astype(np.float64) - g[f"{kname}/score64"]) <= bound)
+        st = ko.train_step(kind, ko.PAIRWISE_HINGE, ko.PAIRED, E, Rm, pos, neg, 3, 1.0, 12.0, ko.OPT_LAZY_ADAM,
+                           [np.zeros_like(E), np.zeros_like(E)], [np.zeros_like(Rm), np.zeros_like(Rm)], 1e-3, 1)
+        np.testing.assert_allclose(st["loss"], g[f"{kname}/pairwize_hinge/0/loss"], rtol=1e-12)
+        np.testing.assert_allclose(st["gE"], g[f"{kname}/pairwize_hinge/0/gE"], rtol=1e-10, atol=1e-14)
+
+
+# ---- oracle internal consistency: analytic gradients vs torch autograd ------------------------------------------
+@pytest.mark.parametrize("kname", list(KINDS))
+def test_score_grads_match_autograd(kname):
+    import torch
+    kind = KINDS[kname]
+    rng = np.random.default_rng(3)
+    d = 6
+    W = 2 * d if kind == ko.COMPLEX else d
+    s, p, o = (rng.normal(size=(5, W)) for _ in range(3))
+    ts, tp, to = (torch.tensor(x, dtype=torch.float64, requires_grad=True) for x in (s, p, o))
+    if kind == ko.DISTMULT:
+        f = (ts * tp * to).sum(-1)
+    elif kind == ko.TRANSE_L1:
+        f = 12.0 - (ts + tp - to).abs().sum(-1)
+    elif kind == ko.TRANSE_L2:
+        f = 12.0 - (ts + tp - to).pow(2).sum(-1).sqrt()
+    elif kind == ko.COMPLEX:
+        sr, si, pr, pi, orr, oi = ts[:, :d], ts[:, d:], tp[:, :d], tp[:, d:], to[:, :d], to[:, d:]
+        f = (sr * pr * orr + pr * si * oi + pi * sr * oi - pi * si * orr).sum(-1)
+    else:
+        x = torch.fft.ifft(torch.conj(torch.fft.fft(ts)) * torch.fft.fft(to)).real
+        f = (tp * x).sum(-1)
+    np.testing.assert_allclose(f.detach().numpy(), ko.score(kind, s, p, o, 12.0, hole_fft=False), rtol=1e-10, atol=1e-12)
+    w = torch.tensor(rng.normal(size=5))
+    (f * w).sum().backward()
+    ds, dp, do = ko.score_grads(kind, s, p, o, 12.0)
+    for got, want in ((ds, ts.grad), (dp, tp.grad), (do, to.grad)):
+        np.testing.assert_allclose(got * w.numpy()[:, None], want.numpy(), rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("lname", list(ko.LOSS_NAMES))
+@pytest.mark.parametrize("pm", [ko.PAIRED, ko.ALLPAIRS])
+def test_loss_coefs_match_autograd(lname, pm):
+    import torch
+    lk = ko.LOSS_NAMES[lname]
+    rng = np.random.default_rng(lk + 10 * pm)
+    B, K = 7, 3
+    t, f = rng.normal(size=B), rng.normal(size=B * K)
+    tt, tf_ = torch.tensor(t, requires_grad=True), torch.tensor(f, requires_grad=True)
+    c = torch.tensor(np.float64(np.float32(1 + 1e-6)))
+    M = 1.0
+    if lk == ko.POINTWISE_HINGE:
+        L = torch.relu(M - tt).mean() + torch.relu(M + tf_).mean()
+    elif lk == ko.POINTWISE_LOGISTIC:
+        L = torch.log(c + torch.exp(-tt)).mean() + torch.log(c + torch.exp(tf_)).mean()
+    elif lk == ko.POINTWISE_SQUARE:
+        L = ((M - tt) ** 2).mean() + ((M + tf_) ** 2).mean()
+    else:
+        X = (tf_.reshape(B, K) - tt.reshape(B, 1)) if pm == ko.PAIRED else (tf_.reshape(-1, 1) - tt.reshape(1, -1))
+        L = {ko.PAIRWISE_HINGE: lambda: torch.relu(M + X).mean(), ko.PAIRWISE_LOGISTIC: lambda: torch.log(c + torch.exp(X)).mean(),
+             ko.PAIRWISE_SQUARE: lambda: (-(X ** 2)).mean()}[lk]()
+    L.backward()
+    Lo, dt, df = ko.loss_and_coefs(lk, pm, t, f, K, M)
+    np.testing.assert_allclose(Lo, L.item(), rtol=1e-12)
+    np.testing.assert_allclose(dt, tt.grad.numpy(), rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(df, tf_.grad.numpy(), rtol=1e-10, atol=1e-14)
+    # and the reference-named function (restated) agrees on the value
+    ref = ko.loss_function_lookup(lname)
+    Lr = ref(t.reshape(-1, 1) if (pm == ko.PAIRED and lk >= ko.PAIRWISE_HINGE) else t, f, M, K if pm == ko.PAIRED else 1)
+    np.testing.assert_allclose(Lr, Lo, rtol=1e-12)
+
+
+def test_rank_identities_property():
+    """rank = 1 + #greater (optimistic ties) == the reference's rankdata('max') formula, and sequential-k fp32 scores
+    rank like the fp64 truth away from ties."""
+    from scipy.stats import rankdata
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        n = int(rng.integers(2, 40))
+        sc = rng.integers(0, 6, n).astype(np.float32)  # many ties
+        tgt = int(rng.integers(0, n))
+        res = np.concatenate([[sc[tgt]], np.delete(sc, tgt)])
+        r = rankdata(res, 'max')
+        assert len(res) - r[0] + 1 == 1 + np.count_nonzero(np.delete(sc, tgt) > sc[tgt])
+
+
+# ---- host mirror: error behaviour and CSR build -------------------------------------------------------------------
+def test_mirror_error_behaviour_and_csr():
+    from KGEkeras import utils as ku
+    from KGEkeras import models as km
+    with pytest.raises(KeyError):
+        ku.loss_function_lookup("hinge")
+    with pytest.raises(TypeError):
+        ku.validate(object(), [(0, 0, 1)], 5, 32)                 # filtering_triples=None, as the reference
+    with pytest.raises(TypeError):
+        ku.validate(object(), [(0, 0, 1)], 5, 32, [(0, 0, 2)])    # not a libkgeb200-backed model: no CPU path
+    test = np.array([[0, 0, 1], [2, 1, 3]])
+    filt = [(0, 0, 4), (0, 0, 2), (0, 0, 2), (9, 1, 3), (5, 1, 3)]
+    offs, ids = ku.build_filter_csr(test, filt, "tail")
+    assert offs.tolist() == [0, 2, 2] and ids.tolist() == [2, 4]
+    offs, ids = ku.build_filter_csr(test, filt, "head")
+    assert offs.tolist() == [0, 0, 2] and ids.tolist() == [5, 9]
+    o2, i2 = ko.filter_csr(test, "head", ko.build_filters(filt)[0])
+    assert o2.tolist() == offs.tolist() and i2.tolist() == ids.tolist()
+    with pytest.raises(ValueError):
+        ku.build_filter_csr(test, filt + [(0, 0, 1)], "tail")     # test triple inside the filter: the reference crashes too
+    m = km.ComplEx(e_dim=8, r_dim=8, num_entities=10, num_relations=3, some_extra=7)
+    assert (m.e_dim, m.r_dim, m.some_extra, m.num_entities, m.margin, m.dp.rate) == (16, 16, 7, 10, 1, 0.2)
+    t = km.TransE(e_dim=8, r_dim=8, num_entities=10, num_relations=3, norm=2, gamma=5)
+    assert (t.gamma, t.norm) == (5, 2)
+    with pytest.raises(NameError):
+        km.CosinE(e_dim=4, r_dim=4, num_entities=3, num_relations=2).func(None, None, None)
+    with pytest.raises(NotImplementedError):
+        km.ConvE(e_dim=4, r_dim=4, num_entities=3, num_relations=2)
+    with pytest.raises(RuntimeError):                              # no GPU here -> loud failure, never a CPU path
+        import torch
+        if torch.cuda.is_available():
+            raise RuntimeError("gpu present")
+        m.predict(np.zeros((1, 3)))
+
+
+# ---- C ABI: the library loads and exports everything the header declares ---------------------------------------------
+def test_abi_library_exports_header_symbols():
+    from KGEkeras import _abi
+    with open(os.path.join(ROOT, "include", "kgeb200.h")) as fh:
+        declared = set(re.findall(r"KGEB_API[^;(]*?\b(kgeb_[a-z0-9_]+)\s*\(", fh.read()))
+    assert declared == set(_abi.PROTOTYPES), declared ^ set(_abi.PROTOTYPES)
+    if not os.path.isfile(_abi.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(_abi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _abi.lib().kgeb_version() == 100
+    import torch
+    if not torch.cuda.is_available():  # kgeb_create must fail cleanly (negative status + message), not crash
+        h = ctypes.c_void_p()
+        rc = _abi.lib().kgeb_create(ctypes.byref(h), 0, 10, 3, 8, 8, 8, 8, 0, 12.0)
+        assert rc < 0 and not h.value and b"CUDA" in _abi.lib().kgeb_last_error(None)

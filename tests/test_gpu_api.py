@@ -1,0 +1,213 @@
+"""GPU tests of the reference-facing API (KGEkeras.models / KGEkeras.utils mirror) against the oracle and the golden
+fixtures produced by the reference's own validate / generate_negative code."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kge_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+GOLD = os.path.join(ROOT, "tests", "golden")
+KINDS = {"DistMult": ko.DISTMULT, "TransE_L1": ko.TRANSE_L1, "TransE_L2": ko.TRANSE_L2, "ComplEx": ko.COMPLEX, "HolE": ko.HOLE}
+with open(os.path.join(GOLD, "validate_ref.json")) as _fh:
+    VALIDATE_META = json.load(_fh)
+
+
+def load_dataset(name):
+    d = np.load(os.path.join(GOLD, "datasets", name + ".npz"))
+    return dict(N=int(d["num_entities"]), R=int(d["num_relations"]), train=d["train"], valid=d["valid"], test=d["test"])
+
+
+def golden_tables(kind, N, R, d, seed, dyadic):
+    rng = np.random.default_rng(seed)
+    W = 2 * d if kind == ko.COMPLEX else d
+    if dyadic:
+        return ko.dyadic_table(rng, N, W), ko.dyadic_table(rng, R, W)
+    return ko.glorot_uniform(rng, N, W), ko.glorot_uniform(rng, R, W)
+
+
+def make_model(kname, N, R, d, E=None, Rm=None, **kw):
+    from KGEkeras import models as km
+    args = dict(e_dim=d, r_dim=d, num_entities=N, num_relations=R, init_entities=E, init_relations=Rm, dp=0.0, **kw)
+    if kname == "DistMult":
+        return km.DistMult(**args)
+    if kname == "TransE_L1":
+        return km.TransE(norm=1, gamma=12, **args)
+    if kname == "TransE_L2":
+        return km.TransE(norm=2, gamma=12, **args)
+    if kname == "ComplEx":
+        return km.ComplEx(**args)
+    return km.HolE(**args)
+
+
+@pytest.mark.parametrize("kname", list(KINDS))
+def test_model_call_predict_func(kname):
+    kind = KINDS[kname]
+    N, R, d = 60, 5, 8
+    E, Rm = golden_tables(kind, N, R, d, 1, False)
+    m = make_model(kname, N, R, d, E, Rm, some_unknown_kw=3)
+    assert m.some_unknown_kw == 3 and m.num_entities == N
+    rng = np.random.default_rng(0)
+    idx = np.stack([rng.integers(0, N, 40), rng.integers(0, R, 40), rng.integers(0, N, 40)], 1)
+    want = ko.score_triples(kind, E, Rm, idx, 12.0, np.float64, hole_fft=False)
+    bound = 1e-5 * ko.score_abs_terms(kind, E, Rm, idx, 12.0)
+    for got in (m(idx).cpu().numpy(), m.call(idx.astype(np.float32)).cpu().numpy(), m.predict(idx), m.predict(idx.reshape(-1, 3, 1)[..., 0])):
+        assert got.shape == (40,) and np.all(np.abs(got - want) <= bound)
+    s, p, o = ko.gather(E, Rm, idx)
+    assert np.all(np.abs(m.func(s, p, o).cpu().numpy() - want) <= bound)
+    w = m.get_weights()
+    np.testing.assert_array_equal(w[0], E)
+    np.testing.assert_array_equal(m.entity_embedding.get_weights()[0], E)
+    m.set_weights([E * 2, Rm])
+    np.testing.assert_array_equal(m.get_weights()[0], E * 2)
+
+
+@pytest.mark.parametrize("key", sorted(VALIDATE_META))
+def test_validate_matches_reference_golden(key):
+    """Filtered ranks / the 15-key metrics dict against what the reference's own validate produced (tests/golden)."""
+    from KGEkeras import utils as ku
+    meta = VALIDATE_META[key]
+    arrs = np.load(os.path.join(GOLD, "validate_ref.npz"))
+    ds = load_dataset(meta["dataset"])
+    kind = KINDS[meta["kind"]]
+    E, Rm = golden_tables(kind, ds["N"], ds["R"], meta["d"], meta["seed"], meta["dyadic"])
+    model = make_model(meta["kind"], ds["N"], ds["R"], meta["d"], E, Rm)
+    test = ds["test"][:meta["ntest"]]
+    filt = np.concatenate([ds["train"], ds["valid"]])
+    tr, hr = ku.filtered_ranks(model, test, filt)
+    metrics = ku.validate(model, [tuple(int(x) for x in r) for r in test], ds["N"], 32, filt)
+    assert list(metrics) == ['tail_hits@1', 'tail_hits@3', 'tail_hits@10', 'tail_mr', 'tail_mrr', 'head_hits@1', 'head_hits@3',
+                             'head_hits@10', 'head_mr', 'head_mrr', 'hits@1', 'hits@3', 'hits@10', 'mr', 'mrr']  # utils.py:247-262
+    assert set(metrics) == set(meta["metrics"])
+    if meta["dyadic"]:
+        # every score is exact in fp32 -> bit-exact ranks, ties included, against the reference's output
+        np.testing.assert_array_equal(tr, arrs[key + "/tail_ranks"])
+        np.testing.assert_array_equal(hr, arrs[key + "/head_ranks"])
+        n = meta["n_ref_per_query"]
+        np.testing.assert_array_equal(tr[:n], arrs[key + "/ref_tail_ranks"])
+        np.testing.assert_array_equal(hr[:n], arrs[key + "/ref_head_ranks"])
+        for k, v in meta["metrics_f64"].items():
+            assert abs(metrics[k] - v) <= 1e-12 * max(1.0, abs(v)), k
+    else:
+        # real-valued tables: bit-exact against the sequential-k fp32 emulation of the kernel's arithmetic ...
+        fh, ft = ko.build_filters([tuple(int(x) for x in r) for r in filt])
+        for side, got, f in (("tail", tr, ft), ("head", hr, fh)):
+            sc = ko.seqk_scores(kind, ko.query_vectors(kind, E, Rm, test, side), E, side, meta["gamma"])
+            np.testing.assert_array_equal(got, ko.ranks_from_scores(sc, test, side, f))
+        # ... and within near-tie noise of the reference's ranks (fp32, another summation order)
+        gt, gh = arrs[key + "/tail_ranks"], arrs[key + "/head_ranks"]
+        assert np.mean(tr != gt) <= 0.02 and np.mean(hr != gh) <= 0.02 and np.max(np.abs(tr - gt)) <= 2
+        for k, v in meta["metrics_f64"].items():
+            assert abs(metrics[k] - v) <= 2e-3 * max(1.0, abs(v)), k
+
+
+def test_validate_error_behaviour():
+    from KGEkeras import utils as ku
+    ds = load_dataset("nations")
+    m = make_model("DistMult", ds["N"], ds["R"], 4)
+    test = [tuple(int(x) for x in r) for r in ds["test"][:5]]
+    with pytest.raises(TypeError):
+        ku.validate(m, test, ds["N"], 32)
+    with pytest.raises(ValueError):  # filter contains the test triples themselves
+        ku.validate(m, test, ds["N"], 32, test)
+
+
+@pytest.mark.parametrize("lname", ["pointwize_hinge", "pointwize_logistic", "pointwize_square_loss", "pointwize_cross_entropy",
+                                   "pairwize_hinge", "pairwize_logistic", "pairwize_square_loss"])
+def test_loss_functions_like_reference(lname):
+    from KGEkeras import utils as ku
+    fn, ref = ku.loss_function_lookup(lname), ko.loss_function_lookup(lname)
+    rng = np.random.default_rng(4)
+    B, K = 50, 4
+    t = rng.normal(size=B).astype(np.float32)
+    f = rng.normal(size=B * K).astype(np.float32)
+    if lname == "pointwize_cross_entropy":
+        t, f = rng.random(B).astype(np.float32), rng.random(B * K).astype(np.float32)
+    pair = lname.startswith("pairwize")
+    # paired layout: true (B,1) against false (B*K,) with negative_samples = K
+    got = float(fn(t.reshape(-1, 1) if pair else t, f, 1.0, K))
+    want = float(ref((t.reshape(-1, 1) if pair else t).astype(np.float64), f.astype(np.float64), 1.0, K))
+    assert abs(got - want) <= 1e-5 * max(1.0, abs(want))
+    # harness layout (tests.py:81): negative_samples = 1 and equal lengths -> (m,m) broadcast
+    f1 = f[:B]
+    got = float(fn(t, f1, 1.0, 1))
+    want = float(ref(t.astype(np.float64), f1.astype(np.float64), 1.0, 1))
+    assert abs(got - want) <= 1e-5 * max(1.0, abs(want))
+    if pair:
+        mat = fn(t.reshape(-1, 1), f, 1.0, K, reduce_mean=False).cpu().numpy()
+        np.testing.assert_allclose(mat, ref(t.reshape(-1, 1), f, 1.0, K, reduce_mean=False), rtol=1e-5, atol=1e-6)
+        with pytest.raises(ValueError):  # (B,) true against (B,K) false does not broadcast, in TF/NumPy and here
+            fn(t, f, 1.0, K)
+
+
+class _Gen:
+    """The harness' DataGenerator (tests.py:29-61) re-typed without Keras: yields ([pos, neg], None)."""
+
+    def __init__(self, kg, num_e, ns=10, batch_size=32):
+        from KGEkeras import utils as ku
+        self.ku, self.kg, self.ns, self.bs, self.num_e = ku, np.asarray(kg), ns, min(batch_size, len(kg)), num_e
+        self.on_epoch_end()
+
+    def __len__(self):
+        return len(self.kg) // self.bs
+
+    def on_epoch_end(self):
+        self.index = np.random.permutation(len(self.kg))
+
+    def __getitem__(self, i):
+        tmp = self.kg[self.index[i * self.bs:(i + 1) * self.bs]]
+        neg = self.ku.generate_negative(tmp, N=self.num_e, negative=self.ns)
+        return self.ku.oversample_data(kgs=[tmp, neg]), None
+
+
+@pytest.mark.parametrize("kname,lname,pair_mode", [("DistMult", "pairwize_hinge", "allpairs"), ("TransE_L1", "pairwize_hinge", "paired"),
+                                                   ("ComplEx", "pointwize_logistic", "paired"), ("HolE", "pairwize_logistic", "paired")])
+def test_fit_learns_kinship(kname, lname, pair_mode):
+    """End to end through the mirror: fit() on bundled kinship drives the loss down and filtered MRR up."""
+    from KGEkeras import utils as ku
+    np.random.seed(0)
+    random.seed(0)
+    ds = load_dataset("kinship")
+    d = 16 if kname == "HolE" else 32
+    m = make_model(kname, ds["N"], ds["R"], d, loss_function=lname, negative_samples=8, margin=1, batch_size=512)
+    m.pair_mode = pair_mode
+    m.corrupt = "either"
+    m.compile(optimizer=type("Adam", (), {"learning_rate": 0.02})())
+    test = ds["test"][:200]
+    filt = np.concatenate([ds["train"], ds["valid"]])
+    before = ku.validate(m, test, ds["N"], 32, filt)
+    if pair_mode == "allpairs":   # the reference harness' own input form: a Sequence of ([pos, neg], None)
+        hist = m.fit(_Gen(ds["train"], ds["N"], ns=4, batch_size=512), epochs=6, verbose=0)
+    else:
+        cb = ku.KGEValidateCallback(test, train_data=filt)
+        hist = m.fit(ds["train"], epochs=12, batch_size=512, verbose=0, callbacks=[cb], validation_data=ds["valid"])
+        assert "val_loss" in hist.history
+    after = ku.validate(m, test, ds["N"], 32, filt)
+    assert hist.history["loss"][-1] < hist.history["loss"][0]
+    assert after["mrr"] > before["mrr"] * 1.5, (before["mrr"], after["mrr"])
+    assert isinstance(m.evaluate(ds["valid"], verbose=0), float)
+
+
+def test_sharded_validate_equals_single_gpu_emulated():
+    """Row shards of the replicated table counted one after the other sum to the unsharded ranks (what every NCCL rank does)."""
+    from KGEkeras import utils as ku, _abi as abi
+    ds = load_dataset("UMLS")
+    E, Rm = golden_tables(ko.COMPLEX, ds["N"], ds["R"], 8, 3, False)
+    m = make_model("ComplEx", ds["N"], ds["R"], 8, E, Rm)
+    test = ds["test"][:100]
+    filt = np.concatenate([ds["train"], ds["valid"]])
+    tr, hr = ku.filtered_ranks(m, test, filt)
+    eng = m._engine_()
+    for world in (2, 4, 8):
+        for side, code, want in (("tail", abi.SIDE_TAIL, tr), ("head", abi.SIDE_HEAD, hr)):
+            offs, ids = ku.build_filter_csr(test, filt, side)
+            acc = torch.zeros(len(test), dtype=torch.int32, device="cuda")
+            for r in range(world):
+                acc += eng.rank_counts(test, code, offs, ids, row_range=ku.shard_rows(ds["N"], world, r))
+            np.testing.assert_array_equal(acc.cpu().numpy() + 1, want)
