@@ -117,6 +117,10 @@ KGEB_API int kgeb_train_fwd_bwd(kgeb_ctx* ctx, const float* E, const float* R, c
                        int32_t* neg_out, float* gE, float* gR, uint8_t* touchedE, uint8_t* touchedR,
                        kgeb_stream stream);
 
+/* ---- l3_reg, models.py:10-11,79-82: loss[0] += w * sum |P|^3 ; G += 3 w P |P| on EVERY row (dense), all flags set ------ */
+KGEB_API int kgeb_l3_reg(kgeb_ctx* ctx, const float* P, int64_t rows, int width, int ld, float w, float* G,
+                         uint8_t* touched, float* loss, kgeb_stream stream);
+
 /* ---- sparse optimizer (K2 second half): applies the update to touched rows, zeroes G and the flags -------- */
 /* P, G: [rows, ld]; state0/state1: Adam m,v (or Adagrad accumulator in state0; unused -> NULL). step >= 1. */
 KGEB_API int kgeb_opt_update(kgeb_ctx* ctx, float* P, float* G, uint8_t* touched, int64_t rows, int width, int ld,

@@ -181,8 +181,15 @@ class Engine:
         self._check(self.lib.kgeb_opt_update(self.ctx, _ptr(self.Rel), _ptr(self.gR), _ptr(self.tR), self.R_, self.wr_k, self.wr_k,
                                              _ptr(m_r), _ptr(v_r), opt_kind, lr, beta1, beta2, eps, self.step, _stream()))
 
-    def train_step(self, pos, neg=None, opt_kind=abi.ADAM_DENSE, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7, **kw):
+    def l3_reg(self, w, loss):
+        """models.py:10-11,79-82: loss += w*sum|E|^3, gE += 3 w E|E| on every entity row (the relation table is not regularised)."""
+        self._check(self.lib.kgeb_l3_reg(self.ctx, _ptr(self.E), self.N, self.we_k, self.we_k, float(w), _ptr(self.gE), _ptr(self.tE),
+                                         _ptr(loss), _stream()))
+
+    def train_step(self, pos, neg=None, opt_kind=abi.ADAM_DENSE, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7, l3=0.0, **kw):
         res = self.forward_backward(pos, neg, opt_kind=opt_kind, **kw)
+        if l3:
+            self.l3_reg(l3, res["loss"])
         self.apply_optimizer(opt_kind, lr, beta1, beta2, eps)
         return res
 

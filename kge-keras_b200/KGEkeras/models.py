@@ -187,8 +187,6 @@ class EmbeddingModel:
         return abi.LOSS_KINDS[self.loss_function]
 
     def _step_kwargs(self):
-        if self.regularization != 0.0:
-            raise NotImplementedError("l3 regularisation (models.py:10-11) makes the gradient dense; not on the B200 path yet")
         if self.dp.rate > 0 and not getattr(self, "_warned_dp", False):
             warnings.warn(f"dropout dp={self.dp.rate} is not applied by the B200 kernels yet; training runs with dp=0")
             self._warned_dp = True
@@ -212,6 +210,7 @@ class EmbeddingModel:
         self._step_counter += 1
         res = self._engine_().train_step(pos, neg, opt_kind=o.kind, lr=o.lr, beta1=o.beta1, beta2=o.beta2, eps=o.eps,
                                          K=int(self.negative_samples), seed=self._seed, offset=self._step_counter,
+                                         l3=float(self.regularization),
                                          **self._step_kwargs())
         return res["loss"]
 

@@ -2,6 +2,7 @@
 // optimizer (K2 second half; Keras Adam/Adagrad/SGD semantics).
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -207,6 +208,51 @@ extern "C" int kgeb_loss_fwd_bwd(kgeb_ctx* ctx, const float* t, int64_t B, const
   k_loss_allpairs<<<grid, AP_TILE, 0, st>>>(t, B, f, Bf, loss_kind, margin, loss_weight, dt, df, loss_acc);
   KGEB_LAUNCH_OK(ctx);
   k_loss_allpairs_finish<<<1, 1, 0, st>>>(loss_acc, (double)loss_weight / ((double)B * (double)Bf), loss);
+  KGEB_LAUNCH_OK(ctx);
+  return KGEB_OK;
+}
+
+namespace {
+// l3_reg (models.py:10-11): w * ||P||_3^3 over the whole table; its gradient 3 w p |p| touches every row.
+__global__ void __launch_bounds__(KGEB_THREADS) k_l3_reg(const float* __restrict__ P, int64_t rows, int w4, int ld4, float w,
+                                                         float* G, uint8_t* touched, float* loss, double* partials,
+                                                         unsigned int* ticket) {
+  const float4* P4 = reinterpret_cast<const float4*>(P);
+  float4* G4 = reinterpret_cast<float4*>(G);
+  double acc = 0.0;
+  const int64_t total = rows * (int64_t)w4;
+  for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = x / w4;
+    const int c = (int)(x - r * w4);
+    const int64_t off = r * ld4 + c;
+    const float4 p = P4[off];
+    float4 g = G4[off];
+    const float a0 = fabsf(p.x), a1 = fabsf(p.y), a2 = fabsf(p.z), a3 = fabsf(p.w);
+    acc += (double)(a0 * a0 * a0) + (double)(a1 * a1 * a1) + (double)(a2 * a2 * a2) + (double)(a3 * a3 * a3);
+    g.x += 3.f * w * p.x * a0; g.y += 3.f * w * p.y * a1; g.z += 3.f * w * p.z * a2; g.w += 3.f * w * p.w * a3;
+    G4[off] = g;
+    if (c == 0) touched[r] = 1;
+  }
+  // the last block writes w * sum into `loss` (a scratch slot here; the host wrapper adds it to the running loss)
+  block_finalize_loss(acc, 0.0, partials, ticket, (double)w, 0.0, loss);
+}
+__global__ void k_add_scalar(float* dst, const float* src) { dst[0] += src[0]; }
+}  // namespace
+
+extern "C" int kgeb_l3_reg(kgeb_ctx* ctx, const float* P, int64_t rows, int width, int ld, float w, float* G, uint8_t* touched,
+                           float* loss, kgeb_stream stream) {
+  if (!ctx) return KGEB_ERR_INVALID;
+  KGEB_REQUIRE(ctx, P && G && touched && loss && rows > 0 && width > 0 && ld >= width, KGEB_ERR_INVALID, "l3_reg: bad arguments");
+  KGEB_REQUIRE(ctx, width % 4 == 0 && ld % 4 == 0 && kgeb_aligned16(P) && kgeb_aligned16(G), KGEB_ERR_ALIGNMENT,
+               "l3_reg needs width, ld multiples of 4 floats and 16-byte aligned buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t blocks = (rows * (width / 4) + KGEB_THREADS - 1) / KGEB_THREADS;
+  const int64_t cap = ctx->num_sms * 8 < KGEB_MAX_PARTIAL_BLOCKS ? ctx->num_sms * 8 : KGEB_MAX_PARTIAL_BLOCKS;
+  if (blocks > cap) blocks = cap;
+  float* tmp = reinterpret_cast<float*>(ctx->d_partials + 2 * KGEB_MAX_PARTIAL_BLOCKS - 2);  // last scratch slot
+  k_l3_reg<<<(int)blocks, KGEB_THREADS, 0, st>>>(P, rows, width / 4, ld / 4, w, G, touched, tmp, ctx->d_partials, ctx->d_ticket);
+  KGEB_LAUNCH_OK(ctx);
+  k_add_scalar<<<1, 1, 0, st>>>(loss, tmp);
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
 }

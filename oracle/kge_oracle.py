@@ -306,6 +306,11 @@ def dense_grads(kind, E, R, idx, dscore, gamma=12.0, dtype=np.float64):
     return gE, gR, tE, tR
 
 
+def l3_reg(E, w):
+    """models.py:10-11: w * ||E||_3^3 = w * sum |e|^3 and its dense gradient 3 w e |e| (entity table only, models.py:92)."""
+    return w * np.sum(np.abs(E) ** 3), 3.0 * w * E * np.abs(E)
+
+
 def opt_update(opt_kind, P, G, touched, state, lr, step, b1=0.9, b2=0.999, eps=1e-7):
     """One optimizer step on a table, in the dtype of P.  state = (m, v) for Adam, (acc,) for Adagrad.
 

@@ -313,3 +313,22 @@ def test_rank_shards_sum_to_whole():
             r0, r1 = g * per, min(1000, (g + 1) * per)
             acc += eng.rank_counts(tri, 0, offs, ids, row_range=(r0, r1)).cpu().numpy()
         np.testing.assert_array_equal(acc, whole)
+
+
+def test_l3_regularization_step():
+    """l3_reg (models.py:10-11): loss += w*sum|E|^3, dense gradient 3 w E|E| on every entity row, all rows updated."""
+    kind, N, R, d, B, K, w = ko.DISTMULT, 90, 4, 16, 32, 3, 0.01
+    eng, E, Rm = make_engine(kind, N, R, d, seed=13, scale=3.0)
+    rng = np.random.default_rng(14)
+    pos = rand_triples(rng, B, N, R)
+    neg = ko.philox_negatives(pos, N, K, 3, 0, ko.CORRUPT_BOTH).astype(np.int32)
+    res = eng.forward_backward(pos, neg, K=K, loss_kind=ko.PAIRWISE_HINGE, margin=1.0, opt_kind=ko.OPT_SGD)
+    eng.l3_reg(w, res["loss"])
+    want = ko.train_step(kind, ko.PAIRWISE_HINGE, ko.PAIRED, E, Rm, pos, neg, K, 1.0, 12.0, ko.OPT_SGD, [], [], 0.1, 1)
+    rl, rg = ko.l3_reg(E.astype(np.float64), w)
+    assert abs(float(res["loss"].item()) - (want["loss"] + rl)) <= 1e-5 * (want["loss"] + rl)
+    g = eng.gE.cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(g, want["gE"] + rg, rtol=1e-4, atol=1e-6 * np.abs(want["gE"] + rg).max())
+    assert int(eng.tE.sum()) == N
+    eng.apply_optimizer(ko.OPT_SGD, lr=0.1)
+    np.testing.assert_allclose(eng.get_tables()[0], E - 0.1 * (want["gE"] + rg), rtol=1e-4, atol=1e-6)
