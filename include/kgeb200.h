@@ -146,6 +146,26 @@ KGEB_API int kgeb_rank_1n(kgeb_ctx* ctx, const float* E_shard, int64_t row_offse
                  const float* tscore, const int32_t* triples, int64_t Q, int side, const int64_t* filt_offsets,
                  const int32_t* filt_ids, int32_t* counts, kgeb_stream stream);
 
+/* ---- 1-N ranking on the tensor cores (tcgen05) for the dot-product scores: DistMult, ComplEx, HolE ------------------
+ * Same result contract as kgeb_rank_1n.  KGEB_TC_BF16X3_EXACT: bf16 hi/lo split contraction used as a filter with a
+ * proven error bound + exact fp32 re-scoring of the undecided pairs -> integer counts IDENTICAL to kgeb_rank_1n.
+ * KGEB_TC_BF16: one bf16 plane, no bound -> approximate (ranks may move at near-ties).  Replaces the per-query
+ * model.predict + rankdata loop of validate, utils.py:210-245. */
+typedef enum { KGEB_TC_BF16 = 0, KGEB_TC_BF16X3_EXACT = 1 } kgeb_tc_mode;
+/* bytes of the packed bf16 image (+ row norms) of an entity shard of n_rows rows */
+KGEB_API int64_t kgeb_rank_tc_packed_bytes(const kgeb_ctx* ctx, int64_t n_rows, int mode);
+/* packs E_shard[n_rows, ldE] once per table version (the table is constant during validate) */
+KGEB_API int kgeb_rank_tc_pack_entities(kgeb_ctx* ctx, const float* E_shard, int64_t n_rows, int mode, void* packed,
+                               int64_t packed_bytes, kgeb_stream stream);
+/* workspace for Q queries: 256-byte header {uint32 appended, uint32 capacity}, worklist of capacity (q,c) pairs,
+ * packed queries, query norms.  After the stream has run the call, appended > capacity means the worklist overflowed:
+ * counts are then incomplete and the call must be repeated with a larger worklist_cap. */
+KGEB_API int64_t kgeb_rank_tc_workspace_bytes(const kgeb_ctx* ctx, int64_t Q, int mode, int64_t worklist_cap);
+KGEB_API int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_offset, int64_t n_rows, const void* packedE,
+                    const float* qvec, const float* tscore, const int32_t* triples, int64_t Q, int side,
+                    const int64_t* filt_offsets, const int32_t* filt_ids, int mode, void* workspace,
+                    int64_t workspace_bytes, int64_t worklist_cap, int32_t* counts, kgeb_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@ PAIRED, ALLPAIRS = 0, 1
 SGD, ADAGRAD, LAZY_ADAM, ADAM_DENSE = range(4)
 CORRUPT_BOTH, CORRUPT_HEAD, CORRUPT_TAIL, CORRUPT_EITHER = range(4)
 SIDE_TAIL, SIDE_HEAD = 0, 1
+TC_BF16, TC_BF16X3_EXACT = 0, 1
 
 LOSS_KINDS = {  # reference names, utils.py:321-330
     "pointwize_hinge": POINTWISE_HINGE, "pointwize_logistic": POINTWISE_LOGISTIC,
@@ -51,6 +52,10 @@ PROTOTYPES = {
     "kgeb_query_prep": (_i, [_p, _p, _i64, _i64, _p, _p, _i64, _i, _p, _p]),
     "kgeb_target_scores": (_i, [_p, _p, _i64, _i64, _p, _p, _i64, _i, _p, _p]),
     "kgeb_rank_1n": (_i, [_p, _p, _i64, _i64, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),
+    "kgeb_rank_tc_packed_bytes": (_i64, [_p, _i64, _i]),
+    "kgeb_rank_tc_pack_entities": (_i, [_p, _p, _i64, _i, _p, _i64, _p]),
+    "kgeb_rank_tc_workspace_bytes": (_i64, [_p, _i64, _i, _i64]),
+    "kgeb_rank_1n_tc": (_i, [_p, _p, _i64, _i64, _p, _p, _p, _p, _i64, _i, _p, _p, _i, _p, _i64, _i64, _p, _p]),
 }
 
 _lib = None

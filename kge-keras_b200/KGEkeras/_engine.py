@@ -220,6 +220,65 @@ class Engine:
         self._keep = (qvec, tscore, tri, fo, fi)  # keep alive until the stream has consumed them
         return counts
 
+    # ---- 1-N filtered ranking on the tensor cores (DistMult / ComplEx / HolE) -------------------------------------------
+    def tc_supported(self):
+        return self.kind in (abi.DISTMULT, abi.COMPLEX, abi.HOLE)
+
+    def pack_entities_tc(self, mode=abi.TC_BF16X3_EXACT, row_range=None):
+        """bf16 (hi/lo) image + row norms of the entity rows [r0, r1): build once per table version, reuse for every query batch."""
+        r0, r1 = (0, self.N) if row_range is None else row_range
+        nbytes = int(self.lib.kgeb_rank_tc_packed_bytes(self.ctx, r1 - r0, mode))
+        if nbytes < 0:
+            self._check(nbytes)
+        packed = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.device)
+        if r1 > r0:
+            e_shard = C.c_void_p(self.E.data_ptr() + r0 * self.we_k * 4)
+            self._check(self.lib.kgeb_rank_tc_pack_entities(self.ctx, e_shard, r1 - r0, mode, _ptr(packed), nbytes, _stream()))
+        return packed
+
+    def rank_counts_tc(self, triples, side, filt_offsets=None, filt_ids=None, row_range=None, counts=None,
+                       mode=abi.TC_BF16X3_EXACT, packed=None, worklist_cap=None, stats=None):
+        """Same contract as rank_counts, computed by the tcgen05 kernel.  In TC_BF16X3_EXACT mode the integer counts are
+        identical to rank_counts'; TC_BF16 is approximate.  The undecided-pair worklist is sized by a heuristic and the
+        pass is repeated with a larger one if it overflowed (checked on the host: one 8-byte read-back per pass)."""
+        tri = as_idx(triples, self.device)
+        Q = tri.shape[0]
+        qw = self.lib.kgeb_query_width(self.ctx, side)
+        qvec = torch.zeros(Q, qw, dtype=torch.float32, device=self.device)
+        tscore = torch.zeros(Q, dtype=torch.float32, device=self.device)
+        st = _stream()
+        self._check(self.lib.kgeb_query_prep(self.ctx, _ptr(self.E), 0, self.N, _ptr(self.Rel), _ptr(tri), Q, side, _ptr(qvec), st))
+        self._check(self.lib.kgeb_target_scores(self.ctx, _ptr(self.E), 0, self.N, _ptr(qvec), _ptr(tri), Q, side, _ptr(tscore), st))
+        r0, r1 = (0, self.N) if row_range is None else row_range
+        fo = fi = None
+        if filt_offsets is not None:
+            fo = (filt_offsets if isinstance(filt_offsets, torch.Tensor) else torch.as_tensor(np.asarray(filt_offsets, dtype=np.int64))).to(self.device, torch.int64).contiguous()
+            fi = (filt_ids if isinstance(filt_ids, torch.Tensor) else torch.as_tensor(np.asarray(filt_ids, dtype=np.int32))).to(self.device, torch.int32).contiguous()
+            if fi.numel() == 0:
+                fo = fi = None
+        out = torch.zeros(Q, dtype=torch.int32, device=self.device) if counts is None else counts
+        if r1 <= r0 or Q == 0:
+            return out
+        if packed is None:
+            packed = self.pack_entities_tc(mode, (r0, r1))
+        cap = int(worklist_cap) if worklist_cap else min(2 ** 31 - 2, max(1 << 20, Q * (64 + (r1 - r0) // 128)))
+        e_shard = C.c_void_p(self.E.data_ptr() + r0 * self.we_k * 4)
+        while True:
+            part = torch.zeros(Q, dtype=torch.int32, device=self.device)
+            nbytes = int(self.lib.kgeb_rank_tc_workspace_bytes(self.ctx, Q, mode, cap))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._check(self.lib.kgeb_rank_1n_tc(self.ctx, e_shard, r0, r1 - r0, _ptr(packed), _ptr(qvec), _ptr(tscore), _ptr(tri), Q,
+                                                 side, _ptr(fo), _ptr(fi), mode, _ptr(ws), nbytes, cap, _ptr(part), st))
+            appended = int(ws[:8].view(torch.int32)[0].item()) & 0xFFFFFFFF
+            if stats is not None:
+                stats.update(undecided_pairs=appended, worklist_cap=cap)
+            if appended <= cap:
+                break
+            cap = min(2 ** 31 - 2, appended + appended // 4)
+        out += part
+        self._keep = (qvec, tscore, tri, fo, fi, ws, packed)
+        return out
+
     # ---- weights ------------------------------------------------------------------------------------------------
     def get_tables(self):
         return self.E[:, :self.we].cpu().numpy(), self.Rel[:, :self.wr].cpu().numpy()

@@ -9,43 +9,11 @@
 // and add (__fmul_rn/__fadd_rn, no FMA), so the three code paths below give bit-identical scores for the same (q,c)
 // and oracle.kge_oracle.seqk_scores reproduces them on the CPU.  The filter is applied as a correction pass:
 // counts -= #{c in filter(q) : score(q,c) > target}.
-#include "common.cuh"
+#include "rank_common.cuh"
+
+using namespace kgeb_rank;
 
 namespace {
-
-enum { OP_DOT = 0, OP_L1_TAIL = 1, OP_L1_HEAD = 2, OP_L2_TAIL = 3, OP_L2_HEAD = 4 };
-
-// one term of the sequential accumulation; a = qvec[k] (a2 = qvec[W+k] for head TransE), e = E[c][k]
-template <int OP>
-__device__ __forceinline__ float seq_term(float acc, float a, float a2, float e) {
-  if (OP == OP_DOT) return __fadd_rn(acc, __fmul_rn(a, e));
-  float r;
-  if (OP == OP_L1_TAIL || OP == OP_L2_TAIL) r = __fsub_rn(a, e);
-  else r = __fsub_rn(__fadd_rn(e, a), a2);
-  if (OP == OP_L1_TAIL || OP == OP_L1_HEAD) return __fadd_rn(acc, fabsf(r));
-  return __fadd_rn(acc, __fmul_rn(r, r));
-}
-template <int OP>
-__device__ __forceinline__ float seq_finish(float acc, float gamma) {
-  if (OP == OP_DOT) return acc;
-  if (OP == OP_L2_TAIL || OP == OP_L2_HEAD) acc = __fsqrt_rn(acc);
-  return gamma > 0.f ? __fsub_rn(gamma, acc) : acc;
-}
-template <int OP>
-__device__ __forceinline__ float seq_score(const float* __restrict__ q, const float* __restrict__ e, int W, float gamma) {
-  float acc = 0.f;
-  for (int k = 0; k < W; ++k) acc = seq_term<OP>(acc, q[k], (OP == OP_L1_HEAD || OP == OP_L2_HEAD) ? q[W + k] : 0.f, e[k]);
-  return seq_finish<OP>(acc, gamma);
-}
-__device__ __forceinline__ float seq_score_dyn(int op, const float* q, const float* e, int W, float gamma) {
-  switch (op) {
-    case OP_DOT: return seq_score<OP_DOT>(q, e, W, gamma);
-    case OP_L1_TAIL: return seq_score<OP_L1_TAIL>(q, e, W, gamma);
-    case OP_L1_HEAD: return seq_score<OP_L1_HEAD>(q, e, W, gamma);
-    case OP_L2_TAIL: return seq_score<OP_L2_TAIL>(q, e, W, gamma);
-    default: return seq_score<OP_L2_HEAD>(q, e, W, gamma);
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------
 // query vectors; one thread per output element
@@ -307,12 +275,22 @@ extern "C" int kgeb_rank_1n(kgeb_ctx* ctx, const float* E_shard, int64_t row_off
     default: KGEB_RANK_LAUNCH(OP_L2_HEAD); break;
   }
   KGEB_LAUNCH_OK(ctx);
-  if (filt_offsets) {
-    // nnz is on the device; size the grid from Q (lists are short) -- the kernel grid-strides over nnz
-    k_filter_correct<<<grid1d(ctx, Q * 8, 128), 128, 0, st>>>(op, E_shard, row_offset, n_rows, ctx->ldE, ctx->we, qvec, qw,
-                                                              tscore, triples, Q, side, ctx->gamma, filt_offsets, filt_ids,
-                                                              counts);
-    KGEB_LAUNCH_OK(ctx);
-  }
+  if (filt_offsets)
+    return kgeb_internal_filter_correct(ctx, E_shard, row_offset, n_rows, qvec, tscore, triples, Q, side, filt_offsets,
+                                        filt_ids, counts, st);
+  return KGEB_OK;
+}
+
+int kgeb_internal_host_op_for(int kind, int side) { return host_op_for(kind, side); }
+
+int kgeb_internal_filter_correct(kgeb_ctx* ctx, const float* E_shard, int64_t row_offset, int64_t n_rows, const float* qvec,
+                                 const float* tscore, const int32_t* triples, int64_t Q, int side,
+                                 const int64_t* filt_offsets, const int32_t* filt_ids, int32_t* counts, cudaStream_t st) {
+  const int qw = kgeb_query_width(ctx, side);
+  // nnz is on the device; size the grid from Q (lists are short) -- the kernel grid-strides over nnz
+  k_filter_correct<<<grid1d(ctx, Q * 8, 128), 128, 0, st>>>(host_op_for(ctx->kind, side), E_shard, row_offset, n_rows, ctx->ldE,
+                                                            ctx->we, qvec, qw, tscore, triples, Q, side, ctx->gamma,
+                                                            filt_offsets, filt_ids, counts);
+  KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
 }

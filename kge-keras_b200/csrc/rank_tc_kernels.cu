@@ -1,0 +1,472 @@
+// rank_tc_kernels.cu -- 1-N filtered ranking for the dot-product score functions (DistMult models.py:171-172, ComplEx
+// 212-222, HolE 231-237 as query x E^T) on the 5th-generation tensor cores.
+//
+//   counts[q] = #{c in shard, c != target(q) : score(q,c) > tscore[q]}  -  (filter correction, rank_kernels.cu)
+//
+// The Q x N score matrix never exists: tcgen05.mma accumulates a 128-query x 256-entity tile in TMEM, eight epilogue
+// warps read it back with tcgen05.ld and keep nothing but integer counters.
+//
+// Exactness.  A bf16 contraction cannot reproduce the fp32 sequential-k scores of rank_common.cuh bit for bit, so the
+// tensor cores are used as a FILTER with a proven error bound and the few undecided pairs are re-scored exactly:
+//   operands   q = qh + ql + rq,  e = eh + el + re  (bf16 hi/lo split, |rq| <= 2^-18 |q|),  the kernel accumulates
+//              qh.eh + qh.el + ql.eh in fp32 (3 MMAs per k-step on the same staged tiles),
+//   bound      |S~ - S_seqk| <= c_eps * ||q||_2 * ||e_c||_2,  c_eps = 1.25 * (2^-16 + (K + 1 + 2*Kacc) * 2^-24)
+//              (representation + sequential fp32 rounding of the reference arithmetic + tensor-core accumulation),
+//   epilogue   S~ > t + bound  -> counted;   S~ < t - bound -> dropped;   otherwise the pair (q,c) goes to a worklist
+//              that k_tc_refine re-scores with the exact sequential-k arithmetic.
+// The integer result is therefore identical to k_rank_tile's.  KGEB_TC_BF16 (single bf16 plane, bound forced to 0) is
+// the approximate mode: one MMA per k-step, ranks can differ at near-ties (tolerance stated in the tests).
+//
+// Data movement.  Both operands are pre-packed (k_tc_pack) into the exact shared-memory image the UMMA descriptors
+// expect -- no-swizzle K-major core matrices, [tile][k-chunk][plane][row][8 x bf16] -- so one pipeline stage is two
+// contiguous bulk async copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier; no tensor map is needed.
+// Roles: warp 0 = copy producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator, warps 4-11 = epilogue.
+#include <cuda_bf16.h>
+
+#include "rank_common.cuh"
+
+using namespace kgeb_rank;
+
+namespace {
+
+constexpr int TC_BM = 128;       // queries per tile  (UMMA M, one TMEM lane per query)
+constexpr int TC_BN = 256;       // entities per tile (UMMA N, one TMEM column per entity)
+constexpr int TC_STAGES = 4;
+constexpr int TC_CH_TOTAL = 8;   // 16-byte k-chunks per stage summed over planes (8 / planes chunks of K each)
+constexpr int TC_THREADS = 384;
+constexpr uint32_t TC_A_STAGE = TC_BM * TC_CH_TOTAL * 16;  // 16 KB
+constexpr uint32_t TC_B_STAGE = TC_BN * TC_CH_TOTAL * 16;  // 32 KB
+constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * (TC_A_STAGE + TC_B_STAGE) + 1024 + 256;
+constexpr int TC_HDR_BYTES = 256;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "TC_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra TC_DONE;\n\t"
+      "bra TC_WAIT;\n\t"
+      "TC_DONE:\n\t"
+      "}" ::"r"(tc_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tc_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(tc_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by ONE thread for the CTA
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on `bar` once every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns of TMEM -> 32 registers per thread (thread = lane = query row)
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, no swizzle, K-major: core matrix = 8 rows x 16 bytes stored contiguously (128 B);
+// LBO = byte distance between the two 16-byte k-chunks of one K=16 step, SBO = byte distance between 8-row groups.
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
+         (1ull << 46);
+}
+// instruction descriptor: fp32 accumulate, A = B = bf16, both K-major, N = 256, M = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+struct TcArgs {
+  const unsigned char* packedQ;  // [qtiles][nkc][planes][128][8] bf16
+  const unsigned char* packedE;  // [ntiles][nkc][planes][256][8] bf16
+  const float* qnorm;            // [qtiles*128]  upper bound of ||q||_2
+  const float* enorm;            // [ntiles*256]  upper bound of ||e||_2, NaN on padding rows (never counted, never ambiguous)
+  const float* tscore;           // [Q] exact target scores
+  const int32_t* triples;        // [Q,3]
+  int32_t* counts;               // [Q]
+  uint32_t* wl_hdr;              // [0] = pairs appended (may exceed cap), [1] = cap
+  uint2* wl;                     // (q, shard-local c)
+  uint32_t wl_cap;
+  int64_t Q, row_offset, n_rows;
+  int nkc, planes, qtiles, ntiles, side;
+  float c_eps, t_slack;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smA = smem;
+  unsigned char* smB = smem + TC_STAGES * TC_A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * (TC_A_STAGE + TC_B_STAGE));
+  uint64_t* full = bars;                     // [TC_STAGES]  copies landed
+  uint64_t* empty = bars + TC_STAGES;        // [TC_STAGES]  MMAs that read the stage completed
+  uint64_t* acc_full = bars + 2 * TC_STAGES; // [2]          accumulator ready for the epilogue
+  uint64_t* acc_empty = acc_full + 2;        // [2]          accumulator drained by all 8 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int planes = a.planes;
+  const int ch_per_stage = TC_CH_TOTAL / planes;           // k-chunks (8 bf16 of K) per stage
+  const int nstage = (a.nkc + ch_per_stage - 1) / ch_per_stage;
+  const int64_t items = (int64_t)a.qtiles * a.ntiles;      // item -> (entity tile, query tile), query tile fastest
+
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) a.wl_hdr[1] = a.wl_cap;
+    for (int i = 0; i < TC_STAGES; ++i) { tc_mbar_init(full + i, 1); tc_mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { tc_mbar_init(acc_full + i, 1); tc_mbar_init(acc_empty + i, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer: one thread streams the packed operand stages =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const size_t a_tile_bytes = (size_t)a.nkc * planes * TC_BM * 16, b_tile_bytes = (size_t)a.nkc * planes * TC_BN * 16;
+      for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+        const int64_t tile = it / a.qtiles, qt = it - tile * a.qtiles;
+        const unsigned char* srcA = a.packedQ + (size_t)qt * a_tile_bytes;
+        const unsigned char* srcB = a.packedE + (size_t)tile * b_tile_bytes;
+        for (int s = 0; s < nstage; ++s) {
+          const int c0 = s * ch_per_stage;
+          const int nch = (a.nkc - c0 < ch_per_stage ? a.nkc - c0 : ch_per_stage) * planes;  // 16-byte chunk columns
+          tc_mbar_wait(empty + stage, phase ^ 1u);
+          const uint32_t ab = (uint32_t)nch * TC_BM * 16, bb = (uint32_t)nch * TC_BN * 16;
+          tc_mbar_expect_tx(full + stage, ab + bb);
+          tc_bulk_g2s(smA + stage * TC_A_STAGE, srcA + (size_t)c0 * planes * TC_BM * 16, ab, full + stage);
+          tc_bulk_g2s(smB + stage * TC_B_STAGE, srcB + (size_t)c0 * planes * TC_BN * 16, bb, full + stage);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      const uint32_t lboA = (uint32_t)planes * TC_BM * 16, lboB = (uint32_t)planes * TC_BN * 16;
+      for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+        tc_mbar_wait(acc_empty + acc, acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * TC_BN;
+        uint32_t accumulate = 0;
+        for (int s = 0; s < nstage; ++s) {
+          const int c0 = s * ch_per_stage;
+          const int nk16 = (a.nkc - c0 < ch_per_stage ? a.nkc - c0 : ch_per_stage) >> 1;  // K=16 steps in this stage
+          tc_mbar_wait(full + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = tc_smem_u32(smA + stage * TC_A_STAGE), sb = tc_smem_u32(smB + stage * TC_B_STAGE);
+          for (int j = 0; j < nk16; ++j) {
+            // chunk column (2j, plane p) starts at (2j*planes + p) * rows * 16 bytes
+            const uint32_t a0 = sa + (uint32_t)(2 * j * planes) * TC_BM * 16, b0 = sb + (uint32_t)(2 * j * planes) * TC_BN * 16;
+            tc_mma_bf16(tmem_d, tc_desc(a0, lboA, 128), tc_desc(b0, lboB, 128), TC_IDESC, accumulate);  // qh . eh
+            accumulate = 1;
+            if (planes == 2) {
+              tc_mma_bf16(tmem_d, tc_desc(a0, lboA, 128), tc_desc(b0 + TC_BN * 16, lboB, 128), TC_IDESC, 1);  // qh . el
+              tc_mma_bf16(tmem_d, tc_desc(a0 + TC_BM * 16, lboA, 128), tc_desc(b0, lboB, 128), TC_IDESC, 1);  // ql . eh
+            }
+          }
+          tc_commit(empty + stage);  // the stage may be overwritten once these MMAs have read it
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(acc_full + acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).. and columns 128*((w-4)/4).. =====
+    const int lq = warp & 3, chalf = (warp - 4) >> 2;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+      const int64_t tile = it / a.qtiles, qt = it - tile * a.qtiles;
+      const int64_t q = qt * TC_BM + lq * 32 + lane;
+      const bool qok = q < a.Q;
+      const float t = qok ? __ldg(a.tscore + q) : 0.f;
+      const float epsq = a.c_eps * (qok ? __ldg(a.qnorm + q) : 0.f);
+      const int64_t tgt = qok ? (int64_t)__ldg(a.triples + 3 * q + (a.side == KGEB_SIDE_TAIL ? 2 : 0)) - a.row_offset : -1;
+      const int64_t n0 = tile * TC_BN + chalf * 128;   // shard-local id of this warp's first column
+      const float t_up = __fmaf_rn(fabsf(t), a.t_slack, t), t_dn = __fmaf_rn(-fabsf(t), a.t_slack, t);
+      const float4* ne4 = reinterpret_cast<const float4*>(a.enorm + n0);
+      int cnt = 0;
+
+      tc_mbar_wait(acc_full + acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * TC_BN + chalf * 128 + ((uint32_t)(lq * 32) << 16);
+#pragma unroll 1
+      for (int jc = 0; jc < 128; jc += 32) {
+        float v[32];
+        tc_ld32(taddr + jc, v);
+        int chi = 0, clo = 0;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 ne = __ldg(ne4 + (jc >> 2) + j4);
+          const float nev[4] = {ne.x, ne.y, ne.z, ne.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float s = v[j4 * 4 + u];
+            const float hi = __fmaf_rn(epsq, nev[u], t_up), lo = __fmaf_rn(-epsq, nev[u], t_dn);
+            chi += s > hi ? 1 : 0;
+            clo += s >= lo ? 1 : 0;
+          }
+        }
+        const int64_t trel = tgt - (n0 + jc);  // the target itself is never a candidate (utils.py:169)
+        const bool tgt_here = trel >= 0 && trel < 32;
+        if (clo != chi || tgt_here) {          // rare: undecided pairs go to the exact re-scoring worklist
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float ne = __ldg(a.enorm + n0 + jc + j);
+            const float s = v[j];
+            const float hi = __fmaf_rn(epsq, ne, t_up), lo = __fmaf_rn(-epsq, ne, t_dn);
+            const bool is_hi = s > hi, is_lo = s >= lo;
+            if (tgt_here && j == (int)trel) {
+              chi -= is_hi ? 1 : 0;
+            } else if (is_lo && !is_hi && qok) {
+              const uint32_t pos = atomicAdd(a.wl_hdr, 1u);
+              if (pos < a.wl_cap) a.wl[pos] = make_uint2((uint32_t)q, (uint32_t)(n0 + jc + j));
+            }
+          }
+        }
+        cnt += chi;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(acc_empty + acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (qok && cnt != 0) atomicAdd(a.counts + q, cnt);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---- operand packing ----------------------------------------------------------------------------------------------
+// one thread per 16-byte output chunk: dst[tile][kchunk][plane][row][0..7], plane 0 = bf16(x), plane 1 = bf16(x - plane0)
+__global__ void k_tc_pack(const float* __restrict__ src, int64_t rows, int W, int ld, int tile_rows, int nkc, int planes,
+                          int64_t ntile, uint4* __restrict__ dst) {
+  const int64_t total = ntile * nkc * planes * tile_rows;
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(o % tile_rows);
+    const int64_t o1 = o / tile_rows;
+    const int plane = (int)(o1 % planes);
+    const int64_t o2 = o1 / planes;
+    const int kc = (int)(o2 % nkc);
+    const int64_t tile = o2 / nkc;
+    const int64_t r = tile * tile_rows + row;
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = 0.f;
+    if (r < rows) {
+      const int k0 = kc * 8;
+      if (k0 + 8 <= W) {
+        const float4 v0 = ldg4(reinterpret_cast<const float4*>(src + r * (int64_t)ld + k0));
+        const float4 v1 = ldg4(reinterpret_cast<const float4*>(src + r * (int64_t)ld + k0 + 4));
+        x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (k0 + e < W) x[e] = __ldg(src + r * (int64_t)ld + k0 + e);
+      }
+    }
+    unsigned short h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      __nv_bfloat16 hi = __float2bfloat16_rn(x[e]);
+      if (plane == 1) hi = __float2bfloat16_rn(__fsub_rn(x[e], __bfloat162float(hi)));
+      h[e] = __bfloat16_as_ushort(hi);
+    }
+    uint4 out;
+    out.x = h[0] | ((uint32_t)h[1] << 16); out.y = h[2] | ((uint32_t)h[3] << 16);
+    out.z = h[4] | ((uint32_t)h[5] << 16); out.w = h[6] | ((uint32_t)h[7] << 16);
+    dst[o] = out;
+  }
+}
+
+// norms[r] = an upper bound of ||src[r,:]||_2 for r < rows; rows..rows_padded-1 get `pad_value` (NaN for entities)
+__global__ void k_tc_norms(const float* __restrict__ src, int64_t rows, int64_t rows_padded, int W, int ld, float pad_value,
+                           float* __restrict__ norms) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < rows_padded; r += nwarps) {
+    if (r >= rows) { if (lane == 0) norms[r] = pad_value; continue; }
+    float acc = 0.f;
+    for (int k = lane; k < W; k += 32) { const float x = __ldg(src + r * (int64_t)ld + k); acc = fmaf(x, x, acc); }
+    acc = warp_sum(acc);
+    if (lane == 0) norms[r] = sqrtf(acc) * 1.0001f;  // fp32 summation error of <= 2^12 terms is < 1e-4 relative
+  }
+}
+
+// exact re-scoring of the undecided pairs: one thread per pair, sequential-k fp32 (rank_common.cuh)
+__global__ void k_tc_refine(const float* __restrict__ Es, int ldE, int W, const float* __restrict__ qvec, int qw,
+                            const float* __restrict__ tscore, const uint32_t* __restrict__ hdr, uint32_t cap,
+                            const uint2* __restrict__ wl, int32_t* counts) {
+  const uint32_t n = hdr[0] < cap ? hdr[0] : cap;
+  for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < n; x += gridDim.x * blockDim.x) {
+    const uint2 pr = wl[x];
+    const float sc = seq_score<OP_DOT>(qvec + (int64_t)pr.x * qw, Es + (int64_t)pr.y * ldE, W, 0.f);
+    if (sc > tscore[pr.x]) atomicAdd(counts + pr.x, 1);
+  }
+}
+
+int tc_planes(int mode) { return mode == KGEB_TC_BF16X3_EXACT ? 2 : 1; }
+int tc_nkc(const kgeb_ctx* ctx) { return ((ctx->we + 15) / 16) * 2; }  // K padded to 16, in 8-element chunks
+int64_t tc_tiles(int64_t rows, int tile_rows) { return (rows + tile_rows - 1) / tile_rows; }
+bool tc_kind_ok(const kgeb_ctx* ctx) { return ctx->kind == KGEB_DISTMULT || ctx->kind == KGEB_COMPLEX || ctx->kind == KGEB_HOLE; }
+size_t tc_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int tc_grid(const kgeb_ctx* ctx, int64_t n, int threads) {
+  int64_t b = (n + threads - 1) / threads;
+  const int64_t cap = (int64_t)ctx->num_sms * 16;
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
+
+}  // namespace
+
+extern "C" int64_t kgeb_rank_tc_packed_bytes(const kgeb_ctx* ctx, int64_t n_rows, int mode) {
+  if (!ctx || n_rows < 0 || (mode != KGEB_TC_BF16 && mode != KGEB_TC_BF16X3_EXACT)) return KGEB_ERR_INVALID;
+  const int64_t nt = tc_tiles(n_rows, TC_BN);
+  return (int64_t)tc_align((size_t)nt * tc_nkc(ctx) * tc_planes(mode) * TC_BN * 16) + nt * TC_BN * 4;
+}
+
+extern "C" int kgeb_rank_tc_pack_entities(kgeb_ctx* ctx, const float* E_shard, int64_t n_rows, int mode, void* packed,
+                                          int64_t packed_bytes, kgeb_stream stream) {
+  if (!ctx) return KGEB_ERR_INVALID;
+  KGEB_REQUIRE(ctx, tc_kind_ok(ctx), KGEB_ERR_UNSUPPORTED, "tensor-core ranking serves DistMult, ComplEx and HolE (dot-product queries)");
+  KGEB_REQUIRE(ctx, E_shard && packed && n_rows > 0, KGEB_ERR_INVALID, "rank_tc_pack_entities: bad arguments");
+  KGEB_REQUIRE(ctx, mode == KGEB_TC_BF16 || mode == KGEB_TC_BF16X3_EXACT, KGEB_ERR_INVALID, "unknown tensor-core mode");
+  KGEB_REQUIRE(ctx, ctx->we % 4 == 0 && ctx->ldE % 4 == 0 && kgeb_aligned16(E_shard) && kgeb_aligned16(packed), KGEB_ERR_ALIGNMENT,
+               "rank_tc needs width, stride multiples of 4 floats and 16-byte aligned buffers");
+  KGEB_REQUIRE(ctx, packed_bytes >= kgeb_rank_tc_packed_bytes(ctx, n_rows, mode), KGEB_ERR_WORKSPACE, "packed entity buffer too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t nt = tc_tiles(n_rows, TC_BN);
+  const int nkc = tc_nkc(ctx), planes = tc_planes(mode);
+  k_tc_pack<<<tc_grid(ctx, nt * nkc * planes * TC_BN, 256), 256, 0, st>>>(E_shard, n_rows, ctx->we, ctx->ldE, TC_BN, nkc, planes, nt,
+                                                                         reinterpret_cast<uint4*>(packed));
+  KGEB_LAUNCH_OK(ctx);
+  float* enorm = reinterpret_cast<float*>(static_cast<unsigned char*>(packed) + tc_align((size_t)nt * nkc * planes * TC_BN * 16));
+  k_tc_norms<<<tc_grid(ctx, nt * TC_BN * 32, 256), 256, 0, st>>>(E_shard, n_rows, nt * TC_BN, ctx->we, ctx->ldE, nanf(""), enorm);
+  KGEB_LAUNCH_OK(ctx);
+  return KGEB_OK;
+}
+
+extern "C" int64_t kgeb_rank_tc_workspace_bytes(const kgeb_ctx* ctx, int64_t Q, int mode, int64_t worklist_cap) {
+  if (!ctx || Q < 0 || worklist_cap < 0 || (mode != KGEB_TC_BF16 && mode != KGEB_TC_BF16X3_EXACT)) return KGEB_ERR_INVALID;
+  const int64_t qt = tc_tiles(Q, TC_BM);
+  return (int64_t)(TC_HDR_BYTES + tc_align((size_t)worklist_cap * 8) + tc_align((size_t)qt * tc_nkc(ctx) * tc_planes(mode) * TC_BM * 16) +
+                   tc_align((size_t)qt * TC_BM * 4));
+}
+
+extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_offset, int64_t n_rows, const void* packedE,
+                               const float* qvec, const float* tscore, const int32_t* triples, int64_t Q, int side,
+                               const int64_t* filt_offsets, const int32_t* filt_ids, int mode, void* workspace,
+                               int64_t workspace_bytes, int64_t worklist_cap, int32_t* counts, kgeb_stream stream) {
+  if (!ctx) return KGEB_ERR_INVALID;
+  KGEB_REQUIRE(ctx, tc_kind_ok(ctx), KGEB_ERR_UNSUPPORTED, "tensor-core ranking serves DistMult, ComplEx and HolE (dot-product queries)");
+  KGEB_REQUIRE(ctx, E_shard && packedE && qvec && tscore && triples && counts && workspace && Q >= 0 && n_rows >= 0 && row_offset >= 0,
+               KGEB_ERR_INVALID, "rank_1n_tc: bad arguments");
+  KGEB_REQUIRE(ctx, side == KGEB_SIDE_TAIL || side == KGEB_SIDE_HEAD, KGEB_ERR_INVALID, "unknown side");
+  KGEB_REQUIRE(ctx, mode == KGEB_TC_BF16 || mode == KGEB_TC_BF16X3_EXACT, KGEB_ERR_INVALID, "unknown tensor-core mode");
+  KGEB_REQUIRE(ctx, (filt_offsets == nullptr) == (filt_ids == nullptr), KGEB_ERR_INVALID, "filter CSR: give both arrays or neither");
+  KGEB_REQUIRE(ctx, worklist_cap > 0 && worklist_cap < 0x7fffffffLL, KGEB_ERR_INVALID, "worklist capacity out of range");
+  KGEB_REQUIRE(ctx, ctx->we % 4 == 0 && ctx->ldE % 4 == 0 && kgeb_aligned16(E_shard) && kgeb_aligned16(qvec) && kgeb_aligned16(packedE) &&
+                        (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
+               KGEB_ERR_ALIGNMENT, "rank_1n_tc needs 16-byte aligned tables and a 256-byte aligned workspace");
+  KGEB_REQUIRE(ctx, workspace_bytes >= kgeb_rank_tc_workspace_bytes(ctx, Q, mode, worklist_cap), KGEB_ERR_WORKSPACE,
+               "rank_1n_tc: workspace smaller than kgeb_rank_tc_workspace_bytes()");
+  if (Q == 0 || n_rows == 0) return KGEB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nkc = tc_nkc(ctx), planes = tc_planes(mode), qw = kgeb_query_width(ctx, side);
+  const int64_t qt = tc_tiles(Q, TC_BM), nt = tc_tiles(n_rows, TC_BN);
+  KGEB_REQUIRE(ctx, qt < 0x7fffffffLL && nt < 0x7fffffffLL, KGEB_ERR_UNSUPPORTED, "too many tiles");
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  uint32_t* hdr = reinterpret_cast<uint32_t*>(ws);
+  uint2* wl = reinterpret_cast<uint2*>(ws + TC_HDR_BYTES);
+  unsigned char* packedQ = ws + TC_HDR_BYTES + tc_align((size_t)worklist_cap * 8);
+  float* qnorm = reinterpret_cast<float*>(packedQ + tc_align((size_t)qt * nkc * planes * TC_BM * 16));
+
+  KGEB_CUDA_OK(ctx, cudaMemsetAsync(hdr, 0, TC_HDR_BYTES, st));
+  k_tc_pack<<<tc_grid(ctx, qt * nkc * planes * TC_BM, 256), 256, 0, st>>>(qvec, Q, ctx->we, qw, TC_BM, nkc, planes, qt,
+                                                                         reinterpret_cast<uint4*>(packedQ));
+  KGEB_LAUNCH_OK(ctx);
+  k_tc_norms<<<tc_grid(ctx, qt * TC_BM * 32, 256), 256, 0, st>>>(qvec, Q, qt * TC_BM, ctx->we, qw, 0.f, qnorm);
+  KGEB_LAUNCH_OK(ctx);
+
+  TcArgs a;
+  a.packedQ = packedQ;
+  a.packedE = static_cast<const unsigned char*>(packedE);
+  a.qnorm = qnorm;
+  a.enorm = reinterpret_cast<const float*>(a.packedE + tc_align((size_t)nt * nkc * planes * TC_BN * 16));
+  a.tscore = tscore; a.triples = triples; a.counts = counts;
+  a.wl_hdr = hdr; a.wl = wl; a.wl_cap = (uint32_t)worklist_cap;
+  a.Q = Q; a.row_offset = row_offset; a.n_rows = n_rows;
+  a.nkc = nkc; a.planes = planes; a.qtiles = (int)qt; a.ntiles = (int)nt; a.side = side;
+  if (mode == KGEB_TC_BF16X3_EXACT) {
+    const double kacc = 3.0 * nkc * 8;  // products accumulated per score by the tensor cores
+    a.c_eps = (float)(1.25 * (1.0 / 65536.0 + (ctx->we + 1 + 2.0 * kacc) / 16777216.0));
+    a.t_slack = 2.4e-7f;
+  } else {
+    a.c_eps = 0.f;
+    a.t_slack = 0.f;
+  }
+  static bool attr_done = false;  // per process; the attribute is per function, setting it again is harmless
+  if (!attr_done) {
+    KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_rank_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    attr_done = true;
+  }
+  const int64_t items = qt * nt;
+  const int grid = (int)(items < ctx->num_sms ? items : ctx->num_sms);
+  k_rank_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
+  KGEB_LAUNCH_OK(ctx);
+  // hdr[0] = pairs appended, hdr[1] = capacity (written by the kernel): the host checks hdr[0] <= hdr[1] after the pass
+  k_tc_refine<<<ctx->num_sms * 8, 128, 0, st>>>(E_shard, ctx->ldE, ctx->we, qvec, qw, tscore, hdr, (uint32_t)worklist_cap, wl, counts);
+  KGEB_LAUNCH_OK(ctx);
+  if (filt_offsets)
+    return kgeb_internal_filter_correct(ctx, E_shard, row_offset, n_rows, qvec, tscore, triples, Q, side, filt_offsets, filt_ids,
+                                        counts, st);
+  return KGEB_OK;
+}

@@ -1,0 +1,122 @@
+"""GPU parity tests of the tcgen05 1-N ranking path (kgeb_rank_1n_tc) for the dot-product scores.
+
+Bars:
+  * KGEB_TC_BF16X3_EXACT: integer filtered-rank counts IDENTICAL to the fp32 CUDA-core kernel (kgeb_rank_1n), which is
+    itself bit-exact against the oracle's sequential-k fp32 scores (tests/test_gpu_kernels.py) -- checked against both;
+  * the error bound the exactness rests on is checked directly: the share of undecided pairs must stay small (the
+    tensor-core scores are far inside the proven band) and dyadic tables (every product and sum exact) must need no
+    re-scoring beyond genuine ties;
+  * KGEB_TC_BF16 (approximate): ranks may move only where the fp64 score gap to the target is below the bf16 band
+    2^-7 * ||q|| * ||e|| (stated tolerance).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kge_oracle as ko
+from test_gpu_kernels import _rank_case, make_engine, rand_triples
+
+pytestmark = pytest.mark.gpu
+
+DOT_KINDS = [ko.DISTMULT, ko.COMPLEX, ko.HOLE]
+
+
+def _abi():
+    from KGEkeras import _abi as abi
+    return abi
+
+
+@pytest.mark.parametrize("kind", DOT_KINDS)
+@pytest.mark.parametrize("side", ["tail", "head"])
+@pytest.mark.parametrize("d,N,Q", [(8, 130, 70), (100, 1000, 257), (36, 64, 64), (200, 2500, 300)])
+def test_tc_exact_counts_equal_cuda_core_and_oracle(kind, side, d, N, Q):
+    abi = _abi()
+    if kind == ko.HOLE and d > 100:
+        pytest.skip("HolE O(d^2) oracle is slow")
+    eng, E, Rm, tri, fh, ft = _rank_case(kind, N, 5, d, Q, seed=31 + d, dyadic=False)
+    filt = ft if side == "tail" else fh
+    offs, ids = ko.filter_csr(tri, side, filt)
+    sd = 0 if side == "tail" else 1
+    want = eng.rank_counts(tri, sd, offs, ids).cpu().numpy()
+    stats = {}
+    got = eng.rank_counts_tc(tri, sd, offs, ids, mode=abi.TC_BF16X3_EXACT, stats=stats).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+    if N * Q * d <= 1000 * 257 * 100:
+        qv = ko.query_vectors(kind, E, Rm, tri, side)
+        sc = ko.seqk_scores(kind, qv, E, side, 12.0)
+        np.testing.assert_array_equal(got, (ko.ranks_from_scores(sc, tri, side, filt) - 1).astype(np.int32))
+    # the bound is loose by design, but the undecided set must stay a small share of the Q x N pairs
+    assert stats["undecided_pairs"] <= max(4 * Q, 0.05 * Q * N), stats
+
+
+@pytest.mark.parametrize("kind", DOT_KINDS)
+@pytest.mark.parametrize("side", ["tail", "head"])
+def test_tc_exact_dyadic_with_ties(kind, side):
+    abi = _abi()
+    eng, E, Rm, tri, fh, ft = _rank_case(kind, 700, 5, 12, 200, seed=3, dyadic=True)
+    filt = ft if side == "tail" else fh
+    offs, ids = ko.filter_csr(tri, side, filt)
+    sd = 0 if side == "tail" else 1
+    got = eng.rank_counts_tc(tri, sd, offs, ids, mode=abi.TC_BF16X3_EXACT).cpu().numpy()
+    sc = ko.all_entity_scores(kind, E, Rm, tri, side, 12.0, np.float32)   # exact on dyadic tables
+    want = ko.ranks_from_scores(sc, tri, side, filt) - 1
+    np.testing.assert_array_equal(got, want.astype(np.int32))
+
+
+def test_tc_exact_no_filter_and_shards_sum_to_whole():
+    abi = _abi()
+    kind = ko.COMPLEX
+    eng, E, Rm, tri, fh, ft = _rank_case(kind, 1500, 5, 40, 300, seed=9, dyadic=False)
+    whole = eng.rank_counts(tri, 0).cpu().numpy()
+    np.testing.assert_array_equal(eng.rank_counts_tc(tri, 0, mode=abi.TC_BF16X3_EXACT).cpu().numpy(), whole)
+    offs, ids = ko.filter_csr(tri, "tail", ft)
+    whole_f = eng.rank_counts(tri, 0, offs, ids).cpu().numpy()
+    for G in (2, 3):
+        per = -(-1500 // G)
+        acc = torch.zeros(len(tri), dtype=torch.int32, device="cuda")
+        for g in range(G):
+            r0, r1 = g * per, min(1500, (g + 1) * per)
+            eng.rank_counts_tc(tri, 0, offs, ids, row_range=(r0, r1), counts=acc, mode=abi.TC_BF16X3_EXACT)
+        np.testing.assert_array_equal(acc.cpu().numpy(), whole_f)
+
+
+def test_tc_worklist_overflow_is_detected_and_retried():
+    abi = _abi()
+    # identical entity rows: every candidate ties the target -> every pair is undecided -> a tiny worklist must overflow
+    N, R, d, Q = 600, 3, 16, 90
+    rng = np.random.default_rng(5)
+    E = np.repeat(ko.glorot_uniform(rng, 1, d), N, axis=0)
+    Rm = ko.glorot_uniform(rng, R, d)
+    from KGEkeras._engine import Engine
+    eng = Engine(abi.DISTMULT, N, R, d, d, 12.0, E=E, R=Rm)
+    tri = rand_triples(rng, Q, N, R)
+    stats = {}
+    got = eng.rank_counts_tc(tri, 0, mode=abi.TC_BF16X3_EXACT, worklist_cap=128, stats=stats).cpu().numpy()
+    assert stats["worklist_cap"] > 128 and stats["undecided_pairs"] >= Q * (N - 1)
+    np.testing.assert_array_equal(got, np.zeros(Q, np.int32))   # all ties: nothing is strictly greater
+    np.testing.assert_array_equal(got, eng.rank_counts(tri, 0).cpu().numpy())
+
+
+@pytest.mark.parametrize("kind", [ko.DISTMULT, ko.COMPLEX])
+def test_tc_bf16_approximate_within_stated_band(kind):
+    abi = _abi()
+    N, Q, d = 2000, 256, 64
+    eng, E, Rm, tri, fh, ft = _rank_case(kind, N, 5, d, Q, seed=77, dyadic=False)
+    offs, ids = ko.filter_csr(tri, "tail", ft)
+    got = eng.rank_counts_tc(tri, 0, offs, ids, mode=abi.TC_BF16).cpu().numpy()
+    sc64 = ko.all_entity_scores(kind, E, Rm, tri, "tail", 12.0, np.float64)
+    r64 = ko.ranks_from_scores(sc64, tri, "tail", ft) - 1
+    qv = ko.query_vectors(kind, E.astype(np.float64), Rm.astype(np.float64), tri, "tail")
+    band = 2.0 ** -7 * np.linalg.norm(qv, axis=1) * np.linalg.norm(E, axis=1).max()
+    for qi in range(Q):
+        if got[qi] != r64[qi]:
+            tgt = tri[qi, 2]
+            near = int(np.sum(np.abs(sc64[qi] - sc64[qi, tgt]) <= band[qi])) - 1
+            assert abs(int(got[qi]) - int(r64[qi])) <= near, (qi, got[qi], r64[qi], near)
+
+
+def test_tc_rejects_transe():
+    abi = _abi()
+    eng, E, Rm = make_engine(ko.TRANSE_L1, 100, 3, 8)
+    with pytest.raises(abi.KgebError):
+        eng.pack_entities_tc(abi.TC_BF16)
