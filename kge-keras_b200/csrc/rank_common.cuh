@@ -50,3 +50,7 @@ int kgeb_internal_host_op_for(int kind, int side);
 int kgeb_internal_filter_correct(kgeb_ctx* ctx, const float* E_shard, int64_t row_offset, int64_t n_rows, const float* qvec,
                                  const float* tscore, const int32_t* triples, int64_t Q, int side,
                                  const int64_t* filt_offsets, const int32_t* filt_ids, int32_t* counts, cudaStream_t st);
+// counts[q] += [seq score(q,c) > tscore[q]] for the first min(wl_hdr[0], wl_cap) pairs (q, shard-local c) of the worklist
+int kgeb_internal_refine_worklist(kgeb_ctx* ctx, const float* E_shard, int64_t n_rows, const float* qvec, const float* tscore,
+                                  int64_t Q, int side, const uint32_t* wl_hdr, uint32_t wl_cap, const uint2* wl, int32_t* counts,
+                                  cudaStream_t st);

@@ -64,34 +64,96 @@ __global__ void k_query_prep(int kind, int side, const float* __restrict__ Es, i
   }
 }
 
-__global__ void k_target_scores(int op, const float* __restrict__ Es, int64_t row_offset, int64_t n_rows, int ldE, int W,
-                                const float* __restrict__ qvec, int qw, const int32_t* __restrict__ triples, int64_t Q,
-                                int side, float gamma, float* __restrict__ tscore) {
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t tgt = side == KGEB_SIDE_TAIL ? triples[3 * q + 2] : triples[3 * q];
-    if (tgt < row_offset || tgt >= row_offset + n_rows) continue;
-    tscore[q] = seq_score_dyn(op, qvec + q * (int64_t)qw, Es + (tgt - row_offset) * (int64_t)ldE, W, gamma);
+// ---------------------------------------------------------------------------------------------------
+// exact scores of explicit (query, candidate) pairs: the target scores, the CSR filter correction and the re-scoring of
+// the pairs the tensor-core kernel could not decide all run through this one kernel.  A warp owns 32 pairs; the rows
+// travel global -> shared memory as coalesced 128-byte segments (32 floats of every pair's query and entity row per
+// pass), then lane p accumulates ITS pair sequentially over k from shared memory (stride 33: conflict free).  The
+// arithmetic is exactly seq_score's (same order, same roundings), only the loads are cooperative.
+// ---------------------------------------------------------------------------------------------------
+enum { PAIRS_TARGET = 0, PAIRS_WORKLIST = 1, PAIRS_FILTER = 2 };
+constexpr int PAIR_WARPS = 2;
+
+struct PairArgs {
+  const float* Es; int64_t row_offset, n_rows; int ldE, W;
+  const float* qvec; int qw;
+  float* tscore;                 // written (TARGET) or read
+  const int32_t* triples; int64_t Q; int side; float gamma;
+  const int64_t* offs; const int32_t* ids;          // FILTER
+  const uint32_t* wl_hdr; uint32_t wl_cap; const uint2* wl;  // WORKLIST
+  int32_t* counts;
+};
+
+template <int OP, int SRC>
+__global__ void __launch_bounds__(PAIR_WARPS * 32) k_seqk_pairs(PairArgs a) {
+  constexpr bool HEAD = (OP == OP_L1_HEAD || OP == OP_L2_HEAD);
+  __shared__ float sq[PAIR_WARPS][32][33];
+  __shared__ float se[PAIR_WARPS][32][33];
+  __shared__ float sq2[HEAD ? PAIR_WARPS : 1][HEAD ? 32 : 1][HEAD ? 33 : 1];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int64_t n;
+  if (SRC == PAIRS_TARGET) n = a.Q;
+  else if (SRC == PAIRS_WORKLIST) n = a.wl_hdr[0] < a.wl_cap ? a.wl_hdr[0] : a.wl_cap;
+  else n = a.offs[a.Q];
+  const int64_t warp0 = (int64_t)blockIdx.x * PAIR_WARPS + w, nwarps = (int64_t)gridDim.x * PAIR_WARPS;
+  for (int64_t base = warp0 * 32; base < n; base += nwarps * 32) {
+    const int64_t x = base + lane;
+    bool valid = x < n;
+    int64_t q = 0, c = 0;
+    if (valid) {
+      if (SRC == PAIRS_TARGET) {
+        q = x;
+        c = (int64_t)(a.side == KGEB_SIDE_TAIL ? a.triples[3 * q + 2] : a.triples[3 * q]) - a.row_offset;
+      } else if (SRC == PAIRS_WORKLIST) {
+        const uint2 pr = a.wl[x];
+        q = pr.x; c = pr.y;
+      } else {
+        int64_t lo = 0, hi = a.Q;  // largest q with offs[q] <= x
+        while (hi - lo > 1) {
+          const int64_t mid = (lo + hi) >> 1;
+          if (a.offs[mid] <= x) lo = mid; else hi = mid;
+        }
+        q = lo;
+        const int64_t id = a.ids[x];
+        const int64_t tgt = a.side == KGEB_SIDE_TAIL ? a.triples[3 * q + 2] : a.triples[3 * q];
+        c = id - a.row_offset;
+        valid = id != tgt;
+      }
+      valid = valid && c >= 0 && c < a.n_rows;   // another shard owns this candidate
+      if (!valid) { q = 0; c = 0; }
+    }
+    float acc = 0.f;
+    for (int k0 = 0; k0 < a.W; k0 += 32) {
+      const int k = k0 + lane;
+      const bool kin = k < a.W;
+#pragma unroll 8
+      for (int p = 0; p < 32; ++p) {
+        const int64_t qq = __shfl_sync(0xffffffffu, q, p), cc = __shfl_sync(0xffffffffu, c, p);
+        sq[w][p][lane] = kin ? __ldg(a.qvec + qq * a.qw + k) : 0.f;
+        se[w][p][lane] = kin ? __ldg(a.Es + cc * a.ldE + k) : 0.f;
+        if (HEAD) sq2[w][p][lane] = kin ? __ldg(a.qvec + qq * a.qw + a.W + k) : 0.f;
+      }
+      __syncwarp();
+      const int klim = a.W - k0 < 32 ? a.W - k0 : 32;
+      for (int kk = 0; kk < klim; ++kk) acc = seq_term<OP>(acc, sq[w][lane][kk], HEAD ? sq2[w][lane][kk] : 0.f, se[w][lane][kk]);
+      __syncwarp();
+    }
+    if (!valid) continue;
+    const float sc = seq_finish<OP>(acc, a.gamma);
+    if (SRC == PAIRS_TARGET) a.tscore[q] = sc;
+    else if (SRC == PAIRS_WORKLIST) { if (sc > a.tscore[q]) atomicAdd(a.counts + q, 1); }
+    else { if (sc > a.tscore[q]) atomicSub(a.counts + q, 1); }
   }
 }
 
-// filter correction: one thread per CSR entry
-__global__ void k_filter_correct(int op, const float* __restrict__ Es, int64_t row_offset, int64_t n_rows, int ldE, int W,
-                                 const float* __restrict__ qvec, int qw, const float* __restrict__ tscore,
-                                 const int32_t* __restrict__ triples, int64_t Q, int side, float gamma,
-                                 const int64_t* __restrict__ offs, const int32_t* __restrict__ ids, int32_t* counts) {
-  const int64_t nnz = offs[Q];
-  for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < nnz; x += (int64_t)gridDim.x * blockDim.x) {
-    int64_t lo = 0, hi = Q;  // largest q with offs[q] <= x
-    while (hi - lo > 1) {
-      const int64_t mid = (lo + hi) >> 1;
-      if (offs[mid] <= x) lo = mid; else hi = mid;
-    }
-    const int64_t q = lo;
-    const int64_t c = ids[x];
-    const int64_t tgt = side == KGEB_SIDE_TAIL ? triples[3 * q + 2] : triples[3 * q];
-    if (c == tgt || c < row_offset || c >= row_offset + n_rows) continue;
-    const float sc = seq_score_dyn(op, qvec + q * (int64_t)qw, Es + (c - row_offset) * (int64_t)ldE, W, gamma);
-    if (sc > tscore[q]) atomicSub(counts + q, 1);
+template <int SRC>
+void launch_pairs(int op, int blocks, cudaStream_t st, const PairArgs& a) {
+  switch (op) {
+    case OP_DOT: k_seqk_pairs<OP_DOT, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
+    case OP_L1_TAIL: k_seqk_pairs<OP_L1_TAIL, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
+    case OP_L1_HEAD: k_seqk_pairs<OP_L1_HEAD, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
+    case OP_L2_TAIL: k_seqk_pairs<OP_L2_TAIL, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
+    default: k_seqk_pairs<OP_L2_HEAD, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
   }
 }
 
@@ -202,6 +264,13 @@ int grid1d(const kgeb_ctx* ctx, int64_t n, int threads) {
   return (int)b;
 }
 
+int pairs_grid(const kgeb_ctx* ctx, int64_t pairs) {
+  int64_t b = (pairs + PAIR_WARPS * 32 - 1) / (PAIR_WARPS * 32);
+  const int64_t cap = (int64_t)ctx->num_sms * 16;
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
+
 int host_op_for(int kind, int side) {
   if (kind == KGEB_TRANSE_L1) return side == KGEB_SIDE_TAIL ? OP_L1_TAIL : OP_L1_HEAD;
   if (kind == KGEB_TRANSE_L2) return side == KGEB_SIDE_TAIL ? OP_L2_TAIL : OP_L2_HEAD;
@@ -237,9 +306,10 @@ extern "C" int kgeb_target_scores(kgeb_ctx* ctx, const float* E_shard, int64_t r
   KGEB_REQUIRE(ctx, E_shard && qvec && triples && tscore && Q >= 0, KGEB_ERR_INVALID, "target_scores: bad arguments");
   if (Q == 0) return KGEB_OK;
   const int qw = kgeb_query_width(ctx, side);
-  k_target_scores<<<grid1d(ctx, Q, 128), 128, 0, (cudaStream_t)stream>>>(host_op_for(ctx->kind, side), E_shard, row_offset,
-                                                                         n_rows, ctx->ldE, ctx->we, qvec, qw, triples, Q,
-                                                                         side, ctx->gamma, tscore);
+  PairArgs a = {};
+  a.Es = E_shard; a.row_offset = row_offset; a.n_rows = n_rows; a.ldE = ctx->ldE; a.W = ctx->we; a.qvec = qvec; a.qw = qw;
+  a.tscore = tscore; a.triples = triples; a.Q = Q; a.side = side; a.gamma = ctx->gamma;
+  launch_pairs<PAIRS_TARGET>(host_op_for(ctx->kind, side), pairs_grid(ctx, Q), (cudaStream_t)stream, a);
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
 }
@@ -287,10 +357,24 @@ int kgeb_internal_filter_correct(kgeb_ctx* ctx, const float* E_shard, int64_t ro
                                  const float* tscore, const int32_t* triples, int64_t Q, int side,
                                  const int64_t* filt_offsets, const int32_t* filt_ids, int32_t* counts, cudaStream_t st) {
   const int qw = kgeb_query_width(ctx, side);
+  PairArgs a = {};
+  a.Es = E_shard; a.row_offset = row_offset; a.n_rows = n_rows; a.ldE = ctx->ldE; a.W = ctx->we; a.qvec = qvec; a.qw = qw;
+  a.tscore = const_cast<float*>(tscore); a.triples = triples; a.Q = Q; a.side = side; a.gamma = ctx->gamma;
+  a.offs = filt_offsets; a.ids = filt_ids; a.counts = counts;
   // nnz is on the device; size the grid from Q (lists are short) -- the kernel grid-strides over nnz
-  k_filter_correct<<<grid1d(ctx, Q * 8, 128), 128, 0, st>>>(host_op_for(ctx->kind, side), E_shard, row_offset, n_rows, ctx->ldE,
-                                                            ctx->we, qvec, qw, tscore, triples, Q, side, ctx->gamma,
-                                                            filt_offsets, filt_ids, counts);
+  launch_pairs<PAIRS_FILTER>(host_op_for(ctx->kind, side), pairs_grid(ctx, Q * 8), st, a);
+  KGEB_LAUNCH_OK(ctx);
+  return KGEB_OK;
+}
+
+int kgeb_internal_refine_worklist(kgeb_ctx* ctx, const float* E_shard, int64_t n_rows, const float* qvec, const float* tscore,
+                                  int64_t Q, int side, const uint32_t* wl_hdr, uint32_t wl_cap, const uint2* wl, int32_t* counts,
+                                  cudaStream_t st) {
+  PairArgs a = {};
+  a.Es = E_shard; a.row_offset = 0; a.n_rows = n_rows; a.ldE = ctx->ldE; a.W = ctx->we; a.qvec = qvec;
+  a.qw = kgeb_query_width(ctx, side); a.tscore = const_cast<float*>(tscore); a.Q = Q; a.side = side; a.gamma = ctx->gamma;
+  a.wl_hdr = wl_hdr; a.wl_cap = wl_cap; a.wl = wl; a.counts = counts;
+  launch_pairs<PAIRS_WORKLIST>(host_op_for(ctx->kind, side), ctx->num_sms * 16, st, a);
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
 }

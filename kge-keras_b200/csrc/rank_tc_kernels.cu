@@ -13,7 +13,8 @@
 //   bound      |S~ - S_seqk| <= c_eps * ||q||_2 * ||e_c||_2,  c_eps = 1.25 * (2^-16 + (K + 1 + 2*Kacc) * 2^-24)
 //              (representation + sequential fp32 rounding of the reference arithmetic + tensor-core accumulation),
 //   epilogue   S~ > t + bound  -> counted;   S~ < t - bound -> dropped;   otherwise the pair (q,c) goes to a worklist
-//              that k_tc_refine re-scores with the exact sequential-k arithmetic.
+//              that k_seqk_pairs (rank_kernels.cu) re-scores with the exact sequential-k arithmetic.  The bound used per
+//              128-entity slice is the slice's largest ||e||, so a thread compares against two constants.
 // The integer result is therefore identical to k_rank_tile's.  KGEB_TC_BF16 (single bf16 plane, bound forced to 0) is
 // the approximate mode: one MMA per k-step, ranks can differ at near-ties (tolerance stated in the tests).
 //
@@ -22,6 +23,7 @@
 // contiguous bulk async copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier; no tensor map is needed.
 // Roles: warp 0 = copy producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator, warps 4-11 = epilogue.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "rank_common.cuh"
 
@@ -36,7 +38,8 @@ constexpr int TC_CH_TOTAL = 8;   // 16-byte k-chunks per stage summed over plane
 constexpr int TC_THREADS = 384;
 constexpr uint32_t TC_A_STAGE = TC_BM * TC_CH_TOTAL * 16;  // 16 KB
 constexpr uint32_t TC_B_STAGE = TC_BN * TC_CH_TOTAL * 16;  // 32 KB
-constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * (TC_A_STAGE + TC_B_STAGE) + 1024 + 256;
+constexpr int TC_WBUF = 128;     // undecided pairs buffered per epilogue warp before one aggregated append
+constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * (TC_A_STAGE + TC_B_STAGE) + 1024 + 256 + 8 * TC_WBUF * 8;
 constexpr int TC_HDR_BYTES = 256;
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
@@ -85,9 +88,10 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
-// 32 lanes x 32 consecutive fp32 columns of TMEM -> 32 registers per thread (thread = lane = query row)
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+// 32 lanes x 32 consecutive fp32 columns of TMEM -> 32 registers per thread (thread = lane = query row).  The load is
+// asynchronous: the registers are valid only after tc_ld_wait, which names them as in/out operands so that no use can
+// be scheduled before it.
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -96,10 +100,31 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
         "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+// one accumulator against the row's band [lo, hi]:  cnt += s > hi;  msk |= bit when lo <= s <= hi (undecided)
+#define TC_CMP(S, HI, LO, CNT, MSK, BIT)                                                                                  \
+  asm("{\n\t.reg .pred ph, pu;\n\tsetp.gt.f32 ph, %2, %3;\n\t@ph add.s32 %0, %0, 1;\n\tsetp.ge.and.f32 pu, %2, %4, !ph;\n\t" \
+      "@pu or.b32 %1, %1, %5;\n\t}"                                                                                       \
+      : "+r"(CNT), "+r"(MSK)                                                                                              \
+      : "r"(S), "f"(HI), "f"(LO), "n"(BIT))
+template <int J>
+__device__ __forceinline__ void tc_cmp32(const uint32_t (&r)[32], float hi, float lo, int& c0, int& c1, uint32_t& m0, uint32_t& m1) {
+  if constexpr (J < 32) {  // two independent counter / mask chains
+    TC_CMP(r[J], hi, lo, c0, m0, 1u << J);
+    TC_CMP(r[J + 1], hi, lo, c1, m1, 1u << (J + 1));
+    tc_cmp32<J + 2>(r, hi, lo, c0, c1, m0, m1);
+  }
 }
 
 // shared-memory matrix descriptor, no swizzle, K-major: core matrix = 8 rows x 16 bytes stored contiguously (128 B);
@@ -115,7 +140,7 @@ struct TcArgs {
   const unsigned char* packedQ;  // [qtiles][nkc][planes][128][8] bf16
   const unsigned char* packedE;  // [ntiles][nkc][planes][256][8] bf16
   const float* qnorm;            // [qtiles*128]  upper bound of ||q||_2
-  const float* enorm;            // [ntiles*256]  upper bound of ||e||_2, NaN on padding rows (never counted, never ambiguous)
+  const float* emax;             // [ntiles*2]    max over each 128-entity slice of the upper bound of ||e||_2
   const float* tscore;           // [Q] exact target scores
   const int32_t* triples;        // [Q,3]
   int32_t* counts;               // [Q]
@@ -123,9 +148,24 @@ struct TcArgs {
   uint2* wl;                     // (q, shard-local c)
   uint32_t wl_cap;
   int64_t Q, row_offset, n_rows;
-  int nkc, planes, qtiles, ntiles, side;
+  int nkc, planes, qtiles, ntiles, side, qgroup;
   float c_eps, t_slack;
 };
+
+// item -> (entity tile, query tile).  Query tiles are walked in groups of `qgroup`: inside a group the query tile varies
+// fastest, so the CTAs running at the same time share a handful of entity tiles (L2 hits) without all hammering one.
+__device__ __forceinline__ void tc_item(const TcArgs& a, int64_t it, int64_t& tile, int64_t& qt) {
+  const int64_t G = a.qgroup, per = G * a.ntiles, full = a.qtiles / G;
+  if (it < full * per) {
+    const int64_t g = it / per, rem = it - g * per;
+    tile = rem / G;
+    qt = g * G + (rem - tile * G);
+  } else {
+    const int64_t rem = it - full * per, Gl = a.qtiles - full * G;
+    tile = rem / Gl;
+    qt = full * G + (rem - tile * Gl);
+  }
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
   extern __shared__ unsigned char tc_smem_raw[];
@@ -138,12 +178,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
   uint64_t* acc_full = bars + 2 * TC_STAGES; // [2]          accumulator ready for the epilogue
   uint64_t* acc_empty = acc_full + 2;        // [2]          accumulator drained by all 8 epilogue warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint2* wbuf_all = reinterpret_cast<uint2*>(smem + TC_STAGES * (TC_A_STAGE + TC_B_STAGE) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int planes = a.planes;
   const int ch_per_stage = TC_CH_TOTAL / planes;           // k-chunks (8 bf16 of K) per stage
   const int nstage = (a.nkc + ch_per_stage - 1) / ch_per_stage;
-  const int64_t items = (int64_t)a.qtiles * a.ntiles;      // item -> (entity tile, query tile), query tile fastest
+  const int64_t items = (int64_t)a.qtiles * a.ntiles;
 
   if (threadIdx.x == 0) {
     if (blockIdx.x == 0) a.wl_hdr[1] = a.wl_cap;
@@ -166,7 +207,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
       uint32_t stage = 0, phase = 0;
       const size_t a_tile_bytes = (size_t)a.nkc * planes * TC_BM * 16, b_tile_bytes = (size_t)a.nkc * planes * TC_BN * 16;
       for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
-        const int64_t tile = it / a.qtiles, qt = it - tile * a.qtiles;
+        int64_t tile, qt;
+        tc_item(a, it, tile, qt);
         const unsigned char* srcA = a.packedQ + (size_t)qt * a_tile_bytes;
         const unsigned char* srcB = a.packedE + (size_t)tile * b_tile_bytes;
         for (int s = 0; s < nstage; ++s) {
@@ -217,64 +259,99 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
   } else if (warp >= 4) {
     // ===== epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).. and columns 128*((w-4)/4).. =====
     const int lq = warp & 3, chalf = (warp - 4) >> 2;
+    uint2* wbuf = wbuf_all + (warp - 4) * TC_WBUF;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t wcnt = 0;  // pairs waiting in wbuf (warp-uniform)
     uint32_t acc = 0, acc_phase = 0;
+    const bool approx = a.c_eps == 0.f;
+
+    auto flush = [&]() {
+      __syncwarp();
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(a.wl_hdr, wcnt);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      for (uint32_t i = lane; i < wcnt; i += 32)
+        if (base + i < a.wl_cap) a.wl[base + i] = wbuf[i];
+      __syncwarp();
+      wcnt = 0;
+    };
+
     for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
-      const int64_t tile = it / a.qtiles, qt = it - tile * a.qtiles;
+      int64_t tile, qt;
+      tc_item(a, it, tile, qt);
       const int64_t q = qt * TC_BM + lq * 32 + lane;
       const bool qok = q < a.Q;
       const float t = qok ? __ldg(a.tscore + q) : 0.f;
       const float epsq = a.c_eps * (qok ? __ldg(a.qnorm + q) : 0.f);
       const int64_t tgt = qok ? (int64_t)__ldg(a.triples + 3 * q + (a.side == KGEB_SIDE_TAIL ? 2 : 0)) - a.row_offset : -1;
       const int64_t n0 = tile * TC_BN + chalf * 128;   // shard-local id of this warp's first column
-      const float t_up = __fmaf_rn(fabsf(t), a.t_slack, t), t_dn = __fmaf_rn(-fabsf(t), a.t_slack, t);
-      const float4* ne4 = reinterpret_cast<const float4*>(a.enorm + n0);
-      int cnt = 0;
+      const float nmax = __ldg(a.emax + tile * 2 + chalf);
+      const float hi = __fmaf_rn(epsq, nmax, __fmaf_rn(fabsf(t), a.t_slack, t));
+      const float lo = __fmaf_rn(-epsq, nmax, __fmaf_rn(-fabsf(t), a.t_slack, t));
+      const int zero_counts = 0.f > hi ? 1 : 0;         // what a zero (padding) column contributes to the count
+      int cnt0 = 0, cnt1 = 0;
+
+      // one 32-column chunk: counts, undecided mask, padding correction, append of the undecided pairs
+      auto process = [&](uint32_t (&r)[32], int jc) {
+        uint32_t m0 = 0, m1 = 0;
+        tc_cmp32<0>(r, hi, lo, cnt0, cnt1, m0, m1);
+        uint32_t mask = m0 | m1;
+        const int64_t c0 = n0 + jc;
+        const int64_t left = a.n_rows - c0;                     // columns of this chunk that are real entities
+        if (left < 32) {                                        // warp-uniform: only in the last entity tile
+          const int nvalid = left < 0 ? 0 : (int)left;
+          mask &= nvalid == 0 ? 0u : (0xffffffffu >> (32 - nvalid));
+          cnt0 -= (32 - nvalid) * zero_counts;                  // padding rows are all-zero: their score is exactly 0
+        }
+        const int64_t trel = tgt - c0;                          // the target itself is never a candidate (utils.py:169)
+        const bool tgt_here = trel >= 0 && trel < 32;
+        if (tgt_here) mask &= ~(1u << (int)trel);
+        if (approx && __any_sync(0xffffffffu, tgt_here)) {
+          // exact mode never counts the target (its score is inside the band by construction); without a band it can
+          uint32_t st = r[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) st = (j == (int)trel) ? r[j] : st;
+          if (tgt_here && __uint_as_float(st) > hi) cnt0 -= 1;
+        }
+        if (!qok) mask = 0;
+        while (true) {
+          const uint32_t have = __ballot_sync(0xffffffffu, mask != 0);
+          if (have == 0) break;
+          if (wcnt + 32 > TC_WBUF) flush();
+          if (mask != 0) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            wbuf[wcnt + __popc(have & lt_mask)] = make_uint2((uint32_t)q, (uint32_t)(c0 + j));
+          }
+          wcnt += __popc(have);
+        }
+      };
 
       tc_mbar_wait(acc_full + acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * TC_BN + chalf * 128 + ((uint32_t)(lq * 32) << 16);
-#pragma unroll 1
-      for (int jc = 0; jc < 128; jc += 32) {
-        float v[32];
-        tc_ld32(taddr + jc, v);
-        int chi = 0, clo = 0;
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 ne = __ldg(ne4 + (jc >> 2) + j4);
-          const float nev[4] = {ne.x, ne.y, ne.z, ne.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float s = v[j4 * 4 + u];
-            const float hi = __fmaf_rn(epsq, nev[u], t_up), lo = __fmaf_rn(-epsq, nev[u], t_dn);
-            chi += s > hi ? 1 : 0;
-            clo += s >= lo ? 1 : 0;
-          }
-        }
-        const int64_t trel = tgt - (n0 + jc);  // the target itself is never a candidate (utils.py:169)
-        const bool tgt_here = trel >= 0 && trel < 32;
-        if (clo != chi || tgt_here) {          // rare: undecided pairs go to the exact re-scoring worklist
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float ne = __ldg(a.enorm + n0 + jc + j);
-            const float s = v[j];
-            const float hi = __fmaf_rn(epsq, ne, t_up), lo = __fmaf_rn(-epsq, ne, t_dn);
-            const bool is_hi = s > hi, is_lo = s >= lo;
-            if (tgt_here && j == (int)trel) {
-              chi -= is_hi ? 1 : 0;
-            } else if (is_lo && !is_hi && qok) {
-              const uint32_t pos = atomicAdd(a.wl_hdr, 1u);
-              if (pos < a.wl_cap) a.wl[pos] = make_uint2((uint32_t)q, (uint32_t)(n0 + jc + j));
-            }
-          }
-        }
-        cnt += chi;
-      }
+      uint32_t rA[32], rB[32];
+      tc_ld32_issue(taddr, rA);
+      tc_ld_wait(rA);
+      tc_ld32_issue(taddr + 32, rB);
+      process(rA, 0);
+      tc_ld_wait(rB);
+      tc_ld32_issue(taddr + 64, rA);
+      process(rB, 32);
+      tc_ld_wait(rA);
+      tc_ld32_issue(taddr + 96, rB);
+      process(rA, 64);
+      tc_ld_wait(rB);
+      // every TMEM read of this accumulator has completed: hand it back to the MMA issuer before the last chunk
       tc_fence_before();
       __syncwarp();
       if (lane == 0) tc_mbar_arrive(acc_empty + acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      process(rB, 96);
+      const int cnt = cnt0 + cnt1;
       if (qok && cnt != 0) atomicAdd(a.counts + q, cnt);
     }
+    if (wcnt != 0) flush();
   }
   tc_fence_before();
   __syncthreads();
@@ -340,15 +417,16 @@ __global__ void k_tc_norms(const float* __restrict__ src, int64_t rows, int64_t 
   }
 }
 
-// exact re-scoring of the undecided pairs: one thread per pair, sequential-k fp32 (rank_common.cuh)
-__global__ void k_tc_refine(const float* __restrict__ Es, int ldE, int W, const float* __restrict__ qvec, int qw,
-                            const float* __restrict__ tscore, const uint32_t* __restrict__ hdr, uint32_t cap,
-                            const uint2* __restrict__ wl, int32_t* counts) {
-  const uint32_t n = hdr[0] < cap ? hdr[0] : cap;
-  for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < n; x += gridDim.x * blockDim.x) {
-    const uint2 pr = wl[x];
-    const float sc = seq_score<OP_DOT>(qvec + (int64_t)pr.x * qw, Es + (int64_t)pr.y * ldE, W, 0.f);
-    if (sc > tscore[pr.x]) atomicAdd(counts + pr.x, 1);
+// emax[slice] = max of the row-norm upper bounds over each 128-row slice (0 for an all-padding slice)
+__global__ void k_tc_slice_max(const float* __restrict__ norms, int64_t nslices, float* __restrict__ emax) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t sl = warp0; sl < nslices; sl += nwarps) {
+    float m = 0.f;
+    for (int i = lane; i < 128; i += 32) m = fmaxf(m, norms[sl * 128 + i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) emax[sl] = m;
   }
 }
 
@@ -370,7 +448,7 @@ int tc_grid(const kgeb_ctx* ctx, int64_t n, int threads) {
 extern "C" int64_t kgeb_rank_tc_packed_bytes(const kgeb_ctx* ctx, int64_t n_rows, int mode) {
   if (!ctx || n_rows < 0 || (mode != KGEB_TC_BF16 && mode != KGEB_TC_BF16X3_EXACT)) return KGEB_ERR_INVALID;
   const int64_t nt = tc_tiles(n_rows, TC_BN);
-  return (int64_t)tc_align((size_t)nt * tc_nkc(ctx) * tc_planes(mode) * TC_BN * 16) + nt * TC_BN * 4;
+  return (int64_t)(tc_align((size_t)nt * tc_nkc(ctx) * tc_planes(mode) * TC_BN * 16) + tc_align((size_t)nt * TC_BN * 4) + nt * 2 * 4);
 }
 
 extern "C" int kgeb_rank_tc_pack_entities(kgeb_ctx* ctx, const float* E_shard, int64_t n_rows, int mode, void* packed,
@@ -389,7 +467,10 @@ extern "C" int kgeb_rank_tc_pack_entities(kgeb_ctx* ctx, const float* E_shard, i
                                                                          reinterpret_cast<uint4*>(packed));
   KGEB_LAUNCH_OK(ctx);
   float* enorm = reinterpret_cast<float*>(static_cast<unsigned char*>(packed) + tc_align((size_t)nt * nkc * planes * TC_BN * 16));
-  k_tc_norms<<<tc_grid(ctx, nt * TC_BN * 32, 256), 256, 0, st>>>(E_shard, n_rows, nt * TC_BN, ctx->we, ctx->ldE, nanf(""), enorm);
+  k_tc_norms<<<tc_grid(ctx, nt * TC_BN * 32, 256), 256, 0, st>>>(E_shard, n_rows, nt * TC_BN, ctx->we, ctx->ldE, 0.f, enorm);
+  KGEB_LAUNCH_OK(ctx);
+  float* emax = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(enorm) + tc_align((size_t)nt * TC_BN * 4));
+  k_tc_slice_max<<<tc_grid(ctx, nt * 2 * 32, 256), 256, 0, st>>>(enorm, nt * 2, emax);
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
 }
@@ -440,11 +521,19 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
   a.packedQ = packedQ;
   a.packedE = static_cast<const unsigned char*>(packedE);
   a.qnorm = qnorm;
-  a.enorm = reinterpret_cast<const float*>(a.packedE + tc_align((size_t)nt * nkc * planes * TC_BN * 16));
+  a.emax = reinterpret_cast<const float*>(a.packedE + tc_align((size_t)nt * nkc * planes * TC_BN * 16) + tc_align((size_t)nt * TC_BN * 4));
   a.tscore = tscore; a.triples = triples; a.counts = counts;
   a.wl_hdr = hdr; a.wl = wl; a.wl_cap = (uint32_t)worklist_cap;
   a.Q = Q; a.row_offset = row_offset; a.n_rows = n_rows;
   a.nkc = nkc; a.planes = planes; a.qtiles = (int)qt; a.ntiles = (int)nt; a.side = side;
+  {
+    // concurrent CTAs (one per SM) should cover a few entity tiles, not one and not all: groups of ~num_sms/4 query tiles
+    const char* env = getenv("KGEB_TC_QGROUP");
+    int64_t g = env ? atoll(env) : (ctx->num_sms + 3) / 4;
+    if (g < 1) g = 1;
+    if (g > qt) g = qt;
+    a.qgroup = (int)g;
+  }
   if (mode == KGEB_TC_BF16X3_EXACT) {
     const double kacc = 3.0 * nkc * 8;  // products accumulated per score by the tensor cores
     a.c_eps = (float)(1.25 * (1.0 / 65536.0 + (ctx->we + 1 + 2.0 * kacc) / 16777216.0));
@@ -463,8 +552,8 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
   k_rank_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
   KGEB_LAUNCH_OK(ctx);
   // hdr[0] = pairs appended, hdr[1] = capacity (written by the kernel): the host checks hdr[0] <= hdr[1] after the pass
-  k_tc_refine<<<ctx->num_sms * 8, 128, 0, st>>>(E_shard, ctx->ldE, ctx->we, qvec, qw, tscore, hdr, (uint32_t)worklist_cap, wl, counts);
-  KGEB_LAUNCH_OK(ctx);
+  const int rc = kgeb_internal_refine_worklist(ctx, E_shard, n_rows, qvec, tscore, Q, side, hdr, (uint32_t)worklist_cap, wl, counts, st);
+  if (rc != KGEB_OK) return rc;
   if (filt_offsets)
     return kgeb_internal_filter_correct(ctx, E_shard, row_offset, n_rows, qvec, tscore, triples, Q, side, filt_offsets, filt_ids,
                                         counts, st);
