@@ -87,10 +87,12 @@ struct PairArgs {
 template <int OP, int SRC>
 __global__ void __launch_bounds__(PAIR_WARPS * 32) k_seqk_pairs(PairArgs a) {
   constexpr bool HEAD = (OP == OP_L1_HEAD || OP == OP_L2_HEAD);
-  __shared__ float sq[PAIR_WARPS][32][33];
-  __shared__ float se[PAIR_WARPS][32][33];
-  __shared__ float sq2[HEAD ? PAIR_WARPS : 1][HEAD ? 32 : 1][HEAD ? 33 : 1];
+  constexpr int LDP = 36;  // row stride in floats: 16-byte aligned rows, conflict-free LDS.128 by row (4*lane groups)
+  __shared__ __align__(16) float sq[PAIR_WARPS][32][LDP];
+  __shared__ __align__(16) float se[PAIR_WARPS][32][LDP];
+  __shared__ __align__(16) float sq2[HEAD ? PAIR_WARPS : 1][HEAD ? 32 : 1][HEAD ? LDP : 4];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int sub = lane >> 3, l8 = lane & 7;  // 8 lanes x float4 cover one 128-byte row segment; 4 pairs per load
   int64_t n;
   if (SRC == PAIRS_TARGET) n = a.Q;
   else if (SRC == PAIRS_WORKLIST) n = a.wl_hdr[0] < a.wl_cap ? a.wl_hdr[0] : a.wl_cap;
@@ -122,20 +124,37 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_seqk_pairs(PairArgs a) {
       valid = valid && c >= 0 && c < a.n_rows;   // another shard owns this candidate
       if (!valid) { q = 0; c = 0; }
     }
+    // element offsets of the two rows of MY pair; the loaders fetch them from the owning lane
+    const int64_t qoff = q * a.qw, eoff = c * (int64_t)a.ldE;
     float acc = 0.f;
     for (int k0 = 0; k0 < a.W; k0 += 32) {
-      const int k = k0 + lane;
-      const bool kin = k < a.W;
-#pragma unroll 8
-      for (int p = 0; p < 32; ++p) {
-        const int64_t qq = __shfl_sync(0xffffffffu, q, p), cc = __shfl_sync(0xffffffffu, c, p);
-        sq[w][p][lane] = kin ? __ldg(a.qvec + qq * a.qw + k) : 0.f;
-        se[w][p][lane] = kin ? __ldg(a.Es + cc * a.ldE + k) : 0.f;
-        if (HEAD) sq2[w][p][lane] = kin ? __ldg(a.qvec + qq * a.qw + a.W + k) : 0.f;
+      const int k = k0 + 4 * l8;
+      const bool kin = k < a.W;                 // W % 4 == 0: a float4 is entirely inside or outside the row
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int p = 4 * i + sub;
+        const int64_t qo = __shfl_sync(0xffffffffu, qoff, p), eo = __shfl_sync(0xffffffffu, eoff, p);
+        const float4 vq = kin ? ldg4(reinterpret_cast<const float4*>(a.qvec + qo + k)) : f4zero();
+        const float4 ve = kin ? ldg4(reinterpret_cast<const float4*>(a.Es + eo + k)) : f4zero();
+        *reinterpret_cast<float4*>(&sq[w][p][4 * l8]) = vq;
+        *reinterpret_cast<float4*>(&se[w][p][4 * l8]) = ve;
+        if (HEAD) {
+          const float4 v2 = kin ? ldg4(reinterpret_cast<const float4*>(a.qvec + qo + a.W + k)) : f4zero();
+          *reinterpret_cast<float4*>(&sq2[w][p][4 * l8]) = v2;
+        }
       }
       __syncwarp();
-      const int klim = a.W - k0 < 32 ? a.W - k0 : 32;
-      for (int kk = 0; kk < klim; ++kk) acc = seq_term<OP>(acc, sq[w][lane][kk], HEAD ? sq2[w][lane][kk] : 0.f, se[w][lane][kk]);
+      const int klim = a.W - k0 < 32 ? a.W - k0 : 32;   // multiple of 4
+      for (int kk = 0; kk < klim; kk += 4) {
+        const float4 x4 = *reinterpret_cast<const float4*>(&sq[w][lane][kk]);
+        const float4 e4 = *reinterpret_cast<const float4*>(&se[w][lane][kk]);
+        float4 y4 = f4zero();
+        if (HEAD) y4 = *reinterpret_cast<const float4*>(&sq2[w][lane][kk]);
+        acc = seq_term<OP>(acc, x4.x, y4.x, e4.x);
+        acc = seq_term<OP>(acc, x4.y, y4.y, e4.y);
+        acc = seq_term<OP>(acc, x4.z, y4.z, e4.z);
+        acc = seq_term<OP>(acc, x4.w, y4.w, e4.w);
+      }
       __syncwarp();
     }
     if (!valid) continue;

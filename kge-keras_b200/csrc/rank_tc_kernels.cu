@@ -10,7 +10,7 @@
 // tensor cores are used as a FILTER with a proven error bound and the few undecided pairs are re-scored exactly:
 //   operands   q = qh + ql + rq,  e = eh + el + re  (bf16 hi/lo split, |rq| <= 2^-18 |q|),  the kernel accumulates
 //              qh.eh + qh.el + ql.eh in fp32 (3 MMAs per k-step on the same staged tiles),
-//   bound      |S~ - S_seqk| <= c_eps * ||q||_2 * ||e_c||_2,  c_eps = 1.25 * (2^-16 + (K + 1 + 2*Kacc) * 2^-24)
+//   bound      |S~ - S_seqk| <= c_eps * ||q||_2 * ||e_c||_2,  c_eps = 1.05 * (2^-16 + (K + 1 + 2*Kacc) * 2^-24)
 //              (representation + sequential fp32 rounding of the reference arithmetic + tensor-core accumulation),
 //   epilogue   S~ > t + bound  -> counted;   S~ < t - bound -> dropped;   otherwise the pair (q,c) goes to a worklist
 //              that k_seqk_pairs (rank_kernels.cu) re-scores with the exact sequential-k arithmetic.  The bound used per
@@ -536,7 +536,7 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
   }
   if (mode == KGEB_TC_BF16X3_EXACT) {
     const double kacc = 3.0 * nkc * 8;  // products accumulated per score by the tensor cores
-    a.c_eps = (float)(1.25 * (1.0 / 65536.0 + (ctx->we + 1 + 2.0 * kacc) / 16777216.0));
+    a.c_eps = (float)(1.05 * (1.0 / 65536.0 + (ctx->we + 1 + 2.0 * kacc) / 16777216.0));
     a.t_slack = 2.4e-7f;
   } else {
     a.c_eps = 0.f;
