@@ -83,6 +83,11 @@ KGEB_API const char* kgeb_last_error(const kgeb_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 KGEB_API int64_t kgeb_launch_count(const kgeb_ctx* ctx);
 KGEB_API int kgeb_num_sms(const kgeb_ctx* ctx);
+/* Measurement aid for bench.py's roofline: with timing on, the library brackets the named kernels with CUDA events on
+ * the caller's stream; kgeb_last_kernel_ms waits for the closing event and returns the device time of the last launch. */
+typedef enum { KGEB_TIMED_RANK_TC = 0, KGEB_TIMED_RANK_REFINE = 1, KGEB_TIMED_RANK_TILE = 2, KGEB_TIMED_TRAIN = 3 } kgeb_timed_kernel;
+KGEB_API int kgeb_set_kernel_timing(kgeb_ctx* ctx, int on);
+KGEB_API int kgeb_last_kernel_ms(kgeb_ctx* ctx, int which, float* ms);
 
 /* ---- scoring: EmbeddingModel.call + func, models.py:134-162 (dropout inactive) ---------------------------- */
 /* scores[m] = func(E[idx[:,0]], R[idx[:,1]], E[idx[:,2]]) */

@@ -13,6 +13,7 @@ SGD, ADAGRAD, LAZY_ADAM, ADAM_DENSE = range(4)
 CORRUPT_BOTH, CORRUPT_HEAD, CORRUPT_TAIL, CORRUPT_EITHER = range(4)
 SIDE_TAIL, SIDE_HEAD = 0, 1
 TC_BF16, TC_BF16X3_EXACT = 0, 1
+TIMED_RANK_TC, TIMED_RANK_REFINE, TIMED_RANK_TILE, TIMED_TRAIN = range(4)
 
 LOSS_KINDS = {  # reference names, utils.py:321-330
     "pointwize_hinge": POINTWISE_HINGE, "pointwize_logistic": POINTWISE_LOGISTIC,
@@ -41,6 +42,8 @@ PROTOTYPES = {
     "kgeb_last_error": (C.c_char_p, [_p]),
     "kgeb_launch_count": (_i64, [_p]),
     "kgeb_num_sms": (_i, [_p]),
+    "kgeb_set_kernel_timing": (_i, [_p, _i]),
+    "kgeb_last_kernel_ms": (_i, [_p, _i, C.POINTER(_f)]),
     "kgeb_score_fwd": (_i, [_p, _p, _p, _p, _i64, _p, _p]),
     "kgeb_score_bwd": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p]),
     "kgeb_negatives": (_i, [_p, _p, _i64, _i, _u64, _u64, _i, _p, _p]),

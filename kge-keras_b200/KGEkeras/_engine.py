@@ -88,6 +88,14 @@ class Engine:
     def _check(self, rc):
         abi.check(rc, self.ctx)
 
+    def set_kernel_timing(self, on=True):
+        self._check(self.lib.kgeb_set_kernel_timing(self.ctx, 1 if on else 0))
+
+    def last_kernel_ms(self, which):
+        ms = C.c_float()
+        self._check(self.lib.kgeb_last_kernel_ms(self.ctx, which, C.byref(ms)))
+        return float(ms.value)
+
     def _ensure_train_buffers(self, opt_kind):
         if self.gE is None:
             self.gE, self.gR = torch.zeros_like(self.E), torch.zeros_like(self.Rel)

@@ -51,6 +51,9 @@ extern "C" int kgeb_destroy(kgeb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->d_partials) cudaFree(ctx->d_partials);
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
+  for (int i = 0; i < KGEB_TIMED_KERNELS; ++i)
+    for (int j = 0; j < 2; ++j)
+      if (ctx->ev[i][j]) cudaEventDestroy(ctx->ev[i][j]);
   delete ctx;
   return KGEB_OK;
 }
@@ -58,3 +61,22 @@ extern "C" int kgeb_destroy(kgeb_ctx* ctx) {
 extern "C" const char* kgeb_last_error(const kgeb_ctx* ctx) { return ctx ? ctx->err : g_kgeb_create_err; }
 extern "C" int64_t kgeb_launch_count(const kgeb_ctx* ctx) { return ctx ? ctx->launches : -1; }
 extern "C" int kgeb_num_sms(const kgeb_ctx* ctx) { return ctx ? ctx->num_sms : KGEB_ERR_INVALID; }
+
+extern "C" int kgeb_set_kernel_timing(kgeb_ctx* ctx, int on) {
+  if (!ctx) return KGEB_ERR_INVALID;
+  if (on) {
+    for (int i = 0; i < KGEB_TIMED_KERNELS; ++i)
+      for (int j = 0; j < 2; ++j)
+        if (!ctx->ev[i][j]) KGEB_CUDA_OK(ctx, cudaEventCreate(&ctx->ev[i][j]));
+  }
+  ctx->timing = on ? 1 : 0;
+  return KGEB_OK;
+}
+
+extern "C" int kgeb_last_kernel_ms(kgeb_ctx* ctx, int which, float* ms) {
+  if (!ctx || !ms || which < 0 || which >= KGEB_TIMED_KERNELS) return KGEB_ERR_INVALID;
+  KGEB_REQUIRE(ctx, ctx->ev_valid[which], KGEB_ERR_INVALID, "kernel timing: that kernel has not been launched with timing on");
+  KGEB_CUDA_OK(ctx, cudaEventSynchronize(ctx->ev[which][1]));
+  KGEB_CUDA_OK(ctx, cudaEventElapsedTime(ms, ctx->ev[which][0], ctx->ev[which][1]));
+  return KGEB_OK;
+}

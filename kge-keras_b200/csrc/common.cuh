@@ -10,6 +10,7 @@
 #define KGEB_WARPS_PER_BLOCK 8
 #define KGEB_THREADS (KGEB_WARPS_PER_BLOCK * 32)
 #define KGEB_MAX_PARTIAL_BLOCKS 4096
+#define KGEB_TIMED_KERNELS 4
 
 struct kgeb_ctx {
   int device;
@@ -23,7 +24,15 @@ struct kgeb_ctx {
   // fixed scratch, allocated once in kgeb_create (nothing allocates afterwards)
   double* d_partials;        // [KGEB_MAX_PARTIAL_BLOCKS * 2] per-block loss partial sums
   unsigned int* d_ticket;    // last-block-done counter (self-resetting)
+  // optional kernel timing (kgeb_set_kernel_timing): events recorded on the caller's stream around selected launches
+  int timing;
+  cudaEvent_t ev[KGEB_TIMED_KERNELS][2];
+  bool ev_valid[KGEB_TIMED_KERNELS];
 };
+
+// brackets one launch with events when timing is on (slot = kgeb_timed_kernel)
+#define KGEB_TIME_BEGIN(ctx, slot, st) do { if ((ctx)->timing) cudaEventRecord((ctx)->ev[slot][0], (st)); } while (0)
+#define KGEB_TIME_END(ctx, slot, st) do { if ((ctx)->timing) { cudaEventRecord((ctx)->ev[slot][1], (st)); (ctx)->ev_valid[slot] = true; } } while (0)
 
 extern char g_kgeb_create_err[512];
 

@@ -356,6 +356,7 @@ extern "C" int kgeb_rank_1n(kgeb_ctx* ctx, const float* E_shard, int64_t row_off
   dim3 grid((unsigned)qtiles, (unsigned)split);
 #define KGEB_RANK_LAUNCH(OPV) \
   k_rank_tile<OPV><<<grid, 256, 0, st>>>(E_shard, n_rows, ctx->ldE, ctx->we, qvec, qw, tscore, Q, ctx->gamma, counts)
+  KGEB_TIME_BEGIN(ctx, KGEB_TIMED_RANK_TILE, st);
   switch (op) {
     case OP_DOT: KGEB_RANK_LAUNCH(OP_DOT); break;
     case OP_L1_TAIL: KGEB_RANK_LAUNCH(OP_L1_TAIL); break;
@@ -363,6 +364,7 @@ extern "C" int kgeb_rank_1n(kgeb_ctx* ctx, const float* E_shard, int64_t row_off
     case OP_L2_TAIL: KGEB_RANK_LAUNCH(OP_L2_TAIL); break;
     default: KGEB_RANK_LAUNCH(OP_L2_HEAD); break;
   }
+  KGEB_TIME_END(ctx, KGEB_TIMED_RANK_TILE, st);
   KGEB_LAUNCH_OK(ctx);
   if (filt_offsets)
     return kgeb_internal_filter_correct(ctx, E_shard, row_offset, n_rows, qvec, tscore, triples, Q, side, filt_offsets,

@@ -549,10 +549,14 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
   }
   const int64_t items = qt * nt;
   const int grid = (int)(items < ctx->num_sms ? items : ctx->num_sms);
+  KGEB_TIME_BEGIN(ctx, KGEB_TIMED_RANK_TC, st);
   k_rank_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
+  KGEB_TIME_END(ctx, KGEB_TIMED_RANK_TC, st);
   KGEB_LAUNCH_OK(ctx);
+  KGEB_TIME_BEGIN(ctx, KGEB_TIMED_RANK_REFINE, st);
   // hdr[0] = pairs appended, hdr[1] = capacity (written by the kernel): the host checks hdr[0] <= hdr[1] after the pass
   const int rc = kgeb_internal_refine_worklist(ctx, E_shard, n_rows, qvec, tscore, Q, side, hdr, (uint32_t)worklist_cap, wl, counts, st);
+  KGEB_TIME_END(ctx, KGEB_TIMED_RANK_REFINE, st);
   if (rc != KGEB_OK) return rc;
   if (filt_offsets)
     return kgeb_internal_filter_correct(ctx, E_shard, row_offset, n_rows, qvec, tscore, triples, Q, side, filt_offsets, filt_ids,

@@ -423,7 +423,9 @@ extern "C" int kgeb_train_fwd_bwd(kgeb_ctx* ctx, const float* E, const float* R,
     KGEB_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_train_ring<KIND, NC, M>, KGEB_THREADS, smem)); \
     int grid = grid_for(ctx, B, occ < 1 ? 1 : occ);                                                                      \
     if (grid > KGEB_MAX_PARTIAL_BLOCKS) grid = KGEB_MAX_PARTIAL_BLOCKS;                                                  \
+    KGEB_TIME_BEGIN(ctx, KGEB_TIMED_TRAIN, st);                                                                          \
     k_train_ring<KIND, NC, M><<<grid, KGEB_THREADS, smem, st>>>(a, D, RB);                                               \
+    KGEB_TIME_END(ctx, KGEB_TIMED_TRAIN, st);                                                                            \
   }
     KGEB_DISPATCH_KIND(ctx->kind, KGEB_DISPATCH_NC(nc, {
       if (mode == 0) KGEB_RING_LAUNCH(0) else if (mode == 1) KGEB_RING_LAUNCH(1) else KGEB_RING_LAUNCH(2)
