@@ -77,6 +77,15 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def ncu_traffic(key):
+    """DRAM bytes per launch of a kernel from the committed ncu capture (profiles/r01_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            return json.load(fh)[key]["bytes"]
+    except Exception:
+        return None
+
+
 def glorot(rng, rows, cols):
     lim = np.sqrt(6.0 / (rows + cols))
     return rng.uniform(-lim, lim, size=(rows, cols)).astype(np.float32)
@@ -308,7 +317,8 @@ def main():
     for mname, v in tensor_eval.items():
         v["roofline"] = {"bound": "tensor", "kernel": "k_rank_tc", "achieved": v["algorithmic_tflops"], "peak": pk["bf16_tflops"],
                          "unit": "TFLOP/s", "frac": v["algorithmic_tflops"] / pk["bf16_tflops"],
-                         "pipe_frac": v["executed_tflops"] / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + ", burst",
+                         "pipe_frac": v["executed_tflops"] / pk["bf16_tflops"],
+                         "traffic": ncu_traffic("k_rank_tc_exact" if mname.startswith("exact") else "k_rank_tc_bf16"), "peak_source": pk["source"] + ", burst",
                          "note": "achieved = algorithmic 2*Q*N*Kc flops / CUDA-event kernel time; pipe_frac counts the MMAs really issued "
                                  "(3 per k-step in the exact hi/lo-split mode)"}
     # algorithmic bytes: fused fwd+bwd kernel reads each unique touched row once and writes its gradient once
@@ -336,7 +346,8 @@ def main():
         "gpu_launches": int(launches),
         "kernel_ms": {"k_train_fwd_bwd": fb_ms, "k_opt_update_x2": op_ms, "wall_ms_per_step_incl_flush": 1e3 * t_wall / steps},
         "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                     "frac": ach / pk["hbm_gbs"],
+                     "traffic": ncu_traffic("k_train_ring" if dom[0] == "k_train_fwd_bwd" else "k_opt_update_E"), "peak_source": pk["source"],
                      "note": "algorithmic = compulsory bytes with perfect on-chip reuse of the %d unique rows; the kernel's "
                              "no-reuse gather+scatter request volume is %.0f MB/launch (L2-resident table)" % (U_E, gather_bytes / 1e6)},
         "roofline_step": {"bound": "hbm", "achieved": ach_step, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_step / pk["hbm_gbs"],
