@@ -8,6 +8,7 @@ run on the GPU through libkgeb200.  No TensorFlow, rdflib or spaCy imports (Lite
 from __future__ import annotations
 
 import math
+import os
 from collections import defaultdict
 from random import choice, choices
 
@@ -157,10 +158,22 @@ def filtered_ranks(model, test_data, filtering_triples, group=None):
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
     rows = shard_rows(eng.N, world, rank)
+    # dot-product models (DistMult, ComplEx, HolE) rank on the tensor cores; "exact" gives the same integers as the fp32
+    # CUDA-core kernel ("cuda"), "bf16" is the approximate single-plane mode.  TransE always takes the CUDA-core kernel.
+    mode = str(getattr(model, "rank_mode", None) or os.environ.get("KGEB_RANK_MODE", "exact")).lower()
+    if mode not in ("exact", "bf16", "cuda"):
+        raise ValueError(f"rank_mode must be 'exact', 'bf16' or 'cuda', got {mode!r}")
+    use_tc = mode != "cuda" and eng.tc_supported() and rows[1] > rows[0]
+    tc_mode = abi.TC_BF16 if mode == "bf16" else abi.TC_BF16X3_EXACT
+    packed = eng.pack_entities_tc(tc_mode, rows) if use_tc else None   # the table is constant during validate: pack once
     out = []
     for side, code in (("tail", abi.SIDE_TAIL), ("head", abi.SIDE_HEAD)):
         offs, ids = build_filter_csr(test, filtering_triples, side)
-        counts = merge_partial_counts(eng.rank_counts(test, code, offs, ids, row_range=rows), group)
+        if use_tc:
+            part = eng.rank_counts_tc(test, code, offs, ids, row_range=rows, mode=tc_mode, packed=packed)
+        else:
+            part = eng.rank_counts(test, code, offs, ids, row_range=rows)
+        counts = merge_partial_counts(part, group)
         out.append(counts.cpu().numpy().astype(np.int64) + 1)
     return out[0], out[1]
 
