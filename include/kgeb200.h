@@ -171,6 +171,14 @@ KGEB_API int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_of
                     const int64_t* filt_offsets, const int32_t* filt_ids, int mode, void* workspace,
                     int64_t workspace_bytes, int64_t worklist_cap, int32_t* counts, kgeb_stream stream);
 
+/* ---- row exchange of the row-sharded training path (the 1M-entity config): the all-to-all itself is NCCL's */
+/* dst[i, :width] = P[idx[i], :width]  (rows another rank requested, packed contiguously for the send) */
+KGEB_API int kgeb_rows_gather(kgeb_ctx* ctx, const float* P, int width, int ld, const int32_t* idx, int64_t n, float* dst,
+                     kgeb_stream stream);
+/* G[idx[i], :width] += src[i, :width]; touched[idx[i]] = 1 (gradient rows returned to their owner; duplicates add up) */
+KGEB_API int kgeb_rows_scatter_add(kgeb_ctx* ctx, float* G, int width, int ld, uint8_t* touched, const int32_t* idx, int64_t n,
+                          const float* src, kgeb_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

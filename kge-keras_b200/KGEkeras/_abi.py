@@ -55,6 +55,8 @@ PROTOTYPES = {
     "kgeb_query_prep": (_i, [_p, _p, _i64, _i64, _p, _p, _i64, _i, _p, _p]),
     "kgeb_target_scores": (_i, [_p, _p, _i64, _i64, _p, _p, _i64, _i, _p, _p]),
     "kgeb_rank_1n": (_i, [_p, _p, _i64, _i64, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),
+    "kgeb_rows_gather": (_i, [_p, _p, _i, _i, _p, _i64, _p, _p]),
+    "kgeb_rows_scatter_add": (_i, [_p, _p, _i, _i, _p, _p, _i64, _p, _p]),
     "kgeb_rank_tc_packed_bytes": (_i64, [_p, _i64, _i]),
     "kgeb_rank_tc_pack_entities": (_i, [_p, _p, _i64, _i, _p, _i64, _p]),
     "kgeb_rank_tc_workspace_bytes": (_i64, [_p, _i64, _i, _i64]),

@@ -70,3 +70,52 @@ def test_shard_rows_covers_everything():
             parts = [shard_rows(N, world, r) for r in range(world)]
             assert parts[0][0] == 0 and parts[-1][1] == N
             assert all(a[1] == b[0] for a, b in zip(parts, parts[1:])) and all(a[0] <= a[1] for a in parts)
+
+
+# ---- row-sharded training: exchange plan + all-to-all on gloo, compute by the oracle ---------------------------------
+def _shard_train_worker(rank, world, port, ret):
+    import sys
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    for p in (root, os.path.join(root, "kge-keras_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from KGEkeras import _sharded as sh, utils as ku
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    kind, N, R, W, B, K, lr = ko.DISTMULT, 61, 3, 8, 12, 3, 0.1
+    rng = np.random.default_rng(0)                       # the same full tables on every rank
+    E, Rm = ko.glorot_uniform(rng, N, W) * 3, ko.glorot_uniform(rng, R, W) * 3
+    pos_all = np.stack([rng.integers(0, N, world * B), rng.integers(0, R, world * B), rng.integers(0, N, world * B)], 1)
+    neg_all = ko.philox_negatives(pos_all, N, K, 5, 0, ko.CORRUPT_BOTH)
+    pos, neg = pos_all[rank * B:(rank + 1) * B], neg_all[rank * B * K:(rank + 1) * B * K]
+    r0, r1 = ku.shard_rows(N, world, rank)
+    E_shard, g_shard = E[r0:r1].astype(np.float64), np.zeros((r1 - r0, W))
+    ids = torch.from_numpy(np.concatenate([pos[:, 0], pos[:, 2], neg[:, 0], neg[:, 2]]))
+    plan = sh.ExchangePlan(ids, N)
+    # rows: owners -> requesters
+    send = torch.from_numpy(E_shard[plan.serve_local.numpy()])
+    Ec = torch.empty(plan.U, W, dtype=torch.float64)
+    sh.all_to_all_rows(Ec, send, plan.req_counts, plan.serve_counts)
+    ok = np.array_equal(Ec.numpy(), E.astype(np.float64)[plan.uniq.numpy()])
+    # the step on the compact table (oracle), mean folded by 1/world
+    w = ko.train_step(kind, ko.PAIRWISE_HINGE, ko.PAIRED, Ec.numpy(), Rm, plan.remap_triples(torch.from_numpy(pos)).numpy(),
+                      plan.remap_triples(torch.from_numpy(neg)).numpy(), K, 1.0, 12.0, ko.OPT_SGD, [], [], lr, 1)
+    back = torch.empty(len(plan.serve_local), W, dtype=torch.float64)
+    sh.all_to_all_rows(back, torch.from_numpy(w["gE"] / world), plan.serve_counts, plan.req_counts)
+    np.add.at(g_shard, plan.serve_local.numpy(), back.numpy())
+    gR = torch.from_numpy(w["gR"] / world)
+    dist.all_reduce(gR)
+    E_new = E_shard - lr * g_shard
+    # single-process truth: one step over the concatenated batch
+    full = ko.train_step(kind, ko.PAIRWISE_HINGE, ko.PAIRED, E, Rm, pos_all, neg_all, K, 1.0, 12.0, ko.OPT_SGD, [], [], lr, 1)
+    ok = ok and np.allclose(E_new, full["E"][r0:r1], rtol=1e-12, atol=1e-14) and np.allclose(gR.numpy(), full["gR"], rtol=1e-12, atol=1e-14)
+    ok = ok and sum(plan.req_counts) == plan.U and len(plan.serve_local) == sum(plan.serve_counts)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_training_exchange_equals_single_process_step(world):
+    ret = mp.Manager().dict()
+    mp.spawn(_shard_train_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert len(ret) == world and all(ret.values()), dict(ret)
