@@ -89,7 +89,14 @@ typedef enum { KGEB_TIMED_RANK_TC = 0, KGEB_TIMED_RANK_REFINE = 1, KGEB_TIMED_RA
 KGEB_API int kgeb_set_kernel_timing(kgeb_ctx* ctx, int on);
 KGEB_API int kgeb_last_kernel_ms(kgeb_ctx* ctx, int which, float* ms);
 
-/* ---- scoring: EmbeddingModel.call + func, models.py:134-162 (dropout inactive) ---------------------------- */
+/* ---- dropout, models.py:122,144-150: Dropout(dp) on each gathered s / p / o row while training ----------------------
+ * p > 0 arms it for the following score_fwd / score_bwd / train_fwd_bwd calls of this context (p = 0 disarms: predict,
+ * validate).  Masks are counter-based (Philox4x32-10 keyed by seed, offset = step): forward and backward regenerate
+ * the same mask; 16 bits per element, so the effective rate is round(p*65536)/65536.  stream_id separates the masks of
+ * the model's positive call (0) from its negative call (1) for score_fwd/score_bwd; train_fwd_bwd uses both itself. */
+KGEB_API int kgeb_set_dropout(kgeb_ctx* ctx, float p, uint64_t seed, uint64_t offset, int stream_id);
+
+/* ---- scoring: EmbeddingModel.call + func, models.py:134-162 ------------------------------------------------------- */
 /* scores[m] = func(E[idx[:,0]], R[idx[:,1]], E[idx[:,2]]) */
 KGEB_API int kgeb_score_fwd(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* idx, int64_t m, float* scores,
                    kgeb_stream stream);

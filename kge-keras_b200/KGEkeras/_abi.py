@@ -44,6 +44,7 @@ PROTOTYPES = {
     "kgeb_num_sms": (_i, [_p]),
     "kgeb_set_kernel_timing": (_i, [_p, _i]),
     "kgeb_last_kernel_ms": (_i, [_p, _i, C.POINTER(_f)]),
+    "kgeb_set_dropout": (_i, [_p, _f, _u64, _u64, _i]),
     "kgeb_score_fwd": (_i, [_p, _p, _p, _p, _i64, _p, _p]),
     "kgeb_score_bwd": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p]),
     "kgeb_negatives": (_i, [_p, _p, _i64, _i, _u64, _u64, _i, _p, _p]),

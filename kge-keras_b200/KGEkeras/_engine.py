@@ -111,20 +111,38 @@ class Engine:
             self.opt_state = (opt_kind,) + st
             self.step = 0
 
+    # ---- dropout ------------------------------------------------------------------------------------------------
+    def set_dropout(self, p=0.0, seed=0, offset=0, stream_id=0):
+        """models.py:122,144-150: arm (p > 0) or disarm (p = 0) dropout for the next scoring / training calls."""
+        self._check(self.lib.kgeb_set_dropout(self.ctx, float(p), int(seed), int(offset), int(stream_id)))
+
     # ---- scoring ------------------------------------------------------------------------------------------------
-    def score(self, idx, out=None):
+    def score(self, idx, out=None, dropout=None):
+        """dropout = (p, seed, offset, stream_id) scores the dropped rows of a training-mode call; None = inference."""
         idx = as_idx(idx, self.device)
         m = idx.shape[0]
         out = torch.empty(m, dtype=torch.float32, device=self.device) if out is None else out
-        self._check(self.lib.kgeb_score_fwd(self.ctx, _ptr(self.E), _ptr(self.Rel), _ptr(idx), m, _ptr(out), _stream()))
+        if dropout is not None:
+            self.set_dropout(*dropout)
+        try:
+            self._check(self.lib.kgeb_score_fwd(self.ctx, _ptr(self.E), _ptr(self.Rel), _ptr(idx), m, _ptr(out), _stream()))
+        finally:
+            if dropout is not None:
+                self.set_dropout(0.0)
         return out
 
-    def score_bwd(self, idx, dscore):
+    def score_bwd(self, idx, dscore, dropout=None):
         idx = as_idx(idx, self.device)
         self._ensure_train_buffers(self.opt_state[0] if self.opt_state else abi.SGD)
         dscore = dscore.to(device=self.device, dtype=torch.float32).contiguous()
-        self._check(self.lib.kgeb_score_bwd(self.ctx, _ptr(self.E), _ptr(self.Rel), _ptr(idx), idx.shape[0], _ptr(dscore),
-                                            _ptr(self.gE), _ptr(self.gR), _ptr(self.tE), _ptr(self.tR), _stream()))
+        if dropout is not None:
+            self.set_dropout(*dropout)
+        try:
+            self._check(self.lib.kgeb_score_bwd(self.ctx, _ptr(self.E), _ptr(self.Rel), _ptr(idx), idx.shape[0], _ptr(dscore),
+                                                _ptr(self.gE), _ptr(self.gR), _ptr(self.tE), _ptr(self.tR), _stream()))
+        finally:
+            if dropout is not None:
+                self.set_dropout(0.0)
 
     def negatives(self, pos, K, seed, offset, corrupt_mode=abi.CORRUPT_BOTH):
         pos = as_idx(pos, self.device)
@@ -145,8 +163,10 @@ class Engine:
     # ---- training -----------------------------------------------------------------------------------------------
     def forward_backward(self, pos, neg=None, K=1, loss_kind=abi.PAIRWISE_HINGE, pair_mode=abi.PAIRED, margin=1.0,
                          loss_weight=1.0, corrupt_mode=abi.CORRUPT_BOTH, seed=0, offset=0, want_scores=False,
-                         want_neg=False, force_unfused=False, opt_kind=abi.ADAM_DENSE):
-        """Scores, loss and gradient scatter of one batch (no parameter update).  Returns a dict of device tensors."""
+                         want_neg=False, force_unfused=False, opt_kind=abi.ADAM_DENSE, dropout=0.0):
+        """Scores, loss and gradient scatter of one batch (no parameter update).  Returns a dict of device tensors.
+        dropout > 0 applies Dropout(dp) to every gathered row (masks keyed by seed / offset, independent for the positive
+        and the negative call, models.py:144-150)."""
         pos = as_idx(pos, self.device)
         B = pos.shape[0]
         if neg is not None:
@@ -165,18 +185,26 @@ class Engine:
             ps = torch.empty(B, dtype=torch.float32, device=self.device) if want_scores else None
             ns = torch.empty(B * K, dtype=torch.float32, device=self.device) if want_scores else None
             no = torch.empty(B * K, 3, dtype=torch.int32, device=self.device) if (want_neg and neg is None) else None
-            self._check(self.lib.kgeb_train_fwd_bwd(
-                self.ctx, _ptr(self.E), _ptr(self.Rel), _ptr(pos), B, _ptr(neg), K, loss_kind, margin, loss_weight,
-                corrupt_mode, seed, offset, _ptr(self._loss), _ptr(ps), _ptr(ns), _ptr(no), _ptr(self.gE), _ptr(self.gR),
-                _ptr(self.tE), _ptr(self.tR), _stream()))
+            if dropout:
+                self.set_dropout(dropout, seed, offset, 0)
+            try:
+                self._check(self.lib.kgeb_train_fwd_bwd(
+                    self.ctx, _ptr(self.E), _ptr(self.Rel), _ptr(pos), B, _ptr(neg), K, loss_kind, margin, loss_weight,
+                    corrupt_mode, seed, offset, _ptr(self._loss), _ptr(ps), _ptr(ns), _ptr(no), _ptr(self.gE), _ptr(self.gR),
+                    _ptr(self.tE), _ptr(self.tR), _stream()))
+            finally:
+                if dropout:
+                    self.set_dropout(0.0)
             res.update(loss=self._loss, pos_scores=ps, neg_scores=ns, neg=neg if neg is not None else no)
         else:
             if neg is None:
                 neg = self.negatives(pos, K, seed, offset, corrupt_mode)
-            t, f = self.score(pos), self.score(neg)
+            dpos = (dropout, seed, offset, 0) if dropout else None
+            dneg = (dropout, seed, offset, 1) if dropout else None
+            t, f = self.score(pos, dropout=dpos), self.score(neg, dropout=dneg)
             loss, dt, df = self.loss(t, f, K, loss_kind, pair_mode, margin, loss_weight)
-            self.score_bwd(pos, dt)
-            self.score_bwd(neg, df)
+            self.score_bwd(pos, dt, dropout=dpos)
+            self.score_bwd(neg, df, dropout=dneg)
             res.update(loss=loss, pos_scores=t, neg_scores=f, neg=neg)
         return res
 

@@ -155,7 +155,11 @@ class EmbeddingModel:
 
     # ---- forward -----------------------------------------------------------------------------------------------
     def call(self, inputs, training=False):
-        """inputs: (batch, 3) ids (int or the harness' float32) -> (batch,) scores as a CUDA torch tensor."""
+        """inputs: (batch, 3) ids (int or the harness' float32) -> (batch,) scores as a CUDA torch tensor.
+        training=True applies Dropout(dp) to the gathered rows (models.py:144-150) with a fresh mask per call."""
+        if training and self.dp.rate > 0:
+            self._call_counter = getattr(self, "_call_counter", 0) + 1
+            return self._engine_().score(inputs, dropout=(self.dp.rate, self._seed ^ 0x5EED, 2 ** 41 + self._call_counter, 0))
         return self._engine_().score(inputs)
 
     __call__ = call
@@ -187,9 +191,6 @@ class EmbeddingModel:
         return abi.LOSS_KINDS[self.loss_function]
 
     def _step_kwargs(self):
-        if self.dp.rate > 0 and not getattr(self, "_warned_dp", False):
-            warnings.warn(f"dropout dp={self.dp.rate} is not applied by the B200 kernels yet; training runs with dp=0")
-            self._warned_dp = True
         return dict(loss_kind=self._loss_kind(), margin=float(self.margin if self.margin is not None else 1), loss_weight=float(self.loss_weight),
                     pair_mode={'paired': abi.PAIRED, 'allpairs': abi.ALLPAIRS}[self.pair_mode],
                     corrupt_mode={'both': abi.CORRUPT_BOTH, 'head': abi.CORRUPT_HEAD, 'tail': abi.CORRUPT_TAIL,
@@ -210,7 +211,7 @@ class EmbeddingModel:
         self._step_counter += 1
         res = self._engine_().train_step(pos, neg, opt_kind=o.kind, lr=o.lr, beta1=o.beta1, beta2=o.beta2, eps=o.eps,
                                          K=int(self.negative_samples), seed=self._seed, offset=self._step_counter,
-                                         l3=float(self.regularization),
+                                         l3=float(self.regularization), dropout=float(self.dp.rate),
                                          **self._step_kwargs())
         return res["loss"]
 

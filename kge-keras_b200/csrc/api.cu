@@ -80,3 +80,14 @@ extern "C" int kgeb_last_kernel_ms(kgeb_ctx* ctx, int which, float* ms) {
   KGEB_CUDA_OK(ctx, cudaEventElapsedTime(ms, ctx->ev[which][0], ctx->ev[which][1]));
   return KGEB_OK;
 }
+
+extern "C" int kgeb_set_dropout(kgeb_ctx* ctx, float p, uint64_t seed, uint64_t offset, int stream_id) {
+  if (!ctx) return KGEB_ERR_INVALID;
+  KGEB_REQUIRE(ctx, p >= 0.f && p < 1.f, KGEB_ERR_INVALID, "dropout rate must be in [0, 1)");
+  KGEB_REQUIRE(ctx, stream_id == 0 || stream_id == 1, KGEB_ERR_INVALID, "dropout stream id is 0 (positive call) or 1 (negative call)");
+  const double thr = (double)p * 65536.0 + 0.5;
+  ctx->dp_thr = (uint32_t)thr;
+  ctx->dp_scale = 1.0f / (1.0f - p);
+  ctx->dp_seed = seed; ctx->dp_offset = offset; ctx->dp_stream = stream_id;
+  return KGEB_OK;
+}

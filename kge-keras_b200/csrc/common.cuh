@@ -24,6 +24,8 @@ struct kgeb_ctx {
   // fixed scratch, allocated once in kgeb_create (nothing allocates afterwards)
   double* d_partials;        // [KGEB_MAX_PARTIAL_BLOCKS * 2] per-block loss partial sums
   unsigned int* d_ticket;    // last-block-done counter (self-resetting)
+  // dropout state (kgeb_set_dropout): thr = round(dp * 65536), 0 = off
+  uint32_t dp_thr; float dp_scale; uint64_t dp_seed, dp_offset; int dp_stream;
   // optional kernel timing (kgeb_set_kernel_timing): events recorded on the caller's stream around selected launches
   int timing;
   cudaEvent_t ev[KGEB_TIMED_KERNELS][2];

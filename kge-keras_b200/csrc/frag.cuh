@@ -145,8 +145,67 @@ __device__ __forceinline__ void score_grads(const Frag<KIND, NC>& s, const Frag<
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Dropout (models.py:122,144-150): an independent Bernoulli(1-dp) keep mask on every gathered s / p / o row of every
+// model call, kept values scaled by 1/(1-dp).  Counter-based so forward, backward and the host restatement
+// (oracle.kge_oracle.dropout_keep) agree without storing masks: 16 random bits per element, keep iff bits >= thr,
+// thr = round(dp * 65536).  One Philox4x32-10 call covers two of a lane's 128-bit chunks:
+//   counter = (32*call + lane, slot | stream<<2 | offset<<3, lo32(g), hi32(g) ^ (offset>>29)),  key = (lo32(seed)^'DROP', hi32(seed))
+// slot 0/1/2 = s/p/o, stream 0 = the positive call, 1 = the negative call, g = index of the triple in its call.
+// ---------------------------------------------------------------------------------------------------
+struct DropArgs {
+  uint32_t thr;   // 0 = dropout off
+  float scale;    // 1 / (1 - dp)
+  uint32_t k0, k1, ylo, whi;
+};
+
+__device__ __forceinline__ uint4 dp_philox(const DropArgs& d, int slot, int stream, uint64_t g, int lane, int call) {
+  return philox4x32_10(make_uint4((uint32_t)(32 * call + lane), d.ylo | (uint32_t)slot | ((uint32_t)stream << 2), (uint32_t)g,
+                                  (uint32_t)(g >> 32) ^ d.whi),
+                       make_uint2(d.k0, d.k1));
+}
+__device__ __forceinline__ uint32_t dp_word(const uint4& r, int h, int e) { return h ? (e < 2 ? r.z : r.w) : (e < 2 ? r.x : r.y); }
+
+// keep bits of this lane's fragment of one row instance: bit 4*t + e for chunk slot t, component e
+template <int KIND, int NC>
+__device__ __forceinline__ uint32_t dp_bits(const DropArgs& d, int slot, int stream, uint64_t g, int lane) {
+  constexpr int NT = Frag<KIND, NC>::NT;
+  uint32_t bits = 0;
+#pragma unroll
+  for (int c = 0; c < (NT + 1) / 2; ++c) {
+    const uint4 r = dp_philox(d, slot, stream, g, lane, c);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int t = 2 * c + h;
+      if (t < NT) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t u = (dp_word(r, h, e) >> (16 * (e & 1))) & 0xFFFFu;
+          bits |= (u >= d.thr ? 1u : 0u) << (4 * t + e);
+        }
+      }
+    }
+  }
+  return bits;
+}
+// f <- f * keep * scale (forward on gathered rows, backward on gradient rows: the same linear map)
+template <int KIND, int NC>
+__device__ __forceinline__ void dp_apply(Frag<KIND, NC>& f, uint32_t bits, float scale) {
+#pragma unroll
+  for (int t = 0; t < Frag<KIND, NC>::NT; ++t) {
+    KGEB_FOR4({ comp(f.v[t], _e) = ((bits >> (4 * t + _e)) & 1u) ? __fmul_rn(comp(f.v[t], _e), scale) : 0.f; })
+  }
+}
+// element-wise form (HolE staging): x = element index in a plain (non-ComplEx) row
+__device__ __forceinline__ bool dp_keep_elem(const DropArgs& d, int slot, int stream, uint64_t g, int x) {
+  const int chunk = x >> 2, e = x & 3, t = chunk >> 5;
+  const uint4 r = dp_philox(d, slot, stream, g, chunk & 31, t >> 1);
+  return ((dp_word(r, t & 1, e) >> (16 * (e & 1))) & 0xFFFFu) >= d.thr;
+}
+
 struct ScoreArgs {
   const float* E; const float* R; int ldE, ldR; RowGeom ge, gr; float gamma;
+  DropArgs dp; int dp_stream;
 };
 
 struct TrainArgs {
@@ -185,6 +244,10 @@ ScoreArgs make_score_args(const kgeb_ctx* ctx, const float* E, const float* R, i
   }
   a.gr = a.ge;
   *nc_out = (a.ge.nch + 31) / 32;
+  a.dp.thr = ctx->dp_thr; a.dp.scale = ctx->dp_scale;
+  a.dp.k0 = (uint32_t)ctx->dp_seed ^ 0x44524F50u; a.dp.k1 = (uint32_t)(ctx->dp_seed >> 32);
+  a.dp.ylo = (uint32_t)(ctx->dp_offset << 3); a.dp.whi = (uint32_t)(ctx->dp_offset >> 29);
+  a.dp_stream = ctx->dp_stream;
   return a;
 }
 

@@ -13,7 +13,7 @@ namespace {
 // ---------------------------------------------------------------------------------------------------
 // score_fwd: one warp per triple
 // ---------------------------------------------------------------------------------------------------
-template <int KIND, int NC>
+template <int KIND, int NC, bool DP>
 __global__ void __launch_bounds__(KGEB_THREADS) k_score_fwd(ScoreArgs a, const int32_t* __restrict__ idx, int64_t m,
                                                             float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
@@ -24,6 +24,11 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_score_fwd(ScoreArgs a, const i
     load_frag(S, a.E, s, a.ldE, a.ge, lane);
     load_frag(P, a.R, p, a.ldR, a.gr, lane);
     load_frag(O, a.E, o, a.ldE, a.ge, lane);
+    if (DP) {
+      dp_apply(S, dp_bits<KIND, NC>(a.dp, 0, a.dp_stream, (uint64_t)t, lane), a.dp.scale);
+      dp_apply(P, dp_bits<KIND, NC>(a.dp, 1, a.dp_stream, (uint64_t)t, lane), a.dp.scale);
+      dp_apply(O, dp_bits<KIND, NC>(a.dp, 2, a.dp_stream, (uint64_t)t, lane), a.dp.scale);
+    }
     const float sum = warp_sum(score_partial(S, P, O));
     if (lane == 0) out[t] = score_finish<KIND>(sum, a.gamma);
   }
@@ -32,7 +37,7 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_score_fwd(ScoreArgs a, const i
 // ---------------------------------------------------------------------------------------------------
 // score_bwd: one warp per triple, gradient rows leave as vector reductions
 // ---------------------------------------------------------------------------------------------------
-template <int KIND, int NC>
+template <int KIND, int NC, bool DP>
 __global__ void __launch_bounds__(KGEB_THREADS) k_score_bwd(ScoreArgs a, const int32_t* __restrict__ idx, int64_t m,
                                                             const float* __restrict__ dscore, float* gE, float* gR,
                                                             uint8_t* tE, uint8_t* tR) {
@@ -47,9 +52,17 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_score_bwd(ScoreArgs a, const i
     load_frag(S, a.E, s, a.ldE, a.ge, lane);
     load_frag(P, a.R, p, a.ldR, a.gr, lane);
     load_frag(O, a.E, o, a.ldE, a.ge, lane);
+    uint32_t mS = 0, mP = 0, mO = 0;
+    if (DP) {
+      mS = dp_bits<KIND, NC>(a.dp, 0, a.dp_stream, (uint64_t)t, lane);
+      mP = dp_bits<KIND, NC>(a.dp, 1, a.dp_stream, (uint64_t)t, lane);
+      mO = dp_bits<KIND, NC>(a.dp, 2, a.dp_stream, (uint64_t)t, lane);
+      dp_apply(S, mS, a.dp.scale); dp_apply(P, mP, a.dp.scale); dp_apply(O, mO, a.dp.scale);
+    }
     float sum = 0.f;
     if (KIND == TRANSE_L2) sum = warp_sum(score_partial(S, P, O));
     score_grads(S, P, O, coef, sum, a.gamma, GS, GP, GO);
+    if (DP) { dp_apply(GS, mS, a.dp.scale); dp_apply(GP, mP, a.dp.scale); dp_apply(GO, mO, a.dp.scale); }
     red_frag(gE, s, a.ldE, a.ge, lane, GS);
     red_frag(gR, p, a.ldR, a.gr, lane, GP);
     red_frag(gE, o, a.ldE, a.ge, lane, GO);
@@ -59,8 +72,13 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_score_bwd(ScoreArgs a, const i
 // ---------------------------------------------------------------------------------------------------
 // HolE: f = sum_k p_k sum_i s_i o_{(i+k) mod d}; rows staged in shared memory, O(d^2/32) per lane
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void hole_stage(float* dst, const float* __restrict__ src, int d, int lane) {
-  for (int i = lane; i < d; i += 32) dst[i] = __ldg(src + i);
+__device__ __forceinline__ void hole_stage(float* dst, const float* __restrict__ src, int d, int lane, const DropArgs& dp, int slot,
+                                           int stream, uint64_t g) {
+  for (int i = lane; i < d; i += 32) {
+    float v = __ldg(src + i);
+    if (dp.thr) v = dp_keep_elem(dp, slot, stream, g, i) ? __fmul_rn(v, dp.scale) : 0.f;
+    dst[i] = v;
+  }
 }
 
 __global__ void __launch_bounds__(KGEB_THREADS) k_hole_fwd(ScoreArgs a, int d, const int32_t* __restrict__ idx, int64_t m,
@@ -73,8 +91,8 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_hole_fwd(ScoreArgs a, int d, c
   for (int64_t t = (int64_t)blockIdx.x * KGEB_WARPS_PER_BLOCK + w; t < m; t += nw) {
     const int s = __ldg(idx + 3 * t), p = __ldg(idx + 3 * t + 1), o = __ldg(idx + 3 * t + 2);
     __syncwarp();
-    hole_stage(ss, a.E + (int64_t)s * a.ldE, d, lane);
-    hole_stage(so, a.E + (int64_t)o * a.ldE, d, lane);
+    hole_stage(ss, a.E + (int64_t)s * a.ldE, d, lane, a.dp, 0, a.dp_stream, (uint64_t)t);
+    hole_stage(so, a.E + (int64_t)o * a.ldE, d, lane, a.dp, 2, a.dp_stream, (uint64_t)t);
     __syncwarp();
     const float* pr = a.R + (int64_t)p * a.ldR;
     float acc = 0.f;
@@ -85,7 +103,9 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_hole_fwd(ScoreArgs a, int d, c
         x = fmaf(ss[i], so[j], x);
         if (++j == d) j = 0;
       }
-      acc = fmaf(__ldg(pr + k), x, acc);
+      float pv = __ldg(pr + k);
+      if (a.dp.thr) pv = dp_keep_elem(a.dp, 1, a.dp_stream, (uint64_t)t, k) ? __fmul_rn(pv, a.dp.scale) : 0.f;
+      acc = fmaf(pv, x, acc);
     }
     acc = warp_sum(acc);
     if (lane == 0) out[t] = acc;
@@ -107,9 +127,9 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_hole_bwd(ScoreArgs a, int d, c
     if (lane == 0) { tE[s] = 1; tE[o] = 1; tR[p] = 1; }
     if (coef == 0.f) continue;
     __syncwarp();
-    hole_stage(ss, a.E + (int64_t)s * a.ldE, d, lane);
-    hole_stage(sp, a.R + (int64_t)p * a.ldR, d, lane);
-    hole_stage(so, a.E + (int64_t)o * a.ldE, d, lane);
+    hole_stage(ss, a.E + (int64_t)s * a.ldE, d, lane, a.dp, 0, a.dp_stream, (uint64_t)t);
+    hole_stage(sp, a.R + (int64_t)p * a.ldR, d, lane, a.dp, 1, a.dp_stream, (uint64_t)t);
+    hole_stage(so, a.E + (int64_t)o * a.ldE, d, lane, a.dp, 2, a.dp_stream, (uint64_t)t);
     __syncwarp();
     float* gs = gE + (int64_t)s * a.ldE;
     float* gp = gR + (int64_t)p * a.ldR;
@@ -126,9 +146,15 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_hole_bwd(ScoreArgs a, int d, c
         if (++jf == d) jf = 0;
         if (--jb < 0) jb = d - 1;
       }
-      atomicAdd(gp + k, coef * xp);
-      atomicAdd(gs + k, coef * xs);
-      atomicAdd(go + k, coef * xo);
+      float cp = coef, cs = coef, co = coef;   // gradient wrt the raw rows = gradient wrt the dropped rows * keep * scale
+      if (a.dp.thr) {
+        cp = dp_keep_elem(a.dp, 1, a.dp_stream, (uint64_t)t, k) ? coef * a.dp.scale : 0.f;
+        cs = dp_keep_elem(a.dp, 0, a.dp_stream, (uint64_t)t, k) ? coef * a.dp.scale : 0.f;
+        co = dp_keep_elem(a.dp, 2, a.dp_stream, (uint64_t)t, k) ? coef * a.dp.scale : 0.f;
+      }
+      atomicAdd(gp + k, cp * xp);
+      atomicAdd(gs + k, cs * xs);
+      atomicAdd(go + k, co * xo);
     }
   }
 }
@@ -169,7 +195,11 @@ extern "C" int kgeb_score_fwd(kgeb_ctx* ctx, const float* E, const float* R, con
     KGEB_LAUNCH_OK(ctx);
     return KGEB_OK;
   }
-  KGEB_DISPATCH_KIND(ctx->kind, KGEB_DISPATCH_NC(nc, (k_score_fwd<KIND, NC><<<grid, KGEB_THREADS, 0, st>>>(a, idx, m, scores))));
+  if (a.dp.thr) {
+    KGEB_DISPATCH_KIND(ctx->kind, KGEB_DISPATCH_NC(nc, (k_score_fwd<KIND, NC, true><<<grid, KGEB_THREADS, 0, st>>>(a, idx, m, scores))));
+  } else {
+    KGEB_DISPATCH_KIND(ctx->kind, KGEB_DISPATCH_NC(nc, (k_score_fwd<KIND, NC, false><<<grid, KGEB_THREADS, 0, st>>>(a, idx, m, scores))));
+  }
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
 }
@@ -197,8 +227,13 @@ extern "C" int kgeb_score_bwd(kgeb_ctx* ctx, const float* E, const float* R, con
     KGEB_LAUNCH_OK(ctx);
     return KGEB_OK;
   }
-  KGEB_DISPATCH_KIND(ctx->kind, KGEB_DISPATCH_NC(nc, (k_score_bwd<KIND, NC><<<grid, KGEB_THREADS, 0, st>>>(
-                                                         a, idx, m, dscore, gE, gR, touchedE, touchedR))));
+  if (a.dp.thr) {
+    KGEB_DISPATCH_KIND(ctx->kind, KGEB_DISPATCH_NC(nc, (k_score_bwd<KIND, NC, true><<<grid, KGEB_THREADS, 0, st>>>(
+                                                           a, idx, m, dscore, gE, gR, touchedE, touchedR))));
+  } else {
+    KGEB_DISPATCH_KIND(ctx->kind, KGEB_DISPATCH_NC(nc, (k_score_bwd<KIND, NC, false><<<grid, KGEB_THREADS, 0, st>>>(
+                                                           a, idx, m, dscore, gE, gR, touchedE, touchedR))));
+  }
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
 }

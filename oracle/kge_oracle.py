@@ -577,3 +577,74 @@ def filter_csr(triples, side, filters):
         ids.extend(fl)
         offs[qi + 1] = len(ids)
     return offs, np.asarray(ids, dtype=np.int32)
+
+
+# --------------------------------------------------------------------------------------------
+# Dropout masks exactly as the kernels draw them (csrc/frag.cuh: dp_bits / dp_keep_elem); models.py:122,144-150
+# --------------------------------------------------------------------------------------------
+def dropout_keep(kind, width, n, slot, stream, p, seed, offset):
+    """(n, width) bool keep mask of row-slot `slot` (0/1/2 = s/p/o) for the n triples of call `stream` (0 = positive call,
+    1 = negative call).  16 Philox bits per element, keep iff bits >= round(p*65536).  `width` = stored row width."""
+    thr = int(p * 65536.0 + 0.5)
+    if kind == COMPLEX:
+        d = width // 2
+        nch = d // 4
+    else:
+        d = width
+        nch = (width + 3) // 4
+    NC = (nch + 31) // 32
+    x = np.arange(width)
+    half = (x >= d).astype(np.int64) if kind == COMPLEX else np.zeros(width, np.int64)
+    xx = x - half * d
+    chunk, e = xx // 4, xx % 4
+    lane, i = chunk % 32, chunk // 32
+    t = i + half * NC
+    call, h = t // 2, t % 2
+    g = np.arange(n, dtype=np.uint64)
+    ctr = np.zeros((n, width, 4), np.uint32)
+    ctr[..., 0] = (32 * call + lane).astype(np.uint32)[None, :]
+    ctr[..., 1] = np.uint32(((int(offset) << 3) & 0xFFFFFFFF) | slot | (stream << 2))
+    ctr[..., 2] = (g & np.uint64(0xFFFFFFFF)).astype(np.uint32)[:, None]
+    ctr[..., 3] = ((g >> np.uint64(32)).astype(np.uint32) ^ np.uint32((int(offset) >> 29) & 0xFFFFFFFF))[:, None]
+    key = np.zeros((n, width, 2), np.uint32)
+    key[..., 0] = np.uint32((int(seed) & 0xFFFFFFFF) ^ 0x44524F50)
+    key[..., 1] = np.uint32((int(seed) >> 32) & 0xFFFFFFFF)
+    r = philox4x32_10(ctr, key)
+    word_idx = (2 * h + (e >= 2)).astype(np.int64)        # h ? (e<2 ? z : w) : (e<2 ? x : y)
+    word = np.take_along_axis(r, np.broadcast_to(word_idx[None, :, None], (n, width, 1)), axis=2)[..., 0]
+    u = (word >> (16 * (e % 2)).astype(np.uint32)[None, :]) & np.uint32(0xFFFF)
+    return u >= thr
+
+
+def dropout_mult(kind, width, n, slot, stream, p, seed, offset, dtype=np.float64):
+    """keep * fp32(1/(1-p)) as an (n, width) multiplier: forward x*mult, backward grad*mult."""
+    keep = dropout_keep(kind, width, n, slot, stream, p, seed, offset)
+    scale = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
+    return keep.astype(dtype) * dtype(scale)
+
+
+def train_step_dropout(kind, loss_kind, E, R, pos, neg, K, margin, gamma, p, seed, offset, dtype=np.float64):
+    """Forward + dense gradients of one PAIRED step with Dropout(p) on every gathered row (independent masks for the
+    positive call, stream 0, and the negative call, stream 1).  Returns loss, scores, gE, gR."""
+    E, R = E.astype(dtype), R.astype(dtype)
+    We, Wr = E.shape[1], R.shape[1]
+    out = {}
+    rows, mults = [], []
+    for stream, idx in ((0, np.asarray(pos)), (1, np.asarray(neg))):
+        s, pr, o = gather(E, R, idx)
+        ms = dropout_mult(kind, We, len(idx), 0, stream, p, seed, offset, dtype)
+        mp = dropout_mult(kind, Wr, len(idx), 1, stream, p, seed, offset, dtype)
+        mo = dropout_mult(kind, We, len(idx), 2, stream, p, seed, offset, dtype)
+        rows.append((s * ms, pr * mp, o * mo))
+        mults.append((ms, mp, mo))
+    t = score(kind, *rows[0], gamma, hole_fft=False)
+    f = score(kind, *rows[1], gamma, hole_fft=False)
+    L, dt_, df_ = loss_and_coefs(loss_kind, PAIRED, t, f, K, margin)
+    gE, gR = np.zeros(E.shape, dtype), np.zeros(R.shape, dtype)
+    for (s, pr, o), (ms, mp, mo), idx, dsc in ((rows[0], mults[0], np.asarray(pos), dt_), (rows[1], mults[1], np.asarray(neg), df_)):
+        ds, dp_, do = score_grads(kind, s, pr, o, gamma)
+        w = np.asarray(dsc, dtype)[:, None]
+        np.add.at(gE, idx[:, 0].astype(np.int64), w * ds * ms)
+        np.add.at(gE, idx[:, 2].astype(np.int64), w * do * mo)
+        np.add.at(gR, idx[:, 1].astype(np.int64), w * dp_ * mp)
+    return dict(loss=L, pos_scores=t, neg_scores=f, gE=gE, gR=gR)
