@@ -140,11 +140,10 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_train_ring(TrainArgs a, int D,
       np = MODE == 0 ? __shfl_sync(0xffffffffu, in_cur ? my_np : ah_np, l) : p;
       hs = MODE == 2 ? __shfl_sync(0xffffffffu, in_cur ? my_hs : ah_hs, l) : 0;
     };
-    auto issue = [&](int j) {
+    auto issue = [&](int j, int st) {   // st = ring stage of negative j, tracked by the callers (a runtime modulo costs ~30 instructions)
       int ns, np, no, hs;
       ids_of(j, ns, np, no, hs);
       if (lane == 0) {
-        const int st = j % D;
         unsigned char* sb = ring + (size_t)(SR * st) * RB;
         uint64_t* bar = bars + 1 + st;
         if (MODE == 1) {
@@ -166,7 +165,7 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_train_ring(TrainArgs a, int D,
       }
     };
     const int prime = K < D ? K : D;
-    for (int j = 0; j < prime; ++j) issue(j);
+    for (int j = 0; j < prime; ++j) issue(j, j);
 
     // positive score
     mbar_wait(bars, phases & 1u);
@@ -202,14 +201,15 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_train_ring(TrainArgs a, int D,
     zero_frag(AS); zero_frag(AP); zero_frag(AO);
     bool usedS = false, usedP = false, usedO = false;
 
+    int st = -1;  // ring stage of negative j
     for (int j = 0; j < K; ++j) {
+      if (++st == D) st = 0;
       if ((j & 31) == 0 && j > 0) {  // crossed into the "ahead" chunk: rotate, then draw the chunk after it
         cur_chunk = j >> 5; my_ns = ah_ns; my_np = ah_np; my_no = ah_no; my_hs = ah_hs;
         if ((cur_chunk + 1) * 32 < K) compute_chunk(cur_chunk + 1, ah_ns, ah_np, ah_no, ah_hs);
       }
       int ns, np, no, hs;
       ids_of(j, ns, np, no, hs);
-      const int st = j % D;
       const unsigned char* sb = ring + (size_t)(SR * st) * RB;
       const float *rS, *rP, *rO;
       bool shS, shP, shO;  // row shared with the positive (warp-uniform)
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_train_ring(TrainArgs a, int D,
       }
       const float fsum = warp_sum(score_partial(Sn, Pn, On));
       // the butterfly consumed every lane's loads of this stage, so the stage can be refilled for negative j + D
-      if (j + D < K) issue(j + D);
+      if (j + D < K) issue(j + D, st);
       const float f = score_finish<KIND>(fsum, gamma);
       float cneg;
       if (pairwise) {
