@@ -110,6 +110,12 @@ KGEB_API int kgeb_score_bwd(kgeb_ctx* ctx, const float* E, const float* R, const
 KGEB_API int kgeb_negatives(kgeb_ctx* ctx, const int32_t* pos, int64_t B, int K, uint64_t seed, uint64_t offset,
                    int corrupt_mode, int32_t* neg, kgeb_stream stream);
 
+/* ---- oversampling: oversample_data utils.py:123-147 (random.choices with replacement) as a device sampler ----------
+ * dst[i,:] = src[u_i,:], u_i = floor(Philox4x32-10(counter=(i, offset), key=seed^'OVRS', stream_id).x * n / 2^32), i < m.
+ * The harness (tests.py:55-61) resamples the positive list (stream 0) and the negative list (stream 1) to a common length. */
+KGEB_API int kgeb_oversample(kgeb_ctx* ctx, const int32_t* src, int64_t n, int64_t m, uint64_t seed, uint64_t offset, int stream_id,
+                    int32_t* dst, kgeb_stream stream);
+
 /* ---- losses on score vectors: utils.py:288-319 ------------------------------------------------------------ */
 /* loss[0] = loss_weight * L(t, f); dt[B], df[Bf] = loss_weight * dL/dt, dL/df (either may be NULL).
  * Bf must be B*K for PAIRED pairwise kinds. */

@@ -48,6 +48,7 @@ PROTOTYPES = {
     "kgeb_score_fwd": (_i, [_p, _p, _p, _p, _i64, _p, _p]),
     "kgeb_score_bwd": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p]),
     "kgeb_negatives": (_i, [_p, _p, _i64, _i, _u64, _u64, _i, _p, _p]),
+    "kgeb_oversample": (_i, [_p, _p, _i64, _i64, _u64, _u64, _i, _p, _p]),
     "kgeb_loss_fwd_bwd": (_i, [_p, _p, _i64, _p, _i64, _i, _i, _i, _f, _f, _p, _p, _p, _p]),
     "kgeb_train_fwd_bwd": (_i, [_p, _p, _p, _p, _i64, _p, _i, _i, _f, _f, _i, _u64, _u64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "kgeb_l3_reg": (_i, [_p, _p, _i64, _i, _i, _f, _p, _p, _p, _p]),

@@ -150,6 +150,22 @@ class Engine:
         self._check(self.lib.kgeb_negatives(self.ctx, _ptr(pos), pos.shape[0], K, seed, offset, corrupt_mode, _ptr(neg), _stream()))
         return neg
 
+    def oversample(self, src, m, seed, offset, stream_id=0):
+        """oversample_data (utils.py:123-147) on the device: m rows drawn from src with replacement."""
+        src = as_idx(src, self.device)
+        dst = torch.empty(int(m), 3, dtype=torch.int32, device=self.device)
+        self._check(self.lib.kgeb_oversample(self.ctx, _ptr(src), src.shape[0], int(m), seed, offset, stream_id, _ptr(dst), _stream()))
+        return dst
+
+    def device_batch(self, kg_batch, negative, seed, step):
+        """The harness' DataGenerator.__get_data (tests.py:55-61) without leaving the GPU: generate_negative (both slots
+        corrupted, relation kept) followed by oversample_data of both lists to the common length m = negative*len(batch).
+        Returns [pos (m,3), neg (m,3)] int32 device tensors -- the unaligned lists the reference feeds its all-pairs loss."""
+        pos = as_idx(kg_batch, self.device)
+        neg = self.negatives(pos, int(negative), seed, step, abi.CORRUPT_BOTH)
+        m = max(pos.shape[0], neg.shape[0])
+        return [self.oversample(pos, m, seed, step, 0), self.oversample(neg, m, seed, step, 1)]
+
     def loss(self, t, f, K, loss_kind, pair_mode, margin, loss_weight=1.0, want_grads=True):
         t = t.to(device=self.device, dtype=torch.float32).contiguous().view(-1)
         f = f.to(device=self.device, dtype=torch.float32).contiguous().view(-1)

@@ -114,23 +114,37 @@ def gen_head_data(test_data, num_entities, bs, filter_h):
 # ---- filtered evaluation (GPU) ---------------------------------------------------------------------------------
 def build_filter_csr(test, filtering_triples, side):
     """Sorted, de-duplicated known-true ids per query in CSR form (offsets int64[Q+1], ids int32[nnz]).
+    Replaces the dict-of-sets of utils.py:201-205 and the per-query list.remove of utils.py:169-171 by one sort of the
+    filter triples and two binary searches per query (vectorised; FB15k-237-sized inputs take milliseconds).
     Raises ValueError if a query's own target is in its filter set -- the reference crashes there (utils.py:169-171)."""
     filt = np.asarray(filtering_triples, dtype=np.int64).reshape(-1, 3)
     test = np.asarray(test, dtype=np.int64).reshape(-1, 3)
     kc = (0, 1) if side == "tail" else (1, 2)       # key columns: (s,p) for tail queries, (p,o) for head queries
     vc = 2 if side == "tail" else 0
-    groups = defaultdict(set)
-    for row in filt:
-        groups[(int(row[kc[0]]), int(row[kc[1]]))].add(int(row[vc]))
-    offs = np.zeros(len(test) + 1, dtype=np.int64)
-    ids = []
-    for q, row in enumerate(test):
-        members = groups.get((int(row[kc[0]]), int(row[kc[1]])), ())
-        if int(row[vc]) in members:
-            raise ValueError("list.remove(x): x not in list")
-        ids.extend(sorted(members))
-        offs[q + 1] = len(ids)
-    return offs, np.asarray(ids, dtype=np.int32)
+    Q = len(test)
+    if len(filt) == 0 or Q == 0:
+        return np.zeros(Q + 1, dtype=np.int64), np.zeros(0, dtype=np.int32)
+    span = int(max(filt.max(), test.max())) + 1
+    if span ** 3 >= 2 ** 62:
+        raise ValueError("ids too large for the packed filter key")
+    # one sortable key per filter triple: (key0, key1, value); unique() sorts and de-duplicates in one pass
+    packed = np.unique((filt[:, kc[0]] * span + filt[:, kc[1]]) * span + filt[:, vc])
+    qkey = (test[:, kc[0]] * span + test[:, kc[1]]) * span
+    lo = np.searchsorted(packed, qkey, side="left")
+    hi = np.searchsorted(packed, qkey + span, side="left")
+    lens = hi - lo
+    offs = np.zeros(Q + 1, dtype=np.int64)
+    np.cumsum(lens, out=offs[1:])
+    # gather the segments [lo_q, hi_q) back to back
+    nnz = int(offs[-1])
+    if nnz == 0:
+        return offs, np.zeros(0, dtype=np.int32)
+    seg = np.repeat(np.arange(Q), lens)
+    pos = lo[seg] + (np.arange(nnz) - offs[seg])
+    ids = packed[pos] - qkey[seg]
+    if np.any(ids == test[seg, vc]):
+        raise ValueError("list.remove(x): x not in list")
+    return offs, ids.astype(np.int32)
 
 
 def shard_rows(num_entities, world, rank):

@@ -172,7 +172,31 @@ __global__ void k_negatives(const int32_t* __restrict__ pos, int64_t B, int K, u
   }
 }
 
+// oversample_data (utils.py:123-147) on the device: dst[i] = src[u_i], u_i uniform in [0, n) with replacement
+__global__ void k_oversample(const int32_t* __restrict__ src, int64_t n, int64_t m, uint64_t seed, uint64_t offset, int stream_id,
+                             int32_t* __restrict__ dst) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)),
+                                  make_uint2((uint32_t)seed ^ 0x4F565253u, (uint32_t)(seed >> 32) ^ (uint32_t)stream_id));
+    const int64_t u = (int64_t)(((unsigned long long)r.x * (unsigned long long)n) >> 32);
+    dst[3 * i] = __ldg(src + 3 * u); dst[3 * i + 1] = __ldg(src + 3 * u + 1); dst[3 * i + 2] = __ldg(src + 3 * u + 2);
+  }
+}
+
 }  // namespace
+
+extern "C" int kgeb_oversample(kgeb_ctx* ctx, const int32_t* src, int64_t n, int64_t m, uint64_t seed, uint64_t offset, int stream_id,
+                               int32_t* dst, kgeb_stream stream) {
+  if (!ctx) return KGEB_ERR_INVALID;
+  KGEB_REQUIRE(ctx, n >= 0 && m >= 0 && n < 0xffffffffLL, KGEB_ERR_INVALID, "oversample: bad sizes");
+  if (m == 0) return KGEB_OK;
+  KGEB_REQUIRE(ctx, src && dst && n > 0, KGEB_ERR_INVALID, "oversample: cannot draw from an empty list");
+  int64_t blocks = (m + 255) / 256;
+  if (blocks > (int64_t)ctx->num_sms * 8) blocks = (int64_t)ctx->num_sms * 8;
+  k_oversample<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, n, m, seed, offset, stream_id, dst);
+  KGEB_LAUNCH_OK(ctx);
+  return KGEB_OK;
+}
 
 extern "C" int kgeb_score_fwd(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* idx, int64_t m, float* scores,
                               kgeb_stream stream) {

@@ -648,3 +648,14 @@ def train_step_dropout(kind, loss_kind, E, R, pos, neg, K, margin, gamma, p, see
         np.add.at(gE, idx[:, 2].astype(np.int64), w * do * mo)
         np.add.at(gR, idx[:, 1].astype(np.int64), w * dp_ * mp)
     return dict(loss=L, pos_scores=t, neg_scores=f, gE=gE, gR=gR)
+
+
+def philox_oversample_indices(n, m, seed, offset, stream_id=0):
+    """Indices exactly as kgeb_oversample draws them (device-side oversample_data, utils.py:123-147)."""
+    i = np.arange(m, dtype=np.uint64)
+    ctr = np.stack([(i & _U32).astype(np.uint32), (i >> np.uint64(32)).astype(np.uint32),
+                    np.full(m, int(offset) & 0xFFFFFFFF, np.uint32), np.full(m, (int(offset) >> 32) & 0xFFFFFFFF, np.uint32)], axis=-1)
+    key = np.stack([np.full(m, (int(seed) & 0xFFFFFFFF) ^ 0x4F565253, np.uint32),
+                    np.full(m, ((int(seed) >> 32) & 0xFFFFFFFF) ^ int(stream_id), np.uint32)], axis=-1)
+    r = philox4x32_10(ctr, key)
+    return ((r[:, 0].astype(np.uint64) * np.uint64(n)) >> np.uint64(32)).astype(np.int64)

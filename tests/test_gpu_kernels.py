@@ -332,3 +332,18 @@ def test_l3_regularization_step():
     assert int(eng.tE.sum()) == N
     eng.apply_optimizer(ko.OPT_SGD, lr=0.1)
     np.testing.assert_allclose(eng.get_tables()[0], E - 0.1 * (want["gE"] + rg), rtol=1e-4, atol=1e-6)
+
+
+def test_device_batch_pipeline_bit_exact():
+    """Device-side DataGenerator.__get_data (tests.py:55-61): Philox negatives + Philox oversampling against the host restatement."""
+    eng, E, Rm = make_engine(ko.DISTMULT, 500, 7, 8, seed=1)
+    rng = np.random.default_rng(3)
+    pos = rand_triples(rng, 100, 500, 7)
+    K, seed, step = 10, 99, 12
+    dpos, dneg = eng.device_batch(pos, K, seed, step)
+    neg = ko.philox_negatives(pos, 500, K, seed, step, ko.CORRUPT_BOTH).astype(np.int32)
+    m = len(neg)
+    np.testing.assert_array_equal(dpos.cpu().numpy(), pos[ko.philox_oversample_indices(len(pos), m, seed, step, 0)])
+    np.testing.assert_array_equal(dneg.cpu().numpy(), neg[ko.philox_oversample_indices(m, m, seed, step, 1)])
+    idx = ko.philox_oversample_indices(100, 200000, 5, 0, 0)
+    assert idx.min() == 0 and idx.max() == 99 and abs(np.bincount(idx, minlength=100).std() / 2000 - np.sqrt(0.99 / 2000)) < 0.01
