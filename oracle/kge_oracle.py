@@ -15,6 +15,8 @@ import numpy as np
 
 # score kinds -- numeric values are shared with include/kgeb200.h (kgeb_score_kind)
 DISTMULT, TRANSE_L1, TRANSE_L2, COMPLEX, HOLE = 0, 1, 2, 3, 4
+# sibling score functions: RotatE models.py:421-459, pRotatE 461-489, ModE 403-418 (norm 1 | 2)
+ROTATE, PROTATE, MODE_L1, MODE_L2 = 5, 6, 7, 8
 SCORE_KINDS = {"DistMult": DISTMULT, "TransE_L1": TRANSE_L1, "TransE_L2": TRANSE_L2,
                "ComplEx": COMPLEX, "HolE": HOLE}
 
@@ -76,7 +78,7 @@ def circular_correlation_direct(a, b):
     return out
 
 
-def score(kind, s, p, o, gamma=12.0, hole_fft=True):
+def score(kind, s, p, o, gamma=12.0, hole_fft=True, param=1.0):
     """func(s,p,o) of the four hot-path models; dtype follows the inputs.
 
     DistMult models.py:171-172, TransE 186-190, ComplEx 212-222, HolE 231-237."""
@@ -102,13 +104,29 @@ def score(kind, s, p, o, gamma=12.0, hole_fft=True):
     if kind == HOLE:
         x = circular_correlation_fft(s, o) if hole_fft else circular_correlation_direct(s, o)
         return np.sum(p * x, axis=-1)
+    if kind == ROTATE:   # models.py:439-459: rows [re | im], p = phases (width d); SIGNED sum of the residuals, no norm
+        d = s.shape[-1] // 2
+        ph = np.arctan2(np.sin(p), np.cos(p))
+        c, sn = np.cos(ph), np.sin(ph)
+        re = s[..., :d] * c - s[..., d:] * sn - o[..., :d]
+        im = s[..., :d] * sn + s[..., d:] * c - o[..., d:]
+        a = np.sum(np.concatenate([re, im], axis=-1), axis=-1)
+        return (dt.type(gamma) - a).astype(dt) if gamma > 0 else a
+    if kind == PROTATE:  # models.py:479-489; `param` = modulus * embedding_range
+        ph = lambda x: np.arctan2(np.sin(x), np.cos(x))
+        a = np.sum(np.abs(np.sin((ph(s) + ph(p) - ph(o)) / 2)), axis=-1) * dt.type(param)
+        return (dt.type(gamma) - a).astype(dt) if gamma > 0 else a
+    if kind in (MODE_L1, MODE_L2):  # models.py:417-418 (with self.gamma assigned, Appendix D)
+        r = s * p - o
+        n = np.sum(np.abs(r), axis=-1) if kind == MODE_L1 else np.sqrt(np.sum(r * r, axis=-1))
+        return (dt.type(gamma) - n).astype(dt)
     raise KeyError(kind)
 
 
-def score_triples(kind, E, R, idx, gamma=12.0, dtype=np.float32, hole_fft=True):
+def score_triples(kind, E, R, idx, gamma=12.0, dtype=np.float32, hole_fft=True, param=1.0):
     """EmbeddingModel.call with dp inactive (models.py:134-162): (B,3) ids -> (B,) scores."""
     s, p, o = gather(E.astype(dtype), R.astype(dtype), idx)
-    return score(kind, s, p, o, gamma, hole_fft)
+    return score(kind, s, p, o, gamma, hole_fft, param)
 
 
 def score_abs_terms(kind, E, R, idx, gamma=12.0):
@@ -129,7 +147,7 @@ def score_abs_terms(kind, E, R, idx, gamma=12.0):
     raise KeyError(kind)
 
 
-def score_grads(kind, s, p, o, gamma=12.0):
+def score_grads(kind, s, p, o, gamma=12.0, param=1.0):
     """Analytic d score / d (s, p, o); checked against torch autograd in tests."""
     if kind == DISTMULT:
         return p * o, s * o, s * p
@@ -160,6 +178,24 @@ def score_grads(kind, s, p, o, gamma=12.0):
             ds += p[..., k:k + 1] * np.roll(o, -k, axis=-1)   # ds_i = sum_k p_k o_{i+k}
             do += p[..., k:k + 1] * np.roll(s, k, axis=-1)    # do_j = sum_k p_k s_{j-k}
         return ds, dp, do
+    sg = -1.0 if gamma > 0 else 1.0
+    if kind == ROTATE:
+        d = s.shape[-1] // 2
+        c, sn = np.cos(p), np.sin(p)
+        sr, si = s[..., :d], s[..., d:]
+        ds = sg * np.concatenate([c + sn, c - sn], axis=-1)
+        dp = sg * (sr * (c - sn) - si * (c + sn))
+        do = sg * -np.ones_like(o)
+        return ds, dp, do
+    if kind == PROTATE:
+        y = (s + p - o) / 2
+        g = sg * param * np.sign(np.sin(y)) * np.cos(y) / 2
+        return g, g, -g
+    if kind in (MODE_L1, MODE_L2):
+        r = s * p - o
+        g = np.sign(r) if kind == MODE_L1 else r / np.sqrt(np.sum(r * r, axis=-1, keepdims=True))
+        g = -g
+        return g * p, g * s, -g
     raise KeyError(kind)
 
 
@@ -287,10 +323,10 @@ def loss_and_coefs(loss_kind, pair_mode, t, f, K, margin):
 # --------------------------------------------------------------------------------------------
 # backward + optimizer (third-party Keras/TF semantics, recalled)
 # --------------------------------------------------------------------------------------------
-def dense_grads(kind, E, R, idx, dscore, gamma=12.0, dtype=np.float64):
+def dense_grads(kind, E, R, idx, dscore, gamma=12.0, dtype=np.float64, param=1.0):
     """IndexedSlices -> dense: sum of dscore_m * dscore/drow over every reference to a row."""
     s, p, o = gather(E.astype(dtype), R.astype(dtype), idx)
-    ds, dp, do = score_grads(kind, s, p, o, gamma)
+    ds, dp, do = score_grads(kind, s, p, o, gamma, param)
     w = np.asarray(dscore, dtype=dtype)[:, None]
     gE = np.zeros(E.shape, dtype)
     gR = np.zeros(R.shape, dtype)
@@ -449,7 +485,7 @@ def build_filters(filtering_triples):
     return filter_h, filter_t
 
 
-def all_entity_scores(kind, E, R, triples, side, gamma=12.0, dtype=np.float32, hole_fft=False):
+def all_entity_scores(kind, E, R, triples, side, gamma=12.0, dtype=np.float32, hole_fft=False, param=1.0):
     """(Q,N) matrix: score of every candidate entity in the `side` slot of each test triple, computed
     exactly like call() would on the (C+1,3) candidate array of gen_tail_data/gen_head_data."""
     triples = np.asarray(triples, dtype=np.int64)
@@ -461,7 +497,7 @@ def all_entity_scores(kind, E, R, triples, side, gamma=12.0, dtype=np.float32, h
         idx[:, 0] = cand if side == "head" else s
         idx[:, 1] = p
         idx[:, 2] = cand if side == "tail" else o
-        out[qi] = score_triples(kind, E, R, idx, gamma, dtype, hole_fft)
+        out[qi] = score_triples(kind, E, R, idx, gamma, dtype, hole_fft, param)
     return out
 
 
@@ -538,30 +574,48 @@ def query_vectors(kind, E, R, triples, side, dtype=np.float32):
             for k in range(d):   # q_i = sum_k p_k o_{(i+k) mod d}, sequential in k
                 q = q + p[:, k:k + 1] * np.roll(o, -k, axis=1)
         return q
-    if kind in (TRANSE_L1, TRANSE_L2):
+    if kind in (TRANSE_L1, TRANSE_L2, PROTATE):
         return s + p if side == "tail" else np.concatenate([p, o], axis=1)
+    if kind in (MODE_L1, MODE_L2):   # tail r = s*p - e, head r = e*p - o
+        return s * p if side == "tail" else np.concatenate([p, o], axis=1)
+    if kind == ROTATE:
+        # the score is linear in the candidate: tail gamma - A = const + sum_j e_j, head = const - e . [(c+s)|(c-s)]
+        # (constants cancel inside one query's ranking); sign flips when gamma <= 0 -- the caller passes gamma_sign
+        c, sn = np.cos(p), np.sin(p)
+        return np.ones_like(s) if side == "tail" else -np.concatenate([c + sn, c - sn], axis=1)
     raise KeyError(kind)
 
 
-def seqk_scores(kind, q, Erows, side, gamma=12.0):
+def seqk_scores(kind, q, Erows, side, gamma=12.0, param=1.0):
     """Scores op(q, e) accumulated sequentially over k in fp32 with separate multiply and add roundings --
     bit-for-bit what kgeb_rank_1n's CUDA-core kernels compute (they use __fmul_rn/__fadd_rn, no FMA)."""
     q = q.astype(np.float32)
     Er = Erows.astype(np.float32)
     Q, Nn, W = q.shape[0], Er.shape[0], Er.shape[1]
     acc = np.zeros((Q, Nn), np.float32)
-    if kind in (DISTMULT, COMPLEX, HOLE):
+    if kind in (DISTMULT, COMPLEX, HOLE, ROTATE):
+        if kind == ROTATE and gamma <= 0:
+            q = -q
         for k in range(W):
             acc = acc + q[:, k:k + 1] * Er[None, :, k]
         return acc
     for k in range(W):
         if side == "tail":
             r = q[:, k:k + 1] - Er[None, :, k]
+        elif kind in (MODE_L1, MODE_L2):
+            r = Er[None, :, k] * q[:, k:k + 1] - q[:, W + k:W + k + 1]
         else:
             r = (Er[None, :, k] + q[:, k:k + 1]) - q[:, W + k:W + k + 1]
-        acc = acc + (np.abs(r) if kind == TRANSE_L1 else r * r)
-    if kind == TRANSE_L2:
+        if kind == PROTATE:
+            acc = acc + np.abs(np.sin(r * np.float32(0.5)))
+        else:
+            acc = acc + (np.abs(r) if kind in (TRANSE_L1, MODE_L1) else r * r)
+    if kind in (TRANSE_L2, MODE_L2):
         acc = np.sqrt(acc)
+    if kind == PROTATE:
+        acc = acc * np.float32(param)
+    if kind in (MODE_L1, MODE_L2):
+        return np.float32(gamma) - acc
     return (np.float32(gamma) - acc) if gamma > 0 else acc
 
 
