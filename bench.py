@@ -43,38 +43,58 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+    """Samples SM clock and throttle reasons through NVML while the warm-up and the timed region run.  NVML is opened
+    in the constructor (it takes longer than a short timed region); samples taken while `timed` is set are the ones
+    reported, the warm-up samples are the fallback when the timed region is shorter than one sampling period."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.err = index, [], set(), False, None, None
-
-    def run(self):
+        self.index, self.samples, self.timed_samples, self.reasons, self.stop_flag = index, [], [], set(), False
+        self.max_mhz, self.err, self.timed, self.h, self.nv = None, None, False, None, None
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
-                     "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
-            while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
-                time.sleep(0.002)
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
         except Exception as e:  # NVML missing: report it, never fake numbers
             self.err = repr(e)
 
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip() != ""]
+        if ids and index < len(ids) and ids[index].strip().isdigit():
+            return int(ids[index])
+        return index
+
+    def sample_once(self):
+        nv, h = self.nv, self.h
+        mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        (self.timed_samples if self.timed else self.samples).append(mhz)
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        for k, bit in (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)):
+            if r & bit:
+                self.reasons.add(k)
+
+    def run(self):
+        if self.h is None:
+            return
+        try:
+            while not self.stop_flag:
+                self.sample_once()
+                time.sleep(0.001)
+        except Exception as e:
+            self.err = repr(e)
+
     def summary(self):
-        if not self.samples:
+        use = self.timed_samples or self.samples
+        if not use:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "error": self.err}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+        return {"sm_mhz": float(np.median(use)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(use), "window": "timed region" if self.timed_samples else "warm-up (timed region shorter than one sample)"}
 
 
 def ncu_traffic(key):
@@ -183,14 +203,15 @@ def main():
     U_E, U_R = int(eng.tE.sum().item()), int(eng.tR.sum().item())
     eng.apply_optimizer(**opt_kw)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(warm):
         flush.zero_()
         eng.train_step(dev_batches[i], None, offset=i, **step_kw, **opt_kw)
     # ---- timed: K steps, device-resident inputs, per-step CUDA events, L2 flushed between steps ----------------------
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.timed = True
     l0 = eng.launches
     t_wall0 = time.perf_counter()
     for i in range(steps):
@@ -203,6 +224,11 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = eng.launches - l0
+    if sampler.h is not None and not sampler.timed_samples:
+        try:
+            sampler.sample_once()   # the device has just finished the last timed step
+        except Exception:
+            pass
     sampler.stop_flag = True
     sampler.join(timeout=2)
     t_fb = np.array([e[0].elapsed_time(e[1]) for e in ev])

@@ -47,8 +47,16 @@ typedef enum {
   KGEB_ERR_WORKSPACE = -5  /* caller workspace too small */
 } kgeb_status;
 
-/* score functions: DistMult models.py:171-172, TransE 186-190 (norm=1|2), ComplEx 212-222, HolE 231-237 */
-typedef enum { KGEB_DISTMULT = 0, KGEB_TRANSE_L1 = 1, KGEB_TRANSE_L2 = 2, KGEB_COMPLEX = 3, KGEB_HOLE = 4 } kgeb_score_kind;
+/* score functions: DistMult models.py:171-172, TransE 186-190 (norm=1|2), ComplEx 212-222, HolE 231-237;
+ * sibling models: RotatE 439-459 (entity rows [re | im] of width 2d, relation rows = d phases, so
+ * we == 2*wr and the kernels need ldR >= we), pRotatE 479-489 (score scaled by kgeb_set_score_param's modulus),
+ * ModE 417-418 (gamma - ||s*p - o||_norm, norm 1 | 2).  The siblings are served by score_fwd / score_bwd and the
+ * CUDA-core ranking kernels (RotatE also by the tensor-core one: its score is linear in the candidate row); the fused
+ * train kernel serves the first four kinds. */
+typedef enum {
+  KGEB_DISTMULT = 0, KGEB_TRANSE_L1 = 1, KGEB_TRANSE_L2 = 2, KGEB_COMPLEX = 3, KGEB_HOLE = 4,
+  KGEB_ROTATE = 5, KGEB_PROTATE = 6, KGEB_MODE_L1 = 7, KGEB_MODE_L2 = 8
+} kgeb_score_kind;
 
 /* losses utils.py:288-319 (pointwize_cross_entropy is composed on the host from kernel scores) */
 typedef enum {
@@ -88,6 +96,10 @@ KGEB_API int kgeb_num_sms(const kgeb_ctx* ctx);
 typedef enum { KGEB_TIMED_RANK_TC = 0, KGEB_TIMED_RANK_REFINE = 1, KGEB_TIMED_RANK_TILE = 2, KGEB_TIMED_TRAIN = 3 } kgeb_timed_kernel;
 KGEB_API int kgeb_set_kernel_timing(kgeb_ctx* ctx, int on);
 KGEB_API int kgeb_last_kernel_ms(kgeb_ctx* ctx, int which, float* ms);
+
+/* Scalar parameter of the score function besides gamma: pRotatE's modulus (models.py:476, modulus*embedding_range).
+ * Default 1; ignored by the other kinds. */
+KGEB_API int kgeb_set_score_param(kgeb_ctx* ctx, float param);
 
 /* ---- dropout, models.py:122,144-150: Dropout(dp) on each gathered s / p / o row while training ----------------------
  * p > 0 arms it for the following score_fwd / score_bwd / train_fwd_bwd calls of this context (p = 0 disarms: predict,

@@ -39,14 +39,14 @@ def as_idx(x, device):
 class Engine:
     """Tables + gradient/optimizer buffers of one model on one GPU, bound to a kgeb context."""
 
-    def __init__(self, kind, num_entities, num_relations, we, wr, gamma=12.0, device=None, E=None, R=None, rng=None):
+    def __init__(self, kind, num_entities, num_relations, we, wr, gamma=12.0, device=None, E=None, R=None, rng=None, param=1.0):
         if not torch.cuda.is_available():
             raise RuntimeError("KGEkeras (B200 build) needs a CUDA device: there is no CPU fallback")
         self.lib = abi.lib()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.kind, self.N, self.R_, self.we, self.wr, self.gamma = kind, int(num_entities), int(num_relations), int(we), int(wr), float(gamma)
         # zero-padded columns are neutral for DistMult/TransE, so odd widths are padded to the 128-bit granule
-        pad_ok = kind in (abi.DISTMULT, abi.TRANSE_L1, abi.TRANSE_L2)
+        pad_ok = kind in (abi.DISTMULT, abi.TRANSE_L1, abi.TRANSE_L2, abi.PROTATE, abi.MODE_L1, abi.MODE_L2)
         self.we_k = (self.we + 3) // 4 * 4 if pad_ok else self.we
         self.wr_k = (self.wr + 3) // 4 * 4 if pad_ok else self.wr
         rng = rng or np.random.default_rng()
@@ -56,6 +56,9 @@ class Engine:
         abi.check(self.lib.kgeb_create(C.byref(h), self.device.index or 0, self.N, self.R_, self.we_k, self.wr_k,
                                        self.we_k, self.wr_k, kind, self.gamma))
         self.ctx = h
+        self.param = float(param)
+        if self.param != 1.0:
+            self._check(self.lib.kgeb_set_score_param(self.ctx, self.param))
         self.gE = self.gR = self.tE = self.tR = None
         self.opt_state = None
         self.step = 0
@@ -194,7 +197,7 @@ class Engine:
                     K = neg.shape[0] // B
         self._ensure_train_buffers(opt_kind)
         pairwise = loss_kind >= abi.PAIRWISE_HINGE
-        fused = (not force_unfused and self.kind != abi.HOLE and not (pairwise and pair_mode == abi.ALLPAIRS)
+        fused = (not force_unfused and self.kind in abi.FUSED_TRAIN_KINDS and not (pairwise and pair_mode == abi.ALLPAIRS)
                  and (neg is None or neg.shape[0] == B * K))
         res = {}
         if fused:
@@ -274,7 +277,7 @@ class Engine:
 
     # ---- 1-N filtered ranking on the tensor cores (DistMult / ComplEx / HolE) -------------------------------------------
     def tc_supported(self):
-        return self.kind in (abi.DISTMULT, abi.COMPLEX, abi.HOLE)
+        return self.kind in (abi.DISTMULT, abi.COMPLEX, abi.HOLE, abi.ROTATE)
 
     def pack_entities_tc(self, mode=abi.TC_BF16X3_EXACT, row_range=None):
         """bf16 (hi/lo) image + row norms of the entity rows [r0, r1): build once per table version, reuse for every query batch."""

@@ -3,8 +3,8 @@
 is computed by libkgeb200's sm_100a kernels through KGEkeras._engine; there is no CPU fallback.
 
 Reference lines mirrored: EmbeddingModel.__init__ models.py:14-129, call 134-162, DistMult 164-172, TransE 175-190,
-ComplEx 203-222, HolE 224-237; sibling classes 192-200, 239-489 keep their constructors (their score kernels are the
-"next" rows of SURVEY 8f and raise NotImplementedError when scored).
+ComplEx 203-222, HolE 224-237; siblings ModE 403-418, RotatE 421-459, pRotatE 461-489 (score_fwd/score_bwd + ranking
+kernels; they train through the unfused kernel sequence).  CosinE keeps its NameError, HAKE its constructor only.
 """
 from __future__ import annotations
 
@@ -138,15 +138,18 @@ class EmbeddingModel:
 
     def _kind_(self):
         if self._score_kind is None:
-            raise NotImplementedError(f"{type(self).__name__}: score kernel not built yet (SURVEY 8f next rows); "
-                                      f"DistMult, TransE, ComplEx and HolE are served")
+            raise NotImplementedError(f"{type(self).__name__}: no score kernel (served: DistMult, TransE, ComplEx, HolE, "
+                                      f"ModE, RotatE, pRotatE)")
         return self._score_kind
+
+    def _param_(self):
+        return 1.0
 
     def _engine_(self):
         if self._eng is None:
             from ._engine import Engine
             self._eng = Engine(self._kind_(), self.num_entities, self.num_relations, self.e_dim, self.r_dim,
-                               gamma=self._gamma_(), E=self._init_E, R=self._init_R)
+                               gamma=self._gamma_(), E=self._init_E, R=self._init_R, param=self._param_())
             self._init_E = self._init_R = None
         return self._eng
 
@@ -171,7 +174,8 @@ class EmbeddingModel:
         from ._engine import Engine
         s, p, o = (torch.as_tensor(np.asarray(x.detach().cpu() if hasattr(x, "detach") else x), dtype=torch.float32) for x in (s, p, o))
         n = s.shape[0]
-        eng = Engine(self._kind_(), 2 * n, n, s.shape[1], p.shape[1], gamma=self._gamma_(), E=torch.cat([s, o]).numpy(), R=p.numpy())
+        eng = Engine(self._kind_(), 2 * n, n, s.shape[1], p.shape[1], gamma=self._gamma_(), E=torch.cat([s, o]).numpy(), R=p.numpy(),
+                     param=self._param_())
         idx = np.stack([np.arange(n), np.arange(n), n + np.arange(n)], axis=1).astype(np.int32)
         return eng.score(idx)
 
@@ -363,6 +367,15 @@ class ModE(EmbeddingModel):
         self.norm = norm
         self.gamma = gamma  # the reference reads self.gamma without assigning it (models.py:415); fixed here
 
+    def _kind_(self):
+        """gamma - ||s*p - o||_norm (models.py:417-418).  The product needs equal stored widths, i.e. 2*e_dim == 3*r_dim
+        as passed by the caller (the reference would fail in TF's broadcast otherwise; here the C ABI reports it)."""
+        if self.norm == 1:
+            return abi.MODE_L1
+        if self.norm == 2:
+            return abi.MODE_L2
+        raise NotImplementedError(f"ModE norm={self.norm!r}: the kernels serve ord 1 and 2")
+
 
 class HAKE(EmbeddingModel):
     def __init__(self, epsilon=2, gamma=12, phase_weight=0.5, mod_weight=1, name='HAKE', **kwargs):
@@ -375,6 +388,8 @@ class HAKE(EmbeddingModel):
 
 
 class RotatE(EmbeddingModel):
+    _score_kind = abi.ROTATE   # models.py:439-459; needs e_dim == r_dim as passed (entity rows 2d, d relation phases)
+
     def __init__(self, gamma=12, norm=2, epsilon=2, name='RotatE', **kwargs):
         kwargs['e_dim'] = 2 * kwargs['e_dim']
         kwargs['r_dim'] = kwargs['r_dim']
@@ -385,6 +400,11 @@ class RotatE(EmbeddingModel):
 
 
 class pRotatE(EmbeddingModel):
+    _score_kind = abi.PROTATE  # models.py:479-489
+
+    def _param_(self):
+        return float(self.modulus)
+
     def __init__(self, gamma=12, epsilon=2, modulus=0.5, name='pRotatE', **kwargs):
         kwargs['e_dim'] = 2 * kwargs['e_dim']
         kwargs['r_dim'] = 2 * kwargs['r_dim']

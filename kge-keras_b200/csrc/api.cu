@@ -14,7 +14,7 @@ extern "C" int kgeb_create(kgeb_ctx** out, int device, int64_t num_entities, int
     return kgeb_fail(nullptr, KGEB_ERR_INVALID, "%s", "kgeb_create: bad table shape");
   if (num_entities > 0x7fffffffLL || num_relations > 0x7fffffffLL)
     return kgeb_fail(nullptr, KGEB_ERR_INVALID, "%s", "kgeb_create: ids are int32");
-  if (score_kind < KGEB_DISTMULT || score_kind > KGEB_HOLE)
+  if (score_kind < KGEB_DISTMULT || score_kind > KGEB_MODE_L2)
     return kgeb_fail(nullptr, KGEB_ERR_INVALID, "%s", "kgeb_create: unknown score kind");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -32,7 +32,7 @@ extern "C" int kgeb_create(kgeb_ctx** out, int device, int64_t num_entities, int
   if (!c) return kgeb_fail(nullptr, KGEB_ERR_INVALID, "%s", "kgeb_create: out of host memory");
   memset(c, 0, sizeof(*c));
   c->device = device; c->N = num_entities; c->R = num_relations; c->we = we; c->wr = wr; c->ldE = ldE; c->ldR = ldR;
-  c->kind = score_kind; c->gamma = gamma; c->num_sms = prop.multiProcessorCount;
+  c->kind = score_kind; c->gamma = gamma; c->param = 1.f; c->num_sms = prop.multiProcessorCount;
   if ((e = cudaMalloc(&c->d_partials, sizeof(double) * 2 * KGEB_MAX_PARTIAL_BLOCKS)) != cudaSuccess ||
       (e = cudaMalloc(&c->d_ticket, sizeof(unsigned int))) != cudaSuccess ||
       (e = cudaMemset(c->d_ticket, 0, sizeof(unsigned int))) != cudaSuccess) {
@@ -78,6 +78,12 @@ extern "C" int kgeb_last_kernel_ms(kgeb_ctx* ctx, int which, float* ms) {
   KGEB_REQUIRE(ctx, ctx->ev_valid[which], KGEB_ERR_INVALID, "kernel timing: that kernel has not been launched with timing on");
   KGEB_CUDA_OK(ctx, cudaEventSynchronize(ctx->ev[which][1]));
   KGEB_CUDA_OK(ctx, cudaEventElapsedTime(ms, ctx->ev[which][0], ctx->ev[which][1]));
+  return KGEB_OK;
+}
+
+extern "C" int kgeb_set_score_param(kgeb_ctx* ctx, float param) {
+  if (!ctx) return KGEB_ERR_INVALID;
+  ctx->param = param;
   return KGEB_OK;
 }
 

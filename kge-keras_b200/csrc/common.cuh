@@ -18,6 +18,7 @@ struct kgeb_ctx {
   int we, wr, ldE, ldR;
   int kind;
   float gamma;
+  float param;   // pRotatE modulus (kgeb_set_score_param), 1 otherwise
   int num_sms;
   int64_t launches;
   char err[512];

@@ -6,11 +6,16 @@
 namespace {
 
 constexpr int DISTMULT = KGEB_DISTMULT, TRANSE_L1 = KGEB_TRANSE_L1, TRANSE_L2 = KGEB_TRANSE_L2, COMPLEX = KGEB_COMPLEX;
+constexpr int ROTATE = KGEB_ROTATE, PROTATE = KGEB_PROTATE, MODE_L1 = KGEB_MODE_L1, MODE_L2 = KGEB_MODE_L2;
 
-// Row fragment: NC chunks per lane (ComplEx: NC chunks of the real half followed by NC of the imaginary half).
+// Rows stored as two halves [re | im]: ComplEx (all three rows) and RotatE (entity rows; its relation row is d phases).
+template <int KIND, bool REL = false>
+constexpr bool split_row() { return KIND == COMPLEX || (KIND == ROTATE && !REL); }
+
+// Row fragment: NC chunks per lane (split rows: NC chunks of the real half followed by NC of the imaginary half).
 template <int KIND, int NC>
 struct Frag {
-  static constexpr int NT = (KIND == COMPLEX) ? 2 * NC : NC;
+  static constexpr int NT = split_row<KIND>() ? 2 * NC : NC;
   float4 v[NT];
 };
 
@@ -19,7 +24,8 @@ struct RowGeom {
   int half4; // ComplEx: offset of the imaginary half in float4 units; otherwise 0
 };
 
-template <int KIND, int NC>
+// REL = true marks the relation row (only RotatE treats it differently: a plain row of d phases in v[0..NC))
+template <int KIND, int NC, bool REL = false>
 __device__ __forceinline__ void load_frag(Frag<KIND, NC>& f, const float* __restrict__ table, int64_t row, int ld,
                                           RowGeom g, int lane) {
   const float4* r4 = reinterpret_cast<const float4*>(table + row * (int64_t)ld);
@@ -28,7 +34,8 @@ __device__ __forceinline__ void load_frag(Frag<KIND, NC>& f, const float* __rest
     const int c = lane + 32 * i;
     const bool ok = c < g.nch;
     f.v[i] = ok ? ldg4(r4 + c) : f4zero();
-    if (KIND == COMPLEX) f.v[NC + i] = ok ? ldg4(r4 + g.half4 + c) : f4zero();
+    if (split_row<KIND, REL>()) f.v[NC + i] = ok ? ldg4(r4 + g.half4 + c) : f4zero();
+    else if (split_row<KIND>()) f.v[NC + i] = f4zero();
   }
 }
 
@@ -45,7 +52,7 @@ __device__ __forceinline__ void add_frag(Frag<KIND, NC>& a, const Frag<KIND, NC>
   }
 }
 
-template <int KIND, int NC>
+template <int KIND, int NC, bool REL = false>
 __device__ __forceinline__ void red_frag(float* __restrict__ table, int64_t row, int ld, RowGeom g, int lane,
                                          const Frag<KIND, NC>& f) {
   float* r = table + row * (int64_t)ld;
@@ -54,7 +61,7 @@ __device__ __forceinline__ void red_frag(float* __restrict__ table, int64_t row,
     const int c = lane + 32 * i;
     if (c < g.nch) {
       red_add4(r + 4 * c, f.v[i]);
-      if (KIND == COMPLEX) red_add4(r + 4 * (g.half4 + c), f.v[NC + i]);
+      if (split_row<KIND, REL>()) red_add4(r + 4 * (g.half4 + c), f.v[NC + i]);
     }
   }
 }
@@ -84,6 +91,21 @@ __device__ __forceinline__ float score_partial(const Frag<KIND, NC>& s, const Fr
       } else if (KIND == TRANSE_L2) {
         const float r = __fsub_rn(__fadd_rn(comp(s.v[i], _e), comp(p.v[i], _e)), comp(o.v[i], _e));
         acc += __fmul_rn(r, r);
+      } else if (KIND == MODE_L1 || KIND == MODE_L2) {   // models.py:418: s * p - o
+        const float r = __fsub_rn(__fmul_rn(comp(s.v[i], _e), comp(p.v[i], _e)), comp(o.v[i], _e));
+        acc += (KIND == MODE_L1) ? fabsf(r) : __fmul_rn(r, r);
+      } else if (KIND == PROTATE) {
+        // models.py:481-485: |sin((ph(s) + ph(p) - ph(o)) / 2)| with ph(x) = atan2(sin x, cos x) = x - 2 pi k: the
+        // half-angle turns the wrap into a sign flip, which the absolute value removes, so ph() is not evaluated
+        acc += fabsf(sinf(0.5f * __fsub_rn(__fadd_rn(comp(s.v[i], _e), comp(p.v[i], _e)), comp(o.v[i], _e))));
+      } else if (KIND == ROTATE) {
+        // models.py:441-453: cos/sin of atan2(sin p, cos p) are cos p / sin p; the SIGNED residuals are summed
+        float sn, c;
+        sincosf(comp(p.v[i], _e), &sn, &c);
+        const float sr = comp(s.v[i], _e), si = comp(s.v[NC + i], _e);
+        const float re = __fsub_rn(__fsub_rn(__fmul_rn(sr, c), __fmul_rn(si, sn)), comp(o.v[i], _e));
+        const float im = __fsub_rn(__fadd_rn(__fmul_rn(sr, sn), __fmul_rn(si, c)), comp(o.v[NC + i], _e));
+        acc += __fadd_rn(re, im);
       } else {
         const float sr = comp(s.v[i], _e), si = comp(s.v[NC + i], _e);
         const float pr = comp(p.v[i], _e), pi = comp(p.v[NC + i], _e);
@@ -100,9 +122,12 @@ __device__ __forceinline__ float score_partial(const Frag<KIND, NC>& s, const Fr
 }
 
 template <int KIND>
-__device__ __forceinline__ float score_finish(float sum, float gamma) {
-  if (KIND == TRANSE_L1) return gamma > 0.f ? gamma - sum : sum;
+__device__ __forceinline__ float score_finish(float sum, float gamma, float param = 1.f) {
+  if (KIND == TRANSE_L1 || KIND == ROTATE) return gamma > 0.f ? gamma - sum : sum;
   if (KIND == TRANSE_L2) { const float n = sqrtf(sum); return gamma > 0.f ? gamma - n : n; }
+  if (KIND == PROTATE) { const float a = __fmul_rn(sum, param); return gamma > 0.f ? gamma - a : a; }
+  if (KIND == MODE_L1) return gamma - sum;            // models.py:418 subtracts unconditionally
+  if (KIND == MODE_L2) return gamma - sqrtf(sum);
   return sum;
 }
 
@@ -110,11 +135,16 @@ __device__ __forceinline__ float score_finish(float sum, float gamma) {
 template <int KIND, int NC>
 __device__ __forceinline__ void score_grads(const Frag<KIND, NC>& s, const Frag<KIND, NC>& p, const Frag<KIND, NC>& o,
                                             float coef, float sum, float gamma, Frag<KIND, NC>& gs, Frag<KIND, NC>& gp,
-                                            Frag<KIND, NC>& go) {
+                                            Frag<KIND, NC>& go, float param = 1.f) {
   float k = coef;
-  if (KIND == TRANSE_L1 || KIND == TRANSE_L2) {
+  if (KIND == TRANSE_L1 || KIND == TRANSE_L2 || KIND == ROTATE || KIND == PROTATE) {
     k = gamma > 0.f ? -coef : coef;
     if (KIND == TRANSE_L2) { const float n = sqrtf(sum); k = n > 0.f ? k / n : 0.f; }  // TF gives NaN at r == 0; we give 0
+    if (KIND == PROTATE) k *= 0.5f * param;
+  }
+  if (KIND == MODE_L1 || KIND == MODE_L2) {
+    k = -coef;
+    if (KIND == MODE_L2) { const float n = sqrtf(sum); k = n > 0.f ? k / n : 0.f; }
   }
 #pragma unroll
   for (int i = 0; i < NC; ++i) {
@@ -130,6 +160,30 @@ __device__ __forceinline__ void score_grads(const Frag<KIND, NC>& s, const Frag<
         comp(gs.v[i], _e) = g;
         comp(gp.v[i], _e) = g;
         comp(go.v[i], _e) = -g;
+      } else if (KIND == MODE_L1 || KIND == MODE_L2) {
+        const float a = comp(s.v[i], _e), b = comp(p.v[i], _e);
+        const float r = __fsub_rn(__fmul_rn(a, b), comp(o.v[i], _e));
+        const float g = (KIND == MODE_L1) ? (r > 0.f ? k : (r < 0.f ? -k : 0.f)) : k * r;
+        comp(gs.v[i], _e) = g * b;
+        comp(gp.v[i], _e) = g * a;
+        comp(go.v[i], _e) = -g;
+      } else if (KIND == PROTATE) {   // d|sin y|/dy = sign(sin y) cos y, y = (s + p - o)/2; k already holds param/2
+        float sn, c;
+        sincosf(0.5f * __fsub_rn(__fadd_rn(comp(s.v[i], _e), comp(p.v[i], _e)), comp(o.v[i], _e)), &sn, &c);
+        const float g = sn > 0.f ? k * c : (sn < 0.f ? -k * c : 0.f);
+        comp(gs.v[i], _e) = g;
+        comp(gp.v[i], _e) = g;
+        comp(go.v[i], _e) = -g;
+      } else if (KIND == ROTATE) {
+        float sn, c;
+        sincosf(comp(p.v[i], _e), &sn, &c);
+        const float sr = comp(s.v[i], _e), si = comp(s.v[NC + i], _e);
+        comp(gs.v[i], _e) = k * (c + sn);
+        comp(gs.v[NC + i], _e) = k * (c - sn);
+        comp(gp.v[i], _e) = k * (sr * (c - sn) - si * (c + sn));
+        comp(gp.v[NC + i], _e) = 0.f;
+        comp(go.v[i], _e) = -k;
+        comp(go.v[NC + i], _e) = -k;
       } else {
         const float sr = comp(s.v[i], _e), si = comp(s.v[NC + i], _e);
         const float pr = comp(p.v[i], _e), pi = comp(p.v[NC + i], _e);
@@ -204,7 +258,7 @@ __device__ __forceinline__ bool dp_keep_elem(const DropArgs& d, int slot, int st
 }
 
 struct ScoreArgs {
-  const float* E; const float* R; int ldE, ldR; RowGeom ge, gr; float gamma;
+  const float* E; const float* R; int ldE, ldR; RowGeom ge, gr; float gamma, param;
   DropArgs dp; int dp_stream;
 };
 
@@ -225,6 +279,11 @@ int check_tables(kgeb_ctx* ctx, const void* E, const void* R) {
   if (ctx->kind == KGEB_HOLE) return KGEB_OK;
   KGEB_REQUIRE(ctx, kgeb_aligned16(E) && kgeb_aligned16(R), KGEB_ERR_ALIGNMENT, "table pointers must be 16-byte aligned");
   KGEB_REQUIRE(ctx, ctx->ldE % 4 == 0 && ctx->ldR % 4 == 0, KGEB_ERR_ALIGNMENT, "row strides must be multiples of 4 floats");
+  if (ctx->kind == KGEB_ROTATE) {
+    KGEB_REQUIRE(ctx, ctx->we == 2 * ctx->wr, KGEB_ERR_UNSUPPORTED, "RotatE needs entity width == 2 * relation width (models.py:441-448)");
+    KGEB_REQUIRE(ctx, ctx->we % 8 == 0, KGEB_ERR_ALIGNMENT, "RotatE needs dim % 4 == 0 (stored entity width % 8 == 0)");
+    return KGEB_OK;
+  }
   KGEB_REQUIRE(ctx, ctx->we == ctx->wr, KGEB_ERR_UNSUPPORTED, "entity and relation widths must match for this score kind");
   if (ctx->kind == KGEB_COMPLEX) {
     KGEB_REQUIRE(ctx, ctx->we % 8 == 0, KGEB_ERR_ALIGNMENT, "ComplEx needs dim % 4 == 0 (stored width % 8 == 0)");
@@ -236,13 +295,14 @@ int check_tables(kgeb_ctx* ctx, const void* E, const void* R) {
 
 ScoreArgs make_score_args(const kgeb_ctx* ctx, const float* E, const float* R, int* nc_out) {
   ScoreArgs a;
-  a.E = E; a.R = R; a.ldE = ctx->ldE; a.ldR = ctx->ldR; a.gamma = ctx->gamma;
-  if (ctx->kind == KGEB_COMPLEX) {
+  a.E = E; a.R = R; a.ldE = ctx->ldE; a.ldR = ctx->ldR; a.gamma = ctx->gamma; a.param = ctx->param;
+  if (ctx->kind == KGEB_COMPLEX || ctx->kind == KGEB_ROTATE) {
     a.ge.nch = ctx->we / 8; a.ge.half4 = ctx->we / 8;
   } else {
     a.ge.nch = ctx->we / 4; a.ge.half4 = 0;
   }
   a.gr = a.ge;
+  if (ctx->kind == KGEB_ROTATE) { a.gr.nch = ctx->wr / 4; a.gr.half4 = 0; }
   *nc_out = (a.ge.nch + 31) / 32;
   a.dp.thr = ctx->dp_thr; a.dp.scale = ctx->dp_scale;
   a.dp.k0 = (uint32_t)ctx->dp_seed ^ 0x44524F50u; a.dp.k1 = (uint32_t)(ctx->dp_seed >> 32);
@@ -275,6 +335,19 @@ int grid_for(const kgeb_ctx* ctx, int64_t warps_needed, int blocks_per_sm) {
     case KGEB_TRANSE_L1: { constexpr int KIND = KGEB_TRANSE_L1; __VA_ARGS__; } break;    \
     case KGEB_TRANSE_L2: { constexpr int KIND = KGEB_TRANSE_L2; __VA_ARGS__; } break;    \
     case KGEB_COMPLEX: { constexpr int KIND = KGEB_COMPLEX; __VA_ARGS__; } break;        \
+    default: return kgeb_fail(ctx, KGEB_ERR_UNSUPPORTED, "the fused train kernel serves DistMult, TransE and ComplEx; other kinds train through score_fwd -> loss_fwd_bwd -> score_bwd"); \
+  }
+// every register-fragment kind (the scoring kernels): the four above + the sibling models
+#define KGEB_DISPATCH_KIND_ALL(KINDV, ...)                                               \
+  switch (KINDV) {                                                                       \
+    case KGEB_DISTMULT: { constexpr int KIND = KGEB_DISTMULT; __VA_ARGS__; } break;      \
+    case KGEB_TRANSE_L1: { constexpr int KIND = KGEB_TRANSE_L1; __VA_ARGS__; } break;    \
+    case KGEB_TRANSE_L2: { constexpr int KIND = KGEB_TRANSE_L2; __VA_ARGS__; } break;    \
+    case KGEB_COMPLEX: { constexpr int KIND = KGEB_COMPLEX; __VA_ARGS__; } break;        \
+    case KGEB_ROTATE: { constexpr int KIND = KGEB_ROTATE; __VA_ARGS__; } break;          \
+    case KGEB_PROTATE: { constexpr int KIND = KGEB_PROTATE; __VA_ARGS__; } break;        \
+    case KGEB_MODE_L1: { constexpr int KIND = KGEB_MODE_L1; __VA_ARGS__; } break;        \
+    case KGEB_MODE_L2: { constexpr int KIND = KGEB_MODE_L2; __VA_ARGS__; } break;        \
     default: return kgeb_fail(ctx, KGEB_ERR_INVALID, "unknown score kind");          \
   }
 

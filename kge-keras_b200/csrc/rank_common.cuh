@@ -7,45 +7,40 @@
 
 namespace kgeb_rank {
 
-enum { OP_DOT = 0, OP_L1_TAIL = 1, OP_L1_HEAD = 2, OP_L2_TAIL = 3, OP_L2_HEAD = 4 };
+// TransE ops, then the sibling models: ModE head (tail queries reuse the TransE tail ops with q = s*p), pRotatE
+enum { OP_DOT = 0, OP_L1_TAIL = 1, OP_L1_HEAD = 2, OP_L2_TAIL = 3, OP_L2_HEAD = 4,
+       OP_ML1_HEAD = 5, OP_ML2_HEAD = 6, OP_PSIN_TAIL = 7, OP_PSIN_HEAD = 8, OP_COUNT = 9 };
 
-// one term of the sequential accumulation; a = qvec[k] (a2 = qvec[W+k] for head TransE), e = E[c][k]
+template <int OP>
+constexpr bool op_two_part() { return OP == OP_L1_HEAD || OP == OP_L2_HEAD || OP == OP_ML1_HEAD || OP == OP_ML2_HEAD || OP == OP_PSIN_HEAD; }
+
+// one term of the sequential accumulation; a = qvec[k] (a2 = qvec[W+k] for the two-part head queries), e = E[c][k]
 template <int OP>
 __device__ __forceinline__ float seq_term(float acc, float a, float a2, float e) {
   if (OP == OP_DOT) return __fadd_rn(acc, __fmul_rn(a, e));
   float r;
-  if (OP == OP_L1_TAIL || OP == OP_L2_TAIL) r = __fsub_rn(a, e);
+  if (OP == OP_L1_TAIL || OP == OP_L2_TAIL || OP == OP_PSIN_TAIL) r = __fsub_rn(a, e);
+  else if (OP == OP_ML1_HEAD || OP == OP_ML2_HEAD) r = __fsub_rn(__fmul_rn(e, a), a2);
   else r = __fsub_rn(__fadd_rn(e, a), a2);
-  if (OP == OP_L1_TAIL || OP == OP_L1_HEAD) return __fadd_rn(acc, fabsf(r));
+  if (OP == OP_PSIN_TAIL || OP == OP_PSIN_HEAD) return __fadd_rn(acc, fabsf(sinf(__fmul_rn(r, 0.5f))));
+  if (OP == OP_L1_TAIL || OP == OP_L1_HEAD || OP == OP_ML1_HEAD) return __fadd_rn(acc, fabsf(r));
   return __fadd_rn(acc, __fmul_rn(r, r));
 }
+// fin.x = gamma, fin.y = 1 if the distance is subtracted from gamma (TransE/pRotatE: gamma > 0; ModE: always), fin.z = param
+struct SeqFin { float gamma; int sub; float param; };
 template <int OP>
-__device__ __forceinline__ float seq_finish(float acc, float gamma) {
+__device__ __forceinline__ float seq_finish(float acc, SeqFin f) {
   if (OP == OP_DOT) return acc;
-  if (OP == OP_L2_TAIL || OP == OP_L2_HEAD) acc = __fsqrt_rn(acc);
-  return gamma > 0.f ? __fsub_rn(gamma, acc) : acc;
+  if (OP == OP_L2_TAIL || OP == OP_L2_HEAD || OP == OP_ML2_HEAD) acc = __fsqrt_rn(acc);
+  if (OP == OP_PSIN_TAIL || OP == OP_PSIN_HEAD) acc = __fmul_rn(acc, f.param);
+  return f.sub ? __fsub_rn(f.gamma, acc) : acc;
 }
-template <int OP>
-__device__ __forceinline__ float seq_score(const float* __restrict__ q, const float* __restrict__ e, int W, float gamma) {
-  float acc = 0.f;
-  for (int k = 0; k < W; ++k) acc = seq_term<OP>(acc, q[k], (OP == OP_L1_HEAD || OP == OP_L2_HEAD) ? q[W + k] : 0.f, e[k]);
-  return seq_finish<OP>(acc, gamma);
-}
-__device__ __forceinline__ float seq_score_dyn(int op, const float* q, const float* e, int W, float gamma) {
-  switch (op) {
-    case OP_DOT: return seq_score<OP_DOT>(q, e, W, gamma);
-    case OP_L1_TAIL: return seq_score<OP_L1_TAIL>(q, e, W, gamma);
-    case OP_L1_HEAD: return seq_score<OP_L1_HEAD>(q, e, W, gamma);
-    case OP_L2_TAIL: return seq_score<OP_L2_TAIL>(q, e, W, gamma);
-    default: return seq_score<OP_L2_HEAD>(q, e, W, gamma);
-  }
-}
-
 
 }  // namespace kgeb_rank
 
 // internal (hidden visibility) launchers shared between the translation units
 int kgeb_internal_host_op_for(int kind, int side);
+kgeb_rank::SeqFin kgeb_internal_seq_fin(const kgeb_ctx* ctx);
 // counts[q] -= #{c in filter(q), c != target, c in shard : seq score(q,c) > tscore[q]}
 int kgeb_internal_filter_correct(kgeb_ctx* ctx, const float* E_shard, int64_t row_offset, int64_t n_rows, const float* qvec,
                                  const float* tscore, const int32_t* triples, int64_t Q, int side,

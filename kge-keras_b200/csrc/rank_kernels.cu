@@ -18,7 +18,7 @@ namespace {
 // ---------------------------------------------------------------------------------------------------
 // query vectors; one thread per output element
 // ---------------------------------------------------------------------------------------------------
-__global__ void k_query_prep(int kind, int side, const float* __restrict__ Es, int64_t row_offset, int64_t n_rows, int ldE,
+__global__ void k_query_prep(int kind, int side, int gamma_sub, const float* __restrict__ Es, int64_t row_offset, int64_t n_rows, int ldE,
                              const float* __restrict__ R, int ldR, int W, const int32_t* __restrict__ triples, int64_t Q,
                              int qw, float* __restrict__ qvec) {
   const int64_t total = Q * (int64_t)qw;
@@ -56,7 +56,23 @@ __global__ void k_query_prep(int kind, int side, const float* __restrict__ Es, i
         }
       }
       out = acc;
-    } else {  // TransE: tail a = s + p; head keeps [p | o] so (e + p) - o follows the reference's order
+    } else if (kind == KGEB_ROTATE) {
+      // models.py:439-459: the score is linear in the candidate row.  tail: gamma - A = const + sum_j o_j -> q = 1;
+      // head: gamma - A = const - e . [(c + s) | (c - s)], c/s = cos/sin of the relation phases.  The per-query constant
+      // cancels inside one query's ranking (target and candidates share it); gamma <= 0 ranks by A itself: sign flips.
+      const int d = W / 2;
+      float v;
+      if (side == KGEB_SIDE_TAIL) v = 1.f;
+      else {
+        float sn, c;
+        sincosf(p[k < d ? k : k - d], &sn, &c);
+        v = k < d ? -__fadd_rn(c, sn) : -__fsub_rn(c, sn);
+      }
+      out = gamma_sub ? v : -v;
+    } else if (kind == KGEB_MODE_L1 || kind == KGEB_MODE_L2) {  // tail r = s*p - e; head r = e*p - o keeps [p | o]
+      if (side == KGEB_SIDE_TAIL) out = __fmul_rn(e[k], p[k]);
+      else out = k < W ? p[k] : e[k - W];
+    } else {  // TransE, pRotatE: tail a = s + p; head keeps [p | o] so (e + p) - o follows the reference's order
       if (side == KGEB_SIDE_TAIL) out = __fadd_rn(e[k], p[k]);
       else out = k < W ? p[k] : e[k - W];
     }
@@ -78,7 +94,7 @@ struct PairArgs {
   const float* Es; int64_t row_offset, n_rows; int ldE, W;
   const float* qvec; int qw;
   float* tscore;                 // written (TARGET) or read
-  const int32_t* triples; int64_t Q; int side; float gamma;
+  const int32_t* triples; int64_t Q; int side; SeqFin fin;
   const int64_t* offs; const int32_t* ids;          // FILTER
   const uint32_t* wl_hdr; uint32_t wl_cap; const uint2* wl;  // WORKLIST
   int32_t* counts;
@@ -86,7 +102,7 @@ struct PairArgs {
 
 template <int OP, int SRC>
 __global__ void __launch_bounds__(PAIR_WARPS * 32) k_seqk_pairs(PairArgs a) {
-  constexpr bool HEAD = (OP == OP_L1_HEAD || OP == OP_L2_HEAD);
+  constexpr bool HEAD = op_two_part<OP>();
   constexpr int LDP = 36;  // row stride in floats: 16-byte aligned rows, conflict-free LDS.128 by row (4*lane groups)
   __shared__ __align__(16) float sq[PAIR_WARPS][32][LDP];
   __shared__ __align__(16) float se[PAIR_WARPS][32][LDP];
@@ -158,7 +174,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_seqk_pairs(PairArgs a) {
       __syncwarp();
     }
     if (!valid) continue;
-    const float sc = seq_finish<OP>(acc, a.gamma);
+    const float sc = seq_finish<OP>(acc, a.fin);
     if (SRC == PAIRS_TARGET) a.tscore[q] = sc;
     else if (SRC == PAIRS_WORKLIST) { if (sc > a.tscore[q]) atomicAdd(a.counts + q, 1); }
     else { if (sc > a.tscore[q]) atomicSub(a.counts + q, 1); }
@@ -168,6 +184,10 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_seqk_pairs(PairArgs a) {
 template <int SRC>
 void launch_pairs(int op, int blocks, cudaStream_t st, const PairArgs& a) {
   switch (op) {
+    case OP_ML1_HEAD: k_seqk_pairs<OP_ML1_HEAD, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
+    case OP_ML2_HEAD: k_seqk_pairs<OP_ML2_HEAD, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
+    case OP_PSIN_TAIL: k_seqk_pairs<OP_PSIN_TAIL, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
+    case OP_PSIN_HEAD: k_seqk_pairs<OP_PSIN_HEAD, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
     case OP_DOT: k_seqk_pairs<OP_DOT, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
     case OP_L1_TAIL: k_seqk_pairs<OP_L1_TAIL, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
     case OP_L1_HEAD: k_seqk_pairs<OP_L1_HEAD, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
@@ -184,8 +204,8 @@ constexpr int BQ = 64, BN = 64, BK = 32, LDS_STRIDE = 68;
 template <int OP>
 __global__ void __launch_bounds__(256) k_rank_tile(const float* __restrict__ Es, int64_t n_rows, int ldE, int W,
                                                    const float* __restrict__ qvec, int qw, const float* __restrict__ tscore,
-                                                   int64_t Q, float gamma, int32_t* counts) {
-  constexpr bool HEAD = (OP == OP_L1_HEAD || OP == OP_L2_HEAD);
+                                                   int64_t Q, SeqFin fin, int32_t* counts) {
+  constexpr bool HEAD = op_two_part<OP>();
   __shared__ __align__(16) float As[BK][LDS_STRIDE];
   __shared__ __align__(16) float As2[HEAD ? BK : 1][LDS_STRIDE];
   __shared__ __align__(16) float Bs[BK][LDS_STRIDE];
@@ -260,7 +280,7 @@ __global__ void __launch_bounds__(256) k_rank_tile(const float* __restrict__ Es,
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int64_t n = n0 + tx * 4 + j;
-        const float sc = seq_finish<OP>(acc[i][j], gamma);
+        const float sc = seq_finish<OP>(acc[i][j], fin);
         cnt[i] += (n < n_rows && sc > tq[i]) ? 1 : 0;
       }
   }
@@ -293,15 +313,28 @@ int pairs_grid(const kgeb_ctx* ctx, int64_t pairs) {
 int host_op_for(int kind, int side) {
   if (kind == KGEB_TRANSE_L1) return side == KGEB_SIDE_TAIL ? OP_L1_TAIL : OP_L1_HEAD;
   if (kind == KGEB_TRANSE_L2) return side == KGEB_SIDE_TAIL ? OP_L2_TAIL : OP_L2_HEAD;
-  return OP_DOT;
+  if (kind == KGEB_MODE_L1) return side == KGEB_SIDE_TAIL ? OP_L1_TAIL : OP_ML1_HEAD;
+  if (kind == KGEB_MODE_L2) return side == KGEB_SIDE_TAIL ? OP_L2_TAIL : OP_ML2_HEAD;
+  if (kind == KGEB_PROTATE) return side == KGEB_SIDE_TAIL ? OP_PSIN_TAIL : OP_PSIN_HEAD;
+  return OP_DOT;  // DistMult, ComplEx, HolE, RotatE (linear in the candidate row)
+}
+
+SeqFin seq_fin(const kgeb_ctx* ctx) {
+  SeqFin f;
+  f.gamma = ctx->gamma; f.param = ctx->param;
+  f.sub = (ctx->kind == KGEB_MODE_L1 || ctx->kind == KGEB_MODE_L2 || ctx->gamma > 0.f) ? 1 : 0;
+  return f;
+}
+
+bool two_part_queries(int kind) {
+  return kind == KGEB_TRANSE_L1 || kind == KGEB_TRANSE_L2 || kind == KGEB_MODE_L1 || kind == KGEB_MODE_L2 || kind == KGEB_PROTATE;
 }
 
 }  // namespace
 
 extern "C" int kgeb_query_width(const kgeb_ctx* ctx, int side) {
   if (!ctx) return KGEB_ERR_INVALID;
-  const bool transe = ctx->kind == KGEB_TRANSE_L1 || ctx->kind == KGEB_TRANSE_L2;
-  return (transe && side == KGEB_SIDE_HEAD) ? 2 * ctx->we : ctx->we;
+  return (two_part_queries(ctx->kind) && side == KGEB_SIDE_HEAD) ? 2 * ctx->we : ctx->we;
 }
 
 extern "C" int kgeb_query_prep(kgeb_ctx* ctx, const float* E_shard, int64_t row_offset, int64_t n_rows, const float* R,
@@ -310,11 +343,12 @@ extern "C" int kgeb_query_prep(kgeb_ctx* ctx, const float* E_shard, int64_t row_
   KGEB_REQUIRE(ctx, E_shard && R && triples && qvec && Q >= 0 && n_rows >= 0 && row_offset >= 0, KGEB_ERR_INVALID,
                "query_prep: bad arguments");
   KGEB_REQUIRE(ctx, side == KGEB_SIDE_TAIL || side == KGEB_SIDE_HEAD, KGEB_ERR_INVALID, "unknown side");
-  KGEB_REQUIRE(ctx, ctx->we == ctx->wr, KGEB_ERR_UNSUPPORTED, "1-N ranking needs e_dim == r_dim");
+  KGEB_REQUIRE(ctx, ctx->kind == KGEB_ROTATE ? ctx->we == 2 * ctx->wr : ctx->we == ctx->wr, KGEB_ERR_UNSUPPORTED,
+               "1-N ranking needs e_dim == r_dim (RotatE: e_dim == 2 * r_dim)");
   if (Q == 0) return KGEB_OK;
   const int qw = kgeb_query_width(ctx, side);
   k_query_prep<<<grid1d(ctx, Q * (int64_t)qw, 256), 256, 0, (cudaStream_t)stream>>>(
-      ctx->kind, side, E_shard, row_offset, n_rows, ctx->ldE, R, ctx->ldR, ctx->we, triples, Q, qw, qvec);
+      ctx->kind, side, ctx->gamma > 0.f ? 1 : 0, E_shard, row_offset, n_rows, ctx->ldE, R, ctx->ldR, ctx->we, triples, Q, qw, qvec);
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
 }
@@ -327,7 +361,7 @@ extern "C" int kgeb_target_scores(kgeb_ctx* ctx, const float* E_shard, int64_t r
   const int qw = kgeb_query_width(ctx, side);
   PairArgs a = {};
   a.Es = E_shard; a.row_offset = row_offset; a.n_rows = n_rows; a.ldE = ctx->ldE; a.W = ctx->we; a.qvec = qvec; a.qw = qw;
-  a.tscore = tscore; a.triples = triples; a.Q = Q; a.side = side; a.gamma = ctx->gamma;
+  a.tscore = tscore; a.triples = triples; a.Q = Q; a.side = side; a.fin = seq_fin(ctx);
   launch_pairs<PAIRS_TARGET>(host_op_for(ctx->kind, side), pairs_grid(ctx, Q), (cudaStream_t)stream, a);
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
@@ -355,9 +389,14 @@ extern "C" int kgeb_rank_1n(kgeb_ctx* ctx, const float* E_shard, int64_t row_off
   if (split > 65535) split = 65535;
   dim3 grid((unsigned)qtiles, (unsigned)split);
 #define KGEB_RANK_LAUNCH(OPV) \
-  k_rank_tile<OPV><<<grid, 256, 0, st>>>(E_shard, n_rows, ctx->ldE, ctx->we, qvec, qw, tscore, Q, ctx->gamma, counts)
+  k_rank_tile<OPV><<<grid, 256, 0, st>>>(E_shard, n_rows, ctx->ldE, ctx->we, qvec, qw, tscore, Q, fin, counts)
+  const SeqFin fin = seq_fin(ctx);
   KGEB_TIME_BEGIN(ctx, KGEB_TIMED_RANK_TILE, st);
   switch (op) {
+    case OP_ML1_HEAD: KGEB_RANK_LAUNCH(OP_ML1_HEAD); break;
+    case OP_ML2_HEAD: KGEB_RANK_LAUNCH(OP_ML2_HEAD); break;
+    case OP_PSIN_TAIL: KGEB_RANK_LAUNCH(OP_PSIN_TAIL); break;
+    case OP_PSIN_HEAD: KGEB_RANK_LAUNCH(OP_PSIN_HEAD); break;
     case OP_DOT: KGEB_RANK_LAUNCH(OP_DOT); break;
     case OP_L1_TAIL: KGEB_RANK_LAUNCH(OP_L1_TAIL); break;
     case OP_L1_HEAD: KGEB_RANK_LAUNCH(OP_L1_HEAD); break;
@@ -373,6 +412,7 @@ extern "C" int kgeb_rank_1n(kgeb_ctx* ctx, const float* E_shard, int64_t row_off
 }
 
 int kgeb_internal_host_op_for(int kind, int side) { return host_op_for(kind, side); }
+kgeb_rank::SeqFin kgeb_internal_seq_fin(const kgeb_ctx* ctx) { return seq_fin(ctx); }
 
 int kgeb_internal_filter_correct(kgeb_ctx* ctx, const float* E_shard, int64_t row_offset, int64_t n_rows, const float* qvec,
                                  const float* tscore, const int32_t* triples, int64_t Q, int side,
@@ -380,7 +420,7 @@ int kgeb_internal_filter_correct(kgeb_ctx* ctx, const float* E_shard, int64_t ro
   const int qw = kgeb_query_width(ctx, side);
   PairArgs a = {};
   a.Es = E_shard; a.row_offset = row_offset; a.n_rows = n_rows; a.ldE = ctx->ldE; a.W = ctx->we; a.qvec = qvec; a.qw = qw;
-  a.tscore = const_cast<float*>(tscore); a.triples = triples; a.Q = Q; a.side = side; a.gamma = ctx->gamma;
+  a.tscore = const_cast<float*>(tscore); a.triples = triples; a.Q = Q; a.side = side; a.fin = seq_fin(ctx);
   a.offs = filt_offsets; a.ids = filt_ids; a.counts = counts;
   // nnz is on the device; size the grid from Q (lists are short) -- the kernel grid-strides over nnz
   launch_pairs<PAIRS_FILTER>(host_op_for(ctx->kind, side), pairs_grid(ctx, Q * 8), st, a);
@@ -393,7 +433,7 @@ int kgeb_internal_refine_worklist(kgeb_ctx* ctx, const float* E_shard, int64_t n
                                   cudaStream_t st) {
   PairArgs a = {};
   a.Es = E_shard; a.row_offset = 0; a.n_rows = n_rows; a.ldE = ctx->ldE; a.W = ctx->we; a.qvec = qvec;
-  a.qw = kgeb_query_width(ctx, side); a.tscore = const_cast<float*>(tscore); a.Q = Q; a.side = side; a.gamma = ctx->gamma;
+  a.qw = kgeb_query_width(ctx, side); a.tscore = const_cast<float*>(tscore); a.Q = Q; a.side = side; a.fin = seq_fin(ctx);
   a.wl_hdr = wl_hdr; a.wl_cap = wl_cap; a.wl = wl; a.counts = counts;
   launch_pairs<PAIRS_WORKLIST>(host_op_for(ctx->kind, side), ctx->num_sms * 16, st, a);
   KGEB_LAUNCH_OK(ctx);

@@ -433,7 +433,7 @@ __global__ void k_tc_slice_max(const float* __restrict__ norms, int64_t nslices,
 int tc_planes(int mode) { return mode == KGEB_TC_BF16X3_EXACT ? 2 : 1; }
 int tc_nkc(const kgeb_ctx* ctx) { return ((ctx->we + 15) / 16) * 2; }  // K padded to 16, in 8-element chunks
 int64_t tc_tiles(int64_t rows, int tile_rows) { return (rows + tile_rows - 1) / tile_rows; }
-bool tc_kind_ok(const kgeb_ctx* ctx) { return ctx->kind == KGEB_DISTMULT || ctx->kind == KGEB_COMPLEX || ctx->kind == KGEB_HOLE; }
+bool tc_kind_ok(const kgeb_ctx* ctx) { return ctx->kind == KGEB_DISTMULT || ctx->kind == KGEB_COMPLEX || ctx->kind == KGEB_HOLE || ctx->kind == KGEB_ROTATE; }
 size_t tc_align(size_t x) { return (x + 255) & ~(size_t)255; }
 
 int tc_grid(const kgeb_ctx* ctx, int64_t n, int threads) {
@@ -454,7 +454,7 @@ extern "C" int64_t kgeb_rank_tc_packed_bytes(const kgeb_ctx* ctx, int64_t n_rows
 extern "C" int kgeb_rank_tc_pack_entities(kgeb_ctx* ctx, const float* E_shard, int64_t n_rows, int mode, void* packed,
                                           int64_t packed_bytes, kgeb_stream stream) {
   if (!ctx) return KGEB_ERR_INVALID;
-  KGEB_REQUIRE(ctx, tc_kind_ok(ctx), KGEB_ERR_UNSUPPORTED, "tensor-core ranking serves DistMult, ComplEx and HolE (dot-product queries)");
+  KGEB_REQUIRE(ctx, tc_kind_ok(ctx), KGEB_ERR_UNSUPPORTED, "tensor-core ranking serves DistMult, ComplEx, HolE and RotatE (dot-product queries)");
   KGEB_REQUIRE(ctx, E_shard && packed && n_rows > 0, KGEB_ERR_INVALID, "rank_tc_pack_entities: bad arguments");
   KGEB_REQUIRE(ctx, mode == KGEB_TC_BF16 || mode == KGEB_TC_BF16X3_EXACT, KGEB_ERR_INVALID, "unknown tensor-core mode");
   KGEB_REQUIRE(ctx, ctx->we % 4 == 0 && ctx->ldE % 4 == 0 && kgeb_aligned16(E_shard) && kgeb_aligned16(packed), KGEB_ERR_ALIGNMENT,
@@ -487,7 +487,7 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
                                const int64_t* filt_offsets, const int32_t* filt_ids, int mode, void* workspace,
                                int64_t workspace_bytes, int64_t worklist_cap, int32_t* counts, kgeb_stream stream) {
   if (!ctx) return KGEB_ERR_INVALID;
-  KGEB_REQUIRE(ctx, tc_kind_ok(ctx), KGEB_ERR_UNSUPPORTED, "tensor-core ranking serves DistMult, ComplEx and HolE (dot-product queries)");
+  KGEB_REQUIRE(ctx, tc_kind_ok(ctx), KGEB_ERR_UNSUPPORTED, "tensor-core ranking serves DistMult, ComplEx, HolE and RotatE (dot-product queries)");
   KGEB_REQUIRE(ctx, E_shard && packedE && qvec && tscore && triples && counts && workspace && Q >= 0 && n_rows >= 0 && row_offset >= 0,
                KGEB_ERR_INVALID, "rank_1n_tc: bad arguments");
   KGEB_REQUIRE(ctx, side == KGEB_SIDE_TAIL || side == KGEB_SIDE_HEAD, KGEB_ERR_INVALID, "unknown side");

@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_score_fwd(ScoreArgs a, const i
     const int s = __ldg(idx + 3 * t), p = __ldg(idx + 3 * t + 1), o = __ldg(idx + 3 * t + 2);
     Frag<KIND, NC> S, P, O;
     load_frag(S, a.E, s, a.ldE, a.ge, lane);
-    load_frag(P, a.R, p, a.ldR, a.gr, lane);
+    load_frag<KIND, NC, true>(P, a.R, p, a.ldR, a.gr, lane);
     load_frag(O, a.E, o, a.ldE, a.ge, lane);
     if (DP) {
       dp_apply(S, dp_bits<KIND, NC>(a.dp, 0, a.dp_stream, (uint64_t)t, lane), a.dp.scale);
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_score_fwd(ScoreArgs a, const i
       dp_apply(O, dp_bits<KIND, NC>(a.dp, 2, a.dp_stream, (uint64_t)t, lane), a.dp.scale);
     }
     const float sum = warp_sum(score_partial(S, P, O));
-    if (lane == 0) out[t] = score_finish<KIND>(sum, a.gamma);
+    if (lane == 0) out[t] = score_finish<KIND>(sum, a.gamma, a.param);
   }
 }
 
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_score_bwd(ScoreArgs a, const i
     if (coef == 0.f) continue;
     Frag<KIND, NC> S, P, O, GS, GP, GO;
     load_frag(S, a.E, s, a.ldE, a.ge, lane);
-    load_frag(P, a.R, p, a.ldR, a.gr, lane);
+    load_frag<KIND, NC, true>(P, a.R, p, a.ldR, a.gr, lane);
     load_frag(O, a.E, o, a.ldE, a.ge, lane);
     uint32_t mS = 0, mP = 0, mO = 0;
     if (DP) {
@@ -60,11 +60,11 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_score_bwd(ScoreArgs a, const i
       dp_apply(S, mS, a.dp.scale); dp_apply(P, mP, a.dp.scale); dp_apply(O, mO, a.dp.scale);
     }
     float sum = 0.f;
-    if (KIND == TRANSE_L2) sum = warp_sum(score_partial(S, P, O));
-    score_grads(S, P, O, coef, sum, a.gamma, GS, GP, GO);
+    if (KIND == TRANSE_L2 || KIND == MODE_L2) sum = warp_sum(score_partial(S, P, O));
+    score_grads(S, P, O, coef, sum, a.gamma, GS, GP, GO, a.param);
     if (DP) { dp_apply(GS, mS, a.dp.scale); dp_apply(GP, mP, a.dp.scale); dp_apply(GO, mO, a.dp.scale); }
     red_frag(gE, s, a.ldE, a.ge, lane, GS);
-    red_frag(gR, p, a.ldR, a.gr, lane, GP);
+    red_frag<KIND, NC, true>(gR, p, a.ldR, a.gr, lane, GP);
     red_frag(gE, o, a.ldE, a.ge, lane, GO);
   }
 }
@@ -220,9 +220,9 @@ extern "C" int kgeb_score_fwd(kgeb_ctx* ctx, const float* E, const float* R, con
     return KGEB_OK;
   }
   if (a.dp.thr) {
-    KGEB_DISPATCH_KIND(ctx->kind, KGEB_DISPATCH_NC(nc, (k_score_fwd<KIND, NC, true><<<grid, KGEB_THREADS, 0, st>>>(a, idx, m, scores))));
+    KGEB_DISPATCH_KIND_ALL(ctx->kind, KGEB_DISPATCH_NC(nc, (k_score_fwd<KIND, NC, true><<<grid, KGEB_THREADS, 0, st>>>(a, idx, m, scores))));
   } else {
-    KGEB_DISPATCH_KIND(ctx->kind, KGEB_DISPATCH_NC(nc, (k_score_fwd<KIND, NC, false><<<grid, KGEB_THREADS, 0, st>>>(a, idx, m, scores))));
+    KGEB_DISPATCH_KIND_ALL(ctx->kind, KGEB_DISPATCH_NC(nc, (k_score_fwd<KIND, NC, false><<<grid, KGEB_THREADS, 0, st>>>(a, idx, m, scores))));
   }
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
@@ -252,10 +252,10 @@ extern "C" int kgeb_score_bwd(kgeb_ctx* ctx, const float* E, const float* R, con
     return KGEB_OK;
   }
   if (a.dp.thr) {
-    KGEB_DISPATCH_KIND(ctx->kind, KGEB_DISPATCH_NC(nc, (k_score_bwd<KIND, NC, true><<<grid, KGEB_THREADS, 0, st>>>(
+    KGEB_DISPATCH_KIND_ALL(ctx->kind, KGEB_DISPATCH_NC(nc, (k_score_bwd<KIND, NC, true><<<grid, KGEB_THREADS, 0, st>>>(
                                                            a, idx, m, dscore, gE, gR, touchedE, touchedR))));
   } else {
-    KGEB_DISPATCH_KIND(ctx->kind, KGEB_DISPATCH_NC(nc, (k_score_bwd<KIND, NC, false><<<grid, KGEB_THREADS, 0, st>>>(
+    KGEB_DISPATCH_KIND_ALL(ctx->kind, KGEB_DISPATCH_NC(nc, (k_score_bwd<KIND, NC, false><<<grid, KGEB_THREADS, 0, st>>>(
                                                            a, idx, m, dscore, gE, gR, touchedE, touchedR))));
   }
   KGEB_LAUNCH_OK(ctx);

@@ -19,6 +19,7 @@ DISTMULT, TRANSE_L1, TRANSE_L2, COMPLEX, HOLE = 0, 1, 2, 3, 4
 ROTATE, PROTATE, MODE_L1, MODE_L2 = 5, 6, 7, 8
 SCORE_KINDS = {"DistMult": DISTMULT, "TransE_L1": TRANSE_L1, "TransE_L2": TRANSE_L2,
                "ComplEx": COMPLEX, "HolE": HOLE}
+SIBLING_KINDS = {"RotatE": ROTATE, "pRotatE": PROTATE, "ModE_L1": MODE_L1, "ModE_L2": MODE_L2}
 
 # loss kinds -- shared with kgeb_loss_kind
 POINTWISE_HINGE, POINTWISE_LOGISTIC, POINTWISE_SQUARE, PAIRWISE_HINGE, PAIRWISE_LOGISTIC, PAIRWISE_SQUARE = range(6)
@@ -144,6 +145,12 @@ def score_abs_terms(kind, E, R, idx, gamma=12.0):
         return np.sum(a * b * c, axis=-1)
     if kind == HOLE:
         return np.sum(np.abs(p) * circular_correlation_direct(np.abs(s), np.abs(o)), axis=-1)
+    if kind == ROTATE:    # |re_s| + |im_s| bounds both rotated components; plus the candidate's own entries
+        return np.abs(gamma) + 2.0 * np.sum(np.abs(s), axis=-1) + np.sum(np.abs(o), axis=-1)
+    if kind == PROTATE:   # d|sin(y/2)|/dy <= 1/2: the argument's rounding scale bounds the term's
+        return np.abs(gamma) + np.sum(np.abs(s) + np.abs(p) + np.abs(o), axis=-1)
+    if kind in (MODE_L1, MODE_L2):
+        return np.abs(gamma) + np.sum(np.abs(s * p) + np.abs(o), axis=-1)
     raise KeyError(kind)
 
 
@@ -640,7 +647,8 @@ def dropout_keep(kind, width, n, slot, stream, p, seed, offset):
     """(n, width) bool keep mask of row-slot `slot` (0/1/2 = s/p/o) for the n triples of call `stream` (0 = positive call,
     1 = negative call).  16 Philox bits per element, keep iff bits >= round(p*65536).  `width` = stored row width."""
     thr = int(p * 65536.0 + 0.5)
-    if kind == COMPLEX:
+    split = kind == COMPLEX or (kind == ROTATE and slot != 1)   # RotatE: entity rows are [re | im], the relation row is plain
+    if split:
         d = width // 2
         nch = d // 4
     else:
@@ -648,7 +656,7 @@ def dropout_keep(kind, width, n, slot, stream, p, seed, offset):
         nch = (width + 3) // 4
     NC = (nch + 31) // 32
     x = np.arange(width)
-    half = (x >= d).astype(np.int64) if kind == COMPLEX else np.zeros(width, np.int64)
+    half = (x >= d).astype(np.int64) if split else np.zeros(width, np.int64)
     xx = x - half * d
     chunk, e = xx // 4, xx % 4
     lane, i = chunk % 32, chunk // 32
