@@ -157,6 +157,13 @@ KGEB_API int kgeb_opt_update(kgeb_ctx* ctx, float* P, float* G, uint8_t* touched
                     float* state0, float* state1, int opt_kind, float lr, float beta1, float beta2, float eps,
                     int64_t step, kgeb_stream stream);
 
+/* The same update on two tables (entity + relation) in one launch: the relation table of the bundled datasets has 11-237
+ * rows, so its own launch is pure latency. */
+KGEB_API int kgeb_opt_update2(kgeb_ctx* ctx, float* P0, float* G0, uint8_t* touched0, int64_t rows0, int width0, int ld0,
+                     float* state00, float* state01, float* P1, float* G1, uint8_t* touched1, int64_t rows1, int width1,
+                     int ld1, float* state10, float* state11, int opt_kind, float lr, float beta1, float beta2, float eps,
+                     int64_t step, kgeb_stream stream);
+
 /* ---- 1-N filtered ranking: validate / gen_tail_data / gen_head_data, utils.py:165-264 --------------------- */
 /* Width in floats of one query vector for `side` (we, or 2*we for TransE head queries). */
 KGEB_API int kgeb_query_width(const kgeb_ctx* ctx, int side);

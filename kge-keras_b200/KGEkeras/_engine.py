@@ -5,6 +5,7 @@ hand-written sm_100a kernels behind the C ABI.  There is no CPU path: constructi
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -231,10 +232,16 @@ class Engine:
         self._ensure_train_buffers(opt_kind)
         self.step += 1
         _, m_e, v_e, m_r, v_r = self.opt_state
-        self._check(self.lib.kgeb_opt_update(self.ctx, _ptr(self.E), _ptr(self.gE), _ptr(self.tE), self.N, self.we_k, self.we_k,
-                                             _ptr(m_e), _ptr(v_e), opt_kind, lr, beta1, beta2, eps, self.step, _stream()))
-        self._check(self.lib.kgeb_opt_update(self.ctx, _ptr(self.Rel), _ptr(self.gR), _ptr(self.tR), self.R_, self.wr_k, self.wr_k,
-                                             _ptr(m_r), _ptr(v_r), opt_kind, lr, beta1, beta2, eps, self.step, _stream()))
+        if os.environ.get("KGEB_OPT_FUSED", "1") == "0":   # A/B switch: one launch per table
+            self._check(self.lib.kgeb_opt_update(self.ctx, _ptr(self.E), _ptr(self.gE), _ptr(self.tE), self.N, self.we_k, self.we_k,
+                                                 _ptr(m_e), _ptr(v_e), opt_kind, lr, beta1, beta2, eps, self.step, _stream()))
+            self._check(self.lib.kgeb_opt_update(self.ctx, _ptr(self.Rel), _ptr(self.gR), _ptr(self.tR), self.R_, self.wr_k, self.wr_k,
+                                                 _ptr(m_r), _ptr(v_r), opt_kind, lr, beta1, beta2, eps, self.step, _stream()))
+            return
+        # entity and relation table in one launch
+        self._check(self.lib.kgeb_opt_update2(self.ctx, _ptr(self.E), _ptr(self.gE), _ptr(self.tE), self.N, self.we_k, self.we_k,
+                                              _ptr(m_e), _ptr(v_e), _ptr(self.Rel), _ptr(self.gR), _ptr(self.tR), self.R_, self.wr_k,
+                                              self.wr_k, _ptr(m_r), _ptr(v_r), opt_kind, lr, beta1, beta2, eps, self.step, _stream()))
 
     def l3_reg(self, w, loss):
         """models.py:10-11,79-82: loss += w*sum|E|^3, gE += 3 w E|E| on every entity row (the relation table is not regularised)."""
