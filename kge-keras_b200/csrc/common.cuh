@@ -140,15 +140,21 @@ __device__ __forceinline__ void block_finalize_loss(double a, double b, double* 
     is_last = (t == gridDim.x - 1);
   }
   __syncthreads();
-  if (is_last && threadIdx.x == 0) {
+  if (is_last && threadIdx.x < 32) {
+    // warp 0 of the last block: lane-strided partial sums in a fixed order, then a fixed butterfly -> deterministic, and
+    // the gridDim.x * 2 partials are fetched 32 at a time instead of one dependent load after the other
     __threadfence();
     double sa = 0, sb = 0;
-    for (unsigned int i = 0; i < gridDim.x; ++i) {  // fixed order -> deterministic
+    for (unsigned int i = lane; i < gridDim.x; i += 32) {
       sa += ((volatile double*)partials)[2 * i];
       sb += ((volatile double*)partials)[2 * i + 1];
     }
-    if (out) out[0] = (float)(scale0 * sa + scale1 * sb);
-    *ticket = 0u;
+    sa = warp_sum_d(sa);
+    sb = warp_sum_d(sb);
+    if (lane == 0) {
+      if (out) out[0] = (float)(scale0 * sa + scale1 * sb);
+      *ticket = 0u;
+    }
   }
 }
 
