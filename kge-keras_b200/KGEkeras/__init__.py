@@ -6,3 +6,4 @@ model does need a GPU (there is no CPU fallback)."""
 __version__ = '0.1.0'
 from .models import *  # noqa: F401,F403
 from .utils import *   # noqa: F401,F403
+from .data import DataGenerator, build_mappings, load_dataset, map_triples  # noqa: F401

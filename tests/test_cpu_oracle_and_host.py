@@ -329,3 +329,90 @@ def test_abi_library_exports_header_symbols():
         h = ctypes.c_void_p()
         rc = _abi.lib().kgeb_create(ctypes.byref(h), 0, 10, 3, 8, 8, 8, 8, 0, 12.0)
         assert rc < 0 and not h.value and b"CUDA" in _abi.lib().kgeb_last_error(None)
+
+
+# ---- dataset ingestion ----------------------------------------------------------------------------
+def _write_split(path, rows):
+    with open(path, "w") as f:
+        for r in rows:
+            f.write("\t".join(r) + "\n")
+
+
+def test_load_dataset_sorted_mapping_and_cache(tmp_path):
+    from KGEkeras import data as kd
+    d = tmp_path / "toy"
+    d.mkdir()
+    train = [("b", "likes", "a"), ("c", "knows", "b"), ("a", "likes", "c")]
+    valid = [("d", "likes", "a")]
+    test = [("a", "knows", "d")]
+    for name, rows in (("train", train), ("valid", valid), ("test", test)):
+        _write_split(d / f"{name}.txt", rows)
+    ds = kd.load_dataset(str(d), cache_dir=str(tmp_path / "cache"))
+    assert ds["entities"] == ["a", "b", "c", "d"] and ds["relations"] == ["knows", "likes"]
+    assert ds["num_entities"] == 4 and ds["num_relations"] == 2
+    np.testing.assert_array_equal(ds["train"], np.asarray([[1, 1, 0], [2, 0, 1], [0, 1, 2]], np.int32))
+    np.testing.assert_array_equal(ds["valid"], [[3, 1, 0]])
+    np.testing.assert_array_equal(ds["test"], [[0, 0, 3]])
+    # second call is served from the cache and is identical
+    assert len(os.listdir(tmp_path / "cache")) == 1
+    ds2 = kd.load_dataset(str(d), cache_dir=str(tmp_path / "cache"))
+    for k in ("train", "valid", "test"):
+        np.testing.assert_array_equal(ds[k], ds2[k])
+    assert ds2["entities"] == ds["entities"] and ds2["num_relations"] == 2
+    # a changed file invalidates the cache key
+    _write_split(d / "test.txt", test + [("e", "knows", "a")])
+    os.utime(d / "test.txt", ns=(10 ** 18, 10 ** 18))
+    ds3 = kd.load_dataset(str(d), cache_dir=str(tmp_path / "cache"))
+    assert ds3["num_entities"] == 5
+    # error behaviour: a missing split and a malformed line
+    os.remove(d / "valid.txt")
+    with pytest.raises(FileNotFoundError):
+        kd.load_dataset(str(d))
+    with pytest.raises(ValueError):
+        kd.build_mappings([["a", "b"]])
+    with pytest.raises(KeyError):
+        kd.map_triples([("zz", "likes", "a")], {"a": 0}, {"likes": 0})
+
+
+@pytest.mark.skipif(not ref_ast.available(), reason="/root/reference not mounted (GPU box)")
+def test_load_dataset_matches_committed_fixture_on_kinship():
+    from KGEkeras import data as kd
+    ds = kd.load_dataset("/root/reference/data/kinship")
+    gold = load_dataset("kinship")
+    assert ds["num_entities"] == gold["N"] and ds["num_relations"] == gold["R"]
+    for k in ("train", "valid", "test"):
+        np.testing.assert_array_equal(ds[k], gold[k])
+
+
+def test_data_generator_host_path_consumes_rng_like_the_harness():
+    """tests.py:29-61 restated literally (set-based num_e, index shuffling, generate_negative + oversample_data) against
+    KGEkeras.data.DataGenerator under the same global seeds."""
+    import random
+    from KGEkeras import data as kd
+    from KGEkeras import utils as ku
+    rng = np.random.default_rng(3)
+    kg = [tuple(int(x) for x in r) for r in np.stack([rng.integers(0, 50, 200), rng.integers(0, 4, 200), rng.integers(0, 50, 200)], 1)]
+
+    def harness_batches(seed, bs, ns, nb):
+        np.random.seed(seed); random.seed(seed)
+        num_e = len(set([s for s, _, _ in kg]) | set([o for _, _, o in kg]))
+        indices = list(range(len(kg)))
+        index = np.arange(len(indices))
+        np.random.shuffle(index)
+        out = []
+        for b in range(nb):
+            sel = index[b * bs:(b + 1) * bs]
+            tmp = np.asarray([kg[indices[k]] for k in sel])
+            neg = ku.generate_negative(tmp, N=num_e, negative=ns)
+            out.append(ku.oversample_data(kgs=[tmp, neg]))
+        return out
+
+    want = harness_batches(11, 32, 5, 3)
+    np.random.seed(11); random.seed(11)
+    gen = kd.DataGenerator(kg, ns=5, batch_size=32)
+    assert len(gen) == 200 // 32
+    for b in range(3):
+        (pos, neg), y = gen[b]
+        assert y is None
+        np.testing.assert_array_equal(pos, want[b][0])
+        np.testing.assert_array_equal(neg, want[b][1])

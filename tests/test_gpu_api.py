@@ -211,3 +211,31 @@ def test_sharded_validate_equals_single_gpu_emulated():
             for r in range(world):
                 acc += eng.rank_counts(test, code, offs, ids, row_range=ku.shard_rows(ds["N"], world, r))
             np.testing.assert_array_equal(acc.cpu().numpy() + 1, want)
+
+
+def test_fit_with_device_side_data_generator():
+    """The harness' own loop (tests.py:130-134) with KGEkeras.DataGenerator: host batches (reference RNG consumption) and
+    device batches (Philox negatives + oversampling on the GPU, nothing crosses PCIe) both train the all-pairs hinge."""
+    import KGEkeras
+    from KGEkeras import utils as ku
+    np.random.seed(0)
+    random.seed(0)
+    ds = load_dataset("kinship")
+    test = ds["test"][:200]
+    filt = np.concatenate([ds["train"], ds["valid"]])
+    for device_side in (False, True):
+        m = make_model("DistMult", ds["N"], ds["R"], 32, loss_function="pairwize_hinge", negative_samples=4, margin=1, batch_size=512)
+        m.pair_mode = "allpairs"
+        m.compile(optimizer=type("Adam", (), {"learning_rate": 0.02})())
+        gen = KGEkeras.DataGenerator(ds["train"], ns=4, batch_size=512, engine=m._engine_() if device_side else None, seed=5)
+        (pos, neg), y = gen[0]
+        assert y is None and tuple(pos.shape) == (2048, 3) and tuple(neg.shape) == (2048, 3)
+        if device_side:
+            assert pos.is_cuda and neg.is_cuda
+            # every oversampled positive is a row of the batch, every negative keeps a relation of the batch
+            assert int(neg[:, [0, 2]].max()) < ds["N"]
+        before = ku.validate(m, test, ds["N"], 32, filt)
+        hist = m.fit(gen, epochs=6, verbose=0)
+        after = ku.validate(m, test, ds["N"], 32, filt)
+        assert hist.history["loss"][-1] < hist.history["loss"][0]
+        assert after["mrr"] > before["mrr"] * 1.5, (device_side, before["mrr"], after["mrr"])
