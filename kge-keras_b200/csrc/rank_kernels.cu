@@ -197,22 +197,30 @@ void launch_pairs(int op, int blocks, cudaStream_t st, const PairArgs& a) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// the tile kernel: CTA = 64 queries x (a strided set of 64-entity tiles); thread = 4 x 4 micro-tile
+// the tile kernel: CTA = 64 queries x (a strided set of 64-entity tiles); thread = 4 x 4 micro-tile of INTERLEAVED rows
+// (queries ty + 16 i, entities tx + 16 j).  Tiles sit in shared memory as they sit in global memory -- row major, k
+// contiguous, rows padded to 36 floats -- so a tile arrives by plain 128-bit stores (no transposing scalar stores, no
+// bank conflicts) and a thread fetches 4 consecutive k of a row with one LDS.128: the 8 threads of a quarter warp read
+// 8 consecutive entity rows = 32 distinct banks, and one query row (broadcast).  Shared memory is double buffered: the
+// next k-chunk is fetched into registers before the current one is consumed and stored into the other buffer behind it,
+// one __syncthreads per chunk.  Per (query, entity) pair the terms are still accumulated in k order.
 // ---------------------------------------------------------------------------------------------------
-constexpr int BQ = 64, BN = 64, BK = 32, LDS_STRIDE = 68;
+constexpr int BQ = 64, BN = 64, BK = 32, BKP = 36;
 
 template <int OP>
 __global__ void __launch_bounds__(256) k_rank_tile(const float* __restrict__ Es, int64_t n_rows, int ldE, int W,
                                                    const float* __restrict__ qvec, int qw, const float* __restrict__ tscore,
                                                    int64_t Q, SeqFin fin, int32_t* counts) {
   constexpr bool HEAD = op_two_part<OP>();
-  __shared__ __align__(16) float As[BK][LDS_STRIDE];
-  __shared__ __align__(16) float As2[HEAD ? BK : 1][LDS_STRIDE];
-  __shared__ __align__(16) float Bs[BK][LDS_STRIDE];
+  extern __shared__ __align__(16) float tile_smem[];
+  typedef float (*TileBuf)[BQ][BKP];   // [buffer][row][k]
+  TileBuf As = reinterpret_cast<TileBuf>(tile_smem);
+  TileBuf Bs = reinterpret_cast<TileBuf>(tile_smem + 2 * BQ * BKP);
+  TileBuf As2 = reinterpret_cast<TileBuf>(tile_smem + 4 * BQ * BKP);   // two-part (head) queries only
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int64_t q0 = (int64_t)blockIdx.x * BQ;
   const int64_t ntiles = (n_rows + BN - 1) / BN;
-  // loader mapping: 8 float4 per 32-float k-chunk row, 32 rows per pass, 2 passes
+  // loader mapping: a 32-float k-chunk of a row is 8 float4; 32 rows per pass, 2 passes
   const int lr = tid >> 3, lk4 = tid & 7;
   const int nkc = (W + BK - 1) / BK;
 
@@ -220,7 +228,7 @@ __global__ void __launch_bounds__(256) k_rank_tile(const float* __restrict__ Es,
   int cnt[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int64_t q = q0 + ty * 4 + i;
+    const int64_t q = q0 + ty + 16 * i;
     tq[i] = q < Q ? __ldg(tscore + q) : 0.f;
   }
 
@@ -235,51 +243,63 @@ __global__ void __launch_bounds__(256) k_rank_tile(const float* __restrict__ Es,
     float4 ra[2], ra2[2], rb[2];
     auto gload = [&](int kc) {
       const int k = kc * BK + lk4 * 4;
+      const bool kin = k < W;   // W % 4 == 0: a float4 is entirely inside or outside the row
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int64_t q = q0 + lr + 32 * h;
         const int64_t n = n0 + lr + 32 * h;
-        const bool kin = k < W;
         ra[h] = (kin && q < Q) ? ldg4(reinterpret_cast<const float4*>(qvec + q * (int64_t)qw + k)) : f4zero();
         if (HEAD) ra2[h] = (kin && q < Q) ? ldg4(reinterpret_cast<const float4*>(qvec + q * (int64_t)qw + W + k)) : f4zero();
         rb[h] = (kin && n < n_rows) ? ldg4(reinterpret_cast<const float4*>(Es + n * (int64_t)ldE + k)) : f4zero();
       }
     };
-    auto sstore = [&]() {
+    auto sstore = [&](int buf) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int r = lr + 32 * h, kk = lk4 * 4;
-        As[kk + 0][r] = ra[h].x; As[kk + 1][r] = ra[h].y; As[kk + 2][r] = ra[h].z; As[kk + 3][r] = ra[h].w;
-        if (HEAD) { As2[kk + 0][r] = ra2[h].x; As2[kk + 1][r] = ra2[h].y; As2[kk + 2][r] = ra2[h].z; As2[kk + 3][r] = ra2[h].w; }
-        Bs[kk + 0][r] = rb[h].x; Bs[kk + 1][r] = rb[h].y; Bs[kk + 2][r] = rb[h].z; Bs[kk + 3][r] = rb[h].w;
+        const int r = lr + 32 * h;
+        *reinterpret_cast<float4*>(&As[buf][r][lk4 * 4]) = ra[h];
+        if (HEAD) *reinterpret_cast<float4*>(&As2[buf][r][lk4 * 4]) = ra2[h];
+        *reinterpret_cast<float4*>(&Bs[buf][r][lk4 * 4]) = rb[h];
       }
     };
 
+    __syncthreads();   // the previous tile's last chunk is fully consumed before its buffer is overwritten
     gload(0);
+    sstore(0);
+    __syncthreads();
     for (int kc = 0; kc < nkc; ++kc) {
-      __syncthreads();  // previous chunk fully consumed
-      sstore();
-      __syncthreads();
+      const int buf = kc & 1;
       if (kc + 1 < nkc) gload(kc + 1);  // in flight while this chunk is computed
-      const int klim = (W - kc * BK) < BK ? (W - kc * BK) : BK;
-#pragma unroll 4
-      for (int k = 0; k < klim; ++k) {
-        const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-        float4 a2 = f4zero();
-        if (HEAD) a2 = *reinterpret_cast<const float4*>(&As2[k][ty * 4]);
-        const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-        const float av[4] = {a.x, a.y, a.z, a.w}, a2v[4] = {a2.x, a2.y, a2.z, a2.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      const int klim = (W - kc * BK) < BK ? (W - kc * BK) : BK;   // multiple of 4
+#pragma unroll 2
+      for (int k = 0; k < klim; k += 4) {
+        float4 a[4], a2[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          a[i] = *reinterpret_cast<const float4*>(&As[buf][ty + 16 * i][k]);
+          a2[i] = HEAD ? *reinterpret_cast<const float4*>(&As2[buf][ty + 16 * i][k]) : f4zero();
+          b[i] = *reinterpret_cast<const float4*>(&Bs[buf][tx + 16 * i][k]);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = seq_term<OP>(acc[i][j], av[i], a2v[i], bv[j]);
+          for (int j = 0; j < 4; ++j) {
+            float c = acc[i][j];
+            c = seq_term<OP>(c, a[i].x, a2[i].x, b[j].x);
+            c = seq_term<OP>(c, a[i].y, a2[i].y, b[j].y);
+            c = seq_term<OP>(c, a[i].z, a2[i].z, b[j].z);
+            c = seq_term<OP>(c, a[i].w, a2[i].w, b[j].w);
+            acc[i][j] = c;
+          }
       }
+      if (kc + 1 < nkc) sstore(buf ^ 1);   // the other buffer was last read in iteration kc - 1, before the barrier below
+      __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int64_t n = n0 + tx * 4 + j;
+        const int64_t n = n0 + tx + 16 * j;
         const float sc = seq_finish<OP>(acc[i][j], fin);
         cnt[i] += (n < n_rows && sc > tq[i]) ? 1 : 0;
       }
@@ -290,7 +310,7 @@ __global__ void __launch_bounds__(256) k_rank_tile(const float* __restrict__ Es,
     int c = cnt[i];
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    const int64_t q = q0 + ty * 4 + i;
+    const int64_t q = q0 + ty + 16 * i;
     if (tx == 0 && q < Q && c != 0) atomicAdd(counts + q, c);
   }
 }
@@ -388,8 +408,12 @@ extern "C" int kgeb_rank_1n(kgeb_ctx* ctx, const float* E_shard, int64_t row_off
   if (split < 1) split = 1;
   if (split > 65535) split = 65535;
   dim3 grid((unsigned)qtiles, (unsigned)split);
-#define KGEB_RANK_LAUNCH(OPV) \
-  k_rank_tile<OPV><<<grid, 256, 0, st>>>(E_shard, n_rows, ctx->ldE, ctx->we, qvec, qw, tscore, Q, fin, counts)
+#define KGEB_RANK_LAUNCH(OPV)                                                                                               \
+  {                                                                                                                         \
+    const size_t tsm = (size_t)(op_two_part<OPV>() ? 6 : 4) * BQ * BKP * sizeof(float);                                     \
+    KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_rank_tile<OPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));       \
+    k_rank_tile<OPV><<<grid, 256, tsm, st>>>(E_shard, n_rows, ctx->ldE, ctx->we, qvec, qw, tscore, Q, fin, counts);         \
+  }
   const SeqFin fin = seq_fin(ctx);
   KGEB_TIME_BEGIN(ctx, KGEB_TIMED_RANK_TILE, st);
   switch (op) {
