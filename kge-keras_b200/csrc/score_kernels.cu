@@ -70,42 +70,91 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_score_bwd(ScoreArgs a, const i
 }
 
 // ---------------------------------------------------------------------------------------------------
-// HolE: f = sum_k p_k sum_i s_i o_{(i+k) mod d}; rows staged in shared memory, O(d^2/32) per lane
+// HolE: f = sum_k p_k x_k,  x_k = sum_i s_i o_{(i+k) mod d}  (circular correlation, models.py:231-237), O(d^2) per triple.
+// One warp per triple; lane l owns 8 CONSECUTIVE k (k0 = 8 l + 256 pass), so for a block of 8 consecutive i the 64 products
+// s_{i+u} o_{i+u+k0+m} read a sliding window of 16 o-values: 2 + 4 LDS.128 per 64 FMA instead of two loads per FMA.  Rows
+// are staged in shared memory, the candidate row twice in a row (o2[x] = o[x mod d]) so the window needs no modulo, the
+// multiplier row zero-padded to a multiple of 8.  Each x_k is still accumulated over i in ascending order with fmaf.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void hole_stage(float* dst, const float* __restrict__ src, int d, int lane, const DropArgs& dp, int slot,
-                                           int stream, uint64_t g) {
-  for (int i = lane; i < d; i += 32) {
+__device__ __forceinline__ int hole_dpad(int d) { return (d + 7) & ~7; }
+// per-warp staging sizes in floats
+__device__ __host__ __forceinline__ int hole_lin(int d) { return ((d + 7) & ~7); }               // zero-padded row
+__device__ __host__ __forceinline__ int hole_dbl(int d) { return 2 * ((d + 7) & ~7) + 32; }      // doubled (circular) row
+
+// dst[x] = row[(x - shift) mod d] for x < len (shift = 0: plain doubling), dropout applied per element
+__device__ __forceinline__ void hole_stage_circ(float* dst, const float* __restrict__ src, int d, int len, int shift, int lane,
+                                                const DropArgs& dp, int slot, int stream, uint64_t g) {
+  for (int x = lane; x < len; x += 32) {
+    int i = (x - shift) % d;
+    if (i < 0) i += d;
     float v = __ldg(src + i);
     if (dp.thr) v = dp_keep_elem(dp, slot, stream, g, i) ? __fmul_rn(v, dp.scale) : 0.f;
+    dst[x] = v;
+  }
+}
+// dst[i] = row[i] for i < d, 0 up to the padded length
+__device__ __forceinline__ void hole_stage_lin(float* dst, const float* __restrict__ src, int d, int lane, const DropArgs& dp, int slot,
+                                               int stream, uint64_t g) {
+  const int dp8 = hole_lin(d);
+  for (int i = lane; i < dp8; i += 32) {
+    float v = 0.f;
+    if (i < d) {
+      v = __ldg(src + i);
+      if (dp.thr) v = dp_keep_elem(dp, slot, stream, g, i) ? __fmul_rn(v, dp.scale) : 0.f;
+    }
     dst[i] = v;
+  }
+}
+__device__ __forceinline__ void ld8(float (&v)[8], const float* p) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld16(float (&v)[16], const float* p) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 a = *reinterpret_cast<const float4*>(p + 4 * q);
+    v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
   }
 }
 
 __global__ void __launch_bounds__(KGEB_THREADS) k_hole_fwd(ScoreArgs a, int d, const int32_t* __restrict__ idx, int64_t m,
                                                            float* __restrict__ out) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float* ss = smem + (size_t)w * 2 * d;
-  float* so = ss + d;
+  const int dl = hole_lin(d), dd = hole_dbl(d);
+  float* ss = smem + (size_t)w * (dl + dd);
+  float* so2 = ss + dl;
   const int64_t nw = (int64_t)gridDim.x * KGEB_WARPS_PER_BLOCK;
   for (int64_t t = (int64_t)blockIdx.x * KGEB_WARPS_PER_BLOCK + w; t < m; t += nw) {
     const int s = __ldg(idx + 3 * t), p = __ldg(idx + 3 * t + 1), o = __ldg(idx + 3 * t + 2);
     __syncwarp();
-    hole_stage(ss, a.E + (int64_t)s * a.ldE, d, lane, a.dp, 0, a.dp_stream, (uint64_t)t);
-    hole_stage(so, a.E + (int64_t)o * a.ldE, d, lane, a.dp, 2, a.dp_stream, (uint64_t)t);
+    hole_stage_lin(ss, a.E + (int64_t)s * a.ldE, d, lane, a.dp, 0, a.dp_stream, (uint64_t)t);
+    hole_stage_circ(so2, a.E + (int64_t)o * a.ldE, d, dd, 0, lane, a.dp, 2, a.dp_stream, (uint64_t)t);
     __syncwarp();
     const float* pr = a.R + (int64_t)p * a.ldR;
     float acc = 0.f;
-    for (int k = lane; k < d; k += 32) {
-      float x = 0.f;
-      int j = k;
-      for (int i = 0; i < d; ++i) {
-        x = fmaf(ss[i], so[j], x);
-        if (++j == d) j = 0;
+    for (int k0 = 8 * lane; k0 < d; k0 += 256) {
+      float x[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) x[q] = 0.f;
+      for (int i0 = 0; i0 < dl; i0 += 8) {
+        float s8[8], w16[16];
+        ld8(s8, ss + i0);
+        ld16(w16, so2 + i0 + k0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) x[q] = fmaf(s8[u], w16[u + q], x[q]);
       }
-      float pv = __ldg(pr + k);
-      if (a.dp.thr) pv = dp_keep_elem(a.dp, 1, a.dp_stream, (uint64_t)t, k) ? __fmul_rn(pv, a.dp.scale) : 0.f;
-      acc = fmaf(pv, x, acc);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int k = k0 + q;
+        if (k < d) {
+          float pv = __ldg(pr + k);
+          if (a.dp.thr) pv = dp_keep_elem(a.dp, 1, a.dp_stream, (uint64_t)t, k) ? __fmul_rn(pv, a.dp.scale) : 0.f;
+          acc = fmaf(pv, x[q], acc);
+        }
+      }
     }
     acc = warp_sum(acc);
     if (lane == 0) out[t] = acc;
@@ -115,11 +164,13 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_hole_fwd(ScoreArgs a, int d, c
 __global__ void __launch_bounds__(KGEB_THREADS) k_hole_bwd(ScoreArgs a, int d, const int32_t* __restrict__ idx, int64_t m,
                                                            const float* __restrict__ dscore, float* gE, float* gR,
                                                            uint8_t* tE, uint8_t* tR) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float* ss = smem + (size_t)w * 3 * d;
-  float* sp = ss + d;
-  float* so = sp + d;
+  const int dl = hole_lin(d), dd = hole_dbl(d);
+  float* ss = smem + (size_t)w * 2 * (dl + dd);   // s, zero padded
+  float* sp = ss + dl;                            // p, zero padded
+  float* so2 = sp + dl;                           // o doubled: so2[x] = o[x mod d]
+  float* sp2 = so2 + dd;                          // p doubled and shifted: sp2[x] = p[(x - dl) mod d]
   const int64_t nw = (int64_t)gridDim.x * KGEB_WARPS_PER_BLOCK;
   for (int64_t t = (int64_t)blockIdx.x * KGEB_WARPS_PER_BLOCK + w; t < m; t += nw) {
     const int s = __ldg(idx + 3 * t), p = __ldg(idx + 3 * t + 1), o = __ldg(idx + 3 * t + 2);
@@ -127,34 +178,49 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_hole_bwd(ScoreArgs a, int d, c
     if (lane == 0) { tE[s] = 1; tE[o] = 1; tR[p] = 1; }
     if (coef == 0.f) continue;
     __syncwarp();
-    hole_stage(ss, a.E + (int64_t)s * a.ldE, d, lane, a.dp, 0, a.dp_stream, (uint64_t)t);
-    hole_stage(sp, a.R + (int64_t)p * a.ldR, d, lane, a.dp, 1, a.dp_stream, (uint64_t)t);
-    hole_stage(so, a.E + (int64_t)o * a.ldE, d, lane, a.dp, 2, a.dp_stream, (uint64_t)t);
+    hole_stage_lin(ss, a.E + (int64_t)s * a.ldE, d, lane, a.dp, 0, a.dp_stream, (uint64_t)t);
+    hole_stage_lin(sp, a.R + (int64_t)p * a.ldR, d, lane, a.dp, 1, a.dp_stream, (uint64_t)t);
+    hole_stage_circ(so2, a.E + (int64_t)o * a.ldE, d, dd, 0, lane, a.dp, 2, a.dp_stream, (uint64_t)t);
+    hole_stage_circ(sp2, a.R + (int64_t)p * a.ldR, d, dd, dl, lane, a.dp, 1, a.dp_stream, (uint64_t)t);
     __syncwarp();
     float* gs = gE + (int64_t)s * a.ldE;
     float* gp = gR + (int64_t)p * a.ldR;
     float* go = gE + (int64_t)o * a.ldE;
-    for (int k = lane; k < d; k += 32) {
-      // dp_k = sum_i s_i o_{i+k};  ds_k = sum_j p_j o_{k+j};  do_k = sum_j p_j s_{k-j}
-      float xp = 0.f, xs = 0.f, xo = 0.f;
-      int jf = k, jb = k;
-      for (int i = 0; i < d; ++i) {
-        const float ov = so[jf];
-        xp = fmaf(ss[i], ov, xp);
-        xs = fmaf(sp[i], ov, xs);
-        xo = fmaf(sp[i], ss[jb], xo);
-        if (++jf == d) jf = 0;
-        if (--jb < 0) jb = d - 1;
+    for (int k0 = 8 * lane; k0 < d; k0 += 256) {
+      // d/dp_k = sum_i s_i o_{i+k};  d/ds_k = sum_j p_j o_{k+j};  d/do_k = sum_j s_j p_{k-j}   (all times coef)
+      float xp[8], xs[8], xo[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { xp[q] = 0.f; xs[q] = 0.f; xo[q] = 0.f; }
+      for (int i0 = 0; i0 < dl; i0 += 8) {
+        float s8[8], p8[8], wo[16], wp[16];
+        ld8(s8, ss + i0);
+        ld8(p8, sp + i0);
+        ld16(wo, so2 + i0 + k0);                  // o_{i0 + u + k0 + q} = wo[u + q]
+        ld16(wp, sp2 + dl + k0 - i0 - 8);         // p_{k0 + q - i0 - u} = wp[8 + q - u]
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            xp[q] = fmaf(s8[u], wo[u + q], xp[q]);
+            xs[q] = fmaf(p8[u], wo[u + q], xs[q]);
+            xo[q] = fmaf(s8[u], wp[8 + q - u], xo[q]);
+          }
       }
-      float cp = coef, cs = coef, co = coef;   // gradient wrt the raw rows = gradient wrt the dropped rows * keep * scale
-      if (a.dp.thr) {
-        cp = dp_keep_elem(a.dp, 1, a.dp_stream, (uint64_t)t, k) ? coef * a.dp.scale : 0.f;
-        cs = dp_keep_elem(a.dp, 0, a.dp_stream, (uint64_t)t, k) ? coef * a.dp.scale : 0.f;
-        co = dp_keep_elem(a.dp, 2, a.dp_stream, (uint64_t)t, k) ? coef * a.dp.scale : 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int k = k0 + q;
+        if (k < d) {
+          float cp = coef, cs = coef, co = coef;   // gradient wrt the raw rows = gradient wrt the dropped rows * keep * scale
+          if (a.dp.thr) {
+            cp = dp_keep_elem(a.dp, 1, a.dp_stream, (uint64_t)t, k) ? coef * a.dp.scale : 0.f;
+            cs = dp_keep_elem(a.dp, 0, a.dp_stream, (uint64_t)t, k) ? coef * a.dp.scale : 0.f;
+            co = dp_keep_elem(a.dp, 2, a.dp_stream, (uint64_t)t, k) ? coef * a.dp.scale : 0.f;
+          }
+          atomicAdd(gp + k, cp * xp[q]);
+          atomicAdd(gs + k, cs * xs[q]);
+          atomicAdd(go + k, co * xo[q]);
+        }
       }
-      atomicAdd(gp + k, cp * xp);
-      atomicAdd(gs + k, cs * xs);
-      atomicAdd(go + k, co * xo);
     }
   }
 }
@@ -212,7 +278,7 @@ extern "C" int kgeb_score_fwd(kgeb_ctx* ctx, const float* E, const float* R, con
   const int grid = grid_for(ctx, m, 8);
   if (ctx->kind == KGEB_HOLE) {
     KGEB_REQUIRE(ctx, ctx->we == ctx->wr, KGEB_ERR_UNSUPPORTED, "HolE needs e_dim == r_dim");
-    const size_t sm = (size_t)KGEB_WARPS_PER_BLOCK * 2 * ctx->we * sizeof(float);
+    const size_t sm = (size_t)KGEB_WARPS_PER_BLOCK * (hole_lin(ctx->we) + hole_dbl(ctx->we)) * sizeof(float);
     KGEB_REQUIRE(ctx, sm <= 200 * 1024, KGEB_ERR_UNSUPPORTED, "HolE dim too large for shared memory staging");
     KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_hole_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_hole_fwd<<<grid, KGEB_THREADS, sm, st>>>(a, ctx->we, idx, m, scores);
@@ -244,7 +310,7 @@ extern "C" int kgeb_score_bwd(kgeb_ctx* ctx, const float* E, const float* R, con
   ScoreArgs a = make_score_args(ctx, E, R, &nc);
   const int grid = grid_for(ctx, m, 8);
   if (ctx->kind == KGEB_HOLE) {
-    const size_t sm = (size_t)KGEB_WARPS_PER_BLOCK * 3 * ctx->we * sizeof(float);
+    const size_t sm = (size_t)KGEB_WARPS_PER_BLOCK * 2 * (hole_lin(ctx->we) + hole_dbl(ctx->we)) * sizeof(float);
     KGEB_REQUIRE(ctx, sm <= 200 * 1024, KGEB_ERR_UNSUPPORTED, "HolE dim too large for shared memory staging");
     KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_hole_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_hole_bwd<<<grid, KGEB_THREADS, sm, st>>>(a, ctx->we, idx, m, dscore, gE, gR, touchedE, touchedR);
