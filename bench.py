@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-steps", type=int, default=10)
     ap.add_argument("--skip-large", action="store_true", help="skip the 1M-entity (8 GB) secondary train measurement")
+    ap.add_argument("--skip-shapes", action="store_true", help="skip the secondary C1 / C3 / C4 shape measurements")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -372,6 +373,59 @@ def main():
         del leng, lb
         torch.cuda.empty_cache()
 
+    # ---- the remaining named shapes (BASELINE configs 0, 2, 3): one fused / unfused train step each, and HolE's 1-N eval ------
+    other_shapes = None
+    if world == 1 and not args.skip_shapes:
+        other_shapes = {}
+        for sname, skind, sN, sR, sW, sB, sK, sloss, snote in (
+                ("C1 DistMult dim=100 kinship-shape (N=104, R=25)", abi.DISTMULT, 104, 25, 100, 2048, 10, abi.PAIRWISE_HINGE,
+                 "harness batch 2048 x 10 negatives, pairwize_hinge; launch-latency bound (41 KB table)"),
+                ("C3 ComplEx dim=200 FB15k-237-shape (N=14541, R=237)", abi.COMPLEX, 14541, 237, 400, 16384, 10, abi.PAIRWISE_HINGE,
+                 "fused ring kernel, pairwize_hinge"),
+                ("C4 HolE dim=256 YAGO3-10-shape (N=123182, R=37)", abi.HOLE, 123182, 37, 256, 2048, 64, abi.POINTWISE_LOGISTIC,
+                 "64 negatives, pointwize_logistic; unfused score_fwd -> loss -> score_bwd (O(d^2) correlation kernels)")):
+            srng = np.random.default_rng(31)
+            seng = Engine(skind, sN, sR, sW, sW, E=glorot(srng, sN, sW), R=glorot(srng, sR, sW))
+            ssteps, swarm = 20, 3
+            sb = torch.from_numpy(np.stack([srng.integers(0, sN, (ssteps + swarm, sB)), srng.integers(0, sR, (ssteps + swarm, sB)),
+                                            srng.integers(0, sN, (ssteps + swarm, sB))], axis=2).astype(np.int32)).to(dev)
+            skw = dict(K=sK, loss_kind=sloss, pair_mode=abi.PAIRED, margin=1.0, corrupt_mode=abi.CORRUPT_BOTH, seed=77, opt_kind=abi.LAZY_ADAM, lr=1e-3)
+            for i in range(swarm):
+                seng.train_step(sb[i], None, offset=i, **skw)
+            sev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(ssteps)]
+            sl0 = seng.launches
+            for i in range(ssteps):
+                flush.zero_()
+                sev[i][0].record()
+                seng.train_step(sb[swarm + i], None, offset=swarm + i, **skw)
+                sev[i][1].record()
+            torch.cuda.synchronize()
+            sms = float(np.mean([e[0].elapsed_time(e[1]) for e in sev]))
+            entry = {"batch_positives": sB, "negatives_per_positive": sK, "ms_per_step": sms, "triples_per_s": sB * (1 + sK) / (sms * 1e-3),
+                     "gpu_launches_per_step": (seng.launches - sl0) // ssteps, "note": snote}
+            if skind == abi.HOLE:   # C4 filtered 1-N eval on the tensor cores (exact mode), 5 000 test triples x 2 sides
+                qn = 5000
+                qtri = torch.from_numpy(np.stack([srng.integers(0, sN, qn), srng.integers(0, sR, qn), srng.integers(0, sN, qn)], axis=1).astype(np.int32)).to(dev)
+                qc_t = tuple(torch.from_numpy(x).to(dev) for x in synth_filter_csr(srng, qn, sN, 5.4))
+                qc_h = tuple(torch.from_numpy(x).to(dev) for x in synth_filter_csr(srng, qn, sN, 23.5))
+                packed = seng.pack_entities_tc(abi.TC_BF16X3_EXACT)
+                qms = []
+                for i in range(5):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    seng.rank_counts_tc(qtri, abi.SIDE_TAIL, qc_t[0], qc_t[1], mode=abi.TC_BF16X3_EXACT, packed=packed)
+                    seng.rank_counts_tc(qtri, abi.SIDE_HEAD, qc_h[0], qc_h[1], mode=abi.TC_BF16X3_EXACT, packed=packed)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    if i >= 2:
+                        qms.append(e0.elapsed_time(e1))
+                entry["eval_exact"] = {"queries_per_pass": 2 * qn, "ms_per_pass": float(np.mean(qms)),
+                                       "queries_per_s": 2 * qn / (float(np.mean(qms)) * 1e-3)}
+            other_shapes[sname] = entry
+            del seng, sb
+            torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -438,6 +492,7 @@ def main():
                         "parity": "exact_bf16x3 counts are bit-identical to the fp32 CUDA-core kernel (tests/test_gpu_rank_tc.py)",
                         **tensor_eval},
         "train_large_table": train_large,
+        "other_shapes": other_shapes,
         "clocks": sampler.summary(),
     }
     if world == 1 and not args.no_cpu_baseline:
