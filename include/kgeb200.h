@@ -58,11 +58,15 @@ typedef enum {
   KGEB_ROTATE = 5, KGEB_PROTATE = 6, KGEB_MODE_L1 = 7, KGEB_MODE_L2 = 8
 } kgeb_score_kind;
 
-/* losses utils.py:288-319 (pointwize_cross_entropy is composed on the host from kernel scores) */
+/* losses utils.py:288-319.  POINTWISE_BCE = pointwize_cross_entropy (utils.py:297-298): Keras binary_crossentropy on the raw
+ * scores, i.e. -log(clip(t) + 1e-7) for positives and -log(1 - clip(f) + 1e-7) for negatives, clip to [1e-7, 1 - 1e-7]. */
 typedef enum {
   KGEB_POINTWISE_HINGE = 0, KGEB_POINTWISE_LOGISTIC = 1, KGEB_POINTWISE_SQUARE = 2,
-  KGEB_PAIRWISE_HINGE = 3, KGEB_PAIRWISE_LOGISTIC = 4, KGEB_PAIRWISE_SQUARE = 5
+  KGEB_PAIRWISE_HINGE = 3, KGEB_PAIRWISE_LOGISTIC = 4, KGEB_PAIRWISE_SQUARE = 5,
+  KGEB_POINTWISE_BCE = 6
 } kgeb_loss_kind;
+#define KGEB_LOSS_KIND_MAX KGEB_POINTWISE_BCE
+#define KGEB_IS_PAIRWISE(k) ((k) >= KGEB_PAIRWISE_HINGE && (k) <= KGEB_PAIRWISE_SQUARE)
 
 /* how pairwise losses pair true with false scores:
  * PAIRED   true (B,1) vs false (B,K)            -- the per-positive pairwise loss

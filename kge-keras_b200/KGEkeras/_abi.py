@@ -8,7 +8,12 @@ import os
 # enum values of include/kgeb200.h
 DISTMULT, TRANSE_L1, TRANSE_L2, COMPLEX, HOLE, ROTATE, PROTATE, MODE_L1, MODE_L2 = range(9)
 FUSED_TRAIN_KINDS = (DISTMULT, TRANSE_L1, TRANSE_L2, COMPLEX)   # kinds the fused train kernel is instantiated for
-POINTWISE_HINGE, POINTWISE_LOGISTIC, POINTWISE_SQUARE, PAIRWISE_HINGE, PAIRWISE_LOGISTIC, PAIRWISE_SQUARE = range(6)
+POINTWISE_HINGE, POINTWISE_LOGISTIC, POINTWISE_SQUARE, PAIRWISE_HINGE, PAIRWISE_LOGISTIC, PAIRWISE_SQUARE, POINTWISE_BCE = range(7)
+
+
+def is_pairwise(loss_kind):
+    return PAIRWISE_HINGE <= loss_kind <= PAIRWISE_SQUARE
+
 PAIRED, ALLPAIRS = 0, 1
 SGD, ADAGRAD, LAZY_ADAM, ADAM_DENSE = range(4)
 CORRUPT_BOTH, CORRUPT_HEAD, CORRUPT_TAIL, CORRUPT_EITHER = range(4)
@@ -20,6 +25,7 @@ LOSS_KINDS = {  # reference names, utils.py:321-330
     "pointwize_hinge": POINTWISE_HINGE, "pointwize_logistic": POINTWISE_LOGISTIC,
     "pointwize_square_loss": POINTWISE_SQUARE, "pairwize_hinge": PAIRWISE_HINGE,
     "pairwize_logistic": PAIRWISE_LOGISTIC, "pairwize_square_loss": PAIRWISE_SQUARE,
+    "pointwize_cross_entropy": POINTWISE_BCE,
 }
 OPT_KINDS = {"sgd": SGD, "adagrad": ADAGRAD, "lazy_adam": LAZY_ADAM, "adam": ADAM_DENSE}
 STATUS = {0: "OK", -1: "INVALID", -2: "CUDA", -3: "ALIGNMENT", -4: "UNSUPPORTED", -5: "WORKSPACE"}

@@ -191,13 +191,13 @@ class Engine:
         B = pos.shape[0]
         if neg is not None:
             neg = as_idx(neg, self.device)
-            if pair_mode == abi.PAIRED or loss_kind < abi.PAIRWISE_HINGE:
-                if neg.shape[0] % B != 0 and loss_kind >= abi.PAIRWISE_HINGE:
+            if pair_mode == abi.PAIRED or not abi.is_pairwise(loss_kind):
+                if neg.shape[0] % B != 0 and abi.is_pairwise(loss_kind):
                     raise ValueError("PAIRED pairwise loss needs len(neg) to be a multiple of len(pos)")
                 if neg.shape[0] % B == 0:
                     K = neg.shape[0] // B
         self._ensure_train_buffers(opt_kind)
-        pairwise = loss_kind >= abi.PAIRWISE_HINGE
+        pairwise = abi.is_pairwise(loss_kind)
         fused = (not force_unfused and self.kind in abi.FUSED_TRAIN_KINDS and not (pairwise and pair_mode == abi.ALLPAIRS)
                  and (neg is None or neg.shape[0] == B * K))
         res = {}

@@ -273,7 +273,7 @@ def _pair_layout(true, false, negative_samples):
 def _loss(kind, true, false, margin, negative_samples, reduce_mean):
     import torch
     eng = _loss_eng()
-    if kind < abi.PAIRWISE_HINGE:
+    if not abi.is_pairwise(kind):
         out, _, _ = eng.loss(_as_dev(true).reshape(-1), _as_dev(false).reshape(-1), 1, kind, abi.PAIRED, float(margin), 1.0, want_grads=False)
         return out[0]
     mode, t, f, shape = _pair_layout(true, false, negative_samples)
@@ -306,15 +306,8 @@ def pointwize_square_loss(true, false, margin=1, negative_samples=1, reduce_mean
 
 
 def pointwize_cross_entropy(true, false, margin=1, negative_samples=1, reduce_mean=True):
-    """utils.py:297-298: Keras binary_crossentropy on raw scores (clip to [1e-7, 1-1e-7]); composed from kernel scores with
-    a handful of elementwise device ops (not a hot-path loss)."""
-    import torch
-    eps = 1e-7
-
-    def bce(y, pred):
-        pred = torch.clamp(_as_dev(pred), eps, 1 - eps)
-        return torch.mean(-(y * torch.log(pred + eps) + (1 - y) * torch.log(1 - pred + eps)), dim=-1)
-    return bce(1.0, true) + bce(0.0, false)
+    """utils.py:297-298: Keras binary_crossentropy on raw scores (clip to [1e-7, 1-1e-7], -log(. + 1e-7)), mean over each list."""
+    return _loss(abi.POINTWISE_BCE, true, false, margin, negative_samples, True)
 
 
 def pairwize_hinge(true, false, margin=1, negative_samples=1, reduce_mean=True):

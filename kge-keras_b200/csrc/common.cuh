@@ -172,6 +172,13 @@ __device__ __forceinline__ void pointwise_terms(int kind, float margin, float x,
     val = logf(KGEB_C1 + e);
     const float sg = e / (KGEB_C1 + e);
     der = positive ? -sg : sg;
+  } else if (kind == KGEB_POINTWISE_BCE) {  // Keras binary_crossentropy(1, t) / (0, f) on raw scores: clip, then -log(. + eps)
+    const float eps = 1e-7f, hi = 1.f - 1e-7f;
+    const float c = fminf(fmaxf(x, eps), hi);
+    const bool inside = x >= eps && x <= hi;          // clip_by_value passes the gradient inside the closed interval
+    const float arg = positive ? c + eps : (1.f - c) + eps;
+    val = -logf(arg);
+    der = inside ? (positive ? -1.f / arg : 1.f / arg) : 0.f;
   } else {  // square
     const float z = positive ? margin - x : margin + x;
     val = z * z;

@@ -214,10 +214,10 @@ extern "C" int kgeb_loss_fwd_bwd(kgeb_ctx* ctx, const float* t, int64_t B, const
                                  kgeb_stream stream) {
   if (!ctx) return KGEB_ERR_INVALID;
   KGEB_REQUIRE(ctx, t && f && loss && B > 0 && Bf > 0, KGEB_ERR_INVALID, "loss_fwd_bwd: bad arguments");
-  KGEB_REQUIRE(ctx, loss_kind >= 0 && loss_kind <= KGEB_PAIRWISE_SQUARE, KGEB_ERR_INVALID, "unknown loss kind");
+  KGEB_REQUIRE(ctx, loss_kind >= 0 && loss_kind <= KGEB_LOSS_KIND_MAX, KGEB_ERR_INVALID, "unknown loss kind");
   cudaStream_t st = (cudaStream_t)stream;
   const int cap = ctx->num_sms * 4 < KGEB_MAX_PARTIAL_BLOCKS ? ctx->num_sms * 4 : KGEB_MAX_PARTIAL_BLOCKS;
-  if (loss_kind < KGEB_PAIRWISE_HINGE) {
+  if (!KGEB_IS_PAIRWISE(loss_kind)) {
     int64_t blocks = (B + Bf + KGEB_THREADS - 1) / KGEB_THREADS;
     if (blocks > cap) blocks = cap;
     k_loss_pointwise<<<(int)blocks, KGEB_THREADS, 0, st>>>(t, B, f, Bf, loss_kind, margin, loss_weight, loss, dt, df,

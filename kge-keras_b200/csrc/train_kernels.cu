@@ -12,7 +12,7 @@ template <int KIND, int NC>
 __global__ void __launch_bounds__(KGEB_THREADS) k_train_fwd_bwd(TrainArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t nw = (int64_t)gridDim.x * KGEB_WARPS_PER_BLOCK;
-  const bool pairwise = a.loss_kind >= KGEB_PAIRWISE_HINGE;
+  const bool pairwise = KGEB_IS_PAIRWISE(a.loss_kind);
   const double cntP = (double)a.B, cntN = (double)a.B * (double)a.K;
   // coefficient scales: pointwise positives /B, everything else /(B*K)
   const float scaleP = (float)((double)a.loss_weight / cntP), scaleN = (float)((double)a.loss_weight / cntN);
@@ -109,7 +109,7 @@ extern "C" int kgeb_train_fwd_bwd(kgeb_ctx* ctx, const float* E, const float* R,
   if (!ctx) return KGEB_ERR_INVALID;
   KGEB_REQUIRE(ctx, pos && loss && gE && gR && touchedE && touchedR && B > 0 && K > 0, KGEB_ERR_INVALID,
                "train_fwd_bwd: bad arguments");
-  KGEB_REQUIRE(ctx, loss_kind >= 0 && loss_kind <= KGEB_PAIRWISE_SQUARE, KGEB_ERR_INVALID, "unknown loss kind");
+  KGEB_REQUIRE(ctx, loss_kind >= 0 && loss_kind <= KGEB_LOSS_KIND_MAX, KGEB_ERR_INVALID, "unknown loss kind");
   KGEB_REQUIRE(ctx, corrupt_mode >= 0 && corrupt_mode <= 3, KGEB_ERR_INVALID, "unknown corrupt mode");
   KGEB_REQUIRE(ctx, ctx->kind != KGEB_HOLE, KGEB_ERR_UNSUPPORTED,
                "HolE uses the unfused sequence score_fwd -> loss_fwd_bwd -> score_bwd");

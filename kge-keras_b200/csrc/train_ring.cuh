@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_train_ring(TrainArgs a, int D,
   const int64_t nw = (int64_t)gridDim.x * KGEB_WARPS_PER_BLOCK;
   const int loss_kind = a.loss_kind;
   const float margin = a.margin;
-  const bool pairwise = loss_kind >= KGEB_PAIRWISE_HINGE;
+  const bool pairwise = KGEB_IS_PAIRWISE(loss_kind);
   const double cntP = (double)a.B, cntN = (double)a.B * (double)a.K;
   const float scaleP = (float)((double)a.loss_weight / cntP), scaleN = (float)((double)a.loss_weight / cntN);
   const int K = a.K;

@@ -22,11 +22,12 @@ SCORE_KINDS = {"DistMult": DISTMULT, "TransE_L1": TRANSE_L1, "TransE_L2": TRANSE
 SIBLING_KINDS = {"RotatE": ROTATE, "pRotatE": PROTATE, "ModE_L1": MODE_L1, "ModE_L2": MODE_L2}
 
 # loss kinds -- shared with kgeb_loss_kind
-POINTWISE_HINGE, POINTWISE_LOGISTIC, POINTWISE_SQUARE, PAIRWISE_HINGE, PAIRWISE_LOGISTIC, PAIRWISE_SQUARE = range(6)
+POINTWISE_HINGE, POINTWISE_LOGISTIC, POINTWISE_SQUARE, PAIRWISE_HINGE, PAIRWISE_LOGISTIC, PAIRWISE_SQUARE, POINTWISE_BCE = range(7)
 LOSS_NAMES = {  # utils.py:321-330 (spelling "wize" is the reference's)
     "pointwize_hinge": POINTWISE_HINGE, "pointwize_logistic": POINTWISE_LOGISTIC,
     "pointwize_square_loss": POINTWISE_SQUARE, "pairwize_hinge": PAIRWISE_HINGE,
     "pairwize_logistic": PAIRWISE_LOGISTIC, "pairwize_square_loss": PAIRWISE_SQUARE,
+    "pointwize_cross_entropy": POINTWISE_BCE,
 }
 # pair modes -- shared with kgeb_pair_mode
 PAIRED, ALLPAIRS = 0, 1
@@ -302,6 +303,12 @@ def loss_and_coefs(loss_kind, pair_mode, t, f, K, margin):
         if loss_kind == POINTWISE_SQUARE:
             L = np.mean(np.square(M - t)) + np.mean(np.square(M + f))
             return L, -2 * (M - t) / B, 2 * (M + f) / Bf
+        if loss_kind == POINTWISE_BCE:   # utils.py:297-298 (Keras clip to [eps, 1-eps], gradient passes inside the interval)
+            eps, hi = dt.type(1e-7), dt.type(1) - dt.type(1e-7)
+            ct, cf = np.clip(t, eps, hi), np.clip(f, eps, hi)
+            L = np.mean(-np.log(ct + eps)) + np.mean(-np.log(dt.type(1) - cf + eps))
+            it, jf = ((t >= eps) & (t <= hi)).astype(dt), ((f >= eps) & (f <= hi)).astype(dt)
+            return L, -it / (ct + eps) / B, jf / (dt.type(1) - cf + eps) / Bf
         if pair_mode == PAIRED:
             F = f.reshape(B, K)
             T = t.reshape(B, 1)

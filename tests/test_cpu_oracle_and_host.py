@@ -247,6 +247,11 @@ def test_loss_coefs_match_autograd(lname, pm):
         L = torch.log(c + torch.exp(-tt)).mean() + torch.log(c + torch.exp(tf_)).mean()
     elif lk == ko.POINTWISE_SQUARE:
         L = ((M - tt) ** 2).mean() + ((M + tf_) ** 2).mean()
+    elif lk == ko.POINTWISE_BCE:   # Keras binary_crossentropy(1, true) + binary_crossentropy(0, false) (utils.py:297-298)
+        t[:3], f[:4] = [0.2, 0.9, 0.5], [0.1, 0.7, 0.999, 0.3]          # some scores inside the clip interval
+        tt, tf_ = torch.tensor(t, requires_grad=True), torch.tensor(f, requires_grad=True)
+        eps = 1e-7
+        L = (-torch.log(torch.clamp(tt, eps, 1 - eps) + eps)).mean() + (-torch.log(1 - torch.clamp(tf_, eps, 1 - eps) + eps)).mean()
     else:
         X = (tf_.reshape(B, K) - tt.reshape(B, 1)) if pm == ko.PAIRED else (tf_.reshape(-1, 1) - tt.reshape(1, -1))
         L = {ko.PAIRWISE_HINGE: lambda: torch.relu(M + X).mean(), ko.PAIRWISE_LOGISTIC: lambda: torch.log(c + torch.exp(X)).mean(),
@@ -258,7 +263,7 @@ def test_loss_coefs_match_autograd(lname, pm):
     np.testing.assert_allclose(df, tf_.grad.numpy(), rtol=1e-10, atol=1e-14)
     # and the reference-named function (restated) agrees on the value
     ref = ko.loss_function_lookup(lname)
-    Lr = ref(t.reshape(-1, 1) if (pm == ko.PAIRED and lk >= ko.PAIRWISE_HINGE) else t, f, M, K if pm == ko.PAIRED else 1)
+    Lr = ref(t.reshape(-1, 1) if (pm == ko.PAIRED and ko.PAIRWISE_HINGE <= lk <= ko.PAIRWISE_SQUARE) else t, f, M, K if pm == ko.PAIRED else 1)
     np.testing.assert_allclose(Lr, Lo, rtol=1e-12)
 
 

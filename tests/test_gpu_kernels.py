@@ -124,18 +124,22 @@ def test_loss_fwd_bwd(lname, pm):
     B, K = 300, 7
     t = rng.normal(size=B).astype(np.float32) * 2
     f = rng.normal(size=B * K).astype(np.float32) * 2
+    if lk == ko.POINTWISE_BCE:   # half of the scores inside the clip interval (0, 1), the rest clipped (zero gradient)
+        t[::2], f[::2] = rng.uniform(0.01, 0.99, len(t[::2])), rng.uniform(0.01, 0.99, len(f[::2]))
     loss, dt, df = eng.loss(torch.from_numpy(t), torch.from_numpy(f), K, lk, pm, 1.0, 1.0)
-    L, wdt, wdf = ko.loss_and_coefs(lk, pm, t.astype(np.float64), f.astype(np.float64), K, 1.0)
+    # the clip bound 1 - 1e-7 is itself rounded in fp32 (0.99999988), in TF as here: the BCE restatement runs in fp32
+    odt = np.float32 if lk == ko.POINTWISE_BCE else np.float64
+    L, wdt, wdf = ko.loss_and_coefs(lk, pm, t.astype(odt), f.astype(odt), K, 1.0)
     assert abs(float(loss.item()) - L) <= 2e-6 * max(1.0, abs(L))
     np.testing.assert_allclose(dt.cpu().numpy(), wdt, rtol=2e-5, atol=2e-7 * np.max(np.abs(wdt)))
     np.testing.assert_allclose(df.cpu().numpy(), wdf, rtol=2e-5, atol=2e-7 * np.max(np.abs(wdf)))
     # the reference function itself (restated) gives the same value
     ref = ko.loss_function_lookup(lname)
     if pm == ko.PAIRED:
-        Lref = ref(t.reshape(-1, 1) if lk >= ko.PAIRWISE_HINGE else t, f, 1.0, K)
+        Lref = ref(t.reshape(-1, 1) if ko.PAIRWISE_HINGE <= lk <= ko.PAIRWISE_SQUARE else t, f, 1.0, K)
     else:
         Lref = ref(t, f, 1.0, 1)
-    assert abs(float(Lref) - L) <= 1e-5 * max(1.0, abs(L))
+    assert abs(float(Lref) - L) <= (1e-2 if lk == ko.POINTWISE_BCE else 1e-5) * max(1.0, abs(L))   # BCE: fp64 vs fp32 clip bound
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -151,7 +155,7 @@ def _state(kind_opt, E, Rm):
 @pytest.mark.parametrize("lname,pm", [("pairwize_hinge", ko.PAIRED), ("pairwize_logistic", ko.PAIRED),
                                       ("pointwize_logistic", ko.PAIRED), ("pointwize_hinge", ko.PAIRED),
                                       ("pairwize_hinge", ko.ALLPAIRS), ("pairwize_square_loss", ko.PAIRED),
-                                      ("pointwize_square_loss", ko.PAIRED)])
+                                      ("pointwize_square_loss", ko.PAIRED), ("pointwize_cross_entropy", ko.PAIRED)])
 @pytest.mark.parametrize("opt", [ko.OPT_LAZY_ADAM, ko.OPT_ADAM_DENSE, ko.OPT_ADAGRAD, ko.OPT_SGD])
 def test_train_step_index_driven(kind, lname, pm, opt):
     if opt in (ko.OPT_ADAGRAD, ko.OPT_SGD) and lname not in ("pairwize_hinge",):
@@ -167,7 +171,8 @@ def test_train_step_index_driven(kind, lname, pm, opt):
     sE, sR = _state(opt, E, Rm)
     # eps = 1e-3 keeps Adam's m/(sqrt(v)+eps) well conditioned for gradients that cancel to ~0 (the fp32 atomics'
     # summation order is free); the default eps = 1e-7 is covered with exact inputs in test_opt_update_exact_inputs
-    want = ko.train_step(kind, lk, pm, E, Rm, pos, neg, K, 1.0, 2.0, opt, sE, sR, lr, 1, np.float64, eps=1e-3)
+    # (the BCE clip bound 1 - 1e-7 only exists rounded in fp32, so its restatement runs in fp32 like the reference would)
+    want = ko.train_step(kind, lk, pm, E, Rm, pos, neg, K, 1.0, 2.0, opt, sE, sR, lr, 1, np.float32 if lk == ko.POINTWISE_BCE else np.float64, eps=1e-3)
     res = eng.forward_backward(pos, neg, K=K, loss_kind=lk, pair_mode=pm, margin=1.0, want_scores=True, opt_kind=opt)
     W = E.shape[1]
     gE = eng.gE.cpu().numpy()[:, :W].astype(np.float64)
