@@ -1,2 +1,2 @@
-cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
+timeout 600 python profiles/sweep_bench.py | tee gpurun_out/sweep_r01.jsonl
