@@ -421,3 +421,42 @@ def test_data_generator_host_path_consumes_rng_like_the_harness():
         assert y is None
         np.testing.assert_array_equal(pos, want[b][0])
         np.testing.assert_array_equal(neg, want[b][1])
+
+
+# ---- optimizer restatement against independent implementations (third-party arithmetic) ----------
+@pytest.mark.parametrize("opt", ["adam_dense", "lazy_adam", "adagrad", "sgd"])
+def test_oracle_optimizer_matches_torch_optim(opt):
+    """Keras/TF are not installable here, so the recalled update rules are pinned against torch.optim's implementations of
+    the same published algorithms.  Keras Adam folds the bias corrections into the step size (epsilon 'hat' form,
+    p -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps)); torch divides m and v first -- identical for eps -> 0, so the
+    comparison runs with eps = 1e-12 on gradients of order 1.  Lazy variant: torch.optim.SparseAdam (touched rows only)."""
+    import torch
+    rng = np.random.default_rng(5)
+    N, W, lr, steps = 30, 6, 0.05, 6
+    P0 = rng.normal(size=(N, W))
+    kind = {"adam_dense": ko.OPT_ADAM_DENSE, "lazy_adam": ko.OPT_LAZY_ADAM, "adagrad": ko.OPT_ADAGRAD, "sgd": ko.OPT_SGD}[opt]
+    P = P0.copy()
+    state = [np.zeros_like(P), np.zeros_like(P)] if "adam" in opt else ([np.full_like(P, 0.1)] if opt == "adagrad" else [])
+    tp = torch.nn.Parameter(torch.tensor(P0.copy()))
+    if opt == "adam_dense":
+        topt = torch.optim.Adam([tp], lr=lr, betas=(0.9, 0.999), eps=1e-12)
+    elif opt == "lazy_adam":
+        topt = torch.optim.SparseAdam([tp], lr=lr, betas=(0.9, 0.999), eps=1e-12)
+    elif opt == "adagrad":
+        topt = torch.optim.Adagrad([tp], lr=lr, initial_accumulator_value=0.1, eps=1e-12)
+    else:
+        topt = torch.optim.SGD([tp], lr=lr)
+    for step in range(1, steps + 1):
+        touched = rng.random(N) < 0.5
+        G = rng.normal(size=(N, W)) * touched[:, None]
+        P, state = ko.opt_update(kind, P, G, touched, state, lr, step, eps=1e-12)
+        if opt == "lazy_adam":
+            rows = torch.tensor(np.nonzero(touched)[0])
+            tp.grad = torch.sparse_coo_tensor(rows.unsqueeze(0), torch.tensor(G[touched]), (N, W))
+        else:
+            tp.grad = torch.tensor(G)
+        topt.step()
+        if opt in ("adagrad", "sgd"):
+            # dense torch optimizers also "update" untouched rows with a zero gradient: a no-op for SGD / Adagrad
+            pass
+        np.testing.assert_allclose(P, tp.detach().numpy(), rtol=1e-7, atol=1e-10)
