@@ -1,6 +1,7 @@
 // api.cu -- context lifecycle of libkgeb200 (see include/kgeb200.h).
 #include "common.cuh"
 #include <new>
+#include <stdlib.h>
 
 char g_kgeb_create_err[512] = "";
 
@@ -33,6 +34,10 @@ extern "C" int kgeb_create(kgeb_ctx** out, int device, int64_t num_entities, int
   memset(c, 0, sizeof(*c));
   c->device = device; c->N = num_entities; c->R = num_relations; c->we = we; c->wr = wr; c->ldE = ldE; c->ldR = ldR;
   c->kind = score_kind; c->gamma = gamma; c->param = 1.f; c->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("KGEB_RING_CTAS")) c->env_ring_ctas = atoi(e);
+  if (const char* e = getenv("KGEB_RING_D")) c->env_ring_d = atoi(e);
+  if (const char* e = getenv("KGEB_TRAIN_KERNEL")) c->env_force_reg = strcmp(e, "reg") == 0;
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) c->ring_cfg[i][j].smem = -1;
   if ((e = cudaMalloc(&c->d_partials, sizeof(double) * 2 * KGEB_MAX_PARTIAL_BLOCKS)) != cudaSuccess ||
       (e = cudaMalloc(&c->d_ticket, sizeof(unsigned int))) != cudaSuccess ||
       (e = cudaMemset(c->d_ticket, 0, sizeof(unsigned int))) != cudaSuccess) {

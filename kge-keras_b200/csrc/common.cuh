@@ -27,6 +27,12 @@ struct kgeb_ctx {
   unsigned int* d_ticket;    // last-block-done counter (self-resetting)
   // dropout state (kgeb_set_dropout): thr = round(dp * 65536), 0 = off
   uint32_t dp_thr; float dp_scale; uint64_t dp_seed, dp_offset; int dp_stream;
+  // tuning knobs read from the environment ONCE at kgeb_create (KGEB_RING_CTAS, KGEB_RING_D, KGEB_TRAIN_KERNEL=reg):
+  // measurement aids, never consulted on the launch path
+  int env_ring_ctas, env_ring_d, env_force_reg;
+  // launch configuration of the ring kernel per (negative mode, dropout flavour), filled on first use: the shared-memory
+  // opt-in and the occupancy query are per-function driver calls that need not be repeated every step
+  struct { int smem, occ; } ring_cfg[3][2];
   // optional kernel timing (kgeb_set_kernel_timing): events recorded on the caller's stream around selected launches
   int timing;
   cudaEvent_t ev[KGEB_TIMED_KERNELS][2];

@@ -135,10 +135,10 @@ extern "C" int kgeb_train_fwd_bwd(kgeb_ctx* ctx, const float* E, const float* R,
   if (D < 3) { ctas = 2; D = stages_for(sm_budget / 2 - 1024); }
   if (D < 2) { ctas = 1; D = stages_for(sm_budget - 1024); }
   if (D > 6) D = 6;
-  if (const char* e = getenv("KGEB_RING_CTAS")) { ctas = atoi(e); D = stages_for(sm_budget / ctas - 1024); if (D > 8) D = 8; }
-  if (const char* e = getenv("KGEB_RING_D")) D = atoi(e);
-  const char* force = getenv("KGEB_TRAIN_KERNEL");
-  const bool use_ring = D >= 1 && (a.sc.dp.thr != 0 || !(force && strcmp(force, "reg") == 0));  // dropout lives in the ring kernel only
+  if (ctx->env_ring_ctas > 0) { ctas = ctx->env_ring_ctas; D = stages_for(sm_budget / ctas - 1024); if (D > 8) D = 8; }
+  if (ctx->env_ring_d > 0) D = ctx->env_ring_d;
+  (void)ctas;
+  const bool use_ring = D >= 1 && (a.sc.dp.thr != 0 || !ctx->env_force_reg);  // dropout lives in the ring kernel only
   KGEB_REQUIRE(ctx, use_ring || a.sc.dp.thr == 0, KGEB_ERR_UNSUPPORTED, "dropout needs the ring kernel, whose stages do not fit for this width");
   if (use_ring) {
     const size_t smem = (size_t)KGEB_WARPS_PER_BLOCK * (3 + SR * D) * RB + (size_t)KGEB_WARPS_PER_BLOCK * (D + 1) * sizeof(uint64_t);

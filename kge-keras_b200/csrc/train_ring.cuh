@@ -301,10 +301,14 @@ template <bool DP>
 int launch_train_ring(kgeb_ctx* ctx, const TrainArgs& a, int nc, int mode, int D, int RB, size_t smem, int64_t B, cudaStream_t st) {
 #define KGEB_RING_LAUNCH(M)                                                                                              \
   {                                                                                                                      \
-    KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_train_ring<KIND, NC, M, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    int occ = 0;                                                                                                         \
-    KGEB_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_train_ring<KIND, NC, M, DP>, KGEB_THREADS, smem)); \
-    int grid = grid_for(ctx, B, occ < 1 ? 1 : occ);                                                                      \
+    auto& cfg = ctx->ring_cfg[M][DP ? 1 : 0];   /* kind and NC are fixed per context */                                  \
+    if (cfg.smem != (int)smem) {                                                                                         \
+      KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_train_ring<KIND, NC, M, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      int occ = 0;                                                                                                       \
+      KGEB_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_train_ring<KIND, NC, M, DP>, KGEB_THREADS, smem)); \
+      cfg.smem = (int)smem; cfg.occ = occ < 1 ? 1 : occ;                                                                 \
+    }                                                                                                                    \
+    int grid = grid_for(ctx, B, cfg.occ);                                                                                \
     if (grid > KGEB_MAX_PARTIAL_BLOCKS) grid = KGEB_MAX_PARTIAL_BLOCKS;                                                  \
     KGEB_TIME_BEGIN(ctx, KGEB_TIMED_TRAIN, st);                                                                          \
     k_train_ring<KIND, NC, M, DP><<<grid, KGEB_THREADS, smem, st>>>(a, D, RB);                                           \
