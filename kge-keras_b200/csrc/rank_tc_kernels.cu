@@ -233,24 +233,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * TC_BN;
         uint32_t accumulate = 0;
-        for (int s = 0; s < nstage; ++s) {
-          const int c0 = s * ch_per_stage;
-          const int nk16 = (a.nkc - c0 < ch_per_stage ? a.nkc - c0 : ch_per_stage) >> 1;  // K=16 steps in this stage
-          tc_mbar_wait(full + stage, phase);
-          tc_fence_after();
-          const uint32_t sa = tc_smem_u32(smA + stage * TC_A_STAGE), sb = tc_smem_u32(smB + stage * TC_B_STAGE);
-          for (int j = 0; j < nk16; ++j) {
-            // chunk column (2j, plane p) starts at (2j*planes + p) * rows * 16 bytes
-            const uint32_t a0 = sa + (uint32_t)(2 * j * planes) * TC_BM * 16, b0 = sb + (uint32_t)(2 * j * planes) * TC_BN * 16;
-            tc_mma_bf16(tmem_d, tc_desc(a0, lboA, 128), tc_desc(b0, lboB, 128), TC_IDESC, accumulate);  // qh . eh
-            accumulate = 1;
-            if (planes == 2) {
-              tc_mma_bf16(tmem_d, tc_desc(a0, lboA, 128), tc_desc(b0 + TC_BN * 16, lboB, 128), TC_IDESC, 1);  // qh . el
-              tc_mma_bf16(tmem_d, tc_desc(a0 + TC_BM * 16, lboA, 128), tc_desc(b0, lboB, 128), TC_IDESC, 1);  // ql . eh
+        // Stages are consumed in PAIRS: the MMAs of two stages are issued back to back and only then are both stages handed
+        // back to the producer (two commits in a row).  Every commit between groups of MMAs costs the tensor pipe a hand-off
+        // of ~0.3 us (measured: the kernel's time follows the number of MMA/commit alternations per tile -- 13, 7 or 4 -- not
+        // the bytes moved or the depth of the ring), so with 4 stages two groups of two alternate.
+        for (int s = 0; s < nstage; s += 2) {
+          uint32_t st_idx[2];
+          int nin = 0;
+          for (int h = 0; h < 2 && s + h < nstage; ++h) {
+            const int c0 = (s + h) * ch_per_stage;
+            const int nk16 = (a.nkc - c0 < ch_per_stage ? a.nkc - c0 : ch_per_stage) >> 1;  // K=16 steps in this stage
+            tc_mbar_wait(full + stage, phase);
+            tc_fence_after();
+            const uint32_t sa = tc_smem_u32(smA + stage * TC_A_STAGE), sb = tc_smem_u32(smB + stage * TC_B_STAGE);
+            for (int j = 0; j < nk16; ++j) {
+              // chunk column (2j, plane p) starts at (2j*planes + p) * rows * 16 bytes
+              const uint32_t a0 = sa + (uint32_t)(2 * j * planes) * TC_BM * 16, b0 = sb + (uint32_t)(2 * j * planes) * TC_BN * 16;
+              tc_mma_bf16(tmem_d, tc_desc(a0, lboA, 128), tc_desc(b0, lboB, 128), TC_IDESC, accumulate);  // qh . eh
+              accumulate = 1;
+              if (planes == 2) {
+                tc_mma_bf16(tmem_d, tc_desc(a0, lboA, 128), tc_desc(b0 + TC_BN * 16, lboB, 128), TC_IDESC, 1);  // qh . el
+                tc_mma_bf16(tmem_d, tc_desc(a0 + TC_BM * 16, lboA, 128), tc_desc(b0, lboB, 128), TC_IDESC, 1);  // ql . eh
+              }
             }
+            st_idx[nin++] = stage;
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
           }
-          tc_commit(empty + stage);  // the stage may be overwritten once these MMAs have read it
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+          for (int h = 0; h < nin; ++h) tc_commit(empty + st_idx[h]);  // the stages may be overwritten once these MMAs have read them
         }
         tc_commit(acc_full + acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
