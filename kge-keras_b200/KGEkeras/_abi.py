@@ -30,7 +30,7 @@ LOSS_KINDS = {  # reference names, utils.py:321-330
 OPT_KINDS = {"sgd": SGD, "adagrad": ADAGRAD, "lazy_adam": LAZY_ADAM, "adam": ADAM_DENSE}
 STATUS = {0: "OK", -1: "INVALID", -2: "CUDA", -3: "ALIGNMENT", -4: "UNSUPPORTED", -5: "WORKSPACE"}
 
-LIB_PATH = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "lib", "libkgeb200.so"))
+LIB_PATH = os.environ.get("KGEB_LIB_PATH") or os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "lib", "libkgeb200.so"))  # env: experiment builds
 
 
 class KgebError(RuntimeError):

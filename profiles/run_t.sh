@@ -1,3 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 300 python -m pytest tests/test_gpu_rank_tc.py tests/test_gpu_fullsize.py tests/test_gpu_siblings.py -m gpu -x -q -k "tc or c3 or c5 or tensor" 2>&1 | tail -2
-for md in bf16 exact; do timeout 120 python profiles/tc_bench.py --shape C3 --mode $md --iters 5 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('pair=2 $md', d['ms'], d['algorithmic_tflops'])"; done
+timeout 200 python -m pytest tests/test_gpu_rank_tc.py -m gpu -x -q 2>&1 | tail -2
+TAG=roles timeout 120 python profiles/exp_tc.py
+for v in noepi noload; do TAG=roles-$v KGEB_LIB_PATH=$PWD/kge-keras_b200/lib_$v/libkgeb200.so timeout 120 python profiles/exp_tc.py; done
+TAG=roles SHAPE=C5 timeout 120 python profiles/exp_tc.py
