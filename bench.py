@@ -480,13 +480,21 @@ def main():
                      "frac": ach / pk["hbm_gbs"],
                      "traffic": ncu_traffic("k_train_ring" if dom[0] == "k_train_fwd_bwd" else "k_opt_update_E"), "peak_source": pk["source"],
                      "note": "algorithmic = compulsory bytes with perfect on-chip reuse of the %d unique rows; the kernel's "
-                             "no-reuse gather+scatter request volume is %.0f MB/launch (L2-resident table)" % (U_E, gather_bytes / 1e6)},
+                             "no-reuse gather+scatter request volume is %.0f MB/launch (L2-resident table)" % (U_E, gather_bytes / 1e6),
+                     "l2_path": {"kernel_us": fb_ms * 1e3, "vector_reduction_floor_us": 59.0, "gather_plus_reduction_floor_us": 67.0,
+                                 "frac_of_floor": 67.0 / (fb_ms * 1e3),
+                                 "source": "profiles/micro/l2_rows.cu on a B200: red.global.add.v4.f32 row reductions sustain 5.1 TB/s "
+                                           "whatever the occupancy (cp.reduce.async.bulk the same), row gathers 14 TB/s; floors are for "
+                                           "this workload's 378 880 x 800 B row references (profiles/r01_v4_train_bound.md)"}},
         "roofline_step": {"bound": "hbm", "achieved": ach_step, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_step / pk["hbm_gbs"],
                           "bytes_step": bytes_step, "formula": "(4+24)*(We*U_E+Wr*U_R)+12*B (SURVEY 8d, Adam)"},
         "eval": {"metric": "filtered_eval_queries_per_s", "value": eval_qps, "unit": "queries/s", "queries_per_pass": 2 * nt,
                  "ms_per_pass": float(np.mean(eval_ms)), "passes": args.eval_steps, "scaling": "strong",
                  "gpu_launches_per_pass": int(eval_launches),
-                 "fp32_alu_tflops": (2 * d * nt * N + 3 * d * nt * N) * 1.0 / (float(np.mean(eval_ms)) * 1e-3) / 1e12},
+                 "fp32_alu_tflops": (2 * d * nt * N + 3 * d * nt * N) * 1.0 / (float(np.mean(eval_ms)) * 1e-3) / 1e12,
+                 "bound": "fp32 issue: two rounded fp32 operations per (query, entity, k) for the tail side, three for the head side; "
+                          "the tile kernel runs at 65 % of the FADD issue ceiling measured by profiles/micro/fadd_peak.cu "
+                          "(profiles/r01_v3_summary.md)"},
         "eval_tensor": {"workload": te["name"], "queries_per_pass": 2 * tnt, "scaling": "strong",
                         "filter": "synthetic CSR, Poisson(5.4) tail / Poisson(23.5) head known-true ids per query",
                         "parity": "exact_bf16x3 counts are bit-identical to the fp32 CUDA-core kernel (tests/test_gpu_rank_tc.py)",
