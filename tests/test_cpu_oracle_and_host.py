@@ -460,3 +460,21 @@ def test_oracle_optimizer_matches_torch_optim(opt):
             # dense torch optimizers also "update" untouched rows with a zero gradient: a no-op for SGD / Adagrad
             pass
         np.testing.assert_allclose(P, tp.detach().numpy(), rtol=1e-7, atol=1e-10)
+
+
+# ---- bench.py contract (reference arm runs on CPU, so it is testable here) ------------------------------------------
+def test_bench_reference_arm_prints_contract_line():
+    import json
+    import subprocess
+    import sys
+    root = ROOT
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--batch", "1024"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and d["metric"] == "train_triples_per_s" and d["unit"] == "triples/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert "workload" in d["config"] and "model" not in d["config"]
