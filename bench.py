@@ -373,6 +373,23 @@ def main():
         del leng, lb
         torch.cuda.empty_cache()
 
+    # ---- the same C2 step with the reference's default Dropout(0.2) on every gathered row (models.py:122; the headline runs
+    #      dp = 0 like the harness' params dict leaves it): Philox mask bits per element double the kernel's instruction count ----
+    train_dropout = None
+    if world == 1:
+        dms = []
+        for i in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.train_step(dev_batches[i % nb], None, offset=50_000 + i, dropout=0.2, **step_kw, **opt_kw)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                dms.append(e0.elapsed_time(e1))
+        train_dropout = {"dropout": 0.2, "ms_per_step": float(np.mean(dms)), "triples_per_s": B * (1 + K) / (float(np.mean(dms)) * 1e-3),
+                         "note": "counter-based Philox keep masks regenerated in the backward pass, nothing stored"}
+
     # ---- the remaining named shapes (BASELINE configs 0, 2, 3): one fused / unfused train step each, and HolE's 1-N eval ------
     other_shapes = None
     if world == 1 and not args.skip_shapes:
@@ -501,6 +518,7 @@ def main():
                         **tensor_eval},
         "train_large_table": train_large,
         "other_shapes": other_shapes,
+        "train_with_dropout": train_dropout,
         "clocks": sampler.summary(),
     }
     if world == 1 and not args.no_cpu_baseline:
