@@ -529,6 +529,29 @@ def main():
         line["cpu_baseline"] = {"value": cb["triples_per_s"], "unit": "triples/s", "cores": cb["threads"], "kind": "port",
                                 "sample": f"{cb['steps']} full steps (B={B}, K={K}) of the PyTorch-CPU fp32 restatement; TensorFlow not installable",
                                 "eval_queries_per_s": ce["queries_per_s"], "eval_sample": f"{ce['queries']} queries, NumPy restatement of validate, 1 process"}
+        # the reference's host batch pipeline (DataGenerator.__get_data, tests.py:55-61: generate_negative + oversample_data,
+        # restated literally in the oracle: per-row Python lists, random.choices) at the harness' batch of 2048 x 10,
+        # beside its device-side replacement (kgeb_negatives + kgeb_oversample through Engine.device_batch)
+        import random
+        hb = np.asarray(host_batches[0][:2048].numpy(), dtype=np.int64)
+        np.random.seed(0); random.seed(0)
+        t0 = time.perf_counter(); nrep = 0
+        while time.perf_counter() - t0 < 3.0:
+            X = ko.oversample_data([hb, ko.generate_negative(hb, N, K)])
+            nrep += 1
+        host_rate = nrep * len(X[0]) / (time.perf_counter() - t0)
+        db = dev_batches[0][:2048]
+        for _ in range(3):
+            eng.device_batch(db, K, 1, 0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(200):
+            eng.device_batch(db, K, 1, i)
+        torch.cuda.synchronize()
+        dev_rate = 200 * 2048 * K / (time.perf_counter() - t0)
+        line["cpu_baseline"]["host_batch_pipeline"] = {"reference_style_pairs_per_s": host_rate, "device_side_pairs_per_s": dev_rate,
+                                                        "batch": "2048 positives x 10 negatives -> (20480,3) positive and negative lists",
+                                                        "note": "1 thread; the reference's loop feeds its GPU step from this host code"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
