@@ -217,7 +217,7 @@ class EmbeddingModel:
                                          K=int(self.negative_samples), seed=self._seed, offset=self._step_counter,
                                          l3=float(self.regularization), dropout=float(self.dp.rate),
                                          **self._step_kwargs())
-        return res["loss"]
+        return res["loss"].clone()   # the engine reuses one device scalar for every step's loss
 
     def test_on_batch(self, x, y=None, **kwargs):
         pos, neg = self._split_xy(x)
@@ -256,22 +256,36 @@ class EmbeddingModel:
                 if hasattr(x, "on_epoch_end"):
                     x.on_epoch_end()
             else:
+                # array input: the triples go to the device once, every batch is a device-side row gather (the shuffle
+                # order comes from the global NumPy stream, like Keras' shuffle=True)
+                import torch
+                from ._engine import as_idx
                 pos, neg = self._split_xy(x)
-                pos = np.asarray(pos)
-                n = len(pos)
-                order = np.random.permutation(n) if shuffle else np.arange(n)
+                dev = self._engine_().device
+                if epoch == 0 or getattr(self, "_fit_cache_src", None) is not x:
+                    self._fit_cache_src = x
+                    self._fit_pos = as_idx(pos, dev)
+                    self._fit_neg = None if neg is None else as_idx(neg, dev)
+                pos_d, neg_d = self._fit_pos, self._fit_neg
+                n = pos_d.shape[0]
+                order = torch.from_numpy(np.random.permutation(n) if shuffle else np.arange(n)).to(dev)
                 nb = (n + bs - 1) // bs if steps_per_epoch is None else steps_per_epoch
-                per = None if neg is None else len(np.asarray(neg)) // n
+                per = None if neg_d is None else neg_d.shape[0] // n
+                ar = None if per is None else torch.arange(per, device=dev)
                 for b in range(nb):
                     sel = order[b * bs:(b + 1) * bs]
-                    if len(sel) == 0:
+                    if sel.numel() == 0:
                         break
-                    if neg is None:
-                        losses.append(self.train_on_batch(pos[sel]))
+                    if neg_d is None:
+                        losses.append(self.train_on_batch(pos_d[sel]))
                     else:
-                        nsel = (sel[:, None] * per + np.arange(per)[None, :]).reshape(-1)
-                        losses.append(self.train_on_batch([pos[sel], np.asarray(neg)[nsel]]))
-            logs = {"loss": float(np.mean([float(l.item()) for l in losses])) if losses else float("nan")}
+                        nsel = (sel[:, None] * per + ar[None, :]).reshape(-1)
+                        losses.append(self.train_on_batch([pos_d[sel], neg_d[nsel]]))
+            if losses:   # one read-back per epoch
+                import torch
+                logs = {"loss": float(torch.stack([l.reshape(()) for l in losses]).double().mean().item())}
+            else:
+                logs = {"loss": float("nan")}
             if validation_data is not None:
                 logs["val_loss"] = float(self.evaluate(validation_data, verbose=0))
             for cb in callbacks:
