@@ -37,13 +37,16 @@ extern "C" int kgeb_create(kgeb_ctx** out, int device, int64_t num_entities, int
   if (const char* e = getenv("KGEB_RING_CTAS")) c->env_ring_ctas = atoi(e);
   if (const char* e = getenv("KGEB_RING_D")) c->env_ring_d = atoi(e);
   if (const char* e = getenv("KGEB_TRAIN_KERNEL")) c->env_force_reg = strcmp(e, "reg") == 0;
+  if (const char* e = getenv("KGEB_ALLPAIRS")) c->env_allpairs_dense = strcmp(e, "dense") == 0;
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) c->ring_cfg[i][j].smem = -1;
   if ((e = cudaMalloc(&c->d_partials, sizeof(double) * 2 * KGEB_MAX_PARTIAL_BLOCKS)) != cudaSuccess ||
       (e = cudaMalloc(&c->d_ticket, sizeof(unsigned int))) != cudaSuccess ||
+      (e = cudaMalloc(&c->d_sort_scratch, KGEB_SORT_SCRATCH_BYTES)) != cudaSuccess ||
       (e = cudaMemset(c->d_ticket, 0, sizeof(unsigned int))) != cudaSuccess) {
     kgeb_fail(nullptr, KGEB_ERR_CUDA, "kgeb_create: %s", cudaGetErrorString(e));
     if (c->d_partials) cudaFree(c->d_partials);
     if (c->d_ticket) cudaFree(c->d_ticket);
+    if (c->d_sort_scratch) cudaFree(c->d_sort_scratch);
     delete c;
     return KGEB_ERR_CUDA;
   }
@@ -56,6 +59,7 @@ extern "C" int kgeb_destroy(kgeb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->d_partials) cudaFree(ctx->d_partials);
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
+  if (ctx->d_sort_scratch) cudaFree(ctx->d_sort_scratch);
   for (int i = 0; i < KGEB_TIMED_KERNELS; ++i)
     for (int j = 0; j < 2; ++j)
       if (ctx->ev[i][j]) cudaEventDestroy(ctx->ev[i][j]);

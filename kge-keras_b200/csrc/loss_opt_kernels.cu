@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(AP_TILE) k_loss_allpairs(const float* __restri
     for (int k = 0; k < lim; ++k) {
       float val, A;
       const float x = own_t ? tile[k] - mine : mine - tile[k];
-      pairwise_terms(kind, margin, x, val, A);
+      pairwise_terms<true>(kind, margin, x, val, A);
       accA += A;
       l32 += val;
     }
@@ -105,6 +105,99 @@ __global__ void __launch_bounds__(AP_TILE) k_loss_allpairs(const float* __restri
   }
 }
 __global__ void k_loss_allpairs_finish(const double* loss_acc, double scale, float* loss) { loss[0] = (float)(loss_acc[0] * scale); }
+
+// -------- ALLPAIRS hinge without the m x m walk ----------------------------------------------------------------------------
+// relu(margin + f_i - t_j) is non-zero exactly for the t_j below a threshold that depends on f_i, and the fp32 predicate
+// fl(margin + fl(f_i - t_j)) > 0 is monotone in t_j and in f_i.  So: sort both vectors in 1024-element chunks (one CTA per
+// chunk, bitonic network in shared memory), keep an exclusive prefix sum (double) of every sorted t-chunk, and let one thread
+// per element binary-search every chunk of the OTHER vector with that same fp32 predicate:
+//   df_i = #{j : pred} / cnt,  dt_j = -#{i : pred} / cnt      -- the integer counts of the m x m kernel, bit for bit
+//   loss = sum_i [ #_i * (margin + f_i) - sum of the t_j counted ] / cnt       (accumulated in double)
+// O(m * m/1024 * 10) probes instead of m^2 terms: the harness' m = 20 480 step (tests.py:81) drops from 251 us to a few us.
+constexpr int SC = 1024;   // chunk length
+__global__ void __launch_bounds__(SC / 2) k_chunk_sort(const float* __restrict__ t, int64_t B, const float* __restrict__ f, int64_t Bf,
+                                                       int tchunks, float* __restrict__ ts, float* __restrict__ fs, double* __restrict__ tp) {
+  __shared__ float s[SC];
+  __shared__ double ps[SC / 2];
+  const bool is_t = (int)blockIdx.x < tchunks;
+  const int c = is_t ? blockIdx.x : blockIdx.x - tchunks;
+  const float* src = is_t ? t : f;
+  const int64_t n = is_t ? B : Bf, base = (int64_t)c * SC;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < SC; i += SC / 2) s[i] = base + i < n ? __ldg(src + base + i) : __int_as_float(0x7f800000);  // +inf padding sorts last
+  __syncthreads();
+  for (int k = 2; k <= SC; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const int i = ((tid & ~(j - 1)) << 1) | (tid & (j - 1));   // the lower index of this thread's compare-exchange pair
+      const int p = i | j;
+      const bool asc = (i & k) == 0;
+      const float a = s[i], b = s[p];
+      if ((a > b) == asc) { s[i] = b; s[p] = a; }
+      __syncthreads();
+    }
+  float* dst = (is_t ? ts : fs) + base;
+  for (int i = tid; i < SC; i += SC / 2) dst[i] = s[i];
+  if (!is_t) return;
+  // exclusive prefix sums of the sorted t-chunk in double: tp[c][x] = sum of the x smallest (x = 0..SC)
+  const double a0 = (double)s[2 * tid], a1 = (double)s[2 * tid + 1];
+  const bool v0 = base + 2 * tid < n, v1 = base + 2 * tid + 1 < n;   // padding contributes nothing
+  ps[tid] = (v0 ? a0 : 0.0) + (v1 ? a1 : 0.0);
+  __syncthreads();
+  for (int off = 1; off < SC / 2; off <<= 1) {
+    const double add = tid >= off ? ps[tid - off] : 0.0;
+    __syncthreads();
+    ps[tid] += add;
+    __syncthreads();
+  }
+  const double before = tid ? ps[tid - 1] : 0.0;
+  double* d = tp + (int64_t)c * (SC + 1);
+  d[2 * tid] = before;
+  d[2 * tid + 1] = before + (v0 ? a0 : 0.0);
+  if (tid == SC / 2 - 1) d[SC] = ps[tid];
+}
+
+// one thread per element of f (blockIdx.y == 0) or of t (blockIdx.y == 1)
+__global__ void __launch_bounds__(256) k_allpairs_hinge_sorted(const float* __restrict__ t, int64_t B, const float* __restrict__ f, int64_t Bf,
+                                                               const float* __restrict__ ts, const float* __restrict__ fs,
+                                                               const double* __restrict__ tp, float margin, float w, float* dt, float* df,
+                                                               double* loss_acc) {
+  const bool f_side = blockIdx.y == 0;
+  const int64_t n_own = f_side ? Bf : B, n_oth = f_side ? B : Bf;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nch = (int)((n_oth + SC - 1) / SC);
+  double accL = 0.0;
+  int64_t cnt = 0;
+  if (i < n_own) {
+    const float mine = __ldg((f_side ? f : t) + i);
+    const float* oth = f_side ? ts : fs;
+    for (int c = 0; c < nch; ++c) {
+      const float* ch = oth + (int64_t)c * SC;
+      const int len = (int)(n_oth - (int64_t)c * SC < SC ? n_oth - (int64_t)c * SC : SC);
+      // f side: pred(f_i, t) holds for the SMALLEST t's -> count = first index where it fails
+      // t side: pred(f, t_j) holds for the LARGEST f's  -> count = len - first index where it holds
+      int lo = 0, hi = len;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const float o = __ldg(ch + mid);
+        const bool pr = f_side ? (__fadd_rn(margin, __fsub_rn(mine, o)) > 0.f) : (__fadd_rn(margin, __fsub_rn(o, mine)) > 0.f);
+        if (f_side ? pr : !pr) lo = mid + 1; else hi = mid;
+      }
+      if (f_side) {
+        cnt += lo;
+        accL += (double)lo * ((double)margin + (double)mine) - tp[(int64_t)c * (SC + 1) + lo];
+      } else {
+        cnt += len - lo;
+      }
+    }
+    const float sc = (float)((double)w / ((double)B * (double)Bf));
+    if (f_side) { if (df) df[i] = (float)cnt * sc; }
+    else        { if (dt) dt[i] = -(float)cnt * sc; }
+  }
+  if (f_side) {
+    accL = warp_sum_d(accL);
+    if ((threadIdx.x & 31) == 0 && accL != 0.0) atomicAdd(loss_acc, accL);
+  }
+}
 
 // -------- optimizer: a warp scans 32 row flags at a time, then updates the touched rows cooperatively -----------
 struct OptArgs {
@@ -235,6 +328,26 @@ extern "C" int kgeb_loss_fwd_bwd(kgeb_ctx* ctx, const float* t, int64_t B, const
     return KGEB_OK;
   }
   KGEB_REQUIRE(ctx, pair_mode == KGEB_ALLPAIRS, KGEB_ERR_INVALID, "unknown pair mode");
+  {
+    const int64_t tch = (B + SC - 1) / SC, fch = (Bf + SC - 1) / SC;
+    const size_t need = (size_t)(tch + fch) * SC * sizeof(float) + (size_t)tch * (SC + 1) * sizeof(double);
+    if (loss_kind == KGEB_PAIRWISE_HINGE && need <= KGEB_SORT_SCRATCH_BYTES && !ctx->env_allpairs_dense) {
+      // sorted path (exact same counts as the m x m walk, see k_allpairs_hinge_sorted)
+      double* tp = reinterpret_cast<double*>(ctx->d_sort_scratch);
+      float* ts = reinterpret_cast<float*>(tp + tch * (SC + 1));
+      float* fs = ts + tch * SC;
+      double* loss_acc = ctx->d_partials;
+      KGEB_CUDA_OK(ctx, cudaMemsetAsync(loss_acc, 0, sizeof(double), st));
+      k_chunk_sort<<<(unsigned)(tch + fch), SC / 2, 0, st>>>(t, B, f, Bf, (int)tch, ts, fs, tp);
+      KGEB_LAUNCH_OK(ctx);
+      const int64_t nmax = B > Bf ? B : Bf;
+      k_allpairs_hinge_sorted<<<dim3((unsigned)((nmax + 255) / 256), 2), 256, 0, st>>>(t, B, f, Bf, ts, fs, tp, margin, loss_weight, dt, df, loss_acc);
+      KGEB_LAUNCH_OK(ctx);
+      k_loss_allpairs_finish<<<1, 1, 0, st>>>(loss_acc, (double)loss_weight / ((double)B * (double)Bf), loss);
+      KGEB_LAUNCH_OK(ctx);
+      return KGEB_OK;
+    }
+  }
   if (dt) KGEB_CUDA_OK(ctx, cudaMemsetAsync(dt, 0, (size_t)B * sizeof(float), st));
   if (df) KGEB_CUDA_OK(ctx, cudaMemsetAsync(df, 0, (size_t)Bf * sizeof(float), st));
   double* loss_acc = ctx->d_partials;  // slot 0 doubles as the ALLPAIRS accumulator

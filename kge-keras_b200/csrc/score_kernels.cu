@@ -76,7 +76,6 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_score_bwd(ScoreArgs a, const i
 // are staged in shared memory, the candidate row twice in a row (o2[x] = o[x mod d]) so the window needs no modulo, the
 // multiplier row zero-padded to a multiple of 8.  Each x_k is still accumulated over i in ascending order with fmaf.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int hole_dpad(int d) { return (d + 7) & ~7; }
 // per-warp staging sizes in floats
 __device__ __host__ __forceinline__ int hole_lin(int d) { return ((d + 7) & ~7); }               // zero-padded row
 __device__ __host__ __forceinline__ int hole_dbl(int d) { return 2 * ((d + 7) & ~7) + 32; }      // doubled (circular) row

@@ -352,3 +352,41 @@ def test_device_batch_pipeline_bit_exact():
     np.testing.assert_array_equal(dneg.cpu().numpy(), neg[ko.philox_oversample_indices(m, m, seed, step, 1)])
     idx = ko.philox_oversample_indices(100, 200000, 5, 0, 0)
     assert idx.min() == 0 and idx.max() == 99 and abs(np.bincount(idx, minlength=100).std() / 2000 - np.sqrt(0.99 / 2000)) < 0.01
+
+
+@pytest.mark.parametrize("B,Bf", [(20480, 20480), (1000, 3333), (1, 5), (1025, 1024), (7, 1)])
+def test_allpairs_hinge_sorted_path_equals_dense_walk(B, Bf, monkeypatch):
+    """The harness' (m,m) hinge (tests.py:81): the chunk-sort + binary-search kernels give the same coefficient vectors as the
+    m x m walk -- integer counts times one scale, where the walk adds per-slice partial products in fp32 -- and the counts
+    are exactly the fp64 restatement's; ties and scores sitting exactly on the margin included."""
+    from KGEkeras._engine import Engine
+    rng = np.random.default_rng(B + Bf)
+    t = (rng.normal(size=B) * 2).astype(np.float32)
+    f = (rng.normal(size=Bf) * 2).astype(np.float32)
+    if B > 4 and Bf > 4:
+        f[:3] = t[:3] - 1.0          # margin + f - t == 0 exactly: not counted (strict >)
+        t[3:5] = t[0]                # ties
+    monkeypatch.setenv("KGEB_ALLPAIRS", "dense")
+    dense = Engine(ko.DISTMULT, 4, 2, 4, 4)
+    monkeypatch.delenv("KGEB_ALLPAIRS")
+    fast = Engine(ko.DISTMULT, 4, 2, 4, 4)
+    tt, ff = torch.from_numpy(t), torch.from_numpy(f)
+    L0, dt0, df0 = dense.loss(tt, ff, 1, ko.PAIRWISE_HINGE, ko.ALLPAIRS, 1.0, 0.7)
+    L1, dt1, df1 = fast.loss(tt, ff, 1, ko.PAIRWISE_HINGE, ko.ALLPAIRS, 1.0, 0.7)
+    torch.testing.assert_close(dt0, dt1, rtol=2e-6, atol=0)
+    torch.testing.assert_close(df0, df1, rtol=2e-6, atol=0)
+    Lw, wdt, wdf = ko.loss_and_coefs(ko.PAIRWISE_HINGE, ko.ALLPAIRS, t.astype(np.float64), f.astype(np.float64), 1, 1.0)
+    cnt = float(B) * float(Bf)
+    # (the restatement decides margin + f - t > 0 in fp64; on fp32 inputs that differs from the fp32 predicate only at exact
+    # cancellations, which the constructed ties cover: they are excluded by both)
+    cf = np.rint(df1.cpu().numpy().astype(np.float64) * cnt / 0.7)
+    ct = np.rint(dt1.cpu().numpy().astype(np.float64) * cnt / 0.7)
+    if B * Bf <= 4_000_000:   # the fp32 predicate itself, all pairs: the integer counts are exact
+        pred = (np.float32(1.0) + (f[:, None] - t[None, :])) > 0
+        np.testing.assert_array_equal(cf, pred.sum(1))
+        np.testing.assert_array_equal(ct, -pred.sum(0))
+    else:                     # against fp64: a pair within one fp32 rounding of the margin may fall on either side
+        assert np.max(np.abs(cf - np.rint(wdf * cnt))) <= 1 and np.mean(cf != np.rint(wdf * cnt)) < 1e-3
+        assert np.max(np.abs(ct - np.rint(wdt * cnt))) <= 1 and np.mean(ct != np.rint(wdt * cnt)) < 1e-3
+    assert abs(float(L1.item()) - 0.7 * Lw) <= 2e-6 * max(1.0, abs(Lw))
+    assert abs(float(L0.item()) - float(L1.item())) <= 2e-6 * max(1.0, abs(Lw))
