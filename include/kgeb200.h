@@ -193,7 +193,8 @@ KGEB_API int kgeb_rank_1n(kgeb_ctx* ctx, const float* E_shard, int64_t row_offse
  * KGEB_TC_BF16: one bf16 plane, no bound -> approximate (ranks may move at near-ties).  Replaces the per-query
  * model.predict + rankdata loop of validate, utils.py:210-245. */
 typedef enum { KGEB_TC_BF16 = 0, KGEB_TC_BF16X3_EXACT = 1 } kgeb_tc_mode;
-/* bytes of the packed bf16 image (+ row norms) of an entity shard of n_rows rows */
+/* (the filter CSR is applied inside the kernel's epilogue as a mask: ids must be sorted ascending per query)
+ * bytes of the packed bf16 image (+ row norms) of an entity shard of n_rows rows */
 KGEB_API int64_t kgeb_rank_tc_packed_bytes(const kgeb_ctx* ctx, int64_t n_rows, int mode);
 /* packs E_shard[n_rows, ldE] once per table version (the table is constant during validate) */
 KGEB_API int kgeb_rank_tc_pack_entities(kgeb_ctx* ctx, const float* E_shard, int64_t n_rows, int mode, void* packed,

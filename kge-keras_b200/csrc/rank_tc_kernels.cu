@@ -112,15 +112,17 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
                :
                : "memory");
 }
-// one accumulator against the row's band [lo, hi]:  cnt += s > hi;  msk |= bit when lo <= s <= hi (undecided)
-#define TC_CMP(S, HI, LO, CNT, MSK, BIT)                                                                                  \
-  asm("{\n\t.reg .pred ph, pu;\n\tsetp.gt.f32 ph, %2, %3;\n\t@ph add.s32 %0, %0, 1;\n\tsetp.ge.and.f32 pu, %2, %4, !ph;\n\t" \
+// one accumulator against the row's band [lo, hi]:  cmsk |= bit when s > hi (counted);  umsk |= bit when lo <= s <= hi
+// (undecided).  Masks instead of a running count: the target and the CSR filter ids are then excluded by clearing bits, and
+// the count is one popc per 32 columns -- the same four instructions per accumulator.
+#define TC_CMP(S, HI, LO, CMSK, UMSK, BIT)                                                                                \
+  asm("{\n\t.reg .pred ph, pu;\n\tsetp.gt.f32 ph, %2, %3;\n\t@ph or.b32 %0, %0, %5;\n\tsetp.ge.and.f32 pu, %2, %4, !ph;\n\t" \
       "@pu or.b32 %1, %1, %5;\n\t}"                                                                                       \
-      : "+r"(CNT), "+r"(MSK)                                                                                              \
+      : "+r"(CMSK), "+r"(UMSK)                                                                                            \
       : "r"(S), "f"(HI), "f"(LO), "n"(BIT))
 template <int J>
-__device__ __forceinline__ void tc_cmp32(const uint32_t (&r)[32], float hi, float lo, int& c0, int& c1, uint32_t& m0, uint32_t& m1) {
-  if constexpr (J < 32) {  // two independent counter / mask chains
+__device__ __forceinline__ void tc_cmp32(const uint32_t (&r)[32], float hi, float lo, uint32_t& c0, uint32_t& c1, uint32_t& m0, uint32_t& m1) {
+  if constexpr (J < 32) {  // two independent mask chains
     TC_CMP(r[J], hi, lo, c0, m0, 1u << J);
     TC_CMP(r[J + 1], hi, lo, c1, m1, 1u << (J + 1));
     tc_cmp32<J + 2>(r, hi, lo, c0, c1, m0, m1);
@@ -143,6 +145,8 @@ struct TcArgs {
   const float* emax;             // [ntiles*2]    max over each 128-entity slice of the upper bound of ||e||_2
   const float* tscore;           // [Q] exact target scores
   const int32_t* triples;        // [Q,3]
+  const int64_t* filt_offs;      // [Q+1] CSR of known-true GLOBAL entity ids per query, sorted ascending (or NULL)
+  const int32_t* filt_ids;
   int32_t* counts;               // [Q]
   uint32_t* wl_hdr;              // [0] = pairs appended (may exceed cap), [1] = cap
   uint2* wl;                     // (q, shard-local c)
@@ -272,7 +276,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t wcnt = 0;  // pairs waiting in wbuf (warp-uniform)
     uint32_t acc = 0, acc_phase = 0;
-    const bool approx = a.c_eps == 0.f;
 
     auto flush = [&]() {
       __syncwarp();
@@ -297,31 +300,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
       const float nmax = __ldg(a.emax + tile * 2 + chalf);
       const float hi = __fmaf_rn(epsq, nmax, __fmaf_rn(fabsf(t), a.t_slack, t));
       const float lo = __fmaf_rn(-epsq, nmax, __fmaf_rn(-fabsf(t), a.t_slack, t));
-      const int zero_counts = 0.f > hi ? 1 : 0;         // what a zero (padding) column contributes to the count
-      int cnt0 = 0, cnt1 = 0;
+      int cnt0 = 0;
+      // cursor into this query's sorted filter list: first id at or beyond this warp's first column (global id space)
+      int64_t fpos = 0, fend = 0;
+      if (a.filt_offs && qok) {
+        int64_t lo_i = __ldg(a.filt_offs + q);
+        fend = __ldg(a.filt_offs + q + 1);
+        const int64_t g0 = a.row_offset + n0;
+        int64_t hi_i = fend;
+        while (lo_i < hi_i) {
+          const int64_t mid = (lo_i + hi_i) >> 1;
+          if ((int64_t)__ldg(a.filt_ids + mid) < g0) lo_i = mid + 1; else hi_i = mid;
+        }
+        fpos = lo_i;
+      }
+      int64_t fnext = fpos < fend ? (int64_t)__ldg(a.filt_ids + fpos) - a.row_offset : INT64_MAX;   // shard-local column of the next filtered id
 
       // one 32-column chunk: counts, undecided mask, padding correction, append of the undecided pairs
       auto process = [&](uint32_t (&r)[32], int jc) {
-        uint32_t m0 = 0, m1 = 0;
-        tc_cmp32<0>(r, hi, lo, cnt0, cnt1, m0, m1);
-        uint32_t mask = m0 | m1;
+        uint32_t k0 = 0, k1 = 0, m0 = 0, m1 = 0;
+        tc_cmp32<0>(r, hi, lo, k0, k1, m0, m1);
+        uint32_t cmask = k0 | k1, mask = m0 | m1;
         const int64_t c0 = n0 + jc;
         const int64_t left = a.n_rows - c0;                     // columns of this chunk that are real entities
+        uint32_t keep = 0xffffffffu;
         if (left < 32) {                                        // warp-uniform: only in the last entity tile
-          const int nvalid = left < 0 ? 0 : (int)left;
-          mask &= nvalid == 0 ? 0u : (0xffffffffu >> (32 - nvalid));
-          cnt0 -= (32 - nvalid) * zero_counts;                  // padding rows are all-zero: their score is exactly 0
+          const int nvalid = left < 0 ? 0 : (int)left;          // padding rows are all-zero: never candidates
+          keep = nvalid == 0 ? 0u : (0xffffffffu >> (32 - nvalid));
         }
         const int64_t trel = tgt - c0;                          // the target itself is never a candidate (utils.py:169)
-        const bool tgt_here = trel >= 0 && trel < 32;
-        if (tgt_here) mask &= ~(1u << (int)trel);
-        if (approx && __any_sync(0xffffffffu, tgt_here)) {
-          // exact mode never counts the target (its score is inside the band by construction); without a band it can
-          uint32_t st = r[0];
-#pragma unroll
-          for (int j = 1; j < 32; ++j) st = (j == (int)trel) ? r[j] : st;
-          if (tgt_here && __uint_as_float(st) > hi) cnt0 -= 1;
+        if (trel >= 0 && trel < 32) keep &= ~(1u << (int)trel);
+        while (fnext < c0 + 32) {                               // known-true ids inside this chunk are not candidates either
+          if (fnext >= c0) keep &= ~(1u << (int)(fnext - c0));
+          ++fpos;
+          fnext = fpos < fend ? (int64_t)__ldg(a.filt_ids + fpos) - a.row_offset : INT64_MAX;
         }
+        cmask &= keep;
+        mask &= keep;
+        cnt0 += __popc(cmask);
         if (!qok) mask = 0;
         while (true) {
           const uint32_t have = __ballot_sync(0xffffffffu, mask != 0);
@@ -357,8 +373,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
       if (lane == 0) tc_mbar_arrive(acc_empty + acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       process(rB, 96);
-      const int cnt = cnt0 + cnt1;
-      if (qok && cnt != 0) atomicAdd(a.counts + q, cnt);
+      if (qok && cnt0 != 0) atomicAdd(a.counts + q, cnt0);
     }
     if (wcnt != 0) flush();
   }
@@ -532,6 +547,7 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
   a.qnorm = qnorm;
   a.emax = reinterpret_cast<const float*>(a.packedE + tc_align((size_t)nt * nkc * planes * TC_BN * 16) + tc_align((size_t)nt * TC_BN * 4));
   a.tscore = tscore; a.triples = triples; a.counts = counts;
+  a.filt_offs = filt_offsets; a.filt_ids = filt_ids;   // applied inside the epilogue as a mask: no correction pass
   a.wl_hdr = hdr; a.wl = wl; a.wl_cap = (uint32_t)worklist_cap;
   a.Q = Q; a.row_offset = row_offset; a.n_rows = n_rows;
   a.nkc = nkc; a.planes = planes; a.qtiles = (int)qt; a.ntiles = (int)nt; a.side = side;
@@ -566,9 +582,5 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
   // hdr[0] = pairs appended, hdr[1] = capacity (written by the kernel): the host checks hdr[0] <= hdr[1] after the pass
   const int rc = kgeb_internal_refine_worklist(ctx, E_shard, n_rows, qvec, tscore, Q, side, hdr, (uint32_t)worklist_cap, wl, counts, st);
   KGEB_TIME_END(ctx, KGEB_TIMED_RANK_REFINE, st);
-  if (rc != KGEB_OK) return rc;
-  if (filt_offsets)
-    return kgeb_internal_filter_correct(ctx, E_shard, row_offset, n_rows, qvec, tscore, triples, Q, side, filt_offsets, filt_ids,
-                                        counts, st);
-  return KGEB_OK;
+  return rc;
 }
