@@ -100,20 +100,36 @@ struct PairArgs {
   int32_t* counts;
 };
 
+// 16-byte asynchronous copy global -> shared (LDGSTS, L2 only); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int PAIR_LDP = 36;    // row stride in floats: 16-byte aligned rows, conflict-free LDS.128 by row (4*lane groups)
+constexpr int PAIR_NBUF = 3;    // k-chunks of 32 floats in flight per warp (two ahead of the one being accumulated)
+
 template <int OP, int SRC>
 __global__ void __launch_bounds__(PAIR_WARPS * 32) k_seqk_pairs(PairArgs a) {
   constexpr bool HEAD = op_two_part<OP>();
-  constexpr int LDP = 36;  // row stride in floats: 16-byte aligned rows, conflict-free LDS.128 by row (4*lane groups)
-  __shared__ __align__(16) float sq[PAIR_WARPS][32][LDP];
-  __shared__ __align__(16) float se[PAIR_WARPS][32][LDP];
-  __shared__ __align__(16) float sq2[HEAD ? PAIR_WARPS : 1][HEAD ? 32 : 1][HEAD ? LDP : 4];
+  constexpr int LDP = PAIR_LDP, NB = PAIR_NBUF;
+  constexpr int ROWS = HEAD ? 3 : 2;            // q, e (and the second query part) per pair
+  extern __shared__ __align__(16) float pair_smem[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int sub = lane >> 3, l8 = lane & 7;  // 8 lanes x float4 cover one 128-byte row segment; 4 pairs per load
+  // per warp: [NB][ROWS][32 pairs][LDP]
+  float* wbase = pair_smem + (size_t)w * NB * ROWS * 32 * LDP;
+  auto buf = [&](int b, int r) { return wbase + ((size_t)(b * ROWS + r) * 32) * LDP; };
+  const int sub = lane >> 3, l8 = lane & 7;  // 8 lanes x 16 bytes cover one 128-byte row segment; 4 pairs per copy instruction
   int64_t n;
   if (SRC == PAIRS_TARGET) n = a.Q;
   else if (SRC == PAIRS_WORKLIST) n = a.wl_hdr[0] < a.wl_cap ? a.wl_hdr[0] : a.wl_cap;
   else n = a.offs[a.Q];
   const int64_t warp0 = (int64_t)blockIdx.x * PAIR_WARPS + w, nwarps = (int64_t)gridDim.x * PAIR_WARPS;
+  const int nkc = (a.W + 31) / 32;
   for (int64_t base = warp0 * 32; base < n; base += nwarps * 32) {
     const int64_t x = base + lane;
     bool valid = x < n;
@@ -140,39 +156,50 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_seqk_pairs(PairArgs a) {
       valid = valid && c >= 0 && c < a.n_rows;   // another shard owns this candidate
       if (!valid) { q = 0; c = 0; }
     }
-    // element offsets of the two rows of MY pair; the loaders fetch them from the owning lane
+    // element offsets of the two rows of MY pair; the copy lanes fetch them from the owning lane
     const int64_t qoff = q * a.qw, eoff = c * (int64_t)a.ldE;
-    float acc = 0.f;
-    for (int k0 = 0; k0 < a.W; k0 += 32) {
-      const int k = k0 + 4 * l8;
-      const bool kin = k < a.W;                 // W % 4 == 0: a float4 is entirely inside or outside the row
+    // issue the asynchronous copies of k-chunk kc (32 floats of every pair's rows) into buffer kc % NB
+    auto issue = [&](int kc) {
+      const int k = kc * 32 + 4 * l8;
+      const bool kin = k < a.W;                 // W % 4 == 0: a 16-byte piece is entirely inside or outside the row
+      const int b = kc % NB;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int p = 4 * i + sub;
         const int64_t qo = __shfl_sync(0xffffffffu, qoff, p), eo = __shfl_sync(0xffffffffu, eoff, p);
-        const float4 vq = kin ? ldg4(reinterpret_cast<const float4*>(a.qvec + qo + k)) : f4zero();
-        const float4 ve = kin ? ldg4(reinterpret_cast<const float4*>(a.Es + eo + k)) : f4zero();
-        *reinterpret_cast<float4*>(&sq[w][p][4 * l8]) = vq;
-        *reinterpret_cast<float4*>(&se[w][p][4 * l8]) = ve;
-        if (HEAD) {
-          const float4 v2 = kin ? ldg4(reinterpret_cast<const float4*>(a.qvec + qo + a.W + k)) : f4zero();
-          *reinterpret_cast<float4*>(&sq2[w][p][4 * l8]) = v2;
-        }
+        cp_async16(buf(b, 0) + p * LDP + 4 * l8, a.qvec + qo + (kin ? k : 0), kin);
+        cp_async16(buf(b, 1) + p * LDP + 4 * l8, a.Es + eo + (kin ? k : 0), kin);
+        if (HEAD) cp_async16(buf(b, 2) + p * LDP + 4 * l8, a.qvec + qo + a.W + (kin ? k : 0), kin);
       }
+      cp_async_commit();
+    };
+    __syncwarp();                                // every lane is done with the previous batch's buffers
+    issue(0);
+    if (nkc > 1) issue(1); else cp_async_commit();
+    float acc = 0.f;
+    for (int kc = 0; kc < nkc; ++kc) {
+      cp_async_wait<1>();                        // chunk kc has landed (at most the newest group is still in flight)
       __syncwarp();
-      const int klim = a.W - k0 < 32 ? a.W - k0 : 32;   // multiple of 4
+      const int b = kc % NB;
+      const float* rq = buf(b, 0) + lane * LDP;
+      const float* re = buf(b, 1) + lane * LDP;
+      const float* rq2 = HEAD ? buf(b, 2) + lane * LDP : nullptr;
+      const int klim = a.W - kc * 32 < 32 ? a.W - kc * 32 : 32;   // multiple of 4
       for (int kk = 0; kk < klim; kk += 4) {
-        const float4 x4 = *reinterpret_cast<const float4*>(&sq[w][lane][kk]);
-        const float4 e4 = *reinterpret_cast<const float4*>(&se[w][lane][kk]);
+        const float4 x4 = *reinterpret_cast<const float4*>(rq + kk);
+        const float4 e4 = *reinterpret_cast<const float4*>(re + kk);
         float4 y4 = f4zero();
-        if (HEAD) y4 = *reinterpret_cast<const float4*>(&sq2[w][lane][kk]);
+        if (HEAD) y4 = *reinterpret_cast<const float4*>(rq2 + kk);
         acc = seq_term<OP>(acc, x4.x, y4.x, e4.x);
         acc = seq_term<OP>(acc, x4.y, y4.y, e4.y);
         acc = seq_term<OP>(acc, x4.z, y4.z, e4.z);
         acc = seq_term<OP>(acc, x4.w, y4.w, e4.w);
       }
-      __syncwarp();
+      // buffer (kc + 2) % NB == (kc - 1) % NB was read in the previous iteration; every lane has passed this iteration's
+      // __syncwarp since, so it may be refilled
+      if (kc + 2 < nkc) issue(kc + 2); else cp_async_commit();
     }
+    cp_async_wait<0>();
     if (!valid) continue;
     const float sc = seq_finish<OP>(acc, a.fin);
     if (SRC == PAIRS_TARGET) a.tscore[q] = sc;
@@ -181,18 +208,27 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_seqk_pairs(PairArgs a) {
   }
 }
 
+constexpr size_t pair_smem_bytes(bool head) { return (size_t)PAIR_WARPS * PAIR_NBUF * (head ? 3 : 2) * 32 * PAIR_LDP * sizeof(float); }
+
+// (more than 48 KB of dynamic shared memory needs the per-function opt-in; setting it again is harmless)
+#define KGEB_PAIRS_LAUNCH(OPV)                                                                                             \
+  {                                                                                                                        \
+    const size_t psm = pair_smem_bytes(op_two_part<OPV>());                                                                \
+    cudaFuncSetAttribute(k_seqk_pairs<OPV, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);                   \
+    k_seqk_pairs<OPV, SRC><<<blocks, PAIR_WARPS * 32, psm, st>>>(a);                                                       \
+  }
 template <int SRC>
 void launch_pairs(int op, int blocks, cudaStream_t st, const PairArgs& a) {
   switch (op) {
-    case OP_ML1_HEAD: k_seqk_pairs<OP_ML1_HEAD, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
-    case OP_ML2_HEAD: k_seqk_pairs<OP_ML2_HEAD, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
-    case OP_PSIN_TAIL: k_seqk_pairs<OP_PSIN_TAIL, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
-    case OP_PSIN_HEAD: k_seqk_pairs<OP_PSIN_HEAD, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
-    case OP_DOT: k_seqk_pairs<OP_DOT, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
-    case OP_L1_TAIL: k_seqk_pairs<OP_L1_TAIL, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
-    case OP_L1_HEAD: k_seqk_pairs<OP_L1_HEAD, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
-    case OP_L2_TAIL: k_seqk_pairs<OP_L2_TAIL, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
-    default: k_seqk_pairs<OP_L2_HEAD, SRC><<<blocks, PAIR_WARPS * 32, 0, st>>>(a); break;
+    case OP_ML1_HEAD: KGEB_PAIRS_LAUNCH(OP_ML1_HEAD); break;
+    case OP_ML2_HEAD: KGEB_PAIRS_LAUNCH(OP_ML2_HEAD); break;
+    case OP_PSIN_TAIL: KGEB_PAIRS_LAUNCH(OP_PSIN_TAIL); break;
+    case OP_PSIN_HEAD: KGEB_PAIRS_LAUNCH(OP_PSIN_HEAD); break;
+    case OP_DOT: KGEB_PAIRS_LAUNCH(OP_DOT); break;
+    case OP_L1_TAIL: KGEB_PAIRS_LAUNCH(OP_L1_TAIL); break;
+    case OP_L1_HEAD: KGEB_PAIRS_LAUNCH(OP_L1_HEAD); break;
+    case OP_L2_TAIL: KGEB_PAIRS_LAUNCH(OP_L2_TAIL); break;
+    default: KGEB_PAIRS_LAUNCH(OP_L2_HEAD); break;
   }
 }
 
