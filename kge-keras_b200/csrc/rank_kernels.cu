@@ -88,7 +88,10 @@ __global__ void k_query_prep(int kind, int side, int gamma_sub, const float* __r
 // arithmetic is exactly seq_score's (same order, same roundings), only the loads are cooperative.
 // ---------------------------------------------------------------------------------------------------
 enum { PAIRS_TARGET = 0, PAIRS_WORKLIST = 1, PAIRS_FILTER = 2 };
-constexpr int PAIR_WARPS = 2;
+#ifndef KGEB_PAIR_WARPS
+#define KGEB_PAIR_WARPS 2
+#endif
+constexpr int PAIR_WARPS = KGEB_PAIR_WARPS;
 
 struct PairArgs {
   const float* Es; int64_t row_offset, n_rows; int ldE, W;
@@ -111,7 +114,10 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 constexpr int PAIR_LDP = 36;    // row stride in floats: 16-byte aligned rows, conflict-free LDS.128 by row (4*lane groups)
-constexpr int PAIR_NBUF = 3;    // k-chunks of 32 floats in flight per warp (two ahead of the one being accumulated)
+#ifndef KGEB_PAIR_NBUF
+#define KGEB_PAIR_NBUF 3
+#endif
+constexpr int PAIR_NBUF = KGEB_PAIR_NBUF;    // k-chunks of 32 floats in flight per warp (two ahead of the one being accumulated)
 
 template <int OP, int SRC>
 __global__ void __launch_bounds__(PAIR_WARPS * 32) k_seqk_pairs(PairArgs a) {
@@ -174,11 +180,13 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_seqk_pairs(PairArgs a) {
       cp_async_commit();
     };
     __syncwarp();                                // every lane is done with the previous batch's buffers
-    issue(0);
-    if (nkc > 1) issue(1); else cp_async_commit();
+#pragma unroll
+    for (int pre = 0; pre < NB - 1; ++pre) {     // NB - 1 chunks ahead; empty groups keep the group count in step
+      if (pre < nkc) issue(pre); else cp_async_commit();
+    }
     float acc = 0.f;
     for (int kc = 0; kc < nkc; ++kc) {
-      cp_async_wait<1>();                        // chunk kc has landed (at most the newest group is still in flight)
+      cp_async_wait<NB - 2>();                   // chunk kc has landed (only the NB - 2 newest groups may still be in flight)
       __syncwarp();
       const int b = kc % NB;
       const float* rq = buf(b, 0) + lane * LDP;
@@ -195,9 +203,9 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_seqk_pairs(PairArgs a) {
         acc = seq_term<OP>(acc, x4.z, y4.z, e4.z);
         acc = seq_term<OP>(acc, x4.w, y4.w, e4.w);
       }
-      // buffer (kc + 2) % NB == (kc - 1) % NB was read in the previous iteration; every lane has passed this iteration's
+      // buffer (kc + NB - 1) % NB == (kc - 1) % NB was read in the previous iteration; every lane has passed this iteration's
       // __syncwarp since, so it may be refilled
-      if (kc + 2 < nkc) issue(kc + 2); else cp_async_commit();
+      if (kc + NB - 1 < nkc) issue(kc + NB - 1); else cp_async_commit();
     }
     cp_async_wait<0>();
     if (!valid) continue;
