@@ -270,8 +270,8 @@ class Engine:
         tri = as_idx(triples, self.device)
         Q = tri.shape[0]
         qw = self.lib.kgeb_query_width(self.ctx, side)
-        qvec = torch.zeros(Q, qw, dtype=torch.float32, device=self.device)
-        tscore = torch.zeros(Q, dtype=torch.float32, device=self.device)
+        qvec = torch.empty(Q, qw, dtype=torch.float32, device=self.device)   # every row is written: the whole table is local
+        tscore = torch.empty(Q, dtype=torch.float32, device=self.device)
         counts = torch.zeros(Q, dtype=torch.int32, device=self.device) if counts is None else counts
         st = _stream()
         self._check(self.lib.kgeb_query_prep(self.ctx, _ptr(self.E), 0, self.N, _ptr(self.Rel), _ptr(tri), Q, side, _ptr(qvec), st))
@@ -314,8 +314,8 @@ class Engine:
         tri = as_idx(triples, self.device)
         Q = tri.shape[0]
         qw = self.lib.kgeb_query_width(self.ctx, side)
-        qvec = torch.zeros(Q, qw, dtype=torch.float32, device=self.device)
-        tscore = torch.zeros(Q, dtype=torch.float32, device=self.device)
+        qvec = torch.empty(Q, qw, dtype=torch.float32, device=self.device)   # every row is written: the whole table is local
+        tscore = torch.empty(Q, dtype=torch.float32, device=self.device)
         st = _stream()
         self._check(self.lib.kgeb_query_prep(self.ctx, _ptr(self.E), 0, self.N, _ptr(self.Rel), _ptr(tri), Q, side, _ptr(qvec), st))
         self._check(self.lib.kgeb_target_scores(self.ctx, _ptr(self.E), 0, self.N, _ptr(qvec), _ptr(tri), Q, side, _ptr(tscore), st))

@@ -16,67 +16,72 @@ using namespace kgeb_rank;
 namespace {
 
 // ---------------------------------------------------------------------------------------------------
-// query vectors; one thread per output element
+// query vectors
 // ---------------------------------------------------------------------------------------------------
-__global__ void k_query_prep(int kind, int side, int gamma_sub, const float* __restrict__ Es, int64_t row_offset, int64_t n_rows, int ldE,
-                             const float* __restrict__ R, int ldR, int W, const int32_t* __restrict__ triples, int64_t Q,
-                             int qw, float* __restrict__ qvec) {
-  const int64_t total = Q * (int64_t)qw;
-  for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t q = x / qw;
-    const int k = (int)(x - q * qw);
+// one WARP per query: the triple and the row pointers are read once, the lanes stride over the output elements (coalesced)
+__global__ void __launch_bounds__(256) k_query_prep(int kind, int side, int gamma_sub, const float* __restrict__ Es, int64_t row_offset,
+                                                    int64_t n_rows, int ldE, const float* __restrict__ R, int ldR, int W,
+                                                    const int32_t* __restrict__ triples, int64_t Q, int qw, float* __restrict__ qvec) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t q = warp0; q < Q; q += nwarps) {
     const int64_t src = side == KGEB_SIDE_TAIL ? triples[3 * q] : triples[3 * q + 2];
     if (src < row_offset || src >= row_offset + n_rows) continue;  // another shard owns this query's source row
     const float* e = Es + (src - row_offset) * (int64_t)ldE;   // s (tail queries) or o (head queries)
     const float* p = R + (int64_t)triples[3 * q + 1] * ldR;
-    float out;
+    float* out = qvec + q * (int64_t)qw;
     if (kind == KGEB_DISTMULT) {
-      out = side == KGEB_SIDE_TAIL ? __fmul_rn(e[k], p[k]) : __fmul_rn(p[k], e[k]);
+      for (int k = lane; k < W; k += 32) out[k] = side == KGEB_SIDE_TAIL ? __fmul_rn(e[k], p[k]) : __fmul_rn(p[k], e[k]);
     } else if (kind == KGEB_COMPLEX) {
       const int d = W / 2;
-      const int j = k < d ? k : k - d;
-      const float er = e[j], ei = e[d + j], pr = p[j], pi = p[d + j];
-      if (side == KGEB_SIDE_TAIL)  // e = s:  [sr pr - si pi | si pr + sr pi]
-        out = k < d ? __fsub_rn(__fmul_rn(er, pr), __fmul_rn(ei, pi)) : __fadd_rn(__fmul_rn(ei, pr), __fmul_rn(er, pi));
-      else                         // e = o:  [pr or + pi oi | pr oi - pi or]
-        out = k < d ? __fadd_rn(__fmul_rn(pr, er), __fmul_rn(pi, ei)) : __fsub_rn(__fmul_rn(pr, ei), __fmul_rn(pi, er));
-    } else if (kind == KGEB_HOLE) {
-      float acc = 0.f;
-      if (side == KGEB_SIDE_TAIL) {  // q_j = sum_i s_i p_{(j-i) mod d}
-        int jj = k;
-        for (int i = 0; i < W; ++i) {
-          acc = __fadd_rn(acc, __fmul_rn(e[i], p[jj]));
-          if (--jj < 0) jj = W - 1;
-        }
-      } else {                        // q_i = sum_k p_k o_{(i+k) mod d}
-        int jj = k;
-        for (int i = 0; i < W; ++i) {
-          acc = __fadd_rn(acc, __fmul_rn(p[i], e[jj]));
-          if (++jj == W) jj = 0;
+      for (int j = lane; j < d; j += 32) {
+        const float er = e[j], ei = e[d + j], pr = p[j], pi = p[d + j];
+        if (side == KGEB_SIDE_TAIL) {   // e = s:  [sr pr - si pi | si pr + sr pi]
+          out[j] = __fsub_rn(__fmul_rn(er, pr), __fmul_rn(ei, pi));
+          out[d + j] = __fadd_rn(__fmul_rn(ei, pr), __fmul_rn(er, pi));
+        } else {                        // e = o:  [pr or + pi oi | pr oi - pi or]
+          out[j] = __fadd_rn(__fmul_rn(pr, er), __fmul_rn(pi, ei));
+          out[d + j] = __fsub_rn(__fmul_rn(pr, ei), __fmul_rn(pi, er));
         }
       }
-      out = acc;
+    } else if (kind == KGEB_HOLE) {
+      for (int k = lane; k < W; k += 32) {
+        float acc = 0.f;
+        if (side == KGEB_SIDE_TAIL) {  // q_j = sum_i s_i p_{(j-i) mod d}
+          int jj = k;
+          for (int i = 0; i < W; ++i) {
+            acc = __fadd_rn(acc, __fmul_rn(e[i], p[jj]));
+            if (--jj < 0) jj = W - 1;
+          }
+        } else {                        // q_i = sum_k p_k o_{(i+k) mod d}
+          int jj = k;
+          for (int i = 0; i < W; ++i) {
+            acc = __fadd_rn(acc, __fmul_rn(p[i], e[jj]));
+            if (++jj == W) jj = 0;
+          }
+        }
+        out[k] = acc;
+      }
     } else if (kind == KGEB_ROTATE) {
       // models.py:439-459: the score is linear in the candidate row.  tail: gamma - A = const + sum_j o_j -> q = 1;
       // head: gamma - A = const - e . [(c + s) | (c - s)], c/s = cos/sin of the relation phases.  The per-query constant
       // cancels inside one query's ranking (target and candidates share it); gamma <= 0 ranks by A itself: sign flips.
       const int d = W / 2;
-      float v;
-      if (side == KGEB_SIDE_TAIL) v = 1.f;
-      else {
-        float sn, c;
-        sincosf(p[k < d ? k : k - d], &sn, &c);
-        v = k < d ? -__fadd_rn(c, sn) : -__fsub_rn(c, sn);
+      for (int k = lane; k < W; k += 32) {
+        float v;
+        if (side == KGEB_SIDE_TAIL) v = 1.f;
+        else {
+          float sn, c;
+          sincosf(p[k < d ? k : k - d], &sn, &c);
+          v = k < d ? -__fadd_rn(c, sn) : -__fsub_rn(c, sn);
+        }
+        out[k] = gamma_sub ? v : -v;
       }
-      out = gamma_sub ? v : -v;
     } else if (kind == KGEB_MODE_L1 || kind == KGEB_MODE_L2) {  // tail r = s*p - e; head r = e*p - o keeps [p | o]
-      if (side == KGEB_SIDE_TAIL) out = __fmul_rn(e[k], p[k]);
-      else out = k < W ? p[k] : e[k - W];
+      for (int k = lane; k < qw; k += 32) out[k] = side == KGEB_SIDE_TAIL ? __fmul_rn(e[k], p[k]) : (k < W ? p[k] : e[k - W]);
     } else {  // TransE, pRotatE: tail a = s + p; head keeps [p | o] so (e + p) - o follows the reference's order
-      if (side == KGEB_SIDE_TAIL) out = __fadd_rn(e[k], p[k]);
-      else out = k < W ? p[k] : e[k - W];
+      for (int k = lane; k < qw; k += 32) out[k] = side == KGEB_SIDE_TAIL ? __fadd_rn(e[k], p[k]) : (k < W ? p[k] : e[k - W]);
     }
-    qvec[x] = out;
   }
 }
 
@@ -411,7 +416,7 @@ extern "C" int kgeb_query_prep(kgeb_ctx* ctx, const float* E_shard, int64_t row_
                "1-N ranking needs e_dim == r_dim (RotatE: e_dim == 2 * r_dim)");
   if (Q == 0) return KGEB_OK;
   const int qw = kgeb_query_width(ctx, side);
-  k_query_prep<<<grid1d(ctx, Q * (int64_t)qw, 256), 256, 0, (cudaStream_t)stream>>>(
+  k_query_prep<<<grid1d(ctx, Q * 32, 256), 256, 0, (cudaStream_t)stream>>>(
       ctx->kind, side, ctx->gamma > 0.f ? 1 : 0, E_shard, row_offset, n_rows, ctx->ldE, R, ctx->ldR, ctx->we, triples, Q, qw, qvec);
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
