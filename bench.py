@@ -290,6 +290,28 @@ def main():
         dist.all_reduce(tev, op=dist.ReduceOp.MAX)
     eval_qps = args.eval_steps * 2 * nt / (float(tev.item()) * 1e-3)
 
+    # ---- the same evaluation end to end through the reference-facing call: validate(model, test, N, bs, filtering_triples) with
+    #      HOST arrays (filter-CSR build, uploads, ranking, read-back of the ranks, the 15-key metrics dict) ------------------------
+    eval_e2e = None
+    if world == 1:
+        import KGEkeras
+        from KGEkeras import utils as ku
+        vm = KGEkeras.TransE(e_dim=d, r_dim=d, num_entities=N, num_relations=R, norm=1, gamma=w["gamma"], dp=0.0, init_entities=E0, init_relations=R0)
+        vfilt = np.stack([erng.integers(0, N, 89869), erng.integers(0, R, 89869), erng.integers(0, N, 89869)], axis=1)   # |train|+|valid| of WN18RR
+        vkey = lambda a: (a[:, 0].astype(np.int64) * R + a[:, 1]) * N + a[:, 2]
+        vfilt = vfilt[~np.isin(vkey(vfilt), vkey(tri))]          # the reference crashes when a test triple is in its own filter
+        ku.validate(vm, tri, N, 32, vfilt)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            vres = ku.validate(vm, tri, N, 32, vfilt)
+        torch.cuda.synchronize()
+        vdt = (time.perf_counter() - t0) / 3
+        eval_e2e = {"api": "KGEkeras.utils.validate(model, test_triples, N, bs, filtering_triples) with host arrays", "queries_per_s": 2 * nt / vdt,
+                    "ms_per_call": vdt * 1e3, "filter_triples": int(len(vfilt)), "mrr": float(vres["mrr"])}
+        del vm
+        torch.cuda.empty_cache()
+
     # ---- 1-N filtered evaluation of a dot-product model on the tensor cores (BASELINE configs[2] shape) --------------
     te = TENSOR_EVAL
     tN, tR, tW, tnt = te["N"], te["R"], 2 * te["d"], te["test_triples"]
@@ -507,7 +529,7 @@ def main():
                           "bytes_step": bytes_step, "formula": "(4+24)*(We*U_E+Wr*U_R)+12*B (SURVEY 8d, Adam)"},
         "eval": {"metric": "filtered_eval_queries_per_s", "value": eval_qps, "unit": "queries/s", "queries_per_pass": 2 * nt,
                  "ms_per_pass": float(np.mean(eval_ms)), "passes": args.eval_steps, "scaling": "strong",
-                 "gpu_launches_per_pass": int(eval_launches),
+                 "gpu_launches_per_pass": int(eval_launches), "e2e": eval_e2e,
                  "fp32_alu_tflops": (2 * d * nt * N + 3 * d * nt * N) * 1.0 / (float(np.mean(eval_ms)) * 1e-3) / 1e12,
                  "bound": "fp32 issue: two rounded fp32 operations per (query, entity, k) for the tail side, three for the head side; "
                           "the tile kernel runs at 65 % of the FADD issue ceiling measured by profiles/micro/fadd_peak.cu "

@@ -127,8 +127,11 @@ def build_filter_csr(test, filtering_triples, side):
     span = int(max(filt.max(), test.max())) + 1
     if span ** 3 >= 2 ** 62:
         raise ValueError("ids too large for the packed filter key")
-    # one sortable key per filter triple: (key0, key1, value); unique() sorts and de-duplicates in one pass
-    packed = np.unique((filt[:, kc[0]] * span + filt[:, kc[1]]) * span + filt[:, vc])
+    # one sortable key per filter triple: (key0, key1, value); sort, then drop adjacent duplicates (np.unique's hash
+    # path is 10x slower than the integer sort on these sizes)
+    packed = np.sort((filt[:, kc[0]] * span + filt[:, kc[1]]) * span + filt[:, vc])
+    if len(packed) > 1:
+        packed = packed[np.concatenate(([True], packed[1:] != packed[:-1]))]
     qkey = (test[:, kc[0]] * span + test[:, kc[1]]) * span
     lo = np.searchsorted(packed, qkey, side="left")
     hi = np.searchsorted(packed, qkey + span, side="left")
@@ -145,6 +148,39 @@ def build_filter_csr(test, filtering_triples, side):
     if np.any(ids == test[seg, vc]):
         raise ValueError("list.remove(x): x not in list")
     return offs, ids.astype(np.int32)
+
+
+def build_filter_csr_device(test_t, filt_t, side):
+    """build_filter_csr on the GPU (index bookkeeping only: one sort of the packed filter keys, two searchsorted, one gather),
+    for validate(): the NumPy builder takes 4-23 ms per side on the bundled datasets, more than the ranking kernels themselves.
+    test_t (Q,3) / filt_t (F,3) int64 CUDA tensors -> (offsets int64[Q+1], ids int32[nnz]) on the same device; same ValueError
+    as the host builder when a query's own target is in its filter set."""
+    import torch
+    kc = (0, 1) if side == "tail" else (1, 2)
+    vc = 2 if side == "tail" else 0
+    Q = test_t.shape[0]
+    dev = test_t.device
+    if filt_t.shape[0] == 0 or Q == 0:
+        return torch.zeros(Q + 1, dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.int32, device=dev)
+    span = int(max(int(filt_t.max()), int(test_t.max()))) + 1
+    if span ** 3 >= 2 ** 62:
+        raise ValueError("ids too large for the packed filter key")
+    packed = torch.unique((filt_t[:, kc[0]] * span + filt_t[:, kc[1]]) * span + filt_t[:, vc])   # sorted, de-duplicated
+    qkey = (test_t[:, kc[0]] * span + test_t[:, kc[1]]) * span
+    lo = torch.searchsorted(packed, qkey)
+    hi = torch.searchsorted(packed, qkey + span)
+    lens = hi - lo
+    offs = torch.zeros(Q + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(lens, 0, out=offs[1:])
+    nnz = int(offs[-1].item())
+    if nnz == 0:
+        return offs, torch.zeros(0, dtype=torch.int32, device=dev)
+    seg = torch.repeat_interleave(torch.arange(Q, device=dev), lens, output_size=nnz)
+    pos = lo[seg] + (torch.arange(nnz, device=dev) - offs[seg])
+    ids = packed[pos] - qkey[seg]
+    if bool((ids == test_t[seg, vc]).any().item()):
+        raise ValueError("list.remove(x): x not in list")
+    return offs, ids.to(torch.int32)
 
 
 def shard_rows(num_entities, world, rank):
@@ -181,12 +217,14 @@ def filtered_ranks(model, test_data, filtering_triples, group=None):
     tc_mode = abi.TC_BF16 if mode == "bf16" else abi.TC_BF16X3_EXACT
     packed = eng.pack_entities_tc(tc_mode, rows) if use_tc else None   # the table is constant during validate: pack once
     out = []
+    test_t = torch.from_numpy(test).to(eng.device)
+    filt_t = torch.from_numpy(np.asarray(filtering_triples, dtype=np.int64).reshape(-1, 3)).to(eng.device)
     for side, code in (("tail", abi.SIDE_TAIL), ("head", abi.SIDE_HEAD)):
-        offs, ids = build_filter_csr(test, filtering_triples, side)
+        offs, ids = build_filter_csr_device(test_t, filt_t, side)
         if use_tc:
-            part = eng.rank_counts_tc(test, code, offs, ids, row_range=rows, mode=tc_mode, packed=packed)
+            part = eng.rank_counts_tc(test_t, code, offs, ids, row_range=rows, mode=tc_mode, packed=packed)
         else:
-            part = eng.rank_counts(test, code, offs, ids, row_range=rows)
+            part = eng.rank_counts(test_t, code, offs, ids, row_range=rows)
         counts = merge_partial_counts(part, group)
         out.append(counts.cpu().numpy().astype(np.int64) + 1)
     return out[0], out[1]
@@ -204,7 +242,7 @@ def validate(model, test_data, num_entities, bs, filtering_triples=None):
 
     def side(r):
         return (np.count_nonzero(r <= 1) / n, np.count_nonzero(r <= 3) / n, np.count_nonzero(r <= 10) / n,
-                np.mean(r), np.mean([1 / m for m in r]))
+                np.mean(r), np.mean(1.0 / r))   # == np.mean([1 / m for m in r]) bit for bit (same float64 array, same reduction)
     t1, t3, t10, tmr, tmrr = side(tail_ranks)
     h1, h3, h10, hmr, hmrr = side(head_ranks)
     return {'tail_hits@1': t1, 'tail_hits@3': t3, 'tail_hits@10': t10, 'tail_mr': tmr, 'tail_mrr': tmrr,

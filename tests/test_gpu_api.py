@@ -239,3 +239,23 @@ def test_fit_with_device_side_data_generator():
         after = ku.validate(m, test, ds["N"], 32, filt)
         assert hist.history["loss"][-1] < hist.history["loss"][0]
         assert after["mrr"] > before["mrr"] * 1.5, (device_side, before["mrr"], after["mrr"])
+
+
+@pytest.mark.parametrize("side", ["tail", "head"])
+def test_device_filter_csr_builder_equals_host_builder(side):
+    from KGEkeras import utils as ku
+    rng = np.random.default_rng(12)
+    N, R, F, Q = 300, 5, 4000, 500
+    filt = np.stack([rng.integers(0, N, F), rng.integers(0, R, F), rng.integers(0, N, F)], 1).astype(np.int64)
+    test = np.stack([rng.integers(0, N, Q), rng.integers(0, R, Q), rng.integers(0, N, Q)], 1).astype(np.int64)
+    # remove the test triples themselves from the filter (the reference crashes on them, and so do both builders)
+    key = lambda a: (a[:, 0] * R + a[:, 1]) * N + a[:, 2]
+    filt = filt[~np.isin(key(filt), key(test))]
+    ho, hi = ku.build_filter_csr(test, filt, side)
+    do, di = ku.build_filter_csr_device(torch.from_numpy(test).cuda(), torch.from_numpy(filt).cuda(), side)
+    np.testing.assert_array_equal(do.cpu().numpy(), ho)
+    np.testing.assert_array_equal(di.cpu().numpy(), hi)
+    with pytest.raises(ValueError):
+        ku.build_filter_csr_device(torch.from_numpy(test).cuda(), torch.from_numpy(np.concatenate([filt, test[:1]])).cuda(), side)
+    eo, ei = ku.build_filter_csr_device(torch.from_numpy(test).cuda(), torch.zeros(0, 3, dtype=torch.int64).cuda(), side)
+    assert eo.numel() == Q + 1 and ei.numel() == 0 and int(eo.sum()) == 0
