@@ -216,6 +216,27 @@ KGEB_API int kgeb_rows_gather(kgeb_ctx* ctx, const float* P, int width, int ld, 
 KGEB_API int kgeb_rows_scatter_add(kgeb_ctx* ctx, float* G, int width, int ld, uint8_t* touched, const int32_t* idx, int64_t n,
                           const float* src, kgeb_stream stream);
 
+/* ---- literal branch of EmbeddingModel.call, models.py:114-120,152-158 (the reference harness trains it: tests.py:113,125-126):
+ *      s' = act([Dropout(E[s]) | Dropout(L[s])] W + b) before the score function, one shared Dense for s and o.
+ * The step materialises the transformed rows (per-reference dropout masks make them a function of the reference, not of the
+ * entity) and scores them with the ordinary kernels through identity ids; these five calls are the Dense part. -------------- */
+typedef enum { KGEB_ACT_LINEAR = 0, KGEB_ACT_TANH = 1, KGEB_ACT_RELU = 2, KGEB_ACT_SIGMOID = 3 } kgeb_act;
+/* X[i, :we] = mask * E[ids[i], :we],  X[i, we:we+wl] = mask * L[ids[i], :wl]  (L may be NULL with wl = 0: relation rows).
+ * mask = the Dropout keep/scale armed by kgeb_set_dropout (row index i and column are the counter; stream_id separates calls);
+ * disarmed -> plain gather. */
+KGEB_API int kgeb_rows_concat(kgeb_ctx* ctx, const float* E, int we, int ldE, const float* L, int wl, int ldL, const int32_t* ids,
+                     int64_t n, float* X, int ldX, kgeb_stream stream);
+/* gE[ids[i], :we] += mask * gX[i, :we]; touched[ids[i]] = 1   (same dropout state as the forward call; literals get no gradient) */
+KGEB_API int kgeb_rows_concat_bwd(kgeb_ctx* ctx, const float* gX, int ldX, int we, const int32_t* ids, int64_t n, float* gE, int ldE,
+                         uint8_t* touched, kgeb_stream stream);
+/* C[M,N] = op(A) op(B) (+ C when accumulate != 0), fp32, row-major; op(A) is M x K (transA: A is stored K x M), op(B) is K x N */
+KGEB_API int kgeb_sgemm(kgeb_ctx* ctx, int transA, int transB, int64_t M, int N, int K, const float* A, int lda, const float* B, int ldb,
+               float* C, int ldc, int accumulate, kgeb_stream stream);
+/* Z <- act(Z + bias) in place (Keras Dense activation) */
+KGEB_API int kgeb_dense_act_fwd(kgeb_ctx* ctx, float* Z, int64_t M, int N, int ld, const float* bias, int act, kgeb_stream stream);
+/* gY <- gY * act'(Y) in place, gbias[n] += sum_m gY[m,n] */
+KGEB_API int kgeb_dense_act_bwd(kgeb_ctx* ctx, const float* Y, float* gY, int64_t M, int N, int ld, int act, float* gbias, kgeb_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@ SGD, ADAGRAD, LAZY_ADAM, ADAM_DENSE = range(4)
 CORRUPT_BOTH, CORRUPT_HEAD, CORRUPT_TAIL, CORRUPT_EITHER = range(4)
 SIDE_TAIL, SIDE_HEAD = 0, 1
 TC_BF16, TC_BF16X3_EXACT = 0, 1
+ACT_KINDS = {None: 0, 'linear': 0, 'tanh': 1, 'relu': 2, 'sigmoid': 3}   # Keras activation names served by the literal Dense
 TIMED_RANK_TC, TIMED_RANK_REFINE, TIMED_RANK_TILE, TIMED_TRAIN = range(4)
 
 LOSS_KINDS = {  # reference names, utils.py:321-330
@@ -68,6 +69,11 @@ PROTOTYPES = {
     "kgeb_rank_1n": (_i, [_p, _p, _i64, _i64, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),
     "kgeb_rows_gather": (_i, [_p, _p, _i, _i, _p, _i64, _p, _p]),
     "kgeb_rows_scatter_add": (_i, [_p, _p, _i, _i, _p, _p, _i64, _p, _p]),
+    "kgeb_rows_concat": (_i, [_p, _p, _i, _i, _p, _i, _i, _p, _i64, _p, _i, _p]),
+    "kgeb_rows_concat_bwd": (_i, [_p, _p, _i, _i, _p, _i64, _p, _i, _p, _p]),
+    "kgeb_sgemm": (_i, [_p, _i, _i, _i64, _i, _i, _p, _i, _p, _i, _p, _i, _i, _p]),
+    "kgeb_dense_act_fwd": (_i, [_p, _p, _i64, _i, _i, _p, _i, _p]),
+    "kgeb_dense_act_bwd": (_i, [_p, _p, _p, _i64, _i, _i, _i, _p, _p]),
     "kgeb_rank_tc_packed_bytes": (_i64, [_p, _i64, _i]),
     "kgeb_rank_tc_pack_entities": (_i, [_p, _p, _i64, _i, _p, _i64, _p]),
     "kgeb_rank_tc_workspace_bytes": (_i64, [_p, _i64, _i, _i64]),

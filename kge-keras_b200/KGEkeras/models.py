@@ -36,6 +36,8 @@ class EmbeddingTable:
 
     def set_weights(self, weights):
         (w,) = weights
+        if self._model._head is not None:
+            self._model._head.version += 1   # the cached inference table of a literal model depends on both tables
         if self._which == "E":
             self._model._engine_().set_tables(E=w)
         else:
@@ -113,8 +115,10 @@ class EmbeddingModel:
         self.name = name
         self.entity_embedding = EmbeddingTable(self, "E", num_entities, e_dim, name + '_entity_embedding')
         self.relational_embedding = EmbeddingTable(self, "R", num_relations, r_dim, name + '_relational_embedding')
-        if literal_activation:
-            raise NotImplementedError("the literal branch (models.py:114-120,152-158) is outside the B200 hot path (SURVEY 8f #4)")
+        # literal branch (models.py:114-120): non-trainable literal table + one shared Dense(e_dim, activation)
+        self._literals = literals if literal_activation else None
+        self._literal_activation = literal_activation if literal_activation else None
+        self._head = None
         self.dp = Dropout(dp)
         self.e_dim = e_dim
         self.r_dim = r_dim
@@ -153,6 +157,22 @@ class EmbeddingModel:
             self._init_E = self._init_R = None
         return self._eng
 
+    def _head_(self):
+        """The literal Dense head (None for models without literals)."""
+        if self._literal_activation is None:
+            return None
+        if self._head is None:
+            from ._literal import LiteralHead
+            act = self._literal_activation if isinstance(self._literal_activation, str) else getattr(self._literal_activation, "__name__", None)
+            self._head = LiteralHead(self._engine_(), self._literals, act)
+            self._literals = None
+        return self._head
+
+    def _eval_engine_(self):
+        """The engine inference runs on: the raw tables, or E' = act([E | L] W + b) for models with literals."""
+        head = self._head_()
+        return self._engine_() if head is None else head.effective_engine()
+
     def get_config(self):
         return self.__dict__
 
@@ -160,10 +180,13 @@ class EmbeddingModel:
     def call(self, inputs, training=False):
         """inputs: (batch, 3) ids (int or the harness' float32) -> (batch,) scores as a CUDA torch tensor.
         training=True applies Dropout(dp) to the gathered rows (models.py:144-150) with a fresh mask per call."""
+        head = self._head_()
         if training and self.dp.rate > 0:
             self._call_counter = getattr(self, "_call_counter", 0) + 1
+            if head is not None:
+                return head.score(inputs, dropout=(self.dp.rate, self._seed ^ 0x5EED, 2 ** 41 + self._call_counter))
             return self._engine_().score(inputs, dropout=(self.dp.rate, self._seed ^ 0x5EED, 2 ** 41 + self._call_counter, 0))
-        return self._engine_().score(inputs)
+        return self._eval_engine_().score(inputs)
 
     __call__ = call
 
@@ -181,7 +204,7 @@ class EmbeddingModel:
 
     def predict(self, x, batch_size=32, verbose=0, **kwargs):
         """Keras Model.predict: numpy (n,) scores.  The whole input is scored in one launch (batch_size is accepted)."""
-        return self._engine_().score(x).cpu().numpy()
+        return self._eval_engine_().score(x).cpu().numpy()
 
     # ---- training ----------------------------------------------------------------------------------------------
     def compile(self, optimizer='adam', loss=None, **kwargs):
@@ -213,15 +236,16 @@ class EmbeddingModel:
         pos, neg = self._split_xy(x)
         o = self._opt
         self._step_counter += 1
-        res = self._engine_().train_step(pos, neg, opt_kind=o.kind, lr=o.lr, beta1=o.beta1, beta2=o.beta2, eps=o.eps,
-                                         K=int(self.negative_samples), seed=self._seed, offset=self._step_counter,
-                                         l3=float(self.regularization), dropout=float(self.dp.rate),
-                                         **self._step_kwargs())
+        stepper = self._head_() or self._engine_()
+        res = stepper.train_step(pos, neg, opt_kind=o.kind, lr=o.lr, beta1=o.beta1, beta2=o.beta2, eps=o.eps,
+                                 K=int(self.negative_samples), seed=self._seed, offset=self._step_counter,
+                                 l3=float(self.regularization), dropout=float(self.dp.rate),
+                                 **self._step_kwargs())
         return res["loss"].clone()   # the engine reuses one device scalar for every step's loss
 
     def test_on_batch(self, x, y=None, **kwargs):
         pos, neg = self._split_xy(x)
-        eng = self._engine_()
+        eng = self._eval_engine_()
         kw = self._step_kwargs()
         if neg is None:
             neg = eng.negatives(pos, int(self.negative_samples), self._seed, 2 ** 40 + self._step_counter, kw["corrupt_mode"])
@@ -313,12 +337,19 @@ class EmbeddingModel:
 
     # ---- weights -----------------------------------------------------------------------------------------------
     def get_weights(self):
+        """[entity table, relation table] (+ [Dense kernel, Dense bias] for models with literals)."""
         E, R = self._engine_().get_tables()
-        return [E, R]
+        head = self._head_()
+        return [E, R] if head is None else [E, R] + head.get_weights()
 
     def set_weights(self, weights):
-        E, R = weights
-        self._engine_().set_tables(E, R)
+        self._engine_().set_tables(weights[0], weights[1])
+        head = self._head_()
+        if head is not None:
+            if len(weights) >= 4:
+                head.set_weights(weights[2], weights[3])
+            else:
+                head.version += 1
 
 
 class DistMult(EmbeddingModel):

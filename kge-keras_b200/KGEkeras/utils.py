@@ -203,7 +203,7 @@ def filtered_ranks(model, test_data, filtering_triples, group=None):
     counts are all-reduced (NCCL over NVLink): the result is identical on every rank and for any world size."""
     import torch
     import torch.distributed as dist
-    eng = model._engine_()
+    eng = model._eval_engine_() if hasattr(model, "_eval_engine_") else model._engine_()
     test = np.asarray(test_data, dtype=np.int64).reshape(-1, 3)
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0

@@ -719,6 +719,72 @@ def train_step_dropout(kind, loss_kind, E, R, pos, neg, K, margin, gamma, p, see
     return dict(loss=L, pos_scores=t, neg_scores=f, gE=gE, gR=gR)
 
 
+# --------------------------------------------------------------------------------------------
+# literal branch (models.py:114-120,152-158; trained by the reference harness, tests.py:113,125-126)
+# --------------------------------------------------------------------------------------------
+ACT_LINEAR, ACT_TANH, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
+
+
+def _act(act, z):
+    if act == ACT_TANH:
+        return np.tanh(z)
+    if act == ACT_RELU:
+        return np.maximum(z, 0)
+    if act == ACT_SIGMOID:
+        return 1.0 / (1.0 + np.exp(-z))
+    return z
+
+
+def _act_grad(act, y):
+    if act == ACT_TANH:
+        return 1.0 - y * y
+    if act == ACT_RELU:
+        return (y > 0).astype(y.dtype)
+    if act == ACT_SIGMOID:
+        return y * (1.0 - y)
+    return np.ones_like(y)
+
+
+def literal_table(E, L, W, b, act, dtype=np.float64):
+    """E' = act([E | L] W + b): what every entity row becomes without dropout (inference)."""
+    X = np.concatenate([E.astype(dtype), L.astype(dtype)], axis=1)
+    return _act(act, X @ W.astype(dtype) + b.astype(dtype))
+
+
+def literal_step(kind, loss_kind, pair_mode, E, R, L, W, b, act, pos, neg, K, margin, gamma, p=0.0, seed=0, offset=0, dtype=np.float64):
+    """Forward + gradients of one step of the literal model: s' = act([dp(E[s]) | dp(L[s])] W + b), o' likewise, relation rows
+    dp(R[p]); masks as the kernels draw them (row index of the materialised list and column as the counter; stream 0 = entity
+    rows, the 2m references ordered [all s | all o]; stream 1 = the m relation rows).  Returns loss, scores, gE, gR, gW, gb."""
+    E, R, L, W, b = (np.asarray(a, dtype=dtype) for a in (E, R, L, W, b))
+    tri = np.concatenate([np.asarray(pos), np.asarray(neg)], axis=0).astype(np.int64)
+    m, B = len(tri), len(pos)
+    we, wl, wr = E.shape[1], L.shape[1], R.shape[1]
+    refs = np.concatenate([tri[:, 0], tri[:, 2]])
+    if p:
+        mX = dropout_mult(DISTMULT, we + wl, 2 * m, 0, 0, p, seed, offset, dtype)
+        mP = dropout_mult(DISTMULT, wr, m, 0, 1, p, seed, offset, dtype)
+    else:
+        mX, mP = np.ones((2 * m, we + wl), dtype), np.ones((m, wr), dtype)
+    X = np.concatenate([E[refs], L[refs]], axis=1) * mX
+    Y = _act(act, X @ W + b)
+    P = R[tri[:, 1]] * mP
+    S, O = Y[:m], Y[m:]
+    sc = score(kind, S, P, O, gamma, hole_fft=False)
+    t, f = sc[:B], sc[B:]
+    Lval, dt_, df_ = loss_and_coefs(loss_kind, pair_mode, t, f, K, margin)
+    w = np.concatenate([dt_, df_])[:, None]
+    ds, dp_, do = score_grads(kind, S, P, O, gamma)
+    gY = np.concatenate([w * ds, w * do], axis=0)
+    gZ = gY * _act_grad(act, Y)
+    gb = gZ.sum(0)
+    gW = X.T @ gZ
+    gX = (gZ @ W.T) * mX
+    gE, gR = np.zeros(E.shape, dtype), np.zeros(R.shape, dtype)
+    np.add.at(gE, refs, gX[:, :we])
+    np.add.at(gR, tri[:, 1], w * dp_ * mP)
+    return dict(loss=Lval, pos_scores=t, neg_scores=f, gE=gE, gR=gR, gW=gW, gb=gb)
+
+
 def philox_oversample_indices(n, m, seed, offset, stream_id=0):
     """Indices exactly as kgeb_oversample draws them (device-side oversample_data, utils.py:123-147)."""
     i = np.arange(m, dtype=np.uint64)

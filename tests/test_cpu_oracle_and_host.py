@@ -478,3 +478,41 @@ def test_bench_reference_arm_prints_contract_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+# ---- literal branch (models.py:114-120,152-158) -----------------------------------------------------------------------
+@pytest.mark.parametrize("act,aname", [(ko.ACT_TANH, "tanh"), (ko.ACT_RELU, "relu"), (ko.ACT_SIGMOID, "sigmoid"), (ko.ACT_LINEAR, None)])
+@pytest.mark.parametrize("p", [0.0, 0.3])
+def test_literal_step_matches_torch_restatement(act, aname, p):
+    """call() of a model with literals written in torch op for op like the reference (concat, Dense, activation, func) with
+    the oracle's dropout masks as fixed multipliers, against the oracle's closed-form forward and gradients."""
+    import torch
+    rng = np.random.default_rng(4)
+    N, Rn, we, wl, B, K = 30, 4, 6, 3, 5, 2
+    E, Rm, L = rng.normal(size=(N, we)), rng.normal(size=(Rn, we)), rng.random((N, wl))
+    W, b = rng.normal(size=(we + wl, we)) * 0.5, rng.normal(size=we) * 0.1
+    pos = np.stack([rng.integers(0, N, B), rng.integers(0, Rn, B), rng.integers(0, N, B)], 1)
+    neg = ko.philox_negatives(pos, N, K, 1, 0, ko.CORRUPT_BOTH)
+    got = ko.literal_step(ko.DISTMULT, ko.PAIRWISE_LOGISTIC, ko.PAIRED, E, Rm, L, W, b, act, pos, neg, K, 0.0, 12.0, p=p, seed=9, offset=2)
+    tE, tR, tW, tb = (torch.tensor(a, requires_grad=True) for a in (E, Rm, W, b))
+    tL = torch.tensor(L)
+    tri = np.concatenate([pos, neg]).astype(np.int64)
+    m = len(tri)
+    mX = torch.tensor(ko.dropout_mult(ko.DISTMULT, we + wl, 2 * m, 0, 0, p, 9, 2)) if p else torch.ones(2 * m, we + wl, dtype=torch.float64)
+    mP = torch.tensor(ko.dropout_mult(ko.DISTMULT, we, m, 0, 1, p, 9, 2)) if p else torch.ones(m, we, dtype=torch.float64)
+    refs = torch.tensor(np.concatenate([tri[:, 0], tri[:, 2]]))
+    X = torch.cat([tE[refs], tL[refs]], dim=1) * mX
+    Z = X @ tW + tb
+    Y = {ko.ACT_TANH: torch.tanh, ko.ACT_RELU: torch.relu, ko.ACT_SIGMOID: torch.sigmoid, ko.ACT_LINEAR: lambda z: z}[act](Z)
+    P = tR[torch.tensor(tri[:, 1])] * mP
+    sc = (Y[:m] * P * Y[m:]).sum(-1)
+    t, f = sc[:B], sc[B:]
+    c = torch.tensor(np.float64(np.float32(1 + 1e-6)))
+    Lt = torch.log(c + torch.exp(f.reshape(B, K) - t.reshape(B, 1))).mean()
+    Lt.backward()
+    np.testing.assert_allclose(got["loss"], Lt.item(), rtol=1e-12)
+    for name, g in (("gE", tE.grad), ("gR", tR.grad), ("gW", tW.grad), ("gb", tb.grad)):
+        np.testing.assert_allclose(got[name], g.numpy(), rtol=1e-9, atol=1e-13, err_msg=name)
+    if not p:   # without dropout the transformed row is a function of the entity: the inference table
+        Ep = ko.literal_table(E, L, W, b, act)
+        np.testing.assert_allclose(Ep[tri[:, 0]], Y[:m].detach().numpy(), rtol=1e-12)
