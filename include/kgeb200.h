@@ -232,6 +232,10 @@ KGEB_API int kgeb_rows_concat_bwd(kgeb_ctx* ctx, const float* gX, int ldX, int w
 /* C[M,N] = op(A) op(B) (+ C when accumulate != 0), fp32, row-major; op(A) is M x K (transA: A is stored K x M), op(B) is K x N */
 KGEB_API int kgeb_sgemm(kgeb_ctx* ctx, int transA, int transB, int64_t M, int N, int K, const float* A, int lda, const float* B, int ldb,
                float* C, int ldc, int accumulate, kgeb_stream stream);
+/* Y[rows, width] = act(X[rows, kin] W[kin, width] + bias): the Dense forward (models.py:118,156-157) with the bias and the
+ * activation applied in the GEMM epilogue */
+KGEB_API int kgeb_dense_fwd(kgeb_ctx* ctx, const float* X, int ldx, int64_t rows, int kin, const float* W, int ldw, int width,
+                   const float* bias, int act, float* Y, int ldy, kgeb_stream stream);
 /* Z <- act(Z + bias) in place (Keras Dense activation) */
 KGEB_API int kgeb_dense_act_fwd(kgeb_ctx* ctx, float* Z, int64_t M, int N, int ld, const float* bias, int act, kgeb_stream stream);
 /* gY <- gY * act'(Y) in place, gbias[n] += sum_m gY[m,n] */

@@ -72,6 +72,7 @@ PROTOTYPES = {
     "kgeb_rows_concat": (_i, [_p, _p, _i, _i, _p, _i, _i, _p, _i64, _p, _i, _p]),
     "kgeb_rows_concat_bwd": (_i, [_p, _p, _i, _i, _p, _i64, _p, _i, _p, _p]),
     "kgeb_sgemm": (_i, [_p, _i, _i, _i64, _i, _i, _p, _i, _p, _i, _p, _i, _i, _p]),
+    "kgeb_dense_fwd": (_i, [_p, _p, _i, _i64, _i, _p, _i, _i, _p, _i, _p, _i, _p]),
     "kgeb_dense_act_fwd": (_i, [_p, _p, _i64, _i, _i, _p, _i, _p]),
     "kgeb_dense_act_bwd": (_i, [_p, _p, _p, _i64, _i, _i, _i, _p, _p]),
     "kgeb_rank_tc_packed_bytes": (_i64, [_p, _i64, _i]),

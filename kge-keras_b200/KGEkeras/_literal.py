@@ -59,9 +59,9 @@ class LiteralHead:
         self._chk(self.lib.kgeb_sgemm(self.main.ctx, ta, tb, M, N, K, _ptr(A), lda, _ptr(B), ldb, _ptr(Cm), ldc, acc, _stream()))
 
     def _dense_fwd(self, X, rows, out):
-        """out[:rows, :we] = act(X[:rows] W + b)"""
-        self._gemm(0, 0, rows, self.we, self.kin, X, self.kin, self.W, self.wek, out, self.wek)
-        self._chk(self.lib.kgeb_dense_act_fwd(self.main.ctx, _ptr(out), rows, self.we, self.wek, _ptr(self.b), self.act, _stream()))
+        """out[:rows] = act(X W + b): one GEMM with the bias and activation in its epilogue."""
+        self._chk(self.lib.kgeb_dense_fwd(self.main.ctx, _ptr(X), self.kin, rows, self.kin, _ptr(self.W), self.wek, self.we, _ptr(self.b), self.act,
+                                          _ptr(out), self.wek, _stream()))
 
     def _scratch(self, m):
         if self._tmp is None or self._tmp.R_ < m:
@@ -145,7 +145,7 @@ class LiteralHead:
         # backward through the Dense: gZ = gY * act'(Y);  gb += colsum(gZ);  gW = X^T gZ;  gX = gZ W^T
         self._chk(self.lib.kgeb_dense_act_bwd(mn.ctx, _ptr(tmp.E), _ptr(tmp.gE), 2 * m, self.we, self.wek, self.act, _ptr(self.gb), _stream()))
         self._gemm(1, 0, self.kin, self.we, 2 * m, X, self.kin, tmp.gE, self.wek, self.gW, self.wek, 1)
-        self._gemm(0, 1, 2 * m, self.kin, self.we, tmp.gE, self.wek, self.W, self.wek, gX, self.kin)
+        self._gemm(0, 1, 2 * m, self.we, self.we, tmp.gE, self.wek, self.W, self.wek, gX, self.kin)   # literal columns get no gradient
         arm(0)
         self._concat_bwd(gX, self.kin, self.we, refs, mn.gE, mn.we_k, mn.tE)
         arm(1)

@@ -103,7 +103,7 @@ class DataGenerator:
         self.shuffle = shuffle
         self.engine = engine
         self.seed = int(seed)
-        self.indices = list(range(len(kg)))
+        self.indices = np.arange(len(self.kg), dtype=np.int64)
         self._step = 0
         self.on_epoch_end()
 
@@ -112,7 +112,7 @@ class DataGenerator:
 
     def __getitem__(self, index):
         index = self.index[index * self.batch_size:(index + 1) * self.batch_size]
-        return self._get_data([self.indices[k] for k in index])
+        return self._get_data(self.indices[index])
 
     def on_epoch_end(self):
         self.index = np.arange(len(self.indices))
@@ -120,7 +120,7 @@ class DataGenerator:
             np.random.shuffle(self.index)
 
     def _get_data(self, batch):
-        tmp_kg = self.kg[np.asarray(batch, dtype=np.int64)]
+        tmp_kg = self.kg[batch]
         if self.engine is not None:
             self._step += 1
             return self.engine.device_batch(tmp_kg, self.ns, self.seed, self._step), None

@@ -11,7 +11,7 @@
 #define KGEB_THREADS (KGEB_WARPS_PER_BLOCK * 32)
 #define KGEB_MAX_PARTIAL_BLOCKS 4096
 #define KGEB_TIMED_KERNELS 4
-#define KGEB_SORT_SCRATCH_BYTES (2u << 20)
+#define KGEB_SORT_SCRATCH_BYTES (8u << 20)
 
 struct kgeb_ctx {
   int device;
@@ -26,7 +26,7 @@ struct kgeb_ctx {
   // fixed scratch, allocated once in kgeb_create (nothing allocates afterwards)
   double* d_partials;        // [KGEB_MAX_PARTIAL_BLOCKS * 2] per-block loss partial sums
   unsigned int* d_ticket;    // last-block-done counter (self-resetting)
-  unsigned char* d_sort_scratch;   // [KGEB_SORT_SCRATCH_BYTES] sorted chunks + prefix sums of the all-pairs hinge loss
+  unsigned char* d_sort_scratch;   // [KGEB_SORT_SCRATCH_BYTES] sorted chunks + prefix sums of the all-pairs hinge loss; split-K slices of kgeb_sgemm
   // dropout state (kgeb_set_dropout): thr = round(dp * 65536), 0 = off
   uint32_t dp_thr; float dp_scale; uint64_t dp_seed, dp_offset; int dp_stream;
   // tuning knobs read from the environment ONCE at kgeb_create (KGEB_RING_CTAS, KGEB_RING_D, KGEB_TRAIN_KERNEL=reg):

@@ -15,25 +15,45 @@
 
 namespace {
 
-// keep * scale of element x of materialised row g (plain rows: the same counter layout as dp_keep_elem / the oracle)
-__device__ __forceinline__ float lit_mult(const DropArgs& dp, int stream, uint64_t g, int x) {
-  if (!dp.thr) return 1.f;
-  return dp_keep_elem(dp, 0, stream, g, x) ? dp.scale : 0.f;
+// multipliers of the four elements of 128-bit chunk c of materialised row g: ONE Philox call per chunk (the counter layout of
+// dp_keep_elem: lane = c & 31, call = c >> 6, half = (c >> 5) & 1)
+__device__ __forceinline__ void lit_mult4(const DropArgs& dp, int stream, uint64_t g, int c, float (&mult)[4]) {
+  if (!dp.thr) {
+    mult[0] = mult[1] = mult[2] = mult[3] = 1.f;
+    return;
+  }
+  const int t = c >> 5;
+  const uint4 r = dp_philox(dp, 0, stream, g, c & 31, t >> 1);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) mult[e] = (((dp_word(r, t & 1, e) >> (16 * (e & 1))) & 0xFFFFu) >= dp.thr) ? dp.scale : 0.f;
 }
 
+// a warp per row, a lane per 4-element chunk (one Philox call covers the chunk)
 __global__ void __launch_bounds__(256) k_rows_concat(const float* __restrict__ E, int we, int ldE, const float* __restrict__ L, int wl, int ldL,
                                                      const int32_t* __restrict__ ids, int64_t n, DropArgs dp, int stream, float* __restrict__ X,
                                                      int ldX) {
   const int lane = threadIdx.x & 31;
+  const int W = we + (L ? wl : 0), nchunk = (W + 3) >> 2;
+  const bool vec = ((ldE | ldX | we) & 3) == 0 && !L && ((reinterpret_cast<uintptr_t>(E) | reinterpret_cast<uintptr_t>(X)) & 15) == 0;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t i = warp0; i < n; i += nwarps) {
     const int64_t r = ids[i];
     const float* e = E + r * ldE;
+    const float* l = L ? L + r * ldL : nullptr;
     float* x = X + i * (int64_t)ldX;
-    for (int k = lane; k < we; k += 32) x[k] = __fmul_rn(__ldg(e + k), lit_mult(dp, stream, (uint64_t)i, k));
-    if (L) {
-      const float* l = L + r * ldL;
-      for (int k = lane; k < wl; k += 32) x[we + k] = __fmul_rn(__ldg(l + k), lit_mult(dp, stream, (uint64_t)i, we + k));
+    for (int c = lane; c < nchunk; c += 32) {
+      float mult[4];
+      lit_mult4(dp, stream, (uint64_t)i, c, mult);
+      if (vec) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(e) + c);
+        *(reinterpret_cast<float4*>(x) + c) = make_float4(__fmul_rn(v.x, mult[0]), __fmul_rn(v.y, mult[1]), __fmul_rn(v.z, mult[2]), __fmul_rn(v.w, mult[3]));
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int k = 4 * c + q;
+          if (k < W) x[k] = __fmul_rn(k < we ? __ldg(e + k) : __ldg(l + (k - we)), mult[q]);
+        }
+      }
     }
   }
 }
@@ -41,62 +61,30 @@ __global__ void __launch_bounds__(256) k_rows_concat(const float* __restrict__ E
 __global__ void __launch_bounds__(256) k_rows_concat_bwd(const float* __restrict__ gX, int ldX, int we, const int32_t* __restrict__ ids, int64_t n,
                                                          DropArgs dp, int stream, float* gE, int ldE, uint8_t* touched) {
   const int lane = threadIdx.x & 31;
+  const int nchunk = (we + 3) >> 2;
+  const bool vred = (ldE & 3) == 0 && (reinterpret_cast<uintptr_t>(gE) & 15) == 0;      // 16-byte aligned destination chunks
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t i = warp0; i < n; i += nwarps) {
     const int64_t r = ids[i];
     const float* g = gX + i * (int64_t)ldX;
     float* dst = gE + r * ldE;
     if (lane == 0) touched[r] = 1;
-    for (int k = lane; k < we; k += 32) {
-      const float v = __fmul_rn(g[k], lit_mult(dp, stream, (uint64_t)i, k));
-      if (v != 0.f) atomicAdd(dst + k, v);
-    }
-  }
-}
-
-// C[M,N] = op(A) op(B) (+ C if accumulate); op(A) is M x K, op(B) is K x N.  64 x 64 tile, 16-wide k-steps, 4 x 4 per thread.
-template <bool TA, bool TB>
-__global__ void __launch_bounds__(256) k_sgemm(int64_t M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-                                               float* __restrict__ C, int ldc, int accumulate) {
-  __shared__ float As[16][64 + 4];
-  __shared__ float Bs[16][64 + 4];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int64_t m0 = (int64_t)blockIdx.y * 64;
-  const int n0 = blockIdx.x * 64;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    for (int x = tid; x < 64 * 16; x += 256) {
-      // A tile: element (m, k)
-      const int mm = TA ? x & 63 : x >> 4, kk = TA ? x >> 6 : x & 15;
-      const int64_t m = m0 + mm;
-      const int k = k0 + kk;
-      As[kk][mm] = (m < M && k < K) ? (TA ? A[(int64_t)k * lda + m] : A[m * lda + k]) : 0.f;
-      // B tile: element (k, n)
-      const int nn = TB ? x >> 4 : x & 63, kb = TB ? x & 15 : x >> 6;
-      const int n = n0 + nn, kq = k0 + kb;
-      Bs[kb][nn] = (n < N && kq < K) ? (TB ? B[(int64_t)n * ldb + kq] : B[(int64_t)kq * ldb + n]) : 0.f;
-    }
-    __syncthreads();
+    for (int c = lane; c < nchunk; c += 32) {
+      float mult[4], v[4];
+      lit_mult4(dp, stream, (uint64_t)i, c, mult);
 #pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      float a[4], b[4];
+      for (int q = 0; q < 4; ++q) {
+        const int k = 4 * c + q;
+        v[q] = k < we ? __fmul_rn(g[k], mult[q]) : 0.f;
+      }
+      if (v[0] == 0.f && v[1] == 0.f && v[2] == 0.f && v[3] == 0.f) continue;
+      if (vred && 4 * c + 3 < we) {
+        red_add4(dst + 4 * c, make_float4(v[0], v[1], v[2], v[3]));
+      } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t m = m0 + ty * 4 + i;
-    if (m >= M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (n < N) C[m * ldc + n] = accumulate ? C[m * ldc + n] + acc[i][j] : acc[i][j];
+        for (int q = 0; q < 4; ++q)
+          if (v[q] != 0.f) atomicAdd(dst + 4 * c + q, v[q]);
+      }
     }
   }
 }
@@ -112,6 +100,112 @@ __device__ __forceinline__ float act_bwd(int act, float y) {   // derivative exp
   if (act == KGEB_ACT_RELU) return y > 0.f ? 1.f : 0.f;
   if (act == KGEB_ACT_SIGMOID) return y * (1.f - y);
   return 1.f;
+}
+
+// C[M,N] = op(A) op(B) (+ C if accumulate); op(A) is M x K, op(B) is K x N.  128 x 64 tile, 16-wide k-steps, 8 x 4 per thread
+// (32 FFMA per 3 LDS.128); the next k-step's global loads are issued into registers before the current one is multiplied, so
+// the L2 latency hides behind the 512 FFMAs a thread spends per step.
+// Split-K (gridDim.z > 1, the weight gradient X^T gY whose K is the batch): slice z covers k in [z * kchunk, (z+1) * kchunk) and
+// writes its partial tile to part[z][M][N]; k_splitk_reduce adds the slices in slice order, so the result does not depend on scheduling.
+constexpr int GM = 128, GN = 64, GK = 16;
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) k_sgemm(int64_t M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                               float* __restrict__ C, int ldc, int accumulate, int kchunk, float* __restrict__ part, const float* __restrict__ bias,
+                                               int act) {
+  __shared__ __align__(16) float As[GK][GM + 4];
+  __shared__ __align__(16) float Bs[GK][GN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.y * GM;
+  const int n0 = blockIdx.x * GN;
+  const int kbeg = blockIdx.z * kchunk;
+  if (gridDim.z > 1) {
+    K = min(K, kbeg + kchunk);
+    C = part + (int64_t)blockIdx.z * M * N;
+    ldc = N;
+    accumulate = 0;
+  }
+  // element x of a tile: the fastest-varying index follows the operand's contiguous axis so that a warp reads whole segments
+  float pa[GM * GK / 256], pb[GN * GK / 256];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < GM * GK / 256; ++j) {
+      const int x = tid + j * 256;
+      const int mm = TA ? x & (GM - 1) : x >> 4, kk = TA ? x / GM : x & 15;
+      const int64_t m = m0 + mm;
+      const int k = k0 + kk;
+      pa[j] = (m < M && k < K) ? (TA ? __ldg(A + (int64_t)k * lda + m) : __ldg(A + m * lda + k)) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < GN * GK / 256; ++j) {
+      const int x = tid + j * 256;
+      const int nn = TB ? x >> 4 : x & (GN - 1), kk = TB ? x & 15 : x / GN;
+      const int n = n0 + nn, k = k0 + kk;
+      pb[j] = (n < N && k < K) ? (TB ? __ldg(B + (int64_t)n * ldb + k) : __ldg(B + (int64_t)k * ldb + n)) : 0.f;
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int j = 0; j < GM * GK / 256; ++j) {
+      const int x = tid + j * 256;
+      As[TA ? x / GM : x & 15][TA ? x & (GM - 1) : x >> 4] = pa[j];
+    }
+#pragma unroll
+    for (int j = 0; j < GN * GK / 256; ++j) {
+      const int x = tid + j * 256;
+      Bs[TB ? x & 15 : x / GN][TB ? x >> 4 : x & (GN - 1)] = pb[j];
+    }
+  };
+  float acc[8][4] = {};
+  if (kbeg < K) fetch(kbeg);
+  for (int k0 = kbeg; k0 < K; k0 += GK) {
+    stash();
+    __syncthreads();
+    if (k0 + GK < K) fetch(k0 + GK);
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + ty * 8 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = accumulate ? C[m * ldc + n] + acc[i][j] : acc[i][j];
+      if (bias) v = act_fwd(act, v + __ldg(bias + n));      // fused Dense epilogue (never with split-K)
+      C[m * ldc + n] = v;
+    }
+  }
+}
+
+__global__ void k_splitk_reduce(const float* __restrict__ part, int splits, int64_t MN, int N, float* __restrict__ C, int ldc, int accumulate) {
+  for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < MN; x += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    int z = 0;
+    for (; z + 8 <= splits; z += 8) {          // eight loads in flight, added in slice order
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = part[(int64_t)(z + u) * MN + x];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; z < splits; ++z) s += part[(int64_t)z * MN + x];
+    const int64_t m = x / N;
+    float* dst = C + m * ldc + (x - m * N);
+    *dst = accumulate ? *dst + s : s;
+  }
 }
 
 __global__ void k_dense_act_fwd(float* Z, int64_t M, int N, int ld, const float* __restrict__ bias, int act) {
@@ -130,7 +224,20 @@ __global__ void __launch_bounds__(256) k_dense_act_bwd(const float* __restrict__
   const int n = blockIdx.x * 32 + lane;
   float s = 0.f;
   if (n < N) {
-    for (int64_t m = (int64_t)blockIdx.y * 8 + w; m < M; m += (int64_t)gridDim.y * 8) {
+    const int64_t step = (int64_t)gridDim.y * 8;
+    int64_t m = (int64_t)blockIdx.y * 8 + w;
+    for (; m + 3 * step < M; m += 4 * step) {     // four rows in flight per warp: the loop is latency-bound otherwise
+      float g[4], y[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { g[u] = gY[(m + u * step) * ld + n]; y[u] = Y[(m + u * step) * ld + n]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        g[u] *= act_bwd(act, y[u]);
+        gY[(m + u * step) * ld + n] = g[u];
+        s += g[u];
+      }
+    }
+    for (; m < M; m += step) {
       const float g = gY[m * ld + n] * act_bwd(act, Y[m * ld + n]);
       gY[m * ld + n] = g;
       s += g;
@@ -184,21 +291,55 @@ extern "C" int kgeb_rows_concat_bwd(kgeb_ctx* ctx, const float* gX, int ldX, int
   return KGEB_OK;
 }
 
+static int launch_sgemm(kgeb_ctx* ctx, int transA, int transB, int64_t M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+                        int ldc, int accumulate, const float* bias, int act, cudaStream_t st) {
+  dim3 grid((unsigned)((N + GN - 1) / GN), (unsigned)((M + GM - 1) / GM));
+  // few output tiles and a long K: slice K so that about two waves of CTAs are in flight (the slices fit the context scratch)
+  const int64_t tiles = (int64_t)grid.x * grid.y;
+  int splits = 1, kchunk = K;
+  if (!bias && tiles < ctx->num_sms && K >= 1024) {
+    int64_t want = (2 * (int64_t)ctx->num_sms + tiles - 1) / tiles;
+    const int64_t fit = (int64_t)KGEB_SORT_SCRATCH_BYTES / (M * N * (int64_t)sizeof(float));
+    if (want > fit) want = fit;
+    if (want > (K + 255) / 256) want = (K + 255) / 256;
+    if (want > 1) {
+      kchunk = (int)(((K + want - 1) / want + 15) / 16 * 16);
+      splits = (K + kchunk - 1) / kchunk;
+    }
+  }
+  grid.z = (unsigned)splits;
+  float* part = reinterpret_cast<float*>(ctx->d_sort_scratch);
+  if (transA && transB) k_sgemm<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, accumulate, kchunk, part, bias, act);
+  else if (transA) k_sgemm<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, accumulate, kchunk, part, bias, act);
+  else if (transB) k_sgemm<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, accumulate, kchunk, part, bias, act);
+  else k_sgemm<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, accumulate, kchunk, part, bias, act);
+  if (splits > 1) {
+    const int64_t MN = M * N;
+    k_splitk_reduce<<<(int)((MN + 63) / 64 < 2048 ? (MN + 63) / 64 : 2048), 64, 0, st>>>(part, splits, MN, N, C, ldc, accumulate);
+  }
+  KGEB_LAUNCH_OK(ctx);
+  return KGEB_OK;
+}
+
 extern "C" int kgeb_sgemm(kgeb_ctx* ctx, int transA, int transB, int64_t M, int N, int K, const float* A, int lda, const float* B, int ldb,
                           float* C, int ldc, int accumulate, kgeb_stream stream) {
   if (!ctx) return KGEB_ERR_INVALID;
   KGEB_REQUIRE(ctx, M >= 0 && N > 0 && K > 0 && ldc >= N, KGEB_ERR_INVALID, "sgemm: bad shape");
   if (M == 0) return KGEB_OK;
   KGEB_REQUIRE(ctx, A && B && C, KGEB_ERR_INVALID, "sgemm: null pointer");
-  KGEB_REQUIRE(ctx, (M + 63) / 64 <= 65535, KGEB_ERR_UNSUPPORTED, "sgemm: too many row tiles");
-  dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64));
-  cudaStream_t st = (cudaStream_t)stream;
-  if (transA && transB) k_sgemm<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, accumulate);
-  else if (transA) k_sgemm<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, accumulate);
-  else if (transB) k_sgemm<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, accumulate);
-  else k_sgemm<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, accumulate);
-  KGEB_LAUNCH_OK(ctx);
-  return KGEB_OK;
+  KGEB_REQUIRE(ctx, (M + GM - 1) / GM <= 65535, KGEB_ERR_UNSUPPORTED, "sgemm: too many row tiles");
+  return launch_sgemm(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, accumulate, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int kgeb_dense_fwd(kgeb_ctx* ctx, const float* X, int ldx, int64_t rows, int kin, const float* W, int ldw, int width, const float* bias,
+                              int act, float* Y, int ldy, kgeb_stream stream) {
+  if (!ctx) return KGEB_ERR_INVALID;
+  KGEB_REQUIRE(ctx, rows >= 0 && kin > 0 && width > 0 && ldx >= kin && ldw >= width && ldy >= width && act >= KGEB_ACT_LINEAR && act <= KGEB_ACT_SIGMOID,
+               KGEB_ERR_INVALID, "dense_fwd: bad arguments");
+  if (rows == 0) return KGEB_OK;
+  KGEB_REQUIRE(ctx, X && W && bias && Y, KGEB_ERR_INVALID, "dense_fwd: null pointer");
+  KGEB_REQUIRE(ctx, (rows + GM - 1) / GM <= 65535, KGEB_ERR_UNSUPPORTED, "dense_fwd: too many row tiles");
+  return launch_sgemm(ctx, 0, 0, rows, width, kin, X, ldx, W, ldw, Y, ldy, 0, bias, act, (cudaStream_t)stream);
 }
 
 extern "C" int kgeb_dense_act_fwd(kgeb_ctx* ctx, float* Z, int64_t M, int N, int ld, const float* bias, int act, kgeb_stream stream) {
@@ -218,8 +359,10 @@ extern "C" int kgeb_dense_act_bwd(kgeb_ctx* ctx, const float* Y, float* gY, int6
   KGEB_REQUIRE(ctx, M >= 0 && N > 0 && ld >= N && act >= KGEB_ACT_LINEAR && act <= KGEB_ACT_SIGMOID, KGEB_ERR_INVALID, "dense_act_bwd: bad arguments");
   if (M == 0) return KGEB_OK;
   KGEB_REQUIRE(ctx, Y && gY && gbias, KGEB_ERR_INVALID, "dense_act_bwd: null pointer");
-  int64_t rows = (M + 7) / 8;
-  if (rows > 64) rows = 64;
+  const int64_t slabs = (N + 31) / 32;
+  int64_t rows = (M + 31) / 32, cap = ((int64_t)ctx->num_sms * 8 + slabs - 1) / slabs;
+  if (rows > cap) rows = cap;
+  if (rows > 65535) rows = 65535;
   k_dense_act_bwd<<<dim3((unsigned)((N + 31) / 32), (unsigned)rows), 256, 0, (cudaStream_t)stream>>>(Y, gY, M, N, ld, act, gbias);
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;

@@ -45,6 +45,28 @@ def test_sgemm_all_transposes():
                 np.testing.assert_allclose(c[:, :N].cpu().numpy(), 2 * want, rtol=1e-5, atol=2e-5)
 
 
+@pytest.mark.parametrize("M,N,K", [(105, 100, 40960), (5, 3, 1031), (64, 64, 100000), (130, 7, 5000)])
+def test_sgemm_split_k(M, N, K):
+    """The weight gradient X^T gY has a short M, N and the batch as K: the K axis is sliced across CTAs and the slices are added
+    in slice order, so two runs agree bit for bit (no atomics) and the value matches fp64 to fp32 accumulation error."""
+    eng, head, *_ = make(ko.DISTMULT, 10, 3, 8, 2, "tanh")
+    rng = np.random.default_rng(M + K)
+    A, B = rng.normal(size=(K, M)).astype(np.float32), rng.normal(size=(K, N)).astype(np.float32)
+    want = A.astype(np.float64).T @ B.astype(np.float64)
+    a, b = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    c = torch.full((M, N + 1), 3.0, device="cuda")
+    head._gemm(1, 0, M, N, K, a, M, b, N, c, N + 1, 0)
+    first = c.clone()
+    tol = 4e-7 * np.sqrt(K) * 8
+    np.testing.assert_allclose(c[:, :N].cpu().numpy(), want, rtol=1e-5, atol=tol * np.abs(want).max())
+    assert float(c[:, N:].min()) == 3.0
+    c.fill_(3.0)
+    head._gemm(1, 0, M, N, K, a, M, b, N, c, N + 1, 0)
+    assert torch.equal(c, first)
+    head._gemm(1, 0, M, N, K, a, M, b, N, c, N + 1, 1)
+    np.testing.assert_allclose(c[:, :N].cpu().numpy(), 2 * want, rtol=1e-5, atol=2 * tol * np.abs(want).max())
+
+
 @pytest.mark.parametrize("kind", [ko.DISTMULT, ko.TRANSE_L1, ko.COMPLEX])
 @pytest.mark.parametrize("aname", list(ACTS))
 @pytest.mark.parametrize("p", [0.0, 0.25])
