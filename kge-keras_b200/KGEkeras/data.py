@@ -105,19 +105,29 @@ class DataGenerator:
         self.seed = int(seed)
         self.indices = np.arange(len(self.kg), dtype=np.int64)
         self._step = 0
+        self._kg_dev = self._index_dev = None
+        if engine is not None and len(self.kg):
+            from ._engine import as_idx
+            self._kg_dev = as_idx(self.kg, engine.device)      # the split lives on the GPU: a batch is a device gather
         self.on_epoch_end()
 
     def __len__(self):
         return len(self.kg) // self.batch_size
 
     def __getitem__(self, index):
-        index = self.index[index * self.batch_size:(index + 1) * self.batch_size]
-        return self._get_data(self.indices[index])
+        lo, hi = index * self.batch_size, (index + 1) * self.batch_size
+        if self._kg_dev is not None:
+            self._step += 1
+            return self.engine.device_batch(self._kg_dev.index_select(0, self._index_dev[lo:hi]), self.ns, self.seed, self._step), None
+        return self._get_data(self.indices[self.index[lo:hi]])
 
     def on_epoch_end(self):
         self.index = np.arange(len(self.indices))
         if self.shuffle:
             np.random.shuffle(self.index)
+        if self._kg_dev is not None:
+            import torch
+            self._index_dev = torch.from_numpy(self.index).to(self._kg_dev.device)   # one upload per epoch
 
     def _get_data(self, batch):
         tmp_kg = self.kg[batch]

@@ -170,23 +170,43 @@ __global__ void __launch_bounds__(256) k_allpairs_hinge_sorted(const float* __re
   if (i < n_own) {
     const float mine = __ldg((f_side ? f : t) + i);
     const float* oth = f_side ? ts : fs;
-    for (int c = 0; c < nch; ++c) {
-      const float* ch = oth + (int64_t)c * SC;
-      const int len = (int)(n_oth - (int64_t)c * SC < SC ? n_oth - (int64_t)c * SC : SC);
+    // G chunks are searched in lockstep: their loads are independent, so a thread keeps G of them in flight instead of
+    // walking 10 dependent L2 round trips per chunk (the grid is a fraction of a wave: this kernel is pure latency)
+    constexpr int G = 8;
+    for (int c0 = 0; c0 < nch; c0 += G) {
+      int lo[G], hi[G], len[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int64_t left = n_oth - (int64_t)(c0 + g) * SC;
+        len[g] = (c0 + g < nch) ? (int)(left < SC ? left : SC) : 0;
+        lo[g] = 0;
+        hi[g] = len[g];
+      }
       // f side: pred(f_i, t) holds for the SMALLEST t's -> count = first index where it fails
       // t side: pred(f, t_j) holds for the LARGEST f's  -> count = len - first index where it holds
-      int lo = 0, hi = len;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        const float o = __ldg(ch + mid);
-        const bool pr = f_side ? (__fadd_rn(margin, __fsub_rn(mine, o)) > 0.f) : (__fadd_rn(margin, __fsub_rn(o, mine)) > 0.f);
-        if (f_side ? pr : !pr) lo = mid + 1; else hi = mid;
+#pragma unroll 1
+      for (int it = 0; it < 11; ++it) {           // ceil(log2(SC + 1)) halvings finish every chunk
+        float o[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) o[g] = lo[g] < hi[g] ? __ldg(oth + (int64_t)(c0 + g) * SC + ((lo[g] + hi[g]) >> 1)) : 0.f;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (lo[g] < hi[g]) {
+            const int mid = (lo[g] + hi[g]) >> 1;
+            const bool pr = f_side ? (__fadd_rn(margin, __fsub_rn(mine, o[g])) > 0.f) : (__fadd_rn(margin, __fsub_rn(o[g], mine)) > 0.f);
+            if (f_side ? pr : !pr) lo[g] = mid + 1; else hi[g] = mid;
+          }
+        }
       }
-      if (f_side) {
-        cnt += lo;
-        accL += (double)lo * ((double)margin + (double)mine) - tp[(int64_t)c * (SC + 1) + lo];
-      } else {
-        cnt += len - lo;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (c0 + g >= nch) continue;
+        if (f_side) {
+          cnt += lo[g];
+          accL += (double)lo[g] * ((double)margin + (double)mine) - tp[(int64_t)(c0 + g) * (SC + 1) + lo[g]];
+        } else {
+          cnt += len[g] - lo[g];
+        }
       }
     }
     const float sc = (float)((double)w / ((double)B * (double)Bf));
@@ -341,7 +361,7 @@ extern "C" int kgeb_loss_fwd_bwd(kgeb_ctx* ctx, const float* t, int64_t B, const
       k_chunk_sort<<<(unsigned)(tch + fch), SC / 2, 0, st>>>(t, B, f, Bf, (int)tch, ts, fs, tp);
       KGEB_LAUNCH_OK(ctx);
       const int64_t nmax = B > Bf ? B : Bf;
-      k_allpairs_hinge_sorted<<<dim3((unsigned)((nmax + 255) / 256), 2), 256, 0, st>>>(t, B, f, Bf, ts, fs, tp, margin, loss_weight, dt, df, loss_acc);
+      k_allpairs_hinge_sorted<<<dim3((unsigned)((nmax + 63) / 64), 2), 64, 0, st>>>(t, B, f, Bf, ts, fs, tp, margin, loss_weight, dt, df, loss_acc);
       KGEB_LAUNCH_OK(ctx);
       k_loss_allpairs_finish<<<1, 1, 0, st>>>(loss_acc, (double)loss_weight / ((double)B * (double)Bf), loss);
       KGEB_LAUNCH_OK(ctx);
