@@ -55,7 +55,8 @@ typedef enum {
  * train kernel serves the first four kinds. */
 typedef enum {
   KGEB_DISTMULT = 0, KGEB_TRANSE_L1 = 1, KGEB_TRANSE_L2 = 2, KGEB_COMPLEX = 3, KGEB_HOLE = 4,
-  KGEB_ROTATE = 5, KGEB_PROTATE = 6, KGEB_MODE_L1 = 7, KGEB_MODE_L2 = 8
+  KGEB_ROTATE = 5, KGEB_PROTATE = 6, KGEB_MODE_L1 = 7, KGEB_MODE_L2 = 8,
+  KGEB_HAKE = 9 /* models.py:383-400; score_fwd / score_bwd only, see kgeb_set_hake_params */
 } kgeb_score_kind;
 
 /* losses utils.py:288-319.  POINTWISE_BCE = pointwize_cross_entropy (utils.py:297-298): Keras binary_crossentropy on the raw
@@ -104,6 +105,14 @@ KGEB_API int kgeb_last_kernel_ms(kgeb_ctx* ctx, int which, float* ms);
 /* Scalar parameter of the score function besides gamma: pRotatE's modulus (models.py:476, modulus*embedding_range).
  * Default 1; ignored by the other kinds. */
 KGEB_API int kgeb_set_score_param(kgeb_ctx* ctx, float param);
+
+/* HAKE (models.py:362-400): entity rows [phase | modulus] (we = 2d), relation rows [phase | modulus | bias] (wr = 3d).
+ * phase_scale = pi / embedding_range, embedding_range = (gamma + epsilon) / we / 2 (models.py:381, we already doubled);
+ * phase_weight, mod_weight: models.py:377-378.  The modulus term is ONE Frobenius norm over all m rows of a kgeb_score_fwd
+ * call (tf.norm without axis, models.py:397): scores and gradients of a call are coupled, exactly as in the reference's
+ * func(); kgeb_score_bwd therefore expects the same idx (and dropout state) as the forward call it differentiates.
+ * No fused training kernel and no 1-N ranking (a candidate's score would depend on its batch).  m <= 2 M rows per call. */
+KGEB_API int kgeb_set_hake_params(kgeb_ctx* ctx, float phase_scale, float phase_weight, float mod_weight);
 
 /* ---- dropout, models.py:122,144-150: Dropout(dp) on each gathered s / p / o row while training ----------------------
  * p > 0 arms it for the following score_fwd / score_bwd / train_fwd_bwd calls of this context (p = 0 disarms: predict,

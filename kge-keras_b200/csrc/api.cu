@@ -15,7 +15,7 @@ extern "C" int kgeb_create(kgeb_ctx** out, int device, int64_t num_entities, int
     return kgeb_fail(nullptr, KGEB_ERR_INVALID, "%s", "kgeb_create: bad table shape");
   if (num_entities > 0x7fffffffLL || num_relations > 0x7fffffffLL)
     return kgeb_fail(nullptr, KGEB_ERR_INVALID, "%s", "kgeb_create: ids are int32");
-  if (score_kind < KGEB_DISTMULT || score_kind > KGEB_MODE_L2)
+  if (score_kind < KGEB_DISTMULT || score_kind > KGEB_HAKE)
     return kgeb_fail(nullptr, KGEB_ERR_INVALID, "%s", "kgeb_create: unknown score kind");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -87,6 +87,14 @@ extern "C" int kgeb_last_kernel_ms(kgeb_ctx* ctx, int which, float* ms) {
   KGEB_REQUIRE(ctx, ctx->ev_valid[which], KGEB_ERR_INVALID, "kernel timing: that kernel has not been launched with timing on");
   KGEB_CUDA_OK(ctx, cudaEventSynchronize(ctx->ev[which][1]));
   KGEB_CUDA_OK(ctx, cudaEventElapsedTime(ms, ctx->ev[which][0], ctx->ev[which][1]));
+  return KGEB_OK;
+}
+
+extern "C" int kgeb_set_hake_params(kgeb_ctx* ctx, float phase_scale, float phase_weight, float mod_weight) {
+  if (!ctx) return KGEB_ERR_INVALID;
+  KGEB_REQUIRE(ctx, ctx->kind == KGEB_HAKE, KGEB_ERR_INVALID, "set_hake_params: the context is not a HAKE context");
+  KGEB_REQUIRE(ctx, phase_scale > 0.f, KGEB_ERR_INVALID, "set_hake_params: phase_scale = pi / embedding_range must be positive");
+  ctx->hake_ps = phase_scale; ctx->hake_pw = phase_weight; ctx->hake_mw = mod_weight;
   return KGEB_OK;
 }
 

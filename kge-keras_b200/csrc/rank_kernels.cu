@@ -412,6 +412,8 @@ extern "C" int kgeb_query_prep(kgeb_ctx* ctx, const float* E_shard, int64_t row_
   KGEB_REQUIRE(ctx, E_shard && R && triples && qvec && Q >= 0 && n_rows >= 0 && row_offset >= 0, KGEB_ERR_INVALID,
                "query_prep: bad arguments");
   KGEB_REQUIRE(ctx, side == KGEB_SIDE_TAIL || side == KGEB_SIDE_HEAD, KGEB_ERR_INVALID, "unknown side");
+  KGEB_REQUIRE(ctx, ctx->kind != KGEB_HAKE, KGEB_ERR_UNSUPPORTED,
+               "HAKE has no 1-N ranking: its modulus term is one norm over the scoring call (models.py:397), so a candidate's score depends on its batch");
   KGEB_REQUIRE(ctx, ctx->kind == KGEB_ROTATE ? ctx->we == 2 * ctx->wr : ctx->we == ctx->wr, KGEB_ERR_UNSUPPORTED,
                "1-N ranking needs e_dim == r_dim (RotatE: e_dim == 2 * r_dim)");
   if (Q == 0) return KGEB_OK;

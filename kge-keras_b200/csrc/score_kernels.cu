@@ -269,6 +269,7 @@ extern "C" int kgeb_score_fwd(kgeb_ctx* ctx, const float* E, const float* R, con
   KGEB_REQUIRE(ctx, m >= 0, KGEB_ERR_INVALID, "score_fwd: negative batch");
   if (m == 0) return KGEB_OK;  /* empty batch: nothing to read, pointers may be null */
   KGEB_REQUIRE(ctx, idx && scores, KGEB_ERR_INVALID, "score_fwd: bad arguments");
+  if (ctx->kind == KGEB_HAKE) return kgeb_internal_hake_fwd(ctx, E, R, idx, m, scores, (cudaStream_t)stream);
   if (int rc = check_tables(ctx, E, R)) return rc;
   if (m == 0) return KGEB_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -300,6 +301,7 @@ extern "C" int kgeb_score_bwd(kgeb_ctx* ctx, const float* E, const float* R, con
   KGEB_REQUIRE(ctx, m >= 0, KGEB_ERR_INVALID, "score_bwd: negative batch");
   if (m == 0) return KGEB_OK;
   KGEB_REQUIRE(ctx, idx && dscore && gE && gR && touchedE && touchedR, KGEB_ERR_INVALID, "score_bwd: bad arguments");
+  if (ctx->kind == KGEB_HAKE) return kgeb_internal_hake_bwd(ctx, E, R, idx, m, dscore, gE, gR, touchedE, touchedR, (cudaStream_t)stream);
   if (int rc = check_tables(ctx, E, R)) return rc;
   KGEB_REQUIRE(ctx, ctx->kind == KGEB_HOLE || (kgeb_aligned16(gE) && kgeb_aligned16(gR)), KGEB_ERR_ALIGNMENT,
                "gradient buffers must be 16-byte aligned");

@@ -20,6 +20,10 @@ ROTATE, PROTATE, MODE_L1, MODE_L2 = 5, 6, 7, 8
 SCORE_KINDS = {"DistMult": DISTMULT, "TransE_L1": TRANSE_L1, "TransE_L2": TRANSE_L2,
                "ComplEx": COMPLEX, "HolE": HOLE}
 SIBLING_KINDS = {"RotatE": ROTATE, "pRotatE": PROTATE, "ModE_L1": MODE_L1, "ModE_L2": MODE_L2}
+# HAKE (models.py:362-400): entity rows [phase | modulus] (2d), relation rows [phase | modulus | bias] (3d).  Its modulus term is
+# ONE Frobenius norm over the whole call (tf.norm without axis, models.py:397), so the scores of a call are coupled: they are
+# restated by hake_scores / hake_row_grads below, not by the per-triple score / score_grads
+HAKE = 9
 
 # loss kinds -- shared with kgeb_loss_kind
 POINTWISE_HINGE, POINTWISE_LOGISTIC, POINTWISE_SQUARE, PAIRWISE_HINGE, PAIRWISE_LOGISTIC, PAIRWISE_SQUARE, POINTWISE_BCE = range(7)
@@ -794,3 +798,80 @@ def philox_oversample_indices(n, m, seed, offset, stream_id=0):
                     np.full(m, ((int(seed) >> 32) & 0xFFFFFFFF) ^ int(stream_id), np.uint32)], axis=-1)
     r = philox4x32_10(ctr, key)
     return ((r[:, 0].astype(np.uint64) * np.uint64(n)) >> np.uint64(32)).astype(np.int64)
+
+
+# --------------------------------------------------------------------------------------------
+# HAKE (models.py:362-400) -- batch-coupled score, restated as written
+# --------------------------------------------------------------------------------------------
+def hake_params(gamma=12.0, epsilon=2.0, e_dim_stored=None, phase_weight=0.5, mod_weight=1.0):
+    """(phase_scale, phase_weight, mod_weight): phase_scale = pi / embedding_range with embedding_range =
+    (gamma + epsilon) / e_dim / 2 and e_dim the STORED entity width 2d (models.py:371,381: e_dim is doubled before super().__init__)."""
+    rng_ = (float(gamma) + float(epsilon)) / float(e_dim_stored) / 2.0
+    return (float(np.pi / rng_), float(phase_weight), float(mod_weight))
+
+
+def _hake_parts(s, p, o, phase_scale):
+    d = s.shape[-1] // 2
+    assert p.shape[-1] == 3 * d and o.shape[-1] == 2 * d
+    a = (s[..., :d] * phase_scale + p[..., :d] * phase_scale - o[..., :d] * phase_scale) / 2     # models.py:390-392,398
+    ms, mo = s[..., d:], o[..., d:]
+    mp, beta = p[..., d:2 * d], p[..., 2 * d:]
+    b1 = np.minimum(beta, 1.0)                                     # K.clip(bias, -inf, 1), models.py:394
+    cond = b1 < -np.abs(mp)                                        # tf.where(bias < -|mod_p|, -|mod_p|, bias), models.py:395
+    b = np.where(cond, -np.abs(mp), b1)
+    u = ms * (mp + b) - np.abs(mo) * (1 - b)                       # models.py:397
+    return d, a, ms, mo, mp, beta, b, cond, u
+
+
+def hake_scores(s, p, o, gamma, phase_scale, phase_weight, mod_weight):
+    """gamma - (phase_weight * sum_k |sin a_k|  +  mod_weight * ||U||_F): the modulus norm runs over EVERY row of the call."""
+    _, a, *_, u = _hake_parts(s, p, o, phase_scale)
+    r = mod_weight * np.sqrt(np.sum(u * u))
+    return gamma - (phase_weight * np.sum(np.abs(np.sin(a)), axis=-1) + r)
+
+
+def hake_row_grads(s, p, o, dscore, gamma, phase_scale, phase_weight, mod_weight):
+    """d(sum_i dscore_i * score_i) / d(s, p, o rows) with TensorFlow's conventions: d|x| = sign(x) (0 at 0), the clip passes the
+    gradient where bias <= 1, the where() routes it to -|mod_p| or to the bias.  A zero modulus norm contributes no gradient
+    (TensorFlow would produce NaN there)."""
+    d, a, ms, mo, mp, beta, b, cond, u = _hake_parts(s, p, o, phase_scale)
+    c = np.asarray(dscore, dtype=s.dtype)[:, None]
+    T = np.sum(u * u)
+    dphi = -phase_weight * c * np.sign(np.sin(a)) * np.cos(a) * 0.5 * phase_scale
+    gu = (-(np.sum(c) * mod_weight) / np.sqrt(T)) * u if T > 0 else np.zeros_like(u)
+    db = gu * (ms + np.abs(mo))
+    g_ms = gu * (mp + b)
+    g_mo = gu * (-np.sign(mo) * (1 - b))
+    g_mp = gu * ms + np.where(cond, db * (-np.sign(mp)), 0.0)
+    g_beta = np.where(cond, 0.0, np.where(beta <= 1.0, db, 0.0))
+    return (np.concatenate([dphi, g_ms], axis=-1), np.concatenate([dphi, g_mp, g_beta], axis=-1), np.concatenate([-dphi, g_mo], axis=-1))
+
+
+def hake_step(loss_kind, pair_mode, E, R, pos, neg, K, margin, gamma, hp, p=0.0, seed=0, offset=0, dtype=np.float64):
+    """One training step's forward + dense gradients: the positive and the negative call are two separate func() calls
+    (models.py:144-150), each with its own modulus norm and, with p > 0, its own dropout masks (plain-row counter layout)."""
+    E, R = E.astype(dtype), R.astype(dtype)
+    calls = []
+    for stream, idx in ((0, np.asarray(pos)), (1, np.asarray(neg))):
+        s, pr, o = gather(E, R, idx)
+        if p > 0:
+            ms_ = dropout_mult(HAKE, E.shape[1], len(idx), 0, stream, p, seed, offset, dtype)
+            mp_ = dropout_mult(HAKE, R.shape[1], len(idx), 1, stream, p, seed, offset, dtype)
+            mo_ = dropout_mult(HAKE, E.shape[1], len(idx), 2, stream, p, seed, offset, dtype)
+        else:
+            ms_ = mp_ = mo_ = None
+        rows = (s, pr, o) if ms_ is None else (s * ms_, pr * mp_, o * mo_)
+        calls.append((idx, rows, (ms_, mp_, mo_)))
+    t = hake_scores(*calls[0][1], gamma, *hp)
+    f = hake_scores(*calls[1][1], gamma, *hp)
+    L, dt_, df_ = loss_and_coefs(loss_kind, pair_mode, t, f, K, margin)
+    gE, gR = np.zeros(E.shape, dtype), np.zeros(R.shape, dtype)
+    for (idx, rows, mults), dsc in zip(calls, (dt_, df_)):
+        ds, dp_, do = hake_row_grads(*rows, dsc, gamma, *hp)
+        if mults[0] is not None:
+            ds, dp_, do = ds * mults[0], dp_ * mults[1], do * mults[2]
+        np.add.at(gE, idx[:, 0].astype(np.int64), ds)
+        np.add.at(gE, idx[:, 2].astype(np.int64), do)
+        np.add.at(gR, idx[:, 1].astype(np.int64), dp_)
+    return dict(loss=L, pos_scores=t, neg_scores=f, gE=gE, gR=gR)
+
