@@ -55,19 +55,25 @@ class Engine:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.kind, self.N, self.R_, self.we, self.wr, self.gamma = kind, int(num_entities), int(num_relations), int(we), int(wr), float(gamma)
         # zero-padded columns are neutral for DistMult/TransE, so odd widths are padded to the 128-bit granule
-        pad_ok = kind in (abi.DISTMULT, abi.TRANSE_L1, abi.TRANSE_L2, abi.PROTATE, abi.MODE_L1, abi.MODE_L2)
+        pad_ok = kind in (abi.DISTMULT, abi.TRANSE_L1, abi.TRANSE_L2, abi.PROTATE, abi.MODE_L1, abi.MODE_L2, abi.HAKE)
         self.we_k = (self.we + 3) // 4 * 4 if pad_ok else self.we
         self.wr_k = (self.wr + 3) // 4 * 4 if pad_ok else self.wr
         rng = rng or np.random.default_rng()
         self.E = self._table(E, self.N, self.we, self.we_k, rng)
         self.Rel = self._table(R, self.R_, self.wr, self.wr_k, rng)
         h = C.c_void_p()
-        abi.check(self.lib.kgeb_create(C.byref(h), self.device.index or 0, self.N, self.R_, self.we_k, self.wr_k,
+        # HAKE rows are [phase | modulus (| bias)]: the kernels split at the TRUE width, the padding only rounds the stride
+        cw = (self.we, self.wr) if kind == abi.HAKE else (self.we_k, self.wr_k)
+        abi.check(self.lib.kgeb_create(C.byref(h), self.device.index or 0, self.N, self.R_, cw[0], cw[1],
                                        self.we_k, self.wr_k, kind, self.gamma))
         self.ctx = h
-        self.param = float(param)
-        if self.param != 1.0:
-            self._check(self.lib.kgeb_set_score_param(self.ctx, self.param))
+        if kind == abi.HAKE:   # param = (pi / embedding_range, phase_weight, mod_weight), models.py:377-381
+            self.param = tuple(float(x) for x in param)
+            self._check(self.lib.kgeb_set_hake_params(self.ctx, *self.param))
+        else:
+            self.param = float(param)
+            if self.param != 1.0:
+                self._check(self.lib.kgeb_set_score_param(self.ctx, self.param))
         self.gE = self.gR = self.tE = self.tR = None
         self.opt_state = None
         self.step = 0

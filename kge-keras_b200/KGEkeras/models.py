@@ -142,7 +142,7 @@ class EmbeddingModel:
 
     def _kind_(self):
         if self._score_kind is None:
-            raise NotImplementedError(f"{type(self).__name__}: no score kernel (served: DistMult, TransE, ComplEx, HolE, "
+            raise NotImplementedError(f"{type(self).__name__}: no score kernel (served: DistMult, TransE, ComplEx, HolE, HAKE, "
                                       f"ModE, RotatE, pRotatE)")
         return self._score_kind
 
@@ -430,6 +430,11 @@ class HAKE(EmbeddingModel):
         self.gamma, self.epsilon, self.phase_weight, self.mod_weight = gamma, epsilon, phase_weight, mod_weight
         self.pi = np.pi
         self.embedding_range = (self.gamma + self.epsilon) / self.e_dim / 2
+
+    _score_kind = abi.HAKE   # models.py:383-400 as written: the modulus norm spans the whole call (kgeb_set_hake_params)
+
+    def _param_(self):
+        return (float(self.pi / self.embedding_range), float(self.phase_weight), float(self.mod_weight))
 
 
 class RotatE(EmbeddingModel):

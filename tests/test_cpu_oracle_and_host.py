@@ -516,3 +516,54 @@ def test_literal_step_matches_torch_restatement(act, aname, p):
     if not p:   # without dropout the transformed row is a function of the entity: the inference table
         Ep = ko.literal_table(E, L, W, b, act)
         np.testing.assert_allclose(Ep[tri[:, 0]], Y[:m].detach().numpy(), rtol=1e-12)
+
+
+def test_hake_oracle_matches_torch_restatement():
+    """HAKE.func (models.py:383-400) typed op for op in torch (chunk / clamp / where / Frobenius norm without axis / L1 norm
+    of the sine) against oracle.hake_scores and, through autograd, oracle.hake_row_grads -- including biases above the clip,
+    below -|mod_p|, and the coupling of every score of a call through the one modulus norm."""
+    import torch
+    rng = np.random.default_rng(0)
+    d, N, R, m = 6, 20, 4, 48
+    E = rng.normal(size=(N, 2 * d)) * 0.5
+    Rm = rng.normal(size=(R, 3 * d)) * 0.8
+    Rm[:, 2 * d:] += 0.5
+    idx = np.stack([rng.integers(0, N, m), rng.integers(0, R, m), rng.integers(0, N, m)], 1)
+    gamma, eps, pw, mw = 12.0, 2.0, 0.5, 1.5
+    hp = ko.hake_params(gamma, eps, 2 * d, pw, mw)
+    s, p, o = ko.gather(E, Rm, idx)
+    assert (p[:, 2 * d:] > 1).any() and (np.minimum(p[:, 2 * d:], 1) < -np.abs(p[:, d:2 * d])).any()
+
+    def func(s, p, o):
+        e_dim = s.shape[-1]
+        embedding_range = (gamma + eps) / e_dim / 2
+        phase_s, mod_s = torch.chunk(s, 2, -1)
+        phase_o, mod_o = torch.chunk(o, 2, -1)
+        phase_p, mod_p, bias_p = torch.chunk(p, 3, -1)
+        phase_s, phase_p, phase_o = (x / (embedding_range / np.pi) for x in (phase_s, phase_p, phase_o))
+        bias_p = torch.clamp(bias_p, max=1.0)
+        bias_p = torch.where(bias_p < -mod_p.abs(), -mod_p.abs(), bias_p)
+        r_score = mw * torch.linalg.norm(mod_s * (mod_p + bias_p) - mod_o.abs() * (1 - bias_p))
+        p_score = pw * torch.sin((phase_s + phase_p - phase_o) / 2).abs().sum(-1)
+        return gamma - (p_score + r_score)
+
+    ts, tp, to = (torch.tensor(x, requires_grad=True) for x in (s, p, o))
+    out = func(ts, tp, to)
+    np.testing.assert_allclose(out.detach().numpy(), ko.hake_scores(s, p, o, gamma, *hp), rtol=1e-12, atol=1e-12)
+    c = rng.normal(size=m)
+    (out * torch.tensor(c)).sum().backward()
+    gs, gp, go = ko.hake_row_grads(s, p, o, c, gamma, *hp)
+    for got, want in ((ts.grad, gs), (tp.grad, gp), (to.grad, go)):
+        np.testing.assert_allclose(got.numpy(), want, rtol=1e-10, atol=1e-12)
+    # hake_step == autograd through loss_and_coefs' loss on the two calls
+    pos, neg = idx[:12], idx[12:]
+    want = ko.hake_step(ko.PAIRWISE_LOGISTIC, ko.PAIRED, E, Rm, pos, neg, 3, 0.0, gamma, hp)
+    tE, tR = torch.tensor(E, requires_grad=True), torch.tensor(Rm, requires_grad=True)
+    tpos, tneg = torch.tensor(pos), torch.tensor(neg)
+    t = func(tE[tpos[:, 0]], tR[tpos[:, 1]], tE[tpos[:, 2]])
+    f = func(tE[tneg[:, 0]], tR[tneg[:, 1]], tE[tneg[:, 2]])
+    L, dt_, df_ = ko.loss_and_coefs(ko.PAIRWISE_LOGISTIC, ko.PAIRED, t.detach().numpy(), f.detach().numpy(), 3, 0.0)
+    ((t * torch.tensor(dt_)).sum() + (f * torch.tensor(df_)).sum()).backward()
+    np.testing.assert_allclose(tE.grad.numpy(), want["gE"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(tR.grad.numpy(), want["gR"], rtol=1e-9, atol=1e-12)
+    assert abs(L - want["loss"]) < 1e-12
