@@ -4,7 +4,8 @@ is computed by libkgeb200's sm_100a kernels through KGEkeras._engine; there is n
 
 Reference lines mirrored: EmbeddingModel.__init__ models.py:14-129, call 134-162, DistMult 164-172, TransE 175-190,
 ComplEx 203-222, HolE 224-237; siblings ModE 403-418, RotatE 421-459, pRotatE 461-489 (score_fwd/score_bwd + ranking
-kernels; they train through the unfused kernel sequence).  CosinE keeps its NameError, HAKE its constructor only.
+kernels; they train through the unfused kernel sequence), HAKE 362-400 (scoring and training as written, no ranking).
+CosinE keeps its NameError.
 """
 from __future__ import annotations
 
@@ -13,6 +14,25 @@ import warnings
 import numpy as np
 
 from . import _abi as abi
+
+
+def l3_reg(weight_matrix, w=0.01):
+    """models.py:10-11: w * ||W||_3^3 = w * sum |W|^3 of a weight matrix (an EmbeddingTable, a CUDA tensor or an array), computed
+    by kgeb_l3_reg -- the kernel the training step uses when `regularization != 0` (models.py:79-82).  Returns a Python float."""
+    import torch
+    from ._engine import Engine, _ptr, _stream
+    if isinstance(weight_matrix, EmbeddingTable):
+        weight_matrix = weight_matrix.embeddings
+    W = torch.as_tensor(np.asarray(weight_matrix, dtype=np.float32)) if not isinstance(weight_matrix, torch.Tensor) else weight_matrix.detach().to(torch.float32)
+    if W.dim() != 2:
+        raise ValueError(f"l3_reg expects a 2-D weight matrix, got shape {tuple(W.shape)}")
+    rows, width = W.shape
+    eng = Engine(abi.DISTMULT, rows, 1, width, width, E=W, R=np.zeros((1, width), np.float32))     # pads rows to the 128-bit granule with zeros
+    G = torch.zeros_like(eng.E)
+    flags = torch.zeros(rows, dtype=torch.uint8, device=eng.device)
+    out = torch.zeros(1, dtype=torch.float32, device=eng.device)
+    eng._check(eng.lib.kgeb_l3_reg(eng.ctx, _ptr(eng.E), rows, eng.we_k, eng.we_k, float(w), _ptr(G), _ptr(flags), _ptr(out), _stream()))
+    return float(out.item())
 
 
 class Dropout:

@@ -20,6 +20,15 @@ EPSILON = 1e-6  # utils.py:12
 
 
 # ---- data preparation (host) -----------------------------------------------------------------------------------
+def isint(value):
+    """utils.py:23-28."""
+    try:
+        int(value)
+        return True
+    except ValueError:
+        return False
+
+
 def load_kg(path):
     """utils.py:106-112: one whitespace-split token list per line (no id mapping)."""
     with open(path, 'r') as f:

@@ -259,3 +259,19 @@ def test_device_filter_csr_builder_equals_host_builder(side):
         ku.build_filter_csr_device(torch.from_numpy(test).cuda(), torch.from_numpy(np.concatenate([filt, test[:1]])).cuda(), side)
     eo, ei = ku.build_filter_csr_device(torch.from_numpy(test).cuda(), torch.zeros(0, 3, dtype=torch.int64).cuda(), side)
     assert eo.numel() == Q + 1 and ei.numel() == 0 and int(eo.sum()) == 0
+
+
+@pytest.mark.gpu
+def test_module_level_l3_reg():
+    """models.l3_reg(weight_matrix, w) (models.py:10-11) on arrays of awkward widths, CUDA tensors and a model's Embedding stand-in."""
+    import KGEkeras
+    rng = np.random.default_rng(3)
+    for rows, width in ((7, 5), (100, 100), (33, 202)):
+        W = rng.normal(size=(rows, width)).astype(np.float32)
+        want = 0.01 * float(np.sum(np.abs(W.astype(np.float64)) ** 3))
+        assert abs(KGEkeras.l3_reg(W) - want) <= 2e-6 * want
+        assert abs(KGEkeras.l3_reg(torch.from_numpy(W).cuda(), w=0.5) - 50 * want) <= 2e-6 * 50 * want
+    m = KGEkeras.DistMult(e_dim=12, r_dim=12, num_entities=40, num_relations=3)
+    E = m.entity_embedding.get_weights()[0]
+    want = 0.01 * float(np.sum(np.abs(E.astype(np.float64)) ** 3))
+    assert abs(KGEkeras.l3_reg(m.entity_embedding) - want) <= 2e-6 * want
