@@ -7,6 +7,7 @@ import os
 
 # enum values of include/kgeb200.h
 DISTMULT, TRANSE_L1, TRANSE_L2, COMPLEX, HOLE, ROTATE, PROTATE, MODE_L1, MODE_L2, HAKE = range(10)
+HOLE_DIRECT, HOLE_FFT = 0, 1
 FUSED_TRAIN_KINDS = (DISTMULT, TRANSE_L1, TRANSE_L2, COMPLEX)   # kinds the fused train kernel is instantiated for
 POINTWISE_HINGE, POINTWISE_LOGISTIC, POINTWISE_SQUARE, PAIRWISE_HINGE, PAIRWISE_LOGISTIC, PAIRWISE_SQUARE, POINTWISE_BCE = range(7)
 
@@ -54,6 +55,7 @@ PROTOTYPES = {
     "kgeb_last_kernel_ms": (_i, [_p, _i, C.POINTER(_f)]),
     "kgeb_set_score_param": (_i, [_p, _f]),
     "kgeb_set_hake_params": (_i, [_p, _f, _f, _f]),
+    "kgeb_set_hole_mode": (_i, [_p, _i]),
     "kgeb_set_dropout": (_i, [_p, _f, _u64, _u64, _i]),
     "kgeb_score_fwd": (_i, [_p, _p, _p, _p, _i64, _p, _p]),
     "kgeb_score_bwd": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p]),

@@ -129,6 +129,10 @@ class Engine:
             self.opt_state = (opt_kind,) + st
             self.step = 0
 
+    def set_hole_mode(self, fft=True):
+        """HolE through the Fourier domain (the reference's own formulation) for power-of-two widths; default = direct O(d^2)."""
+        self._check(self.lib.kgeb_set_hole_mode(self.ctx, abi.HOLE_FFT if fft else abi.HOLE_DIRECT))
+
     # ---- dropout ------------------------------------------------------------------------------------------------
     def set_dropout(self, p=0.0, seed=0, offset=0, stream_id=0):
         """models.py:122,144-150: arm (p > 0) or disarm (p = 0) dropout for the next scoring / training calls."""

@@ -37,6 +37,7 @@ extern "C" int kgeb_create(kgeb_ctx** out, int device, int64_t num_entities, int
   if (const char* e = getenv("KGEB_RING_CTAS")) c->env_ring_ctas = atoi(e);
   if (const char* e = getenv("KGEB_RING_D")) c->env_ring_d = atoi(e);
   if (const char* e = getenv("KGEB_TRAIN_KERNEL")) c->env_force_reg = strcmp(e, "reg") == 0;
+  if (const char* e = getenv("KGEB_HOLE")) c->hole_fft = strcmp(e, "fft") == 0;
   if (const char* e = getenv("KGEB_ALLPAIRS")) c->env_allpairs_dense = strcmp(e, "dense") == 0;
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) c->ring_cfg[i][j].smem = -1;
   if ((e = cudaMalloc(&c->d_partials, sizeof(double) * 2 * KGEB_MAX_PARTIAL_BLOCKS)) != cudaSuccess ||
@@ -87,6 +88,13 @@ extern "C" int kgeb_last_kernel_ms(kgeb_ctx* ctx, int which, float* ms) {
   KGEB_REQUIRE(ctx, ctx->ev_valid[which], KGEB_ERR_INVALID, "kernel timing: that kernel has not been launched with timing on");
   KGEB_CUDA_OK(ctx, cudaEventSynchronize(ctx->ev[which][1]));
   KGEB_CUDA_OK(ctx, cudaEventElapsedTime(ms, ctx->ev[which][0], ctx->ev[which][1]));
+  return KGEB_OK;
+}
+
+extern "C" int kgeb_set_hole_mode(kgeb_ctx* ctx, int mode) {
+  if (!ctx) return KGEB_ERR_INVALID;
+  KGEB_REQUIRE(ctx, mode == KGEB_HOLE_DIRECT || mode == KGEB_HOLE_FFT, KGEB_ERR_INVALID, "set_hole_mode: unknown mode");
+  ctx->hole_fft = mode == KGEB_HOLE_FFT;
   return KGEB_OK;
 }
 

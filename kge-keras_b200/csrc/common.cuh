@@ -20,6 +20,7 @@ struct kgeb_ctx {
   int kind;
   float gamma;
   float param;   // pRotatE modulus (kgeb_set_score_param), 1 otherwise
+  int hole_fft;  // kgeb_set_hole_mode: HolE through the Fourier domain for power-of-two widths
   float hake_ps, hake_pw, hake_mw;   // HAKE: pi / embedding_range, phase_weight, mod_weight (kgeb_set_hake_params)
   int num_sms;
   int64_t launches;
@@ -72,6 +73,10 @@ static inline int kgeb_fail(kgeb_ctx* ctx, int code, const char* fmt, const char
 
 static inline bool kgeb_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// HolE through the Fourier domain (hole_fft_kernels.cu); KGEB_ERR_UNSUPPORTED = shape not served, use the direct kernels
+int kgeb_internal_hole_fft_fwd(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* idx, int64_t m, float* scores, cudaStream_t st);
+int kgeb_internal_hole_fft_bwd(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* idx, int64_t m, const float* dscore, float* gE, float* gR,
+                               uint8_t* tE, uint8_t* tR, cudaStream_t st);
 // HAKE's batch-coupled score (hake_kernels.cu), reached through kgeb_score_fwd / kgeb_score_bwd
 int kgeb_internal_hake_fwd(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* idx, int64_t m, float* scores, cudaStream_t st);
 int kgeb_internal_hake_bwd(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* idx, int64_t m, const float* dscore, float* gE, float* gR,

@@ -278,6 +278,10 @@ extern "C" int kgeb_score_fwd(kgeb_ctx* ctx, const float* E, const float* R, con
   const int grid = grid_for(ctx, m, 8);
   if (ctx->kind == KGEB_HOLE) {
     KGEB_REQUIRE(ctx, ctx->we == ctx->wr, KGEB_ERR_UNSUPPORTED, "HolE needs e_dim == r_dim");
+    if (ctx->hole_fft) {
+      const int rc = kgeb_internal_hole_fft_fwd(ctx, E, R, idx, m, scores, st);
+      if (rc != KGEB_ERR_UNSUPPORTED) return rc;      // not a power-of-two width: the direct kernel below
+    }
     const size_t sm = (size_t)KGEB_WARPS_PER_BLOCK * (hole_lin(ctx->we) + hole_dbl(ctx->we)) * sizeof(float);
     KGEB_REQUIRE(ctx, sm <= 200 * 1024, KGEB_ERR_UNSUPPORTED, "HolE dim too large for shared memory staging");
     KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_hole_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -311,6 +315,10 @@ extern "C" int kgeb_score_bwd(kgeb_ctx* ctx, const float* E, const float* R, con
   ScoreArgs a = make_score_args(ctx, E, R, &nc);
   const int grid = grid_for(ctx, m, 8);
   if (ctx->kind == KGEB_HOLE) {
+    if (ctx->hole_fft) {
+      const int rc = kgeb_internal_hole_fft_bwd(ctx, E, R, idx, m, dscore, gE, gR, touchedE, touchedR, st);
+      if (rc != KGEB_ERR_UNSUPPORTED) return rc;
+    }
     const size_t sm = (size_t)KGEB_WARPS_PER_BLOCK * 2 * (hole_lin(ctx->we) + hole_dbl(ctx->we)) * sizeof(float);
     KGEB_REQUIRE(ctx, sm <= 200 * 1024, KGEB_ERR_UNSUPPORTED, "HolE dim too large for shared memory staging");
     KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_hole_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
