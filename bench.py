@@ -429,19 +429,31 @@ def main():
             sb = torch.from_numpy(np.stack([srng.integers(0, sN, (ssteps + swarm, sB)), srng.integers(0, sR, (ssteps + swarm, sB)),
                                             srng.integers(0, sN, (ssteps + swarm, sB))], axis=2).astype(np.int32)).to(dev)
             skw = dict(K=sK, loss_kind=sloss, pair_mode=abi.PAIRED, margin=1.0, corrupt_mode=abi.CORRUPT_BOTH, seed=77, opt_kind=abi.LAZY_ADAM, lr=1e-3)
-            for i in range(swarm):
-                seng.train_step(sb[i], None, offset=i, **skw)
-            sev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(ssteps)]
-            sl0 = seng.launches
-            for i in range(ssteps):
-                flush.zero_()
-                sev[i][0].record()
-                seng.train_step(sb[swarm + i], None, offset=swarm + i, **skw)
-                sev[i][1].record()
-            torch.cuda.synchronize()
-            sms = float(np.mean([e[0].elapsed_time(e[1]) for e in sev]))
+            def time_shape():
+                for i in range(swarm):
+                    seng.train_step(sb[i], None, offset=i, **skw)
+                sev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(ssteps)]
+                sl0 = seng.launches
+                for i in range(ssteps):
+                    flush.zero_()
+                    sev[i][0].record()
+                    seng.train_step(sb[swarm + i], None, offset=swarm + i, **skw)
+                    sev[i][1].record()
+                torch.cuda.synchronize()
+                sms = float(np.mean([e[0].elapsed_time(e[1]) for e in sev]))
+                return sms, (seng.launches - sl0) // ssteps
+
+            direct = None
+            if skind == abi.HOLE:   # the O(d^2) sequential-contract kernels first, then the Fourier-domain mode (the reference's own formulation)
+                dms, _ = time_shape()
+                direct = {"ms_per_step": dms, "triples_per_s": sB * (1 + sK) / (dms * 1e-3), "note": "default mode: direct O(d^2) correlation, fp32 sequential contract"}
+                seng.set_hole_mode(True)
+                snote = "64 negatives, pointwize_logistic; unfused score_fwd -> loss -> score_bwd, kgeb_set_hole_mode(KGEB_HOLE_FFT): shared-memory radix-4 FFTs"
+            sms, slaunch = time_shape()
             entry = {"batch_positives": sB, "negatives_per_positive": sK, "ms_per_step": sms, "triples_per_s": sB * (1 + sK) / (sms * 1e-3),
-                     "gpu_launches_per_step": (seng.launches - sl0) // ssteps, "note": snote}
+                     "gpu_launches_per_step": slaunch, "note": snote}
+            if direct is not None:
+                entry["direct_kernels"] = direct
             if skind == abi.HOLE:   # C4 filtered 1-N eval on the tensor cores (exact mode), 5 000 test triples x 2 sides
                 qn = 5000
                 qtri = torch.from_numpy(np.stack([srng.integers(0, sN, qn), srng.integers(0, sR, qn), srng.integers(0, sN, qn)], axis=1).astype(np.int32)).to(dev)

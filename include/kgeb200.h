@@ -108,7 +108,7 @@ KGEB_API int kgeb_set_score_param(kgeb_ctx* ctx, float param);
 
 /* HolE arithmetic.  KGEB_HOLE_DIRECT (default): the O(d^2) circular correlation accumulated sequentially in fp32 (the contract the
  * bit-exact tests pin).  KGEB_HOLE_FFT: the reference's own formulation (models.py:233-234, ifft(conj(fft(s)) * fft(o))) with
- * shared-memory radix-2 FFTs, for power-of-two widths 32..1024 (other widths keep the direct kernels); same results to fp32
+ * shared-memory radix-4 FFTs, for power-of-two widths 32..1024 (other widths keep the direct kernels); same results to fp32
  * FFT rounding (1e-6 relative to the summed magnitudes), ~3 length-d FFTs per triple instead of 3 d^2 multiply-adds.
  * Applies to kgeb_score_fwd / kgeb_score_bwd.  Environment KGEB_HOLE=fft selects it at kgeb_create. */
 typedef enum { KGEB_HOLE_DIRECT = 0, KGEB_HOLE_FFT = 1 } kgeb_hole_mode;

@@ -9,7 +9,8 @@
 //   dp = F^-1( sum_run c conj(S) O )                 accumulated in the Fourier domain over a run of triples that share the
 //                                                    relation (the K negatives of one positive), one inverse FFT per run
 // A warp owns a contiguous range of triples, so runs stay together; P = F(p) is recomputed only when the relation changes.
-// FFT: radix-2 Stockham autosort in shared memory (two d-complex buffers per warp), twiddles from a per-block table.
+// FFT: radix-4 (+ one radix-2 stage for odd log2 d) Stockham autosort in shared memory (two d-complex buffers per warp),
+// twiddles from a per-block table.
 #include "frag.cuh"
 
 namespace {
@@ -24,12 +25,37 @@ struct HoleFftArgs {
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
-// in-place on (x, y): returns the buffer that holds the result.  INV uses conjugated twiddles (no 1/d scale).
+// ping-pong between x and y: returns the buffer that holds the result.  INV uses conjugated twiddles (no 1/d scale).
+// Radix-4 Stockham autosort stages (each pass reads and writes every element once, so half the shared-memory traffic of
+// radix-2), plus one radix-2 stage when log2(d) is odd.  tw[k] = exp(-2 pi i k / d), k < d.
 template <bool INV>
 __device__ __forceinline__ float2* warp_fft(float2* x, float2* y, const float2* __restrict__ tw, int d, int logd, int lane) {
-  const int t = d >> 1;
-  for (int s = 0; s < logd; ++s) {
-    const int p = 1 << s, sh = logd - 1 - s;          // twiddle index k * d / (2 p) = k << sh
+  int p = 1, lp = 0;
+  for (; 4 * p <= d; p <<= 2, lp += 2) {
+    const int t = d >> 2, sh = logd - 2 - lp;          // twiddle index m * k * d / (4 p) = (m * k) << sh
+    __syncwarp();
+    for (int i = lane; i < t; i += 32) {
+      const int k = i & (p - 1), j = ((i - k) << 2) + k;
+      float2 w1 = tw[k << sh], w2 = tw[(2 * k) << sh], w3 = tw[(3 * k) << sh];
+      if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+      const float2 u0 = x[i], u1 = cmul(x[i + t], w1), u2 = cmul(x[i + 2 * t], w2), u3 = cmul(x[i + 3 * t], w3);
+      const float2 v0 = make_float2(u0.x + u2.x, u0.y + u2.y), v1 = make_float2(u0.x - u2.x, u0.y - u2.y);
+      const float2 v2 = make_float2(u1.x + u3.x, u1.y + u3.y);
+      const float2 df = make_float2(u1.x - u3.x, u1.y - u3.y);
+      const float2 v3 = INV ? make_float2(-df.y, df.x) : make_float2(df.y, -df.x);      // (+/-) i * (u1 - u3)
+      const float2 y0 = make_float2(v0.x + v2.x, v0.y + v2.y), y1 = make_float2(v1.x + v3.x, v1.y + v3.y);
+      const float2 y2 = make_float2(v0.x - v2.x, v0.y - v2.y), y3 = make_float2(v1.x - v3.x, v1.y - v3.y);
+      if (p == 1) {                                      // the four outputs are adjacent: two 128-bit stores
+        *reinterpret_cast<float4*>(y + j) = make_float4(y0.x, y0.y, y1.x, y1.y);
+        *reinterpret_cast<float4*>(y + j + 2) = make_float4(y2.x, y2.y, y3.x, y3.y);
+      } else {
+        y[j] = y0; y[j + p] = y1; y[j + 2 * p] = y2; y[j + 3 * p] = y3;
+      }
+    }
+    float2* tmp = x; x = y; y = tmp;
+  }
+  if (p < d) {                                           // log2(d) odd: one radix-2 stage with p = d / 2
+    const int t = d >> 1, sh = logd - 1 - lp;
     __syncwarp();
     for (int i = lane; i < t; i += 32) {
       const int k = i & (p - 1), j = ((i - k) << 1) + k;
@@ -90,13 +116,13 @@ __device__ __forceinline__ void hf_split(const float2* Z, int f, int d, float2& 
 }
 
 __device__ __forceinline__ void hf_setup(const HoleFftArgs& a, float2* smem, float2*& tw, HfWarp& w) {
-  tw = smem;                                   // d/2 twiddles exp(-2 pi i k / d), shared by the block
-  for (int k = threadIdx.x; k < (a.d >> 1); k += blockDim.x) {
+  tw = smem;                                   // d twiddles exp(-2 pi i k / d), shared by the block (radix-4 stages index up to 3d/4)
+  for (int k = threadIdx.x; k < a.d; k += blockDim.x) {
     float sn, cs;
     sincospif(-2.f * (float)k / (float)a.d, &sn, &cs);
     tw[k] = make_float2(cs, sn);
   }
-  float2* base = smem + (a.d >> 1) + (size_t)(threadIdx.x >> 5) * 4 * a.d;
+  float2* base = smem + a.d + (size_t)(threadIdx.x >> 5) * 4 * a.d;
   w.a = base; w.b = base + a.d; w.P = base + 2 * a.d; w.acc = base + 3 * a.d;
   __syncthreads();
 }
@@ -220,7 +246,7 @@ bool hf_args(const kgeb_ctx* ctx, const float* E, const float* R, HoleFftArgs* a
   a->stream = ctx->dp_stream;
   return true;
 }
-size_t hf_smem_bytes(int d) { return ((size_t)(d >> 1) + (size_t)HF_WARPS * 4 * d) * sizeof(float2); }
+size_t hf_smem_bytes(int d) { return ((size_t)d + (size_t)HF_WARPS * 4 * d) * sizeof(float2); }
 int hf_grid(const kgeb_ctx* ctx, int64_t m, size_t smem) {
   int per_sm = (int)((200u * 1024u) / smem);
   if (per_sm > 8) per_sm = 8;
