@@ -74,6 +74,7 @@ class Engine:
             self.param = float(param)
             if self.param != 1.0:
                 self._check(self.lib.kgeb_set_score_param(self.ctx, self.param))
+        self.hole_fft = False
         self.gE = self.gR = self.tE = self.tR = None
         self.opt_state = None
         self.step = 0
@@ -132,6 +133,7 @@ class Engine:
     def set_hole_mode(self, fft=True):
         """HolE through the Fourier domain (the reference's own formulation) for power-of-two widths; default = direct O(d^2)."""
         self._check(self.lib.kgeb_set_hole_mode(self.ctx, abi.HOLE_FFT if fft else abi.HOLE_DIRECT))
+        self.hole_fft = bool(fft)
 
     # ---- dropout ------------------------------------------------------------------------------------------------
     def set_dropout(self, p=0.0, seed=0, offset=0, stream_id=0):

@@ -68,6 +68,8 @@ class LiteralHead:
             cap = max(m, 1024)
             mn = self.main
             self._tmp = Engine(mn.kind, 2 * cap, cap, mn.we, mn.wr, mn.gamma, E=torch.zeros(2 * cap, mn.we), R=torch.zeros(cap, mn.wr), param=mn.param)
+            if mn.hole_fft:
+                self._tmp.set_hole_mode(True)
             self._X = torch.empty(2 * cap, self.kin, dtype=torch.float32, device=self.dev)
             self._gX = torch.empty(2 * cap, self.kin, dtype=torch.float32, device=self.dev)
         return self._tmp
@@ -79,6 +81,8 @@ class LiteralHead:
             if self._eff is None:
                 self._eff = Engine(mn.kind, mn.N, mn.R_, mn.we, mn.wr, mn.gamma, E=torch.zeros(1, mn.we).expand(mn.N, mn.we), R=torch.zeros(mn.R_, mn.wr),
                                    param=mn.param)
+                if mn.hole_fft:
+                    self._eff.set_hole_mode(True)
             ids = torch.arange(mn.N, dtype=torch.int32, device=self.dev)
             X = torch.empty(mn.N, self.kin, dtype=torch.float32, device=self.dev)
             mn.set_dropout(0.0)

@@ -410,8 +410,18 @@ class HolE(EmbeddingModel):
     _score_kind = abi.HOLE
 
     def __init__(self, name='HolE', **kwargs):
-        """HolE (models.py:224-237): sum_k p_k (s (*) o)_k, circular correlation."""
+        """HolE (models.py:224-237): sum_k p_k (s (*) o)_k, circular correlation.  `fft=True` (default) scores and differentiates
+        through the Fourier domain like the reference (models.py:233-234) when the width is a power of two in 32..1024;
+        `fft=False` keeps the direct O(d^2) kernels with their sequential fp32 contract (other widths always use them)."""
+        self.fft = bool(kwargs.pop("fft", True))
         super(HolE, self).__init__(name=name, **kwargs)
+
+    def _engine_(self):
+        fresh = self._eng is None
+        eng = super(HolE, self)._engine_()
+        if fresh:
+            eng.set_hole_mode(self.fft)
+        return eng
 
 
 # ---- sibling classes: constructors kept (same keywords, same width multipliers), score kernels are SURVEY 8f "next" ----
