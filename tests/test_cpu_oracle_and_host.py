@@ -567,3 +567,17 @@ def test_hake_oracle_matches_torch_restatement():
     np.testing.assert_allclose(tE.grad.numpy(), want["gE"], rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(tR.grad.numpy(), want["gR"], rtol=1e-9, atol=1e-12)
     assert abs(L - want["loss"]) < 1e-12
+
+
+def test_hake_and_hole_constructors_without_gpu():
+    """Width multipliers and derived constants of the sibling constructors (models.py:371-381) are host logic: no GPU needed."""
+    import KGEkeras
+    m = KGEkeras.HAKE(e_dim=10, r_dim=10, num_entities=5, num_relations=2, gamma=12, epsilon=2, phase_weight=0.25, mod_weight=2.0)
+    assert (m.e_dim, m.r_dim) == (20, 30)
+    assert abs(m.embedding_range - (12 + 2) / 20 / 2) < 1e-12
+    ps, pw, mw = m._param_()
+    assert abs(ps - np.pi / m.embedding_range) < 1e-9 and (pw, mw) == (0.25, 2.0)
+    assert ko.hake_params(12, 2, 20, 0.25, 2.0) == pytest.approx((ps, pw, mw))
+    h = KGEkeras.HolE(e_dim=64, r_dim=64, num_entities=5, num_relations=2, fft=False)
+    assert h.fft is False and KGEkeras.HolE(e_dim=64, r_dim=64, num_entities=5, num_relations=2).fft is True
+    assert KGEkeras.isint("12") and not KGEkeras.isint("1.5x")
