@@ -220,6 +220,9 @@ class Engine:
         pairwise = abi.is_pairwise(loss_kind)
         fused = (not force_unfused and self.kind in abi.FUSED_TRAIN_KINDS and not (pairwise and pair_mode == abi.ALLPAIRS)
                  and (neg is None or neg.shape[0] == B * K))
+        if (not force_unfused and self.kind == abi.HOLE and self.hole_fft and not pairwise and (neg is None or neg.shape[0] == B * K)
+                and 32 <= self.we <= 1024 and self.we & (self.we - 1) == 0):
+            fused = True      # Fourier-domain HolE: one fused kernel for the pointwise losses (hole_fft_kernels.cu)
         res = {}
         if fused:
             ps = torch.empty(B, dtype=torch.float32, device=self.device) if want_scores else None

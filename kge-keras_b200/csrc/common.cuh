@@ -77,6 +77,9 @@ static inline bool kgeb_aligned16(const void* p) { return (reinterpret_cast<uint
 int kgeb_internal_hole_fft_fwd(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* idx, int64_t m, float* scores, cudaStream_t st);
 int kgeb_internal_hole_fft_bwd(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* idx, int64_t m, const float* dscore, float* gE, float* gR,
                                uint8_t* tE, uint8_t* tR, cudaStream_t st);
+int kgeb_internal_hole_fft_train(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* pos, int64_t B, const int32_t* neg, int K, int loss_kind,
+                                 float margin, float loss_weight, int corrupt_mode, uint64_t seed, uint64_t offset, float* loss, float* pos_scores,
+                                 float* neg_scores, int32_t* neg_out, float* gE, float* gR, uint8_t* tE, uint8_t* tR, cudaStream_t st);
 // HAKE's batch-coupled score (hake_kernels.cu), reached through kgeb_score_fwd / kgeb_score_bwd
 int kgeb_internal_hake_fwd(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* idx, int64_t m, float* scores, cudaStream_t st);
 int kgeb_internal_hake_bwd(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* idx, int64_t m, const float* dscore, float* gE, float* gR,

@@ -233,6 +233,121 @@ __global__ void __launch_bounds__(HF_WARPS * 32) k_hole_fft_bwd(HoleFftArgs a, c
   flush();
 }
 
+// The whole step for the POINTWISE losses (a triple's loss coefficient depends on its own score only): Z = F(s + i o) is
+// transformed once, the score, the loss term and its derivative follow, and the same spectra give the gradients.  Triples are
+// the concatenation [positives ; negatives]; negatives come from `neg` or from the in-kernel Philox draw (neg == NULL).
+struct HoleTrainArgs {
+  const int32_t* pos; int64_t B; const int32_t* neg; int K;
+  int loss_kind; float margin, w; int corrupt_mode; uint64_t seed, offset; uint32_t N;
+  float* loss; float* pos_scores; float* neg_scores; int32_t* neg_out;
+  float* gE; float* gR; uint8_t* tE; uint8_t* tR;
+  double* partials; unsigned int* ticket;
+};
+
+template <bool DP>
+__global__ void __launch_bounds__(HF_WARPS * 32) k_hole_fft_train(HoleFftArgs a, HoleTrainArgs t) {
+  extern __shared__ __align__(16) float2 hf_smem[];
+  float2* tw; HfWarp w;
+  hf_setup(a, hf_smem, tw, w);
+  const int lane = threadIdx.x & 31, d = a.d;
+  const int64_t m = t.B * (1 + (int64_t)t.K);
+  const int64_t nw = (int64_t)gridDim.x * HF_WARPS, wid = (int64_t)blockIdx.x * HF_WARPS + (threadIdx.x >> 5);
+  const int64_t per = (m + nw - 1) / nw, i0 = wid * per, i1 = i0 + per < m ? i0 + per : m;
+  const float inv_d = 1.f / (float)d;
+  const float sP = (float)((double)t.w / (double)t.B), sN = (float)((double)t.w / ((double)t.B * (double)t.K));
+  double lp = 0.0, ln = 0.0;
+  int64_t prel = -1, pg = -1;
+  int pstream = 0;
+  bool acc_live = false;
+  auto flush = [&]() {
+    if (!acc_live) return;
+    for (int f = lane; f < d; f += 32) w.a[f] = w.acc[f];
+    const float2* g = warp_fft<true>(w.a, w.b, tw, d, a.logd, lane);
+    float* dst = t.gR + prel * a.ldR;
+    for (int c = lane; c < (d >> 2); c += 32) {
+      float mp[4];
+      hf_mult4(a.dp, 1, pstream, (uint64_t)pg, c, mp);
+      const float4 v = make_float4(g[4 * c].x * inv_d * mp[0], g[4 * c + 1].x * inv_d * mp[1], g[4 * c + 2].x * inv_d * mp[2], g[4 * c + 3].x * inv_d * mp[3]);
+      if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add4(dst + 4 * c, v);
+    }
+    __syncwarp();
+    acc_live = false;
+  };
+  for (int64_t x = i0; x < i1; ++x) {
+    const bool is_pos = x < t.B;
+    const int64_t g = is_pos ? x : x - t.B;            // index of the triple inside its call (dropout counter)
+    int64_t s, p, o;
+    if (is_pos) {
+      s = t.pos[3 * x]; p = t.pos[3 * x + 1]; o = t.pos[3 * x + 2];
+    } else if (t.neg) {
+      s = t.neg[3 * g]; p = t.neg[3 * g + 1]; o = t.neg[3 * g + 2];
+    } else {
+      const int64_t i = g / t.K;
+      int ns, no;
+      philox_corrupt(t.pos[3 * i], t.pos[3 * i + 2], (uint64_t)g, t.seed, t.offset, t.N, t.corrupt_mode, ns, no);
+      s = ns; p = t.pos[3 * i + 1]; o = no;
+      if (t.neg_out && lane == 0) { t.neg_out[3 * g] = ns; t.neg_out[3 * g + 1] = (int32_t)p; t.neg_out[3 * g + 2] = no; }
+    }
+    if (lane == 0) { t.tE[s] = 1; t.tE[o] = 1; t.tR[p] = 1; }
+    HoleFftArgs ac = a;
+    ac.stream = is_pos ? 0 : 1;
+    if (p != prel || DP) {
+      flush();
+      hf_load_p(ac, a.R + p * a.ldR, (uint64_t)g, w.a, lane);
+      const float2* Pf = warp_fft<false>(w.a, w.b, tw, d, a.logd, lane);
+      for (int f = lane; f < d; f += 32) { w.P[f] = Pf[f]; w.acc[f] = make_float2(0.f, 0.f); }
+      prel = p;
+    }
+    pg = g; pstream = ac.stream;
+    __syncwarp();
+    hf_load_so(ac, a.E + s * a.ldE, a.E + o * a.ldE, (uint64_t)g, w.a, lane);
+    float2* Z = warp_fft<false>(w.a, w.b, tw, d, a.logd, lane);
+    float part = 0.f;
+    for (int f = lane; f < d; f += 32) {
+      float2 S, O;
+      hf_split(Z, f, d, S, O);
+      const float2 q = cmul(cconj(w.P[f]), cconj(S));
+      part += q.x * O.x - q.y * O.y;
+    }
+    const float score = warp_sum(part) * inv_d;
+    float val, der;
+    pointwise_terms(t.loss_kind, t.margin, score, is_pos, val, der);
+    if (lane == 0) {
+      if (is_pos) { lp += (double)val; if (t.pos_scores) t.pos_scores[x] = score; }
+      else { ln += (double)val; if (t.neg_scores) t.neg_scores[g] = score; }
+    }
+    const float c = der * (is_pos ? sP : sN);
+    if (c == 0.f) continue;                            // warp-uniform (the score is a full butterfly sum)
+    float2* Gb = (Z == w.a) ? w.b : w.a;
+    for (int f = lane; f < d; f += 32) {
+      float2 S, O;
+      hf_split(Z, f, d, S, O);
+      const float2 P = w.P[f];
+      const float2 gs = cmul(cconj(P), O), go = cmul(P, S);
+      Gb[f] = make_float2(c * (gs.x - go.y), c * (gs.y + go.x));
+      const float2 gp = cmul(cconj(S), O);
+      w.acc[f].x += c * gp.x;
+      w.acc[f].y += c * gp.y;
+    }
+    acc_live = true;
+    __syncwarp();
+    const float2* gr = warp_fft<true>(Gb, Z, tw, d, a.logd, lane);
+    float* ds = t.gE + s * a.ldE;
+    float* dO = t.gE + o * a.ldE;
+    for (int cch = lane; cch < (d >> 2); cch += 32) {
+      float ms[4], mo[4];
+      hf_mult4(a.dp, 0, ac.stream, (uint64_t)g, cch, ms);
+      hf_mult4(a.dp, 2, ac.stream, (uint64_t)g, cch, mo);
+      const float2 g0 = gr[4 * cch], g1 = gr[4 * cch + 1], g2 = gr[4 * cch + 2], g3 = gr[4 * cch + 3];
+      red_add4(ds + 4 * cch, make_float4(g0.x * inv_d * ms[0], g1.x * inv_d * ms[1], g2.x * inv_d * ms[2], g3.x * inv_d * ms[3]));
+      red_add4(dO + 4 * cch, make_float4(g0.y * inv_d * mo[0], g1.y * inv_d * mo[1], g2.y * inv_d * mo[2], g3.y * inv_d * mo[3]));
+    }
+    __syncwarp();
+  }
+  flush();
+  block_finalize_loss(lp, ln, t.partials, t.ticket, (double)t.w / (double)t.B, (double)t.w / ((double)t.B * (double)t.K), t.loss);
+}
+
 bool hf_args(const kgeb_ctx* ctx, const float* E, const float* R, HoleFftArgs* a) {
   const int d = ctx->we;
   if (d != ctx->wr || d < 32 || d > 1024 || (d & (d - 1)) != 0) return false;
@@ -288,6 +403,30 @@ int kgeb_internal_hole_fft_bwd(kgeb_ctx* ctx, const float* E, const float* R, co
   } else {
     KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_hole_fft_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_hole_fft_bwd<false><<<grid, HF_WARPS * 32, sm, st>>>(a, idx, m, dscore, gE, gR, tE, tR);
+  }
+  KGEB_LAUNCH_OK(ctx);
+  return KGEB_OK;
+}
+
+// fused step; KGEB_ERR_UNSUPPORTED (ctx->err untouched) when the width or the loss is not served
+int kgeb_internal_hole_fft_train(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* pos, int64_t B, const int32_t* neg, int K, int loss_kind,
+                                 float margin, float loss_weight, int corrupt_mode, uint64_t seed, uint64_t offset, float* loss, float* pos_scores,
+                                 float* neg_scores, int32_t* neg_out, float* gE, float* gR, uint8_t* tE, uint8_t* tR, cudaStream_t st) {
+  HoleFftArgs a;
+  if (KGEB_IS_PAIRWISE(loss_kind) || !hf_args(ctx, E, R, &a) || !kgeb_aligned16(gE) || !kgeb_aligned16(gR)) return KGEB_ERR_UNSUPPORTED;
+  HoleTrainArgs t;
+  t.pos = pos; t.B = B; t.neg = neg; t.K = K; t.loss_kind = loss_kind; t.margin = margin; t.w = loss_weight; t.corrupt_mode = corrupt_mode;
+  t.seed = seed; t.offset = offset; t.N = (uint32_t)ctx->N; t.loss = loss; t.pos_scores = pos_scores; t.neg_scores = neg_scores; t.neg_out = neg_out;
+  t.gE = gE; t.gR = gR; t.tE = tE; t.tR = tR; t.partials = ctx->d_partials; t.ticket = ctx->d_ticket;
+  const size_t sm = hf_smem_bytes(a.d);
+  int grid = hf_grid(ctx, B * (1 + (int64_t)K), sm);
+  if (grid > KGEB_MAX_PARTIAL_BLOCKS) grid = KGEB_MAX_PARTIAL_BLOCKS;
+  if (a.dp.thr) {
+    KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_hole_fft_train<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_hole_fft_train<true><<<grid, HF_WARPS * 32, sm, st>>>(a, t);
+  } else {
+    KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_hole_fft_train<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_hole_fft_train<false><<<grid, HF_WARPS * 32, sm, st>>>(a, t);
   }
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;

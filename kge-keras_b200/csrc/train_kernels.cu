@@ -111,8 +111,14 @@ extern "C" int kgeb_train_fwd_bwd(kgeb_ctx* ctx, const float* E, const float* R,
                "train_fwd_bwd: bad arguments");
   KGEB_REQUIRE(ctx, loss_kind >= 0 && loss_kind <= KGEB_LOSS_KIND_MAX, KGEB_ERR_INVALID, "unknown loss kind");
   KGEB_REQUIRE(ctx, corrupt_mode >= 0 && corrupt_mode <= 3, KGEB_ERR_INVALID, "unknown corrupt mode");
+  if (ctx->kind == KGEB_HOLE && ctx->hole_fft) {   // Fourier-domain mode: one fused kernel for the pointwise losses
+    KGEB_REQUIRE(ctx, E && R, KGEB_ERR_INVALID, "null table pointer");
+    const int rc = kgeb_internal_hole_fft_train(ctx, E, R, pos, B, neg, K, loss_kind, margin, loss_weight, corrupt_mode, seed, offset, loss, pos_scores,
+                                                neg_scores, neg_out, gE, gR, touchedE, touchedR, (cudaStream_t)stream);
+    if (rc != KGEB_ERR_UNSUPPORTED) return rc;
+  }
   KGEB_REQUIRE(ctx, ctx->kind != KGEB_HOLE && ctx->kind != KGEB_HAKE, KGEB_ERR_UNSUPPORTED,
-               "HolE and HAKE use the unfused sequence score_fwd -> loss_fwd_bwd -> score_bwd");
+               "HolE (outside the Fourier-domain mode with a pointwise loss) and HAKE use the unfused sequence score_fwd -> loss_fwd_bwd -> score_bwd");
   if (int rc = check_tables(ctx, E, R)) return rc;
   KGEB_REQUIRE(ctx, kgeb_aligned16(gE) && kgeb_aligned16(gR), KGEB_ERR_ALIGNMENT, "gradient buffers must be 16-byte aligned");
   int nc;

@@ -94,3 +94,46 @@ def test_other_widths_keep_the_direct_kernels():
     got = eng.score(idx).cpu().numpy()
     eng.set_hole_mode(False)
     np.testing.assert_array_equal(got, eng.score(idx).cpu().numpy())
+
+
+@pytest.mark.parametrize("loss", [ko.POINTWISE_LOGISTIC, ko.POINTWISE_HINGE, ko.POINTWISE_SQUARE])
+@pytest.mark.parametrize("p", [0.0, 0.25])
+@pytest.mark.parametrize("given_neg", [True, False])
+def test_fused_step_matches_unfused_sequence(loss, p, given_neg):
+    """kgeb_train_fwd_bwd in the Fourier-domain mode (one kernel: transform, score, loss term, gradients) against
+    score_fwd -> loss_fwd_bwd -> score_bwd of the same mode, with listed negatives and with the in-kernel Philox draw."""
+    N, R, d, B, K = 180, 5, 128, 96, 6
+    eng, E, Rm = make(N, R, d, seed=6)
+    rng = np.random.default_rng(2)
+    pos = np.stack([rng.integers(0, N, B), rng.integers(0, R, B), rng.integers(0, N, B)], 1).astype(np.int32)
+    neg = ko.philox_negatives(pos, N, K, 3, 7, ko.CORRUPT_BOTH).astype(np.int32)
+    out = {}
+    for unfused in (False, True):
+        if eng.gE is not None:
+            eng.gE.zero_(); eng.gR.zero_(); eng.tE.zero_(); eng.tR.zero_()
+        l0 = eng.launches
+        res = eng.forward_backward(pos, neg if given_neg else None, K=K, loss_kind=loss, margin=1.0, seed=3, offset=7, opt_kind=ko.OPT_SGD, dropout=p,
+                                   want_scores=True, want_neg=True, force_unfused=unfused)
+        out[unfused] = (float(res["loss"].item()), res["pos_scores"].cpu().numpy(), res["neg_scores"].cpu().numpy(), eng.gE.cpu().numpy().copy(),
+                        eng.gR.cpu().numpy().copy(), eng.tE.cpu().numpy().copy(), eng.tR.cpu().numpy().copy(), res["neg"].cpu().numpy(), eng.launches - l0)
+    f, u = out[False], out[True]
+    assert f[8] == 1 and u[8] > 1                                  # one launch against the unfused sequence
+    np.testing.assert_array_equal(f[7], neg)                       # the in-kernel draw is the oracle's Philox stream
+    assert abs(f[0] - u[0]) <= 2e-6 * max(1.0, abs(u[0]))
+    np.testing.assert_allclose(f[1], u[1], rtol=1e-6, atol=1e-6 * np.abs(u[1]).max())
+    np.testing.assert_allclose(f[2], u[2], rtol=1e-6, atol=1e-6 * np.abs(u[2]).max())
+    gs = max(np.abs(u[3]).max(), np.abs(u[4]).max())
+    np.testing.assert_allclose(f[3], u[3], rtol=1e-4, atol=1e-5 * gs)
+    np.testing.assert_allclose(f[4], u[4], rtol=1e-4, atol=1e-5 * gs)
+    np.testing.assert_array_equal(f[5], u[5])
+    np.testing.assert_array_equal(f[6], u[6])
+    # and against the fp64 oracle (direct correlation)
+    if p == 0.0:
+        t = ko.score_triples(ko.HOLE, E, Rm, pos, 12.0, np.float64, hole_fft=False)
+        fs = ko.score_triples(ko.HOLE, E, Rm, neg, 12.0, np.float64, hole_fft=False)
+        L, dt_, df_ = ko.loss_and_coefs(loss, ko.PAIRED, t, fs, K, 1.0)
+        assert abs(f[0] - L) <= 2e-5 * max(1.0, abs(L))
+        gE1, gR1, _, _ = ko.dense_grads(ko.HOLE, E, Rm, pos, dt_, 12.0)
+        gE2, gR2, _, _ = ko.dense_grads(ko.HOLE, E, Rm, neg, df_, 12.0)
+        np.testing.assert_allclose(f[3][:, :d], gE1 + gE2, rtol=2e-4, atol=2e-5 * gs)
+        np.testing.assert_allclose(f[4][:, :d], gR1 + gR2, rtol=2e-4, atol=2e-5 * gs)
