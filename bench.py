@@ -448,7 +448,7 @@ def main():
                 dms, _ = time_shape()
                 direct = {"ms_per_step": dms, "triples_per_s": sB * (1 + sK) / (dms * 1e-3), "note": "default mode: direct O(d^2) correlation, fp32 sequential contract"}
                 seng.set_hole_mode(True)
-                snote = "64 negatives, pointwize_logistic; unfused score_fwd -> loss -> score_bwd, kgeb_set_hole_mode(KGEB_HOLE_FFT): shared-memory radix-4 FFTs"
+                snote = "64 negatives, pointwize_logistic; kgeb_set_hole_mode(KGEB_HOLE_FFT): one fused kgeb_train_fwd_bwd kernel on shared-memory radix-4 FFTs + the optimizer"
             sms, slaunch = time_shape()
             entry = {"batch_positives": sB, "negatives_per_positive": sK, "ms_per_step": sms, "triples_per_s": sB * (1 + sK) / (sms * 1e-3),
                      "gpu_launches_per_step": slaunch, "note": snote}
