@@ -234,9 +234,10 @@ def filtered_ranks(model, test_data, filtering_triples, group=None):
             part = eng.rank_counts_tc(test_t, code, offs, ids, row_range=rows, mode=tc_mode, packed=packed)
         else:
             part = eng.rank_counts(test_t, code, offs, ids, row_range=rows)
-        counts = merge_partial_counts(part, group)
-        out.append(counts.cpu().numpy().astype(np.int64) + 1)
-    return out[0], out[1]
+        out.append(merge_partial_counts(part, group))
+    # one read-back after BOTH sides are queued: the head side's filter build and launches overlap the tail kernel
+    both = torch.stack(out).cpu().numpy().astype(np.int64) + 1
+    return both[0], both[1]
 
 
 def validate(model, test_data, num_entities, bs, filtering_triples=None):
