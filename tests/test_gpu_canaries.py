@@ -95,3 +95,39 @@ def test_score_and_negatives_outputs_stay_inside():
     assert out.intact() and bool(torch.isfinite(out.view).all())
     neg = eng.negatives(idx, 7, 5, 9)
     assert tuple(neg.shape) == (7 * M, 3) and int(neg[:, [0, 2]].max()) < 517 and int(neg.min()) >= 0
+
+
+@pytest.mark.parametrize("case", ["hole_fft_fused", "hole_fft_unfused", "hole_fft_dropout", "hake", "hake_dropout"])
+def test_fourier_hole_and_hake_write_only_inside_their_buffers(case):
+    """The Fourier-domain HolE kernels (fused step and the score_fwd / score_bwd pair) and the HAKE kernels, on tables whose last
+    row is referenced and with a batch that does not divide the warp ranges."""
+    from KGEkeras._engine import Engine
+    N, R, B, K = 1003, 7, 301, 5
+    rng = np.random.default_rng(4)
+    if case.startswith("hole"):
+        W = 64
+        eng = Engine(ko.HOLE, N, R, W, W, 12.0, E=ko.glorot_uniform(rng, N, W) * 3, R=ko.glorot_uniform(rng, R, W) * 3)
+        eng.set_hole_mode(True)
+        loss = ko.POINTWISE_LOGISTIC
+    else:
+        d = 18
+        eng = Engine(ko.HAKE, N, R, 2 * d, 3 * d, 12.0, E=ko.glorot_uniform(rng, N, 2 * d), R=ko.glorot_uniform(rng, R, 3 * d),
+                     param=ko.hake_params(12.0, 2.0, 2 * d, 0.5, 1.0))
+        loss = ko.PAIRWISE_LOGISTIC
+    eng._ensure_train_buffers(ko.OPT_LAZY_ADAM)
+    g = {"gE": Guarded(tuple(eng.E.shape), torch.float32), "gR": Guarded(tuple(eng.Rel.shape), torch.float32),
+         "tE": Guarded((N,), torch.uint8), "tR": Guarded((R,), torch.uint8)}
+    eng.gE, eng.gR, eng.tE, eng.tR = g["gE"].view, g["gR"].view, g["tE"].view, g["tR"].view
+    st = [Guarded(tuple(eng.E.shape), torch.float32), Guarded(tuple(eng.E.shape), torch.float32),
+          Guarded(tuple(eng.Rel.shape), torch.float32), Guarded(tuple(eng.Rel.shape), torch.float32)]
+    eng.opt_state = (ko.OPT_LAZY_ADAM, st[0].view, st[1].view, st[2].view, st[3].view)
+    pos = np.stack([rng.integers(0, N, B), rng.integers(0, R, B), rng.integers(0, N, B)], 1).astype(np.int32)
+    pos[-1] = [N - 1, R - 1, N - 1]
+    res = eng.train_step(pos, None, opt_kind=ko.OPT_LAZY_ADAM, lr=1e-3, K=K, loss_kind=loss, margin=0.0, seed=3, offset=1, want_scores=True,
+                         want_neg=True, dropout=0.25 if case.endswith("dropout") else 0.0, force_unfused=case == "hole_fft_unfused")
+    torch.cuda.synchronize()
+    assert np.isfinite(float(res["loss"].item()))
+    assert res["neg"].shape == (B * K, 3) and int(res["neg"].max()) < N
+    for name, buf in list(g.items()) + [(f"state{i}", b) for i, b in enumerate(st)]:
+        assert buf.intact(), name
+    assert float(eng.gE.abs().max()) == 0.0 and int(eng.tE.sum()) == 0
