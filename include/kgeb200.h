@@ -12,7 +12,9 @@
  *     synchronising; nothing allocates after kgeb_create;
  *   - return value 0 = ok, negative = kgeb_status; kgeb_last_error() gives the text; nothing throws;
  *   - a context is bound to one device and one model shape; contexts are independent, a single context is
- *     not thread-safe;
+ *     not thread-safe.  It owns a few MB of device scratch (loss partial sums, the sorted chunks of the all-pairs
+ *     hinge loss, the split-K slices of kgeb_sgemm, HAKE's per-row sums): calls on ONE context must therefore be
+ *     ordered on one stream (or by events); use one context per concurrent stream;
  *   - tables are row-major fp32, row stride `ld` floats (ld >= width).  The vectorised kernels need
  *     ld % 4 == 0 and 16-byte aligned base pointers; anything else returns KGEB_ERR_ALIGNMENT (never a slow
  *     silent path);
