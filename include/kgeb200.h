@@ -170,6 +170,21 @@ KGEB_API int kgeb_train_fwd_bwd(kgeb_ctx* ctx, const float* E, const float* R, c
                        int32_t* neg_out, float* gE, float* gR, uint8_t* touchedE, uint8_t* touchedR,
                        kgeb_stream stream);
 
+/* ---- filter sets of validate(), utils.py:201-205 + the per-query list.remove of utils.py:169-171,185-187 -----------------
+ * One sorted, de-duplicated CSR per side: ids[offsets[q] .. offsets[q+1]) = every known-true candidate of query q
+ * (tail: all o with (s_q, p_q, o) in filt; head: all s with (s, p_q, o_q) in filt), ascending -- the layout kgeb_rank_1n /
+ * kgeb_rank_1n_tc take.  Two steps because the caller owns the ids buffer:
+ *   count: packs, radix-sorts and de-duplicates the F filtering triples into `workspace`, writes offsets[0..Q] (offsets[Q] = nnz);
+ *   fill : (after reading nnz and allocating ids) copies the segments; *target_hit |= 1 if some query's own target is in its
+ *          segment (the reference's list.remove raises there: the caller decides).
+ * queries, filt: int32 [.,3] device; offsets int64 [Q+1], ids int32 [nnz], target_hit int32 [1] (zeroed by the caller) device.
+ * workspace: device, kgeb_filter_csr_workspace bytes, untouched between count and fill. */
+KGEB_API int kgeb_filter_csr_workspace(kgeb_ctx* ctx, int64_t Q, int64_t F, int64_t* bytes);
+KGEB_API int kgeb_filter_csr_count(kgeb_ctx* ctx, const int32_t* queries, int64_t Q, const int32_t* filt, int64_t F, int side,
+                          int64_t* offsets, void* workspace, int64_t workspace_bytes, kgeb_stream stream);
+KGEB_API int kgeb_filter_csr_fill(kgeb_ctx* ctx, const int32_t* queries, int64_t Q, int64_t F, int side, const int64_t* offsets,
+                         int32_t* ids, int32_t* target_hit, const void* workspace, kgeb_stream stream);
+
 /* ---- l3_reg, models.py:10-11,79-82: loss[0] += w * sum |P|^3 ; G += 3 w P |P| on EVERY row (dense), all flags set ------ */
 KGEB_API int kgeb_l3_reg(kgeb_ctx* ctx, const float* P, int64_t rows, int width, int ld, float w, float* G,
                          uint8_t* touched, float* loss, kgeb_stream stream);

@@ -56,6 +56,9 @@ PROTOTYPES = {
     "kgeb_set_score_param": (_i, [_p, _f]),
     "kgeb_set_hake_params": (_i, [_p, _f, _f, _f]),
     "kgeb_set_hole_mode": (_i, [_p, _i]),
+    "kgeb_filter_csr_workspace": (_i, [_p, _i64, _i64, _p]),
+    "kgeb_filter_csr_count": (_i, [_p, _p, _i64, _p, _i64, _i, _p, _p, _i64, _p]),
+    "kgeb_filter_csr_fill": (_i, [_p, _p, _i64, _i64, _i, _p, _p, _p, _p, _p]),
     "kgeb_set_dropout": (_i, [_p, _f, _u64, _u64, _i]),
     "kgeb_score_fwd": (_i, [_p, _p, _p, _p, _i64, _p, _p]),
     "kgeb_score_bwd": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p]),

@@ -278,6 +278,32 @@ class Engine:
         self.apply_optimizer(opt_kind, lr, beta1, beta2, eps)
         return res
 
+    # ---- filter sets ----------------------------------------------------------------------------------------------
+    def filter_csr(self, queries, filtering_triples, side):
+        """Sorted, de-duplicated known-true ids per query (utils.py:201-205) in CSR form, built on the device by
+        kgeb_filter_csr_count / kgeb_filter_csr_fill: (offsets int64[Q+1], ids int32[nnz]).  Raises ValueError when a query's own
+        target is in its filter set -- the reference's list.remove crashes there (utils.py:169-171)."""
+        q = as_idx(queries, self.device)
+        f = as_idx(filtering_triples, self.device) if len(filtering_triples) else None
+        Q = q.shape[0]
+        offs = torch.zeros(Q + 1, dtype=torch.int64, device=self.device)
+        if f is None or Q == 0:
+            return offs, torch.zeros(0, dtype=torch.int32, device=self.device)
+        F = f.shape[0]
+        nbytes = C.c_int64()
+        self._check(self.lib.kgeb_filter_csr_workspace(self.ctx, Q, F, C.byref(nbytes)))
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        st = _stream()
+        self._check(self.lib.kgeb_filter_csr_count(self.ctx, _ptr(q), Q, _ptr(f), F, side, _ptr(offs), _ptr(ws), nbytes.value, st))
+        nnz = int(offs[-1].item())
+        ids = torch.empty(nnz, dtype=torch.int32, device=self.device)
+        if nnz:
+            hit = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._check(self.lib.kgeb_filter_csr_fill(self.ctx, _ptr(q), Q, F, side, _ptr(offs), _ptr(ids), _ptr(hit), _ptr(ws), st))
+            if int(hit.item()):
+                raise ValueError("list.remove(x): x not in list")
+        return offs, ids
+
     # ---- 1-N filtered ranking -----------------------------------------------------------------------------------
     def rank_counts(self, triples, side, filt_offsets=None, filt_ids=None, row_range=None, counts=None):
         """int32 partial counts #{c in rows, c not filtered : score > target score} for every query.

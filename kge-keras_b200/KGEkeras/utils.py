@@ -160,8 +160,8 @@ def build_filter_csr(test, filtering_triples, side):
 
 
 def build_filter_csr_device(test_t, filt_t, side):
-    """build_filter_csr on the GPU (index bookkeeping only: one sort of the packed filter keys, two searchsorted, one gather),
-    for validate(): the NumPy builder takes 4-23 ms per side on the bundled datasets, more than the ranking kernels themselves.
+    """build_filter_csr restated with torch index ops on the GPU -- kept as a CHECKER of Engine.filter_csr (the library's own
+    builder, which validate() uses); the NumPy builder takes 4-23 ms per side on the bundled datasets.
     test_t (Q,3) / filt_t (F,3) int64 CUDA tensors -> (offsets int64[Q+1], ids int32[nnz]) on the same device; same ValueError
     as the host builder when a query's own target is in its filter set."""
     import torch
@@ -226,10 +226,10 @@ def filtered_ranks(model, test_data, filtering_triples, group=None):
     tc_mode = abi.TC_BF16 if mode == "bf16" else abi.TC_BF16X3_EXACT
     packed = eng.pack_entities_tc(tc_mode, rows) if use_tc else None   # the table is constant during validate: pack once
     out = []
-    test_t = torch.from_numpy(test).to(eng.device)
-    filt_t = torch.from_numpy(np.asarray(filtering_triples, dtype=np.int64).reshape(-1, 3)).to(eng.device)
+    test_t = torch.from_numpy(test.astype(np.int32)).to(eng.device)
+    filt_t = torch.from_numpy(np.asarray(filtering_triples, dtype=np.int32).reshape(-1, 3)).to(eng.device)
     for side, code in (("tail", abi.SIDE_TAIL), ("head", abi.SIDE_HEAD)):
-        offs, ids = build_filter_csr_device(test_t, filt_t, side)
+        offs, ids = eng.filter_csr(test_t, filt_t, code)     # kgeb_filter_csr_count / _fill
         if use_tc:
             part = eng.rank_counts_tc(test_t, code, offs, ids, row_range=rows, mode=tc_mode, packed=packed)
         else:

@@ -275,3 +275,31 @@ def test_module_level_l3_reg():
     E = m.entity_embedding.get_weights()[0]
     want = 0.01 * float(np.sum(np.abs(E.astype(np.float64)) ** 3))
     assert abs(KGEkeras.l3_reg(m.entity_embedding) - want) <= 2e-6 * want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("side", ["tail", "head"])
+@pytest.mark.parametrize("N,R,F,Q", [(300, 5, 4000, 500), (17, 40, 900, 33), (40943, 11, 93003, 3134), (50, 3, 1, 1)])
+def test_library_filter_csr_equals_host_builder(side, N, R, F, Q):
+    """kgeb_filter_csr_count / _fill (Engine.filter_csr, what validate() uses) against the NumPy builder: duplicates in the
+    filter, relations outnumbering entities, WN18RR-sized inputs, queries without any filter entry, the target-in-filter error."""
+    from KGEkeras import utils as ku, _abi as abi
+    from KGEkeras._engine import Engine
+    rng = np.random.default_rng(N + F)
+    eng = Engine(ko.DISTMULT, N, R, 4, 4)
+    filt = np.stack([rng.integers(0, N, F), rng.integers(0, R, F), rng.integers(0, N, F)], 1).astype(np.int64)
+    filt = np.concatenate([filt, filt[: F // 3]])                       # duplicates
+    test = np.stack([rng.integers(0, N, Q), rng.integers(0, R, Q), rng.integers(0, N, Q)], 1).astype(np.int64)
+    key = lambda a: (a[:, 0] * R + a[:, 1]) * N + a[:, 2]
+    filt = filt[~np.isin(key(filt), key(test))]
+    if len(filt) == 0:
+        filt = np.array([[(test[0, 0] + 1) % N, test[0, 1], test[0, 2]]], dtype=np.int64)
+    code = abi.SIDE_TAIL if side == "tail" else abi.SIDE_HEAD
+    ho, hi = ku.build_filter_csr(test, filt, side)
+    do, di = eng.filter_csr(test, filt, code)
+    np.testing.assert_array_equal(do.cpu().numpy(), ho)
+    np.testing.assert_array_equal(di.cpu().numpy(), hi)
+    with pytest.raises(ValueError):
+        eng.filter_csr(test, np.concatenate([filt, test[:1]]), code)
+    eo, ei = eng.filter_csr(test, np.zeros((0, 3), np.int64), code)
+    assert eo.numel() == Q + 1 and ei.numel() == 0 and int(eo.sum()) == 0
