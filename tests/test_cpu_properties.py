@@ -81,3 +81,49 @@ def test_philox_negatives_range_and_structure(N, K, seed, offset, mode):
     if mode == ko.CORRUPT_EITHER:
         assert np.all((neg[:, 0] == rep[:, 0]) | (neg[:, 2] == rep[:, 2]))      # exactly one slot is redrawn
     np.testing.assert_array_equal(neg, ko.philox_negatives(pos, N, K, seed, offset, mode))   # counter based: reproducible
+
+
+@settings(max_examples=60, deadline=None)
+@given(d=st.integers(1, 9), m=st.integers(2, 12), seed=st.integers(0, 10_000), pw=st.floats(0.1, 2.0), mw=st.floats(0.1, 2.0))
+def test_hake_call_coupling_properties(d, m, seed, pw, mw):
+    """Properties of HAKE as the reference wrote it (models.py:397, norm without axis): within a call every score carries the
+    same modulus term, so score differences are pure phase terms; a sub-call's scores are never below the full call's (its
+    Frobenius norm is over fewer rows); the gradient of sum_i c_i score_i through the modulus term scales with sum_i c_i."""
+    rng = np.random.default_rng(seed)
+    s, o = rng.normal(size=(2, m, 2 * d))
+    p = rng.normal(size=(m, 3 * d))
+    hp = (float(np.pi / 0.35), pw, mw)
+    full = ko.hake_scores(s, p, o, 12.0, *hp)
+    phase_only = ko.hake_scores(s, p, o, 12.0, hp[0], pw, 0.0)
+    np.testing.assert_allclose(full - full[0], phase_only - phase_only[0], rtol=0, atol=1e-9)      # one shared modulus term
+    sub = ko.hake_scores(s[: m // 2 + 1], p[: m // 2 + 1], o[: m // 2 + 1], 12.0, *hp)
+    assert np.all(sub >= full[: m // 2 + 1] - 1e-12)
+    c = rng.normal(size=m)
+    c -= c.mean()                                                                                    # sum c_i = 0 ...
+    gs, gp, go = ko.hake_row_grads(s, p, o, c, 12.0, *hp)
+    g0 = ko.hake_row_grads(s, p, o, c, 12.0, hp[0], pw, 0.0)
+    for a, b in zip((gs, gp, go), g0):                                                               # ... kills the modulus gradient
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-9 * (1 + np.abs(b).max()))
+
+
+@settings(max_examples=40, deadline=None)
+@given(logd=st.integers(1, 6), seed=st.integers(0, 1000))
+def test_hole_fourier_identities_used_by_the_fft_kernels(logd, seed):
+    """The identities hole_fft_kernels.cu relies on, in fp64: one complex FFT of s + i o yields both spectra; the score is
+    (1/d) Re sum conj(P) conj(S) O; ds + i do = F^-1(c conj(P) O + i c P S); dp = Re F^-1(c conj(S) O)."""
+    d = 2 ** logd
+    rng = np.random.default_rng(seed)
+    s, p, o = rng.normal(size=(3, d))
+    c = float(rng.normal())
+    Z = np.fft.fft(s + 1j * o)
+    Zm = np.conj(Z[(-np.arange(d)) % d])
+    S, O, P = (Z + Zm) / 2, -1j * (Z - Zm) / 2, np.fft.fft(p)
+    np.testing.assert_allclose(S, np.fft.fft(s), atol=1e-9)
+    np.testing.assert_allclose(O, np.fft.fft(o), atol=1e-9)
+    score = ko.score(ko.HOLE, s[None], p[None], o[None], hole_fft=False)[0]
+    assert abs(score - np.sum((np.conj(P) * np.conj(S) * O).real) / d) < 1e-9 * (1 + abs(score))
+    ds, dp, do = ko.score_grads(ko.HOLE, s[None], p[None], o[None])
+    g = np.fft.ifft(c * np.conj(P) * O + 1j * c * P * S)
+    np.testing.assert_allclose(g.real, c * ds[0], atol=1e-9 * (1 + np.abs(ds).max()))
+    np.testing.assert_allclose(g.imag, c * do[0], atol=1e-9 * (1 + np.abs(do).max()))
+    np.testing.assert_allclose(np.fft.ifft(c * np.conj(S) * O).real, c * dp[0], atol=1e-9 * (1 + np.abs(dp).max()))
