@@ -100,9 +100,13 @@ KGEB_API int64_t kgeb_launch_count(const kgeb_ctx* ctx);
 KGEB_API int kgeb_num_sms(const kgeb_ctx* ctx);
 /* Measurement aid for bench.py's roofline: with timing on, the library brackets the named kernels with CUDA events on
  * the caller's stream; kgeb_last_kernel_ms waits for the closing event and returns the device time of the last launch. */
-typedef enum { KGEB_TIMED_RANK_TC = 0, KGEB_TIMED_RANK_REFINE = 1, KGEB_TIMED_RANK_TILE = 2, KGEB_TIMED_TRAIN = 3 } kgeb_timed_kernel;
+typedef enum { KGEB_TIMED_RANK_TC = 0, KGEB_TIMED_RANK_REFINE = 1, KGEB_TIMED_RANK_TILE = 2, KGEB_TIMED_TRAIN = 3,
+               KGEB_TIMED_OPT = 4, KGEB_TIMED_AUX = 5 } kgeb_timed_kernel;
 KGEB_API int kgeb_set_kernel_timing(kgeb_ctx* ctx, int on);
 KGEB_API int kgeb_last_kernel_ms(kgeb_ctx* ctx, int which, float* ms);
+/* Sum of the device times of the (up to 64 most recent) launches of that kernel since the previous call, and how many
+ * launches that was; resets the count.  Lets a timed region of several passes report the kernel's average duration. */
+KGEB_API int kgeb_kernel_ms_sum(kgeb_ctx* ctx, int which, float* ms_sum, int* launches);
 
 /* Scalar parameter of the score function besides gamma: pRotatE's modulus (models.py:476, modulus*embedding_range).
  * Default 1; ignored by the other kinds. */

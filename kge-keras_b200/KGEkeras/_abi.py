@@ -21,7 +21,7 @@ CORRUPT_BOTH, CORRUPT_HEAD, CORRUPT_TAIL, CORRUPT_EITHER = range(4)
 SIDE_TAIL, SIDE_HEAD = 0, 1
 TC_BF16, TC_BF16X3_EXACT = 0, 1
 ACT_KINDS = {None: 0, 'linear': 0, 'tanh': 1, 'relu': 2, 'sigmoid': 3}   # Keras activation names served by the literal Dense
-TIMED_RANK_TC, TIMED_RANK_REFINE, TIMED_RANK_TILE, TIMED_TRAIN = range(4)
+TIMED_RANK_TC, TIMED_RANK_REFINE, TIMED_RANK_TILE, TIMED_TRAIN, TIMED_OPT, TIMED_AUX = range(6)
 
 LOSS_KINDS = {  # reference names, utils.py:321-330
     "pointwize_hinge": POINTWISE_HINGE, "pointwize_logistic": POINTWISE_LOGISTIC,
@@ -53,6 +53,7 @@ PROTOTYPES = {
     "kgeb_num_sms": (_i, [_p]),
     "kgeb_set_kernel_timing": (_i, [_p, _i]),
     "kgeb_last_kernel_ms": (_i, [_p, _i, C.POINTER(_f)]),
+    "kgeb_kernel_ms_sum": (_i, [_p, _i, C.POINTER(_f), C.POINTER(_i)]),
     "kgeb_set_score_param": (_i, [_p, _f]),
     "kgeb_set_hake_params": (_i, [_p, _f, _f, _f]),
     "kgeb_set_hole_mode": (_i, [_p, _i]),

@@ -84,7 +84,10 @@ class Engine:
         if init is None:  # GlorotUniform, models.py:87-88
             lim = float(np.sqrt(6.0 / (rows + w)))
             init = rng.uniform(-lim, lim, size=(rows, w)).astype(np.float32)
-        a = torch.as_tensor(np.asarray(init, dtype=np.float32)) if not isinstance(init, torch.Tensor) else init.detach().to(torch.float32).cpu()
+        if isinstance(init, torch.Tensor):      # device tensors are copied on the device (a 2 GB table must not visit the host)
+            a = init.detach().to(torch.float32)
+        else:
+            a = torch.as_tensor(np.asarray(init, dtype=np.float32))
         if tuple(a.shape) != (rows, w):
             raise ValueError(f"initial weights have shape {tuple(a.shape)}, expected {(rows, w)}")
         t = torch.zeros(rows, wk, dtype=torch.float32, device=self.device)
@@ -114,6 +117,12 @@ class Engine:
         ms = C.c_float()
         self._check(self.lib.kgeb_last_kernel_ms(self.ctx, which, C.byref(ms)))
         return float(ms.value)
+
+    def kernel_ms_sum(self, which):
+        """(total ms, launches) of that timed kernel since the previous call (kgeb_kernel_ms_sum)."""
+        ms, n = C.c_float(), C.c_int()
+        self._check(self.lib.kgeb_kernel_ms_sum(self.ctx, which, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
 
     def _ensure_train_buffers(self, opt_kind):
         if self.gE is None:
@@ -390,6 +399,11 @@ class Engine:
         self._keep = (qvec, tscore, tri, fo, fi, ws, packed)
         return out
 
+    def rank_plan(self, triples, filt_tail=None, filt_head=None, row_range=None, mode="exact", group=None, worklist_cap=None,
+                  packed=None):
+        """A reusable filtered-ranking pass over a fixed query set (both sides): see RankPlan."""
+        return RankPlan(self, triples, filt_tail, filt_head, row_range, mode, group, worklist_cap, packed)
+
     # ---- weights ------------------------------------------------------------------------------------------------
     def get_tables(self):
         return self.E[:, :self.we].cpu().numpy(), self.Rel[:, :self.wr].cpu().numpy()
@@ -399,3 +413,140 @@ class Engine:
             self.E[:, :self.we] = torch.as_tensor(np.asarray(E, dtype=np.float32)).to(self.device)
         if R is not None:
             self.Rel[:, :self.wr] = torch.as_tensor(np.asarray(R, dtype=np.float32)).to(self.device)
+
+
+class RankPlan:
+    """One filtered 1-N ranking pass (tail AND head side) over a fixed set of test triples, with everything it needs
+    allocated once: query vectors, target scores, the packed table image, worklists, the [2, Q] count buffer.
+
+    `run()` only enqueues work on the caller's stream -- query prep, target scores, the ranking kernels of both sides, the
+    exact re-scoring -- and, when the entity rows are sharded over a process group, ONE all-reduce of the 2*Q integer
+    partial counts.  No host synchronisation, no allocation, no read-back happens inside a pass; whether a
+    worklist overflowed is read afterwards (`overflowed()`, two 8-byte headers) and `ranks()` repeats the pass with a larger
+    worklist in that (rare) case.  `capture()` records the pass into a CUDA graph, so that the ~14 launches of a small
+    shape cost one graph launch.
+
+    mode: "exact" (tcgen05, integer counts identical to the CUDA-core kernel), "bf16" (tcgen05, approximate),
+          "cuda" (fp32 CUDA-core kernels; the only mode for TransE and the other norm-based kinds)."""
+
+    def __init__(self, eng, triples, filt_tail=None, filt_head=None, row_range=None, mode="exact", group=None, worklist_cap=None,
+                 packed=None):
+        self.eng, self.group = eng, group
+        self.tri = as_idx(triples, eng.device)
+        self.Q = Q = int(self.tri.shape[0])
+        self.r0, self.r1 = (0, eng.N) if row_range is None else (int(row_range[0]), int(row_range[1]))
+        mode = str(mode).lower()
+        if mode not in ("exact", "bf16", "cuda"):
+            raise ValueError(f"rank mode must be 'exact', 'bf16' or 'cuda', got {mode!r}")
+        self.use_tc = mode != "cuda" and eng.tc_supported() and self.r1 > self.r0 and Q > 0
+        self.mode = mode if self.use_tc else "cuda"
+        self.tc_mode = abi.TC_BF16 if mode == "bf16" else abi.TC_BF16X3_EXACT
+        dev = eng.device
+
+        def csr(f):
+            if f is None:
+                return None, None
+            fo = (f[0] if isinstance(f[0], torch.Tensor) else torch.as_tensor(np.asarray(f[0], dtype=np.int64))).to(dev, torch.int64).contiguous()
+            fi = (f[1] if isinstance(f[1], torch.Tensor) else torch.as_tensor(np.asarray(f[1], dtype=np.int32))).to(dev, torch.int32).contiguous()
+            return (None, None) if fi.numel() == 0 else (fo, fi)
+        self.filt = [csr(filt_tail), csr(filt_head)]
+        self.counts = torch.zeros(2, max(Q, 1), dtype=torch.int32, device=dev)
+        self.qvec = [torch.empty(max(Q, 1), eng.lib.kgeb_query_width(eng.ctx, sd), dtype=torch.float32, device=dev) for sd in (0, 1)]
+        self.tscore = [torch.empty(max(Q, 1), dtype=torch.float32, device=dev) for _ in (0, 1)]
+        self.packed = packed
+        self.ws = [None, None]
+        self.cap = 0
+        if self.use_tc:
+            if self.packed is None:
+                self.packed = eng.pack_entities_tc(self.tc_mode, (self.r0, self.r1))
+            cap = int(worklist_cap) if worklist_cap else min(2 ** 31 - 2, max(1 << 20, Q * (64 + (self.r1 - self.r0) // 128)))
+            self._alloc_ws(cap)
+        self.graph = None
+        self.dist_on = False
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.dist_on = torch.distributed.get_world_size(group) > 1
+
+    def _alloc_ws(self, cap):
+        eng = self.eng
+        self.cap = int(cap)
+        nbytes = int(eng.lib.kgeb_rank_tc_workspace_bytes(eng.ctx, self.Q, self.tc_mode, self.cap))
+        if nbytes < 0:
+            eng._check(nbytes)
+        self.ws_bytes = nbytes
+        self.ws = [torch.empty(nbytes, dtype=torch.uint8, device=eng.device) for _ in (0, 1)]
+        self.graph = None
+
+    def _enqueue(self):
+        eng, lib, Q = self.eng, self.eng.lib, self.Q
+        st = _stream()
+        self.counts.zero_()
+        if Q == 0:
+            return
+        e_shard = C.c_void_p(eng.E.data_ptr() + self.r0 * eng.we_k * 4)
+        for sd in (abi.SIDE_TAIL, abi.SIDE_HEAD):
+            qv, ts, (fo, fi), cnt = self.qvec[sd], self.tscore[sd], self.filt[sd], self.counts[sd]
+            eng._check(lib.kgeb_query_prep(eng.ctx, _ptr(eng.E), 0, eng.N, _ptr(eng.Rel), _ptr(self.tri), Q, sd, _ptr(qv), st))
+            eng._check(lib.kgeb_target_scores(eng.ctx, _ptr(eng.E), 0, eng.N, _ptr(qv), _ptr(self.tri), Q, sd, _ptr(ts), st))
+            if self.r1 <= self.r0:
+                continue
+            if self.use_tc:
+                eng._check(lib.kgeb_rank_1n_tc(eng.ctx, e_shard, self.r0, self.r1 - self.r0, _ptr(self.packed), _ptr(qv), _ptr(ts),
+                                               _ptr(self.tri), Q, sd, _ptr(fo), _ptr(fi), self.tc_mode, _ptr(self.ws[sd]), self.ws_bytes,
+                                               self.cap, _ptr(cnt), st))
+            else:
+                eng._check(lib.kgeb_rank_1n(eng.ctx, e_shard, self.r0, self.r1 - self.r0, _ptr(qv), _ptr(ts), _ptr(self.tri), Q, sd,
+                                            _ptr(fo), _ptr(fi), _ptr(cnt), st))
+
+    def capture(self):
+        """Record the device work of one pass (everything but the all-reduce) into a CUDA graph; run() then replays it."""
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._enqueue()          # warm-up outside capture: lazy attribute / module loading must not happen while capturing
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._enqueue()
+        self.graph = g
+        return self
+
+    def run(self):
+        """Enqueue one pass; returns the [2, Q] int32 device counts (tail, head), summed over the shards of `group`."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue()
+        if self.dist_on:
+            torch.distributed.all_reduce(self.counts, group=self.group)
+        return self.counts[:, :self.Q]
+
+    def undecided(self):
+        """(tail, head) number of pairs the last pass sent to the exact re-scoring (host read-back)."""
+        if not self.use_tc:
+            return (0, 0)
+        return tuple(int(self.ws[sd][:4].view(torch.int32)[0].item()) & 0xFFFFFFFF for sd in (0, 1))
+
+    def overflowed(self):
+        return self.use_tc and max(self.undecided()) > self.cap
+
+    def ranks(self):
+        """Run to completion: (tail_ranks, head_ranks) int64 host arrays, rank = 1 + count."""
+        while True:
+            c = self.run()
+            host = c.cpu().numpy()          # synchronises: the headers are final once this returns
+            if not self.use_tc:
+                break
+            und = max(self.undecided())
+            if self.dist_on:                # every rank must take the same branch
+                t = torch.tensor([und > self.cap], dtype=torch.int32, device=self.eng.device)
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=self.group)
+                over = bool(t.item())
+            else:
+                over = und > self.cap
+            if not over:
+                break
+            self._alloc_ws(min(2 ** 31 - 2, max(und + und // 4, 2 * self.cap)))
+        host = host.astype(np.int64) + 1
+        return host[0], host[1]

@@ -98,6 +98,11 @@ class ShardedTrainer:
 
     def __init__(self, kind, num_entities, num_relations, we, wr, gamma=12.0, group=None, seed=0, E=None, R=None):
         from ._engine import Engine
+        if kind not in abi.FUSED_TRAIN_KINDS:
+            # the compact-table engine below carries no per-kind parameters (pRotatE modulus, HAKE weights, HolE mode):
+            # refuse instead of silently scoring with defaults
+            raise ValueError(f"ShardedTrainer serves the fused-step score kinds {abi.FUSED_TRAIN_KINDS} "
+                             f"(DistMult, TransE L1/L2, ComplEx); got kind {kind}")
         self.group = group
         self.world, self.rank = _world(group)
         self.kind, self.N, self.R_, self.we, self.wr, self.gamma = kind, int(num_entities), int(num_relations), int(we), int(wr), float(gamma)
@@ -119,6 +124,7 @@ class ShardedTrainer:
                                        self.shard.we_k, self.shard.wr_k, kind, self.gamma))
         self._sampler = h
         self.compact = None
+        self._shape_checked = None
         self.last = {}
 
     def __del__(self):
@@ -152,6 +158,7 @@ class ShardedTrainer:
             abi.check(self.lib.kgeb_create(C.byref(h), self.device.index or 0, cap, self.R_, sh.we_k, sh.wr_k, sh.we_k, sh.wr_k, self.kind, self.gamma))
             ce.ctx = h
             ce.step = 0
+            ce.hole_fft, ce.param = False, 1.0
             ce._loss = torch.zeros(1, dtype=torch.float32, device=self.device)
             self.compact = ce
         ce = self.compact
@@ -175,6 +182,15 @@ class ShardedTrainer:
         else:
             neg = as_idx(neg, self.device)
             K = neg.shape[0] // pos.shape[0]
+        # every rank's mean is folded into the global mean with weight 1/world: exact only for equal batch shapes
+        if self.world > 1 and self._shape_checked != (pos.shape[0], K):
+            shp = torch.tensor([pos.shape[0], K, -pos.shape[0], -K], dtype=torch.int64, device=self.device)
+            dist.all_reduce(shp, op=dist.ReduceOp.MAX, group=self.group)
+            mx = shp.cpu().tolist()
+            if mx[0] != -mx[2] or mx[1] != -mx[3]:
+                raise ValueError("ShardedTrainer.step needs the same number of positives and negatives on every rank "
+                                 f"(this rank: B={pos.shape[0]}, K={K}; max over ranks B={mx[0]}, K={mx[1]})")
+            self._shape_checked = (pos.shape[0], K)
         plan = ExchangePlan(torch.cat([pos[:, 0], pos[:, 2], neg[:, 0], neg[:, 2]]), self.N, self.group)
         ce = self._compact_engine(plan.U, opt_kind)
         W, st = self.W, _stream()

@@ -222,22 +222,12 @@ def filtered_ranks(model, test_data, filtering_triples, group=None):
     mode = str(getattr(model, "rank_mode", None) or os.environ.get("KGEB_RANK_MODE", "exact")).lower()
     if mode not in ("exact", "bf16", "cuda"):
         raise ValueError(f"rank_mode must be 'exact', 'bf16' or 'cuda', got {mode!r}")
-    use_tc = mode != "cuda" and eng.tc_supported() and rows[1] > rows[0]
-    tc_mode = abi.TC_BF16 if mode == "bf16" else abi.TC_BF16X3_EXACT
-    packed = eng.pack_entities_tc(tc_mode, rows) if use_tc else None   # the table is constant during validate: pack once
-    out = []
     test_t = torch.from_numpy(test.astype(np.int32)).to(eng.device)
     filt_t = torch.from_numpy(np.asarray(filtering_triples, dtype=np.int32).reshape(-1, 3)).to(eng.device)
-    for side, code in (("tail", abi.SIDE_TAIL), ("head", abi.SIDE_HEAD)):
-        offs, ids = eng.filter_csr(test_t, filt_t, code)     # kgeb_filter_csr_count / _fill
-        if use_tc:
-            part = eng.rank_counts_tc(test_t, code, offs, ids, row_range=rows, mode=tc_mode, packed=packed)
-        else:
-            part = eng.rank_counts(test_t, code, offs, ids, row_range=rows)
-        out.append(merge_partial_counts(part, group))
-    # one read-back after BOTH sides are queued: the head side's filter build and launches overlap the tail kernel
-    both = torch.stack(out).cpu().numpy().astype(np.int64) + 1
-    return both[0], both[1]
+    csr = [eng.filter_csr(test_t, filt_t, code) for code in (abi.SIDE_TAIL, abi.SIDE_HEAD)]     # kgeb_filter_csr_count / _fill
+    # one plan = both sides queued back to back, ONE all-reduce of the 2*Q partial counts, one read-back at the end
+    plan = eng.rank_plan(test_t, csr[0], csr[1], row_range=rows, mode=mode, group=group)
+    return plan.ranks()
 
 
 def validate(model, test_data, num_entities, bs, filtering_triples=None):

@@ -62,8 +62,9 @@ extern "C" int kgeb_destroy(kgeb_ctx* ctx) {
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
   if (ctx->d_sort_scratch) cudaFree(ctx->d_sort_scratch);
   for (int i = 0; i < KGEB_TIMED_KERNELS; ++i)
-    for (int j = 0; j < 2; ++j)
-      if (ctx->ev[i][j]) cudaEventDestroy(ctx->ev[i][j]);
+    for (int p = 0; p < KGEB_TIMED_POOL; ++p)
+      for (int j = 0; j < 2; ++j)
+        if (ctx->ev[i][p][j]) cudaEventDestroy(ctx->ev[i][p][j]);
   delete ctx;
   return KGEB_OK;
 }
@@ -76,18 +77,37 @@ extern "C" int kgeb_set_kernel_timing(kgeb_ctx* ctx, int on) {
   if (!ctx) return KGEB_ERR_INVALID;
   if (on) {
     for (int i = 0; i < KGEB_TIMED_KERNELS; ++i)
-      for (int j = 0; j < 2; ++j)
-        if (!ctx->ev[i][j]) KGEB_CUDA_OK(ctx, cudaEventCreate(&ctx->ev[i][j]));
+      for (int p = 0; p < KGEB_TIMED_POOL; ++p)
+        for (int j = 0; j < 2; ++j)
+          if (!ctx->ev[i][p][j]) KGEB_CUDA_OK(ctx, cudaEventCreate(&ctx->ev[i][p][j]));
   }
+  for (int i = 0; i < KGEB_TIMED_KERNELS; ++i) ctx->ev_n[i] = 0;
   ctx->timing = on ? 1 : 0;
   return KGEB_OK;
 }
 
 extern "C" int kgeb_last_kernel_ms(kgeb_ctx* ctx, int which, float* ms) {
   if (!ctx || !ms || which < 0 || which >= KGEB_TIMED_KERNELS) return KGEB_ERR_INVALID;
-  KGEB_REQUIRE(ctx, ctx->ev_valid[which], KGEB_ERR_INVALID, "kernel timing: that kernel has not been launched with timing on");
-  KGEB_CUDA_OK(ctx, cudaEventSynchronize(ctx->ev[which][1]));
-  KGEB_CUDA_OK(ctx, cudaEventElapsedTime(ms, ctx->ev[which][0], ctx->ev[which][1]));
+  KGEB_REQUIRE(ctx, ctx->ev_n[which] > 0, KGEB_ERR_INVALID, "kernel timing: that kernel has not been launched with timing on");
+  const int p = (ctx->ev_n[which] - 1) % KGEB_TIMED_POOL;
+  KGEB_CUDA_OK(ctx, cudaEventSynchronize(ctx->ev[which][p][1]));
+  KGEB_CUDA_OK(ctx, cudaEventElapsedTime(ms, ctx->ev[which][p][0], ctx->ev[which][p][1]));
+  return KGEB_OK;
+}
+
+extern "C" int kgeb_kernel_ms_sum(kgeb_ctx* ctx, int which, float* ms_sum, int* launches) {
+  if (!ctx || !ms_sum || !launches || which < 0 || which >= KGEB_TIMED_KERNELS) return KGEB_ERR_INVALID;
+  const int n = ctx->ev_n[which] < KGEB_TIMED_POOL ? ctx->ev_n[which] : KGEB_TIMED_POOL;   // older launches fell out of the ring
+  float total = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const int p = (ctx->ev_n[which] - 1 - i) % KGEB_TIMED_POOL;
+    float ms = 0.f;
+    KGEB_CUDA_OK(ctx, cudaEventSynchronize(ctx->ev[which][p][1]));
+    KGEB_CUDA_OK(ctx, cudaEventElapsedTime(&ms, ctx->ev[which][p][0], ctx->ev[which][p][1]));
+    total += ms;
+  }
+  *ms_sum = total; *launches = n;
+  ctx->ev_n[which] = 0;
   return KGEB_OK;
 }
 

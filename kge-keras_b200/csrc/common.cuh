@@ -10,7 +10,8 @@
 #define KGEB_WARPS_PER_BLOCK 8
 #define KGEB_THREADS (KGEB_WARPS_PER_BLOCK * 32)
 #define KGEB_MAX_PARTIAL_BLOCKS 4096
-#define KGEB_TIMED_KERNELS 4
+#define KGEB_TIMED_KERNELS 6
+#define KGEB_TIMED_POOL 64   // event pairs kept per timed kernel: kgeb_kernel_ms_sum adds up the launches since its last call
 #define KGEB_SORT_SCRATCH_BYTES (8u << 20)
 
 struct kgeb_ctx {
@@ -39,13 +40,13 @@ struct kgeb_ctx {
   struct { int smem, occ; } ring_cfg[3][2];
   // optional kernel timing (kgeb_set_kernel_timing): events recorded on the caller's stream around selected launches
   int timing;
-  cudaEvent_t ev[KGEB_TIMED_KERNELS][2];
-  bool ev_valid[KGEB_TIMED_KERNELS];
+  cudaEvent_t ev[KGEB_TIMED_KERNELS][KGEB_TIMED_POOL][2];
+  int ev_n[KGEB_TIMED_KERNELS];      // launches bracketed since the last kgeb_kernel_ms_sum (the pool is a ring)
 };
 
 // brackets one launch with events when timing is on (slot = kgeb_timed_kernel)
-#define KGEB_TIME_BEGIN(ctx, slot, st) do { if ((ctx)->timing) cudaEventRecord((ctx)->ev[slot][0], (st)); } while (0)
-#define KGEB_TIME_END(ctx, slot, st) do { if ((ctx)->timing) { cudaEventRecord((ctx)->ev[slot][1], (st)); (ctx)->ev_valid[slot] = true; } } while (0)
+#define KGEB_TIME_BEGIN(ctx, slot, st) do { if ((ctx)->timing) cudaEventRecord((ctx)->ev[slot][(ctx)->ev_n[slot] % KGEB_TIMED_POOL][0], (st)); } while (0)
+#define KGEB_TIME_END(ctx, slot, st) do { if ((ctx)->timing) { cudaEventRecord((ctx)->ev[slot][(ctx)->ev_n[slot] % KGEB_TIMED_POOL][1], (st)); (ctx)->ev_n[slot]++; } } while (0)
 
 extern char g_kgeb_create_err[512];
 

@@ -437,7 +437,9 @@ extern "C" int kgeb_opt_update(kgeb_ctx* ctx, float* P, float* G, uint8_t* touch
   int blocks = 0;
   if (int rc = fill_opt_args(ctx, a, &blocks, P, G, touched, rows, width, ld, state0, state1, opt_kind, lr, beta1, beta2, eps, step)) return rc;
   if (rows == 0) return KGEB_OK;
+  KGEB_TIME_BEGIN(ctx, KGEB_TIMED_OPT, (cudaStream_t)stream);
   k_opt_update<<<blocks, KGEB_THREADS, 0, (cudaStream_t)stream>>>(a);
+  KGEB_TIME_END(ctx, KGEB_TIMED_OPT, (cudaStream_t)stream);
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
 }
@@ -454,7 +456,9 @@ extern "C" int kgeb_opt_update2(kgeb_ctx* ctx, float* P0, float* G0, uint8_t* to
   if (rows1 == 0) a.nblocks[1] = 0;
   const int gx = a.nblocks[0] + a.nblocks[1];
   if (gx == 0) return KGEB_OK;
+  KGEB_TIME_BEGIN(ctx, KGEB_TIMED_OPT, (cudaStream_t)stream);
   k_opt_update2<<<gx, KGEB_THREADS, 0, (cudaStream_t)stream>>>(a);
+  KGEB_TIME_END(ctx, KGEB_TIMED_OPT, (cudaStream_t)stream);
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
 }

@@ -8,10 +8,15 @@
 //
 // Exactness.  A bf16 contraction cannot reproduce the fp32 sequential-k scores of rank_common.cuh bit for bit, so the
 // tensor cores are used as a FILTER with a proven error bound and the few undecided pairs are re-scored exactly:
-//   operands   q = qh + ql + rq,  e = eh + el + re  (bf16 hi/lo split, |rq| <= 2^-18 |q|),  the kernel accumulates
-//              qh.eh + qh.el + ql.eh in fp32 (3 MMAs per k-step on the same staged tiles),
-//   bound      |S~ - S_seqk| <= c_eps * ||q||_2 * ||e_c||_2,  c_eps = 1.05 * (2^-16 + (K + 1 + 2*Kacc) * 2^-24)
-//              (representation + sequential fp32 rounding of the reference arithmetic + tensor-core accumulation),
+//   operands   q = qh + ql + rq,  e = eh + el + re  (bf16 hi/lo split).  bf16 keeps 8 significant bits, so round-to-nearest
+//              has unit roundoff 2^-8: |ql| = |q - qh| <= 2^-8 |q| (the subtraction is exact in fp32) and
+//              |rq| = |(q - qh) - ql| <= 2^-8 |ql| <= 2^-16 |q|, elementwise; the same for e.  The kernel accumulates
+//              qh.eh + qh.el + ql.eh in fp32 (3 MMAs per k-step on the same staged tiles); it DROPS
+//              ql.el + rq.e + (qh+ql).re, each at most (1 + 2^-15) * 2^-16 * sum_k |q_k||e_k| <= ... * ||q||_2 ||e||_2
+//              (Cauchy-Schwarz), i.e. 3 * 2^-16 together (the first build budgeted one such term, not three),
+//   bound      |S~ - S_seqk| <= c_eps * ||q||_2 * ||e_c||_2,  c_eps = 1.05 * (3 * 2^-16 + (K + 1 + 2*Kacc) * 2^-24)
+//              (representation + sequential fp32 rounding of the reference arithmetic + tensor-core accumulation:
+//              every accumulated product may lose one ulp(2^-23) of the running magnitude <= sum_k |terms|),
 //   epilogue   S~ > t + bound  -> counted;   S~ < t - bound -> dropped;   otherwise the pair (q,c) goes to a worklist
 //              that k_seqk_pairs (rank_kernels.cu) re-scores with the exact sequential-k arithmetic.  The bound used per
 //              128-entity slice is the slice's largest ||e||, so a thread compares against two constants.
@@ -561,7 +566,7 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
   }
   if (mode == KGEB_TC_BF16X3_EXACT) {
     const double kacc = 3.0 * nkc * 8;  // products accumulated per score by the tensor cores
-    a.c_eps = (float)(1.05 * (1.0 / 65536.0 + (ctx->we + 1 + 2.0 * kacc) / 16777216.0));
+    a.c_eps = (float)(1.05 * (3.0 / 65536.0 + (ctx->we + 1 + 2.0 * kacc) / 16777216.0));
     a.t_slack = 2.4e-7f;
   } else {
     a.c_eps = 0.f;

@@ -146,6 +146,7 @@ extern "C" int kgeb_train_fwd_bwd(kgeb_ctx* ctx, const float* E, const float* R,
   (void)ctas;
   const bool use_ring = D >= 1 && (a.sc.dp.thr != 0 || !ctx->env_force_reg);  // dropout lives in the ring kernel only
   KGEB_REQUIRE(ctx, use_ring || a.sc.dp.thr == 0, KGEB_ERR_UNSUPPORTED, "dropout needs the ring kernel, whose stages do not fit for this width");
+  KGEB_TIME_BEGIN(ctx, KGEB_TIMED_TRAIN, st);
   if (use_ring) {
     const size_t smem = (size_t)KGEB_WARPS_PER_BLOCK * (3 + SR * D) * RB + (size_t)KGEB_WARPS_PER_BLOCK * (D + 1) * sizeof(uint64_t);
     KGEB_REQUIRE(ctx, smem <= 227 * 1024, KGEB_ERR_UNSUPPORTED, "ring stages do not fit shared memory");
@@ -157,6 +158,7 @@ extern "C" int kgeb_train_fwd_bwd(kgeb_ctx* ctx, const float* E, const float* R,
     if (grid > KGEB_MAX_PARTIAL_BLOCKS) grid = KGEB_MAX_PARTIAL_BLOCKS;
     KGEB_DISPATCH_KIND(ctx->kind, KGEB_DISPATCH_NC(nc, (k_train_fwd_bwd<KIND, NC><<<grid, KGEB_THREADS, 0, st>>>(a))));
   }
+  KGEB_TIME_END(ctx, KGEB_TIMED_TRAIN, st);
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
 }

@@ -100,3 +100,37 @@ def time_eval(kind, E, R, triples, filt_known, gamma, max_queries=64, budget_s=1
             break
     dt = time.perf_counter() - t0
     return dict(queries_per_s=done / dt, queries=done, seconds=dt)
+
+
+def time_eval_dot(kind, E, R, triples, csr_tail, csr_head, max_triples=32, chunk=8, budget_s=20.0):
+    """queries/s of the NumPy restatement of validate for the dot-product models on a BOUNDED sample of test triples, written
+    the way that is kindest to the CPU: the candidate scores of a chunk of queries are ONE BLAS sgemm q.E^T (all host threads;
+    SURVEY Appendix A regrouping of models.py:171-172 / 212-222) instead of the reference's (C+1, 3) gather-multiply-sum per
+    query, then rank = 1 + #{c not filtered, c != target : s_c > s_t} (utils.py:210-215).  csr_* = (offsets, ids) known-true
+    ids per query."""
+    tri = np.asarray(triples)[:max_triples].astype(np.int64)
+    E = np.asarray(E, np.float32)
+    t0 = time.perf_counter()
+    done = 0
+    ranks = []
+    for i in range(0, len(tri), chunk):
+        part = tri[i:i + chunk]
+        for side, (offs, ids) in (("tail", csr_tail), ("head", csr_head)):
+            rows, inv = np.unique(part[:, [0, 2]], return_inverse=True)     # query_vectors copies its table: give it the few rows it reads
+            loc = np.stack([inv.reshape(-1, 2)[:, 0], part[:, 1], inv.reshape(-1, 2)[:, 1]], axis=1)
+            q = ko.query_vectors(kind, E[rows], R, loc, side)
+            sc = q @ E.T
+            for j, (s, p, o) in enumerate(part):
+                tgt = o if side == "tail" else s
+                row = sc[j]
+                t = row[tgt]
+                cnt = int(np.count_nonzero(row > t))
+                fl = np.asarray(ids[offs[i + j]:offs[i + j + 1]], dtype=np.int64)
+                fl = fl[fl != tgt]
+                cnt -= int(np.count_nonzero(row[fl] > t))
+                ranks.append(1 + cnt)
+        done += 2 * len(part)
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return dict(queries_per_s=done / dt, queries=done, seconds=dt, mean_rank=float(np.mean(ranks)))

@@ -1,0 +1,52 @@
+"""CPU checks of the BASELINE-config fixtures (tests/golden/full/): the table expansion is reproducible, the oracle's
+vectorised restatement of validate reproduces the reference's per-query ranks on a sample of every config, and the 15-key
+dict follows from the ranks by the reference's formulas."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import full_fixtures as ff  # noqa: E402
+from oracle import kge_oracle as ko  # noqa: E402
+
+KINDS = {"DistMult": ko.DISTMULT, "TransE_L1": ko.TRANSE_L1, "TransE_L2": ko.TRANSE_L2, "ComplEx": ko.COMPLEX, "HolE": ko.HOLE}
+
+
+@pytest.mark.parametrize("name", sorted(ff.CONFIGS))
+def test_fixture_is_complete_and_oracle_reproduces_reference_ranks(name):
+    assert ff.available(name), f"fixture tests/golden/full/{name}.npz missing (run tests/golden/make_golden_full.py)"
+    fx = ff.load(name)
+    meta = fx["meta"]
+    ds = ff.load_dataset(meta["dataset"])
+    assert len(fx["tail_ranks"]) == len(ds["test"]) == meta["ntest"] and len(fx["head_ranks"]) == meta["ntest"]
+    assert fx["E"].dtype == np.float32 and fx["E"].shape[0] == meta["N"]
+    assert hashlib.sha256(np.ascontiguousarray(fx["E"]).tobytes()).hexdigest() == meta["E_sha256"]
+    # the 15-key dict is a function of the ranks (utils.py:216-262)
+    want = ko.metrics_from_ranks(fx["tail_ranks"], fx["head_ranks"])
+    for k, v in meta["metrics_f64"].items():
+        assert want[k] == v, k
+    # the oracle on a sample of the test split == what the reference's validate recorded for those queries
+    kind = KINDS[meta["kind"]]
+    filt = np.concatenate([ds[sp] for sp in meta.get("filter_splits", ("train", "valid"))], axis=0)
+    fh, ft = ko.build_filters([tuple(int(x) for x in r) for r in filt])
+    n = len(ds["test"])
+    sample = np.unique(np.linspace(0, n - 1, 24 if meta["N"] > 5000 else 100).astype(np.int64))
+    part = ds["test"][sample]
+    for side, gold, f in (("tail", fx["tail_ranks"], ft), ("head", fx["head_ranks"], fh)):
+        sc = ko.seqk_scores(kind, ko.query_vectors(kind, fx["E"], fx["R"], part, side), fx["E"], side, meta["gamma"])
+        np.testing.assert_array_equal(ko.ranks_from_scores(sc, part, side, f), gold[sample])
+
+
+def test_trained_tables_rank_far_better_than_chance():
+    """The fixtures' tables are trained: their filtered MRR is far above the ~(ln N + 0.58)/N of random scores."""
+    for name in sorted(ff.CONFIGS):
+        if not ff.available(name):
+            continue
+        meta = ff.load(name)["meta"]
+        if meta["gamma"] <= 0:      # distance scores ranked as if higher were better (models.py:189-190): trained, but upside down
+            continue
+        chance = (np.log(meta["N"]) + 0.58) / meta["N"]
+        assert meta["metrics_f64"]["mrr"] > 2 * chance, (name, meta["metrics_f64"]["mrr"], chance)

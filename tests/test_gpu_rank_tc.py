@@ -120,3 +120,29 @@ def test_tc_rejects_transe():
     eng, E, Rm = make_engine(ko.TRANSE_L1, 100, 3, 8)
     with pytest.raises(abi.KgebError):
         eng.pack_entities_tc(abi.TC_BF16)
+
+
+@pytest.mark.parametrize("width", [64, 200])
+def test_tc_exact_adversarial_split_residuals(width):
+    """Rows built so that the bf16 hi/lo split leaves its LARGEST residuals and every dropped product has the same sign
+    (all entries positive, ql ~ 2^-8 q, el ~ 2^-8 e): the dropped terms ql.el + rq.e + q.re then add up coherently to ~3 * 2^-16
+    of ||q|| ||e|| -- the case the representation term of c_eps has to cover.  Candidate scores are spread from far inside
+    to a few bands outside the target's band, so every decision class (counted / dropped / undecided) occurs."""
+    abi = _abi()
+    from KGEkeras._engine import Engine
+    N, R, Q = 1024, 2, 128
+    rng = np.random.default_rng(width)
+    base = np.float32(1.0 + 2.0 ** -8 - 2.0 ** -16)            # rounds DOWN to bf16 1.0: lo plane ~ 2^-8, residual ~ 2^-16
+    steps = (rng.integers(-600, 600, size=(N, 1)) * np.float32(2.0 ** -21)).astype(np.float32)   # row scale 1 + j*2^-21: up to ~18 * 2^-16
+    wobble = (rng.integers(0, 4, size=(N, width)) * np.float32(2.0 ** -23)).astype(np.float32)
+    E = (base * (np.float32(1.0) + steps) + wobble).astype(np.float32)
+    Rm = np.ones((R, width), np.float32)
+    eng = Engine(abi.DISTMULT, N, R, width, width, 12.0, E=E, R=Rm)
+    tri = rand_triples(rng, Q, N, R)
+    want = eng.rank_counts(tri, 0).cpu().numpy()
+    stats = {}
+    got = eng.rank_counts_tc(tri, 0, mode=abi.TC_BF16X3_EXACT, stats=stats).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+    sc = ko.seqk_scores(ko.DISTMULT, ko.query_vectors(ko.DISTMULT, E, Rm, tri, "tail"), E, "tail", 12.0)
+    np.testing.assert_array_equal(got, (ko.ranks_from_scores(sc, tri, "tail", {}) - 1).astype(np.int32))
+    assert 0 < stats["undecided_pairs"] < Q * N     # some pairs are decided by the tensor cores, some are not
