@@ -127,6 +127,10 @@ KGEB_API int kgeb_set_hole_mode(kgeb_ctx* ctx, int mode);
  * func(); kgeb_score_bwd therefore expects the same idx (and dropout state) as the forward call it differentiates.
  * No fused training kernel and no 1-N ranking (a candidate's score would depend on its batch).  m <= 2 M rows per call. */
 KGEB_API int kgeb_set_hake_params(kgeb_ctx* ctx, float phase_scale, float phase_weight, float mod_weight);
+/* HAKE inference as Keras runs it: Model.predict scores its input in consecutive batches of `rows` triples (batch_size,
+ * default 32), each batch its own call of func() with its own norm (models.py:397).  rows = 0 (default): the whole
+ * kgeb_score_fwd call is one batch.  Forward only. */
+KGEB_API int kgeb_set_hake_call_rows(kgeb_ctx* ctx, int64_t rows);
 
 /* ---- dropout, models.py:122,144-150: Dropout(dp) on each gathered s / p / o row while training ----------------------
  * p > 0 arms it for the following score_fwd / score_bwd / train_fwd_bwd calls of this context (p = 0 disarms: predict,
@@ -161,6 +165,16 @@ KGEB_API int kgeb_oversample(kgeb_ctx* ctx, const int32_t* src, int64_t n, int64
 KGEB_API int kgeb_loss_fwd_bwd(kgeb_ctx* ctx, const float* t, int64_t B, const float* f, int64_t Bf, int K, int loss_kind,
                       int pair_mode, float margin, float loss_weight, float* loss, float* dt, float* df,
                       kgeb_stream stream);
+
+/* ---- sort-segmented entity backward (K2) --------------------------------------------------------------------
+ * With a workspace armed, kgeb_train_fwd_bwd forms the ENTITY gradient rows by sorting (entity id, reference) records
+ * (CUB radix sort on the id bits, stable) and adding each segment in registers -- one plain read-modify-write per
+ * touched row, a reproducible summation order -- instead of one vector reduction per row reference.  Relation rows
+ * (few rows, thousands of references each) keep the in-register group sums.  Replaces the IndexedSlices de-duplication
+ * the reference's optimizer performs (tests.py:86, `adam` on embedding gradients).  workspace == NULL disarms it.
+ * Not available together with dropout (the masks are not regenerated in the segment kernel). */
+KGEB_API int64_t kgeb_sortseg_workspace_bytes(const kgeb_ctx* ctx, int64_t B, int K);
+KGEB_API int kgeb_set_grad_sortseg(kgeb_ctx* ctx, void* workspace, int64_t workspace_bytes);
 
 /* ---- fused train step forward + gradient (K1): gather, negatives, score, loss, gradient scatter ----------- */
 /* One pass over B positives, each with K negatives: negatives come from `neg` ([B*K,3], index-driven parity
@@ -218,6 +232,11 @@ KGEB_API int kgeb_query_prep(kgeb_ctx* ctx, const float* E_shard, int64_t row_of
  * (so a candidate that ties the target is never counted).  Written only for targets inside the shard. */
 KGEB_API int kgeb_target_scores(kgeb_ctx* ctx, const float* E_shard, int64_t row_offset, int64_t n_rows, const float* qvec,
                        const int32_t* triples, int64_t Q, int side, float* tscore, kgeb_stream stream);
+/* count[0] += #{i != target : scores[i] > scores[target]} -- the rank of a score vector that came from a model the library
+ * does not score itself (validate() driven through a foreign model's predict, utils.py:211-215: rankdata(res,'max') with the
+ * target in row 0 gives rank = 1 + that count; ties are not counted). */
+KGEB_API int kgeb_count_greater(kgeb_ctx* ctx, const float* scores, int64_t n, int64_t target, int32_t* count, kgeb_stream stream);
+
 /* counts[q] += #{c in shard, c not in filter(q), c != target(q) : score(q,c) > tscore[q]}   (rank = 1 + sum over
  * shards).  filt_offsets int64[Q+1] / filt_ids int32[nnz] = CSR of known-true ids per query (may be
  * NULL/NULL).  Integer partial counts: summing them over any row partition gives bit-identical ranks. */

@@ -56,6 +56,7 @@ PROTOTYPES = {
     "kgeb_kernel_ms_sum": (_i, [_p, _i, C.POINTER(_f), C.POINTER(_i)]),
     "kgeb_set_score_param": (_i, [_p, _f]),
     "kgeb_set_hake_params": (_i, [_p, _f, _f, _f]),
+    "kgeb_set_hake_call_rows": (_i, [_p, _i64]),
     "kgeb_set_hole_mode": (_i, [_p, _i]),
     "kgeb_filter_csr_workspace": (_i, [_p, _i64, _i64, _p]),
     "kgeb_filter_csr_count": (_i, [_p, _p, _i64, _p, _i64, _i, _p, _p, _i64, _p]),
@@ -67,6 +68,8 @@ PROTOTYPES = {
     "kgeb_oversample": (_i, [_p, _p, _i64, _i64, _u64, _u64, _i, _p, _p]),
     "kgeb_loss_fwd_bwd": (_i, [_p, _p, _i64, _p, _i64, _i, _i, _i, _f, _f, _p, _p, _p, _p]),
     "kgeb_train_fwd_bwd": (_i, [_p, _p, _p, _p, _i64, _p, _i, _i, _f, _f, _i, _u64, _u64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "kgeb_sortseg_workspace_bytes": (_i64, [_p, _i64, _i]),
+    "kgeb_set_grad_sortseg": (_i, [_p, _p, _i64]),
     "kgeb_l3_reg": (_i, [_p, _p, _i64, _i, _i, _f, _p, _p, _p, _p]),
     "kgeb_opt_update": (_i, [_p, _p, _p, _p, _i64, _i, _i, _p, _p, _i, _f, _f, _f, _f, _i64, _p]),
     "kgeb_opt_update2": (_i, [_p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _i, _f, _f, _f, _f, _i64, _p]),
@@ -74,6 +77,7 @@ PROTOTYPES = {
     "kgeb_query_prep": (_i, [_p, _p, _i64, _i64, _p, _p, _i64, _i, _p, _p]),
     "kgeb_target_scores": (_i, [_p, _p, _i64, _i64, _p, _p, _i64, _i, _p, _p]),
     "kgeb_rank_1n": (_i, [_p, _p, _i64, _i64, _p, _p, _p, _i64, _i, _p, _p, _p, _p]),
+    "kgeb_count_greater": (_i, [_p, _p, _i64, _i64, _p, _p]),
     "kgeb_rows_gather": (_i, [_p, _p, _i, _i, _p, _i64, _p, _p]),
     "kgeb_rows_scatter_add": (_i, [_p, _p, _i, _i, _p, _p, _i64, _p, _p]),
     "kgeb_rows_concat": (_i, [_p, _p, _i, _i, _p, _i, _i, _p, _i64, _p, _i, _p]),

@@ -75,6 +75,7 @@ class Engine:
             if self.param != 1.0:
                 self._check(self.lib.kgeb_set_score_param(self.ctx, self.param))
         self.hole_fft = False
+        self.grad_mode, self._ss_ws = "red", None
         self.gE = self.gR = self.tE = self.tR = None
         self.opt_state = None
         self.step = 0
@@ -143,6 +144,25 @@ class Engine:
         """HolE through the Fourier domain (the reference's own formulation) for power-of-two widths; default = direct O(d^2)."""
         self._check(self.lib.kgeb_set_hole_mode(self.ctx, abi.HOLE_FFT if fft else abi.HOLE_DIRECT))
         self.hole_fft = bool(fft)
+
+    def set_grad_mode(self, mode="red"):
+        """'red' (default): every row reference adds its gradient row with a 128-bit vector reduction.  'sortseg': the entity
+        gradient rows are sort-segmented by entity id and added once per touched row in a reproducible order (kgeb_set_grad_sortseg;
+        fused-step kinds, no dropout)."""
+        if mode not in ("red", "sortseg"):
+            raise ValueError(f"grad mode must be 'red' or 'sortseg', got {mode!r}")
+        self.grad_mode = mode
+        if mode == "red":
+            self._check(self.lib.kgeb_set_grad_sortseg(self.ctx, None, 0))
+            self._ss_ws = None
+
+    def _arm_sortseg(self, B, K):
+        need = int(self.lib.kgeb_sortseg_workspace_bytes(self.ctx, B, K))
+        if need < 0:
+            self._check(need)
+        if self._ss_ws is None or self._ss_ws.numel() < need:
+            self._ss_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._check(self.lib.kgeb_set_grad_sortseg(self.ctx, _ptr(self._ss_ws), self._ss_ws.numel()))
 
     # ---- dropout ------------------------------------------------------------------------------------------------
     def set_dropout(self, p=0.0, seed=0, offset=0, stream_id=0):
@@ -239,6 +259,8 @@ class Engine:
             no = torch.empty(B * K, 3, dtype=torch.int32, device=self.device) if (want_neg and neg is None) else None
             if dropout:
                 self.set_dropout(dropout, seed, offset, 0)
+            if self.grad_mode == "sortseg" and self.kind in abi.FUSED_TRAIN_KINDS:
+                self._arm_sortseg(B, K)
             try:
                 self._check(self.lib.kgeb_train_fwd_bwd(
                     self.ctx, _ptr(self.E), _ptr(self.Rel), _ptr(pos), B, _ptr(neg), K, loss_kind, margin, loss_weight,

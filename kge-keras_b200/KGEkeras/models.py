@@ -466,6 +466,18 @@ class HAKE(EmbeddingModel):
     def _param_(self):
         return (float(self.pi / self.embedding_range), float(self.phase_weight), float(self.mod_weight))
 
+    def predict(self, x, batch_size=32, verbose=0, **kwargs):
+        """Keras Model.predict scores its input in consecutive batches of `batch_size` rows (default 32) and every batch is its
+        own call of func(): the axis-less norm of models.py:397 therefore couples the rows of ONE batch, and HAKE's predictions
+        -- hence the ranks the reference's validate derives from them (utils.py:211) -- depend on the batching.  Reproduced
+        here by kgeb_set_hake_call_rows: one launch, one norm per group of batch_size rows (batch_size=None: one group)."""
+        eng = self._eval_engine_()
+        eng._check(eng.lib.kgeb_set_hake_call_rows(eng.ctx, int(batch_size) if batch_size else 0))
+        try:
+            return eng.score(x).cpu().numpy()
+        finally:
+            eng._check(eng.lib.kgeb_set_hake_call_rows(eng.ctx, 0))
+
 
 class RotatE(EmbeddingModel):
     _score_kind = abi.ROTATE   # models.py:439-459; needs e_dim == r_dim as passed (entity rows 2d, d relation phases)

@@ -230,15 +230,57 @@ def filtered_ranks(model, test_data, filtering_triples, group=None):
     return plan.ranks()
 
 
+def predict_ranks(model, test_data, num_entities, filtering_triples):
+    """(tail_ranks, head_ranks) for ANY object with a Keras-style `.predict((n,3)) -> (n,)`, the way the reference drives it
+    (utils.py:207-245): per test triple the (C+1,3) candidate array of gen_tail_data / gen_head_data (target in row 0) goes
+    through `model.predict` in ONE call, exactly as the reference passes it -- a model whose predictions depend on the call's
+    batching (HAKE, models.py:397) therefore ranks as it does there.  The scores are ranked on the GPU (kgeb_count_greater:
+    rankdata(res,'max') with the target in row 0 == 1 + #{res > res[0]}); one read-back at the end."""
+    import ctypes as C
+    import torch
+    from collections import defaultdict
+    from . import _engine as E_
+    eng = model._eval_engine_() if hasattr(model, "_eval_engine_") else _loss_eng()
+    filter_h, filter_t = defaultdict(set), defaultdict(set)
+    for s, p, o in filtering_triples:          # utils.py:201-205
+        filter_h[(int(p), int(o))].add(int(s))
+        filter_t[(int(s), int(p))].add(int(o))
+    test = [(int(s), int(p), int(o)) for s, p, o in np.asarray(test_data).reshape(-1, 3)]
+    Q = len(test)
+    counts = torch.zeros(2, max(Q, 1), dtype=torch.int32, device=eng.device)
+    keep = []
+    for side, gen in ((0, gen_tail_data(test, num_entities, None, filter_t)), (1, gen_head_data(test, num_entities, None, filter_h))):
+        for qi, cand in enumerate(gen):
+            res = np.ascontiguousarray(np.asarray(model.predict(cand), dtype=np.float32).reshape(-1))
+            if res.shape[0] != cand.shape[0]:
+                raise ValueError(f"predict returned {res.shape[0]} scores for {cand.shape[0]} candidate triples")
+            sc = torch.from_numpy(res).to(eng.device, non_blocking=True)
+            eng._check(eng.lib.kgeb_count_greater(eng.ctx, C.c_void_p(sc.data_ptr()), sc.numel(), 0,
+                                                  C.c_void_p(counts[side, qi:].data_ptr()), E_._stream()))
+            keep.append(sc)
+            if len(keep) >= 256:               # the copies are asynchronous: hold the buffers until the stream has used them
+                torch.cuda.current_stream().synchronize()
+                keep.clear()
+    host = counts[:, :Q].cpu().numpy().astype(np.int64) + 1
+    return host[0], host[1]
+
+
 def validate(model, test_data, num_entities, bs, filtering_triples=None):
     """utils.py:199-264: filtered Hits@1/3/10, MR, MRR for tail and head prediction and their means, as the reference's
-    15-key dict.  `filtering_triples=None` raises TypeError like the reference; `bs` is unused there and here."""
+    15-key dict.  `filtering_triples=None` raises TypeError like the reference; `bs` is unused there and here.
+    A KGEkeras model with a 1-N ranking kernel is ranked by it (every candidate of every query in one pass); any other
+    object with `.predict` -- a foreign model, or HAKE, whose scores depend on predict's batching -- is driven exactly like
+    the reference drives it (predict_ranks)."""
     if filtering_triples is None:
         raise TypeError("'NoneType' object is not iterable")
-    if not hasattr(model, "_engine_"):
-        raise TypeError("validate() needs a KGEkeras EmbeddingModel backed by libkgeb200 (no CPU path)")
     n = float(len(test_data))
-    tail_ranks, head_ranks = filtered_ranks(model, test_data, filtering_triples)
+    fast = hasattr(model, "_engine_") and getattr(model, "_score_kind", None) != abi.HAKE
+    if fast:
+        tail_ranks, head_ranks = filtered_ranks(model, test_data, filtering_triples)
+    elif hasattr(model, "predict"):
+        tail_ranks, head_ranks = predict_ranks(model, test_data, num_entities, filtering_triples)
+    else:
+        raise AttributeError(f"{type(model).__name__!r} object has no attribute 'predict'")   # what utils.py:211 would raise
 
     def side(r):
         return (np.count_nonzero(r <= 1) / n, np.count_nonzero(r <= 3) / n, np.count_nonzero(r <= 10) / n,

@@ -126,6 +126,13 @@ extern "C" int kgeb_set_hake_params(kgeb_ctx* ctx, float phase_scale, float phas
   return KGEB_OK;
 }
 
+extern "C" int kgeb_set_hake_call_rows(kgeb_ctx* ctx, int64_t rows) {
+  if (!ctx) return KGEB_ERR_INVALID;
+  KGEB_REQUIRE(ctx, ctx->kind == KGEB_HAKE && rows >= 0, KGEB_ERR_INVALID, "set_hake_call_rows: HAKE context and rows >= 0 expected");
+  ctx->hake_group = rows;
+  return KGEB_OK;
+}
+
 extern "C" int kgeb_set_score_param(kgeb_ctx* ctx, float param) {
   if (!ctx) return KGEB_ERR_INVALID;
   ctx->param = param;

@@ -23,6 +23,7 @@ struct kgeb_ctx {
   float param;   // pRotatE modulus (kgeb_set_score_param), 1 otherwise
   int hole_fft;  // kgeb_set_hole_mode: HolE through the Fourier domain for power-of-two widths
   float hake_ps, hake_pw, hake_mw;   // HAKE: pi / embedding_range, phase_weight, mod_weight (kgeb_set_hake_params)
+  int64_t hake_group;                // HAKE inference: rows per Model.predict batch (kgeb_set_hake_call_rows), 0 = the whole call is one batch
   int num_sms;
   int64_t launches;
   char err[512];
@@ -42,6 +43,8 @@ struct kgeb_ctx {
   int timing;
   cudaEvent_t ev[KGEB_TIMED_KERNELS][KGEB_TIMED_POOL][2];
   int ev_n[KGEB_TIMED_KERNELS];      // launches bracketed since the last kgeb_kernel_ms_sum (the pool is a ring)
+  // sort-segmented entity backward (kgeb_set_grad_sortseg): caller-owned workspace, NULL = vector-reduction path
+  unsigned char* ss_ws; int64_t ss_bytes;
 };
 
 // brackets one launch with events when timing is on (slot = kgeb_timed_kernel)
@@ -81,6 +84,10 @@ int kgeb_internal_hole_fft_bwd(kgeb_ctx* ctx, const float* E, const float* R, co
 int kgeb_internal_hole_fft_train(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* pos, int64_t B, const int32_t* neg, int K, int loss_kind,
                                  float margin, float loss_weight, int corrupt_mode, uint64_t seed, uint64_t offset, float* loss, float* pos_scores,
                                  float* neg_scores, int32_t* neg_out, float* gE, float* gR, uint8_t* tE, uint8_t* tR, cudaStream_t st);
+// sort-segmented entity backward (sortseg_kernels.cu), driven by kgeb_train_fwd_bwd when a workspace is armed
+int kgeb_internal_sortseg_carve(kgeb_ctx* ctx, int64_t B, int K, float** coef, int32_t** negbuf);
+int kgeb_internal_sortseg_entities(kgeb_ctx* ctx, const void* score_args, int nc, const int32_t* pos, const int32_t* neg, int64_t B, int K,
+                                   float* gE, cudaStream_t st);
 // HAKE's batch-coupled score (hake_kernels.cu), reached through kgeb_score_fwd / kgeb_score_bwd
 int kgeb_internal_hake_fwd(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* idx, int64_t m, float* scores, cudaStream_t st);
 int kgeb_internal_hake_bwd(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* idx, int64_t m, const float* dscore, float* gE, float* gR,

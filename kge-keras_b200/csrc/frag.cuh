@@ -269,6 +269,10 @@ struct TrainArgs {
   float* loss; float* pos_scores; float* neg_scores; int32_t* neg_out;
   float* gE; float* gR; uint8_t* tE; uint8_t* tR;
   double* partials; unsigned int* ticket;
+  // sort-segmented entity backward (sortseg_kernels.cu): when set, the kernel writes dL/dscore of every scored triple
+  // (coef_out[g] for positive g, coef_out[B + g*K + j] for its negative j) and leaves the ENTITY gradient rows to the
+  // segment kernel; relation gradients keep the in-register group sum + one vector reduction per group
+  float* coef_out;
 };
 
 // ---------------------------------------------------------------------------------------------------

@@ -103,6 +103,19 @@ __global__ void __launch_bounds__(1024) k_hake_finish(const float* __restrict__ 
   }
 }
 
+// inference through Keras' Model.predict scores the input in consecutive batches (batch_size, default 32), and every batch is
+// its own call of func(): one norm per GROUP of `group` consecutive rows (the last group may be short).  One thread per group.
+__global__ void k_hake_finish_groups(const float* __restrict__ rsq, int64_t m, int64_t group, float mw, float* __restrict__ scores) {
+  const int64_t ng = (m + group - 1) / group;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i0 = g * group, i1 = i0 + group < m ? i0 + group : m;
+    double t = 0.0;
+    for (int64_t i = i0; i < i1; ++i) t += (double)rsq[i];
+    const float r = (float)((double)mw * sqrt(t));
+    for (int64_t i = i0; i < i1; ++i) scores[i] = __fsub_rn(scores[i], r);
+  }
+}
+
 __device__ __forceinline__ float sgn(float x) { return (float)((x > 0.f) - (x < 0.f)); }
 __device__ __forceinline__ void add_nz(float* p, float v) { if (v != 0.f) atomicAdd(p, v); }
 
@@ -166,7 +179,12 @@ int kgeb_internal_hake_fwd(kgeb_ctx* ctx, const float* E, const float* R, const 
   if (a.dp.thr) k_hake_rows<true><<<grid, KGEB_THREADS, 0, st>>>(a, idx, m, scores, rsq);
   else k_hake_rows<false><<<grid, KGEB_THREADS, 0, st>>>(a, idx, m, scores, rsq);
   KGEB_LAUNCH_OK(ctx);
-  k_hake_finish<<<1, 1024, 0, st>>>(rsq, nullptr, m, a.mw, scores, tc);
+  if (ctx->hake_group > 0 && ctx->hake_group < m) {
+    const int64_t ng = (m + ctx->hake_group - 1) / ctx->hake_group;
+    k_hake_finish_groups<<<(int)((ng + 127) / 128 < 1024 ? (ng + 127) / 128 : 1024), 128, 0, st>>>(rsq, m, ctx->hake_group, a.mw, scores);
+  } else {
+    k_hake_finish<<<1, 1024, 0, st>>>(rsq, nullptr, m, a.mw, scores, tc);
+  }
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
 }
@@ -175,6 +193,7 @@ int kgeb_internal_hake_bwd(kgeb_ctx* ctx, const float* E, const float* R, const 
                            uint8_t* tE, uint8_t* tR, cudaStream_t st) {
   HakeArgs a;
   if (int rc = hake_args(ctx, E, R, m, &a)) return rc;
+  KGEB_REQUIRE(ctx, ctx->hake_group == 0, KGEB_ERR_UNSUPPORTED, "HAKE backward: kgeb_set_hake_call_rows() is an inference setting (Model.predict batches); reset it to 0");
   double* tc = reinterpret_cast<double*>(ctx->d_sort_scratch);
   float* rsq = reinterpret_cast<float*>(ctx->d_sort_scratch + 16);
   const int grid = grid_for(ctx, m, 8);

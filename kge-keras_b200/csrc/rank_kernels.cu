@@ -514,3 +514,24 @@ int kgeb_internal_refine_worklist(kgeb_ctx* ctx, const float* E_shard, int64_t n
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
 }
+
+// ---- ranking of scores that came from somewhere else (validate() driven by a foreign model's predict) ---------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_count_greater(const float* __restrict__ scores, int64_t n, int64_t target, int32_t* __restrict__ count) {
+  const float t = __ldg(scores + target);
+  int c = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    c += (i != target && __ldg(scores + i) > t) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c != 0) atomicAdd(count, c);
+}
+}  // namespace
+
+extern "C" int kgeb_count_greater(kgeb_ctx* ctx, const float* scores, int64_t n, int64_t target, int32_t* count, kgeb_stream stream) {
+  if (!ctx) return KGEB_ERR_INVALID;
+  KGEB_REQUIRE(ctx, scores && count && n > 0 && target >= 0 && target < n, KGEB_ERR_INVALID, "count_greater: bad arguments");
+  k_count_greater<<<grid1d(ctx, n, 256), 256, 0, (cudaStream_t)stream>>>(scores, n, target, count);
+  KGEB_LAUNCH_OK(ctx);
+  return KGEB_OK;
+}

@@ -128,7 +128,15 @@ extern "C" int kgeb_train_fwd_bwd(kgeb_ctx* ctx, const float* E, const float* R,
   a.corrupt_mode = corrupt_mode; a.seed = seed; a.offset = offset; a.N = (uint32_t)ctx->N;
   a.loss = loss; a.pos_scores = pos_scores; a.neg_scores = neg_scores; a.neg_out = neg_out;
   a.gE = gE; a.gR = gR; a.tE = touchedE; a.tR = touchedR; a.partials = ctx->d_partials; a.ticket = ctx->d_ticket;
+  a.coef_out = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
+  const bool sortseg = ctx->ss_ws != nullptr;   // kgeb_set_grad_sortseg: entity gradient rows by sort + segment instead of vector reductions
+  if (sortseg) {
+    KGEB_REQUIRE(ctx, a.sc.dp.thr == 0, KGEB_ERR_UNSUPPORTED, "the sort-segmented backward does not regenerate dropout masks: use the reduction path with dropout");
+    int32_t* negbuf = nullptr;
+    if (int rc = kgeb_internal_sortseg_carve(ctx, B, K, &a.coef_out, &negbuf)) return rc;
+    if (!neg && !neg_out) a.neg_out = negbuf;   // the kernel's Philox ids are the segment kernel's input
+  }
   // shared-memory ring version: per warp the positive's 3 rows + D stages of SR rows; as many CTAs/SM as fit (<= 3)
   const int RB = ctx->we * (int)sizeof(float);
   const int mode = neg ? 0 : (corrupt_mode == KGEB_CORRUPT_BOTH ? 1 : 2);
@@ -144,9 +152,9 @@ extern "C" int kgeb_train_fwd_bwd(kgeb_ctx* ctx, const float* E, const float* R,
   if (ctx->env_ring_ctas > 0) { ctas = ctx->env_ring_ctas; D = stages_for(sm_budget / ctas - 1024); if (D > 8) D = 8; }
   if (ctx->env_ring_d > 0) D = ctx->env_ring_d;
   (void)ctas;
-  const bool use_ring = D >= 1 && (a.sc.dp.thr != 0 || !ctx->env_force_reg);  // dropout lives in the ring kernel only
+  const bool use_ring = D >= 1 && (a.sc.dp.thr != 0 || sortseg || !ctx->env_force_reg);  // dropout and sortseg live in the ring kernel only
+  KGEB_REQUIRE(ctx, use_ring || !sortseg, KGEB_ERR_UNSUPPORTED, "the sort-segmented backward needs the ring kernel, whose stages do not fit for this width");
   KGEB_REQUIRE(ctx, use_ring || a.sc.dp.thr == 0, KGEB_ERR_UNSUPPORTED, "dropout needs the ring kernel, whose stages do not fit for this width");
-  KGEB_TIME_BEGIN(ctx, KGEB_TIMED_TRAIN, st);
   if (use_ring) {
     const size_t smem = (size_t)KGEB_WARPS_PER_BLOCK * (3 + SR * D) * RB + (size_t)KGEB_WARPS_PER_BLOCK * (D + 1) * sizeof(uint64_t);
     KGEB_REQUIRE(ctx, smem <= 227 * 1024, KGEB_ERR_UNSUPPORTED, "ring stages do not fit shared memory");
@@ -156,9 +164,11 @@ extern "C" int kgeb_train_fwd_bwd(kgeb_ctx* ctx, const float* E, const float* R,
   } else {
     int grid = grid_for(ctx, B, 4);
     if (grid > KGEB_MAX_PARTIAL_BLOCKS) grid = KGEB_MAX_PARTIAL_BLOCKS;
+    KGEB_TIME_BEGIN(ctx, KGEB_TIMED_TRAIN, st);
     KGEB_DISPATCH_KIND(ctx->kind, KGEB_DISPATCH_NC(nc, (k_train_fwd_bwd<KIND, NC><<<grid, KGEB_THREADS, 0, st>>>(a))));
+    KGEB_TIME_END(ctx, KGEB_TIMED_TRAIN, st);
   }
-  KGEB_TIME_END(ctx, KGEB_TIMED_TRAIN, st);
   KGEB_LAUNCH_OK(ctx);
+  if (sortseg) return kgeb_internal_sortseg_entities(ctx, &a.sc, nc, pos, neg ? neg : a.neg_out, B, K, gE, st);
   return KGEB_OK;
 }

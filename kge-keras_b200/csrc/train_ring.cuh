@@ -259,7 +259,15 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_train_ring(TrainArgs a, int D,
         cneg = der * scaleN;
       }
       if (lane == 0 && a.neg_scores) a.neg_scores[g * (int64_t)K + j] = f;
-      if (cneg != 0.f) {
+      if (a.coef_out) {   // sort-segmented mode: entity rows are reduced by segment later; only the relation gradient is formed here
+        if (lane == 0) a.coef_out[a.B + g * (int64_t)K + j] = cneg;
+        if (cneg != 0.f) {
+          Frag<KIND, NC> GS, GP, GO;
+          score_grads(Sn, Pn, On, cneg, fsum, gamma, GS, GP, GO);
+          if (DP) dp_apply(GP, mP, sc.dp.scale);
+          if (!shP) red_frag_l(gRl + (int64_t)np * ldR, half4, okl, GP); else { add_frag(AP, GP); usedP = true; }
+        }
+      } else if (cneg != 0.f) {
         Frag<KIND, NC> GS, GP, GO;
         score_grads(Sn, Pn, On, cneg, fsum, gamma, GS, GP, GO);
         if (DP) { dp_apply(GS, mS, sc.dp.scale); dp_apply(GP, mP, sc.dp.scale); dp_apply(GO, mO, sc.dp.scale); }
@@ -268,6 +276,7 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_train_ring(TrainArgs a, int D,
         if (!shO) red_frag_l(gEl + (int64_t)no * ldE, half4, okl, GO); else { add_frag(AO, GO); usedO = true; }
       }
     }
+    if (a.coef_out && lane == 0) a.coef_out[g] = cpos;
     if (cpos != 0.f) {
       Frag<KIND, NC> S, P, O, GS, GP, GO;
       lds_frag(S, posS, half4, okl, lane);
@@ -278,7 +287,9 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_train_ring(TrainArgs a, int D,
       if (DP) { dp_apply(GS, mposS, sc.dp.scale); dp_apply(GP, mposP, sc.dp.scale); dp_apply(GO, mposO, sc.dp.scale); }
       add_frag(AP, GP);
       usedP = true;
-      if (MODE == 1) {  // nothing else accumulates on the positive's entity rows: reduce them directly
+      if (a.coef_out) {
+        // entity rows of the positive: left to the segment kernel
+      } else if (MODE == 1) {  // nothing else accumulates on the positive's entity rows: reduce them directly
         red_frag_l(gEl + (int64_t)s * ldE, half4, okl, GS);
         red_frag_l(gEl + (int64_t)o * ldE, half4, okl, GO);
       } else {
@@ -286,9 +297,9 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_train_ring(TrainArgs a, int D,
         usedS = usedO = true;
       }
     }
-    if (MODE != 1 && usedS) red_frag_l(gEl + (int64_t)s * ldE, half4, okl, AS);
+    if (MODE != 1 && usedS && !a.coef_out) red_frag_l(gEl + (int64_t)s * ldE, half4, okl, AS);
     if (usedP) red_frag_l(gRl + (int64_t)p * ldR, half4, okl, AP);
-    if (MODE != 1 && usedO) red_frag_l(gEl + (int64_t)o * ldE, half4, okl, AO);
+    if (MODE != 1 && usedO && !a.coef_out) red_frag_l(gEl + (int64_t)o * ldE, half4, okl, AO);
   }
   if (lane != 0) { lp = 0.0; ln = 0.0; }
   const double wgt = (double)a.loss_weight;

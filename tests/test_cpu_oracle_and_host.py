@@ -289,8 +289,8 @@ def test_mirror_error_behaviour_and_csr():
         ku.loss_function_lookup("hinge")
     with pytest.raises(TypeError):
         ku.validate(object(), [(0, 0, 1)], 5, 32)                 # filtering_triples=None, as the reference
-    with pytest.raises(TypeError):
-        ku.validate(object(), [(0, 0, 1)], 5, 32, [(0, 0, 2)])    # not a libkgeb200-backed model: no CPU path
+    with pytest.raises(AttributeError):
+        ku.validate(object(), [(0, 0, 1)], 5, 32, [(0, 0, 2)])    # no .predict: what utils.py:211 raises in the reference
     test = np.array([[0, 0, 1], [2, 1, 3]])
     filt = [(0, 0, 4), (0, 0, 2), (0, 0, 2), (9, 1, 3), (5, 1, 3)]
     offs, ids = ku.build_filter_csr(test, filt, "tail")
@@ -468,16 +468,19 @@ def test_bench_reference_arm_prints_contract_line():
     import subprocess
     import sys
     root = ROOT
-    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--batch", "1024"], capture_output=True, text=True, timeout=300, cwd=root)
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     d = json.loads(line)
-    assert d["impl"] == "reference" and d["metric"] == "train_triples_per_s" and d["unit"] == "triples/s"
-    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["impl"] == "reference" and d["metric"] == "filtered_eval_queries_per_s" and d["unit"] == "queries/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1 and d["scaling"] == "strong"
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"] and "model" not in d["config"]
+    sys.path.insert(0, root)
+    import bench
+    assert d["config"] == bench.headline_config(None)      # both arms print the same config keys and values
 
 
 # ---- literal branch (models.py:114-120,152-158) -----------------------------------------------------------------------
