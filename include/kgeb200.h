@@ -245,19 +245,22 @@ KGEB_API int kgeb_rank_1n(kgeb_ctx* ctx, const float* E_shard, int64_t row_offse
                  const int32_t* filt_ids, int32_t* counts, kgeb_stream stream);
 
 /* ---- 1-N ranking on the tensor cores (tcgen05) for the dot-product scores: DistMult, ComplEx, HolE ------------------
- * Same result contract as kgeb_rank_1n.  KGEB_TC_BF16X3_EXACT: bf16 hi/lo split contraction used as a filter with a
- * proven error bound + exact fp32 re-scoring of the undecided pairs -> integer counts IDENTICAL to kgeb_rank_1n.
+ * Same result contract as kgeb_rank_1n.  KGEB_TC_F16X3_EXACT: 16-bit hi/lo split contraction (three MMAs per k-step on
+ * power-of-two scaled fp16 planes) used as a filter with a proven error bound + exact fp32 re-scoring of the undecided
+ * pairs -> integer counts IDENTICAL to kgeb_rank_1n (rank_tc_kernels.cu states the bound; the tensor-core accumulation
+ * model it rests on is measured by profiles/micro/tc_numerics.cu).  KGEB_TC_BF16X3_EXACT is the first build's name of the
+ * same mode (its planes were bf16) and is kept as an alias.
  * KGEB_TC_BF16: one bf16 plane, no bound -> approximate (ranks may move at near-ties).  Replaces the per-query
  * model.predict + rankdata loop of validate, utils.py:210-245. */
-typedef enum { KGEB_TC_BF16 = 0, KGEB_TC_BF16X3_EXACT = 1 } kgeb_tc_mode;
+typedef enum { KGEB_TC_BF16 = 0, KGEB_TC_BF16X3_EXACT = 1, KGEB_TC_F16X3_EXACT = 1 } kgeb_tc_mode;
 /* (the filter CSR is applied inside the kernel's epilogue as a mask: ids must be sorted ascending per query)
- * bytes of the packed bf16 image (+ row norms) of an entity shard of n_rows rows */
+ * bytes of the packed 16-bit image (+ row norms, slice maxima, scale) of an entity shard of n_rows rows; 256-byte aligned */
 KGEB_API int64_t kgeb_rank_tc_packed_bytes(const kgeb_ctx* ctx, int64_t n_rows, int mode);
 /* packs E_shard[n_rows, ldE] once per table version (the table is constant during validate) */
 KGEB_API int kgeb_rank_tc_pack_entities(kgeb_ctx* ctx, const float* E_shard, int64_t n_rows, int mode, void* packed,
                                int64_t packed_bytes, kgeb_stream stream);
-/* workspace for Q queries: 256-byte header {uint32 appended, uint32 capacity}, worklist of capacity (q,c) pairs,
- * packed queries, query norms.  After the stream has run the call, appended > capacity means the worklist overflowed:
+/* workspace for Q queries (256-byte aligned): 256-byte header {uint32 appended, uint32 capacity, .., uint32 query scale at
+ * byte 16}, worklist of capacity (q,c) pairs, packed queries, query norms.  After the stream has run the call, appended > capacity means the worklist overflowed:
  * counts are then incomplete and the call must be repeated with a larger worklist_cap. */
 KGEB_API int64_t kgeb_rank_tc_workspace_bytes(const kgeb_ctx* ctx, int64_t Q, int mode, int64_t worklist_cap);
 KGEB_API int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_offset, int64_t n_rows, const void* packedE,

@@ -20,6 +20,7 @@ SGD, ADAGRAD, LAZY_ADAM, ADAM_DENSE = range(4)
 CORRUPT_BOTH, CORRUPT_HEAD, CORRUPT_TAIL, CORRUPT_EITHER = range(4)
 SIDE_TAIL, SIDE_HEAD = 0, 1
 TC_BF16, TC_BF16X3_EXACT = 0, 1
+TC_F16X3_EXACT = TC_BF16X3_EXACT   # the exact mode's planes are fp16 since round 2; the first name is kept
 ACT_KINDS = {None: 0, 'linear': 0, 'tanh': 1, 'relu': 2, 'sigmoid': 3}   # Keras activation names served by the literal Dense
 TIMED_RANK_TC, TIMED_RANK_REFINE, TIMED_RANK_TILE, TIMED_TRAIN, TIMED_OPT, TIMED_AUX = range(6)
 

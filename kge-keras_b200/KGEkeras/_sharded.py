@@ -159,6 +159,7 @@ class ShardedTrainer:
             ce.ctx = h
             ce.step = 0
             ce.hole_fft, ce.param = False, 1.0
+            ce.grad_mode, ce._ss_ws = "red", None
             ce._loss = torch.zeros(1, dtype=torch.float32, device=self.device)
             self.compact = ce
         ce = self.compact

@@ -6,28 +6,39 @@
 // The Q x N score matrix never exists: tcgen05.mma accumulates a 128-query x 256-entity tile in TMEM, eight epilogue
 // warps read it back with tcgen05.ld and keep nothing but integer counters.
 //
-// Exactness.  A bf16 contraction cannot reproduce the fp32 sequential-k scores of rank_common.cuh bit for bit, so the
+// Exactness.  A 16-bit contraction cannot reproduce the fp32 sequential-k scores of rank_common.cuh bit for bit, so the
 // tensor cores are used as a FILTER with a proven error bound and the few undecided pairs are re-scored exactly:
-//   operands   q = qh + ql + rq,  e = eh + el + re  (bf16 hi/lo split).  bf16 keeps 8 significant bits, so round-to-nearest
-//              has unit roundoff 2^-8: |ql| = |q - qh| <= 2^-8 |q| (the subtraction is exact in fp32) and
-//              |rq| = |(q - qh) - ql| <= 2^-8 |ql| <= 2^-16 |q|, elementwise; the same for e.  The kernel accumulates
-//              qh.eh + qh.el + ql.eh in fp32 (3 MMAs per k-step on the same staged tiles); it DROPS
-//              ql.el + rq.e + (qh+ql).re, each at most (1 + 2^-15) * 2^-16 * sum_k |q_k||e_k| <= ... * ||q||_2 ||e||_2
-//              (Cauchy-Schwarz), i.e. 3 * 2^-16 together (the first build budgeted one such term, not three),
-//   bound      |S~ - S_seqk| <= c_eps * ||q||_2 * ||e_c||_2,  c_eps = 1.05 * (3 * 2^-16 + (K + 1 + 2*Kacc) * 2^-24)
-//              (representation + sequential fp32 rounding of the reference arithmetic + tensor-core accumulation:
-//              every accumulated product may lose one ulp(2^-23) of the running magnitude <= sum_k |terms|),
-//   epilogue   S~ > t + bound  -> counted;   S~ < t - bound -> dropped;   otherwise the pair (q,c) goes to a worklist
-//              that k_seqk_pairs (rank_kernels.cu) re-scores with the exact sequential-k arithmetic.  The bound used per
-//              128-entity slice is the slice's largest ||e||, so a thread compares against two constants.
-// The integer result is therefore identical to k_rank_tile's.  KGEB_TC_BF16 (single bf16 plane, bound forced to 0) is
-// the approximate mode: one MMA per k-step, ranks can differ at near-ties (tolerance stated in the tests).
+//   operands   Q = 2^b q and Ee = 2^a e (one power-of-two scale per query batch / per packed table, chosen on the device so
+//              that the largest magnitude lands in [2^13, 2^14): exact, and it keeps the planes in fp16's normal range) are
+//              split into fp16 planes  Q = qh + ql + rq,  Ee = eh + el + re.  fp16 keeps 11 significant bits, so
+//              |ql| <= 2^-11 |Q| and |rq| <= 2^-22 |Q| + 2^-25 elementwise (the constant covers a subnormal low plane).
+//              The kernel accumulates qh.eh + qh.el + ql.eh in fp32 (3 MMAs per k-step on the same staged tiles) and DROPS
+//              ql.el + rq.Ee + (qh+ql).re  <=  3.001 * 2^-22 ||Q|| ||Ee||  +  2^-25 sqrt(K) (||Q|| + ||Ee||)   (Cauchy-Schwarz),
+//   reference  the sequential fp32 sum itself: |seq - exact| <= u T + 16.01 u Z,  u = 2^-24, T = sum_k |q_k e_k| <= ||q|| ||e||,
+//              Z = sum over the K/16 blocks j of T_j (T_j = the sum of |q_k e_k| up to the end of block j): every partial sum
+//              of block j is at most T_j in magnitude and is rounded once per added term,
+//   tensor     tcgen05.mma kind::f16 with fp32 accumulation, MEASURED (profiles/micro/tc_numerics.cu, r02_tc_numerics.md):
+//              the 16 products and the incoming accumulator of one instruction are aligned to the largest exponent E among
+//              them, each truncated toward zero to a multiple of 2^(E-25) (two bits below the fp32 ulp of the largest),
+//              summed exactly, and the sum is truncated toward zero to fp32.  One instruction therefore loses less than
+//              16 * 2^(E-25) + ulp(result) <= 10 u B, B = the sum of the magnitudes accumulated so far <= 1.002 T_j; the
+//              bound budgets 12 u B per instruction, 3 instructions per block: 36.1 u Z,
+//   spread     Z <= sum_j ||q_(blocks <= j)|| ||e_(blocks <= j)|| <= Aq * Ae  (Cauchy-Schwarz over j) with the WEIGHTED norms
+//              A^2 = sum_k w_k x_k^2, w_k = number of blocks at or after k's.  For rows whose mass is spread over k this is
+//              half of the worst case (K/16) ||q|| ||e|| that a plain norm bound has to assume,
+//   bound      |S~ / 2^(a+b) - S_seqk| <= 1.02 * u * (13 ||q|| ||e|| + 52.11 Aq Ae) + 1.02 * 2^-25 sqrt(K) (||q|| 2^-a + ||e|| 2^-b),
+//   epilogue   S~ > hi -> counted;   S~ < lo -> dropped;   otherwise the pair (q,c) goes to a worklist that k_seqk_pairs
+//              (rank_kernels.cu) re-scores with the exact sequential-k arithmetic.  The bound used per 128-entity slice takes
+//              the slice's largest ||e|| and largest Ae, so a thread compares against two constants.
+// The integer result is therefore identical to k_rank_tile's.  KGEB_TC_BF16 (single bf16 plane, unscaled, bound forced to 0)
+// is the approximate mode: one MMA per k-step, ranks can differ at near-ties (tolerance stated in the tests).
 //
 // Data movement.  Both operands are pre-packed (k_tc_pack) into the exact shared-memory image the UMMA descriptors
 // expect -- no-swizzle K-major core matrices, [tile][k-chunk][plane][row][8 x bf16] -- so one pipeline stage is two
 // contiguous bulk async copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier; no tensor map is needed.
 // Roles: warp 0 = copy producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator, warps 4-11 = epilogue.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "rank_common.cuh"
@@ -140,14 +151,28 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
          (1ull << 46);
 }
-// instruction descriptor: fp32 accumulate, A = B = bf16, both K-major, N = 256, M = 128
-constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+// instruction descriptor: fp32 accumulate, A and B both K-major, N = 256, M = 128; operand format fp16 (0) or bf16 (1)
+constexpr uint32_t TC_IDESC_F16 = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+constexpr uint32_t TC_IDESC_BF16 = TC_IDESC_F16 | (1u << 7) | (1u << 10);
+
+// power-of-two scale that moves a largest magnitude `amax` (given as its fp32 bits) into [2^13, 2^14); 1 for an all-zero table
+__device__ __forceinline__ float tc_scale_from_bits(uint32_t bits) {
+  const float amax = __uint_as_float(bits);
+  if (!(amax > 0.f) || isinf(amax)) return 1.f;
+  int a = 13 - ilogbf(amax);
+  a = a < -60 ? -60 : (a > 60 ? 60 : a);
+  return ldexpf(1.f, a);
+}
 
 struct TcArgs {
   const unsigned char* packedQ;  // [qtiles][nkc][planes][128][8] bf16
   const unsigned char* packedE;  // [ntiles][nkc][planes][256][8] bf16
   const float* qnorm;            // [qtiles*128]  upper bound of ||q||_2
+  const float* qwnorm;           // [qtiles*128]  upper bound of the weighted norm Aq (exact mode)
   const float* emax;             // [ntiles*2]    max over each 128-entity slice of the upper bound of ||e||_2
+  const float* ewmax;            // [ntiles*2]    max over each slice of the weighted norm Ae (exact mode)
+  const uint32_t* escale_bits;   // largest |E| of the packed rows / largest |q| of the batch as fp32 bits (exact mode; else NULL)
+  const uint32_t* qscale_bits;
   const float* tscore;           // [Q] exact target scores
   const int32_t* triples;        // [Q,3]
   const int64_t* filt_offs;      // [Q+1] CSR of known-true GLOBAL entity ids per query, sorted ascending (or NULL)
@@ -158,7 +183,8 @@ struct TcArgs {
   uint32_t wl_cap;
   int64_t Q, row_offset, n_rows;
   int nkc, planes, qtiles, ntiles, side, qgroup;
-  float c_eps, t_slack;
+  uint32_t idesc;
+  float c_norm, c_wnorm, c_abs, t_slack;   // band = c_norm ||q|| ||e|| + c_wnorm Aq Ae + c_abs (||q|| / 2^a + ||e|| / 2^b)
 };
 
 // item -> (entity tile, query tile).  Query tiles are walked in groups of `qgroup`: inside a group the query tile varies
@@ -258,11 +284,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
             for (int j = 0; j < nk16; ++j) {
               // chunk column (2j, plane p) starts at (2j*planes + p) * rows * 16 bytes
               const uint32_t a0 = sa + (uint32_t)(2 * j * planes) * TC_BM * 16, b0 = sb + (uint32_t)(2 * j * planes) * TC_BN * 16;
-              tc_mma_bf16(tmem_d, tc_desc(a0, lboA, 128), tc_desc(b0, lboB, 128), TC_IDESC, accumulate);  // qh . eh
+              tc_mma_bf16(tmem_d, tc_desc(a0, lboA, 128), tc_desc(b0, lboB, 128), a.idesc, accumulate);  // qh . eh
               accumulate = 1;
               if (planes == 2) {
-                tc_mma_bf16(tmem_d, tc_desc(a0, lboA, 128), tc_desc(b0 + TC_BN * 16, lboB, 128), TC_IDESC, 1);  // qh . el
-                tc_mma_bf16(tmem_d, tc_desc(a0 + TC_BM * 16, lboA, 128), tc_desc(b0, lboB, 128), TC_IDESC, 1);  // ql . eh
+                tc_mma_bf16(tmem_d, tc_desc(a0, lboA, 128), tc_desc(b0 + TC_BN * 16, lboB, 128), a.idesc, 1);  // qh . el
+                tc_mma_bf16(tmem_d, tc_desc(a0 + TC_BM * 16, lboA, 128), tc_desc(b0, lboB, 128), a.idesc, 1);  // ql . eh
               }
             }
             st_idx[nin++] = stage;
@@ -281,6 +307,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t wcnt = 0;  // pairs waiting in wbuf (warp-uniform)
     uint32_t acc = 0, acc_phase = 0;
+    // exact mode: the accumulators carry the scores times 2^(a+b) (operand scales, powers of two: every product below is exact)
+    const float scE = a.escale_bits ? tc_scale_from_bits(__ldg(a.escale_bits)) : 1.f;
+    const float scQ = a.qscale_bits ? tc_scale_from_bits(__ldg(a.qscale_bits)) : 1.f;
+    const float sc = scE * scQ;
 
     auto flush = [&]() {
       __syncwarp();
@@ -299,12 +329,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
       const int64_t q = qt * TC_BM + lq * 32 + lane;
       const bool qok = q < a.Q;
       const float t = qok ? __ldg(a.tscore + q) : 0.f;
-      const float epsq = a.c_eps * (qok ? __ldg(a.qnorm + q) : 0.f);
+      const float qn = qok ? __ldg(a.qnorm + q) : 0.f;
+      const float epsq = __fmaf_rn(a.c_norm, qn, a.c_abs / scQ);                       // multiplies the slice's largest ||e||
+      const float epsw = a.c_wnorm * ((qok && a.qwnorm) ? __ldg(a.qwnorm + q) : 0.f);  // multiplies the slice's largest Ae
+      const float absq = a.c_abs * qn / scE;
       const int64_t tgt = qok ? (int64_t)__ldg(a.triples + 3 * q + (a.side == KGEB_SIDE_TAIL ? 2 : 0)) - a.row_offset : -1;
       const int64_t n0 = tile * TC_BN + chalf * 128;   // shard-local id of this warp's first column
       const float nmax = __ldg(a.emax + tile * 2 + chalf);
-      const float hi = __fmaf_rn(epsq, nmax, __fmaf_rn(fabsf(t), a.t_slack, t));
-      const float lo = __fmaf_rn(-epsq, nmax, __fmaf_rn(-fabsf(t), a.t_slack, t));
+      const float wmax = a.ewmax ? __ldg(a.ewmax + tile * 2 + chalf) : 0.f;
+      const float band = __fmaf_rn(epsq, nmax, __fmaf_rn(epsw, wmax, absq));
+      const float hi = __fmul_rn(__fadd_rn(__fmaf_rn(fabsf(t), a.t_slack, t), band), sc);
+      const float lo = __fmul_rn(__fsub_rn(__fmaf_rn(-fabsf(t), a.t_slack, t), band), sc);
       int cnt0 = 0;
       // cursor into this query's sorted filter list: first id at or beyond this warp's first column (global id space)
       int64_t fpos = 0, fend = 0;
@@ -391,10 +426,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
 }
 
 // ---- operand packing ----------------------------------------------------------------------------------------------
-// one thread per 16-byte output chunk: dst[tile][kchunk][plane][row][0..7], plane 0 = bf16(x), plane 1 = bf16(x - plane0)
+// largest |x| of a table as fp32 bits (non-negative floats order like their bit patterns); *out must be zero before the launch
+__global__ void k_tc_absmax(const float* __restrict__ src, int64_t rows, int W, int ld, uint32_t* __restrict__ out) {
+  uint32_t m = 0;
+  const int64_t total = rows * (int64_t)W;
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = o / W;
+    const uint32_t b = __float_as_uint(__ldg(src + r * (int64_t)ld + (o - r * W))) & 0x7fffffffu;
+    m = b > m ? b : m;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const uint32_t v = __shfl_xor_sync(0xffffffffu, m, o); m = v > m ? v : m; }
+  if ((threadIdx.x & 31) == 0 && m != 0) atomicMax(out, m);
+}
+
+// one thread per 16-byte output chunk: dst[tile][kchunk][plane][row][0..7].
+//   scale_bits == NULL: bf16, plane 0 = bf16(x)                                  (approximate mode, one plane)
+//   scale_bits != NULL: fp16 of y = x * 2^a, plane 0 = fp16(y), plane 1 = fp16(y - plane0)   (exact mode)
 __global__ void k_tc_pack(const float* __restrict__ src, int64_t rows, int W, int ld, int tile_rows, int nkc, int planes,
-                          int64_t ntile, uint4* __restrict__ dst) {
+                          int64_t ntile, const uint32_t* __restrict__ scale_bits, uint4* __restrict__ dst) {
   const int64_t total = ntile * nkc * planes * tile_rows;
+  const float scale = scale_bits ? tc_scale_from_bits(__ldg(scale_bits)) : 1.f;
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
     const int row = (int)(o % tile_rows);
     const int64_t o1 = o / tile_rows;
@@ -419,11 +471,17 @@ __global__ void k_tc_pack(const float* __restrict__ src, int64_t rows, int W, in
       }
     }
     unsigned short h[8];
+    if (scale_bits) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      __nv_bfloat16 hi = __float2bfloat16_rn(x[e]);
-      if (plane == 1) hi = __float2bfloat16_rn(__fsub_rn(x[e], __bfloat162float(hi)));
-      h[e] = __bfloat16_as_ushort(hi);
+      for (int e = 0; e < 8; ++e) {
+        const float y = __fmul_rn(x[e], scale);                  // exact: power of two, |y| < 2^14
+        __half hi = __float2half_rn(y);
+        if (plane == 1) hi = __float2half_rn(__fsub_rn(y, __half2float(hi)));   // the subtraction is exact in fp32
+        h[e] = __half_as_ushort(hi);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) h[e] = __bfloat16_as_ushort(__float2bfloat16_rn(x[e]));
     }
     uint4 out;
     out.x = h[0] | ((uint32_t)h[1] << 16); out.y = h[2] | ((uint32_t)h[3] << 16);
@@ -432,17 +490,27 @@ __global__ void k_tc_pack(const float* __restrict__ src, int64_t rows, int W, in
   }
 }
 
-// norms[r] = an upper bound of ||src[r,:]||_2 for r < rows; rows..rows_padded-1 get `pad_value` (NaN for entities)
-__global__ void k_tc_norms(const float* __restrict__ src, int64_t rows, int64_t rows_padded, int W, int ld, float pad_value,
-                           float* __restrict__ norms) {
+// norms[r] = an upper bound of ||src[r,:]||_2 for r < rows; wnorms[r] (optional) = an upper bound of the weighted norm
+// sqrt(sum_k w_k x_k^2), w_k = nblk - k/16 (the number of K=16 blocks at or after k's); rows..rows_padded-1 get `pad_value`
+__global__ void k_tc_norms(const float* __restrict__ src, int64_t rows, int64_t rows_padded, int W, int ld, int nblk, float pad_value,
+                           float* __restrict__ norms, float* __restrict__ wnorms) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t r = warp0; r < rows_padded; r += nwarps) {
-    if (r >= rows) { if (lane == 0) norms[r] = pad_value; continue; }
-    float acc = 0.f;
-    for (int k = lane; k < W; k += 32) { const float x = __ldg(src + r * (int64_t)ld + k); acc = fmaf(x, x, acc); }
+    if (r >= rows) { if (lane == 0) { norms[r] = pad_value; if (wnorms) wnorms[r] = pad_value; } continue; }
+    float acc = 0.f, wacc = 0.f;
+    for (int k = lane; k < W; k += 32) {
+      const float x = __ldg(src + r * (int64_t)ld + k);
+      const float x2 = x * x;
+      acc += x2;
+      wacc = fmaf((float)(nblk - (k >> 4)), x2, wacc);
+    }
     acc = warp_sum(acc);
-    if (lane == 0) norms[r] = sqrtf(acc) * 1.0001f;  // fp32 summation error of <= 2^12 terms is < 1e-4 relative
+    wacc = warp_sum(wacc);
+    if (lane == 0) {
+      norms[r] = sqrtf(acc) * 1.0001f;  // fp32 summation error of <= 2^12 non-negative terms is < 1e-4 relative
+      if (wnorms) wnorms[r] = sqrtf(wacc) * 1.0001f;
+    }
   }
 }
 
@@ -472,12 +540,38 @@ int tc_grid(const kgeb_ctx* ctx, int64_t n, int threads) {
   return (int)(b < 1 ? 1 : b);
 }
 
+// packed entity buffer: [operand image][row norms nt*256][slice max nt*2][weighted norms nt*256][their slice max nt*2][scale bits]
+struct TcPackedLayout { size_t image, norms, smax, wnorms, wmax, scale, total; };
+TcPackedLayout tc_packed_layout(const kgeb_ctx* ctx, int64_t n_rows, int mode) {
+  const int64_t nt = tc_tiles(n_rows, TC_BN);
+  TcPackedLayout L;
+  L.image = 0;
+  L.norms = tc_align((size_t)nt * tc_nkc(ctx) * tc_planes(mode) * TC_BN * 16);
+  L.smax = L.norms + tc_align((size_t)nt * TC_BN * 4);
+  L.wnorms = L.smax + tc_align((size_t)nt * 2 * 4);
+  L.wmax = L.wnorms + tc_align((size_t)nt * TC_BN * 4);
+  L.scale = L.wmax + tc_align((size_t)nt * 2 * 4);
+  L.total = L.scale + 256;
+  return L;
+}
+// workspace: [header 256 B: appended, capacity, query scale bits at +16][worklist][packed queries][query norms][weighted query norms]
+struct TcWsLayout { size_t wl, packedQ, qnorm, qwnorm, total; };
+TcWsLayout tc_ws_layout(const kgeb_ctx* ctx, int64_t Q, int mode, int64_t worklist_cap) {
+  const int64_t qt = tc_tiles(Q, TC_BM);
+  TcWsLayout L;
+  L.wl = TC_HDR_BYTES;
+  L.packedQ = L.wl + tc_align((size_t)worklist_cap * 8);
+  L.qnorm = L.packedQ + tc_align((size_t)qt * tc_nkc(ctx) * tc_planes(mode) * TC_BM * 16);
+  L.qwnorm = L.qnorm + tc_align((size_t)qt * TC_BM * 4);
+  L.total = L.qwnorm + tc_align((size_t)qt * TC_BM * 4);
+  return L;
+}
+
 }  // namespace
 
 extern "C" int64_t kgeb_rank_tc_packed_bytes(const kgeb_ctx* ctx, int64_t n_rows, int mode) {
   if (!ctx || n_rows < 0 || (mode != KGEB_TC_BF16 && mode != KGEB_TC_BF16X3_EXACT)) return KGEB_ERR_INVALID;
-  const int64_t nt = tc_tiles(n_rows, TC_BN);
-  return (int64_t)(tc_align((size_t)nt * tc_nkc(ctx) * tc_planes(mode) * TC_BN * 16) + tc_align((size_t)nt * TC_BN * 4) + nt * 2 * 4);
+  return (int64_t)tc_packed_layout(ctx, n_rows, mode).total;
 }
 
 extern "C" int kgeb_rank_tc_pack_entities(kgeb_ctx* ctx, const float* E_shard, int64_t n_rows, int mode, void* packed,
@@ -486,29 +580,41 @@ extern "C" int kgeb_rank_tc_pack_entities(kgeb_ctx* ctx, const float* E_shard, i
   KGEB_REQUIRE(ctx, tc_kind_ok(ctx), KGEB_ERR_UNSUPPORTED, "tensor-core ranking serves DistMult, ComplEx, HolE and RotatE (dot-product queries)");
   KGEB_REQUIRE(ctx, E_shard && packed && n_rows > 0, KGEB_ERR_INVALID, "rank_tc_pack_entities: bad arguments");
   KGEB_REQUIRE(ctx, mode == KGEB_TC_BF16 || mode == KGEB_TC_BF16X3_EXACT, KGEB_ERR_INVALID, "unknown tensor-core mode");
-  KGEB_REQUIRE(ctx, ctx->we % 4 == 0 && ctx->ldE % 4 == 0 && kgeb_aligned16(E_shard) && kgeb_aligned16(packed), KGEB_ERR_ALIGNMENT,
-               "rank_tc needs width, stride multiples of 4 floats and 16-byte aligned buffers");
+  KGEB_REQUIRE(ctx, ctx->we % 4 == 0 && ctx->ldE % 4 == 0 && kgeb_aligned16(E_shard) && (reinterpret_cast<uintptr_t>(packed) & 255u) == 0,
+               KGEB_ERR_ALIGNMENT, "rank_tc needs width, stride multiples of 4 floats, a 16-byte aligned table and a 256-byte aligned packed buffer");
   KGEB_REQUIRE(ctx, packed_bytes >= kgeb_rank_tc_packed_bytes(ctx, n_rows, mode), KGEB_ERR_WORKSPACE, "packed entity buffer too small");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t nt = tc_tiles(n_rows, TC_BN);
   const int nkc = tc_nkc(ctx), planes = tc_planes(mode);
+  const bool exact = mode == KGEB_TC_BF16X3_EXACT;
+  const TcPackedLayout L = tc_packed_layout(ctx, n_rows, mode);
+  unsigned char* base = static_cast<unsigned char*>(packed);
+  uint32_t* scale_bits = reinterpret_cast<uint32_t*>(base + L.scale);
+  if (exact) {
+    KGEB_CUDA_OK(ctx, cudaMemsetAsync(scale_bits, 0, 256, st));
+    k_tc_absmax<<<tc_grid(ctx, n_rows * (int64_t)ctx->we, 256), 256, 0, st>>>(E_shard, n_rows, ctx->we, ctx->ldE, scale_bits);
+    KGEB_LAUNCH_OK(ctx);
+  }
   k_tc_pack<<<tc_grid(ctx, nt * nkc * planes * TC_BN, 256), 256, 0, st>>>(E_shard, n_rows, ctx->we, ctx->ldE, TC_BN, nkc, planes, nt,
-                                                                         reinterpret_cast<uint4*>(packed));
+                                                                         exact ? scale_bits : nullptr, reinterpret_cast<uint4*>(base));
   KGEB_LAUNCH_OK(ctx);
-  float* enorm = reinterpret_cast<float*>(static_cast<unsigned char*>(packed) + tc_align((size_t)nt * nkc * planes * TC_BN * 16));
-  k_tc_norms<<<tc_grid(ctx, nt * TC_BN * 32, 256), 256, 0, st>>>(E_shard, n_rows, nt * TC_BN, ctx->we, ctx->ldE, 0.f, enorm);
+  float* enorm = reinterpret_cast<float*>(base + L.norms);
+  float* ewnorm = reinterpret_cast<float*>(base + L.wnorms);
+  k_tc_norms<<<tc_grid(ctx, nt * TC_BN * 32, 256), 256, 0, st>>>(E_shard, n_rows, nt * TC_BN, ctx->we, ctx->ldE, nkc / 2, 0.f, enorm,
+                                                                exact ? ewnorm : nullptr);
   KGEB_LAUNCH_OK(ctx);
-  float* emax = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(enorm) + tc_align((size_t)nt * TC_BN * 4));
-  k_tc_slice_max<<<tc_grid(ctx, nt * 2 * 32, 256), 256, 0, st>>>(enorm, nt * 2, emax);
+  k_tc_slice_max<<<tc_grid(ctx, nt * 2 * 32, 256), 256, 0, st>>>(enorm, nt * 2, reinterpret_cast<float*>(base + L.smax));
   KGEB_LAUNCH_OK(ctx);
+  if (exact) {
+    k_tc_slice_max<<<tc_grid(ctx, nt * 2 * 32, 256), 256, 0, st>>>(ewnorm, nt * 2, reinterpret_cast<float*>(base + L.wmax));
+    KGEB_LAUNCH_OK(ctx);
+  }
   return KGEB_OK;
 }
 
 extern "C" int64_t kgeb_rank_tc_workspace_bytes(const kgeb_ctx* ctx, int64_t Q, int mode, int64_t worklist_cap) {
   if (!ctx || Q < 0 || worklist_cap < 0 || (mode != KGEB_TC_BF16 && mode != KGEB_TC_BF16X3_EXACT)) return KGEB_ERR_INVALID;
-  const int64_t qt = tc_tiles(Q, TC_BM);
-  return (int64_t)(TC_HDR_BYTES + tc_align((size_t)worklist_cap * 8) + tc_align((size_t)qt * tc_nkc(ctx) * tc_planes(mode) * TC_BM * 16) +
-                   tc_align((size_t)qt * TC_BM * 4));
+  return (int64_t)tc_ws_layout(ctx, Q, mode, worklist_cap).total;
 }
 
 extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_offset, int64_t n_rows, const void* packedE,
@@ -523,34 +629,48 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
   KGEB_REQUIRE(ctx, mode == KGEB_TC_BF16 || mode == KGEB_TC_BF16X3_EXACT, KGEB_ERR_INVALID, "unknown tensor-core mode");
   KGEB_REQUIRE(ctx, (filt_offsets == nullptr) == (filt_ids == nullptr), KGEB_ERR_INVALID, "filter CSR: give both arrays or neither");
   KGEB_REQUIRE(ctx, worklist_cap > 0 && worklist_cap < 0x7fffffffLL, KGEB_ERR_INVALID, "worklist capacity out of range");
-  KGEB_REQUIRE(ctx, ctx->we % 4 == 0 && ctx->ldE % 4 == 0 && kgeb_aligned16(E_shard) && kgeb_aligned16(qvec) && kgeb_aligned16(packedE) &&
-                        (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
-               KGEB_ERR_ALIGNMENT, "rank_1n_tc needs 16-byte aligned tables and a 256-byte aligned workspace");
+  KGEB_REQUIRE(ctx, ctx->we % 4 == 0 && ctx->ldE % 4 == 0 && kgeb_aligned16(E_shard) && kgeb_aligned16(qvec) &&
+                        (reinterpret_cast<uintptr_t>(packedE) & 255u) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
+               KGEB_ERR_ALIGNMENT, "rank_1n_tc needs 16-byte aligned tables and 256-byte aligned packed / workspace buffers");
   KGEB_REQUIRE(ctx, workspace_bytes >= kgeb_rank_tc_workspace_bytes(ctx, Q, mode, worklist_cap), KGEB_ERR_WORKSPACE,
                "rank_1n_tc: workspace smaller than kgeb_rank_tc_workspace_bytes()");
   if (Q == 0 || n_rows == 0) return KGEB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int nkc = tc_nkc(ctx), planes = tc_planes(mode), qw = kgeb_query_width(ctx, side);
+  const bool exact = mode == KGEB_TC_BF16X3_EXACT;
   const int64_t qt = tc_tiles(Q, TC_BM), nt = tc_tiles(n_rows, TC_BN);
   KGEB_REQUIRE(ctx, qt < 0x7fffffffLL && nt < 0x7fffffffLL, KGEB_ERR_UNSUPPORTED, "too many tiles");
+  const TcWsLayout W = tc_ws_layout(ctx, Q, mode, worklist_cap);
+  const TcPackedLayout L = tc_packed_layout(ctx, n_rows, mode);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   uint32_t* hdr = reinterpret_cast<uint32_t*>(ws);
-  uint2* wl = reinterpret_cast<uint2*>(ws + TC_HDR_BYTES);
-  unsigned char* packedQ = ws + TC_HDR_BYTES + tc_align((size_t)worklist_cap * 8);
-  float* qnorm = reinterpret_cast<float*>(packedQ + tc_align((size_t)qt * nkc * planes * TC_BM * 16));
+  uint32_t* qscale_bits = hdr + 4;
+  uint2* wl = reinterpret_cast<uint2*>(ws + W.wl);
+  unsigned char* packedQ = ws + W.packedQ;
+  float* qnorm = reinterpret_cast<float*>(ws + W.qnorm);
+  float* qwnorm = reinterpret_cast<float*>(ws + W.qwnorm);
 
   KGEB_CUDA_OK(ctx, cudaMemsetAsync(hdr, 0, TC_HDR_BYTES, st));
+  if (exact) {
+    k_tc_absmax<<<tc_grid(ctx, Q * (int64_t)ctx->we, 256), 256, 0, st>>>(qvec, Q, ctx->we, qw, qscale_bits);
+    KGEB_LAUNCH_OK(ctx);
+  }
   k_tc_pack<<<tc_grid(ctx, qt * nkc * planes * TC_BM, 256), 256, 0, st>>>(qvec, Q, ctx->we, qw, TC_BM, nkc, planes, qt,
-                                                                         reinterpret_cast<uint4*>(packedQ));
+                                                                         exact ? qscale_bits : nullptr, reinterpret_cast<uint4*>(packedQ));
   KGEB_LAUNCH_OK(ctx);
-  k_tc_norms<<<tc_grid(ctx, qt * TC_BM * 32, 256), 256, 0, st>>>(qvec, Q, qt * TC_BM, ctx->we, qw, 0.f, qnorm);
+  k_tc_norms<<<tc_grid(ctx, qt * TC_BM * 32, 256), 256, 0, st>>>(qvec, Q, qt * TC_BM, ctx->we, qw, nkc / 2, 0.f, qnorm, exact ? qwnorm : nullptr);
   KGEB_LAUNCH_OK(ctx);
 
+  const unsigned char* pe = static_cast<const unsigned char*>(packedE);
   TcArgs a;
   a.packedQ = packedQ;
-  a.packedE = static_cast<const unsigned char*>(packedE);
+  a.packedE = pe;
   a.qnorm = qnorm;
-  a.emax = reinterpret_cast<const float*>(a.packedE + tc_align((size_t)nt * nkc * planes * TC_BN * 16) + tc_align((size_t)nt * TC_BN * 4));
+  a.qwnorm = exact ? qwnorm : nullptr;
+  a.emax = reinterpret_cast<const float*>(pe + L.smax);
+  a.ewmax = exact ? reinterpret_cast<const float*>(pe + L.wmax) : nullptr;
+  a.escale_bits = exact ? reinterpret_cast<const uint32_t*>(pe + L.scale) : nullptr;
+  a.qscale_bits = exact ? qscale_bits : nullptr;
   a.tscore = tscore; a.triples = triples; a.counts = counts;
   a.filt_offs = filt_offsets; a.filt_ids = filt_ids;   // applied inside the epilogue as a mask: no correction pass
   a.wl_hdr = hdr; a.wl = wl; a.wl_cap = (uint32_t)worklist_cap;
@@ -564,12 +684,18 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
     if (g > qt) g = qt;
     a.qgroup = (int)g;
   }
-  if (mode == KGEB_TC_BF16X3_EXACT) {
-    const double kacc = 3.0 * nkc * 8;  // products accumulated per score by the tensor cores
-    a.c_eps = (float)(1.05 * (3.0 / 65536.0 + (ctx->we + 1 + 2.0 * kacc) / 16777216.0));
+  if (exact) {
+    // the proven band of the header comment; 1.02 absorbs the 1.0001 of each norm bound and the fp32 rounding of the
+    // half-dozen operations that form the thresholds in the epilogue
+    const double u = 1.0 / 16777216.0;
+    a.idesc = TC_IDESC_F16;
+    a.c_norm = (float)(1.02 * 13.0 * u);
+    a.c_wnorm = (float)(1.02 * 52.11 * u);
+    a.c_abs = (float)(1.02 * sqrt((double)nkc * 8.0) / 33554432.0);
     a.t_slack = 2.4e-7f;
   } else {
-    a.c_eps = 0.f;
+    a.idesc = TC_IDESC_BF16;
+    a.c_norm = a.c_wnorm = a.c_abs = 0.f;
     a.t_slack = 0.f;
   }
   static bool attr_done = false;  // per process; the attribute is per function, setting it again is harmless

@@ -122,27 +122,85 @@ def test_tc_rejects_transe():
         eng.pack_entities_tc(abi.TC_BF16)
 
 
-@pytest.mark.parametrize("width", [64, 200])
-def test_tc_exact_adversarial_split_residuals(width):
-    """Rows built so that the bf16 hi/lo split leaves its LARGEST residuals and every dropped product has the same sign
-    (all entries positive, ql ~ 2^-8 q, el ~ 2^-8 e): the dropped terms ql.el + rq.e + q.re then add up coherently to ~3 * 2^-16
-    of ||q|| ||e|| -- the case the representation term of c_eps has to cover.  Candidate scores are spread from far inside
-    to a few bands outside the target's band, so every decision class (counted / dropped / undecided) occurs."""
+def _near_tie_table(rng, N, base_row, step_bits=21, spread=600):
+    """N rows that are tiny multiples of one pattern: row_j = base * (1 + j * 2^-step_bits) (+ an ulp-sized wobble), so the
+    candidates' scores sit from far inside to a few bands outside the target's band and every decision class of the
+    tensor-core filter (counted / dropped / undecided) occurs."""
+    W = base_row.shape[0]
+    steps = (rng.integers(-spread, spread, size=(N, 1)) * np.float32(2.0 ** -step_bits)).astype(np.float32)
+    wobble = (rng.integers(0, 4, size=(N, W)) * np.float32(2.0 ** -23)).astype(np.float32)
+    return (base_row[None, :] * (np.float32(1.0) + steps) * (np.float32(1.0) + wobble)).astype(np.float32)
+
+
+def _check_exact_against_cuda_core(E, Rm, kind=None, Q=128, seed=0, want_both=True):
     abi = _abi()
     from KGEkeras._engine import Engine
-    N, R, Q = 1024, 2, 128
-    rng = np.random.default_rng(width)
-    base = np.float32(1.0 + 2.0 ** -8 - 2.0 ** -16)            # rounds DOWN to bf16 1.0: lo plane ~ 2^-8, residual ~ 2^-16
-    steps = (rng.integers(-600, 600, size=(N, 1)) * np.float32(2.0 ** -21)).astype(np.float32)   # row scale 1 + j*2^-21: up to ~18 * 2^-16
-    wobble = (rng.integers(0, 4, size=(N, width)) * np.float32(2.0 ** -23)).astype(np.float32)
-    E = (base * (np.float32(1.0) + steps) + wobble).astype(np.float32)
-    Rm = np.ones((R, width), np.float32)
-    eng = Engine(abi.DISTMULT, N, R, width, width, 12.0, E=E, R=Rm)
-    tri = rand_triples(rng, Q, N, R)
-    want = eng.rank_counts(tri, 0).cpu().numpy()
+    kind = ko.DISTMULT if kind is None else kind
+    N, W = E.shape
+    eng = Engine(kind, N, Rm.shape[0], W, W, 12.0, E=E, R=Rm)
+    tri = rand_triples(np.random.default_rng(seed), Q, N, Rm.shape[0])
     stats = {}
-    got = eng.rank_counts_tc(tri, 0, mode=abi.TC_BF16X3_EXACT, stats=stats).cpu().numpy()
-    np.testing.assert_array_equal(got, want)
+    for sd in (0, 1):
+        want = eng.rank_counts(tri, sd).cpu().numpy()
+        got = eng.rank_counts_tc(tri, sd, mode=abi.TC_F16X3_EXACT, stats=stats).cpu().numpy()
+        np.testing.assert_array_equal(got, want)
+    return stats, tri, eng
+
+
+@pytest.mark.parametrize("width", [64, 200])
+@pytest.mark.parametrize("pbits", [8, 11])
+def test_tc_exact_adversarial_split_residuals(width, pbits):
+    """Rows built so that the hi/lo split leaves its LARGEST residuals and every dropped product has the same sign: all entries
+    positive and equal to 1 + 2^-p - 2^-2p, which rounds DOWN to 1.0 in a p-bit format (p = 11: the fp16 planes of the exact
+    mode; p = 8: the bf16 planes of the first build), so lo ~ 2^-p and the residual ~ 2^-2p.  The dropped terms
+    ql.el + rq.e + q.re then add up coherently -- the case the representation term of the band has to cover -- and, the rows
+    being parallel and positive, sum|q_k e_k| = ||q|| ||e|| and every tensor-core truncation has the same sign."""
+    N, R = 1024, 2
+    rng = np.random.default_rng(width + pbits)
+    base = np.full(width, 1.0 + 2.0 ** -pbits - 2.0 ** (-2 * pbits), np.float32)
+    E = _near_tie_table(rng, N, base)
+    Rm = np.ones((R, width), np.float32)
+    stats, tri, eng = _check_exact_against_cuda_core(E, Rm, seed=width)
     sc = ko.seqk_scores(ko.DISTMULT, ko.query_vectors(ko.DISTMULT, E, Rm, tri, "tail"), E, "tail", 12.0)
+    got = eng.rank_counts_tc(tri, 0, mode=_abi().TC_F16X3_EXACT).cpu().numpy()
     np.testing.assert_array_equal(got, (ko.ranks_from_scores(sc, tri, "tail", {}) - 1).astype(np.int32))
-    assert 0 < stats["undecided_pairs"] < Q * N     # some pairs are decided by the tensor cores, some are not
+    assert 0 < stats["undecided_pairs"] < 128 * N     # some pairs are decided by the tensor cores, some are not
+
+
+@pytest.mark.parametrize("shape", ["front_loaded", "back_loaded", "wide_range", "tiny_rows", "alternating"])
+def test_tc_exact_band_covers_unfriendly_magnitude_profiles(shape):
+    """The band's weighted-norm term assumes nothing about WHERE along k the mass of a row sits, and its absolute terms cover
+    elements that fall below the fp16 planes' normal range after the table-wide power-of-two scale.  Profiles: all the mass in
+    the first K=16 block (the accumulator is large from the first instruction on: the worst case of the weighted norms), all in
+    the last block, magnitudes spread over 2^-30..1 inside every row (low planes go subnormal), rows whose norm is 2^-20 of
+    the table's largest (their relative precision after the common scale is poor), alternating signs (cancellation)."""
+    N, R, W = 768, 2, 208
+    rng = np.random.default_rng(len(shape))
+    k = np.arange(W)
+    if shape == "front_loaded":
+        base = np.where(k < 16, 1.0, 2.0 ** -12) * rng.uniform(0.5, 1.0, W)
+    elif shape == "back_loaded":
+        base = np.where(k >= W - 16, 1.0, 2.0 ** -12) * rng.uniform(0.5, 1.0, W)
+    elif shape == "wide_range":
+        base = 2.0 ** -rng.integers(0, 31, W).astype(np.float64) * rng.uniform(0.5, 1.0, W)
+    elif shape == "tiny_rows":
+        base = rng.uniform(0.5, 1.0, W)
+    else:
+        base = rng.uniform(0.5, 1.0, W) * np.where(k % 2 == 0, 1.0, -1.0)
+    E = _near_tie_table(rng, N, base.astype(np.float32))
+    if shape == "tiny_rows":
+        E[: N // 2] *= np.float32(2.0 ** -20)          # half of the table is 2^-20 of the other half; near-ties inside both halves
+    Rm = np.ones((R, W), np.float32)
+    if shape == "alternating":
+        Rm[1] = -1.0
+    stats, _, _ = _check_exact_against_cuda_core(E, Rm, seed=7)
+    assert stats["undecided_pairs"] > 0
+
+
+@pytest.mark.parametrize("kind", [ko.COMPLEX, ko.HOLE])
+def test_tc_exact_near_ties_complex_and_hole(kind):
+    N, R, W = 512, 3, 64
+    rng = np.random.default_rng(11)
+    E = _near_tie_table(rng, N, rng.uniform(-1, 1, W).astype(np.float32))
+    Rm = rng.uniform(-1, 1, (R, W)).astype(np.float32)
+    _check_exact_against_cuda_core(E, Rm, kind=kind, Q=96, seed=5)
