@@ -279,6 +279,8 @@ def main():
     model = KGEkeras.ComplEx(e_dim=C5["W"] // 2, r_dim=C5["W"] // 2, num_entities=C5["N"], num_relations=C5["R"], dp=0.0,
                              init_entities=E_h.numpy(), init_relations=R_h.numpy())
     eng = model._engine_()
+    if world > 1:
+        eng.comm_init_from_torch()     # the partial counts are summed by the library's own NCCL binding (kgeb_allreduce_counts)
     tri, csr_t, csr_h = c5_queries()
     tri_d = torch.from_numpy(tri).to(dev)
     csr_t_d = tuple(torch.from_numpy(a).to(dev) for a in csr_t)
@@ -393,6 +395,8 @@ def sec_train_c2(args, rank, world, dev, barrier, max_over_ranks, timed_passes, 
     rng = np.random.default_rng(0)
     E0, R0 = glorot(rng, N, d), glorot(rng, R, d)
     eng = Engine(abi.TRANSE_L1, N, R, d, d, gamma=w["gamma"], E=E0, R=R0)
+    if world > 1:
+        eng.comm_init_from_torch()
     brng = np.random.default_rng(1000 + rank)
     tsteps, twarm = 50, 5
     nb = tsteps + twarm
@@ -471,6 +475,8 @@ def sec_eval_c3(args, rank, world, dev, barrier, max_over_ranks, timed_passes, p
     c = C3
     trng = np.random.default_rng(11)
     teng = Engine(abi.COMPLEX, c["N"], c["R"], c["W"], c["W"], E=glorot(trng, c["N"], c["W"]), R=glorot(trng, c["R"], c["W"]))
+    if world > 1:
+        teng.comm_init_from_torch()
     ttri = torch.from_numpy(synth_triples(trng, c["triples"], c["N"], c["R"])).to(dev)
     tct = tuple(torch.from_numpy(a).to(dev) for a in synth_filter_csr(trng, c["triples"], c["N"], 5.4))
     tch = tuple(torch.from_numpy(a).to(dev) for a in synth_filter_csr(trng, c["triples"], c["N"], 23.5))
@@ -501,7 +507,14 @@ def sec_train_sharded_c5(args, rank, world, dev, barrier, max_over_ranks, timed_
     out = {}
     if True:
         from KGEkeras._sharded import ShardedTrainer
-        st = ShardedTrainer(abi.COMPLEX, C5["N"], C5["R"], C5["W"], C5["W"], seed=5)
+        comm = None
+        if world > 1:      # the row exchange runs over the library's own NCCL binding (kgeb_alltoall_rows)
+            import torch.distributed as dist
+            from KGEkeras._engine import comm_unique_id
+            box = [comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            comm = (box[0], rank, world)
+        st = ShardedTrainer(abi.COMPLEX, C5["N"], C5["R"], C5["W"], C5["W"], seed=5, comm=comm)
         srng = np.random.default_rng(500 + rank)
         ssteps, swarm = 5, 2
         sb = torch.from_numpy(np.stack([srng.integers(0, C5["N"], (ssteps + swarm, C5["B"])), srng.integers(0, C5["R"], (ssteps + swarm, C5["B"])),

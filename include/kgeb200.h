@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define KGEB_VERSION 100 /* 0.1.0 */
+#define KGEB_VERSION 110 /* 0.1.1: fp16 exact ranking planes, kgeb_comm_* */
 #if defined(__GNUC__)
 #define KGEB_API __attribute__((visibility("default")))
 #else
@@ -275,6 +275,32 @@ KGEB_API int kgeb_rows_gather(kgeb_ctx* ctx, const float* P, int width, int ld, 
 /* G[idx[i], :width] += src[i, :width]; touched[idx[i]] = 1 (gradient rows returned to their owner; duplicates add up) */
 KGEB_API int kgeb_rows_scatter_add(kgeb_ctx* ctx, float* G, int width, int ld, uint8_t* touched, const int32_t* idx, int64_t n,
                           const float* src, kgeb_stream stream);
+
+/* ---- collectives of the sharded paths: NCCL over NVLink behind the C ABI ------------------------------------
+ * The reference is one Python process (tests.py:130-134) and has no counterpart; these are what a host without
+ * torch.distributed binds to shard (a) the 1-N ranking -- every GPU ranks all queries against its entity rows and the int32
+ * partial counts are summed -- and (b) the 1M-entity training step -- requested rows travel owners -> requesters, gradient rows
+ * travel back.  NCCL is loaded at run time (libnccl.so.2; KGEB_NCCL_LIB overrides the name): KGEB_ERR_UNSUPPORTED if absent.
+ * One communicator per context; every call is enqueued on the caller's stream and never synchronises. */
+#define KGEB_COMM_ID_BYTES 128
+/* rank 0 fills id_out[KGEB_COMM_ID_BYTES] (ncclGetUniqueId) and hands the bytes to the other ranks by any side channel */
+KGEB_API int kgeb_comm_unique_id(void* id_out);
+KGEB_API int kgeb_comm_version(void);                       /* NCCL version code of the loaded library, or KGEB_ERR_UNSUPPORTED */
+/* collective: every rank of `world` calls it with the same id (ncclCommInitRank on the context's device) */
+KGEB_API int kgeb_comm_init(kgeb_ctx* ctx, const void* id, int rank, int world);
+/* orderly teardown (ncclCommDestroy): CUDA graphs that captured collectives of this communicator must be destroyed first --
+ * NCCL waits for them.  kgeb_destroy on a context that still has a communicator aborts it instead (never blocks). */
+KGEB_API int kgeb_comm_destroy(kgeb_ctx* ctx);
+KGEB_API int kgeb_comm_info(const kgeb_ctx* ctx, int* rank, int* world);   /* (0, 1) without a communicator */
+/* counts[n] <- sum over the ranks, in place: rank = 1 + the summed partial counts of kgeb_rank_1n / kgeb_rank_1n_tc */
+KGEB_API int kgeb_allreduce_counts(kgeb_ctx* ctx, int32_t* counts, int64_t n, kgeb_stream stream);
+/* buf[n] <- sum over the ranks (replicated relation gradient, loss); flags[n] <- max over the ranks (touched flags) */
+KGEB_API int kgeb_allreduce_f32(kgeb_ctx* ctx, float* buf, int64_t n, kgeb_stream stream);
+KGEB_API int kgeb_allreduce_flags(kgeb_ctx* ctx, uint8_t* flags, int64_t n, kgeb_stream stream);
+/* rows of `width` floats: `send` holds send_rows[g] rows for rank g, concatenated in rank order; `recv` gets recv_rows[g] rows
+ * from rank g in rank order.  send_rows / recv_rows are HOST arrays of length world (grouped ncclSend / ncclRecv). */
+KGEB_API int kgeb_alltoall_rows(kgeb_ctx* ctx, const float* send, const int64_t* send_rows, float* recv, const int64_t* recv_rows,
+                       int width, kgeb_stream stream);
 
 /* ---- literal branch of EmbeddingModel.call, models.py:114-120,152-158 (the reference harness trains it: tests.py:113,125-126):
  *      s' = act([Dropout(E[s]) | Dropout(L[s])] W + b) before the score function, one shared Dense for s and o.

@@ -22,6 +22,7 @@ SIDE_TAIL, SIDE_HEAD = 0, 1
 TC_BF16, TC_BF16X3_EXACT = 0, 1
 TC_F16X3_EXACT = TC_BF16X3_EXACT   # the exact mode's planes are fp16 since round 2; the first name is kept
 ACT_KINDS = {None: 0, 'linear': 0, 'tanh': 1, 'relu': 2, 'sigmoid': 3}   # Keras activation names served by the literal Dense
+COMM_ID_BYTES = 128
 TIMED_RANK_TC, TIMED_RANK_REFINE, TIMED_RANK_TILE, TIMED_TRAIN, TIMED_OPT, TIMED_AUX = range(6)
 
 LOSS_KINDS = {  # reference names, utils.py:321-330
@@ -81,6 +82,15 @@ PROTOTYPES = {
     "kgeb_count_greater": (_i, [_p, _p, _i64, _i64, _p, _p]),
     "kgeb_rows_gather": (_i, [_p, _p, _i, _i, _p, _i64, _p, _p]),
     "kgeb_rows_scatter_add": (_i, [_p, _p, _i, _i, _p, _p, _i64, _p, _p]),
+    "kgeb_comm_unique_id": (_i, [_p]),
+    "kgeb_comm_version": (_i, []),
+    "kgeb_comm_init": (_i, [_p, _p, _i, _i]),
+    "kgeb_comm_destroy": (_i, [_p]),
+    "kgeb_comm_info": (_i, [_p, C.POINTER(_i), C.POINTER(_i)]),
+    "kgeb_allreduce_counts": (_i, [_p, _p, _i64, _p]),
+    "kgeb_allreduce_f32": (_i, [_p, _p, _i64, _p]),
+    "kgeb_allreduce_flags": (_i, [_p, _p, _i64, _p]),
+    "kgeb_alltoall_rows": (_i, [_p, _p, C.POINTER(_i64), _p, C.POINTER(_i64), _i, _p]),
     "kgeb_rows_concat": (_i, [_p, _p, _i, _i, _p, _i, _i, _p, _i64, _p, _i, _p]),
     "kgeb_rows_concat_bwd": (_i, [_p, _p, _i, _i, _p, _i64, _p, _i, _p, _p]),
     "kgeb_sgemm": (_i, [_p, _i, _i, _i64, _i, _i, _p, _i, _p, _i, _p, _i, _i, _p]),

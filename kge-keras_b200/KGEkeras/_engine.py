@@ -45,6 +45,13 @@ def as_idx(x, device):
     return t.to(torch.int32).contiguous()
 
 
+def comm_unique_id():
+    """128 bytes identifying a new NCCL communicator (rank 0 calls this and ships the bytes to the other ranks)."""
+    buf = C.create_string_buffer(abi.COMM_ID_BYTES)
+    abi.check(abi.lib().kgeb_comm_unique_id(buf))
+    return buf.raw
+
+
 class Engine:
     """Tables + gradient/optimizer buffers of one model on one GPU, bound to a kgeb context."""
 
@@ -163,6 +170,43 @@ class Engine:
         if self._ss_ws is None or self._ss_ws.numel() < need:
             self._ss_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
             self._check(self.lib.kgeb_set_grad_sortseg(self.ctx, _ptr(self._ss_ws), self._ss_ws.numel()))
+
+    # ---- collectives behind the C ABI (comm.cu) --------------------------------------------------------------------
+    comm_rank, comm_world = 0, 1
+
+    def comm_init(self, id_bytes, rank, world):
+        """Join an NCCL communicator through the library's own binding (kgeb_comm_init): no torch.distributed involved.
+        `id_bytes` = the 128 bytes rank 0 obtained from `comm_unique_id()` and handed to the other ranks."""
+        if len(id_bytes) != abi.COMM_ID_BYTES:
+            raise ValueError(f"an NCCL unique id has {abi.COMM_ID_BYTES} bytes, got {len(id_bytes)}")
+        buf = C.create_string_buffer(bytes(id_bytes), abi.COMM_ID_BYTES)
+        self._check(self.lib.kgeb_comm_init(self.ctx, buf, int(rank), int(world)))
+        self.comm_rank, self.comm_world = int(rank), int(world)
+        return self
+
+    def comm_init_from_torch(self, group=None):
+        """Same, with the unique id carried to the other ranks by an existing torch.distributed group (one broadcast)."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        return self.comm_init(box[0], rank, world)
+
+    def comm_destroy(self):
+        """Orderly teardown.  NCCL waits for every CUDA graph that captured one of the communicator's collectives, so the
+        captured passes of this engine's RankPlans are dropped first (they are re-captured on demand)."""
+        for plan in list(getattr(self, "_plans", ())):
+            plan.graph = None
+        torch.cuda.synchronize()
+        self._check(self.lib.kgeb_comm_destroy(self.ctx))
+        self.comm_rank, self.comm_world = 0, 1
+
+    def allreduce_counts(self, counts):
+        """In-place sum of int32 partial rank counts over the communicator's ranks, on the current stream."""
+        if counts.dtype != torch.int32 or not counts.is_contiguous():
+            raise ValueError("allreduce_counts needs a contiguous int32 tensor")
+        self._check(self.lib.kgeb_allreduce_counts(self.ctx, _ptr(counts), counts.numel(), _stream()))
+        return counts
 
     # ---- dropout ------------------------------------------------------------------------------------------------
     def set_dropout(self, p=0.0, seed=0, offset=0, stream_id=0):
@@ -484,8 +528,15 @@ class RankPlan:
             cap = int(worklist_cap) if worklist_cap else min(2 ** 31 - 2, max(1 << 20, Q * (64 + (self.r1 - self.r0) // 128)))
             self._alloc_ws(cap)
         self.graph = None
+        if not hasattr(eng, "_plans"):
+            import weakref
+            eng._plans = weakref.WeakSet()
+        eng._plans.add(self)
         self.dist_on = False
-        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        # the partial counts are summed by the library's own NCCL binding when the engine joined a communicator
+        # (kgeb_comm_init: the all-reduce is then part of the enqueued pass and of its CUDA graph), else by torch.distributed
+        self.kgeb_comm = eng.comm_world > 1
+        if not self.kgeb_comm and (group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.dist_on = torch.distributed.get_world_size(group) > 1
 
     def _alloc_ws(self, cap):
@@ -504,6 +555,11 @@ class RankPlan:
         self.counts.zero_()
         if Q == 0:
             return
+        self._enqueue_sides(eng, lib, Q, st)
+        if self.kgeb_comm:
+            eng._check(lib.kgeb_allreduce_counts(eng.ctx, _ptr(self.counts), self.counts.numel(), st))
+
+    def _enqueue_sides(self, eng, lib, Q, st):
         e_shard = C.c_void_p(eng.E.data_ptr() + self.r0 * eng.we_k * 4)
         for sd in (abi.SIDE_TAIL, abi.SIDE_HEAD):
             qv, ts, (fo, fi), cnt = self.qvec[sd], self.tscore[sd], self.filt[sd], self.counts[sd]
@@ -520,7 +576,8 @@ class RankPlan:
                                             _ptr(fo), _ptr(fi), _ptr(cnt), st))
 
     def capture(self):
-        """Record the device work of one pass (everything but the all-reduce) into a CUDA graph; run() then replays it."""
+        """Record the device work of one pass into a CUDA graph; run() then replays it.  The all-reduce of the partial counts is
+        part of the graph when it goes through the library's NCCL binding (kgeb_comm_init), and follows the replay otherwise."""
         torch.cuda.synchronize()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -565,6 +622,9 @@ class RankPlan:
                 t = torch.tensor([und > self.cap], dtype=torch.int32, device=self.eng.device)
                 torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=self.group)
                 over = bool(t.item())
+            elif self.kgeb_comm:
+                t = torch.tensor([int(und > self.cap)], dtype=torch.int32, device=self.eng.device)
+                over = bool(self.eng.allreduce_counts(t).item())
             else:
                 over = und > self.cap
             if not over:

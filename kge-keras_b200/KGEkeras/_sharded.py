@@ -35,14 +35,77 @@ def _world(group=None):
     return 1, 0
 
 
-def all_to_all_rows(out, inp, out_splits, in_splits, group=None):
-    """out <- rows from every rank (out_splits[g] rows from rank g); inp rows go out (in_splits[g] rows to rank g)."""
-    world, _ = _world(group)
-    if world == 1:
-        out.copy_(inp)
+class TorchExchange:
+    """The step's collectives through torch.distributed (NCCL on GPUs, gloo in the CPU suite)."""
+    kind = "torch.distributed all_to_all_single"
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world, self.rank = _world(group)
+
+    def all_to_all(self, out, inp, out_splits, in_splits):
+        """out <- rows from every rank (out_splits[g] rows from rank g); inp rows go out (in_splits[g] rows to rank g)."""
+        if self.world == 1:
+            out.copy_(inp)
+            return out
+        dist.all_to_all_single(out, inp, output_split_sizes=list(out_splits), input_split_sizes=list(in_splits), group=self.group)
         return out
-    dist.all_to_all_single(out, inp, output_split_sizes=list(out_splits), input_split_sizes=list(in_splits), group=group)
-    return out
+
+    def sum_(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, group=self.group)
+        return t
+
+    def max_(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
+
+class KgebExchange:
+    """The same collectives through the library's own NCCL binding (kgeb_alltoall_rows / kgeb_allreduce_*, comm.cu): what a
+    host without torch.distributed uses.  `eng` is an Engine that joined a communicator (Engine.comm_init).  Index tensors
+    (int64 ids, counts) travel as rows of two floats: NCCL moves bytes, nothing is converted."""
+    kind = "libkgeb200 NCCL binding (grouped ncclSend/ncclRecv)"
+
+    def __init__(self, eng):
+        self.eng, self.lib = eng, eng.lib
+        self.world, self.rank = eng.comm_world, eng.comm_rank
+
+    def all_to_all(self, out, inp, out_splits, in_splits):
+        if self.world == 1:
+            out.copy_(inp)
+            return out
+        if out.dtype != inp.dtype or out.dtype not in (torch.float32, torch.int64):
+            raise TypeError("KgebExchange moves float32 rows or int64 ids")
+        width = (int(inp.shape[1]) if inp.dim() == 2 else 1) * (2 if inp.dtype == torch.int64 else 1)
+        snd = (C.c_int64 * self.world)(*[int(x) for x in in_splits])
+        rcv = (C.c_int64 * self.world)(*[int(x) for x in out_splits])
+        self.eng._check(self.lib.kgeb_alltoall_rows(self.eng.ctx, _ptr(inp.contiguous()), snd, _ptr(out), rcv, width, _stream()))
+        return out
+
+    def sum_(self, t):
+        if self.world > 1:
+            if t.dtype == torch.float32 and t.is_contiguous():
+                self.eng._check(self.lib.kgeb_allreduce_f32(self.eng.ctx, _ptr(t), t.numel(), _stream()))
+            elif t.dtype == torch.int32 and t.is_contiguous():
+                self.eng._check(self.lib.kgeb_allreduce_counts(self.eng.ctx, _ptr(t), t.numel(), _stream()))
+            else:
+                raise TypeError("KgebExchange.sum_ serves contiguous float32 / int32 tensors")
+        return t
+
+    def max_(self, t):
+        if self.world > 1:
+            if t.dtype == torch.uint8:
+                self.eng._check(self.lib.kgeb_allreduce_flags(self.eng.ctx, _ptr(t), t.numel(), _stream()))
+            else:
+                raise TypeError("KgebExchange.max_ serves uint8 flags")
+        return t
+
+
+def all_to_all_rows(out, inp, out_splits, in_splits, group=None):
+    """(kept for callers of the first build) out <- rows from every rank over torch.distributed."""
+    return TorchExchange(group).all_to_all(out, inp, out_splits, in_splits)
 
 
 class ExchangePlan:
@@ -56,8 +119,9 @@ class ExchangePlan:
     serve_counts list[world]
     """
 
-    def __init__(self, ids, num_entities, group=None):
-        world, rank = _world(group)
+    def __init__(self, ids, num_entities, group=None, exchange=None):
+        ex = exchange if exchange is not None else TorchExchange(group)
+        world, rank = ex.world, ex.rank
         dev = ids.device
         N = int(num_entities)
         mark = torch.zeros(N, dtype=torch.int32, device=dev)
@@ -72,10 +136,10 @@ class ExchangePlan:
         self.req_counts = [upto[g + 1] - upto[g] for g in range(world)]
         req = torch.tensor(self.req_counts, dtype=torch.int64, device=dev)
         serve = torch.empty(world, dtype=torch.int64, device=dev)
-        all_to_all_rows(serve, req, [1] * world, [1] * world, group)
+        ex.all_to_all(serve, req, [1] * world, [1] * world)
         self.serve_counts = [int(x) for x in serve.cpu().tolist()]
         serve_ids = torch.empty(sum(self.serve_counts), dtype=torch.int64, device=dev)
-        all_to_all_rows(serve_ids, self.uniq, self.serve_counts, self.req_counts, group)
+        ex.all_to_all(serve_ids, self.uniq, self.serve_counts, self.req_counts)
         self.row0 = shard_rows(N, world, rank)[0]
         self.serve_local = (serve_ids - self.row0).to(torch.int32)
 
@@ -96,7 +160,9 @@ def _stream():
 class ShardedTrainer:
     """One model, entity rows sharded over the ranks of `group` (one process per GPU)."""
 
-    def __init__(self, kind, num_entities, num_relations, we, wr, gamma=12.0, group=None, seed=0, E=None, R=None):
+    def __init__(self, kind, num_entities, num_relations, we, wr, gamma=12.0, group=None, seed=0, E=None, R=None, comm=None):
+        """comm = None: the collectives go through torch.distributed (`group`).  comm = (id_bytes, rank, world): they go through
+        the library's own NCCL binding (kgeb_comm_init / kgeb_alltoall_rows / kgeb_allreduce_*), torch.distributed is not used."""
         from ._engine import Engine
         if kind not in abi.FUSED_TRAIN_KINDS:
             # the compact-table engine below carries no per-kind parameters (pRotatE modulus, HAKE weights, HolE mode):
@@ -104,7 +170,7 @@ class ShardedTrainer:
             raise ValueError(f"ShardedTrainer serves the fused-step score kinds {abi.FUSED_TRAIN_KINDS} "
                              f"(DistMult, TransE L1/L2, ComplEx); got kind {kind}")
         self.group = group
-        self.world, self.rank = _world(group)
+        self.world, self.rank = (int(comm[2]), int(comm[1])) if comm is not None else _world(group)
         self.kind, self.N, self.R_, self.we, self.wr, self.gamma = kind, int(num_entities), int(num_relations), int(we), int(wr), float(gamma)
         self.r0, self.r1 = shard_rows(self.N, self.world, self.rank)
         if E is None:   # GlorotUniform of the GLOBAL table shape (models.py:87-88); each rank draws only its rows
@@ -118,6 +184,12 @@ class ShardedTrainer:
         self.shard = Engine(kind, max(self.r1 - self.r0, 1), self.R_, self.we, self.wr, gamma, E=E_local if self.r1 > self.r0 else None, R=R)
         self.lib, self.device = self.shard.lib, self.shard.device
         self.W = self.shard.we_k
+        if comm is not None:
+            self.shard.comm_init(comm[0], self.rank, self.world)
+            self.ex = KgebExchange(self.shard)
+        else:
+            self.ex = TorchExchange(group)
+        self.exchange_kind = self.ex.kind
         # a table-less context bound to the GLOBAL entity count: the Philox sampler draws ids in [0, N)
         h = C.c_void_p()
         abi.check(self.lib.kgeb_create(C.byref(h), self.device.index or 0, self.N, self.R_, self.shard.we_k, self.shard.wr_k,
@@ -185,35 +257,36 @@ class ShardedTrainer:
             K = neg.shape[0] // pos.shape[0]
         # every rank's mean is folded into the global mean with weight 1/world: exact only for equal batch shapes
         if self.world > 1 and self._shape_checked != (pos.shape[0], K):
-            shp = torch.tensor([pos.shape[0], K, -pos.shape[0], -K], dtype=torch.int64, device=self.device)
-            dist.all_reduce(shp, op=dist.ReduceOp.MAX, group=self.group)
-            mx = shp.cpu().tolist()
-            if mx[0] != -mx[2] or mx[1] != -mx[3]:
+            # every rank writes its (B, K) into its own slot of a zero vector; the sum hands everyone the whole list
+            shp = torch.zeros(self.world, 2, dtype=torch.int32, device=self.device)
+            shp[self.rank, 0], shp[self.rank, 1] = int(pos.shape[0]), int(K)
+            allshp = self.ex.sum_(shp).cpu().tolist()
+            if any(tuple(x) != (int(pos.shape[0]), int(K)) for x in allshp):
                 raise ValueError("ShardedTrainer.step needs the same number of positives and negatives on every rank "
-                                 f"(this rank: B={pos.shape[0]}, K={K}; max over ranks B={mx[0]}, K={mx[1]})")
+                                 f"(this rank: B={pos.shape[0]}, K={K}; all ranks: {allshp})")
             self._shape_checked = (pos.shape[0], K)
-        plan = ExchangePlan(torch.cat([pos[:, 0], pos[:, 2], neg[:, 0], neg[:, 2]]), self.N, self.group)
+        plan = ExchangePlan(torch.cat([pos[:, 0], pos[:, 2], neg[:, 0], neg[:, 2]]), self.N, exchange=self.ex)
         ce = self._compact_engine(plan.U, opt_kind)
         W, st = self.W, _stream()
         # rows: owners -> requesters
         nserve = int(plan.serve_local.numel())
         send = torch.empty(nserve, W, dtype=torch.float32, device=self.device)
         abi.check(self.lib.kgeb_rows_gather(sh.ctx, _ptr(sh.E), W, W, _ptr(plan.serve_local), nserve, _ptr(send), st), sh.ctx)
-        all_to_all_rows(ce.E[:plan.U], send, plan.req_counts, plan.serve_counts, self.group)
+        self.ex.all_to_all(ce.E[:plan.U], send, plan.req_counts, plan.serve_counts)
         # the ordinary fused step on the compact table; 1/world folds the ranks' means into the global mean
         res = ce.forward_backward(plan.remap_triples(pos), plan.remap_triples(neg), K=K, loss_kind=loss_kind, margin=margin,
                                   loss_weight=loss_weight / self.world, opt_kind=opt_kind)
         # gradient rows: requesters -> owners
         back = torch.empty(nserve, W, dtype=torch.float32, device=self.device)
-        all_to_all_rows(back, ce.gE[:plan.U], plan.serve_counts, plan.req_counts, self.group)
+        self.ex.all_to_all(back, ce.gE[:plan.U], plan.serve_counts, plan.req_counts)
         ce.gE[:plan.U].zero_()
         ce.tE[:plan.U].zero_()
         abi.check(self.lib.kgeb_rows_scatter_add(sh.ctx, _ptr(sh.gE), W, W, _ptr(sh.tE), _ptr(plan.serve_local), nserve, _ptr(back), st), sh.ctx)
         loss = res["loss"].clone()
         if self.world > 1:
-            dist.all_reduce(sh.gR, group=self.group)
-            dist.all_reduce(sh.tR, op=dist.ReduceOp.MAX, group=self.group)
-            dist.all_reduce(loss, group=self.group)
+            self.ex.sum_(sh.gR)
+            self.ex.max_(sh.tR)
+            self.ex.sum_(loss)
         sh.apply_optimizer(opt_kind, lr, beta1, beta2, eps)
         self.last = {"unique_rows": plan.U, "served_rows": nserve, "a2a_bytes_fwd": nserve * W * 4, "a2a_bytes_bwd": plan.U * W * 4}
         self._keep = (send, back, plan, pos, neg)
@@ -227,6 +300,6 @@ class ShardedTrainer:
         per = shard_rows(self.N, self.world, 0)[1]
         pad = torch.zeros(per, self.we, dtype=torch.float32, device=self.device)
         pad[: local.shape[0]] = local
-        parts = [torch.empty_like(pad) for _ in range(self.world)]
-        dist.all_gather(parts, pad, group=self.group)
-        return torch.cat(parts)[: self.N].cpu().numpy()
+        out = torch.empty(self.world * per, self.we, dtype=torch.float32, device=self.device)
+        self.ex.all_to_all(out, pad.repeat(self.world, 1), [per] * self.world, [per] * self.world)   # an all-gather as an all-to-all
+        return out[: self.N].cpu().numpy()

@@ -58,6 +58,7 @@ extern "C" int kgeb_create(kgeb_ctx** out, int device, int64_t num_entities, int
 extern "C" int kgeb_destroy(kgeb_ctx* ctx) {
   if (!ctx) return KGEB_ERR_INVALID;
   cudaSetDevice(ctx->device);
+  kgeb_internal_comm_release(ctx);
   if (ctx->d_partials) cudaFree(ctx->d_partials);
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
   if (ctx->d_sort_scratch) cudaFree(ctx->d_sort_scratch);

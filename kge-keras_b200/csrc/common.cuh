@@ -45,6 +45,8 @@ struct kgeb_ctx {
   int ev_n[KGEB_TIMED_KERNELS];      // launches bracketed since the last kgeb_kernel_ms_sum (the pool is a ring)
   // sort-segmented entity backward (kgeb_set_grad_sortseg): caller-owned workspace, NULL = vector-reduction path
   unsigned char* ss_ws; int64_t ss_bytes;
+  // NCCL communicator of the sharded paths (kgeb_comm_init, comm.cu); NULL = single GPU
+  void* comm; int comm_rank, comm_world;
 };
 
 // brackets one launch with events when timing is on (slot = kgeb_timed_kernel)
@@ -88,6 +90,8 @@ int kgeb_internal_hole_fft_train(kgeb_ctx* ctx, const float* E, const float* R, 
 int kgeb_internal_sortseg_carve(kgeb_ctx* ctx, int64_t B, int K, float** coef, int32_t** negbuf);
 int kgeb_internal_sortseg_entities(kgeb_ctx* ctx, const void* score_args, int nc, const int32_t* pos, const int32_t* neg, int64_t B, int K,
                                    float* gE, cudaStream_t st);
+// comm.cu: releases the context's NCCL communicator (kgeb_destroy)
+void kgeb_internal_comm_release(kgeb_ctx* ctx);
 // HAKE's batch-coupled score (hake_kernels.cu), reached through kgeb_score_fwd / kgeb_score_bwd
 int kgeb_internal_hake_fwd(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* idx, int64_t m, float* scores, cudaStream_t st);
 int kgeb_internal_hake_bwd(kgeb_ctx* ctx, const float* E, const float* R, const int32_t* idx, int64_t m, const float* dscore, float* gE, float* gR,

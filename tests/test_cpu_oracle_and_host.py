@@ -328,7 +328,7 @@ def test_abi_library_exports_header_symbols():
     lib = ctypes.CDLL(_abi.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _abi.lib().kgeb_version() == 100
+    assert _abi.lib().kgeb_version() == 110
     import torch
     if not torch.cuda.is_available():  # kgeb_create must fail cleanly (negative status + message), not crash
         h = ctypes.c_void_p()
