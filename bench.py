@@ -501,40 +501,59 @@ def sec_eval_c3(args, rank, world, dev, barrier, max_over_ranks, timed_passes, p
 
 
 def sec_train_sharded_c5(args, rank, world, dev, barrier, max_over_ranks, timed_passes, pk):
-    """C5 row-sharded training: owner-sharded table + Adam state, exchange of rows and gradient rows between the ranks."""
+    """C5 row-sharded training: owner-sharded table + Adam state.  Two exchanges of rows and gradient rows are measured:
+    `train_sharded_c5` = peer-mapped table, the fused kernel reads remote rows / reduces remote gradient rows over NVLink itself
+    (KGEkeras/_peer.py); `train_sharded_c5_alltoall` = compact table filled and drained by two NCCL all-to-alls (_sharded.py)."""
     import torch
     from KGEkeras import _abi as abi
     out = {}
-    if True:
-        from KGEkeras._sharded import ShardedTrainer
-        comm = None
-        if world > 1:      # the row exchange runs over the library's own NCCL binding (kgeb_alltoall_rows)
-            import torch.distributed as dist
-            from KGEkeras._engine import comm_unique_id
+    comm_of = lambda: None
+    if world > 1:      # both run over the library's own NCCL binding (kgeb_comm_*)
+        import torch.distributed as dist
+        from KGEkeras._engine import comm_unique_id
+
+        def comm_of():
             box = [comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(box, src=0)
-            comm = (box[0], rank, world)
-        st = ShardedTrainer(abi.COMPLEX, C5["N"], C5["R"], C5["W"], C5["W"], seed=5, comm=comm)
-        srng = np.random.default_rng(500 + rank)
-        ssteps, swarm = 5, 2
-        sb = torch.from_numpy(np.stack([srng.integers(0, C5["N"], (ssteps + swarm, C5["B"])), srng.integers(0, C5["R"], (ssteps + swarm, C5["B"])),
-                                        srng.integers(0, C5["N"], (ssteps + swarm, C5["B"]))], axis=2).astype(np.int32)).to(dev)
-        skw = dict(K=C5["K"], loss_kind=abi.PAIRWISE_LOGISTIC, margin=1.0, seed=99, opt_kind=abi.LAZY_ADAM, lr=1e-3)
-        for i in range(swarm):
-            st.step(sb[i], None, offset=i, **skw)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(ssteps):
-            st.step(sb[swarm + i], None, offset=swarm + i, **skw)
-        e1.record()
-        barrier()
-        s_ms = max_over_ranks(e0.elapsed_time(e1))
-        out["train_sharded_c5"] = {"workload": "C5 ComplEx dim=256, N=1e6 rows + Adam state sharded by owner; %d x %d triples per rank per step" % (C5["B"], 1 + C5["K"]),
-                                   "value": rnd(world * ssteps * C5["B"] * (1 + C5["K"]) / (s_ms * 1e-3)), "unit": "triples/s", "ms_per_step": rnd(s_ms / ssteps),
-                                   "scaling": "weak", "unique_rows_per_rank": st.last.get("unique_rows"), "exchange": getattr(st, "exchange_kind", "nccl all_to_all_single"),
-                                   "a2a_bytes_per_rank_per_step": int(st.last.get("a2a_bytes_fwd", 0) + st.last.get("a2a_bytes_bwd", 0))}
-        del st, sb
+            return (box[0], rank, world)
+    srng = np.random.default_rng(500 + rank)
+    ssteps, swarm = 5, 3
+    sb = torch.from_numpy(np.stack([srng.integers(0, C5["N"], (ssteps + swarm, C5["B"])), srng.integers(0, C5["R"], (ssteps + swarm, C5["B"])),
+                                    srng.integers(0, C5["N"], (ssteps + swarm, C5["B"]))], axis=2).astype(np.int32)).to(dev)
+    skw = dict(K=C5["K"], loss_kind=abi.PAIRWISE_LOGISTIC, margin=1.0, seed=99, opt_kind=abi.LAZY_ADAM, lr=1e-3)
+    for key in ("train_sharded_c5", "train_sharded_c5_alltoall"):
+        try:
+            if key == "train_sharded_c5":
+                from KGEkeras._peer import PeerShardedTrainer
+                st = PeerShardedTrainer(abi.COMPLEX, C5["N"], C5["R"], C5["W"], C5["W"], seed=5, comm=comm_of(), tag="bench")
+            else:
+                from KGEkeras._sharded import ShardedTrainer
+                st = ShardedTrainer(abi.COMPLEX, C5["N"], C5["R"], C5["W"], C5["W"], seed=5, comm=comm_of())
+            for i in range(swarm):
+                st.step(sb[i], None, offset=i, **skw)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(ssteps):
+                st.step(sb[swarm + i], None, offset=swarm + i, **skw)
+            e1.record()
+            barrier()
+            s_ms = max_over_ranks(e0.elapsed_time(e1))
+            out[key] = {"workload": "C5 ComplEx dim=256, N=1e6 rows + Adam state sharded by owner; %d x %d triples per rank per step" % (C5["B"], 1 + C5["K"]),
+                        "value": rnd(world * ssteps * C5["B"] * (1 + C5["K"]) / (s_ms * 1e-3)), "unit": "triples/s", "ms_per_step": rnd(s_ms / ssteps),
+                        "scaling": "weak", "exchange": st.exchange_kind}
+            if key.endswith("alltoall"):
+                out[key].update(unique_rows_per_rank=st.last.get("unique_rows"),
+                                a2a_bytes_per_rank_per_step=int(st.last.get("a2a_bytes_fwd", 0) + st.last.get("a2a_bytes_bwd", 0)))
+            else:
+                refs = 2 * C5["B"] * (1 + C5["K"])
+                out[key].update(rows_per_shard=st.per, nvlink_bytes_per_rank_per_step=int(2 * refs * C5["W"] * 4 * (world - 1) / world),
+                                note="every row reference is a 2 KiB load and a 2 KiB reduction; (world-1)/world of them cross NVLink")
+                st.close()
+            del st
+        except Exception as ex:
+            out[key] = {"error": repr(ex)[:300]}
+        torch.cuda.empty_cache()
     return out
 
 

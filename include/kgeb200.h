@@ -302,6 +302,27 @@ KGEB_API int kgeb_allreduce_flags(kgeb_ctx* ctx, uint8_t* flags, int64_t n, kgeb
 KGEB_API int kgeb_alltoall_rows(kgeb_ctx* ctx, const float* send, const int64_t* send_rows, float* recv, const int64_t* recv_rows,
                        int width, kgeb_stream stream);
 
+/* ---- one table over the GPUs of an NVLink box (the 1M-entity config; peer.cu) -----------------------------------
+ * `world` equal shards, shard g in the memory of GPU g, mapped back to back at ONE virtual range on every rank (CUDA virtual
+ * memory management, POSIX file-descriptor handles): base + row * ld * 4 addresses a row wherever it lives, so kgeb_train_fwd_bwd
+ * runs unchanged on GLOBAL ids -- its bulk-async row gathers become NVLink peer loads and its vector reductions NVLink peer
+ * reductions into the owner's gradient shard: the row exchange happens inside the scoring kernel, row by row, not as two
+ * all-to-alls around it.  Needs P2P access between the GPUs (KGEB_ERR_CUDA from kgeb_peer_import_fd otherwise).  The reference
+ * (one process, one device, tests.py:130-134) has no counterpart. */
+typedef struct kgeb_peer_table kgeb_peer_table;
+KGEB_API int64_t kgeb_peer_granularity(int device);      /* shard sizes are rounded up to this many bytes (2 MiB today) */
+/* allocates this rank's shard on `device`, reserves the range of world shards and maps the own shard at slot `rank` */
+KGEB_API int kgeb_peer_create(kgeb_peer_table** out, int device, int rank, int world, int64_t shard_bytes);
+KGEB_API int kgeb_peer_destroy(kgeb_peer_table* t);
+KGEB_API const char* kgeb_peer_last_error(const kgeb_peer_table* t);
+KGEB_API int64_t kgeb_peer_shard_bytes(const kgeb_peer_table* t);          /* after rounding */
+KGEB_API void* kgeb_peer_base(const kgeb_peer_table* t);                   /* device pointer of slot 0 */
+/* a file descriptor naming this rank's shard (owned by the table); hand it to the other ranks' processes (SCM_RIGHTS) */
+KGEB_API int kgeb_peer_export_fd(kgeb_peer_table* t, int* fd);
+/* maps rank src_rank's shard, received as a descriptor valid in this process, at slot src_rank */
+KGEB_API int kgeb_peer_import_fd(kgeb_peer_table* t, int src_rank, int fd);
+KGEB_API int kgeb_peer_complete(const kgeb_peer_table* t);                 /* 1 once every slot is mapped */
+
 /* ---- literal branch of EmbeddingModel.call, models.py:114-120,152-158 (the reference harness trains it: tests.py:113,125-126):
  *      s' = act([Dropout(E[s]) | Dropout(L[s])] W + b) before the score function, one shared Dense for s and o.
  * The step materialises the transformed rows (per-reference dropout masks make them a function of the reference, not of the

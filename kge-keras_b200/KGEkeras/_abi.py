@@ -91,6 +91,15 @@ PROTOTYPES = {
     "kgeb_allreduce_f32": (_i, [_p, _p, _i64, _p]),
     "kgeb_allreduce_flags": (_i, [_p, _p, _i64, _p]),
     "kgeb_alltoall_rows": (_i, [_p, _p, C.POINTER(_i64), _p, C.POINTER(_i64), _i, _p]),
+    "kgeb_peer_granularity": (_i64, [_i]),
+    "kgeb_peer_create": (_i, [C.POINTER(_p), _i, _i, _i, _i64]),
+    "kgeb_peer_destroy": (_i, [_p]),
+    "kgeb_peer_last_error": (C.c_char_p, [_p]),
+    "kgeb_peer_shard_bytes": (_i64, [_p]),
+    "kgeb_peer_base": (_p, [_p]),
+    "kgeb_peer_export_fd": (_i, [_p, C.POINTER(_i)]),
+    "kgeb_peer_import_fd": (_i, [_p, _i, _i]),
+    "kgeb_peer_complete": (_i, [_p]),
     "kgeb_rows_concat": (_i, [_p, _p, _i, _i, _p, _i, _i, _p, _i64, _p, _i, _p]),
     "kgeb_rows_concat_bwd": (_i, [_p, _p, _i, _i, _p, _i64, _p, _i, _p, _p]),
     "kgeb_sgemm": (_i, [_p, _i, _i, _i64, _i, _i, _p, _i, _p, _i, _p, _i, _i, _p]),
