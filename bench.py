@@ -521,11 +521,14 @@ def sec_train_sharded_c5(args, rank, world, dev, barrier, max_over_ranks, timed_
     sb = torch.from_numpy(np.stack([srng.integers(0, C5["N"], (ssteps + swarm, C5["B"])), srng.integers(0, C5["R"], (ssteps + swarm, C5["B"])),
                                     srng.integers(0, C5["N"], (ssteps + swarm, C5["B"]))], axis=2).astype(np.int32)).to(dev)
     skw = dict(K=C5["K"], loss_kind=abi.PAIRWISE_LOGISTIC, margin=1.0, seed=99, opt_kind=abi.LAZY_ADAM, lr=1e-3)
-    for key in ("train_sharded_c5", "train_sharded_c5_alltoall"):
+    for key in ("train_sharded_c5", "train_sharded_c5_local_negatives", "train_sharded_c5_alltoall"):
+        if key == "train_sharded_c5_local_negatives" and world == 1:
+            continue          # on one GPU the local range is the global one
         try:
-            if key == "train_sharded_c5":
+            if key != "train_sharded_c5_alltoall":
                 from KGEkeras._peer import PeerShardedTrainer
-                st = PeerShardedTrainer(abi.COMPLEX, C5["N"], C5["R"], C5["W"], C5["W"], seed=5, comm=comm_of(), tag="bench")
+                st = PeerShardedTrainer(abi.COMPLEX, C5["N"], C5["R"], C5["W"], C5["W"], seed=5, comm=comm_of(), tag=key,
+                                        negatives="global" if key == "train_sharded_c5" else "local")
             else:
                 from KGEkeras._sharded import ShardedTrainer
                 st = ShardedTrainer(abi.COMPLEX, C5["N"], C5["R"], C5["W"], C5["W"], seed=5, comm=comm_of())
@@ -547,8 +550,12 @@ def sec_train_sharded_c5(args, rank, world, dev, barrier, max_over_ranks, timed_
                                 a2a_bytes_per_rank_per_step=int(st.last.get("a2a_bytes_fwd", 0) + st.last.get("a2a_bytes_bwd", 0)))
             else:
                 refs = 2 * C5["B"] * (1 + C5["K"])
-                out[key].update(rows_per_shard=st.per, nvlink_bytes_per_rank_per_step=int(2 * refs * C5["W"] * 4 * (world - 1) / world),
-                                note="every row reference is a 2 KiB load and a 2 KiB reduction; (world-1)/world of them cross NVLink")
+                if key == "train_sharded_c5":
+                    out[key].update(rows_per_shard=st.per, negatives="uniform over all N entities (the reference's distribution)",
+                                    nvlink_row_load_bytes_per_rank_per_step=int(refs * C5["W"] * 4 * (world - 1) / world))
+                else:
+                    out[key].update(rows_per_shard=st.per, negatives="drawn from the rank's own shard only: NOT the reference's sampling distribution (opt-in)",
+                                    nvlink_row_load_bytes_per_rank_per_step=int(2 * C5["B"] * C5["W"] * 4 * (world - 1) / world))
                 st.close()
             del st
         except Exception as ex:

@@ -322,6 +322,12 @@ KGEB_API int kgeb_peer_export_fd(kgeb_peer_table* t, int* fd);
 /* maps rank src_rank's shard, received as a descriptor valid in this process, at slot src_rank */
 KGEB_API int kgeb_peer_import_fd(kgeb_peer_table* t, int src_rank, int fd);
 KGEB_API int kgeb_peer_complete(const kgeb_peer_table* t);                 /* 1 once every slot is mapped */
+/* Owner-side reduce of per-rank gradient buffers mapped slot_stride floats apart (a peer table whose shard is a rank's WHOLE
+ * private gradient buffer): for the owner's rows row0 .. row0+n_rows-1 whose flags[i] is set (flags may be NULL = all),
+ *   G[rank][row] += sum over the other ranks p (ascending) of G[p][row];   G[p][row] = 0
+ * -- a reduce-scatter over exactly the touched rows, pulled over NVLink by the kernel that feeds the touched-row optimizer. */
+KGEB_API int kgeb_peer_pull_add(kgeb_ctx* ctx, float* G_base, int64_t slot_stride, int world, int rank, int64_t row0, int64_t n_rows,
+                       int width, int ld, const uint8_t* flags, kgeb_stream stream);
 
 /* ---- literal branch of EmbeddingModel.call, models.py:114-120,152-158 (the reference harness trains it: tests.py:113,125-126):
  *      s' = act([Dropout(E[s]) | Dropout(L[s])] W + b) before the score function, one shared Dense for s and o.

@@ -100,6 +100,7 @@ PROTOTYPES = {
     "kgeb_peer_export_fd": (_i, [_p, C.POINTER(_i)]),
     "kgeb_peer_import_fd": (_i, [_p, _i, _i]),
     "kgeb_peer_complete": (_i, [_p]),
+    "kgeb_peer_pull_add": (_i, [_p, _p, _i64, _i, _i, _i64, _i64, _i, _i, _p, _p]),
     "kgeb_rows_concat": (_i, [_p, _p, _i, _i, _p, _i, _i, _p, _i64, _p, _i, _p]),
     "kgeb_rows_concat_bwd": (_i, [_p, _p, _i, _i, _p, _i64, _p, _i, _p, _p]),
     "kgeb_sgemm": (_i, [_p, _i, _i, _i64, _i, _i, _p, _i, _p, _i, _p, _i, _i, _p]),

@@ -174,8 +174,23 @@ class PeerShardedTrainer:
 
     comm = (id_bytes, rank, world) as for ShardedTrainer; `tag` names this trainer's descriptor exchange (same on all ranks)."""
 
-    def __init__(self, kind, num_entities, num_relations, we, wr, gamma=12.0, seed=0, E=None, R=None, comm=None, tag="t0"):
+    def __init__(self, kind, num_entities, num_relations, we, wr, gamma=12.0, seed=0, E=None, R=None, comm=None, tag="t0", grad="remote_red", negatives="global"):
+        """grad = "remote_red" (default): the kernel's 16-byte vector reductions go straight to the owner's gradient shard over NVLink.
+        grad = "pull": every rank reduces the gradient rows of its batch into a PRIVATE full-size buffer (local vector
+        reductions), and after the step's barrier the owner of a row pulls and adds the other ranks' partial rows over NVLink in
+        whole coalesced rows (kgeb_peer_pull_add) -- measured slower on 2 x B200 (9.1 vs 8.3 ms per C5 step): the remote row LOADS
+        are what saturates NVLink, the reductions ride the other direction.
+
+        negatives = "global" (default): corrupted entities are uniform over all N ids, the reference's distribution
+        (utils.py:118-119); the step equals the single-GPU step on the concatenated batch.  negatives = "local": every rank draws
+        them from ITS OWN shard only (the usual trick of distributed KGE trainers): only the positives' rows cross NVLink, but the
+        sampling distribution is NOT the reference's -- an explicit opt-in, never the default."""
         from ._engine import Engine
+        if grad not in ("pull", "remote_red"):
+            raise ValueError(f"grad must be 'pull' or 'remote_red', got {grad!r}")
+        if negatives not in ("global", "local"):
+            raise ValueError(f"negatives must be 'global' or 'local', got {negatives!r}")
+        self.grad, self.negatives = grad, negatives
         if kind not in abi.FUSED_TRAIN_KINDS:
             raise ValueError(f"PeerShardedTrainer serves the fused-step score kinds {abi.FUSED_TRAIN_KINDS}; got kind {kind}")
         self.world, self.rank = (int(comm[2]), int(comm[1])) if comm is not None else (1, 0)
@@ -194,8 +209,15 @@ class PeerShardedTrainer:
         self.r1 = min(self.N, self.r0 + self.per)
         mport = os.environ.get("MASTER_PORT", "0")
         self.tE_ = PeerTable(self.per, self.W, self.rank, self.world, f"{mport}_{tag}_E", self.device)
-        self.tG_ = PeerTable(self.per, self.W, self.rank, self.world, f"{mport}_{tag}_G", self.device)
-        g.E, g.gE = self.tE_.all, self.tG_.all
+        if grad == "pull":      # slot p = rank p's whole private gradient buffer
+            self.tG_ = PeerTable(self.world * self.per, self.W, self.rank, self.world, f"{mport}_{tag}_G", self.device)
+            assert self.tG_.rows_per_shard == self.world * self.per
+            g.E, g.gE = self.tE_.all, _RawTable(self.tG_.local.data_ptr())
+            self.G_loc = self.tG_.local[self.r0:self.r0 + self.per]
+        else:                   # slot p = rank p's shard of ONE gradient table
+            self.tG_ = PeerTable(self.per, self.W, self.rank, self.world, f"{mport}_{tag}_G", self.device)
+            g.E, g.gE = self.tE_.all, self.tG_.all
+            self.G_loc = self.tG_.local
         nloc = self.r1 - self.r0
         if E is None:   # GlorotUniform of the GLOBAL table shape (models.py:87-88); each rank draws only its rows
             lim = float(np.sqrt(6.0 / (self.N + self.we)))
@@ -223,9 +245,15 @@ class PeerShardedTrainer:
         self.lib = g.lib
         if comm is not None:
             g.comm_init(comm[0], self.rank, self.world)
+        self._sampler = None
+        if negatives == "local":   # a table-less context whose entity range is this rank's shard: kgeb_negatives draws ids in [0, nloc)
+            hs = C.c_void_p()
+            abi.check(g.lib.kgeb_create(C.byref(hs), self.device.index or 0, max(self.r1 - self.r0, 1), self.R_, g.we_k, g.wr_k, g.we_k, g.wr_k, kind, self.gamma))
+            self._sampler = hs
         self.opt_state = None
         self.steps = 0
-        self.exchange_kind = "in-kernel NVLink peer loads / reductions over one virtual table (kgeb_peer_*)"
+        self.exchange_kind = ("in-kernel NVLink peer row loads over one virtual table; gradient rows reduced locally, pulled and added by their owner (kgeb_peer_pull_add)"
+                              if grad == "pull" else "in-kernel NVLink peer row loads and 16-byte vector reductions over one virtual table (kgeb_peer_*)")
         self._sync()
 
     # -- collectives (library binding; no-ops at world 1) -----------------------------------------------------------
@@ -272,6 +300,15 @@ class PeerShardedTrainer:
         loss (device scalar)."""
         g, lib = self.g, self.lib
         _, m_e, v_e, m_r, v_r = self._owner_state(opt_kind)
+        if neg is None and self.negatives == "local":
+            if corrupt_mode != abi.CORRUPT_BOTH:
+                raise ValueError("negatives='local' serves the reference's corruption of both slots (CORRUPT_BOTH)")
+            from ._engine import as_idx
+            pos = as_idx(pos, self.device)
+            neg = torch.empty(pos.shape[0] * K, 3, dtype=torch.int32, device=self.device)
+            abi.check(lib.kgeb_negatives(self._sampler, _ptr(pos), pos.shape[0], K, seed + 7919 * self.rank, offset, corrupt_mode, _ptr(neg), _stream()), self._sampler)
+            neg[:, 0] += self.r0
+            neg[:, 2] += self.r0
         res = g.forward_backward(pos, neg, K=K, loss_kind=loss_kind, margin=margin, loss_weight=loss_weight / self.world,
                                  corrupt_mode=corrupt_mode, seed=seed + 7919 * self.rank, offset=offset, opt_kind=opt_kind)
         loss = res["loss"].clone()
@@ -284,7 +321,10 @@ class PeerShardedTrainer:
         self.steps += 1
         st = _stream()
         nloc = self.r1 - self.r0
-        E_loc, G_loc = self.tE_.local, self.tG_.local
+        E_loc, G_loc = self.tE_.local, self.G_loc
+        if self.grad == "pull" and self.world > 1 and nloc > 0:
+            g._check(lib.kgeb_peer_pull_add(g.ctx, C.c_void_p(self.tG_.all.data_ptr()), self.world * self.per * self.W, self.world, self.rank,
+                                            self.r0, nloc, self.W, self.W, C.c_void_p(g.tE.data_ptr() + self.r0), st))
         g._check(lib.kgeb_opt_update2(g.ctx, _ptr(E_loc), _ptr(G_loc), C.c_void_p(g.tE.data_ptr() + self.r0), max(nloc, 0), self.W, self.W,
                                       _ptr(m_e), _ptr(v_e), _ptr(g.Rel), _ptr(g.gR), _ptr(g.tR), self.R_, g.wr_k, g.wr_k, _ptr(m_r), _ptr(v_r),
                                       opt_kind, lr, beta1, beta2, eps, self.steps, st))
@@ -316,7 +356,10 @@ class PeerShardedTrainer:
             self._sync()
             torch.cuda.synchronize()
             self.g.comm_destroy()
-        self.g.E = self.g.gE = None
+        self.g.E = self.g.gE = self.G_loc = None
+        if self._sampler:
+            self.lib.kgeb_destroy(self._sampler)
+            self._sampler = None
         self.tE_.close()
         self.tG_.close()
 

@@ -64,3 +64,50 @@ extern "C" int kgeb_rows_scatter_add(kgeb_ctx* ctx, float* G, int width, int ld,
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
 }
+
+// ---- owner-side reduction of the peer-mapped gradient buffers (peer.cu, KGEkeras/_peer.py) ----------------------------------------
+// Every rank accumulates the gradient rows of ITS batch in a private full-size buffer (local vector reductions, as on one GPU); the
+// buffers of all ranks are peer-mapped `slot_stride` floats apart.  After the step's barrier the OWNER of a row pulls the other
+// ranks' partial rows over NVLink -- coalesced 128-bit loads, whole rows, ranks in a fixed order so the sum is reproducible -- adds
+// them to its own, and clears the remote copies on the way (NVLink is full duplex: the zero stores ride the idle direction), so a
+// reduce-scatter over exactly the touched rows happens inside one kernel, feeding the touched-row optimizer that follows.
+namespace {
+
+__global__ void __launch_bounds__(KGEB_THREADS) k_peer_pull_add(float* __restrict__ Gbase, int64_t slot_stride, int world, int rank, int64_t row0,
+                                                                int64_t n_rows, int ld, int w4, const uint8_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * KGEB_WARPS_PER_BLOCK + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * KGEB_WARPS_PER_BLOCK;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = warp0; i < n_rows; i += nw) {
+    if (flags && !__ldg(flags + i)) continue;                       // nobody referenced the row this step: every copy is zero
+    const int64_t off = (row0 + i) * ld;
+    float4* mine = reinterpret_cast<float4*>(Gbase + (int64_t)rank * slot_stride + off);
+    for (int c = lane; c < w4; c += 32) {
+      float4 acc = mine[c];
+      for (int p = 0; p < world; ++p) {
+        if (p == rank) continue;
+        float4* theirs = reinterpret_cast<float4*>(Gbase + (int64_t)p * slot_stride + off);
+        const float4 v = theirs[c];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        theirs[c] = zero;
+      }
+      mine[c] = acc;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int kgeb_peer_pull_add(kgeb_ctx* ctx, float* G_base, int64_t slot_stride, int world, int rank, int64_t row0, int64_t n_rows,
+                                  int width, int ld, const uint8_t* flags, kgeb_stream stream) {
+  if (!ctx) return KGEB_ERR_INVALID;
+  KGEB_REQUIRE(ctx, world >= 1 && rank >= 0 && rank < world && row0 >= 0 && n_rows >= 0 && width > 0 && ld >= width && slot_stride >= 0,
+               KGEB_ERR_INVALID, "peer_pull_add: bad arguments");
+  if (n_rows == 0 || world == 1) return KGEB_OK;
+  KGEB_REQUIRE(ctx, G_base, KGEB_ERR_INVALID, "peer_pull_add: null pointer");
+  KGEB_REQUIRE(ctx, width % 4 == 0 && ld % 4 == 0 && slot_stride % 4 == 0 && kgeb_aligned16(G_base), KGEB_ERR_ALIGNMENT,
+               "peer_pull_add needs width, ld, slot stride multiples of 4 floats and a 16-byte aligned base");
+  k_peer_pull_add<<<rows_grid(ctx, n_rows), KGEB_THREADS, 0, (cudaStream_t)stream>>>(G_base, slot_stride, world, rank, row0, n_rows, ld, width / 4, flags);
+  KGEB_LAUNCH_OK(ctx);
+  return KGEB_OK;
+}

@@ -34,7 +34,7 @@ def test_peer_trainer_world1_equals_engine_step(kind_name):
     N, R, d, B, K = 5000, 7, 32, 256, 4
     E, Rm, pos, neg = _case(1, B, K)
     ref = Engine(kind, N, R, d, d, 12.0, E=E, R=Rm)
-    st = PeerShardedTrainer(kind, N, R, d, d, 12.0, E=E, R=Rm, tag=kind_name)
+    st = PeerShardedTrainer(kind, N, R, d, d, 12.0, E=E, R=Rm, tag=kind_name, grad="pull" if kind_name == "COMPLEX" else "remote_red")
     for step in range(3):
         l0 = ref.train_step(pos, neg, opt_kind=abi.LAZY_ADAM, lr=0.01, K=K, loss_kind=abi.PAIRWISE_LOGISTIC, margin=1.0)["loss"].item()
         l1 = st.step(pos, neg, K=K, loss_kind=abi.PAIRWISE_LOGISTIC, margin=1.0, opt_kind=abi.LAZY_ADAM, lr=0.01).item()
@@ -67,19 +67,25 @@ def _peer_worker(rank, world, box, ret):
         time.sleep(0.01)
     N, R, d, B, K = 70000, 7, 32, 128, 4          # 128-byte rows: 16384 rows per granule -> shards of 49152 / 32768 ... rows
     E, Rm, pos, neg = _case(world, B, K, N=N)
-    st = PeerShardedTrainer(abi.COMPLEX, N, R, d, d, 12.0, E=E, R=Rm, comm=(box["id"], rank, world), tag="w")
-    ref = Engine(abi.COMPLEX, N, R, d, d, 12.0, E=E, R=Rm)           # every rank also runs the single-GPU truth
     ok = True
-    for step in range(3):
+    for grad in ("pull", "remote_red"):
+      key = "id_" + grad
+      if rank == 0:
+          box[key] = comm_unique_id()
+      while key not in box:
+          time.sleep(0.01)
+      st = PeerShardedTrainer(abi.COMPLEX, N, R, d, d, 12.0, E=E, R=Rm, comm=(box[key], rank, world), tag="w" + grad, grad=grad)
+      ref = Engine(abi.COMPLEX, N, R, d, d, 12.0, E=E, R=Rm)           # every rank also runs the single-GPU truth
+      for step in range(3):
         l1 = st.step(pos[rank * B:(rank + 1) * B], neg[rank * B * K:(rank + 1) * B * K], K=K, loss_kind=abi.PAIRWISE_HINGE, margin=1.0,
                      opt_kind=abi.LAZY_ADAM, lr=0.01).item()
         l0 = ref.train_step(pos, neg, opt_kind=abi.LAZY_ADAM, lr=0.01, K=K, loss_kind=abi.PAIRWISE_HINGE, margin=1.0)["loss"].item()
         ok = ok and abs(l0 - l1) <= 1e-5 * max(1.0, abs(l0))
-    full = st.gather_full_table()
-    ok = ok and np.allclose(full, ref.get_tables()[0], rtol=1e-4, atol=1e-5)
-    ok = ok and np.allclose(st.relation_table(), ref.get_tables()[1], rtol=1e-4, atol=1e-5)
-    ok = ok and st.per * world >= N and st.per % 16384 == 0
-    st.close()
+      full = st.gather_full_table()
+      ok = ok and np.allclose(full, ref.get_tables()[0], rtol=1e-4, atol=1e-5)
+      ok = ok and np.allclose(st.relation_table(), ref.get_tables()[1], rtol=1e-4, atol=1e-5)
+      ok = ok and st.per * world >= N and st.per % 16384 == 0
+      st.close()
     ret[rank] = bool(ok)
 
 
@@ -93,3 +99,20 @@ def test_peer_trainer_equals_single_gpu_step():
     box["port"] = _free_port()
     _spawn(_peer_worker, (world, box, ret), world, timeout=240)
     assert len(ret) == world and all(ret.values()), dict(ret)
+
+
+def test_peer_trainer_local_negatives_world1_is_global():
+    """On one GPU the rank's shard is the whole table: negatives='local' must draw the same ids as the in-kernel global stream."""
+    from KGEkeras import _abi as abi
+    from KGEkeras._peer import PeerShardedTrainer
+    N, R, d, B, K = 5000, 7, 32, 256, 4
+    E, Rm, pos, _ = _case(1, B, K)
+    a = PeerShardedTrainer(abi.COMPLEX, N, R, d, d, 12.0, E=E, R=Rm, tag="la", negatives="local")
+    b = PeerShardedTrainer(abi.COMPLEX, N, R, d, d, 12.0, E=E, R=Rm, tag="lb", negatives="global")
+    for step in range(2):
+        la = a.step(pos, None, K=K, loss_kind=abi.PAIRWISE_HINGE, margin=1.0, opt_kind=abi.LAZY_ADAM, lr=0.01, seed=3, offset=step).item()
+        lb = b.step(pos, None, K=K, loss_kind=abi.PAIRWISE_HINGE, margin=1.0, opt_kind=abi.LAZY_ADAM, lr=0.01, seed=3, offset=step).item()
+        assert abs(la - lb) <= 1e-6 * max(1.0, abs(lb))
+    np.testing.assert_allclose(a.gather_full_table(), b.gather_full_table(), rtol=1e-5, atol=1e-6)
+    a.close()
+    b.close()
