@@ -276,6 +276,15 @@ KGEB_API int kgeb_rows_gather(kgeb_ctx* ctx, const float* P, int width, int ld, 
 KGEB_API int kgeb_rows_scatter_add(kgeb_ctx* ctx, float* G, int width, int ld, uint8_t* touched, const int32_t* idx, int64_t n,
                           const float* src, kgeb_stream stream);
 
+/* ---- the split form of the backward: (unique_ids, grad_rows) for a host that keeps its own optimizer ---------------
+ * A tf.keras Embedding gives its optimizer IndexedSlices (models.py:89-112, tests.py:86); a registered gradient of the TF op shim
+ * returns exactly this pair.  Compacts the touched rows of a dense gradient buffer filled by kgeb_train_fwd_bwd / kgeb_score_bwd:
+ * ids_out[i] ascending, one per touched row, rows_out[i, :width] = G[ids_out[i], :width]; *count_out (device int64) = number of
+ * touched rows (entries beyond `cap` are counted but not written: size the outputs with cap = n_rows, or repeat).  clear != 0
+ * zeroes the consumed buffer rows and flags, leaving the buffer ready for the next step (what kgeb_opt_update does itself). */
+KGEB_API int kgeb_grad_rows_export(kgeb_ctx* ctx, float* G, uint8_t* touched, int64_t n_rows, int width, int ld, int32_t* ids_out,
+                          float* rows_out, int64_t cap, int64_t* count_out, int clear, kgeb_stream stream);
+
 /* ---- collectives of the sharded paths: NCCL over NVLink behind the C ABI ------------------------------------
  * The reference is one Python process (tests.py:130-134) and has no counterpart; these are what a host without
  * torch.distributed binds to shard (a) the 1-N ranking -- every GPU ranks all queries against its entity rows and the int32

@@ -82,6 +82,7 @@ PROTOTYPES = {
     "kgeb_count_greater": (_i, [_p, _p, _i64, _i64, _p, _p]),
     "kgeb_rows_gather": (_i, [_p, _p, _i, _i, _p, _i64, _p, _p]),
     "kgeb_rows_scatter_add": (_i, [_p, _p, _i, _i, _p, _p, _i64, _p, _p]),
+    "kgeb_grad_rows_export": (_i, [_p, _p, _p, _i64, _i, _i, _p, _p, _i64, _p, _i, _p]),
     "kgeb_comm_unique_id": (_i, [_p]),
     "kgeb_comm_version": (_i, []),
     "kgeb_comm_init": (_i, [_p, _p, _i, _i]),

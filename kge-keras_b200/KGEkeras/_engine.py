@@ -341,6 +341,20 @@ class Engine:
                                               _ptr(m_e), _ptr(v_e), _ptr(self.Rel), _ptr(self.gR), _ptr(self.tR), self.R_, self.wr_k,
                                               self.wr_k, _ptr(m_r), _ptr(v_r), opt_kind, lr, beta1, beta2, eps, self.step, _stream()))
 
+    def export_grad_rows(self, table="entity", clear=True):
+        """The backward's result as (unique_ids, grad_rows) -- the IndexedSlices a tf.keras Embedding hands its optimizer
+        (models.py:89-112) -- instead of an in-library update: ids int32 ascending, rows float32 [len(ids), width].
+        clear=True leaves the dense buffer and its flags all-zero for the next step (kgeb_grad_rows_export)."""
+        if self.gE is None:
+            raise RuntimeError("no gradient buffer yet: run forward_backward / score_bwd first")
+        G, t, n, w, wk = (self.gE, self.tE, self.N, self.we, self.we_k) if table == "entity" else (self.gR, self.tR, self.R_, self.wr, self.wr_k)
+        ids = torch.empty(n, dtype=torch.int32, device=self.device)
+        rows = torch.empty(n, wk, dtype=torch.float32, device=self.device)
+        cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._check(self.lib.kgeb_grad_rows_export(self.ctx, _ptr(G), _ptr(t), n, wk, wk, _ptr(ids), _ptr(rows), n, _ptr(cnt), 1 if clear else 0, _stream()))
+        k = int(cnt.item())
+        return ids[:k], rows[:k, :w]
+
     def l3_reg(self, w, loss):
         """models.py:10-11,79-82: loss += w*sum|E|^3, gE += 3 w E|E| on every entity row (the relation table is not regularised)."""
         self._check(self.lib.kgeb_l3_reg(self.ctx, _ptr(self.E), self.N, self.we_k, self.we_k, float(w), _ptr(self.gE), _ptr(self.tE),

@@ -303,3 +303,31 @@ def test_library_filter_csr_equals_host_builder(side, N, R, F, Q):
         eng.filter_csr(test, np.concatenate([filt, test[:1]]), code)
     eo, ei = eng.filter_csr(test, np.zeros((0, 3), np.int64), code)
     assert eo.numel() == Q + 1 and ei.numel() == 0 and int(eo.sum()) == 0
+
+
+@pytest.mark.parametrize("N", [37, 1024, 5000])
+def test_grad_rows_export_is_the_indexed_slices_of_the_backward(N):
+    """kgeb_grad_rows_export: (unique_ids, grad_rows) == the touched rows of the dense gradient buffer, ids ascending; with clear
+    the buffer is all-zero afterwards, and feeding the pair to an external optimizer reproduces the in-library SGD step."""
+    from KGEkeras import _abi as abi
+    from KGEkeras._engine import Engine
+    R, d, B, K = 5, 16, 64, 3
+    rng = np.random.default_rng(N)
+    E0, R0 = ko.glorot_uniform(rng, N, d), ko.glorot_uniform(rng, R, d)
+    pos = np.stack([rng.integers(0, N, B), rng.integers(0, R, B), rng.integers(0, N, B)], 1).astype(np.int32)
+    a, b = Engine(abi.DISTMULT, N, R, d, d, 12.0, E=E0, R=R0), Engine(abi.DISTMULT, N, R, d, d, 12.0, E=E0, R=R0)
+    kw = dict(K=K, loss_kind=abi.PAIRWISE_LOGISTIC, margin=1.0, seed=4, offset=1)
+    a.forward_backward(pos, None, opt_kind=abi.SGD, **kw)
+    dense, flags = a.gE.clone(), a.tE.clone()
+    ids, rows = a.export_grad_rows("entity", clear=True)
+    want = torch.nonzero(flags).reshape(-1)
+    assert torch.equal(ids.long(), want) and rows.shape == (len(want), d)
+    assert torch.equal(rows, dense[want][:, :d])
+    assert float(a.gE.abs().sum().item()) == 0.0 and int(a.tE.sum().item()) == 0
+    rid, rrows = a.export_grad_rows("relation", clear=True)
+    # external SGD on the exported slices == the library's own touched-row SGD
+    a.E[ids.long(), :d] -= 0.1 * rows
+    a.Rel[rid.long(), :d] -= 0.1 * rrows
+    b.train_step(pos, None, opt_kind=abi.SGD, lr=0.1, **kw)
+    np.testing.assert_array_equal(a.get_tables()[0], b.get_tables()[0])
+    np.testing.assert_array_equal(a.get_tables()[1], b.get_tables()[1])
