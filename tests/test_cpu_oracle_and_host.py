@@ -584,3 +584,24 @@ def test_hake_and_hole_constructors_without_gpu():
     h = KGEkeras.HolE(e_dim=64, r_dim=64, num_entities=5, num_relations=2, fft=False)
     assert h.fft is False and KGEkeras.HolE(e_dim=64, r_dim=64, num_entities=5, num_relations=2).fft is True
     assert KGEkeras.isint("12") and not KGEkeras.isint("1.5x")
+
+
+def test_tf_shim_type_checks_against_the_header():
+    """The TensorFlow op shim cannot be built here (no TensorFlow), but its calls into the C ABI can be type-checked: compile it with
+    -fsyntax-only against tests/tf_stub (a stand-in for the few TensorFlow classes it uses) and the REAL include/kgeb200.h."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.isfile(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("no CUDA headers")
+    src = os.path.join(ROOT, "kge-keras_b200", "tf_shim", "kgeb_tf_ops.cc")
+    r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "tests", "tf_stub"),
+                        "-I" + os.path.join(ROOT, "include"), "-I" + cuda_inc, src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    with open(src) as fh:
+        text = fh.read()
+    for op in ("KgebScore", "KgebScoreGrad", "KgebScoreGradSlices", "KgebTrainStep", "KgebRank1N"):
+        assert f'REGISTER_OP("{op}")' in text and f'Name("{op}")' in text, op
