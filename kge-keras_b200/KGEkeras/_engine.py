@@ -104,6 +104,9 @@ class Engine:
 
     def __del__(self):
         try:
+            for h in getattr(self, "_samplers", {}).values():
+                self.lib.kgeb_destroy(h)
+            self.__dict__.pop("_samplers", None)
             if getattr(self, "ctx", None):
                 self.lib.kgeb_destroy(self.ctx)
                 self.ctx = None
@@ -241,11 +244,28 @@ class Engine:
             if dropout is not None:
                 self.set_dropout(0.0)
 
-    def negatives(self, pos, K, seed, offset, corrupt_mode=abi.CORRUPT_BOTH):
+    def negatives(self, pos, K, seed, offset, corrupt_mode=abi.CORRUPT_BOTH, num_entities=None):
+        """Philox negatives.  num_entities bounds the corrupted ids ([0, num_entities), default: the whole vocabulary) -- the
+        harness draws below the number of DISTINCT entities of its split (tests.py:34), which can be smaller than the table."""
         pos = as_idx(pos, self.device)
         neg = torch.empty(pos.shape[0] * K, 3, dtype=torch.int32, device=self.device)
-        self._check(self.lib.kgeb_negatives(self.ctx, _ptr(pos), pos.shape[0], K, seed, offset, corrupt_mode, _ptr(neg), _stream()))
+        ctx = self.ctx
+        if num_entities is not None and int(num_entities) != self.N:
+            ctx = self._sampler_ctx(int(num_entities))
+        abi.check(self.lib.kgeb_negatives(ctx, _ptr(pos), pos.shape[0], K, seed, offset, corrupt_mode, _ptr(neg), _stream()), ctx)
         return neg
+
+    def _sampler_ctx(self, n):
+        """A table-less context whose entity range is [0, n): only kgeb_negatives is ever called on it."""
+        if not 0 < n <= self.N:
+            raise ValueError(f"negative-sampling range {n} outside (0, {self.N}]")
+        cache = self.__dict__.setdefault("_samplers", {})
+        if n not in cache:
+            h = C.c_void_p()
+            abi.check(self.lib.kgeb_create(C.byref(h), self.device.index or 0, n, self.R_, self.we_k, self.wr_k, self.we_k, self.wr_k,
+                                           self.kind if self.kind != abi.HAKE else abi.DISTMULT, self.gamma))
+            cache[n] = h
+        return cache[n]
 
     def oversample(self, src, m, seed, offset, stream_id=0):
         """oversample_data (utils.py:123-147) on the device: m rows drawn from src with replacement."""
@@ -254,12 +274,12 @@ class Engine:
         self._check(self.lib.kgeb_oversample(self.ctx, _ptr(src), src.shape[0], int(m), seed, offset, stream_id, _ptr(dst), _stream()))
         return dst
 
-    def device_batch(self, kg_batch, negative, seed, step):
+    def device_batch(self, kg_batch, negative, seed, step, num_entities=None):
         """The harness' DataGenerator.__get_data (tests.py:55-61) without leaving the GPU: generate_negative (both slots
         corrupted, relation kept) followed by oversample_data of both lists to the common length m = negative*len(batch).
         Returns [pos (m,3), neg (m,3)] int32 device tensors -- the unaligned lists the reference feeds its all-pairs loss."""
         pos = as_idx(kg_batch, self.device)
-        neg = self.negatives(pos, int(negative), seed, step, abi.CORRUPT_BOTH)
+        neg = self.negatives(pos, int(negative), seed, step, abi.CORRUPT_BOTH, num_entities=num_entities)
         m = max(pos.shape[0], neg.shape[0])
         return [self.oversample(pos, m, seed, step, 0), self.oversample(neg, m, seed, step, 1)]
 

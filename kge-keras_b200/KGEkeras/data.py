@@ -92,7 +92,8 @@ class DataGenerator:
 
     device=None reproduces the reference on the host (same global np.random / random consumption).  With an Engine
     (`engine=model._engine_()`) the negatives and the oversampling are drawn on the GPU by counter-based Philox
-    (seed, step) and the batch never leaves the device -- the reference's host pipeline caps any GPU step at ~1 M triples/s."""
+    (seed, step) and the batch never leaves the device -- the reference's host pipeline caps any GPU step at ~1 M triples/s.
+    Both paths corrupt with ids below `num_e`, the number of distinct entities of the split (tests.py:34)."""
 
     def __init__(self, kg, ns=10, batch_size=32, shuffle=True, engine=None, seed=0):
         self.batch_size = min(batch_size, len(kg))
@@ -118,7 +119,8 @@ class DataGenerator:
         lo, hi = index * self.batch_size, (index + 1) * self.batch_size
         if self._kg_dev is not None:
             self._step += 1
-            return self.engine.device_batch(self._kg_dev.index_select(0, self._index_dev[lo:hi]), self.ns, self.seed, self._step), None
+            return self.engine.device_batch(self._kg_dev.index_select(0, self._index_dev[lo:hi]), self.ns, self.seed, self._step,
+                                            num_entities=self.num_e), None
         return self._get_data(self.indices[self.index[lo:hi]])
 
     def on_epoch_end(self):
@@ -133,7 +135,7 @@ class DataGenerator:
         tmp_kg = self.kg[batch]
         if self.engine is not None:
             self._step += 1
-            return self.engine.device_batch(tmp_kg, self.ns, self.seed, self._step), None
+            return self.engine.device_batch(tmp_kg, self.ns, self.seed, self._step, num_entities=self.num_e), None
         negative_kg = generate_negative(tmp_kg, N=self.num_e, negative=self.ns)
         X = oversample_data(kgs=[tmp_kg, negative_kg])
         return X, None

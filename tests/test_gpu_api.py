@@ -331,3 +331,24 @@ def test_grad_rows_export_is_the_indexed_slices_of_the_backward(N):
     b.train_step(pos, None, opt_kind=abi.SGD, lr=0.1, **kw)
     np.testing.assert_array_equal(a.get_tables()[0], b.get_tables()[0])
     np.testing.assert_array_equal(a.get_tables()[1], b.get_tables()[1])
+
+
+def test_device_generator_draws_negatives_below_the_splits_entity_count():
+    """the host path corrupts with ids in [0, num_e), num_e = distinct entities of the split (tests.py:34); the device path
+    must use the same bound even when the model's vocabulary is larger."""
+    import KGEkeras
+    rng = np.random.default_rng(3)
+    kg = np.stack([rng.integers(0, 40, 600), rng.integers(0, 3, 600), rng.integers(0, 40, 600)], 1)      # ids < 40 ...
+    m = KGEkeras.DistMult(e_dim=8, r_dim=8, num_entities=500, num_relations=3, dp=0.0)                    # ... vocabulary of 500
+    gen = KGEkeras.DataGenerator(kg, ns=5, batch_size=128, engine=m._engine_(), seed=1)
+    assert gen.num_e == len(np.unique(kg[:, [0, 2]])) <= 40
+    seen = 0
+    for i in range(len(gen)):
+        (pos, neg), _ = gen[i]
+        neg = neg.cpu().numpy()
+        assert neg[:, [0, 2]].max() < gen.num_e and neg[:, [0, 2]].min() >= 0
+        seen = max(seen, int(neg[:, [0, 2]].max()))
+    assert seen >= gen.num_e - 3          # the whole range is used
+    # full-vocabulary bound: unchanged default
+    neg = m._engine_().negatives(kg[:128], 8, 1, 1).cpu().numpy()
+    assert neg[:, [0, 2]].max() > 60
