@@ -191,7 +191,7 @@ def run_reference(args, rank, world):
     qps = n * 2 * per_step / float(np.sum(times))
     line = {
         "impl": "reference", "metric": "filtered_eval_queries_per_s", "value": rnd(qps), "unit": "queries/s",
-        "n_gpus": args.gpus, "steps": n, "warmup": warm, "ms_per_step": rnd(1e3 * float(np.mean(times))),
+        "n_gpus": args.gpus, "steps": n, "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup, "ms_per_step": rnd(1e3 * float(np.mean(times))),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": headline_config(args),
         "cpu_baseline": {"value": rnd(qps), "unit": "queries/s", "cores": threads, "kind": "port",
@@ -350,19 +350,23 @@ def main():
     line = {
         "metric": "filtered_eval_queries_per_s", "value": rnd(hx["value"]), "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warm,
         "ms_per_step": rnd(hx["ms_per_step"]), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "bf16x3+f32", "data": "synthetic",
+        "dtype": "f16x3+f32", "data": "synthetic",
         "config": headline_config(args),
         "e2e": e2e,
         "gpu_launches": int(hx["launches"]),
         "kernel_ms": {"k_rank_tc (one side, this rank's shard)": rnd(hx["k_rank_tc_ms"]), "exact re-scoring k_seqk_pairs (one side)": rnd(hx["refine_ms"]),
                       "undecided_pairs_per_pass": hx["undecided_pairs"]},
-        "roofline": {"bound": "tensor", "kernel": "k_rank_tc (exact mode: 3 MMAs per k-step on the hi/lo bf16 planes)",
-                     "achieved": rnd(hx["alg_tflops"]), "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": rnd(hx["alg_tflops"] / pk["bf16_tflops"]),
-                     "pipe_frac_issued_mmas": rnd(hx["issued_tflops"] / pk["bf16_tflops"]), "traffic": ncu_traffic("k_rank_tc_exact_c5"),
-                     "peak_source": pk["source"] + ", burst", "algorithmic": "2*Q*N*Kc flops per launch (SURVEY 8d), Q=16384, N=rows of this rank, Kc=512"},
+        # the kernel runs tens of milliseconds back to back inside a long step: the SUSTAINED measured peak is its denominator
+        "roofline": {"bound": "tensor", "kernel": "k_rank_tc (exact mode: 3 MMAs per k-step on the scaled hi/lo fp16 planes)",
+                     "achieved": rnd(hx["alg_tflops"]), "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": rnd(hx["alg_tflops"] / pk["bf16_sustained"]),
+                     "pipe_frac_issued_mmas": rnd(hx["issued_tflops"] / pk["bf16_sustained"]), "frac_of_burst_peak": rnd(hx["alg_tflops"] / pk["bf16_tflops"]),
+                     "traffic": ncu_traffic("k_rank_tc_exact_c5"),
+                     "peak_source": pk["source"] + ": sustained 16-bit dense rate (kernel timed inside a long step); burst = %g" % pk["bf16_tflops"],
+                     "algorithmic": "2*Q*N*Kc flops per launch (SURVEY 8d), Q=16384, N=rows of this rank, Kc=512; the exact mode issues 3x that"},
         "approx_bf16": {"value": rnd(ha["value"]), "unit": "queries/s", "ms_per_step": rnd(ha["ms_per_step"]), "k_rank_tc_ms": rnd(ha["k_rank_tc_ms"]),
-                        "roofline": {"bound": "tensor", "achieved": rnd(ha["alg_tflops"]), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                                     "frac": rnd(ha["alg_tflops"] / pk["bf16_tflops"]), "traffic": ncu_traffic("k_rank_tc_bf16_c5")},
+                        "roofline": {"bound": "tensor", "achieved": rnd(ha["alg_tflops"]), "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                                     "frac": rnd(ha["alg_tflops"] / pk["bf16_sustained"]), "frac_of_burst_peak": rnd(ha["alg_tflops"] / pk["bf16_tflops"]),
+                                     "traffic": ncu_traffic("k_rank_tc_bf16_c5")},
                         "mean_relative_rank_difference_vs_exact": rnd(rank_moved)},
         "clocks": sampler.summary(),
     }

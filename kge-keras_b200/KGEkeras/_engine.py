@@ -52,6 +52,23 @@ def comm_unique_id():
     return buf.raw
 
 
+_CHECK_TRAIN_IDS = os.environ.get("KGEB_CHECK_IDS", "0") == "1"
+
+
+def check_ids(tri, num_entities, num_relations, what="triples"):
+    """Raise IndexError for ids outside the tables (the reference's Embedding lookup raises InvalidArgumentError on CPU and reads
+    zeros on GPU; the kernels here would read or reduce out of bounds).  One small reduction + read-back: used on the evaluation
+    inputs always and on training batches when KGEB_CHECK_IDS=1."""
+    if tri.numel() == 0:
+        return
+    lo = tri.amin(dim=0)
+    hi = tri.amax(dim=0)
+    v = torch.stack([lo, hi]).cpu().tolist()
+    if v[0][0] < 0 or v[0][1] < 0 or v[0][2] < 0 or v[1][0] >= num_entities or v[1][2] >= num_entities or v[1][1] >= num_relations:
+        raise IndexError(f"{what}: ids out of range (entities must be in [0, {num_entities}), relations in [0, {num_relations}); "
+                         f"column minima {v[0]}, maxima {v[1]})")
+
+
 class Engine:
     """Tables + gradient/optimizer buffers of one model on one GPU, bound to a kgeb context."""
 
@@ -302,8 +319,12 @@ class Engine:
         and the negative call, models.py:144-150)."""
         pos = as_idx(pos, self.device)
         B = pos.shape[0]
+        if _CHECK_TRAIN_IDS:
+            check_ids(pos, self.N, self.R_, "positive triples")
         if neg is not None:
             neg = as_idx(neg, self.device)
+            if _CHECK_TRAIN_IDS:
+                check_ids(neg, self.N, self.R_, "negative triples")
             if pair_mode == abi.PAIRED or not abi.is_pairwise(loss_kind):
                 if neg.shape[0] % B != 0 and abi.is_pairwise(loss_kind):
                     raise ValueError("PAIRED pairwise loss needs len(neg) to be a multiple of len(pos)")
@@ -394,6 +415,9 @@ class Engine:
         target is in its filter set -- the reference's list.remove crashes there (utils.py:169-171)."""
         q = as_idx(queries, self.device)
         f = as_idx(filtering_triples, self.device) if len(filtering_triples) else None
+        check_ids(q, self.N, self.R_, "filter_csr queries")
+        if f is not None:
+            check_ids(f, self.N, self.R_, "filtering_triples")
         Q = q.shape[0]
         offs = torch.zeros(Q + 1, dtype=torch.int64, device=self.device)
         if f is None or Q == 0:
@@ -533,6 +557,7 @@ class RankPlan:
                  packed=None):
         self.eng, self.group = eng, group
         self.tri = as_idx(triples, eng.device)
+        check_ids(self.tri, eng.N, eng.R_, "test triples")
         self.Q = Q = int(self.tri.shape[0])
         self.r0, self.r1 = (0, eng.N) if row_range is None else (int(row_range[0]), int(row_range[1]))
         mode = str(mode).lower()

@@ -352,3 +352,16 @@ def test_device_generator_draws_negatives_below_the_splits_entity_count():
     # full-vocabulary bound: unchanged default
     neg = m._engine_().negatives(kg[:128], 8, 1, 1).cpu().numpy()
     assert neg[:, [0, 2]].max() > 60
+
+
+def test_out_of_range_ids_raise_on_the_evaluation_path():
+    import KGEkeras
+    from KGEkeras import utils as ku
+    m = KGEkeras.DistMult(e_dim=8, r_dim=8, num_entities=50, num_relations=3, dp=0.0)
+    good = np.asarray([[1, 0, 2], [3, 1, 4]])
+    with pytest.raises(IndexError, match="out of range"):
+        ku.validate(m, np.asarray([[1, 0, 50]]), 50, 32, good)
+    with pytest.raises(IndexError, match="out of range"):
+        ku.validate(m, good, 50, 32, np.asarray([[1, 3, 2]]))
+    with pytest.raises(IndexError, match="out of range"):
+        ku.validate(m, np.asarray([[-1, 0, 2]]), 50, 32, good)
