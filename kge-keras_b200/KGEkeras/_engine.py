@@ -465,7 +465,11 @@ class Engine:
         return counts
 
     # ---- 1-N filtered ranking on the tensor cores (DistMult / ComplEx / HolE) -------------------------------------------
-    def tc_supported(self):
+    def tc_supported(self, mode="exact"):
+        """Kinds the tcgen05 ranking kernel serves: the dot-product scores in both modes, TransE-L2 in the exact mode only (its
+        approximate single-plane mode is not built: a request for it is served by the exact CUDA-core kernel)."""
+        if self.kind == abi.TRANSE_L2:
+            return str(mode).lower() == "exact"
         return self.kind in (abi.DISTMULT, abi.COMPLEX, abi.HOLE, abi.ROTATE)
 
     def pack_entities_tc(self, mode=abi.TC_BF16X3_EXACT, row_range=None):
@@ -563,7 +567,7 @@ class RankPlan:
         mode = str(mode).lower()
         if mode not in ("exact", "bf16", "cuda"):
             raise ValueError(f"rank mode must be 'exact', 'bf16' or 'cuda', got {mode!r}")
-        self.use_tc = mode != "cuda" and eng.tc_supported() and self.r1 > self.r0 and Q > 0
+        self.use_tc = mode != "cuda" and eng.tc_supported(mode) and self.r1 > self.r0 and Q > 0
         self.mode = mode if self.use_tc else "cuda"
         self.tc_mode = abi.TC_BF16 if mode == "bf16" else abi.TC_BF16X3_EXACT
         dev = eng.device

@@ -33,6 +33,25 @@
 // The integer result is therefore identical to k_rank_tile's.  KGEB_TC_BF16 (single bf16 plane, unscaled, bound forced to 0)
 // is the approximate mode: one MMA per k-step, ranks can differ at near-ties (tolerance stated in the tests).
 //
+// TransE with the L2 norm (models.py:186-190, norm = 2) ranks by a distance, not by a dot product, but
+//   D'^2(q', e) = ||q'||^2 - 2 S,   S = q'.e - ||e||^2 / 2,      q' = fl(s + p) (tail) or fl(o - p) (head),
+// and S IS a contraction once three extra slots ride along in the LAST K=16 block(s): the entity row carries -W_e split into three
+// fp16 values (W_e = 2^(2a) ||e||^2 / 2 from a double-precision sum; hi / mid / lo parts divided by 2^15, 2^4, 2^-7), the query
+// row carries the matching powers of two.  The kernel, its pipeline and its filter epilogue are unchanged; what changes is the
+// per-query centre of the band and a few more terms in it (k_tc_l2_query, the L2 branch of the epilogue):
+//   decision   score_c > t  <=>  the reference's sequential accumulator acc_c (sum of fl(r_k^2), r_k = fl(q_k - e_k) or
+//              fl(fl(e_k + p_k) - o_k)) lies below A(t); with eps = 1.01 u (2 D_t + |gamma|), D_t = gamma - t, both roundings of
+//              gamma - sqrt(acc) are covered by   acc <= A_lo = (D_t - eps)^2  =>  counted,   acc >= A_hi = (D_t + eps)^2  =>  not
+//              (gamma <= 0, where the score is +sqrt(acc): the roles swap and the query operand is negated),
+//   reference  |acc - D'^2| <= eta D'^2 + c D',  eta = (W + 8) u (non-negative terms: the sequential sum's relative error) and, on the
+//              head side only, c = 2.1 u (||e|| + ||p|| + ||q'||) for the reference's fl(e + p) and this kernel's fl(o - p);
+//              both sides are monotone in D' beyond c/2, so checking the two boundary values X_lo, X_hi of D'^2 suffices,
+//   tensor     the band of the dot-product case with T + V and Z + 2V in place of T and Z (V = ||e||^2 / 2 <= nmax^2 / 2: the
+//              extra slots add their magnitude to at most the last two blocks) and 2^-31 V for the three-way split of W_e.
+// The operands of this mode share the exponent window: entities are scaled to [2^9, 2^10) so that W_e / 2^15 fits fp16 for every
+// width up to 4000, the query scale is the entities' or smaller (the extra slots need 2^(aQ - aE) in [2^-17, 1]; a query batch
+// 2^17 times larger than the table is declared degenerate: empty planes, every pair re-scored).
+//
 // Data movement.  Both operands are pre-packed (k_tc_pack) into the exact shared-memory image the UMMA descriptors
 // expect -- no-swizzle K-major core matrices, [tile][k-chunk][plane][row][8 x bf16] -- so one pipeline stage is two
 // contiguous bulk async copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier; no tensor map is needed.
@@ -156,12 +175,22 @@ constexpr uint32_t TC_IDESC_F16 = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | (
 constexpr uint32_t TC_IDESC_BF16 = TC_IDESC_F16 | (1u << 7) | (1u << 10);
 
 // power-of-two scale that moves a largest magnitude `amax` (given as its fp32 bits) into [2^13, 2^14); 1 for an all-zero table
-__device__ __forceinline__ float tc_scale_from_bits(uint32_t bits) {
+__device__ __forceinline__ int tc_scale_exp(uint32_t bits, int target) {
   const float amax = __uint_as_float(bits);
-  if (!(amax > 0.f) || isinf(amax)) return 1.f;
-  int a = 13 - ilogbf(amax);
-  a = a < -60 ? -60 : (a > 60 ? 60 : a);
-  return ldexpf(1.f, a);
+  if (!(amax > 0.f) || isinf(amax)) return 0;
+  const int a = target - ilogbf(amax);
+  return a < -60 ? -60 : (a > 60 ? 60 : a);
+}
+__device__ __forceinline__ float tc_scale_from_bits(uint32_t bits) { return ldexpf(1.f, tc_scale_exp(bits, 13)); }
+// L2 mode: entities to [2^9, 2^10); the query scale never exceeds the entities' and stays within 2^-17 of it.  scQ = 0 flags the
+// degenerate batch (queries more than 2^17 times larger than the table): empty query planes, every pair undecided.
+__device__ __forceinline__ void tc_l2_scales(uint32_t ebits, uint32_t qbits, float& scE, float& scQ) {
+  const int aE = tc_scale_exp(ebits, 9);
+  int aQ = tc_scale_exp(qbits, 9);
+  scE = ldexpf(1.f, aE);
+  if (__uint_as_float(qbits) > 0.f && aQ < aE - 17) { scQ = 0.f; return; }
+  if (aQ > aE || !(__uint_as_float(qbits) > 0.f)) aQ = aE;
+  scQ = ldexpf(1.f, aQ);
 }
 
 struct TcArgs {
@@ -185,6 +214,9 @@ struct TcArgs {
   int nkc, planes, qtiles, ntiles, side, qgroup;
   uint32_t idesc;
   float c_norm, c_wnorm, c_abs, t_slack;   // band = c_norm ||q|| ||e|| + c_wnorm Aq Ae + c_abs (||q|| / 2^a + ||e|| / 2^b)
+  // TransE-L2 (see the header comment): per-query arrays [6][qpad] = ||q'||^2, A_lo, A_hi, sqrt(A_hi), D_t bound, c_q
+  const float* l2q; int64_t l2_stride; int l2, l2_reverse;
+  float l2_eta, l2_c_e, l2_c_v;
 };
 
 // item -> (entity tile, query tile).  Query tiles are walked in groups of `qgroup`: inside a group the query tile varies
@@ -308,8 +340,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
     uint32_t wcnt = 0;  // pairs waiting in wbuf (warp-uniform)
     uint32_t acc = 0, acc_phase = 0;
     // exact mode: the accumulators carry the scores times 2^(a+b) (operand scales, powers of two: every product below is exact)
-    const float scE = a.escale_bits ? tc_scale_from_bits(__ldg(a.escale_bits)) : 1.f;
-    const float scQ = a.qscale_bits ? tc_scale_from_bits(__ldg(a.qscale_bits)) : 1.f;
+    float scE = a.escale_bits ? tc_scale_from_bits(__ldg(a.escale_bits)) : 1.f;
+    float scQ = a.qscale_bits ? tc_scale_from_bits(__ldg(a.qscale_bits)) : 1.f;
+    bool degenerate = false;
+    if (a.l2) {
+      tc_l2_scales(__ldg(a.escale_bits), __ldg(a.qscale_bits), scE, scQ);
+      degenerate = scQ == 0.f;
+      if (degenerate) scQ = 1.f;
+    }
     const float sc = scE * scQ;
 
     auto flush = [&]() {
@@ -337,9 +375,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
       const int64_t n0 = tile * TC_BN + chalf * 128;   // shard-local id of this warp's first column
       const float nmax = __ldg(a.emax + tile * 2 + chalf);
       const float wmax = a.ewmax ? __ldg(a.ewmax + tile * 2 + chalf) : 0.f;
-      const float band = __fmaf_rn(epsq, nmax, __fmaf_rn(epsw, wmax, absq));
-      const float hi = __fmul_rn(__fadd_rn(__fmaf_rn(fabsf(t), a.t_slack, t), band), sc);
-      const float lo = __fmul_rn(__fsub_rn(__fmaf_rn(-fabsf(t), a.t_slack, t), band), sc);
+      float band = __fmaf_rn(epsq, nmax, __fmaf_rn(epsw, wmax, absq));
+      float hi, lo;
+      if (!a.l2) {
+        hi = __fmul_rn(__fadd_rn(__fmaf_rn(fabsf(t), a.t_slack, t), band), sc);
+        lo = __fmul_rn(__fsub_rn(__fmaf_rn(-fabsf(t), a.t_slack, t), band), sc);
+      } else {
+        const int64_t qi = qok ? q : 0;
+        const float qn2 = __ldg(a.l2q + qi), A_lo = __ldg(a.l2q + a.l2_stride + qi), A_hi = __ldg(a.l2q + 2 * a.l2_stride + qi);
+        const float sA_hi = __ldg(a.l2q + 3 * a.l2_stride + qi), Dt_up = __ldg(a.l2q + 4 * a.l2_stride + qi);
+        const float c = __fmaf_rn(a.l2_c_e, nmax, __ldg(a.l2q + 5 * a.l2_stride + qi));
+        const float om = 1.f - a.l2_eta;
+        const float X_lo = __fmaf_rn(A_lo, om, -c * Dt_up);                     // acc <= A_lo is certain for D'^2 <= X_lo
+        const float y0 = (c + sA_hi) / om;
+        const float X_hi = __fmaf_rn(c, y0, A_hi) / om;                         // acc >= A_hi is certain for D'^2 >= X_hi
+        band = __fmaf_rn(a.l2_c_v * nmax, nmax, band);
+        const float slack = 4.8e-7f * (qn2 + X_hi);                            // fp32 rounding of the handful of operations here
+        float hiS = 0.5f * (qn2 - X_lo) + band + slack;                         // S >= hiS  =>  D'^2 <= X_lo
+        const float loS = 0.5f * (qn2 - X_hi) - band - slack;                   // S <= loS  =>  D'^2 >= X_hi
+        if (A_lo < 0.f || X_lo < 0.f) hiS = __int_as_float(0x7f800000);         // nothing can be that close
+        if (!a.l2_reverse) { hi = hiS * sc; lo = loS * sc; }
+        else { hi = -loS * sc; lo = -hiS * sc; }                                // the query operand was negated: S~ -> -S~
+        if (degenerate) { hi = __int_as_float(0x7f800000); lo = __int_as_float(0xff800000); }
+      }
       int cnt0 = 0;
       // cursor into this query's sorted filter list: first id at or beyond this warp's first column (global id space)
       int64_t fpos = 0, fend = 0;
@@ -443,41 +501,69 @@ __global__ void k_tc_absmax(const float* __restrict__ src, int64_t rows, int W, 
 // one thread per 16-byte output chunk: dst[tile][kchunk][plane][row][0..7].
 //   scale_bits == NULL: bf16, plane 0 = bf16(x)                                  (approximate mode, one plane)
 //   scale_bits != NULL: fp16 of y = x * 2^a, plane 0 = fp16(y), plane 1 = fp16(y - plane0)   (exact mode)
-__global__ void k_tc_pack(const float* __restrict__ src, int64_t rows, int W, int ld, int tile_rows, int nkc, int planes,
-                          int64_t ntile, const uint32_t* __restrict__ scale_bits, uint4* __restrict__ dst) {
-  const int64_t total = ntile * nkc * planes * tile_rows;
-  const float scale = scale_bits ? tc_scale_from_bits(__ldg(scale_bits)) : 1.f;
+//   l2_role (TransE-L2): 1 = entity rows: scale from tc_l2_scales, positions W..W+2 of plane 0 take extras[row][0..2] (-W_e split);
+//                        2 = query rows: scale and sign from tc_l2_scales / `negate`, positions W..W+2 take the matching powers of two
+struct TcPackArgs {
+  const float* src; int64_t rows; int W, ld, tile_rows, nkc, planes; int64_t ntile;
+  const uint32_t* scale_bits; const uint32_t* other_bits; const __half* extras; int l2_role, negate;
+  uint4* dst;
+};
+__global__ void k_tc_pack(TcPackArgs a) {
+  const int64_t total = a.ntile * a.nkc * a.planes * a.tile_rows;
+  float scale = a.scale_bits ? tc_scale_from_bits(__ldg(a.scale_bits)) : 1.f;
+  float qx[3] = {0.f, 0.f, 0.f};
+  if (a.l2_role == 1) {
+    float scQ;
+    tc_l2_scales(__ldg(a.scale_bits), 0u, scale, scQ);
+  } else if (a.l2_role == 2) {
+    float scE;
+    tc_l2_scales(__ldg(a.other_bits), __ldg(a.scale_bits), scE, scale);      // scale = scQ (0 for a degenerate batch: empty planes)
+    const float ratio = scale / scE;                                          // 2^(aQ - aE) in [2^-17, 1], or 0
+    qx[0] = ratio * 32768.f; qx[1] = ratio * 16.f; qx[2] = ratio * 0.0078125f;
+    if (a.negate) { scale = -scale; qx[0] = -qx[0]; qx[1] = -qx[1]; qx[2] = -qx[2]; }
+  }
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
-    const int row = (int)(o % tile_rows);
-    const int64_t o1 = o / tile_rows;
-    const int plane = (int)(o1 % planes);
-    const int64_t o2 = o1 / planes;
-    const int kc = (int)(o2 % nkc);
-    const int64_t tile = o2 / nkc;
-    const int64_t r = tile * tile_rows + row;
+    const int row = (int)(o % a.tile_rows);
+    const int64_t o1 = o / a.tile_rows;
+    const int plane = (int)(o1 % a.planes);
+    const int64_t o2 = o1 / a.planes;
+    const int kc = (int)(o2 % a.nkc);
+    const int64_t tile = o2 / a.nkc;
+    const int64_t r = tile * a.tile_rows + row;
+    const int k0 = kc * 8;
     float x[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) x[e] = 0.f;
-    if (r < rows) {
-      const int k0 = kc * 8;
-      if (k0 + 8 <= W) {
-        const float4 v0 = ldg4(reinterpret_cast<const float4*>(src + r * (int64_t)ld + k0));
-        const float4 v1 = ldg4(reinterpret_cast<const float4*>(src + r * (int64_t)ld + k0 + 4));
+    if (r < a.rows) {
+      if (k0 + 8 <= a.W) {
+        const float4 v0 = ldg4(reinterpret_cast<const float4*>(a.src + r * (int64_t)a.ld + k0));
+        const float4 v1 = ldg4(reinterpret_cast<const float4*>(a.src + r * (int64_t)a.ld + k0 + 4));
         x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
       } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e)
-          if (k0 + e < W) x[e] = __ldg(src + r * (int64_t)ld + k0 + e);
+          if (k0 + e < a.W) x[e] = __ldg(a.src + r * (int64_t)a.ld + k0 + e);
       }
     }
     unsigned short h[8];
-    if (scale_bits) {
+    if (a.scale_bits) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float y = __fmul_rn(x[e], scale);                  // exact: power of two, |y| < 2^14
         __half hi = __float2half_rn(y);
         if (plane == 1) hi = __float2half_rn(__fsub_rn(y, __half2float(hi)));   // the subtraction is exact in fp32
         h[e] = __half_as_ushort(hi);
+      }
+      if (a.l2_role && r < a.rows && k0 + 8 > a.W && k0 < a.W + 3) {   // the three extra slots (plane 0 only; plane 1 stays zero)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int j = k0 + e - a.W;
+          if (j >= 0 && j < 3) {
+            __half v = __float2half_rn(0.f);
+            if (plane == 0) v = a.l2_role == 1 ? a.extras[r * 4 + j] : __float2half_rn(qx[j]);   // powers of two: exact
+            h[e] = __half_as_ushort(v);
+          }
+        }
       }
     } else {
 #pragma unroll
@@ -486,7 +572,80 @@ __global__ void k_tc_pack(const float* __restrict__ src, int64_t rows, int W, in
     uint4 out;
     out.x = h[0] | ((uint32_t)h[1] << 16); out.y = h[2] | ((uint32_t)h[3] << 16);
     out.z = h[4] | ((uint32_t)h[5] << 16); out.w = h[6] | ((uint32_t)h[7] << 16);
-    dst[o] = out;
+    a.dst[o] = out;
+  }
+}
+
+// TransE-L2 entity rows: extras[r][0..2] = -(hi, mid, lo) parts of W_e = 2^(2a) ||e_r||^2 / 2, divided by 2^15, 2^4, 2^-7 so that each
+// fits fp16; the sum of squares runs in double, so W_e is exact to 2^-50 and the three-way split leaves less than 2^-33 W_e
+__global__ void k_tc_l2_extras(const float* __restrict__ src, int64_t rows, int64_t rows_padded, int W, int ld,
+                               const uint32_t* __restrict__ scale_bits, __half* __restrict__ extras) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float scE, scQ;
+  tc_l2_scales(__ldg(scale_bits), 0u, scE, scQ);
+  for (int64_t r = warp0; r < rows_padded; r += nwarps) {
+    double acc = 0.0;
+    if (r < rows)
+      for (int k = lane; k < W; k += 32) { const double x = (double)__ldg(src + r * (int64_t)ld + k); acc += x * x; }
+    acc = warp_sum_d(acc);
+    if (lane == 0) {
+      const double We = 0.5 * acc * (double)scE * (double)scE;
+      const __half e1 = __float2half_rn((float)(We * (1.0 / 32768.0)));
+      const double r1 = We - 32768.0 * (double)__half2float(e1);
+      const __half e2 = __float2half_rn((float)(r1 * (1.0 / 16.0)));
+      const double r2 = r1 - 16.0 * (double)__half2float(e2);
+      const __half e3 = __float2half_rn((float)(r2 * 128.0));
+      extras[r * 4 + 0] = __hneg(e1); extras[r * 4 + 1] = __hneg(e2); extras[r * 4 + 2] = __hneg(e3); extras[r * 4 + 3] = __float2half_rn(0.f);
+    }
+  }
+}
+
+// TransE-L2 queries (one warp each): q' = the vector whose distance to the candidate rows is ranked -- qvec itself (tail: fl(s + p))
+// or fl(o - p) from the two-part head query [p | o] -- and the per-query constants of the epilogue's L2 branch
+__global__ void k_tc_l2_query(const float* __restrict__ qvec, int qw, int W, int side, const float* __restrict__ tscore, int64_t Q,
+                              int64_t qpad, float gamma, int sub, float* __restrict__ q2, float* __restrict__ l2q) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const double u = 1.0 / 16777216.0;
+  for (int64_t q = warp0; q < qpad; q += nwarps) {
+    if (q >= Q) {
+      if (lane < 6) l2q[lane * qpad + q] = 0.f;
+      continue;
+    }
+    const float* src = qvec + q * (int64_t)qw;
+    double n2 = 0.0, p2 = 0.0;
+    for (int k = lane; k < W; k += 32) {
+      float v;
+      if (side == KGEB_SIDE_TAIL) v = src[k];
+      else { v = __fsub_rn(src[W + k], src[k]); p2 += (double)src[k] * (double)src[k]; }
+      q2[q * (int64_t)W + k] = v;
+      n2 += (double)v * (double)v;
+    }
+    n2 = warp_sum_d(n2);
+    p2 = warp_sum_d(p2);
+    if (lane == 0) {
+      const double t = (double)tscore[q];
+      double A_lo, A_hi, Dt_up;
+      if (sub) {                       // score = gamma - sqrt(acc)
+        const double Dt = (double)gamma - t, Dp = Dt > 0.0 ? Dt : 0.0;
+        const double eps = 1.01 * u * (2.0 * Dp + fabs((double)gamma)) + 1e-37;
+        A_lo = Dt > eps ? (Dt - eps) * (Dt - eps) : -1.0;
+        A_hi = (Dp + eps) * (Dp + eps);
+        Dt_up = Dp + eps;
+      } else {                         // score = +sqrt(acc): counted from (t (1 + 2u))^2 up, certainly not counted up to (t (1 - 2u))^2
+        const double tp = t > 0.0 ? t : 0.0;
+        A_lo = tp * (1.0 - 2.0 * u) * tp * (1.0 - 2.0 * u);
+        A_hi = tp * (1.0 + 2.0 * u) * tp * (1.0 + 2.0 * u) + 1e-37;
+        Dt_up = tp * (1.0 + 2.0 * u);
+      }
+      l2q[0 * qpad + q] = (float)n2;
+      l2q[1 * qpad + q] = A_lo < 0.0 ? -1.f : (float)(A_lo * (1.0 - 1e-6));          // outward: a smaller A_lo, a larger A_hi
+      l2q[2 * qpad + q] = (float)(A_hi * (1.0 + 1e-6));
+      l2q[3 * qpad + q] = (float)(sqrt(A_hi) * (1.0 + 1e-6));
+      l2q[4 * qpad + q] = (float)(Dt_up * (1.0 + 1e-6));
+      l2q[5 * qpad + q] = side == KGEB_SIDE_TAIL ? 0.f : (float)(2.1 * u * (sqrt(p2) + sqrt(n2)) * 1.001);
+    }
   }
 }
 
@@ -528,9 +687,14 @@ __global__ void k_tc_slice_max(const float* __restrict__ norms, int64_t nslices,
 }
 
 int tc_planes(int mode) { return mode == KGEB_TC_BF16X3_EXACT ? 2 : 1; }
-int tc_nkc(const kgeb_ctx* ctx) { return ((ctx->we + 15) / 16) * 2; }  // K padded to 16, in 8-element chunks
+bool tc_l2_kind(const kgeb_ctx* ctx) { return ctx->kind == KGEB_TRANSE_L2; }
+// K padded to 16, in 8-element chunks; the L2 mode appends three slots to every row
+int tc_nkc(const kgeb_ctx* ctx) { return ((ctx->we + (tc_l2_kind(ctx) ? 3 : 0) + 15) / 16) * 2; }
 int64_t tc_tiles(int64_t rows, int tile_rows) { return (rows + tile_rows - 1) / tile_rows; }
-bool tc_kind_ok(const kgeb_ctx* ctx) { return ctx->kind == KGEB_DISTMULT || ctx->kind == KGEB_COMPLEX || ctx->kind == KGEB_HOLE || ctx->kind == KGEB_ROTATE; }
+bool tc_kind_ok(const kgeb_ctx* ctx) {
+  return ctx->kind == KGEB_DISTMULT || ctx->kind == KGEB_COMPLEX || ctx->kind == KGEB_HOLE || ctx->kind == KGEB_ROTATE || tc_l2_kind(ctx);
+}
+#define KGEB_TC_KINDS_MSG "tensor-core ranking serves DistMult, ComplEx, HolE, RotatE (dot-product queries) and TransE with the L2 norm"
 size_t tc_align(size_t x) { return (x + 255) & ~(size_t)255; }
 
 int tc_grid(const kgeb_ctx* ctx, int64_t n, int threads) {
@@ -541,7 +705,7 @@ int tc_grid(const kgeb_ctx* ctx, int64_t n, int threads) {
 }
 
 // packed entity buffer: [operand image][row norms nt*256][slice max nt*2][weighted norms nt*256][their slice max nt*2][scale bits]
-struct TcPackedLayout { size_t image, norms, smax, wnorms, wmax, scale, total; };
+struct TcPackedLayout { size_t image, norms, smax, wnorms, wmax, scale, extras, total; };
 TcPackedLayout tc_packed_layout(const kgeb_ctx* ctx, int64_t n_rows, int mode) {
   const int64_t nt = tc_tiles(n_rows, TC_BN);
   TcPackedLayout L;
@@ -551,11 +715,12 @@ TcPackedLayout tc_packed_layout(const kgeb_ctx* ctx, int64_t n_rows, int mode) {
   L.wnorms = L.smax + tc_align((size_t)nt * 2 * 4);
   L.wmax = L.wnorms + tc_align((size_t)nt * TC_BN * 4);
   L.scale = L.wmax + tc_align((size_t)nt * 2 * 4);
-  L.total = L.scale + 256;
+  L.extras = L.scale + 256;                                                   // L2 mode: 4 halfs per (padded) row
+  L.total = L.extras + (tc_l2_kind(ctx) ? tc_align((size_t)nt * TC_BN * 8) : 0);
   return L;
 }
 // workspace: [header 256 B: appended, capacity, query scale bits at +16][worklist][packed queries][query norms][weighted query norms]
-struct TcWsLayout { size_t wl, packedQ, qnorm, qwnorm, total; };
+struct TcWsLayout { size_t wl, packedQ, qnorm, qwnorm, q2, l2q, total; };
 TcWsLayout tc_ws_layout(const kgeb_ctx* ctx, int64_t Q, int mode, int64_t worklist_cap) {
   const int64_t qt = tc_tiles(Q, TC_BM);
   TcWsLayout L;
@@ -563,7 +728,9 @@ TcWsLayout tc_ws_layout(const kgeb_ctx* ctx, int64_t Q, int mode, int64_t workli
   L.packedQ = L.wl + tc_align((size_t)worklist_cap * 8);
   L.qnorm = L.packedQ + tc_align((size_t)qt * tc_nkc(ctx) * tc_planes(mode) * TC_BM * 16);
   L.qwnorm = L.qnorm + tc_align((size_t)qt * TC_BM * 4);
-  L.total = L.qwnorm + tc_align((size_t)qt * TC_BM * 4);
+  L.q2 = L.qwnorm + tc_align((size_t)qt * TC_BM * 4);                         // L2 mode: q' [qt*128, W] and six per-query arrays
+  L.l2q = L.q2 + (tc_l2_kind(ctx) ? tc_align((size_t)qt * TC_BM * ctx->we * 4) : 0);
+  L.total = L.l2q + (tc_l2_kind(ctx) ? tc_align((size_t)6 * qt * TC_BM * 4) : 0);
   return L;
 }
 
@@ -577,7 +744,7 @@ extern "C" int64_t kgeb_rank_tc_packed_bytes(const kgeb_ctx* ctx, int64_t n_rows
 extern "C" int kgeb_rank_tc_pack_entities(kgeb_ctx* ctx, const float* E_shard, int64_t n_rows, int mode, void* packed,
                                           int64_t packed_bytes, kgeb_stream stream) {
   if (!ctx) return KGEB_ERR_INVALID;
-  KGEB_REQUIRE(ctx, tc_kind_ok(ctx), KGEB_ERR_UNSUPPORTED, "tensor-core ranking serves DistMult, ComplEx, HolE and RotatE (dot-product queries)");
+  KGEB_REQUIRE(ctx, tc_kind_ok(ctx), KGEB_ERR_UNSUPPORTED, KGEB_TC_KINDS_MSG);
   KGEB_REQUIRE(ctx, E_shard && packed && n_rows > 0, KGEB_ERR_INVALID, "rank_tc_pack_entities: bad arguments");
   KGEB_REQUIRE(ctx, mode == KGEB_TC_BF16 || mode == KGEB_TC_BF16X3_EXACT, KGEB_ERR_INVALID, "unknown tensor-core mode");
   KGEB_REQUIRE(ctx, ctx->we % 4 == 0 && ctx->ldE % 4 == 0 && kgeb_aligned16(E_shard) && (reinterpret_cast<uintptr_t>(packed) & 255u) == 0,
@@ -590,14 +757,26 @@ extern "C" int kgeb_rank_tc_pack_entities(kgeb_ctx* ctx, const float* E_shard, i
   const TcPackedLayout L = tc_packed_layout(ctx, n_rows, mode);
   unsigned char* base = static_cast<unsigned char*>(packed);
   uint32_t* scale_bits = reinterpret_cast<uint32_t*>(base + L.scale);
+  const bool l2 = tc_l2_kind(ctx);
+  KGEB_REQUIRE(ctx, !l2 || (exact && ctx->we <= 4000), KGEB_ERR_UNSUPPORTED, "TransE-L2 on the tensor cores: exact mode only, width <= 4000");
+  __half* extras = reinterpret_cast<__half*>(base + L.extras);
   if (exact) {
     KGEB_CUDA_OK(ctx, cudaMemsetAsync(scale_bits, 0, 256, st));
     k_tc_absmax<<<tc_grid(ctx, n_rows * (int64_t)ctx->we, 256), 256, 0, st>>>(E_shard, n_rows, ctx->we, ctx->ldE, scale_bits);
     KGEB_LAUNCH_OK(ctx);
   }
-  k_tc_pack<<<tc_grid(ctx, nt * nkc * planes * TC_BN, 256), 256, 0, st>>>(E_shard, n_rows, ctx->we, ctx->ldE, TC_BN, nkc, planes, nt,
-                                                                         exact ? scale_bits : nullptr, reinterpret_cast<uint4*>(base));
-  KGEB_LAUNCH_OK(ctx);
+  if (l2) {
+    k_tc_l2_extras<<<tc_grid(ctx, nt * TC_BN * 32, 256), 256, 0, st>>>(E_shard, n_rows, nt * TC_BN, ctx->we, ctx->ldE, scale_bits, extras);
+    KGEB_LAUNCH_OK(ctx);
+  }
+  {
+    TcPackArgs pa = {};
+    pa.src = E_shard; pa.rows = n_rows; pa.W = ctx->we; pa.ld = ctx->ldE; pa.tile_rows = TC_BN; pa.nkc = nkc; pa.planes = planes; pa.ntile = nt;
+    pa.scale_bits = exact ? scale_bits : nullptr; pa.other_bits = nullptr; pa.extras = l2 ? extras : nullptr; pa.l2_role = l2 ? 1 : 0; pa.negate = 0;
+    pa.dst = reinterpret_cast<uint4*>(base);
+    k_tc_pack<<<tc_grid(ctx, nt * nkc * planes * TC_BN, 256), 256, 0, st>>>(pa);
+    KGEB_LAUNCH_OK(ctx);
+  }
   float* enorm = reinterpret_cast<float*>(base + L.norms);
   float* ewnorm = reinterpret_cast<float*>(base + L.wnorms);
   k_tc_norms<<<tc_grid(ctx, nt * TC_BN * 32, 256), 256, 0, st>>>(E_shard, n_rows, nt * TC_BN, ctx->we, ctx->ldE, nkc / 2, 0.f, enorm,
@@ -622,7 +801,7 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
                                const int64_t* filt_offsets, const int32_t* filt_ids, int mode, void* workspace,
                                int64_t workspace_bytes, int64_t worklist_cap, int32_t* counts, kgeb_stream stream) {
   if (!ctx) return KGEB_ERR_INVALID;
-  KGEB_REQUIRE(ctx, tc_kind_ok(ctx), KGEB_ERR_UNSUPPORTED, "tensor-core ranking serves DistMult, ComplEx, HolE and RotatE (dot-product queries)");
+  KGEB_REQUIRE(ctx, tc_kind_ok(ctx), KGEB_ERR_UNSUPPORTED, KGEB_TC_KINDS_MSG);
   KGEB_REQUIRE(ctx, E_shard && packedE && qvec && tscore && triples && counts && workspace && Q >= 0 && n_rows >= 0 && row_offset >= 0,
                KGEB_ERR_INVALID, "rank_1n_tc: bad arguments");
   KGEB_REQUIRE(ctx, side == KGEB_SIDE_TAIL || side == KGEB_SIDE_HEAD, KGEB_ERR_INVALID, "unknown side");
@@ -650,15 +829,35 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
   float* qnorm = reinterpret_cast<float*>(ws + W.qnorm);
   float* qwnorm = reinterpret_cast<float*>(ws + W.qwnorm);
 
+  const bool l2 = tc_l2_kind(ctx);
+  KGEB_REQUIRE(ctx, !l2 || exact, KGEB_ERR_UNSUPPORTED, "TransE-L2 on the tensor cores: exact mode only");
+  const int64_t qpad = qt * TC_BM;
+  float* q2 = reinterpret_cast<float*>(ws + W.q2);
+  float* l2q = reinterpret_cast<float*>(ws + W.l2q);
+  const float* qsrc = qvec;          // what the operand image, the norms and the scale are taken from
+  int qld = qw;
+  const int reverse = l2 && !(ctx->gamma > 0.f);
   KGEB_CUDA_OK(ctx, cudaMemsetAsync(hdr, 0, TC_HDR_BYTES, st));
+  if (l2) {
+    k_tc_l2_query<<<tc_grid(ctx, qpad * 32, 256), 256, 0, st>>>(qvec, qw, ctx->we, side, tscore, Q, qpad, ctx->gamma, ctx->gamma > 0.f ? 1 : 0, q2, l2q);
+    KGEB_LAUNCH_OK(ctx);
+    qsrc = q2; qld = ctx->we;
+  }
   if (exact) {
-    k_tc_absmax<<<tc_grid(ctx, Q * (int64_t)ctx->we, 256), 256, 0, st>>>(qvec, Q, ctx->we, qw, qscale_bits);
+    k_tc_absmax<<<tc_grid(ctx, Q * (int64_t)ctx->we, 256), 256, 0, st>>>(qsrc, Q, ctx->we, qld, qscale_bits);
     KGEB_LAUNCH_OK(ctx);
   }
-  k_tc_pack<<<tc_grid(ctx, qt * nkc * planes * TC_BM, 256), 256, 0, st>>>(qvec, Q, ctx->we, qw, TC_BM, nkc, planes, qt,
-                                                                         exact ? qscale_bits : nullptr, reinterpret_cast<uint4*>(packedQ));
-  KGEB_LAUNCH_OK(ctx);
-  k_tc_norms<<<tc_grid(ctx, qt * TC_BM * 32, 256), 256, 0, st>>>(qvec, Q, qt * TC_BM, ctx->we, qw, nkc / 2, 0.f, qnorm, exact ? qwnorm : nullptr);
+  {
+    TcPackArgs pa = {};
+    pa.src = qsrc; pa.rows = Q; pa.W = ctx->we; pa.ld = qld; pa.tile_rows = TC_BM; pa.nkc = nkc; pa.planes = planes; pa.ntile = qt;
+    pa.scale_bits = exact ? qscale_bits : nullptr;
+    pa.other_bits = l2 ? reinterpret_cast<const uint32_t*>(static_cast<const unsigned char*>(packedE) + L.scale) : nullptr;
+    pa.extras = nullptr; pa.l2_role = l2 ? 2 : 0; pa.negate = reverse;
+    pa.dst = reinterpret_cast<uint4*>(packedQ);
+    k_tc_pack<<<tc_grid(ctx, qt * nkc * planes * TC_BM, 256), 256, 0, st>>>(pa);
+    KGEB_LAUNCH_OK(ctx);
+  }
+  k_tc_norms<<<tc_grid(ctx, qt * TC_BM * 32, 256), 256, 0, st>>>(qsrc, Q, qt * TC_BM, ctx->we, qld, nkc / 2, 0.f, qnorm, exact ? qwnorm : nullptr);
   KGEB_LAUNCH_OK(ctx);
 
   const unsigned char* pe = static_cast<const unsigned char*>(packedE);
@@ -693,10 +892,22 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
     a.c_wnorm = (float)(1.02 * 52.11 * u);
     a.c_abs = (float)(1.02 * sqrt((double)nkc * 8.0) / 33554432.0);
     a.t_slack = 2.4e-7f;
+    if (l2) {   // no sequential-dot term: the reference's own rounding lives in eta and c (acc space); Z grows by 2 V, T by V
+      a.c_norm = (float)(1.02 * 12.004 * u);
+      a.c_wnorm = (float)(1.02 * 36.1 * u);
+    }
   } else {
     a.idesc = TC_IDESC_BF16;
     a.c_norm = a.c_wnorm = a.c_abs = 0.f;
     a.t_slack = 0.f;
+  }
+  a.l2 = l2 ? 1 : 0; a.l2_reverse = reverse; a.l2q = l2q; a.l2_stride = qpad;
+  {
+    const double u = 1.0 / 16777216.0;
+    a.l2_eta = (float)((ctx->we + 8) * u * 1.001);
+    a.l2_c_e = side == KGEB_SIDE_HEAD ? (float)(2.1 * u * 1.001) : 0.f;
+    // V = ||e||^2 / 2 <= nmax^2 / 2 enters Z twice (the slots may straddle the last two blocks) and the split of W_e once
+    a.l2_c_v = (float)(1.02 * (2.0 * 36.1 * u + 1.0 / 2147483648.0) * 0.5);
   }
   static bool attr_done = false;  // per process; the attribute is per function, setting it again is harmless
   if (!attr_done) {

@@ -115,7 +115,7 @@ def test_tc_bf16_approximate_within_stated_band(kind):
             assert abs(int(got[qi]) - int(r64[qi])) <= near, (qi, got[qi], r64[qi], near)
 
 
-def test_tc_rejects_transe():
+def test_tc_rejects_transe_l1():
     abi = _abi()
     eng, E, Rm = make_engine(ko.TRANSE_L1, 100, 3, 8)
     with pytest.raises(abi.KgebError):
@@ -204,3 +204,98 @@ def test_tc_exact_near_ties_complex_and_hole(kind):
     E = _near_tie_table(rng, N, rng.uniform(-1, 1, W).astype(np.float32))
     Rm = rng.uniform(-1, 1, (R, W)).astype(np.float32)
     _check_exact_against_cuda_core(E, Rm, kind=kind, Q=96, seed=5)
+
+
+# ---- TransE with the L2 norm on the tensor cores: ||q - e||^2 = ||q||^2 - 2 (q.e - ||e||^2 / 2) ------------------------------------
+@pytest.mark.parametrize("gamma", [12.0, 0.0, -1.0])
+@pytest.mark.parametrize("side", ["tail", "head"])
+@pytest.mark.parametrize("d,N,Q", [(8, 130, 70), (100, 1000, 257), (36, 64, 64), (200, 2500, 300), (28, 700, 129)])
+def test_tc_transe_l2_counts_equal_cuda_core_and_oracle(gamma, side, d, N, Q):
+    """Integer filtered-rank counts of the tensor-core path IDENTICAL to the fp32 CUDA-core kernel and to the oracle's sequential
+    scores -- gamma > 0 (score = gamma - distance), gamma <= 0 (score = +distance, models.py:189-190: the ranking is NOT flipped),
+    widths whose three extra slots fall into the last real block (28, 36, 100, 200) and into a block of their own (8 -> 8..10)."""
+    abi = _abi()
+    from KGEkeras._engine import Engine
+    rng = np.random.default_rng(int(31 + d + 7 * gamma))
+    E, Rm = ko.glorot_uniform(rng, N, d) * 3, ko.glorot_uniform(rng, 5, d) * 3
+    eng = Engine(abi.TRANSE_L2, N, 5, d, d, gamma, E=E, R=Rm)
+    tri = rand_triples(rng, Q, N, 5)
+    known = rand_triples(rng, 4 * Q, N, 5)
+    known[:Q, :2] = tri[:, :2]
+    known[Q:2 * Q, 1:] = tri[:, 1:]
+    fh, ft = ko.build_filters([tuple(int(x) for x in r) for r in known])
+    filt = ft if side == "tail" else fh
+    offs, ids = ko.filter_csr(tri, side, filt)
+    sd = 0 if side == "tail" else 1
+    want = eng.rank_counts(tri, sd, offs, ids).cpu().numpy()
+    stats = {}
+    got = eng.rank_counts_tc(tri, sd, offs, ids, mode=abi.TC_F16X3_EXACT, stats=stats).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+    if N * Q * d <= 1000 * 257 * 100:
+        sc = ko.seqk_scores(ko.TRANSE_L2, ko.query_vectors(ko.TRANSE_L2, E, Rm, tri, side), E, side, gamma)
+        np.testing.assert_array_equal(got, (ko.ranks_from_scores(sc, tri, side, filt) - 1).astype(np.int32))
+    assert stats["undecided_pairs"] <= max(4 * Q, 0.05 * Q * N), stats
+
+
+@pytest.mark.parametrize("gamma", [12.0, -1.0])
+@pytest.mark.parametrize("profile", ["near_ties", "tiny_rows", "far_queries", "coincident"])
+def test_tc_transe_l2_band_on_unfriendly_tables(gamma, profile):
+    """near_ties: candidates that are ulp-sized steps of one row (distances from far inside to a few bands outside the target's);
+    tiny_rows: half of the table 2^-12 of the other half; far_queries: relation rows 2^6 times the entities (||q|| >> ||e||);
+    coincident: s + p == o exactly for many queries (target distance 0, score == gamma)."""
+    abi = _abi()
+    from KGEkeras._engine import Engine
+    N, R, W, Q = 768, 3, 64, 128
+    rng = np.random.default_rng(len(profile) + int(gamma))
+    base = rng.uniform(-1, 1, W).astype(np.float32)
+    E = _near_tie_table(rng, N, base, step_bits=18, spread=4000)
+    Rm = (rng.uniform(-1, 1, (R, W)) * 2.0 ** -10).astype(np.float32)
+    if profile == "tiny_rows":
+        E[: N // 2] *= np.float32(2.0 ** -12)
+    elif profile == "far_queries":
+        Rm = (rng.uniform(-1, 1, (R, W)) * 64).astype(np.float32)
+    elif profile == "coincident":
+        Rm[0] = 0.0                                      # relation 0: s + p == s, and many rows of E are bit-identical pairs
+        E[1::2] = E[0::2]
+    eng = Engine(abi.TRANSE_L2, N, R, W, W, gamma, E=E, R=Rm)
+    tri = rand_triples(rng, Q, N, R)
+    if profile == "coincident":
+        tri[: Q // 2, 1] = 0
+        tri[: Q // 2, 2] = tri[: Q // 2, 0] ^ 1          # the target is the bit-identical twin of the subject: distance exactly 0
+    stats = {}
+    for sd in (0, 1):
+        want = eng.rank_counts(tri, sd).cpu().numpy()
+        got = eng.rank_counts_tc(tri, sd, mode=abi.TC_F16X3_EXACT, stats=stats).cpu().numpy()
+        np.testing.assert_array_equal(got, want)
+
+
+def test_tc_transe_l2_shards_sum_to_whole_and_validate_uses_it():
+    abi = _abi()
+    import KGEkeras
+    from KGEkeras import utils as ku
+    N, R, d = 1500, 4, 40
+    rng = np.random.default_rng(2)
+    E, Rm = ko.glorot_uniform(rng, N, d) * 3, ko.glorot_uniform(rng, R, d) * 3
+    m = KGEkeras.TransE(e_dim=d, r_dim=d, num_entities=N, num_relations=R, norm=2, gamma=12, init_entities=E, init_relations=Rm, dp=0.0)
+    eng = m._engine_()
+    assert eng.tc_supported()
+    tri = rand_triples(rng, 300, N, R)
+    whole = eng.rank_counts(tri, 0).cpu().numpy()
+    for G in (2, 3):
+        per = -(-N // G)
+        acc = torch.zeros(len(tri), dtype=torch.int32, device="cuda")
+        for g in range(G):
+            eng.rank_counts_tc(tri, 0, row_range=(g * per, min(N, (g + 1) * per)), counts=acc, mode=abi.TC_F16X3_EXACT)
+        np.testing.assert_array_equal(acc.cpu().numpy(), whole)
+    filt = rand_triples(rng, 2000, N, R)
+    key = lambda a: (a[:, 0].astype(np.int64) * R + a[:, 1]) * N + a[:, 2]
+    filt = filt[~np.isin(key(filt), key(tri))]
+    res = ku.validate(m, tri, N, 32, filt)                      # default rank mode: exact, on the tensor cores for this kind now
+    fh, ft = ko.build_filters([tuple(int(x) for x in r) for r in filt])
+    ranks = []
+    for side, f in (("tail", ft), ("head", fh)):
+        sc = ko.seqk_scores(ko.TRANSE_L2, ko.query_vectors(ko.TRANSE_L2, E, Rm, tri, side), E, side, 12.0)
+        ranks.append(ko.ranks_from_scores(sc, tri, side, f))
+    want = ko.metrics_from_ranks(ranks[0], ranks[1])
+    for k in ("mrr", "hits@10", "mr"):
+        assert abs(res[k] - want[k]) <= 1e-6 * max(1.0, abs(want[k])), (k, res[k], want[k])
