@@ -576,32 +576,46 @@ def sec_train_large(args, rank, world, dev, barrier, max_over_ranks, timed_passe
     out = {}
     if world == 1:
         lN, lR, lW, lB, lK = C5["N"], C5["R"], C5["W"], C5["B"], C5["K"]
-        lrng = np.random.default_rng(21)
-        lim = float(np.sqrt(6.0 / (lN + lW)))
-        leng = Engine(abi.COMPLEX, lN, lR, lW, lW, E=torch.empty(lN, lW, device=dev).uniform_(-lim, lim), R=glorot(lrng, lR, lW))
-        lsteps, lwarm = 8, 2
-        lb = torch.from_numpy(np.stack([lrng.integers(0, lN, (lsteps + lwarm, lB)), lrng.integers(0, lR, (lsteps + lwarm, lB)),
-                                        lrng.integers(0, lN, (lsteps + lwarm, lB))], axis=2).astype(np.int32)).to(dev)
-        lkw = dict(K=lK, loss_kind=abi.PAIRWISE_LOGISTIC, pair_mode=abi.PAIRED, margin=1.0, corrupt_mode=abi.CORRUPT_BOTH, seed=99)
-        leng.forward_backward(lb[0], None, offset=0, **lkw, opt_kind=abi.LAZY_ADAM)
-        lU_E, lU_R = int(leng.tE.sum().item()), int(leng.tR.sum().item())
-        leng.apply_optimizer(abi.LAZY_ADAM, lr=1e-3)
-        for i in range(lwarm):
-            leng.train_step(lb[i], None, offset=i, **lkw, opt_kind=abi.LAZY_ADAM, lr=1e-3)
-        leng.set_kernel_timing(True)
-        torch.cuda.synchronize()
-        for i in range(lsteps):
-            leng.train_step(lb[lwarm + i], None, offset=lwarm + i, **lkw, opt_kind=abi.LAZY_ADAM, lr=1e-3)
-        torch.cuda.synchronize()
-        kf, ko_ = leng.kernel_ms_sum(abi.TIMED_TRAIN), leng.kernel_ms_sum(abi.TIMED_OPT)
-        lfb, lop = kf[0] / max(1, kf[1]), ko_[0] / max(1, ko_[1])
-        bstep = 28.0 * lW * (lU_E + lU_R) + 12.0 * lB
-        out["train_large_table"] = {"workload": "C5 step unsharded on one GPU (table 2 GB + Adam 4 GB + gradient 2 GB >> L2)", "batch_positives": lB,
-                                    "negatives_per_positive": lK, "unique_rows": [lU_E, lU_R], "value": rnd(lB * (1 + lK) / ((lfb + lop) * 1e-3)), "unit": "triples/s",
-                                    "kernel_ms": {"k_train_ring": rnd(lfb), "k_opt_update2": rnd(lop)},
-                                    "roofline_step": {"bound": "hbm", "achieved": rnd(bstep / ((lfb + lop) * 1e-3) / 1e9), "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                                      "frac": rnd(bstep / ((lfb + lop) * 1e-3) / 1e9 / pk["hbm_gbs"]), "traffic": ncu_traffic("c5_step")}}
-        del leng, lb
+        for key, gmode in (("train_large_table", "red"), ("train_large_table_sortseg_fused", "sortseg_fused")):
+            lrng = np.random.default_rng(21)
+            lim = float(np.sqrt(6.0 / (lN + lW)))
+            leng = Engine(abi.COMPLEX, lN, lR, lW, lW, E=torch.empty(lN, lW, device=dev).uniform_(-lim, lim), R=glorot(lrng, lR, lW))
+            leng.set_grad_mode(gmode)
+            lsteps, lwarm = 8, 3
+            lb = torch.from_numpy(np.stack([lrng.integers(0, lN, (lsteps + lwarm, lB)), lrng.integers(0, lR, (lsteps + lwarm, lB)),
+                                            lrng.integers(0, lN, (lsteps + lwarm, lB))], axis=2).astype(np.int32)).to(dev)
+            lkw = dict(K=lK, loss_kind=abi.PAIRWISE_LOGISTIC, pair_mode=abi.PAIRED, margin=1.0, corrupt_mode=abi.CORRUPT_BOTH, seed=99)
+            for i in range(lwarm):
+                leng.train_step(lb[i], None, offset=i, **lkw, opt_kind=abi.LAZY_ADAM, lr=1e-3)
+            lU_E, lU_R = int((leng.tE2 if gmode == "sortseg_fused" else leng.tE).sum().item()), lR
+            if gmode == "red":      # flags are cleared by the update: count on a forward pass of the next batch
+                leng.forward_backward(lb[lwarm], None, offset=lwarm, **lkw, opt_kind=abi.LAZY_ADAM)
+                lU_E, lU_R = int(leng.tE.sum().item()), int(leng.tR.sum().item())
+                leng.apply_optimizer(abi.LAZY_ADAM, lr=1e-3)
+            leng.set_kernel_timing(True)
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(lsteps)]
+            torch.cuda.synchronize()
+            for i in range(lsteps):
+                ev[i][0].record()
+                leng.train_step(lb[(lwarm + i) % (lsteps + lwarm)], None, offset=lwarm + 1 + i, **lkw, opt_kind=abi.LAZY_ADAM, lr=1e-3)
+                ev[i][1].record()
+            torch.cuda.synchronize()
+            lms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+            kf, ka, ko_ = leng.kernel_ms_sum(abi.TIMED_TRAIN), leng.kernel_ms_sum(abi.TIMED_AUX), leng.kernel_ms_sum(abi.TIMED_OPT)
+            bstep = 28.0 * lW * (lU_E + lU_R) + 12.0 * lB
+            out[key] = {"workload": "C5 step unsharded on one GPU (table 2 GB + Adam state 4 GB >> L2)", "backward": {
+                            "red": "vector reductions into a dense gradient buffer + touched-row update (2 launches)",
+                            "sortseg_fused": "records sorted by entity id, a warp per segment sums the row's gradient and applies LazyAdam there "
+                                             "(kgeb_train_step_sortseg: no gradient buffer, two table copies)"}[gmode],
+                        "batch_positives": lB, "negatives_per_positive": lK, "unique_rows": [lU_E, lU_R], "value": rnd(lB * (1 + lK) / (lms * 1e-3)),
+                        "unit": "triples/s", "ms_per_step": rnd(lms),
+                        "kernel_ms": {"k_train_ring": rnd(kf[0] / max(1, kf[1])), "records+sort+segments(+optimizer)": rnd(ka[0] / max(1, ka[1])),
+                                      "k_opt_update": rnd(ko_[0] / max(1, ko_[1]))},
+                        "roofline_step": {"bound": "hbm", "achieved": rnd(bstep / (lms * 1e-3) / 1e9), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                          "frac": rnd(bstep / (lms * 1e-3) / 1e9 / pk["hbm_gbs"]), "traffic": ncu_traffic("c5_step"),
+                                          "algorithmic": "28 * W * (U_E + U_R) + 12 * B bytes per step (SURVEY 8d)"}}
+            del leng, lb
+            torch.cuda.empty_cache()
     if args.full and world == 1:
         out["other_shapes"] = other_shapes(dev, torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev))
     return out

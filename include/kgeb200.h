@@ -276,6 +276,20 @@ KGEB_API int kgeb_rows_gather(kgeb_ctx* ctx, const float* P, int width, int ld, 
 KGEB_API int kgeb_rows_scatter_add(kgeb_ctx* ctx, float* G, int width, int ld, uint8_t* touched, const int32_t* idx, int64_t n,
                           const float* src, kgeb_stream stream);
 
+/* ---- one whole step, sort-segmented, with the optimizer applied at segment end (north-star item 2) -------------
+ * Forward as kgeb_train_fwd_bwd (Philox negatives, scores, loss, relation gradient by vector reductions), then (entity id, triple,
+ * slot) records are radix-sorted by id, one warp per segment re-forms and sums the row's gradient in registers in sorted order
+ * and applies SGD / Adagrad / LazyAdam right there: the updated row is written to E_next (the kernel reads E_cur: rows of other
+ * entities are still being read), the moments in place.  No entity gradient buffer is touched.  The caller swaps E_cur / E_next
+ * and touched_now / touched_prev after every call; both table copies must start identical, both flag arrays zero.  Replaces
+ * tests.py:86 (`adam` on IndexedSlices: dedup by id, then update) for tables far larger than the L2; on L2-resident tables the
+ * vector-reduction path + kgeb_opt_update2 is faster (profiles/r02_sortseg.jsonl).  Needs kgeb_set_grad_sortseg armed. */
+KGEB_API int kgeb_train_step_sortseg(kgeb_ctx* ctx, const float* E_cur, float* E_next, float* R, const int32_t* pos, int64_t B,
+                            const int32_t* neg, int K, int loss_kind, float margin, float loss_weight, int corrupt_mode,
+                            uint64_t seed, uint64_t offset, float* loss, float* gR, uint8_t* touchedR, uint8_t* touched_now,
+                            uint8_t* touched_prev, float* mE, float* vE, float* mR, float* vR, int opt_kind, float lr,
+                            float beta1, float beta2, float eps, int64_t step, kgeb_stream stream);
+
 /* ---- the split form of the backward: (unique_ids, grad_rows) for a host that keeps its own optimizer ---------------
  * A tf.keras Embedding gives its optimizer IndexedSlices (models.py:89-112, tests.py:86); a registered gradient of the TF op shim
  * returns exactly this pair.  Compacts the touched rows of a dense gradient buffer filled by kgeb_train_fwd_bwd / kgeb_score_bwd:

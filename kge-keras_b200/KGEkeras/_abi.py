@@ -72,6 +72,7 @@ PROTOTYPES = {
     "kgeb_train_fwd_bwd": (_i, [_p, _p, _p, _p, _i64, _p, _i, _i, _f, _f, _i, _u64, _u64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "kgeb_sortseg_workspace_bytes": (_i64, [_p, _i64, _i]),
     "kgeb_set_grad_sortseg": (_i, [_p, _p, _i64]),
+    "kgeb_train_step_sortseg": (_i, [_p, _p, _p, _p, _p, _i64, _p, _i, _i, _f, _f, _i, _u64, _u64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _f, _f, _f, _i64, _p]),
     "kgeb_l3_reg": (_i, [_p, _p, _i64, _i, _i, _f, _p, _p, _p, _p]),
     "kgeb_opt_update": (_i, [_p, _p, _p, _p, _i64, _i, _i, _p, _p, _i, _f, _f, _f, _f, _i64, _p]),
     "kgeb_opt_update2": (_i, [_p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _i, _f, _f, _f, _f, _i64, _p]),

@@ -100,6 +100,7 @@ class Engine:
                 self._check(self.lib.kgeb_set_score_param(self.ctx, self.param))
         self.hole_fft = False
         self.grad_mode, self._ss_ws = "red", None
+        self.E2 = self.tE2 = None
         self.gE = self.gR = self.tE = self.tR = None
         self.opt_state = None
         self.step = 0
@@ -152,11 +153,13 @@ class Engine:
         self._check(self.lib.kgeb_kernel_ms_sum(self.ctx, which, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
 
-    def _ensure_train_buffers(self, opt_kind):
-        if self.gE is None:
-            self.gE, self.gR = torch.zeros_like(self.E), torch.zeros_like(self.Rel)
+    def _ensure_train_buffers(self, opt_kind, need_gE=True):
+        if self.gR is None:
+            self.gR = torch.zeros_like(self.Rel)
             self.tE = torch.zeros(self.N, dtype=torch.uint8, device=self.device)
             self.tR = torch.zeros(self.R_, dtype=torch.uint8, device=self.device)
+        if need_gE and self.gE is None:      # the fused sort-segment step never needs it
+            self.gE = torch.zeros_like(self.E)
         if self.opt_state is None or self.opt_state[0] != opt_kind:
             if opt_kind == abi.SGD:
                 st = (None, None, None, None)
@@ -175,13 +178,25 @@ class Engine:
     def set_grad_mode(self, mode="red"):
         """'red' (default): every row reference adds its gradient row with a 128-bit vector reduction.  'sortseg': the entity
         gradient rows are sort-segmented by entity id and added once per touched row in a reproducible order (kgeb_set_grad_sortseg;
-        fused-step kinds, no dropout)."""
-        if mode not in ("red", "sortseg"):
-            raise ValueError(f"grad mode must be 'red' or 'sortseg', got {mode!r}")
+        fused-step kinds, no dropout).  'sortseg_fused': as 'sortseg', and train_step applies the optimizer at segment end
+        (kgeb_train_step_sortseg): no entity gradient buffer, two copies of the entity table that swap every step -- the faster
+        step for tables far larger than the L2 (C5: 1M x 512), slower on L2-resident ones."""
+        if mode not in ("red", "sortseg", "sortseg_fused"):
+            raise ValueError(f"grad mode must be 'red', 'sortseg' or 'sortseg_fused', got {mode!r}")
         self.grad_mode = mode
         if mode == "red":
             self._check(self.lib.kgeb_set_grad_sortseg(self.ctx, None, 0))
             self._ss_ws = None
+        if mode == "sortseg_fused" and getattr(self, "E2", None) is None:
+            self.E2 = self.E.clone()                       # the copy the next step writes; both start identical
+            self.tE2 = torch.zeros(self.N, dtype=torch.uint8, device=self.device)
+        if mode != "sortseg_fused":
+            self.E2 = self.tE2 = None
+
+    def _fused_sortseg_ok(self, neg, B, K, opt_kind, loss_kind, pair_mode, dropout, l3):
+        return (self.grad_mode == "sortseg_fused" and self.kind in abi.FUSED_TRAIN_KINDS and opt_kind in (abi.SGD, abi.ADAGRAD, abi.LAZY_ADAM)
+                and not dropout and not l3 and not (abi.is_pairwise(loss_kind) and pair_mode == abi.ALLPAIRS)
+                and (neg is None or neg.shape[0] == B * K))
 
     def _arm_sortseg(self, B, K):
         need = int(self.lib.kgeb_sortseg_workspace_bytes(self.ctx, B, K))
@@ -402,11 +417,52 @@ class Engine:
                                          _ptr(loss), _stream()))
 
     def train_step(self, pos, neg=None, opt_kind=abi.ADAM_DENSE, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7, l3=0.0, **kw):
+        if self.grad_mode == "sortseg_fused":
+            r = self._train_step_sortseg_fused(pos, neg, opt_kind, lr, beta1, beta2, eps, l3, **kw)
+            if r is not None:
+                return r
+            # a request the fused entry does not serve (dense Adam, dropout, all-pairs loss, L3): ordinary in-place step on the
+            # current copy, then the other copy is brought up to date wholesale (correct, not fast: leave this mode for such runs)
+            self._check(self.lib.kgeb_set_grad_sortseg(self.ctx, None, 0))     # plain reduction path for this step
+            self._ss_ws = None
+            res = self.forward_backward(pos, neg, opt_kind=opt_kind, **kw)
+            if l3:
+                self.l3_reg(l3, res["loss"])
+            self.apply_optimizer(opt_kind, lr, beta1, beta2, eps)
+            self.E2.copy_(self.E)
+            self.tE2.zero_()
+            return res
         res = self.forward_backward(pos, neg, opt_kind=opt_kind, **kw)
         if l3:
             self.l3_reg(l3, res["loss"])
         self.apply_optimizer(opt_kind, lr, beta1, beta2, eps)
         return res
+
+    def _train_step_sortseg_fused(self, pos, neg, opt_kind, lr, beta1, beta2, eps, l3, K=1, loss_kind=abi.PAIRWISE_HINGE, pair_mode=abi.PAIRED,
+                                  margin=1.0, loss_weight=1.0, corrupt_mode=abi.CORRUPT_BOTH, seed=0, offset=0, dropout=0.0, **other):
+        """The whole step through kgeb_train_step_sortseg; None when the request is outside what that entry serves (the caller
+        then takes the ordinary two-kernel path on the CURRENT table copy)."""
+        pos = as_idx(pos, self.device)
+        B = pos.shape[0]
+        if neg is not None:
+            neg = as_idx(neg, self.device)
+            if neg.shape[0] % B == 0:
+                K = neg.shape[0] // B
+        if other.get("want_scores") or other.get("want_neg") or other.get("force_unfused"):
+            return None
+        if not self._fused_sortseg_ok(neg, B, K, opt_kind, loss_kind, pair_mode, dropout, l3):
+            return None
+        self._ensure_train_buffers(opt_kind, need_gE=False)
+        self._arm_sortseg(B, K)
+        self.step += 1
+        _, m_e, v_e, m_r, v_r = self.opt_state
+        self._check(self.lib.kgeb_train_step_sortseg(
+            self.ctx, _ptr(self.E), _ptr(self.E2), _ptr(self.Rel), _ptr(pos), B, _ptr(neg), K, loss_kind, margin, loss_weight, corrupt_mode,
+            seed, offset, _ptr(self._loss), _ptr(self.gR), _ptr(self.tR), _ptr(self.tE), _ptr(self.tE2), _ptr(m_e), _ptr(v_e), _ptr(m_r), _ptr(v_r),
+            opt_kind, lr, beta1, beta2, eps, self.step, _stream()))
+        self.E, self.E2 = self.E2, self.E            # the copy just written is the table now
+        self.tE, self.tE2 = self.tE2, self.tE        # this step's flags become "previous"; the cleared array is the next step's
+        return {"loss": self._loss, "pos_scores": None, "neg_scores": None, "neg": neg}
 
     # ---- filter sets ----------------------------------------------------------------------------------------------
     def filter_csr(self, queries, filtering_triples, side):
@@ -539,6 +595,8 @@ class Engine:
     def set_tables(self, E=None, R=None):
         if E is not None:
             self.E[:, :self.we] = torch.as_tensor(np.asarray(E, dtype=np.float32)).to(self.device)
+            if getattr(self, "E2", None) is not None:
+                self.E2.copy_(self.E)
         if R is not None:
             self.Rel[:, :self.wr] = torch.as_tensor(np.asarray(R, dtype=np.float32)).to(self.device)
 

@@ -45,6 +45,7 @@ struct kgeb_ctx {
   int ev_n[KGEB_TIMED_KERNELS];      // launches bracketed since the last kgeb_kernel_ms_sum (the pool is a ring)
   // sort-segmented entity backward (kgeb_set_grad_sortseg): caller-owned workspace, NULL = vector-reduction path
   unsigned char* ss_ws; int64_t ss_bytes;
+  const void* ss_fused;   // non-NULL only inside kgeb_train_step_sortseg: the optimizer applied at segment end (sortseg_kernels.cu)
   // NCCL communicator of the sharded paths (kgeb_comm_init, comm.cu); NULL = single GPU
   void* comm; int comm_rank, comm_world;
 };

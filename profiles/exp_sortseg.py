@@ -1,5 +1,7 @@
-"""Step time of the fused train step with the vector-reduction backward ('red') against the sort-segmented one ('sortseg')
-on the C2 shape (L2-resident table) and the C5 shape (2 GB table), with the kernels' own CUDA-event times.
+"""Step time of the fused train step with the vector-reduction backward ('red') against the sort-segmented one ('sortseg') and the
+sort-segmented one with the optimizer applied at segment end ('sortseg_fused': kgeb_train_step_sortseg, no gradient buffer, two
+table copies) on the C2 shape (L2-resident table) and the C5 shape (2 GB table), with the kernels' own CUDA-event times
+(in the fused mode the segment kernel's time includes the optimizer, and k_opt_update is the relation table's alone).
     python profiles/exp_sortseg.py > profiles/r02_sortseg.jsonl"""
 import json
 import os
@@ -22,7 +24,7 @@ SHAPES = [("C2 TransE-L1 d=200 N=40943 B=16384 K=10", abi.TRANSE_L1, 40943, 11, 
 for name, kind, N, R, W, B, K, loss, cm in SHAPES:
     rng = np.random.default_rng(0)
     lim = float(np.sqrt(6.0 / (N + W)))
-    for mode in ("red", "sortseg"):
+    for mode in ("red", "sortseg", "sortseg_fused"):
         eng = Engine(kind, N, R, W, W, E=torch.empty(N, W, device=dev).uniform_(-lim, lim), R=rng.uniform(-0.1, 0.1, (R, W)).astype(np.float32))
         eng.set_grad_mode(mode)
         steps, warm = 10, 3

@@ -94,3 +94,78 @@ def test_sortseg_refuses_dropout_and_disarms():
     eng.forward_backward(pos, None, K=4, dropout=0.2, seed=1, offset=0, opt_kind=abi.LAZY_ADAM)
     with pytest.raises(ValueError):
         eng.set_grad_mode("atomic")
+
+
+# ---- the optimizer fused at segment end (kgeb_train_step_sortseg): no gradient buffer, two table copies ----------------------------
+@pytest.mark.parametrize("kind_name,d", [("TRANSE_L1", 40), ("COMPLEX", 32), ("DISTMULT", 100), ("TRANSE_L2", 64)])
+@pytest.mark.parametrize("opt_name", ["LAZY_ADAM", "ADAGRAD", "SGD"])
+def test_fused_sortseg_step_equals_reduction_path(kind_name, d, opt_name):
+    """Several steps with changing batches (rows touched by one step and not by the next exercise the copy-over of stale rows):
+    tables, moments and loss equal to the vector-reduction path + kgeb_opt_update2 within fp32 summation-order noise."""
+    from KGEkeras import _abi as abi
+    from KGEkeras._engine import Engine
+    kind, opt = getattr(abi, kind_name), getattr(abi, opt_name)
+    N, R, B, K = 3000, 6, 256, 5
+    rng = np.random.default_rng(d)
+    E0, R0 = ko.glorot_uniform(rng, N, d) * 3, ko.glorot_uniform(rng, R, d) * 3
+    a, b = Engine(kind, N, R, d, d, 12.0, E=E0, R=R0), Engine(kind, N, R, d, d, 12.0, E=E0, R=R0)
+    b.set_grad_mode("sortseg_fused")
+    for step in range(5):
+        lo, hi = (0, N) if step % 2 == 0 else (step * 300, step * 300 + 600)          # odd steps touch a small id window only
+        pos = np.stack([rng.integers(lo, hi, B), rng.integers(0, R, B), rng.integers(lo, hi, B)], 1).astype(np.int32)
+        neg = np.stack([rng.integers(lo, hi, B * K), np.repeat(pos[:, 1], K), rng.integers(lo, hi, B * K)], 1).astype(np.int32)
+        kw = dict(K=K, loss_kind=abi.PAIRWISE_LOGISTIC, margin=1.0, opt_kind=opt, lr=0.01)
+        la = a.train_step(pos, neg, **kw)["loss"].item()
+        lb = b.train_step(pos, neg, **kw)["loss"].item()
+        assert abs(la - lb) <= 1e-6 * max(1.0, abs(la))
+        np.testing.assert_allclose(b.get_tables()[0], a.get_tables()[0], rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(b.get_tables()[1], a.get_tables()[1], rtol=2e-5, atol=2e-6)
+    assert b.gE is None                                                               # no entity gradient buffer was ever made
+    # both copies agree on every row the last step did not touch
+    touched_last = b.tE2.bool().cpu().numpy()
+    np.testing.assert_array_equal(b.E.cpu().numpy()[~touched_last], b.E2.cpu().numpy()[~touched_last])
+    if opt != abi.SGD:
+        np.testing.assert_allclose(b.opt_state[1].cpu().numpy(), a.opt_state[1].cpu().numpy(), rtol=2e-5, atol=1e-7)
+
+
+def test_fused_sortseg_is_reproducible_and_serves_philox_negatives():
+    from KGEkeras import _abi as abi
+    from KGEkeras._engine import Engine
+    N, R, d, B, K = 2000, 4, 64, 512, 8
+    rng = np.random.default_rng(1)
+    E0, R0 = ko.glorot_uniform(rng, N, d) * 3, ko.glorot_uniform(rng, R, d) * 3
+    pos = np.stack([rng.integers(0, N, B), rng.integers(0, R, B), rng.integers(0, N, B)], 1).astype(np.int32)
+    outs, first = [], []
+    for _ in range(2):
+        e = Engine(abi.COMPLEX, N, R, d, d, 12.0, E=E0, R=R0)
+        e.set_grad_mode("sortseg_fused")
+        for step in range(3):
+            e.train_step(pos, None, K=K, loss_kind=abi.PAIRWISE_HINGE, margin=1.0, opt_kind=abi.LAZY_ADAM, lr=0.01, seed=9, offset=step)
+            if step == 0:
+                first.append(e.get_tables()[0])
+        outs.append(e.get_tables()[0])
+    # entity rows of ONE step are bit-identical run to run (every sum runs in sorted order); later steps inherit the low-bit noise of
+    # the relation table, whose gradient still arrives by vector reductions
+    np.testing.assert_array_equal(first[0], first[1])
+    np.testing.assert_allclose(outs[0], outs[1], rtol=1e-5, atol=1e-6)
+    ref = Engine(abi.COMPLEX, N, R, d, d, 12.0, E=E0, R=R0)
+    for step in range(3):
+        ref.train_step(pos, None, K=K, loss_kind=abi.PAIRWISE_HINGE, margin=1.0, opt_kind=abi.LAZY_ADAM, lr=0.01, seed=9, offset=step)
+    np.testing.assert_allclose(outs[0], ref.get_tables()[0], rtol=2e-5, atol=2e-6)
+
+
+def test_fused_sortseg_falls_back_for_dense_adam():
+    from KGEkeras import _abi as abi
+    from KGEkeras._engine import Engine
+    N, R, d, B, K = 500, 3, 16, 64, 2
+    rng = np.random.default_rng(2)
+    E0, R0 = ko.glorot_uniform(rng, N, d), ko.glorot_uniform(rng, R, d)
+    pos = np.stack([rng.integers(0, N, B), rng.integers(0, R, B), rng.integers(0, N, B)], 1).astype(np.int32)
+    a, b = Engine(abi.DISTMULT, N, R, d, d, 12.0, E=E0, R=R0), Engine(abi.DISTMULT, N, R, d, d, 12.0, E=E0, R=R0)
+    b.set_grad_mode("sortseg_fused")
+    for step in range(2):
+        kw = dict(K=K, loss_kind=abi.PAIRWISE_HINGE, margin=1.0, opt_kind=abi.ADAM_DENSE, lr=0.01, seed=1, offset=step)
+        a.train_step(pos, None, **kw)
+        b.train_step(pos, None, **kw)
+    np.testing.assert_allclose(b.get_tables()[0], a.get_tables()[0], rtol=2e-5, atol=2e-6)
+    assert torch.equal(b.E, b.E2)
