@@ -291,8 +291,29 @@ extern "C" int kgeb_rows_concat_bwd(kgeb_ctx* ctx, const float* gX, int ldX, int
   return KGEB_OK;
 }
 
+// tensor-core path (gemm_tc_kernels.cu): tcgen05 kind::tf32 with a three-term split; KGEB_GEMM=ffma keeps the CUDA-core kernel (A/B)
+int kgeb_internal_gemm_tc(kgeb_ctx* ctx, int transA, int transB, int64_t M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                          float* C, int ldc, int accumulate, const float* bias, int act, float* part, size_t part_bytes, int* splits_out,
+                          cudaStream_t st);
+
 static int launch_sgemm(kgeb_ctx* ctx, int transA, int transB, int64_t M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
                         int ldc, int accumulate, const float* bias, int act, cudaStream_t st) {
+  static const bool force_ffma = [] { const char* e = getenv("KGEB_GEMM"); return e && strcmp(e, "ffma") == 0; }();
+  if (!force_ffma) {
+    int tc_splits = 1;
+    const int rc = kgeb_internal_gemm_tc(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, accumulate, bias, act,
+                                         reinterpret_cast<float*>(ctx->d_sort_scratch), KGEB_SORT_SCRATCH_BYTES, &tc_splits, st);
+    if (rc == KGEB_OK) {
+      if (tc_splits > 1) {
+        const int64_t MN = M * N;
+        k_splitk_reduce<<<(int)((MN + 63) / 64 < 2048 ? (MN + 63) / 64 : 2048), 64, 0, st>>>(reinterpret_cast<float*>(ctx->d_sort_scratch), tc_splits, MN, N, C,
+                                                                                        ldc, accumulate);
+        KGEB_LAUNCH_OK(ctx);
+      }
+      return KGEB_OK;
+    }
+    if (rc != KGEB_ERR_UNSUPPORTED) return rc;
+  }
   dim3 grid((unsigned)((N + GN - 1) / GN), (unsigned)((M + GM - 1) / GM));
   // few output tiles and a long K: slice K so that about two waves of CTAs are in flight (the slices fit the context scratch)
   const int64_t tiles = (int64_t)grid.x * grid.y;
