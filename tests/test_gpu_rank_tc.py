@@ -299,3 +299,41 @@ def test_tc_transe_l2_shards_sum_to_whole_and_validate_uses_it():
     want = ko.metrics_from_ranks(ranks[0], ranks[1])
     for k in ("mrr", "hits@10", "mr"):
         assert abs(res[k] - want[k]) <= 1e-6 * max(1.0, abs(want[k])), (k, res[k], want[k])
+
+
+# ---- compute-sanitizer is closed on the pool: a race in the producer / MMA / epilogue hand-offs would show up as counts that change
+# from run to run or differ from the CUDA-core kernel on SOME shape; this sweeps the shapes that move every pipeline parameter ----------
+def test_tc_stress_shapes_and_repeatability():
+    """Widths that give 1..13 pipeline stages per tile in both modes (odd stage counts exercise the paired hand-off's tail), query and
+    entity counts around the tile edges (127/128/129 queries, 255/256/257/513 entities), shards that start inside a tile, queries >> SMs
+    (every CTA walks several items: both TMEM accumulator buffers and all ring stages wrap many times).  Every case: exact mode ==
+    CUDA-core kernel, and 8 repeats of the same pass return the same integers (approximate mode included)."""
+    abi = _abi()
+    from KGEkeras._engine import Engine
+    rng = np.random.default_rng(123)
+    cases = [(16, 255, 127), (32, 256, 128), (48, 257, 129), (64, 513, 64), (104, 1000, 300), (208, 777, 257), (400, 520, 140),
+             (16, 40000, 2500), (136, 9000, 1100)]
+    for W, N, Q in cases:
+        kind = abi.COMPLEX if W % 8 == 0 and rng.integers(2) else abi.DISTMULT
+        E, Rm = ko.glorot_uniform(rng, N, W) * 3, ko.glorot_uniform(rng, 4, W) * 3
+        eng = Engine(kind, N, 4, W, W, 12.0, E=E, R=Rm)
+        tri = rand_triples(rng, Q, N, 4)
+        r0 = int(rng.integers(0, min(N // 3, 300)))
+        want = torch.zeros(Q, dtype=torch.int32, device="cuda")
+        for lo, hi in ((0, r0), (r0, N)):
+            if hi > lo:
+                eng.rank_counts(tri, 1, row_range=(lo, hi), counts=want)
+        base = {}
+        for rep in range(8):
+            for mode in (abi.TC_F16X3_EXACT, abi.TC_BF16):
+                got = torch.zeros(Q, dtype=torch.int32, device="cuda")
+                for lo, hi in ((0, r0), (r0, N)):
+                    if hi > lo:
+                        eng.rank_counts_tc(tri, 1, row_range=(lo, hi), counts=got, mode=mode)
+                if rep == 0:
+                    base[mode] = got.clone()
+                    if mode == abi.TC_F16X3_EXACT:
+                        assert torch.equal(got, want), (W, N, Q, r0)
+                else:
+                    assert torch.equal(got, base[mode]), (W, N, Q, r0, mode, rep)
+        del eng
