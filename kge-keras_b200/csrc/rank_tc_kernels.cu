@@ -483,6 +483,267 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
   }
 }
 
+// ---- the approximate mode with the QUERY tile resident in tensor memory -------------------------------------------------
+// k_rank_tc is bound by shared-memory traffic in the single-plane mode: every K=16 step the MMA fetches 12 KB of operands from
+// shared memory while the bulk copies refill it at the same rate (profiles/r01_tc_v2_summary.md).  A CTA keeps the same 128
+// queries for thousands of entity tiles, so here their operand lives in TMEM (columns 256.., written once per query tile with
+// tcgen05.st: lane = query, a 32-bit column = two consecutive k -- the layout the A-from-TMEM form of tcgen05.mma reads, checked
+// bit for bit by profiles/micro/tc_numerics.cu with TC_A_TMEM=1) and only the entity operand streams: 128-row tiles, 16 KB
+// stages, eight of them in flight, N = 128 accumulators double-buffered in columns 0..255.  Shared-memory bytes per flop
+// drop by a third on both sides (fill and MMA fetch).  K <= 512 (256 columns of A); wider tables keep k_rank_tc.
+// RESULT (profiles/r02_tc_ts.md): correct (every approximate-mode test passes, ranks identical to k_rank_tc's) and SLOWER --
+// 22.0 ms against 16.0 ms per side on C5.  Tensor memory has one 64 B/clk read port: an M128 N128 K16 MMA fetches its 4 KB A
+// operand from it in 64 clk (all of it), and the epilogue's tcgen05.ld of the 64 KB accumulator tile needs another 32 B/clk.
+// The shared-memory operand path of k_rank_tc is the faster one on this chip; the kernel is kept behind KGEB_TC_TS=1.
+constexpr int TS_BN = 128;
+constexpr int TS_STAGES = 8;
+constexpr uint32_t TS_B_STAGE = TS_BN * TC_CH_TOTAL * 16;   // 16 KB: 8 k-chunks = 64 k of 128 entity rows
+constexpr uint32_t TS_SMEM_BYTES = TS_STAGES * TS_B_STAGE + 1024 + 256 + 8 * TC_WBUF * 8;
+constexpr uint32_t TS_IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TS_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+__device__ __forceinline__ void ts_mma_bf16(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// work split: the CTAs form a (G query lanes) x (T tile lanes) grid; inside a group of G query tiles CTA (lq, lt) keeps query tile
+// g*G + lq and walks entity tiles lt, lt + T, ...: the query operand is reloaded only when the group changes
+struct TsWalk {
+  int G, T, lq, lt; bool idle;
+  __device__ TsWalk(const TcArgs& a) {
+    const int P = (int)gridDim.x;
+    G = a.qgroup < P ? a.qgroup : P;
+    if (G > a.qtiles) G = a.qtiles;
+    T = P / G;
+    lq = (int)blockIdx.x % G; lt = (int)blockIdx.x / G;
+    idle = lt >= T;
+  }
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_ts(TcArgs a) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smB = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TS_STAGES * TS_B_STAGE);
+  uint64_t* full = bars;                       // [TS_STAGES]
+  uint64_t* empty = bars + TS_STAGES;          // [TS_STAGES]
+  uint64_t* acc_full = bars + 2 * TS_STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint64_t* a_ready = acc_empty + 2;           // [1] the 8 epilogue warps have written the query operand of the current group
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
+  uint2* wbuf_all = reinterpret_cast<uint2*>(smem + TS_STAGES * TS_B_STAGE + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nstage = (a.nkc + TC_CH_TOTAL - 1) / TC_CH_TOTAL;
+  const TsWalk wk(a);
+  const int ngroups = (a.qtiles + wk.G - 1) / wk.G;
+
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) a.wl_hdr[1] = a.wl_cap;
+    for (int i = 0; i < TS_STAGES; ++i) { tc_mbar_init(full + i, 1); tc_mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { tc_mbar_init(acc_full + i, 1); tc_mbar_init(acc_empty + i, 8); }
+    tc_mbar_init(a_ready, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_a = tmem_base + 256u;
+
+  if (warp == 0) {
+    // ===== producer: one thread streams the packed entity stages =====
+    if (lane == 0 && !wk.idle) {
+      uint32_t stage = 0, phase = 0;
+      const size_t b_tile_bytes = (size_t)a.nkc * TS_BN * 16;
+      for (int g = 0; g < ngroups; ++g) {
+        if (g * wk.G + wk.lq >= a.qtiles) continue;
+        for (int64_t tile = wk.lt; tile < a.ntiles; tile += wk.T) {
+          const unsigned char* srcB = a.packedE + (size_t)tile * b_tile_bytes;
+          for (int s = 0; s < nstage; ++s) {
+            const int c0 = s * TC_CH_TOTAL;
+            const int nch = a.nkc - c0 < TC_CH_TOTAL ? a.nkc - c0 : TC_CH_TOTAL;
+            tc_mbar_wait(empty + stage, phase ^ 1u);
+            const uint32_t bb = (uint32_t)nch * TS_BN * 16;
+            tc_mbar_expect_tx(full + stage, bb);
+            tc_bulk_g2s(smB + stage * TS_B_STAGE, srcB + (size_t)c0 * TS_BN * 16, bb, full + stage);
+            if (++stage == TS_STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread =====
+    if (lane == 0 && !wk.idle) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, a_phase = 0;
+      for (int g = 0; g < ngroups; ++g) {
+        if (g * wk.G + wk.lq >= a.qtiles) continue;
+        tc_mbar_wait(a_ready, a_phase);          // the group's query operand is in TMEM (every MMA of the previous group has completed)
+        a_phase ^= 1u;
+        tc_fence_after();
+        for (int64_t tile = wk.lt; tile < a.ntiles; tile += wk.T) {
+          tc_mbar_wait(acc_empty + acc, acc_phase ^ 1u);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * TS_BN;
+          uint32_t accumulate = 0;
+          // stages are consumed in groups of four: the MMAs of four stages are issued back to back and only then are the stages
+          // handed back (every MMA/commit alternation costs the tensor pipe a hand-off; see k_rank_tc)
+          for (int s = 0; s < nstage; s += 4) {
+            uint32_t st_idx[4];
+            int nin = 0;
+            for (int h = 0; h < 4 && s + h < nstage; ++h) {
+              const int c0 = (s + h) * TC_CH_TOTAL;
+              const int nk16 = (a.nkc - c0 < TC_CH_TOTAL ? a.nkc - c0 : TC_CH_TOTAL) >> 1;
+              tc_mbar_wait(full + stage, phase);
+              tc_fence_after();
+              const uint32_t sb = tc_smem_u32(smB + stage * TS_B_STAGE);
+              for (int j = 0; j < nk16; ++j) {
+                ts_mma_bf16(tmem_d, tmem_a + (uint32_t)(c0 / 2 + j) * 8u, tc_desc(sb + (uint32_t)(2 * j) * TS_BN * 16, TS_BN * 16, 128), TS_IDESC_BF16,
+                            accumulate);
+                accumulate = 1;
+              }
+              st_idx[nin++] = stage;
+              if (++stage == TS_STAGES) { stage = 0; phase ^= 1u; }
+            }
+            for (int h = 0; h < nin; ++h) tc_commit(empty + st_idx[h]);
+          }
+          tc_commit(acc_full + acc);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4 && !wk.idle) {
+    // ===== query-operand loaders + epilogue: 8 warps; warp w owns TMEM lanes 32*(w%4).. and columns 64*((w-4)/4).. of an accumulator =====
+    const int lq = warp & 3, chalf = (warp - 4) >> 2;
+    uint2* wbuf = wbuf_all + (warp - 4) * TC_WBUF;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t wcnt = 0;
+    uint32_t acc = 0, acc_phase = 0;
+
+    auto flush = [&]() {
+      __syncwarp();
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(a.wl_hdr, wcnt);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      for (uint32_t i = lane; i < wcnt; i += 32)
+        if (base + i < a.wl_cap) a.wl[base + i] = wbuf[i];
+      __syncwarp();
+      wcnt = 0;
+    };
+
+    for (int g = 0; g < ngroups; ++g) {
+      const int64_t qt = (int64_t)g * wk.G + wk.lq;
+      if (qt >= a.qtiles) continue;
+      // ---- this group's query operand -> TMEM: the previous group's accumulators have all been read by this warp (program order),
+      //      and they were complete, so no MMA still reads the old operand.  Warp (lq, chalf) writes its 32 lanes, half of the k range.
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(a.packedQ + (size_t)qt * a.nkc * TC_BM * 16);
+        const int kc0 = chalf * (a.nkc >> 1), kc1 = chalf ? a.nkc : (a.nkc >> 1);
+        for (int kc = kc0; kc < kc1; ++kc) {
+          const uint4 v = __ldg(src + (size_t)kc * TC_BM + lq * 32 + lane);
+          const uint32_t taddr = tmem_a + (uint32_t)kc * 4u + ((uint32_t)(lq * 32) << 16);
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(a_ready);
+      }
+      const int64_t q = qt * TC_BM + lq * 32 + lane;
+      const bool qok = q < a.Q;
+      const float t = qok ? __ldg(a.tscore + q) : 0.f;
+      const int64_t tgt = qok ? (int64_t)__ldg(a.triples + 3 * q + (a.side == KGEB_SIDE_TAIL ? 2 : 0)) - a.row_offset : -1;
+      int64_t f_lo = 0, f_end = 0;
+      if (a.filt_offs && qok) { f_lo = __ldg(a.filt_offs + q); f_end = __ldg(a.filt_offs + q + 1); }
+      int cnt0 = 0;
+
+      for (int64_t tile = wk.lt; tile < a.ntiles; tile += wk.T) {
+        const int64_t n0 = tile * TS_BN + chalf * 64;     // shard-local id of this warp's first column
+        // cursor into the query's sorted filter list: first id at or beyond this warp's first column (global id space)
+        int64_t fpos = f_end;
+        if (f_lo < f_end) {
+          int64_t lo_i = f_lo, hi_i = f_end;
+          const int64_t g0 = a.row_offset + n0;
+          while (lo_i < hi_i) {
+            const int64_t mid = (lo_i + hi_i) >> 1;
+            if ((int64_t)__ldg(a.filt_ids + mid) < g0) lo_i = mid + 1; else hi_i = mid;
+          }
+          fpos = lo_i;
+        }
+        int64_t fnext = fpos < f_end ? (int64_t)__ldg(a.filt_ids + fpos) - a.row_offset : INT64_MAX;
+
+        auto process = [&](uint32_t (&r)[32], int jc) {
+          uint32_t k0 = 0, k1 = 0, m0 = 0, m1 = 0;
+          tc_cmp32<0>(r, t, t, k0, k1, m0, m1);              // approximate mode: no band -- counted above t, "undecided" exactly at t
+          uint32_t cmask = k0 | k1, mask = m0 | m1;
+          const int64_t c0 = n0 + jc;
+          const int64_t left = a.n_rows - c0;
+          uint32_t keep = 0xffffffffu;
+          if (left < 32) {
+            const int nvalid = left < 0 ? 0 : (int)left;
+            keep = nvalid == 0 ? 0u : (0xffffffffu >> (32 - nvalid));
+          }
+          const int64_t trel = tgt - c0;
+          if (trel >= 0 && trel < 32) keep &= ~(1u << (int)trel);
+          while (fnext < c0 + 32) {
+            if (fnext >= c0) keep &= ~(1u << (int)(fnext - c0));
+            ++fpos;
+            fnext = fpos < f_end ? (int64_t)__ldg(a.filt_ids + fpos) - a.row_offset : INT64_MAX;
+          }
+          cmask &= keep;
+          mask &= keep;
+          cnt0 += __popc(cmask);
+          if (!qok) mask = 0;
+          while (true) {
+            const uint32_t have = __ballot_sync(0xffffffffu, mask != 0);
+            if (have == 0) break;
+            if (wcnt + 32 > TC_WBUF) flush();
+            if (mask != 0) {
+              const int j = __ffs(mask) - 1;
+              mask &= mask - 1;
+              wbuf[wcnt + __popc(have & lt_mask)] = make_uint2((uint32_t)q, (uint32_t)(c0 + j));
+            }
+            wcnt += __popc(have);
+          }
+        };
+
+        tc_mbar_wait(acc_full + acc, acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * TS_BN + chalf * 64 + ((uint32_t)(lq * 32) << 16);
+        uint32_t rA[32], rB[32];
+        tc_ld32_issue(taddr, rA);
+        tc_ld_wait(rA);
+        tc_ld32_issue(taddr + 32, rB);
+        process(rA, 0);
+        tc_ld_wait(rB);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(acc_empty + acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        process(rB, 32);
+      }
+      if (qok && cnt0 != 0) atomicAdd(a.counts + q, cnt0);
+    }
+    if (wcnt != 0) flush();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ---- operand packing ----------------------------------------------------------------------------------------------
 // largest |x| of a table as fp32 bits (non-negative floats order like their bit patterns); *out must be zero before the launch
 __global__ void k_tc_absmax(const float* __restrict__ src, int64_t rows, int W, int ld, uint32_t* __restrict__ out) {
@@ -704,19 +965,28 @@ int tc_grid(const kgeb_ctx* ctx, int64_t n, int threads) {
   return (int)(b < 1 ? 1 : b);
 }
 
-// packed entity buffer: [operand image][row norms nt*256][slice max nt*2][weighted norms nt*256][their slice max nt*2][scale bits]
+// KGEB_TC_TS=1 (an experiment, OFF by default): approximate mode, K <= 512, with the query operand in TMEM (k_rank_tc_ts) and the
+// entity image packed in 128-row tiles.  Measured on C5: 22.0 ms per side against 16.0 ms for k_rank_tc (profiles/r02_tc_ts.md).
+bool tc_use_ts(const kgeb_ctx* ctx, int mode) {
+  static const bool on = [] { const char* e = getenv("KGEB_TC_TS"); return e && e[0] == '1'; }();
+  return on && mode == KGEB_TC_BF16 && !tc_l2_kind(ctx) && tc_nkc(ctx) <= 64;
+}
+int tc_bn(const kgeb_ctx* ctx, int mode) { return tc_use_ts(ctx, mode) ? TS_BN : TC_BN; }
+
+// packed entity buffer: [operand image][row norms nt*bn][slice max][weighted norms nt*bn][their slice max][scale bits]  (bn = rows per tile)
 struct TcPackedLayout { size_t image, norms, smax, wnorms, wmax, scale, extras, total; };
 TcPackedLayout tc_packed_layout(const kgeb_ctx* ctx, int64_t n_rows, int mode) {
-  const int64_t nt = tc_tiles(n_rows, TC_BN);
+  const int bn = tc_bn(ctx, mode);
+  const int64_t nt = tc_tiles(n_rows, bn), nsl = nt * (bn / 128);
   TcPackedLayout L;
   L.image = 0;
-  L.norms = tc_align((size_t)nt * tc_nkc(ctx) * tc_planes(mode) * TC_BN * 16);
-  L.smax = L.norms + tc_align((size_t)nt * TC_BN * 4);
-  L.wnorms = L.smax + tc_align((size_t)nt * 2 * 4);
-  L.wmax = L.wnorms + tc_align((size_t)nt * TC_BN * 4);
-  L.scale = L.wmax + tc_align((size_t)nt * 2 * 4);
+  L.norms = tc_align((size_t)nt * tc_nkc(ctx) * tc_planes(mode) * bn * 16);
+  L.smax = L.norms + tc_align((size_t)nt * bn * 4);
+  L.wnorms = L.smax + tc_align((size_t)nsl * 4);
+  L.wmax = L.wnorms + tc_align((size_t)nt * bn * 4);
+  L.scale = L.wmax + tc_align((size_t)nsl * 4);
   L.extras = L.scale + 256;                                                   // L2 mode: 4 halfs per (padded) row
-  L.total = L.extras + (tc_l2_kind(ctx) ? tc_align((size_t)nt * TC_BN * 8) : 0);
+  L.total = L.extras + (tc_l2_kind(ctx) ? tc_align((size_t)nt * bn * 8) : 0);
   return L;
 }
 // workspace: [header 256 B: appended, capacity, query scale bits at +16][worklist][packed queries][query norms][weighted query norms]
@@ -751,7 +1021,8 @@ extern "C" int kgeb_rank_tc_pack_entities(kgeb_ctx* ctx, const float* E_shard, i
                KGEB_ERR_ALIGNMENT, "rank_tc needs width, stride multiples of 4 floats, a 16-byte aligned table and a 256-byte aligned packed buffer");
   KGEB_REQUIRE(ctx, packed_bytes >= kgeb_rank_tc_packed_bytes(ctx, n_rows, mode), KGEB_ERR_WORKSPACE, "packed entity buffer too small");
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t nt = tc_tiles(n_rows, TC_BN);
+  const int bn = tc_bn(ctx, mode);
+  const int64_t nt = tc_tiles(n_rows, bn), nsl = nt * (bn / 128);
   const int nkc = tc_nkc(ctx), planes = tc_planes(mode);
   const bool exact = mode == KGEB_TC_BF16X3_EXACT;
   const TcPackedLayout L = tc_packed_layout(ctx, n_rows, mode);
@@ -766,26 +1037,26 @@ extern "C" int kgeb_rank_tc_pack_entities(kgeb_ctx* ctx, const float* E_shard, i
     KGEB_LAUNCH_OK(ctx);
   }
   if (l2) {
-    k_tc_l2_extras<<<tc_grid(ctx, nt * TC_BN * 32, 256), 256, 0, st>>>(E_shard, n_rows, nt * TC_BN, ctx->we, ctx->ldE, scale_bits, extras);
+    k_tc_l2_extras<<<tc_grid(ctx, nt * bn * 32, 256), 256, 0, st>>>(E_shard, n_rows, nt * bn, ctx->we, ctx->ldE, scale_bits, extras);
     KGEB_LAUNCH_OK(ctx);
   }
   {
     TcPackArgs pa = {};
-    pa.src = E_shard; pa.rows = n_rows; pa.W = ctx->we; pa.ld = ctx->ldE; pa.tile_rows = TC_BN; pa.nkc = nkc; pa.planes = planes; pa.ntile = nt;
+    pa.src = E_shard; pa.rows = n_rows; pa.W = ctx->we; pa.ld = ctx->ldE; pa.tile_rows = bn; pa.nkc = nkc; pa.planes = planes; pa.ntile = nt;
     pa.scale_bits = exact ? scale_bits : nullptr; pa.other_bits = nullptr; pa.extras = l2 ? extras : nullptr; pa.l2_role = l2 ? 1 : 0; pa.negate = 0;
     pa.dst = reinterpret_cast<uint4*>(base);
-    k_tc_pack<<<tc_grid(ctx, nt * nkc * planes * TC_BN, 256), 256, 0, st>>>(pa);
+    k_tc_pack<<<tc_grid(ctx, nt * nkc * planes * bn, 256), 256, 0, st>>>(pa);
     KGEB_LAUNCH_OK(ctx);
   }
   float* enorm = reinterpret_cast<float*>(base + L.norms);
   float* ewnorm = reinterpret_cast<float*>(base + L.wnorms);
-  k_tc_norms<<<tc_grid(ctx, nt * TC_BN * 32, 256), 256, 0, st>>>(E_shard, n_rows, nt * TC_BN, ctx->we, ctx->ldE, nkc / 2, 0.f, enorm,
+  k_tc_norms<<<tc_grid(ctx, nt * bn * 32, 256), 256, 0, st>>>(E_shard, n_rows, nt * bn, ctx->we, ctx->ldE, nkc / 2, 0.f, enorm,
                                                                 exact ? ewnorm : nullptr);
   KGEB_LAUNCH_OK(ctx);
-  k_tc_slice_max<<<tc_grid(ctx, nt * 2 * 32, 256), 256, 0, st>>>(enorm, nt * 2, reinterpret_cast<float*>(base + L.smax));
+  k_tc_slice_max<<<tc_grid(ctx, nsl * 32, 256), 256, 0, st>>>(enorm, nsl, reinterpret_cast<float*>(base + L.smax));
   KGEB_LAUNCH_OK(ctx);
   if (exact) {
-    k_tc_slice_max<<<tc_grid(ctx, nt * 2 * 32, 256), 256, 0, st>>>(ewnorm, nt * 2, reinterpret_cast<float*>(base + L.wmax));
+    k_tc_slice_max<<<tc_grid(ctx, nsl * 32, 256), 256, 0, st>>>(ewnorm, nsl, reinterpret_cast<float*>(base + L.wmax));
     KGEB_LAUNCH_OK(ctx);
   }
   return KGEB_OK;
@@ -817,7 +1088,8 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
   cudaStream_t st = (cudaStream_t)stream;
   const int nkc = tc_nkc(ctx), planes = tc_planes(mode), qw = kgeb_query_width(ctx, side);
   const bool exact = mode == KGEB_TC_BF16X3_EXACT;
-  const int64_t qt = tc_tiles(Q, TC_BM), nt = tc_tiles(n_rows, TC_BN);
+  const bool ts = tc_use_ts(ctx, mode);
+  const int64_t qt = tc_tiles(Q, TC_BM), nt = tc_tiles(n_rows, tc_bn(ctx, mode));
   KGEB_REQUIRE(ctx, qt < 0x7fffffffLL && nt < 0x7fffffffLL, KGEB_ERR_UNSUPPORTED, "too many tiles");
   const TcWsLayout W = tc_ws_layout(ctx, Q, mode, worklist_cap);
   const TcPackedLayout L = tc_packed_layout(ctx, n_rows, mode);
@@ -912,12 +1184,14 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
   static bool attr_done = false;  // per process; the attribute is per function, setting it again is harmless
   if (!attr_done) {
     KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_rank_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_rank_tc_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM_BYTES));
     attr_done = true;
   }
   const int64_t items = qt * nt;
   const int grid = (int)(items < ctx->num_sms ? items : ctx->num_sms);
   KGEB_TIME_BEGIN(ctx, KGEB_TIMED_RANK_TC, st);
-  k_rank_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
+  if (ts) k_rank_tc_ts<<<grid, TC_THREADS, TS_SMEM_BYTES, st>>>(a);
+  else k_rank_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
   KGEB_TIME_END(ctx, KGEB_TIMED_RANK_TC, st);
   KGEB_LAUNCH_OK(ctx);
   KGEB_TIME_BEGIN(ctx, KGEB_TIMED_RANK_REFINE, st);

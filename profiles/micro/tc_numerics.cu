@@ -44,7 +44,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // smem image: no-swizzle K-major core matrices, [k-chunk of 8][row][8 x 16 bit]; LBO = rows*16, SBO = 128
 __global__ void __launch_bounds__(128, 1) k_probe(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B, int ktot, int fmt, int nseg,
-                                                 int nrep, float* __restrict__ D) {
+                                                 int nrep, int a_tmem, float* __restrict__ D) {
   extern __shared__ unsigned char raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
   const int nkc = ktot / 8;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(128, 1) k_probe(const uint16_t* __restrict__ A
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 32) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores above -> visible to the MMA's async proxy
@@ -73,6 +73,26 @@ __global__ void __launch_bounds__(128, 1) k_probe(const uint16_t* __restrict__ A
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *slot;
+  // a_tmem: the A operand lives in TMEM columns 256.. : thread t (= lane t = row t) stores its K elements, two 16-bit values per
+  // 32-bit column, with tcgen05.st -- the layout the .ts form of tcgen05.mma is assumed to read (this probe checks the assumption)
+  if (a_tmem) {
+    const int warp_ = threadIdx.x >> 5;
+    for (int c0 = 0; c0 < ktot / 2; c0 += 8) {
+      uint32_t v[8];
+      for (int e = 0; e < 8; ++e) {
+        const int k = 2 * (c0 + e);
+        v[e] = (uint32_t)A[(size_t)threadIdx.x * ktot + k] | ((uint32_t)A[(size_t)threadIdx.x * ktot + k + 1] << 16);
+      }
+      const uint32_t taddr = tmem + 256u + (uint32_t)c0 + ((uint32_t)(warp_ * 32) << 16);
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                   "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                   : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
   // instruction descriptor: fp32 accumulate (bit 4), A/B format (bits 7.., 10..: 0 = fp16, 1 = bf16), N = 256, M = 128, K-major both
   const uint32_t idesc = (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
   if (threadIdx.x == 0) {
@@ -83,6 +103,12 @@ __global__ void __launch_bounds__(128, 1) k_probe(const uint16_t* __restrict__ A
       const uint64_t ad = desc(s32(smA) + (uint32_t)(2 * j) * 128 * 16, 128 * 16, 128);
       const uint64_t bd = desc(s32(smB) + (uint32_t)(2 * j) * 256 * 16, 256 * 16, 128);
       const uint32_t accumulate = jj > 0;
+      if (a_tmem) {
+        const uint32_t at = tmem + 256u + (uint32_t)(8 * j);      // 16 k = 8 columns per instruction
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem), "r"(at),
+                     "l"(bd), "r"(idesc), "r"(accumulate)
+                     : "memory");
+      } else
       asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(ad),
                    "l"(bd), "r"(idesc), "r"(accumulate)
                    : "memory");
@@ -112,7 +138,7 @@ __global__ void __launch_bounds__(128, 1) k_probe(const uint16_t* __restrict__ A
   __syncthreads();
   if (threadIdx.x < 32) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 }
 
@@ -136,7 +162,7 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(dB, B.data(), B.size() * 2, cudaMemcpyHostToDevice));
   const int smem = (ktot / 8) * (128 + 256) * 16 + 1024 + 64;
   CK(cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  k_probe<<<1, 128, smem>>>(dA, dB, ktot, fmt, nseg, nrep, dD);
+  k_probe<<<1, 128, smem>>>(dA, dB, ktot, fmt, nseg, nrep, getenv("TC_A_TMEM") ? 1 : 0, dD);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   std::vector<float> D(128 * 256);
