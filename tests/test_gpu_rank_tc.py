@@ -337,3 +337,19 @@ def test_tc_stress_shapes_and_repeatability():
                 else:
                     assert torch.equal(got, base[mode]), (W, N, Q, r0, mode, rep)
         del eng
+
+
+def test_tc_ts_variant_passes_the_approximate_mode_tests():
+    """k_rank_tc_ts (query operand in TMEM; off by default: profiles/r02_tc_ts.md) is selected by KGEB_TC_TS=1, read once per process:
+    run the approximate-mode tests and the shape sweep in a child process with it set."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("KGEB_TC_TS") == "1":
+        pytest.skip("already inside the child")
+    env = dict(os.environ, KGEB_TC_TS="1")
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-k", "bf16_approximate or stress_shapes"], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "passed" in r.stdout
