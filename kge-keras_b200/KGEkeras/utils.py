@@ -133,15 +133,17 @@ def build_filter_csr(test, filtering_triples, side):
     Q = len(test)
     if len(filt) == 0 or Q == 0:
         return np.zeros(Q + 1, dtype=np.int64), np.zeros(0, dtype=np.int32)
-    span = int(max(filt.max(), test.max())) + 1
-    if span ** 3 >= 2 ** 62:
+    # one span per column (how many ids it can hold), so that the packed key stays below 2^63 for N * R * N, not max(N, R)^3
+    sp = [int(max(filt[:, c].max(), test[:, c].max())) + 1 for c in range(3)]
+    s0, s1, span = sp[kc[0]], sp[kc[1]], sp[vc]
+    if s0 * s1 * span >= 2 ** 63:
         raise ValueError("ids too large for the packed filter key")
     # one sortable key per filter triple: (key0, key1, value); sort, then drop adjacent duplicates (np.unique's hash
     # path is 10x slower than the integer sort on these sizes)
-    packed = np.sort((filt[:, kc[0]] * span + filt[:, kc[1]]) * span + filt[:, vc])
+    packed = np.sort((filt[:, kc[0]] * s1 + filt[:, kc[1]]) * span + filt[:, vc])
     if len(packed) > 1:
         packed = packed[np.concatenate(([True], packed[1:] != packed[:-1]))]
-    qkey = (test[:, kc[0]] * span + test[:, kc[1]]) * span
+    qkey = (test[:, kc[0]] * s1 + test[:, kc[1]]) * span
     lo = np.searchsorted(packed, qkey, side="left")
     hi = np.searchsorted(packed, qkey + span, side="left")
     lens = hi - lo

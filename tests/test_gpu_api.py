@@ -365,3 +365,30 @@ def test_out_of_range_ids_raise_on_the_evaluation_path():
         ku.validate(m, good, 50, 32, np.asarray([[1, 3, 2]]))
     with pytest.raises(IndexError, match="out of range"):
         ku.validate(m, np.asarray([[-1, 0, 2]]), 50, 32, good)
+
+
+def test_filter_csr_serves_tables_beyond_the_first_builds_key_limit():
+    """the packed filter key cubed max(N, R) and refused N > 1.66 M; per-column spans (N * R * N < 2^63) lift that.
+    A context with N = 5 M entities (no table is needed for the filter build) must build the same CSR as the host mirror."""
+    import ctypes as C
+    from KGEkeras import _abi as abi, utils as ku
+    from KGEkeras._engine import Engine
+    lib = abi.lib()
+    N, R, Q, F = 5_000_000, 40, 300, 5000
+    rng = np.random.default_rng(8)
+    q = np.stack([rng.integers(0, N, Q), rng.integers(0, R, Q), rng.integers(0, N, Q)], 1).astype(np.int32)
+    f = np.stack([rng.integers(0, N, F), rng.integers(0, R, F), rng.integers(0, N, F)], 1).astype(np.int32)
+    f[:Q, :2] = q[:, :2]                       # some filter triples share (s, p) ...
+    f[Q:2 * Q, 1:] = q[:, 1:]                  # ... and (p, o) with the queries
+    f[:2 * Q][np.all(f[:2 * Q] == np.concatenate([q, q]), axis=1), 2] ^= 1   # never the query itself
+    eng = Engine.__new__(Engine)               # filter_csr touches nothing but the context and the device
+    eng.lib, eng.device, eng.N, eng.R_ = lib, torch.device("cuda", torch.cuda.current_device()), N, R
+    h = C.c_void_p()
+    abi.check(lib.kgeb_create(C.byref(h), 0, N, R, 8, 8, 8, 8, abi.DISTMULT, 12.0))
+    eng.ctx = h
+    fh, ft = ko.build_filters([tuple(int(x) for x in r) for r in f])      # the reference's dict-of-sets (utils.py:201-205), no packing
+    for side, code, filt in (("tail", abi.SIDE_TAIL, ft), ("head", abi.SIDE_HEAD, fh)):
+        offs, ids = eng.filter_csr(q, f, code)
+        want_o, want_i = ko.filter_csr(q, side, filt)
+        np.testing.assert_array_equal(offs.cpu().numpy(), np.asarray(want_o, np.int64))
+        np.testing.assert_array_equal(ids.cpu().numpy(), np.asarray(want_i, np.int32))
