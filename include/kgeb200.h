@@ -121,12 +121,13 @@ typedef enum { KGEB_HOLE_DIRECT = 0, KGEB_HOLE_FFT = 1 } kgeb_hole_mode;
 KGEB_API int kgeb_set_hole_mode(kgeb_ctx* ctx, int mode);
 
 /* HAKE (models.py:362-400): entity rows [phase | modulus] (we = 2d), relation rows [phase | modulus | bias] (wr = 3d).
- * phase_scale = pi / embedding_range, embedding_range = (gamma + epsilon) / we / 2 (models.py:381, we already doubled);
+ * phase_div = embedding_range / pi -- the DIVISOR of models.py:390-392 (the phases are divided by it in fp32, op for op) --,
+ * embedding_range = (gamma + epsilon) / we / 2 (models.py:381, we already doubled);
  * phase_weight, mod_weight: models.py:377-378.  The modulus term is ONE Frobenius norm over all m rows of a kgeb_score_fwd
  * call (tf.norm without axis, models.py:397): scores and gradients of a call are coupled, exactly as in the reference's
  * func(); kgeb_score_bwd therefore expects the same idx (and dropout state) as the forward call it differentiates.
  * No fused training kernel and no 1-N ranking (a candidate's score would depend on its batch).  m <= 2 M rows per call. */
-KGEB_API int kgeb_set_hake_params(kgeb_ctx* ctx, float phase_scale, float phase_weight, float mod_weight);
+KGEB_API int kgeb_set_hake_params(kgeb_ctx* ctx, float phase_div, float phase_weight, float mod_weight);
 /* HAKE inference as Keras runs it: Model.predict scores its input in consecutive batches of `rows` triples (batch_size,
  * default 32), each batch its own call of func() with its own norm (models.py:397).  rows = 0 (default): the whole
  * kgeb_score_fwd call is one batch.  Forward only. */

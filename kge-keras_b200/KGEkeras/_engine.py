@@ -91,7 +91,7 @@ class Engine:
         abi.check(self.lib.kgeb_create(C.byref(h), self.device.index or 0, self.N, self.R_, cw[0], cw[1],
                                        self.we_k, self.wr_k, kind, self.gamma))
         self.ctx = h
-        if kind == abi.HAKE:   # param = (pi / embedding_range, phase_weight, mod_weight), models.py:377-381
+        if kind == abi.HAKE:   # param = (embedding_range / pi, phase_weight, mod_weight), models.py:377-381,390-392
             self.param = tuple(float(x) for x in param)
             self._check(self.lib.kgeb_set_hake_params(self.ctx, *self.param))
         else:

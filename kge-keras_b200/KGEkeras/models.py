@@ -464,7 +464,7 @@ class HAKE(EmbeddingModel):
     _score_kind = abi.HAKE   # models.py:383-400 as written: the modulus norm spans the whole call (kgeb_set_hake_params)
 
     def _param_(self):
-        return (float(self.pi / self.embedding_range), float(self.phase_weight), float(self.mod_weight))
+        return (float(self.embedding_range / self.pi), float(self.phase_weight), float(self.mod_weight))   # the divisor of models.py:390-392
 
     def predict(self, x, batch_size=32, verbose=0, **kwargs):
         """Keras Model.predict scores its input in consecutive batches of `batch_size` rows (default 32) and every batch is its

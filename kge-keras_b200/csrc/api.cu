@@ -119,11 +119,11 @@ extern "C" int kgeb_set_hole_mode(kgeb_ctx* ctx, int mode) {
   return KGEB_OK;
 }
 
-extern "C" int kgeb_set_hake_params(kgeb_ctx* ctx, float phase_scale, float phase_weight, float mod_weight) {
+extern "C" int kgeb_set_hake_params(kgeb_ctx* ctx, float phase_div, float phase_weight, float mod_weight) {
   if (!ctx) return KGEB_ERR_INVALID;
   KGEB_REQUIRE(ctx, ctx->kind == KGEB_HAKE, KGEB_ERR_INVALID, "set_hake_params: the context is not a HAKE context");
-  KGEB_REQUIRE(ctx, phase_scale > 0.f, KGEB_ERR_INVALID, "set_hake_params: phase_scale = pi / embedding_range must be positive");
-  ctx->hake_ps = phase_scale; ctx->hake_pw = phase_weight; ctx->hake_mw = mod_weight;
+  KGEB_REQUIRE(ctx, phase_div > 0.f, KGEB_ERR_INVALID, "set_hake_params: phase_div = embedding_range / pi must be positive");
+  ctx->hake_ps = phase_div; ctx->hake_pw = phase_weight; ctx->hake_mw = mod_weight;
   return KGEB_OK;
 }
 

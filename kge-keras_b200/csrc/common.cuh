@@ -22,7 +22,7 @@ struct kgeb_ctx {
   float gamma;
   float param;   // pRotatE modulus (kgeb_set_score_param), 1 otherwise
   int hole_fft;  // kgeb_set_hole_mode: HolE through the Fourier domain for power-of-two widths
-  float hake_ps, hake_pw, hake_mw;   // HAKE: pi / embedding_range, phase_weight, mod_weight (kgeb_set_hake_params)
+  float hake_ps, hake_pw, hake_mw;   // HAKE: embedding_range / pi (the phase DIVISOR), phase_weight, mod_weight (kgeb_set_hake_params)
   int64_t hake_group;                // HAKE inference: rows per Model.predict batch (kgeb_set_hake_call_rows), 0 = the whole call is one batch
   int num_sms;
   int64_t launches;

@@ -8,7 +8,7 @@
 //             k_hake_finish (one block: T = sum_i rsq[i] in double, fixed order; scores -= mod_weight * sqrt(T))
 //   backward  k_hake_rows + k_hake_finish again (T and C = sum_i dscore_i; the negative call ran in between)
 //             k_hake_bwd  (warp per triple: d/d rows of  sum_i dscore_i * score_i, TensorFlow's conventions for |x|, clip, where)
-// fp32 contract: phi = x * phase_scale, a = ((phi_s + phi_p) - phi_o) * 0.5, sinf / cosf, sums over k lane-strided then butterfly.
+// fp32 contract: phi = x / phase_div (phase_div = fp32(embedding_range / pi): the reference DIVIDES, models.py:390-392), a = ((phi_s + phi_p) - phi_o) * 0.5, sinf / cosf, sums over k lane-strided then butterfly.
 #include "frag.cuh"
 
 namespace {
@@ -44,7 +44,7 @@ __device__ __forceinline__ HakeElem hake_elem(const HakeArgs& a, const float* es
   e.mo = hake_ld<DP>(a, eo, d + k, 2, g, e.m_om);
   e.mp = hake_ld<DP>(a, rp, d + k, 1, g, e.m_pm);
   e.beta = hake_ld<DP>(a, rp, 2 * d + k, 1, g, e.m_pb);
-  e.a = __fmul_rn(__fsub_rn(__fadd_rn(__fmul_rn(phs, a.ps), __fmul_rn(php, a.ps)), __fmul_rn(pho, a.ps)), 0.5f);
+  e.a = __fmul_rn(__fsub_rn(__fadd_rn(__fdiv_rn(phs, a.ps), __fdiv_rn(php, a.ps)), __fdiv_rn(pho, a.ps)), 0.5f);
   const float b1 = fminf(e.beta, 1.f), nb = -fabsf(e.mp);
   e.cond = b1 < nb;
   e.b = e.cond ? nb : b1;
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(KGEB_THREADS) k_hake_bwd(HakeArgs a, const int
     if (cP == 0.f && coefU == 0.f) continue;
     for (int k = lane; k < d; k += 32) {
       const HakeElem e = hake_elem<DP>(a, es, rp, eo, k, (uint64_t)i);
-      const float dphi = cP * sgn(sinf(e.a)) * cosf(e.a) * 0.5f * a.ps;
+      const float dphi = __fdiv_rn(cP * sgn(sinf(e.a)) * cosf(e.a) * 0.5f, a.ps);
       add_nz(gs + k, dphi * e.m_sph);
       add_nz(gp + k, dphi * e.m_pph);
       add_nz(go + k, -dphi * e.m_oph);

@@ -360,6 +360,33 @@ def dense_grads(kind, E, R, idx, dscore, gamma=12.0, dtype=np.float64, param=1.0
     return gE, gR, tE, tR
 
 
+def dense_grads_abs(kind, E, R, idx, dscore, gamma=12.0, param=1.0):
+    """sum over the references to a row of |dscore_m * dscore/drow| in fp64: the magnitude the parity bar of a gradient entry is
+    stated against (1e-5 of the summed magnitudes of its terms, like the scores; BASELINE north star)."""
+    s, p, o = gather(E.astype(np.float64), R.astype(np.float64), idx)
+    if kind == COMPLEX:        # an entry is a signed sum of two products (pr*or + pi*oi, pr*oi - pi*or, ...): its terms are the products
+        d = s.shape[-1] // 2
+        (sr, si), (pr, pi), (orr, oi) = [(np.abs(x[..., :d]), np.abs(x[..., d:])) for x in (s, p, o)]
+        ds = np.concatenate([pr * orr + pi * oi, pr * oi + pi * orr], axis=-1)
+        dp = np.concatenate([sr * orr + si * oi, sr * oi + si * orr], axis=-1)
+        do = np.concatenate([sr * pr + pi * si, pr * si + pi * sr], axis=-1)
+    elif kind == HOLE:         # every term of the correlation carries a plus sign: the same formulas on |inputs|
+        ds, dp, do = score_grads(kind, np.abs(s), np.abs(p), np.abs(o), gamma, param)
+    else:
+        ds, dp, do = score_grads(kind, s, p, o, gamma, param)
+        ds, dp, do = np.abs(ds), np.abs(dp), np.abs(do)
+    if kind == TRANSE_L2:      # an entry is r_k / ||r|| with r_k = s_k + p_k - o_k: its terms are the three operands, not their (cancelling) sum
+        nr = np.maximum(np.linalg.norm(s + p - o, axis=1, keepdims=True), 1e-300)
+        ds = dp = do = (np.abs(s) + np.abs(p) + np.abs(o)) / nr
+    w = np.abs(np.asarray(dscore, dtype=np.float64))[:, None]
+    aE, aR = np.zeros(E.shape, np.float64), np.zeros(R.shape, np.float64)
+    idx = np.asarray(idx).astype(np.int64)
+    np.add.at(aE, idx[:, 0], w * ds)
+    np.add.at(aE, idx[:, 2], w * do)
+    np.add.at(aR, idx[:, 1], w * dp)
+    return aE, aR
+
+
 def l3_reg(E, w):
     """models.py:10-11: w * ||E||_3^3 = w * sum |e|^3 and its dense gradient 3 w e |e| (entity table only, models.py:92)."""
     return w * np.sum(np.abs(E) ** 3), 3.0 * w * E * np.abs(E)
@@ -804,16 +831,16 @@ def philox_oversample_indices(n, m, seed, offset, stream_id=0):
 # HAKE (models.py:362-400) -- batch-coupled score, restated as written
 # --------------------------------------------------------------------------------------------
 def hake_params(gamma=12.0, epsilon=2.0, e_dim_stored=None, phase_weight=0.5, mod_weight=1.0):
-    """(phase_scale, phase_weight, mod_weight): phase_scale = pi / embedding_range with embedding_range =
+    """(phase_div, phase_weight, mod_weight): phase_div = embedding_range / pi -- what models.py:390-392 DIVIDE the phases by -- with embedding_range =
     (gamma + epsilon) / e_dim / 2 and e_dim the STORED entity width 2d (models.py:371,381: e_dim is doubled before super().__init__)."""
     rng_ = (float(gamma) + float(epsilon)) / float(e_dim_stored) / 2.0
-    return (float(np.pi / rng_), float(phase_weight), float(mod_weight))
+    return (float(rng_ / np.pi), float(phase_weight), float(mod_weight))
 
 
-def _hake_parts(s, p, o, phase_scale):
+def _hake_parts(s, p, o, phase_div):
     d = s.shape[-1] // 2
     assert p.shape[-1] == 3 * d and o.shape[-1] == 2 * d
-    a = (s[..., :d] * phase_scale + p[..., :d] * phase_scale - o[..., :d] * phase_scale) / 2     # models.py:390-392,398
+    a = (s[..., :d] / phase_div + p[..., :d] / phase_div - o[..., :d] / phase_div) / 2     # models.py:390-392,398: three divisions, op for op
     ms, mo = s[..., d:], o[..., d:]
     mp, beta = p[..., d:2 * d], p[..., 2 * d:]
     b1 = np.minimum(beta, 1.0)                                     # K.clip(bias, -inf, 1), models.py:394
@@ -823,21 +850,21 @@ def _hake_parts(s, p, o, phase_scale):
     return d, a, ms, mo, mp, beta, b, cond, u
 
 
-def hake_scores(s, p, o, gamma, phase_scale, phase_weight, mod_weight):
+def hake_scores(s, p, o, gamma, phase_div, phase_weight, mod_weight):
     """gamma - (phase_weight * sum_k |sin a_k|  +  mod_weight * ||U||_F): the modulus norm runs over EVERY row of the call."""
-    _, a, *_, u = _hake_parts(s, p, o, phase_scale)
+    _, a, *_, u = _hake_parts(s, p, o, phase_div)
     r = mod_weight * np.sqrt(np.sum(u * u))
     return gamma - (phase_weight * np.sum(np.abs(np.sin(a)), axis=-1) + r)
 
 
-def hake_row_grads(s, p, o, dscore, gamma, phase_scale, phase_weight, mod_weight):
+def hake_row_grads(s, p, o, dscore, gamma, phase_div, phase_weight, mod_weight):
     """d(sum_i dscore_i * score_i) / d(s, p, o rows) with TensorFlow's conventions: d|x| = sign(x) (0 at 0), the clip passes the
     gradient where bias <= 1, the where() routes it to -|mod_p| or to the bias.  A zero modulus norm contributes no gradient
     (TensorFlow would produce NaN there)."""
-    d, a, ms, mo, mp, beta, b, cond, u = _hake_parts(s, p, o, phase_scale)
+    d, a, ms, mo, mp, beta, b, cond, u = _hake_parts(s, p, o, phase_div)
     c = np.asarray(dscore, dtype=s.dtype)[:, None]
     T = np.sum(u * u)
-    dphi = -phase_weight * c * np.sign(np.sin(a)) * np.cos(a) * 0.5 * phase_scale
+    dphi = -phase_weight * c * np.sign(np.sin(a)) * np.cos(a) * 0.5 / phase_div
     gu = (-(np.sum(c) * mod_weight) / np.sqrt(T)) * u if T > 0 else np.zeros_like(u)
     db = gu * (ms + np.abs(mo))
     g_ms = gu * (mp + b)

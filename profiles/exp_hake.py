@@ -6,7 +6,7 @@ from KGEkeras import _abi as abi
 from KGEkeras._engine import Engine
 N, R, d, B, K = 40943, 11, 100, 16384, 10
 rng = np.random.default_rng(0)
-eng = Engine(abi.HAKE, N, R, 2 * d, 3 * d, 12.0, param=(float(np.pi / ((12.0 + 2.0) / (2 * d) / 2)), 0.5, 1.0))   # pi / embedding_range, phase_weight, mod_weight
+eng = Engine(abi.HAKE, N, R, 2 * d, 3 * d, 12.0, param=(float(((12.0 + 2.0) / (2 * d) / 2) / np.pi), 0.5, 1.0))   # embedding_range / pi, phase_weight, mod_weight
 pos = torch.from_numpy(np.stack([rng.integers(0, N, B), rng.integers(0, R, B), rng.integers(0, N, B)], 1).astype(np.int32)).cuda()
 kw = dict(K=K, loss_kind=abi.PAIRWISE_HINGE, margin=1.0, seed=1, opt_kind=abi.LAZY_ADAM)
 for i in range(3):

@@ -579,7 +579,7 @@ def test_hake_and_hole_constructors_without_gpu():
     assert (m.e_dim, m.r_dim) == (20, 30)
     assert abs(m.embedding_range - (12 + 2) / 20 / 2) < 1e-12
     ps, pw, mw = m._param_()
-    assert abs(ps - np.pi / m.embedding_range) < 1e-9 and (pw, mw) == (0.25, 2.0)
+    assert abs(ps - m.embedding_range / np.pi) < 1e-12 and (pw, mw) == (0.25, 2.0)      # the DIVISOR of models.py:390-392
     assert ko.hake_params(12, 2, 20, 0.25, 2.0) == pytest.approx((ps, pw, mw))
     h = KGEkeras.HolE(e_dim=64, r_dim=64, num_entities=5, num_relations=2, fft=False)
     assert h.fft is False and KGEkeras.HolE(e_dim=64, r_dim=64, num_entities=5, num_relations=2).fft is True
@@ -605,3 +605,21 @@ def test_tf_shim_type_checks_against_the_header():
         text = fh.read()
     for op in ("KgebScore", "KgebScoreGrad", "KgebScoreGradSlices", "KgebTrainStep", "KgebRank1N"):
         assert f'REGISTER_OP("{op}")' in text and f'Name("{op}")' in text, op
+
+
+@pytest.mark.parametrize("kind", [ko.DISTMULT, ko.TRANSE_L1, ko.TRANSE_L2, ko.COMPLEX, ko.HOLE])
+def test_dense_grads_abs_bounds_the_gradient_and_the_fp32_pass(kind):
+    """The magnitude the gradient parity bar is stated against (sum of |terms| of an entry) dominates the entry itself, and the
+    oracle's own fp32 pass sits inside 1e-5 of it: the bar the GPU tests apply is attainable in fp32 for every headline kind."""
+    rng = np.random.default_rng(5 + kind)
+    N, R, d, m = 40, 4, 16, 200
+    W = 2 * d if kind == ko.COMPLEX else d
+    E, Rm = ko.glorot_uniform(rng, N, W) * 4.0, ko.glorot_uniform(rng, R, W) * 4.0
+    idx = np.stack([rng.integers(0, N, m), rng.integers(0, R, m), rng.integers(0, N, m)], axis=1).astype(np.int32)
+    dscore = rng.normal(size=m)
+    g64 = ko.dense_grads(kind, E, Rm, idx, dscore, 2.0, np.float64)
+    g32 = ko.dense_grads(kind, E, Rm, idx, dscore.astype(np.float32), 2.0, np.float32)
+    aE, aR = ko.dense_grads_abs(kind, E, Rm, idx, dscore, 2.0)
+    assert np.all(np.abs(g64[0]) <= aE * (1 + 1e-12) + 1e-300) and np.all(np.abs(g64[1]) <= aR * (1 + 1e-12) + 1e-300)
+    assert np.all(np.abs(g32[0].astype(np.float64) - g64[0]) <= 1e-5 * aE + 1e-30)
+    assert np.all(np.abs(g32[1].astype(np.float64) - g64[1]) <= 1e-5 * aR + 1e-30)
