@@ -9,6 +9,7 @@
 // and add (__fmul_rn/__fadd_rn, no FMA), so the three code paths below give bit-identical scores for the same (q,c)
 // and oracle.kge_oracle.seqk_scores reproduces them on the CPU.  The filter is applied as a correction pass:
 // counts -= #{c in filter(q) : score(q,c) > target}.
+#include <stdlib.h>
 #include "rank_common.cuh"
 
 using namespace kgeb_rank;
@@ -364,6 +365,210 @@ __global__ void __launch_bounds__(256) k_rank_tile(const float* __restrict__ Es,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// the packed tile kernel (round 2): the same 64 x 64 tile and the same per-pair sequential-k fp32 arithmetic, issued as the
+// sm_100 two-wide fp32 add (add.rn.f32x2 -> SASS FADD2).  The two halves of a packed accumulator are two
+// DIFFERENT (query, entity) pairs -- one query against the entity pair (n, n + 32) at the same k -- so every pair still sees its
+// terms in k order with separately rounded operations: bit-identical scores, half the issue slots.  ptxas folds what the scalar
+// form got from operand modifiers into the packed instruction as well: the query value enters as a scalar broadcast operand
+// (`R.F32`), the negation of e and the |x| of the L1 term as `-R.F32x2` / `|R|.F32x2` (checked in SASS; no MOV, no LOP3).
+// Entity tiles sit in shared memory pair-interleaved -- row p holds (e_p[k], e_{p+32}[k]) for k = 0..31 -- so one LDS.128
+// delivers two k of a pair already in aligned register pairs; the loader thread that fetches rows p and p + 32 interleaves
+// them in registers and still stores 128 bits at a time (chunk order swapped in the upper half of a quarter warp: no bank
+// conflicts).  Work is one flat list of (query tile, entity tile) items cut into equal contiguous ranges over a grid of
+// exactly SMs x resident CTAs, so no wave is partially filled whatever Q and N are (the 2-D grid of the scalar kernel ran
+// 637 CTAs on 296 slots on the WN18RR shape: a third wave 15 % full); counts are flushed when a range crosses into the next
+// query tile.
+// ---------------------------------------------------------------------------------------------------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float lo2(u64 v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi2(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 bc2(float a) { return pk2(a, a); }
+__device__ __forceinline__ u64 neg2(u64 v) { return pk2(-lo2(v), -hi2(v)); }
+__device__ __forceinline__ u64 abs2(u64 v) { return pk2(fabsf(lo2(v)), fabsf(hi2(v))); }
+
+// seq_term<OP> on two pairs at once: a, a2 belong to the query, e2 = (E[c][k], E[c + 32][k]).  x - y is issued as x + (-y): the same
+// IEEE result.  Only the L1 ops are packed: ptxas contracts a packed multiply (mul.rn.f32x2, or fma.rn.f32x2 with a -0 addend) and
+// the packed add behind it into ONE FFMA2 whatever the .rn qualifiers and --fmad say (seen in SASS), which rounds once where the
+// contract rounds twice -- so the dot-product, L2 and ModE ops stay on the scalar kernel, whose __fmul_rn / __fadd_rn are honoured.
+template <int OP>
+__device__ __forceinline__ u64 seq_term2(u64 acc, float a, float a2, u64 e2) {
+  static_assert(OP == OP_L1_TAIL || OP == OP_L1_HEAD, "packed ops: L1 only");
+  const u64 r = OP == OP_L1_TAIL ? add2(bc2(a), neg2(e2)) : add2(add2(e2, bc2(a)), bc2(-a2));
+  return add2(acc, abs2(r));
+}
+template <int OP>
+constexpr bool op_packed() { return OP == OP_L1_TAIL || OP == OP_L1_HEAD; }
+
+constexpr int BPP = 68;   // floats per pair row: 32 k x 2 + 4 (row stride = 4 banks mod 32: 8 rows of a quarter warp cover all banks)
+
+template <int OP>
+__global__ void __launch_bounds__(256, 2) k_rank_tile2(const float* __restrict__ Es, int64_t n_rows, int ldE, int W,
+                                                       const float* __restrict__ qvec, int qw, const float* __restrict__ tscore,
+                                                       int64_t Q, SeqFin fin, int32_t* counts) {
+  constexpr bool HEAD = op_two_part<OP>();
+  extern __shared__ __align__(16) float tile_smem[];
+  typedef float (*TileBuf)[BQ][BKP];    // [buffer][query row][k]
+  typedef float (*PairBuf)[BN / 2][BPP];   // [buffer][entity pair][k][2]
+  TileBuf As = reinterpret_cast<TileBuf>(tile_smem);
+  PairBuf Bp = reinterpret_cast<PairBuf>(tile_smem + 2 * BQ * BKP);
+  TileBuf As2 = reinterpret_cast<TileBuf>(tile_smem + 2 * BQ * BKP + 2 * (BN / 2) * BPP);   // two-part (head) queries only
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t ntiles = (n_rows + BN - 1) / BN;
+  const int64_t items = ((Q + BQ - 1) / BQ) * ntiles;
+  const int64_t t0 = items * blockIdx.x / gridDim.x, t1 = items * (blockIdx.x + 1) / gridDim.x;
+  if (t0 >= t1) return;
+  const int lr = tid >> 3, lk4 = tid & 7;
+  const int swp = (lk4 >> 2) & 1;
+  const int nkc = (W + BK - 1) / BK;
+
+  float tq[4] = {0.f, 0.f, 0.f, 0.f};
+  int cnt[4] = {0, 0, 0, 0};
+  int64_t cur_qt = -1, q0 = 0;
+  auto flush = [&]() {
+    // the 16 tx lanes of one ty live in one half-warp: butterfly inside 16 lanes, then one integer atomic per query
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int c = cnt[i];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      const int64_t q = q0 + ty + 16 * i;
+      if (tx == 0 && q < Q && c != 0) atomicAdd(counts + q, c);
+      cnt[i] = 0;
+    }
+  };
+
+  // the k-chunks of all items of this CTA form ONE pipeline: while chunk (t, kc) is consumed, the chunk after it -- the first one
+  // of item t + 1 after the last one of item t -- is in flight from global memory into registers, and is stored into the other
+  // buffer behind the computation; one barrier per chunk, no load latency exposed between items
+  float4 ra[2], ra2[2], rb[2];
+  auto gload = [&](int64_t gq0, int64_t gn0, int kc) {   // first query / first entity row of the item the chunk belongs to
+    const int k = kc * BK + lk4 * 4;
+    const bool kin = k < W;   // W % 4 == 0: a float4 is entirely inside or outside the row
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t q = gq0 + lr + 32 * h;
+      const int64_t n = gn0 + lr + 32 * h;
+      ra[h] = (kin && q < Q) ? ldg4(reinterpret_cast<const float4*>(qvec + q * (int64_t)qw + k)) : f4zero();
+      if (HEAD) ra2[h] = (kin && q < Q) ? ldg4(reinterpret_cast<const float4*>(qvec + q * (int64_t)qw + W + k)) : f4zero();
+      rb[h] = (kin && n < n_rows) ? ldg4(reinterpret_cast<const float4*>(Es + n * (int64_t)ldE + k)) : f4zero();
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = lr + 32 * h;
+      *reinterpret_cast<float4*>(&As[buf][r][lk4 * 4]) = ra[h];
+      if (HEAD) *reinterpret_cast<float4*>(&As2[buf][r][lk4 * 4]) = ra2[h];
+    }
+    // rows lr and lr + 32 interleaved: chunk 2 lk4 = k, k+1; chunk 2 lk4 + 1 = k+2, k+3
+    const float4 c0 = make_float4(rb[0].x, rb[1].x, rb[0].y, rb[1].y), c1 = make_float4(rb[0].z, rb[1].z, rb[0].w, rb[1].w);
+    float* row = &Bp[buf][lr][lk4 * 8];
+    *reinterpret_cast<float4*>(row + 4 * swp) = swp ? c1 : c0;
+    *reinterpret_cast<float4*>(row + 4 * (1 - swp)) = swp ? c0 : c1;
+  };
+
+  int64_t qt = t0 / ntiles, nt = t0 - qt * ntiles;   // the only division: items advance entity tile first, then query tile
+  gload(qt * BQ, nt * BN, 0);
+  sstore(0);
+  __syncthreads();
+  int buf = 0;
+  for (int64_t t = t0; t < t1; ++t) {
+    const int64_t n0 = nt * BN;
+    int64_t qt_next = qt, nt_next = nt + 1;
+    if (nt_next == ntiles) { nt_next = 0; ++qt_next; }
+    if (qt != cur_qt) {   // CTA-uniform
+      if (cur_qt >= 0) flush();
+      cur_qt = qt; q0 = qt * BQ;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t q = q0 + ty + 16 * i;
+        tq[i] = q < Q ? __ldg(tscore + q) : 0.f;
+      }
+    }
+    u64 acc[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[i][0] = 0ull; acc[i][1] = 0ull; }
+
+    for (int kc = 0; kc < nkc; ++kc) {
+      const bool more = kc + 1 < nkc || t + 1 < t1;
+      if (more) { if (kc + 1 < nkc) gload(q0, n0, kc + 1); else gload(qt_next * BQ, nt_next * BN, 0); }  // in flight while this chunk is computed
+      const int klim = (W - kc * BK) < BK ? (W - kc * BK) : BK;   // multiple of 4
+#pragma unroll 2
+      for (int k = 0; k < klim; k += 4) {
+        float4 a[4], a2[4];
+        ulonglong2 b[2][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          a[i] = *reinterpret_cast<const float4*>(&As[buf][ty + 16 * i][k]);
+          a2[i] = HEAD ? *reinterpret_cast<const float4*>(&As2[buf][ty + 16 * i][k]) : f4zero();
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          b[j][0] = *reinterpret_cast<const ulonglong2*>(&Bp[buf][tx + 16 * j][2 * k]);
+          b[j][1] = *reinterpret_cast<const ulonglong2*>(&Bp[buf][tx + 16 * j][2 * k + 4]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            u64 c = acc[i][j];
+            c = seq_term2<OP>(c, a[i].x, a2[i].x, b[j][0].x);
+            c = seq_term2<OP>(c, a[i].y, a2[i].y, b[j][0].y);
+            c = seq_term2<OP>(c, a[i].z, a2[i].z, b[j][1].x);
+            c = seq_term2<OP>(c, a[i].w, a2[i].w, b[j][1].y);
+            acc[i][j] = c;
+          }
+      }
+      if (more) sstore(buf ^ 1);   // the other buffer was last read one chunk ago, before the previous barrier
+      __syncthreads();
+      buf ^= 1;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int64_t n = n0 + tx + 16 * j;   // the pair's rows: n and n + 32
+        const float s_lo = seq_finish<OP>(lo2(acc[i][j]), fin), s_hi = seq_finish<OP>(hi2(acc[i][j]), fin);
+        cnt[i] += (n < n_rows && s_lo > tq[i]) ? 1 : 0;
+        cnt[i] += (n + 32 < n_rows && s_hi > tq[i]) ? 1 : 0;
+      }
+    qt = qt_next; nt = nt_next;
+  }
+  flush();
+}
+
+// launches the tile kernel of one op: the packed kernel on a grid of exactly SMs x resident CTAs, or (ops with a multiply or sinf; KGEB_RANK_TILE=scalar
+// for A/B runs -- identical integer counts either way) the round-1 scalar kernel on its 2-D grid
+template <int OP>
+int launch_tile(kgeb_ctx* ctx, dim3 grid2d, int64_t items, cudaStream_t st, const float* E_shard, int64_t n_rows, const float* qvec,
+                int qw, const float* tscore, int64_t Q, SeqFin fin, int32_t* counts) {
+  static const bool scalar_tile = [] { const char* e = getenv("KGEB_RANK_TILE"); return e && !strcmp(e, "scalar"); }();
+  if constexpr (op_packed<OP>()) {
+    if (!scalar_tile) {
+      auto kern = k_rank_tile2<OP>;
+      const size_t tsm = ((size_t)(op_two_part<OP>() ? 4 : 2) * BQ * BKP + 2 * (BN / 2) * BPP) * sizeof(float);
+      static int occ = 0;   // resident CTAs per SM of this instantiation, asked once
+      if (occ == 0) {
+        KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+        int o = 0;
+        KGEB_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, 256, tsm));
+        occ = o < 1 ? 1 : o;
+      }
+      int64_t g = (int64_t)ctx->num_sms * occ;
+      if (g > items) g = items;
+      kern<<<(unsigned)g, 256, tsm, st>>>(E_shard, n_rows, ctx->ldE, ctx->we, qvec, qw, tscore, Q, fin, counts);
+      return KGEB_OK;
+    }
+  }
+  const size_t tsm = (size_t)(op_two_part<OP>() ? 6 : 4) * BQ * BKP * sizeof(float);
+  KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_rank_tile<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+  k_rank_tile<OP><<<grid2d, 256, tsm, st>>>(E_shard, n_rows, ctx->ldE, ctx->we, qvec, qw, tscore, Q, fin, counts);
+  return KGEB_OK;
+}
+
 int grid1d(const kgeb_ctx* ctx, int64_t n, int threads) {
   int64_t b = (n + threads - 1) / threads;
   const int64_t cap = (int64_t)ctx->num_sms * 16;
@@ -459,14 +664,10 @@ extern "C" int kgeb_rank_1n(kgeb_ctx* ctx, const float* E_shard, int64_t row_off
   if (split < 1) split = 1;
   if (split > 65535) split = 65535;
   dim3 grid((unsigned)qtiles, (unsigned)split);
-#define KGEB_RANK_LAUNCH(OPV)                                                                                               \
-  {                                                                                                                         \
-    const size_t tsm = (size_t)(op_two_part<OPV>() ? 6 : 4) * BQ * BKP * sizeof(float);                                     \
-    KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_rank_tile<OPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));       \
-    k_rank_tile<OPV><<<grid, 256, tsm, st>>>(E_shard, n_rows, ctx->ldE, ctx->we, qvec, qw, tscore, Q, fin, counts);         \
-  }
   const SeqFin fin = seq_fin(ctx);
   KGEB_TIME_BEGIN(ctx, KGEB_TIMED_RANK_TILE, st);
+  int rc = KGEB_OK;
+#define KGEB_RANK_LAUNCH(OPV) rc = launch_tile<OPV>(ctx, grid, qtiles * ntiles, st, E_shard, n_rows, qvec, qw, tscore, Q, fin, counts)
   switch (op) {
     case OP_ML1_HEAD: KGEB_RANK_LAUNCH(OP_ML1_HEAD); break;
     case OP_ML2_HEAD: KGEB_RANK_LAUNCH(OP_ML2_HEAD); break;
@@ -478,6 +679,7 @@ extern "C" int kgeb_rank_1n(kgeb_ctx* ctx, const float* E_shard, int64_t row_off
     case OP_L2_TAIL: KGEB_RANK_LAUNCH(OP_L2_TAIL); break;
     default: KGEB_RANK_LAUNCH(OP_L2_HEAD); break;
   }
+  if (rc != KGEB_OK) return rc;
   KGEB_TIME_END(ctx, KGEB_TIMED_RANK_TILE, st);
   KGEB_LAUNCH_OK(ctx);
   if (filt_offsets)

@@ -291,6 +291,45 @@ def test_rank_counts_dyadic_exact_with_ties(kind, side):
     np.testing.assert_array_equal(counts, want.astype(np.int32))
 
 
+@pytest.mark.parametrize("side", ["tail", "head"])
+@pytest.mark.parametrize("gamma", [12.0, 0.0])
+def test_rank_tile_flat_work_list(side, gamma):
+    """The packed TransE-L1 tile kernel cuts ONE list of (query tile, entity tile) items into equal ranges over SMs x resident CTAs:
+    with 11 x 101 items on <= 296 CTAs every CTA owns several items, ranges start and end inside a query tile and cross into the next
+    one (counts flushed, target scores reloaded, the chunk pipeline running across the boundary); ragged last tiles on both axes and a
+    ragged last k-chunk (52 = 32 + 20).  Integer counts equal the oracle's sequential-k fp32 ranks."""
+    kind, N, R, d, Q = ko.TRANSE_L1, 6400 + 17, 5, 52, 640 + 5
+    eng, E, Rm = make_engine(kind, N, R, d, seed=77, gamma=gamma)
+    rng = np.random.default_rng(78)
+    tri = rand_triples(rng, Q, N, R)
+    sd = 0 if side == "tail" else 1
+    counts = eng.rank_counts(tri, sd).cpu().numpy()
+    qv = ko.query_vectors(kind, E, Rm, tri, side)
+    sc = ko.seqk_scores(kind, qv, E, side, gamma)
+    tgt = tri[:, 2] if side == "tail" else tri[:, 0]
+    want = (sc > sc[np.arange(Q), tgt][:, None]).sum(axis=1)
+    np.testing.assert_array_equal(counts, want.astype(np.int32))
+    # any row partition adds up to the same integers (each shard is its own flat list)
+    acc = np.zeros_like(counts)
+    for r0, r1 in ((0, 1000), (1000, 1063), (1063, N)):
+        acc += eng.rank_counts(tri, sd, row_range=(r0, r1)).cpu().numpy()
+    np.testing.assert_array_equal(acc, counts)
+
+
+def test_scalar_tile_kernel_variant_in_child_process():
+    """KGEB_RANK_TILE=scalar (read once per process) keeps the round-1 scalar tile kernel for A/B runs: the TransE-L1 rank tests pass on it too."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("KGEB_RANK_TILE") == "scalar":
+        pytest.skip("already inside the child")
+    env = dict(os.environ, KGEB_RANK_TILE="scalar")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
+                        "rank_tile_flat_work_list or rank_shards_sum or (rank_counts and not HOLE)"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "passed" in r.stdout
+
+
 @pytest.mark.parametrize("opt", [ko.OPT_SGD, ko.OPT_ADAGRAD, ko.OPT_LAZY_ADAM, ko.OPT_ADAM_DENSE])
 def test_opt_update_exact_inputs(opt):
     """Optimizer kernel alone, fed the same fp32 gradient as the oracle, Keras default eps = 1e-7, 3 steps."""
