@@ -649,6 +649,10 @@ class RankPlan:
             cap = int(worklist_cap) if worklist_cap else min(2 ** 31 - 2, max(1 << 20, Q * (64 + (self.r1 - self.r0) // 128)))
             self._alloc_ws(cap)
         self.graph = None
+        # run the two sides as parallel branches when a side is too small to fill the GPU (see _enqueue_sides); KGEB_RANK_FORK=0/1 overrides
+        fk = os.environ.get("KGEB_RANK_FORK")
+        self.fork_sides = (Q * max(self.r1 - self.r0, 0) < 10 ** 9) if fk is None else fk == "1"
+        self._side_streams = None
         if not hasattr(eng, "_plans"):
             import weakref
             eng._plans = weakref.WeakSet()
@@ -682,19 +686,37 @@ class RankPlan:
 
     def _enqueue_sides(self, eng, lib, Q, st):
         e_shard = C.c_void_p(eng.E.data_ptr() + self.r0 * eng.we_k * 4)
+        if self.fork_sides:
+            # the two sides share nothing but read-only inputs (own query vectors, target scores, worklist, count row): on small shards,
+            # where a side's kernels do not fill the GPU and a pass is mostly launch-to-launch latency, they run as two branches
+            # (two streams joined by events; two parallel branches of the CUDA graph when captured)
+            main = torch.cuda.current_stream()
+            if self._side_streams is None:
+                self._side_streams = [torch.cuda.Stream(device=eng.device) for _ in (0, 1)]
+            for sd in (abi.SIDE_TAIL, abi.SIDE_HEAD):
+                ss = self._side_streams[sd]
+                ss.wait_stream(main)
+                with torch.cuda.stream(ss):
+                    self._enqueue_side(eng, lib, Q, C.c_void_p(ss.cuda_stream), e_shard, sd)
+            for ss in self._side_streams:
+                main.wait_stream(ss)
+            return
         for sd in (abi.SIDE_TAIL, abi.SIDE_HEAD):
-            qv, ts, (fo, fi), cnt = self.qvec[sd], self.tscore[sd], self.filt[sd], self.counts[sd]
-            eng._check(lib.kgeb_query_prep(eng.ctx, _ptr(eng.E), 0, eng.N, _ptr(eng.Rel), _ptr(self.tri), Q, sd, _ptr(qv), st))
-            eng._check(lib.kgeb_target_scores(eng.ctx, _ptr(eng.E), 0, eng.N, _ptr(qv), _ptr(self.tri), Q, sd, _ptr(ts), st))
-            if self.r1 <= self.r0:
-                continue
-            if self.use_tc:
-                eng._check(lib.kgeb_rank_1n_tc(eng.ctx, e_shard, self.r0, self.r1 - self.r0, _ptr(self.packed), _ptr(qv), _ptr(ts),
-                                               _ptr(self.tri), Q, sd, _ptr(fo), _ptr(fi), self.tc_mode, _ptr(self.ws[sd]), self.ws_bytes,
-                                               self.cap, _ptr(cnt), st))
-            else:
-                eng._check(lib.kgeb_rank_1n(eng.ctx, e_shard, self.r0, self.r1 - self.r0, _ptr(qv), _ptr(ts), _ptr(self.tri), Q, sd,
-                                            _ptr(fo), _ptr(fi), _ptr(cnt), st))
+            self._enqueue_side(eng, lib, Q, st, e_shard, sd)
+
+    def _enqueue_side(self, eng, lib, Q, st, e_shard, sd):
+        qv, ts, (fo, fi), cnt = self.qvec[sd], self.tscore[sd], self.filt[sd], self.counts[sd]
+        eng._check(lib.kgeb_query_prep(eng.ctx, _ptr(eng.E), 0, eng.N, _ptr(eng.Rel), _ptr(self.tri), Q, sd, _ptr(qv), st))
+        eng._check(lib.kgeb_target_scores(eng.ctx, _ptr(eng.E), 0, eng.N, _ptr(qv), _ptr(self.tri), Q, sd, _ptr(ts), st))
+        if self.r1 <= self.r0:
+            return
+        if self.use_tc:
+            eng._check(lib.kgeb_rank_1n_tc(eng.ctx, e_shard, self.r0, self.r1 - self.r0, _ptr(self.packed), _ptr(qv), _ptr(ts),
+                                           _ptr(self.tri), Q, sd, _ptr(fo), _ptr(fi), self.tc_mode, _ptr(self.ws[sd]), self.ws_bytes,
+                                           self.cap, _ptr(cnt), st))
+        else:
+            eng._check(lib.kgeb_rank_1n(eng.ctx, e_shard, self.r0, self.r1 - self.r0, _ptr(qv), _ptr(ts), _ptr(self.tri), Q, sd,
+                                        _ptr(fo), _ptr(fi), _ptr(cnt), st))
 
     def capture(self):
         """Record the device work of one pass into a CUDA graph; run() then replays it.  The all-reduce of the partial counts is
