@@ -401,6 +401,14 @@ __device__ __forceinline__ u64 seq_term2(u64 acc, float a, float a2, u64 e2) {
 }
 template <int OP>
 constexpr bool op_packed() { return OP == OP_L1_TAIL || OP == OP_L1_HEAD; }
+// the same term with the roles swapped (k_rank_tile3): e is the scalar, a / a2 the packed values of a query pair.  Tail: e - a, and
+// |e - a| = |a - e| bit for bit; head: (e + a) - a2 as written.
+template <int OP>
+__device__ __forceinline__ u64 seq_term3(u64 acc, float e, u64 a, u64 a2) {
+  static_assert(OP == OP_L1_TAIL || OP == OP_L1_HEAD, "packed ops: L1 only");
+  const u64 r = OP == OP_L1_TAIL ? add2(bc2(e), neg2(a)) : add2(add2(bc2(e), a), neg2(a2));
+  return add2(acc, abs2(r));
+}
 
 constexpr int BPP = 68;   // floats per pair row: 32 k x 2 + 4 (row stride = 4 banks mod 32: 8 rows of a quarter warp cover all banks)
 
@@ -540,6 +548,228 @@ __global__ void __launch_bounds__(256, 2) k_rank_tile2(const float* __restrict__
   flush();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// the decoupled packed tile kernel: same arithmetic as k_rank_tile2, no load instruction and no CTA-wide barrier in the compute
+// warps' steady state.  profiles/r02_rank_tile2_summary.md: the k-loop of k_rank_tile2 alone reaches ~90 % of the fp32 add pipe, staging
+// the next chunk through registers costs 14 % and the per-chunk barrier 7 %.  Here
+//   * one PRODUCER warp streams the candidate tiles: every k-chunk of a 64-row entity tile is 64 bulk async copies (cp.async.bulk, one
+//     128-byte piece of a row each, rows padded to 144 bytes in shared memory: conflict-free LDS.128) into a ring of NST stages that
+//     complete on mbarriers (full: transaction bytes; empty: one arrival per consumer warp);
+//   * the 64-query tile is RESIDENT in shared memory for as long as the CTA's items stay in that query tile, stored pair-interleaved
+//     (row p = queries p and p + 32, (q_p[k], q_{p+32}[k]) adjacent), so the packed operand of FADD2 is now the QUERY pair and the candidate
+//     value is the scalar broadcast operand: d = e - q (|e - q| = |q - e| exactly), or (e + a) - a2 for the head side;
+//   * two consumer groups of 8 warps share the resident query tile and take alternate entity tiles; their chunks interleave in the ring.
+// One CTA of 17 warps per SM; used when the resident tile fits (TransE-L1 widths up to ~400 tail / ~200 head), else k_rank_tile2.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rk_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rk_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rk_smem(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void rk_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rk_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rk_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rk_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void rk_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rk_smem(dst)), "l"(src),
+               "r"(bytes), "r"(rk_smem(bar))
+               : "memory");
+}
+__device__ __forceinline__ void rk_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "RK_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra RK_DONE;\n\t"
+      "bra RK_WAIT;\n\t"
+      "RK_DONE:\n\t"
+      "}" ::"r"(rk_smem(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+constexpr int T3_NST = 8;                       // ring stages (a stage = one k-chunk of one 64-row entity tile)
+constexpr int T3_ESTR = 36;                     // floats per candidate row in a stage: 32 + 4 (row stride = 4 banks mod 32)
+constexpr int T3_STAGE_FLOATS = BN * T3_ESTR;
+constexpr int T3_PW = 4;                        // producer warps: a bulk copy is a UNIFORM instruction (UBLKCP), a warp issues its lanes' copies one
+                                                // by one (ELECT + R2UR per copy, ~40 cycles each), so the 64 rows of a stage are spread over 4 warps
+constexpr int T3_THREADS = (16 + T3_PW) * 32;   // 2 consumer groups x 8 warps + the producer warps
+__host__ __device__ inline int t3_qstride(int W) { return 2 * W + ((2 * W) % 32 == 0 ? 8 : 0); }   // floats per pair row; adjacent rows in distinct banks
+inline size_t t3_smem_bytes(int W, bool head) {
+  return ((size_t)(head ? 2 : 1) * (BQ / 2) * t3_qstride(W) + (size_t)T3_NST * T3_STAGE_FLOATS) * sizeof(float) + 2 * T3_NST * sizeof(uint64_t);
+}
+
+template <int OP>
+__global__ void __launch_bounds__(T3_THREADS, 1) k_rank_tile3(const float* __restrict__ Es, int64_t n_rows, int ldE, int W,
+                                                              const float* __restrict__ qvec, int qw, const float* __restrict__ tscore,
+                                                              int64_t Q, SeqFin fin, int32_t* counts) {
+  constexpr bool HEAD = op_two_part<OP>();
+  extern __shared__ __align__(16) float tile_smem[];
+  const int QS = t3_qstride(W);
+  float* q2 = tile_smem;                                              // [part][32 pairs][QS]
+  float* ring = tile_smem + (HEAD ? 2 : 1) * (BQ / 2) * QS;           // [NST][64 rows][ESTR]
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + T3_NST * T3_STAGE_FLOATS);
+  uint64_t* empty = full + T3_NST;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ntiles = (n_rows + BN - 1) / BN;
+  const int64_t items = ((Q + BQ - 1) / BQ) * ntiles;
+  const int64_t t0 = items * blockIdx.x / gridDim.x, t1 = items * (blockIdx.x + 1) / gridDim.x;
+  const int nkc = (W + BK - 1) / BK;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < T3_NST; ++i) { rk_mbar_init(full + i, T3_PW); rk_mbar_init(empty + i, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (t0 >= t1) return;
+  // the CTA's items as runs inside one query tile: run r covers items [ta, tb) of query tile qt; inside a run the items pair up
+  // (2 P, 2 P + 1) -> (group 0, group 1) and the chunks enter the ring in the order (P, kc, group)
+  const int64_t qt_first = t0 / ntiles;
+
+  if (warp >= 16) {
+    // ---------------- producers: warp pw streams rows [16 pw, 16 pw + 16) of every stage ----------------
+    const int pw = warp - 16;
+    const int r = 16 * pw + (lane & 15);
+    uint32_t pos = 0;
+    int64_t ta = t0;
+    for (int64_t qt = qt_first; ta < t1; ++qt) {
+      const int64_t tb = (qt + 1) * ntiles < t1 ? (qt + 1) * ntiles : t1;
+      const int64_t nt0 = ta - qt * ntiles;
+      const int n = (int)(tb - ta);
+      for (int i = 0; i < n; i += 2) {
+        const int both = i + 1 < n ? 2 : 1;
+        for (int kc = 0; kc < nkc; ++kc) {
+          const uint32_t bytes = (uint32_t)((W - kc * BK) < BK ? (W - kc * BK) : BK) * 4u;
+          for (int g = 0; g < both; ++g, ++pos) {
+            const int st = pos % T3_NST;
+            const int64_t n0 = (nt0 + i + g) * BN;
+            const int64_t left = n_rows - n0 - 16 * pw;               // rows of this warp's slice that exist
+            const uint32_t nv = left >= 16 ? 16u : (left > 0 ? (uint32_t)left : 0u);
+            if (lane == 0) {
+              if (pos >= T3_NST) rk_mbar_wait(empty + st, ((pos / T3_NST) - 1) & 1u);
+              rk_mbar_expect_tx(full + st, nv * bytes);               // one arrival per producer warp (also when its slice is empty)
+            }
+            __syncwarp();
+            float* dst = ring + (size_t)st * T3_STAGE_FLOATS;
+            if (lane < 16 && (uint32_t)(lane & 15) < nv) rk_bulk_g2s(dst + r * T3_ESTR, Es + (n0 + r) * (int64_t)ldE + kc * BK, bytes, full + st);
+          }
+        }
+      }
+      ta = tb;
+    }
+    return;
+  }
+
+  // ---------------- consumers ----------------
+  const int g = warp >> 3;                       // consumer group
+  const int tg = threadIdx.x & 255, tx = tg & 15, ty = tg >> 4;
+  uint32_t run_base = 0;
+  int64_t ta = t0;
+  for (int64_t qt = qt_first; ta < t1; ++qt) {
+    const int64_t tb = (qt + 1) * ntiles < t1 ? (qt + 1) * ntiles : t1;
+    const int64_t nt0 = ta - qt * ntiles, q0 = qt * BQ;
+    const int n = (int)(tb - ta);
+    // (re)load the resident query tile, pair-interleaved; every consumer thread is past the previous run when the first barrier opens
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    {
+      const int w4 = W >> 2;
+      for (int idx = threadIdx.x; idx < (HEAD ? 2 : 1) * (BQ / 2) * w4; idx += 512) {
+        const int part = idx / ((BQ / 2) * w4), rem = idx - part * (BQ / 2) * w4;
+        const int pr = rem / w4, k = (rem - pr * w4) * 4;
+        const int64_t qa = q0 + pr, qb = q0 + pr + 32;
+        const float4 a = qa < Q ? ldg4(reinterpret_cast<const float4*>(qvec + qa * (int64_t)qw + part * W + k)) : f4zero();
+        const float4 b = qb < Q ? ldg4(reinterpret_cast<const float4*>(qvec + qb * (int64_t)qw + part * W + k)) : f4zero();
+        float* row = q2 + ((size_t)part * (BQ / 2) + pr) * QS + 2 * k;
+        *reinterpret_cast<float4*>(row) = make_float4(a.x, b.x, a.y, b.y);
+        *reinterpret_cast<float4*>(row + 4) = make_float4(a.z, b.z, a.w, b.w);
+      }
+    }
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    float tq[4];
+    int cnt[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int64_t qa = q0 + ty + 16 * i, qb = qa + 32;
+      tq[2 * i] = qa < Q ? __ldg(tscore + qa) : 0.f;
+      tq[2 * i + 1] = qb < Q ? __ldg(tscore + qb) : 0.f;
+    }
+    const float* qrow0 = q2 + (size_t)ty * QS;
+    const float* qrow1 = q2 + (size_t)(ty + 16) * QS;
+    const size_t part2 = (size_t)(BQ / 2) * QS;   // offset of the second part (head queries)
+
+    for (int i = g; i < n; i += 2) {
+      const int both = (i | 1) < n ? 2 : 1;       // this pair of items has a partner for the other group
+      const uint32_t base = run_base + (uint32_t)(i >> 1) * 2u * (uint32_t)nkc;
+      const int64_t n0 = (nt0 + i) * BN;
+      u64 acc[2][4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[a][j] = 0ull;
+      for (int kc = 0; kc < nkc; ++kc) {
+        const uint32_t pos = base + (both == 2 ? 2u * kc + g : (uint32_t)kc);
+        const int st = pos % T3_NST;
+        rk_mbar_wait(full + st, (pos / T3_NST) & 1u);
+        const float* eb = ring + (size_t)st * T3_STAGE_FLOATS + tx * T3_ESTR;
+        const int klim = (W - kc * BK) < BK ? (W - kc * BK) : BK;   // multiple of 4
+        const float* qa0 = qrow0 + 2 * kc * BK;
+        const float* qa1 = qrow1 + 2 * kc * BK;
+#pragma unroll 2
+        for (int k = 0; k < klim; k += 4) {
+          ulonglong2 a[2][2], a2[2][2];
+          float4 e[4];
+          a[0][0] = *reinterpret_cast<const ulonglong2*>(qa0 + 2 * k);
+          a[0][1] = *reinterpret_cast<const ulonglong2*>(qa0 + 2 * k + 4);
+          a[1][0] = *reinterpret_cast<const ulonglong2*>(qa1 + 2 * k);
+          a[1][1] = *reinterpret_cast<const ulonglong2*>(qa1 + 2 * k + 4);
+          if (HEAD) {
+            a2[0][0] = *reinterpret_cast<const ulonglong2*>(qa0 + part2 + 2 * k);
+            a2[0][1] = *reinterpret_cast<const ulonglong2*>(qa0 + part2 + 2 * k + 4);
+            a2[1][0] = *reinterpret_cast<const ulonglong2*>(qa1 + part2 + 2 * k);
+            a2[1][1] = *reinterpret_cast<const ulonglong2*>(qa1 + part2 + 2 * k + 4);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) e[j] = *reinterpret_cast<const float4*>(eb + 16 * j * T3_ESTR + k);
+#pragma unroll
+          for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              u64 c = acc[p][j];
+              c = seq_term3<OP>(c, e[j].x, a[p][0].x, a2[p][0].x);
+              c = seq_term3<OP>(c, e[j].y, a[p][0].y, a2[p][0].y);
+              c = seq_term3<OP>(c, e[j].z, a[p][1].x, a2[p][1].x);
+              c = seq_term3<OP>(c, e[j].w, a[p][1].y, a2[p][1].y);
+              acc[p][j] = c;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) rk_mbar_arrive(empty + st);   // this warp is done with the stage
+      }
+#pragma unroll
+      for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t nn = n0 + tx + 16 * j;
+          const float s_lo = seq_finish<OP>(lo2(acc[p][j]), fin), s_hi = seq_finish<OP>(hi2(acc[p][j]), fin);
+          cnt[2 * p] += (nn < n_rows && s_lo > tq[2 * p]) ? 1 : 0;
+          cnt[2 * p + 1] += (nn < n_rows && s_hi > tq[2 * p + 1]) ? 1 : 0;
+        }
+    }
+    // the 16 tx lanes of one ty live in one half-warp: butterfly inside 16 lanes, then one integer atomic per query and group
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int c = cnt[i];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      const int64_t q = q0 + ty + 16 * (i >> 1) + 32 * (i & 1);
+      if (tx == 0 && q < Q && c != 0) atomicAdd(counts + q, c);
+    }
+    run_base += (uint32_t)n * (uint32_t)nkc;
+    ta = tb;
+  }
+}
+
 // launches the tile kernel of one op: the packed kernel on a grid of exactly SMs x resident CTAs, or (ops with a multiply or sinf; KGEB_RANK_TILE=scalar
 // for A/B runs -- identical integer counts either way) the round-1 scalar kernel on its 2-D grid
 template <int OP>
@@ -548,6 +778,19 @@ int launch_tile(kgeb_ctx* ctx, dim3 grid2d, int64_t items, cudaStream_t st, cons
   static const bool scalar_tile = [] { const char* e = getenv("KGEB_RANK_TILE"); return e && !strcmp(e, "scalar"); }();
   if constexpr (op_packed<OP>()) {
     if (!scalar_tile) {
+      static const bool no_t3 = [] { const char* e = getenv("KGEB_RANK_TILE"); return e && !strcmp(e, "packed2"); }();
+      const size_t sm3 = t3_smem_bytes(ctx->we, op_two_part<OP>());
+      if (!no_t3 && sm3 <= 227 * 1024) {   // the resident query tile fits: decoupled producer / consumer kernel, one CTA per SM
+        static size_t set3 = 0;
+        if (set3 < sm3) {
+          KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_rank_tile3<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+          set3 = sm3;
+        }
+        int64_t g3 = ctx->num_sms;
+        if (g3 > items) g3 = items;
+        k_rank_tile3<OP><<<(unsigned)g3, T3_THREADS, sm3, st>>>(E_shard, n_rows, ctx->ldE, ctx->we, qvec, qw, tscore, Q, fin, counts);
+        return KGEB_OK;
+      }
       auto kern = k_rank_tile2<OP>;
       const size_t tsm = ((size_t)(op_two_part<OP>() ? 4 : 2) * BQ * BKP + 2 * (BN / 2) * BPP) * sizeof(float);
       static int occ = 0;   // resident CTAs per SM of this instantiation, asked once
