@@ -9,6 +9,7 @@
 // and add (__fmul_rn/__fadd_rn, no FMA), so the three code paths below give bit-identical scores for the same (q,c)
 // and oracle.kge_oracle.seqk_scores reproduces them on the CPU.  The filter is applied as a correction pass:
 // counts -= #{c in filter(q) : score(q,c) > target}.
+#include <cuda.h>   // CUtensorMap (types only: the encoder is reached through cudaGetDriverEntryPoint, no libcuda at link time)
 #include <stdlib.h>
 #include "rank_common.cuh"
 
@@ -552,9 +553,13 @@ __global__ void __launch_bounds__(256, 2) k_rank_tile2(const float* __restrict__
 // the decoupled packed tile kernel: same arithmetic as k_rank_tile2, no load instruction and no CTA-wide barrier in the compute
 // warps' steady state.  profiles/r02_rank_tile2_summary.md: the k-loop of k_rank_tile2 alone reaches ~90 % of the fp32 add pipe, staging
 // the next chunk through registers costs 14 % and the per-chunk barrier 7 %.  Here
-//   * one PRODUCER warp streams the candidate tiles: every k-chunk of a 64-row entity tile is 64 bulk async copies (cp.async.bulk, one
-//     128-byte piece of a row each, rows padded to 144 bytes in shared memory: conflict-free LDS.128) into a ring of NST stages that
-//     complete on mbarriers (full: transaction bytes; empty: one arrival per consumer warp);
+//   * ONE producer thread streams the candidate tiles by TMA: every k-chunk of a 64-row entity tile is one
+//     cp.async.bulk.tensor.2d (SASS UTMALDG) of a 32-float x 64-row box of the table's tensor map into a ring of NST 8 KB stages that
+//     complete on mbarriers (full: transaction bytes; empty: one arrival per consumer warp).  The box lands as dense 128-byte rows with
+//     the 128-byte swizzle (16-byte chunk c of row r sits at chunk c ^ (r & 7)), so the 8 rows a quarter warp reads with one LDS.128
+//     fall in 8 different bank groups; rows past the shard and k past the row width arrive as zeros (never counted / never read).
+//     (The first version issued one 128-byte cp.async.bulk per row: UBLKCP is a uniform instruction, a warp issues its lanes' copies one
+//     at a time, and a single producer warp could not keep up -- 3.36 ms; four producer warps: 1.81 ms.)
 //   * the 64-query tile is RESIDENT in shared memory for as long as the CTA's items stay in that query tile, stored pair-interleaved
 //     (row p = queries p and p + 32, (q_p[k], q_{p+32}[k]) adjacent), so the packed operand of FADD2 is now the QUERY pair and the candidate
 //     value is the scalar broadcast operand: d = e - q (|e - q| = |q - e| exactly), or (e + a) - a2 for the head side;
@@ -571,9 +576,9 @@ __device__ __forceinline__ void rk_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 __device__ __forceinline__ void rk_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rk_smem(bar)) : "memory");
 }
-__device__ __forceinline__ void rk_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rk_smem(dst)), "l"(src),
-               "r"(bytes), "r"(rk_smem(bar))
+__device__ __forceinline__ void rk_tma_2d(void* dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(rk_smem(dst)),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(rk_smem(bar))
                : "memory");
 }
 __device__ __forceinline__ void rk_mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -590,27 +595,24 @@ __device__ __forceinline__ void rk_mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-constexpr int T3_NST = 8;                       // ring stages (a stage = one k-chunk of one 64-row entity tile)
-constexpr int T3_ESTR = 36;                     // floats per candidate row in a stage: 32 + 4 (row stride = 4 banks mod 32)
-constexpr int T3_STAGE_FLOATS = BN * T3_ESTR;
-constexpr int T3_PW = 4;                        // producer warps: a bulk copy is a UNIFORM instruction (UBLKCP), a warp issues its lanes' copies one
-                                                // by one (ELECT + R2UR per copy, ~40 cycles each), so the 64 rows of a stage are spread over 4 warps
-constexpr int T3_THREADS = (16 + T3_PW) * 32;   // 2 consumer groups x 8 warps + the producer warps
+constexpr int T3_NST = 8;                       // ring stages (a stage = one k-chunk of one 64-row entity tile: a 32 x 64 fp32 box)
+constexpr int T3_STAGE_BYTES = BN * BK * 4;     // 8192: dense 128-byte rows, 128-byte swizzle (stage bases are 1024-byte aligned)
+constexpr int T3_THREADS = 17 * 32;             // 2 consumer groups x 8 warps + the producer warp (one thread of it issues the TMA copies)
 __host__ __device__ inline int t3_qstride(int W) { return 2 * W + ((2 * W) % 32 == 0 ? 8 : 0); }   // floats per pair row; adjacent rows in distinct banks
 inline size_t t3_smem_bytes(int W, bool head) {
-  return ((size_t)(head ? 2 : 1) * (BQ / 2) * t3_qstride(W) + (size_t)T3_NST * T3_STAGE_FLOATS) * sizeof(float) + 2 * T3_NST * sizeof(uint64_t);
+  return (size_t)T3_NST * T3_STAGE_BYTES + (size_t)(head ? 2 : 1) * (BQ / 2) * t3_qstride(W) * sizeof(float) + 2 * T3_NST * sizeof(uint64_t) + 1024;
 }
 
 template <int OP>
-__global__ void __launch_bounds__(T3_THREADS, 1) k_rank_tile3(const float* __restrict__ Es, int64_t n_rows, int ldE, int W,
+__global__ void __launch_bounds__(T3_THREADS, 1) k_rank_tile3(const __grid_constant__ CUtensorMap tmapE, int64_t n_rows, int W,
                                                               const float* __restrict__ qvec, int qw, const float* __restrict__ tscore,
                                                               int64_t Q, SeqFin fin, int32_t* counts) {
   constexpr bool HEAD = op_two_part<OP>();
-  extern __shared__ __align__(16) float tile_smem[];
+  extern __shared__ __align__(1024) unsigned char tile3_smem[];
+  unsigned char* ring = tile3_smem + ((1024u - (rk_smem(tile3_smem) & 1023u)) & 1023u);   // [NST][64 rows][128 B], 1024-byte aligned (swizzle atom)
   const int QS = t3_qstride(W);
-  float* q2 = tile_smem;                                              // [part][32 pairs][QS]
-  float* ring = tile_smem + (HEAD ? 2 : 1) * (BQ / 2) * QS;           // [NST][64 rows][ESTR]
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + T3_NST * T3_STAGE_FLOATS);
+  float* q2 = reinterpret_cast<float*>(ring + T3_NST * T3_STAGE_BYTES);          // [part][32 pairs][QS]
+  uint64_t* full = reinterpret_cast<uint64_t*>(q2 + (HEAD ? 2 : 1) * (BQ / 2) * QS);
   uint64_t* empty = full + T3_NST;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ntiles = (n_rows + BN - 1) / BN;
@@ -618,7 +620,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_rank_tile3(const float* __res
   const int64_t t0 = items * blockIdx.x / gridDim.x, t1 = items * (blockIdx.x + 1) / gridDim.x;
   const int nkc = (W + BK - 1) / BK;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < T3_NST; ++i) { rk_mbar_init(full + i, T3_PW); rk_mbar_init(empty + i, 8); }
+    for (int i = 0; i < T3_NST; ++i) { rk_mbar_init(full + i, 1); rk_mbar_init(empty + i, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -627,10 +629,10 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_rank_tile3(const float* __res
   // (2 P, 2 P + 1) -> (group 0, group 1) and the chunks enter the ring in the order (P, kc, group)
   const int64_t qt_first = t0 / ntiles;
 
-  if (warp >= 16) {
-    // ---------------- producers: warp pw streams rows [16 pw, 16 pw + 16) of every stage ----------------
-    const int pw = warp - 16;
-    const int r = 16 * pw + (lane & 15);
+  if (warp == 16) {
+    // ---------------- producer: one thread, one TMA box per stage ----------------
+    if (lane != 0) return;
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapE) : "memory");
     uint32_t pos = 0;
     int64_t ta = t0;
     for (int64_t qt = qt_first; ta < t1; ++qt) {
@@ -640,19 +642,11 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_rank_tile3(const float* __res
       for (int i = 0; i < n; i += 2) {
         const int both = i + 1 < n ? 2 : 1;
         for (int kc = 0; kc < nkc; ++kc) {
-          const uint32_t bytes = (uint32_t)((W - kc * BK) < BK ? (W - kc * BK) : BK) * 4u;
           for (int g = 0; g < both; ++g, ++pos) {
             const int st = pos % T3_NST;
-            const int64_t n0 = (nt0 + i + g) * BN;
-            const int64_t left = n_rows - n0 - 16 * pw;               // rows of this warp's slice that exist
-            const uint32_t nv = left >= 16 ? 16u : (left > 0 ? (uint32_t)left : 0u);
-            if (lane == 0) {
-              if (pos >= T3_NST) rk_mbar_wait(empty + st, ((pos / T3_NST) - 1) & 1u);
-              rk_mbar_expect_tx(full + st, nv * bytes);               // one arrival per producer warp (also when its slice is empty)
-            }
-            __syncwarp();
-            float* dst = ring + (size_t)st * T3_STAGE_FLOATS;
-            if (lane < 16 && (uint32_t)(lane & 15) < nv) rk_bulk_g2s(dst + r * T3_ESTR, Es + (n0 + r) * (int64_t)ldE + kc * BK, bytes, full + st);
+            if (pos >= T3_NST) rk_mbar_wait(empty + st, ((pos / T3_NST) - 1) & 1u);
+            rk_mbar_expect_tx(full + st, T3_STAGE_BYTES);     // the whole box is written: out-of-range elements arrive as zeros
+            rk_tma_2d(ring + (size_t)st * T3_STAGE_BYTES, &tmapE, kc * BK, (int)((nt0 + i + g) * BN), full + st);
           }
         }
       }
@@ -664,6 +658,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_rank_tile3(const float* __res
   // ---------------- consumers ----------------
   const int g = warp >> 3;                       // consumer group
   const int tg = threadIdx.x & 255, tx = tg & 15, ty = tg >> 4;
+  const int x7 = tx & 7;                         // swizzle key of this thread's candidate rows (tx + 16 j: the low three bits are tx's)
   uint32_t run_base = 0;
   int64_t ta = t0;
   for (int64_t qt = qt_first; ta < t1; ++qt) {
@@ -711,7 +706,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_rank_tile3(const float* __res
         const uint32_t pos = base + (both == 2 ? 2u * kc + g : (uint32_t)kc);
         const int st = pos % T3_NST;
         rk_mbar_wait(full + st, (pos / T3_NST) & 1u);
-        const float* eb = ring + (size_t)st * T3_STAGE_FLOATS + tx * T3_ESTR;
+        const unsigned char* eb = ring + (size_t)st * T3_STAGE_BYTES + tx * 128;
         const int klim = (W - kc * BK) < BK ? (W - kc * BK) : BK;   // multiple of 4
         const float* qa0 = qrow0 + 2 * kc * BK;
         const float* qa1 = qrow1 + 2 * kc * BK;
@@ -729,8 +724,9 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_rank_tile3(const float* __res
             a2[1][0] = *reinterpret_cast<const ulonglong2*>(qa1 + part2 + 2 * k);
             a2[1][1] = *reinterpret_cast<const ulonglong2*>(qa1 + part2 + 2 * k + 4);
           }
+          const int sw = (((k >> 2) ^ x7) << 4);   // byte offset of k-chunk k/4 inside the swizzled 128-byte row
 #pragma unroll
-          for (int j = 0; j < 4; ++j) e[j] = *reinterpret_cast<const float4*>(eb + 16 * j * T3_ESTR + k);
+          for (int j = 0; j < 4; ++j) e[j] = *reinterpret_cast<const float4*>(eb + 16 * j * 128 + sw);
 #pragma unroll
           for (int p = 0; p < 2; ++p)
 #pragma unroll
@@ -770,6 +766,26 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_rank_tile3(const float* __res
   }
 }
 
+// tensor map of a row shard for k_rank_tile3: fp32 [n_rows][W] with row stride ldE, 32 x 64 boxes, 128-byte swizzle, zeros out of range.
+// cuTensorMapEncodeTiled is a host-side encoder (no GPU work); it is looked up once through the runtime.
+typedef CUresult (*kgeb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+bool t3_tensor_map(const float* E_shard, int64_t n_rows, int W, int ldE, CUtensorMap* out) {
+  static kgeb_encode_tiled_fn enc = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+    return (kgeb_encode_tiled_fn)fn;
+  }();
+  if (!enc || n_rows <= 0 || n_rows > 0x7fffffffLL) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)n_rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ldE * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN}, estr[2] = {1, 1};
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(E_shard), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // launches the tile kernel of one op: the packed kernel on a grid of exactly SMs x resident CTAs, or (ops with a multiply or sinf; KGEB_RANK_TILE=scalar
 // for A/B runs -- identical integer counts either way) the round-1 scalar kernel on its 2-D grid
 template <int OP>
@@ -780,7 +796,9 @@ int launch_tile(kgeb_ctx* ctx, dim3 grid2d, int64_t items, cudaStream_t st, cons
     if (!scalar_tile) {
       static const bool no_t3 = [] { const char* e = getenv("KGEB_RANK_TILE"); return e && !strcmp(e, "packed2"); }();
       const size_t sm3 = t3_smem_bytes(ctx->we, op_two_part<OP>());
-      if (!no_t3 && sm3 <= 227 * 1024) {   // the resident query tile fits: decoupled producer / consumer kernel, one CTA per SM
+      CUtensorMap tmapE;
+      if (!no_t3 && sm3 <= 227 * 1024 && t3_tensor_map(E_shard, n_rows, ctx->we, ctx->ldE, &tmapE)) {
+        // the resident query tile fits: decoupled TMA producer / packed consumer kernel, one CTA per SM
         static size_t set3 = 0;
         if (set3 < sm3) {
           KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_rank_tile3<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
@@ -788,7 +806,7 @@ int launch_tile(kgeb_ctx* ctx, dim3 grid2d, int64_t items, cudaStream_t st, cons
         }
         int64_t g3 = ctx->num_sms;
         if (g3 > items) g3 = items;
-        k_rank_tile3<OP><<<(unsigned)g3, T3_THREADS, sm3, st>>>(E_shard, n_rows, ctx->ldE, ctx->we, qvec, qw, tscore, Q, fin, counts);
+        k_rank_tile3<OP><<<(unsigned)g3, T3_THREADS, sm3, st>>>(tmapE, n_rows, ctx->we, qvec, qw, tscore, Q, fin, counts);
         return KGEB_OK;
       }
       auto kern = k_rank_tile2<OP>;
