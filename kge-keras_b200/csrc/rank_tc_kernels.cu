@@ -69,6 +69,7 @@ namespace {
 constexpr int TC_BM = 128;       // queries per tile  (UMMA M, one TMEM lane per query)
 constexpr int TC_BN = 256;       // entities per tile (UMMA N, one TMEM column per entity)
 constexpr int TC_STAGES = 4;
+constexpr int TC2_STAGES = 6;    // CTA-pair kernel: a stage holds 16 KB of queries + 16 KB (half) of the entity tile
 constexpr int TC_CH_TOTAL = 8;   // 16-byte k-chunks per stage summed over planes (8 / planes chunks of K each)
 constexpr int TC_THREADS = 384;
 constexpr uint32_t TC_A_STAGE = TC_BM * TC_CH_TOTAL * 16;  // 16 KB
@@ -122,6 +123,38 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
 // arrives on `bar` once every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+// ---- CTA-pair forms (cta_group::2: one MMA spans two SMs; the leader CTA of the pair issues it) ----
+__device__ __forceinline__ uint32_t tc_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void tc_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void tc_mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(tc_smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair once every MMA issued so far has completed
+__device__ __forceinline__ void tc_commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns of TMEM -> 32 registers per thread (thread = lane = query row).  The load is
 // asynchronous: the registers are valid only after tc_ld_wait, which names them as in/out operands so that no use can
@@ -212,6 +245,7 @@ struct TcArgs {
   uint32_t wl_cap;
   int64_t Q, row_offset, n_rows;
   int nkc, planes, qtiles, ntiles, side, qgroup;
+  int qtiles_real;               // CTA-pair kernel: `qtiles` counts PAIRS of query tiles, this is the number of 128-query tiles
   uint32_t idesc;
   float c_norm, c_wnorm, c_abs, t_slack;   // band = c_norm ||q|| ||e|| + c_wnorm Aq Ae + c_abs (||q|| / 2^a + ||e|| / 2^b)
   // TransE-L2 (see the header comment): per-query arrays [6][qpad] = ||q'||^2, A_lo, A_hi, sqrt(A_hi), D_t bound, c_q
@@ -234,18 +268,31 @@ __device__ __forceinline__ void tc_item(const TcArgs& a, int64_t it, int64_t& ti
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
+// NCTA = 1: one CTA per tile (128 queries x 256 entities).  NCTA = 2 (cta_group::2, clusters of two CTAs on the two SMs of a TPC): one MMA
+// covers 256 queries x 256 entities -- each CTA stages its own 128-query tile and only HALF of the entity tile (128 rows), so the
+// shared-memory fill and fetch per MMA flop drop by a third; the accumulator rows of a CTA's queries live in its own TMEM and its
+// epilogue is unchanged.  The leader (cluster rank 0) issues the MMAs once its own stage and the peer's have landed (the peer forwards
+// its "stage full" with a remote mbarrier arrive), and its commits arrive on the stage / accumulator barriers of BOTH CTAs (multicast).
+template <int NCTA>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a) {
+  constexpr int STAGES = NCTA == 2 ? TC2_STAGES : TC_STAGES;
+  constexpr uint32_t BROWS = TC_BN / NCTA;                  // entity rows of a stage held by this CTA
+  constexpr uint32_t B_STAGE = TC_B_STAGE / NCTA;
+  const uint32_t crank = NCTA == 2 ? tc_cluster_rank() : 0u;
+  const bool leader = crank == 0;
+  const int64_t unit = NCTA == 2 ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x, nunits = NCTA == 2 ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
   extern __shared__ unsigned char tc_smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* smA = smem;
-  unsigned char* smB = smem + TC_STAGES * TC_A_STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * (TC_A_STAGE + TC_B_STAGE));
-  uint64_t* full = bars;                     // [TC_STAGES]  copies landed
-  uint64_t* empty = bars + TC_STAGES;        // [TC_STAGES]  MMAs that read the stage completed
-  uint64_t* acc_full = bars + 2 * TC_STAGES; // [2]          accumulator ready for the epilogue
-  uint64_t* acc_empty = acc_full + 2;        // [2]          accumulator drained by all 8 epilogue warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  uint2* wbuf_all = reinterpret_cast<uint2*>(smem + TC_STAGES * (TC_A_STAGE + TC_B_STAGE) + 256);
+  unsigned char* smB = smem + STAGES * TC_A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (TC_A_STAGE + B_STAGE));
+  uint64_t* full = bars;                     // [STAGES]  copies landed (this CTA's)
+  uint64_t* empty = bars + STAGES;           // [STAGES]  MMAs that read the stage completed
+  uint64_t* acc_full = bars + 2 * STAGES;    // [2]       accumulator ready for the epilogue
+  uint64_t* acc_empty = acc_full + 2;        // [2]       accumulator drained by all 8 epilogue warps (of both CTAs: the leader's copy counts)
+  uint64_t* pfull = acc_empty + 2;           // [STAGES]  CTA pair, leader's copy: the PEER's copies of the stage landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull + STAGES);
+  uint2* wbuf_all = reinterpret_cast<uint2*>(smem + STAGES * (TC_A_STAGE + B_STAGE) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int planes = a.planes;
@@ -255,16 +302,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
 
   if (threadIdx.x == 0) {
     if (blockIdx.x == 0) a.wl_hdr[1] = a.wl_cap;
-    for (int i = 0; i < TC_STAGES; ++i) { tc_mbar_init(full + i, 1); tc_mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { tc_mbar_init(acc_full + i, 1); tc_mbar_init(acc_empty + i, 8); }
+    for (int i = 0; i < STAGES; ++i) { tc_mbar_init(full + i, 1); tc_mbar_init(empty + i, 1); tc_mbar_init(pfull + i, 1); }
+    for (int i = 0; i < 2; ++i) { tc_mbar_init(acc_full + i, 1); tc_mbar_init(acc_empty + i, 8 * NCTA); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (NCTA == 2) {   // the same warp of both CTAs, the same slot address
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) tc_cluster_sync(); else __syncthreads();   // pair: the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -273,29 +325,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       const size_t a_tile_bytes = (size_t)a.nkc * planes * TC_BM * 16, b_tile_bytes = (size_t)a.nkc * planes * TC_BN * 16;
-      for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+      for (int64_t it = unit; it < items; it += nunits) {
         int64_t tile, qt;
         tc_item(a, it, tile, qt);
+        if (NCTA == 2) {   // this CTA's query tile of the pair; an odd last pair re-reads the last tile (its epilogue rows are all q >= Q)
+          qt = 2 * qt + crank;
+          if (qt >= a.qtiles_real) qt = a.qtiles_real - 1;
+        }
         const unsigned char* srcA = a.packedQ + (size_t)qt * a_tile_bytes;
         const unsigned char* srcB = a.packedE + (size_t)tile * b_tile_bytes;
         for (int s = 0; s < nstage; ++s) {
           const int c0 = s * ch_per_stage;
           const int nch = (a.nkc - c0 < ch_per_stage ? a.nkc - c0 : ch_per_stage) * planes;  // 16-byte chunk columns
           tc_mbar_wait(empty + stage, phase ^ 1u);
-          const uint32_t ab = (uint32_t)nch * TC_BM * 16, bb = (uint32_t)nch * TC_BN * 16;
+          const uint32_t ab = (uint32_t)nch * TC_BM * 16, bb = (uint32_t)nch * BROWS * 16;
           tc_mbar_expect_tx(full + stage, ab + bb);
           tc_bulk_g2s(smA + stage * TC_A_STAGE, srcA + (size_t)c0 * planes * TC_BM * 16, ab, full + stage);
-          tc_bulk_g2s(smB + stage * TC_B_STAGE, srcB + (size_t)c0 * planes * TC_BN * 16, bb, full + stage);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+          if (NCTA == 1) {
+            tc_bulk_g2s(smB + stage * B_STAGE, srcB + (size_t)c0 * planes * TC_BN * 16, bb, full + stage);
+          } else {         // this CTA's 128 of the 256 rows of every chunk column: 2 KB pieces, 4 KB apart in the packed image
+            for (int j = 0; j < nch; ++j)
+              tc_bulk_g2s(smB + stage * B_STAGE + (size_t)j * BROWS * 16, srcB + ((size_t)c0 * planes + j) * TC_BN * 16 + (size_t)crank * BROWS * 16,
+                          BROWS * 16, full + stage);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: one thread =====
-    if (lane == 0) {
+    if (NCTA == 2 && !leader) {
+      // ===== peer CTA: forward "my copies of the stage landed" to the leader's MMA issuer =====
+      if (lane == 0) {
+        uint32_t stage = 0, phase = 0;
+        for (int64_t it = unit; it < items; it += nunits)
+          for (int s = 0; s < nstage; ++s) {
+            tc_mbar_wait(full + stage, phase);
+            tc_mbar_arrive_remote(pfull + stage, 0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+      }
+    } else if (lane == 0) {
+      // ===== MMA issuer: one thread (of the leader CTA in a pair) =====
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      const uint32_t lboA = (uint32_t)planes * TC_BM * 16, lboB = (uint32_t)planes * TC_BN * 16;
-      for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+      const uint32_t lboA = (uint32_t)planes * TC_BM * 16, lboB = (uint32_t)planes * BROWS * 16;
+      const uint32_t idesc = NCTA == 2 ? (a.idesc & ~(0x1Fu << 24)) | ((uint32_t)((TC_BM * 2) >> 4) << 24) : a.idesc;   // M = 256 across the pair
+      for (int64_t it = unit; it < items; it += nunits) {
         tc_mbar_wait(acc_empty + acc, acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * TC_BN;
@@ -311,24 +385,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
             const int c0 = (s + h) * ch_per_stage;
             const int nk16 = (a.nkc - c0 < ch_per_stage ? a.nkc - c0 : ch_per_stage) >> 1;  // K=16 steps in this stage
             tc_mbar_wait(full + stage, phase);
+            if (NCTA == 2) tc_mbar_wait(pfull + stage, phase);
             tc_fence_after();
-            const uint32_t sa = tc_smem_u32(smA + stage * TC_A_STAGE), sb = tc_smem_u32(smB + stage * TC_B_STAGE);
+            const uint32_t sa = tc_smem_u32(smA + stage * TC_A_STAGE), sb = tc_smem_u32(smB + stage * B_STAGE);
             for (int j = 0; j < nk16; ++j) {
               // chunk column (2j, plane p) starts at (2j*planes + p) * rows * 16 bytes
-              const uint32_t a0 = sa + (uint32_t)(2 * j * planes) * TC_BM * 16, b0 = sb + (uint32_t)(2 * j * planes) * TC_BN * 16;
-              tc_mma_bf16(tmem_d, tc_desc(a0, lboA, 128), tc_desc(b0, lboB, 128), a.idesc, accumulate);  // qh . eh
-              accumulate = 1;
-              if (planes == 2) {
-                tc_mma_bf16(tmem_d, tc_desc(a0, lboA, 128), tc_desc(b0 + TC_BN * 16, lboB, 128), a.idesc, 1);  // qh . el
-                tc_mma_bf16(tmem_d, tc_desc(a0 + TC_BM * 16, lboA, 128), tc_desc(b0, lboB, 128), a.idesc, 1);  // ql . eh
+              const uint32_t a0 = sa + (uint32_t)(2 * j * planes) * TC_BM * 16, b0 = sb + (uint32_t)(2 * j * planes) * BROWS * 16;
+              if (NCTA == 2) {
+                tc_mma_bf16_2cta(tmem_d, tc_desc(a0, lboA, 128), tc_desc(b0, lboB, 128), idesc, accumulate);  // qh . eh
+                if (planes == 2) {
+                  tc_mma_bf16_2cta(tmem_d, tc_desc(a0, lboA, 128), tc_desc(b0 + BROWS * 16, lboB, 128), idesc, 1);  // qh . el
+                  tc_mma_bf16_2cta(tmem_d, tc_desc(a0 + TC_BM * 16, lboA, 128), tc_desc(b0, lboB, 128), idesc, 1);  // ql . eh
+                }
+              } else {
+                tc_mma_bf16(tmem_d, tc_desc(a0, lboA, 128), tc_desc(b0, lboB, 128), idesc, accumulate);  // qh . eh
+                if (planes == 2) {
+                  tc_mma_bf16(tmem_d, tc_desc(a0, lboA, 128), tc_desc(b0 + BROWS * 16, lboB, 128), idesc, 1);  // qh . el
+                  tc_mma_bf16(tmem_d, tc_desc(a0 + TC_BM * 16, lboA, 128), tc_desc(b0, lboB, 128), idesc, 1);  // ql . eh
+                }
               }
+              accumulate = 1;
             }
             st_idx[nin++] = stage;
-            if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-          for (int h = 0; h < nin; ++h) tc_commit(empty + st_idx[h]);  // the stages may be overwritten once these MMAs have read them
+          for (int h = 0; h < nin; ++h) {   // the stages may be overwritten once these MMAs have read them
+            if (NCTA == 2) tc_commit_2cta(empty + st_idx[h]); else tc_commit(empty + st_idx[h]);
+          }
         }
-        tc_commit(acc_full + acc);
+        if (NCTA == 2) tc_commit_2cta(acc_full + acc); else tc_commit(acc_full + acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -361,9 +446,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
       wcnt = 0;
     };
 
-    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+    for (int64_t it = unit; it < items; it += nunits) {
       int64_t tile, qt;
       tc_item(a, it, tile, qt);
+      if (NCTA == 2) qt = 2 * qt + crank;   // past the last tile for the second CTA of an odd last pair: every q >= Q below
       const int64_t q = qt * TC_BM + lq * 32 + lane;
       const bool qok = q < a.Q;
       const float t = qok ? __ldg(a.tscore + q) : 0.f;
@@ -468,7 +554,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
       // every TMEM read of this accumulator has completed: hand it back to the MMA issuer before the last chunk
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc_mbar_arrive(acc_empty + acc);
+      if (lane == 0) { if (NCTA == 2 && !leader) tc_mbar_arrive_remote(acc_empty + acc, 0); else tc_mbar_arrive(acc_empty + acc); }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       process(rB, 96);
       if (qok && cnt0 != 0) atomicAdd(a.counts + q, cnt0);
@@ -476,10 +562,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc(TcArgs a) {
     if (wcnt != 0) flush();
   }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) tc_cluster_sync(); else __syncthreads();   // pair: nothing of either CTA is still in flight towards the other
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (NCTA == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -1183,15 +1270,34 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
   }
   static bool attr_done = false;  // per process; the attribute is per function, setting it again is harmless
   if (!attr_done) {
-    KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_rank_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_rank_tc_t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_rank_tc_t<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
     KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_rank_tc_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM_BYTES));
     attr_done = true;
   }
   const int64_t items = qt * nt;
   const int grid = (int)(items < ctx->num_sms ? items : ctx->num_sms);
+  // KGEB_TC_2CTA=1: CTA pairs (cta_group::2), one MMA over 256 queries x 256 entities, half of the entity tile staged per CTA
+  static const bool pair = [] { const char* e = getenv("KGEB_TC_2CTA"); return e && e[0] == '1'; }();
+  a.qtiles_real = (int)qt;
   KGEB_TIME_BEGIN(ctx, KGEB_TIMED_RANK_TC, st);
   if (ts) k_rank_tc_ts<<<grid, TC_THREADS, TS_SMEM_BYTES, st>>>(a);
-  else k_rank_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
+  else if (pair) {
+    const int64_t qpairs = (qt + 1) / 2;
+    a.qtiles = (int)qpairs;
+    if (a.qgroup > qpairs) a.qgroup = (int)qpairs;
+    const int64_t units = qpairs * nt, max_pairs = ctx->num_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * (units < max_pairs ? units : max_pairs)));
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    KGEB_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, k_rank_tc_t<2>, a));
+  } else k_rank_tc_t<1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
   KGEB_TIME_END(ctx, KGEB_TIMED_RANK_TC, st);
   KGEB_LAUNCH_OK(ctx);
   KGEB_TIME_BEGIN(ctx, KGEB_TIMED_RANK_REFINE, st);

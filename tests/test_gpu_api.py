@@ -329,8 +329,10 @@ def test_grad_rows_export_is_the_indexed_slices_of_the_backward(N):
     a.E[ids.long(), :d] -= 0.1 * rows
     a.Rel[rid.long(), :d] -= 0.1 * rrows
     b.train_step(pos, None, opt_kind=abi.SGD, lr=0.1, **kw)
-    np.testing.assert_array_equal(a.get_tables()[0], b.get_tables()[0])
-    np.testing.assert_array_equal(a.get_tables()[1], b.get_tables()[1])
+    # a and b are two runs of the backward: their fp32 reductions into a row may be applied in a different order (last-bit differences
+    # on rows with many references; seen once in ~10 runs at N = 37), so the two steps agree to rounding, not bit for bit
+    np.testing.assert_allclose(a.get_tables()[0], b.get_tables()[0], rtol=2e-6, atol=1e-8)
+    np.testing.assert_allclose(a.get_tables()[1], b.get_tables()[1], rtol=2e-6, atol=1e-8)
 
 
 def test_device_generator_draws_negatives_below_the_splits_entity_count():

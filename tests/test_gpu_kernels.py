@@ -294,10 +294,11 @@ def test_rank_counts_dyadic_exact_with_ties(kind, side):
 @pytest.mark.parametrize("side", ["tail", "head"])
 @pytest.mark.parametrize("gamma", [12.0, 0.0])
 def test_rank_tile_flat_work_list(side, gamma):
-    """The packed TransE-L1 tile kernel cuts ONE list of (query tile, entity tile) items into equal ranges over SMs x resident CTAs:
-    with 11 x 101 items on <= 296 CTAs every CTA owns several items, ranges start and end inside a query tile and cross into the next
-    one (counts flushed, target scores reloaded, the chunk pipeline running across the boundary); ragged last tiles on both axes and a
-    ragged last k-chunk (52 = 32 + 20).  Integer counts equal the oracle's sequential-k fp32 ranks."""
+    """The packed TransE-L1 tile kernels cut ONE list of (query tile, entity tile) items into equal ranges over the CTAs (148 for the
+    TMA-fed kernel, <= 296 for the register-staged one): with 11 x 101 items every CTA owns several, ranges start and end inside a query
+    tile and cross into the next one (counts flushed, target scores and the resident query tile reloaded, the stage ring running across
+    the boundary, odd and even numbers of items per run for the two consumer groups); ragged last tiles on both axes (TMA zero fill) and
+    a ragged last k-chunk (52 = 32 + 20).  Integer counts equal the oracle's sequential-k fp32 ranks."""
     kind, N, R, d, Q = ko.TRANSE_L1, 6400 + 17, 5, 52, 640 + 5
     eng, E, Rm = make_engine(kind, N, R, d, seed=77, gamma=gamma)
     rng = np.random.default_rng(78)
@@ -316,16 +317,31 @@ def test_rank_tile_flat_work_list(side, gamma):
     np.testing.assert_array_equal(acc, counts)
 
 
-def test_scalar_tile_kernel_variant_in_child_process():
-    """KGEB_RANK_TILE=scalar (read once per process) keeps the round-1 scalar tile kernel for A/B runs: the TransE-L1 rank tests pass on it too."""
+@pytest.mark.parametrize("side", ["tail", "head"])
+def test_rank_tile_wide_rows(side):
+    """d = 320: the tail side's resident query tile still fits the TMA-fed kernel (k_rank_tile3), the head side's two-part tile does not
+    and runs on k_rank_tile2 -- both give the oracle's integers."""
+    kind, N, R, d, Q = ko.TRANSE_L1, 1000 + 3, 4, 320, 130
+    eng, E, Rm = make_engine(kind, N, R, d, seed=79)
+    tri = rand_triples(np.random.default_rng(80), Q, N, R)
+    counts = eng.rank_counts(tri, 0 if side == "tail" else 1).cpu().numpy()
+    sc = ko.seqk_scores(kind, ko.query_vectors(kind, E, Rm, tri, side), E, side, 12.0)
+    tgt = tri[:, 2] if side == "tail" else tri[:, 0]
+    np.testing.assert_array_equal(counts, (sc > sc[np.arange(Q), tgt][:, None]).sum(axis=1).astype(np.int32))
+
+
+@pytest.mark.parametrize("variant", ["scalar", "packed2"])
+def test_tile_kernel_variants_in_child_process(variant):
+    """KGEB_RANK_TILE (read once per process) selects the round-1 scalar tile kernel ("scalar") or the register-staged packed kernel
+    ("packed2") instead of the TMA-fed one for A/B runs: the TransE-L1 rank tests pass on each of them too."""
     import os
     import subprocess
     import sys
-    if os.environ.get("KGEB_RANK_TILE") == "scalar":
+    if os.environ.get("KGEB_RANK_TILE"):
         pytest.skip("already inside the child")
-    env = dict(os.environ, KGEB_RANK_TILE="scalar")
+    env = dict(os.environ, KGEB_RANK_TILE=variant)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
-                        "rank_tile_flat_work_list or rank_shards_sum or (rank_counts and not HOLE)"], env=env, capture_output=True, text=True, timeout=600)
+                        "rank_tile_flat_work_list or rank_tile_wide or rank_shards_sum or (rank_counts and not HOLE)"], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "passed" in r.stdout
 
