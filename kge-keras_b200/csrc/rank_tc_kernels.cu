@@ -56,6 +56,7 @@
 // expect -- no-swizzle K-major core matrices, [tile][k-chunk][plane][row][8 x bf16] -- so one pipeline stage is two
 // contiguous bulk async copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier; no tensor map is needed.
 // Roles: warp 0 = copy producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator, warps 4-11 = epilogue.
+#include <cuda.h>   // CUtensorMap (types only; the encoder comes through cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -148,6 +149,18 @@ __device__ __forceinline__ void tc_mma_bf16_2cta(uint32_t tmem_d, uint64_t adesc
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 2-D TMA box into THIS CTA's shared memory whose transaction bytes complete on the barrier at the same offset in the LEADER CTA
+// (cp.async.bulk.tensor ... .cta_group::2: the one copy form whose destination and barrier may sit in different CTAs of the pair)
+__device__ __forceinline__ void tc_tma_2d_pair(void* dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rb;\n\t"
+      "mapa.shared::cluster.u32 rb, %4, 0;\n\t"
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [rb];\n\t"
+      "}" ::"r"(tc_smem_u32(dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(tc_smem_u32(bar))
       : "memory");
 }
 // arrives on the barrier at this offset in BOTH CTAs of the pair once every MMA issued so far has completed
@@ -271,10 +284,12 @@ __device__ __forceinline__ void tc_item(const TcArgs& a, int64_t it, int64_t& ti
 // NCTA = 1: one CTA per tile (128 queries x 256 entities).  NCTA = 2 (cta_group::2, clusters of two CTAs on the two SMs of a TPC): one MMA
 // covers 256 queries x 256 entities -- each CTA stages its own 128-query tile and only HALF of the entity tile (128 rows), so the
 // shared-memory fill and fetch per MMA flop drop by a third; the accumulator rows of a CTA's queries live in its own TMEM and its
-// epilogue is unchanged.  The leader (cluster rank 0) issues the MMAs once its own stage and the peer's have landed (the peer forwards
-// its "stage full" with a remote mbarrier arrive), and its commits arrive on the stage / accumulator barriers of BOTH CTAs (multicast).
+// epilogue is unchanged.  Both CTAs fetch their stage with TMA boxes of the packed images (tensor maps over 64-bit words: one box = the 8
+// chunk columns of a stage) whose bytes complete on the LEADER's barrier (.cta_group::2); the leader (cluster rank 0) issues the MMAs and
+// its commits arrive on the stage / accumulator barriers of BOTH CTAs (multicast).  (First version: 1-D bulk copies completing on each
+// CTA's own barrier, the peer forwarding "stage full" with a remote arrive -- 18.5 ms against 17.0 ms for one CTA per tile on C5 bf16.)
 template <int NCTA>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmE) {
   constexpr int STAGES = NCTA == 2 ? TC2_STAGES : TC_STAGES;
   constexpr uint32_t BROWS = TC_BN / NCTA;                  // entity rows of a stage held by this CTA
   constexpr uint32_t B_STAGE = TC_B_STAGE / NCTA;
@@ -286,12 +301,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a) {
   unsigned char* smA = smem;
   unsigned char* smB = smem + STAGES * TC_A_STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (TC_A_STAGE + B_STAGE));
-  uint64_t* full = bars;                     // [STAGES]  copies landed (this CTA's)
+  uint64_t* full = bars;                     // [STAGES]  copies landed (pair: the leader's copy collects both CTAs' bytes)
   uint64_t* empty = bars + STAGES;           // [STAGES]  MMAs that read the stage completed
   uint64_t* acc_full = bars + 2 * STAGES;    // [2]       accumulator ready for the epilogue
   uint64_t* acc_empty = acc_full + 2;        // [2]       accumulator drained by all 8 epilogue warps (of both CTAs: the leader's copy counts)
-  uint64_t* pfull = acc_empty + 2;           // [STAGES]  CTA pair, leader's copy: the PEER's copies of the stage landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull + STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   uint2* wbuf_all = reinterpret_cast<uint2*>(smem + STAGES * (TC_A_STAGE + B_STAGE) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -302,7 +316,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a) {
 
   if (threadIdx.x == 0) {
     if (blockIdx.x == 0) a.wl_hdr[1] = a.wl_cap;
-    for (int i = 0; i < STAGES; ++i) { tc_mbar_init(full + i, 1); tc_mbar_init(empty + i, 1); tc_mbar_init(pfull + i, 1); }
+    for (int i = 0; i < STAGES; ++i) { tc_mbar_init(full + i, 1); tc_mbar_init(empty + i, 1); }
     for (int i = 0; i < 2; ++i) { tc_mbar_init(acc_full + i, 1); tc_mbar_init(acc_empty + i, 8 * NCTA); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -338,15 +352,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a) {
           const int c0 = s * ch_per_stage;
           const int nch = (a.nkc - c0 < ch_per_stage ? a.nkc - c0 : ch_per_stage) * planes;  // 16-byte chunk columns
           tc_mbar_wait(empty + stage, phase ^ 1u);
-          const uint32_t ab = (uint32_t)nch * TC_BM * 16, bb = (uint32_t)nch * BROWS * 16;
-          tc_mbar_expect_tx(full + stage, ab + bb);
-          tc_bulk_g2s(smA + stage * TC_A_STAGE, srcA + (size_t)c0 * planes * TC_BM * 16, ab, full + stage);
           if (NCTA == 1) {
+            const uint32_t ab = (uint32_t)nch * TC_BM * 16, bb = (uint32_t)nch * BROWS * 16;
+            tc_mbar_expect_tx(full + stage, ab + bb);
+            tc_bulk_g2s(smA + stage * TC_A_STAGE, srcA + (size_t)c0 * planes * TC_BM * 16, ab, full + stage);
             tc_bulk_g2s(smB + stage * B_STAGE, srcB + (size_t)c0 * planes * TC_BN * 16, bb, full + stage);
-          } else {         // this CTA's 128 of the 256 rows of every chunk column: 2 KB pieces, 4 KB apart in the packed image
-            for (int j = 0; j < nch; ++j)
-              tc_bulk_g2s(smB + stage * B_STAGE + (size_t)j * BROWS * 16, srcB + ((size_t)c0 * planes + j) * TC_BN * 16 + (size_t)crank * BROWS * 16,
-                          BROWS * 16, full + stage);
+          } else {
+            // whole boxes always (a short last stage reads on into the next tile's columns or the zero fill past the image)
+            if (leader) tc_mbar_expect_tx(full + stage, 2u * (TC_A_STAGE + B_STAGE));
+            const int colq = (int)(qt * a.nkc + c0) * planes, cole = (int)(tile * a.nkc + c0) * planes;
+            tc_tma_2d_pair(smA + stage * TC_A_STAGE, &tmQ, 0, colq, full + stage);
+            tc_tma_2d_pair(smB + stage * B_STAGE, &tmE, (int)(crank * (BROWS * 2)), cole, full + stage);   // this CTA's 128 of the 256 rows (64-bit words)
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -354,16 +370,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a) {
     }
   } else if (warp == 1) {
     if (NCTA == 2 && !leader) {
-      // ===== peer CTA: forward "my copies of the stage landed" to the leader's MMA issuer =====
-      if (lane == 0) {
-        uint32_t stage = 0, phase = 0;
-        for (int64_t it = unit; it < items; it += nunits)
-          for (int s = 0; s < nstage; ++s) {
-            tc_mbar_wait(full + stage, phase);
-            tc_mbar_arrive_remote(pfull + stage, 0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-          }
-      }
+      // peer CTA: the leader issues the MMAs of the pair
     } else if (lane == 0) {
       // ===== MMA issuer: one thread (of the leader CTA in a pair) =====
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
@@ -385,7 +392,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a) {
             const int c0 = (s + h) * ch_per_stage;
             const int nk16 = (a.nkc - c0 < ch_per_stage ? a.nkc - c0 : ch_per_stage) >> 1;  // K=16 steps in this stage
             tc_mbar_wait(full + stage, phase);
-            if (NCTA == 2) tc_mbar_wait(pfull + stage, phase);
             tc_fence_after();
             const uint32_t sa = tc_smem_u32(smA + stage * TC_A_STAGE), sb = tc_smem_u32(smB + stage * B_STAGE);
             for (int j = 0; j < nk16; ++j) {
@@ -1091,6 +1097,27 @@ TcWsLayout tc_ws_layout(const kgeb_ctx* ctx, int64_t Q, int mode, int64_t workli
   return L;
 }
 
+// tensor map over a packed operand image seen as 64-bit words: one row per chunk column (tile_rows x 16 bytes), boxes of 128 rows'
+// worth of words (256) x the 8 chunk columns of a pipeline stage, no swizzle: the box lands as the [chunk column][128 rows][16 B]
+// image the UMMA descriptors read.  The encoder is host code, looked up once through the runtime.
+typedef CUresult (*tc_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+bool tc_image_map(const void* image, int tile_rows, int64_t columns, CUtensorMap* out) {
+  static tc_encode_tiled_fn enc = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+    return (tc_encode_tiled_fn)fn;
+  }();
+  if (!enc || columns <= 0 || columns > 0x7fffffffLL) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)tile_rows * 2, (cuuint64_t)columns};
+  const cuuint64_t strides[1] = {(cuuint64_t)tile_rows * 16};
+  const cuuint32_t box[2] = {256, (cuuint32_t)TC_CH_TOTAL}, estr[2] = {1, 1};
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(image), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace
 
 extern "C" int64_t kgeb_rank_tc_packed_bytes(const kgeb_ctx* ctx, int64_t n_rows, int mode) {
@@ -1268,6 +1295,8 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
     // V = ||e||^2 / 2 <= nmax^2 / 2 enters Z twice (the slots may straddle the last two blocks) and the split of W_e once
     a.l2_c_v = (float)(1.02 * (2.0 * 36.1 * u + 1.0 / 2147483648.0) * 0.5);
   }
+  CUtensorMap tmQ, tmE;
+  memset(&tmQ, 0, sizeof(tmQ)); memset(&tmE, 0, sizeof(tmE));
   static bool attr_done = false;  // per process; the attribute is per function, setting it again is harmless
   if (!attr_done) {
     KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_rank_tc_t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
@@ -1282,7 +1311,7 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
   a.qtiles_real = (int)qt;
   KGEB_TIME_BEGIN(ctx, KGEB_TIMED_RANK_TC, st);
   if (ts) k_rank_tc_ts<<<grid, TC_THREADS, TS_SMEM_BYTES, st>>>(a);
-  else if (pair) {
+  else if (pair && tc_image_map(packedQ, TC_BM, qt * nkc * planes, &tmQ) && tc_image_map(pe, TC_BN, nt * nkc * planes, &tmE)) {
     const int64_t qpairs = (qt + 1) / 2;
     a.qtiles = (int)qpairs;
     if (a.qgroup > qpairs) a.qgroup = (int)qpairs;
@@ -1296,8 +1325,8 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    KGEB_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, k_rank_tc_t<2>, a));
-  } else k_rank_tc_t<1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
+    KGEB_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, k_rank_tc_t<2>, a, tmQ, tmE));
+  } else k_rank_tc_t<1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, tmQ, tmE);
   KGEB_TIME_END(ctx, KGEB_TIMED_RANK_TC, st);
   KGEB_LAUNCH_OK(ctx);
   KGEB_TIME_BEGIN(ctx, KGEB_TIMED_RANK_REFINE, st);
