@@ -201,6 +201,18 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
       "@pu or.b32 %1, %1, %5;\n\t}"                                                                                       \
       : "+r"(CMSK), "+r"(UMSK)                                                                                            \
       : "r"(S), "f"(HI), "f"(LO), "n"(BIT))
+// approximate mode: no band, so one compare and one predicated OR per accumulator (a score equal to the target's is simply not counted,
+// as in the reference's strict >); half the epilogue's CUDA-core work -- which matters on a power-capped chip
+#define TC_CMP1(S, HI, CMSK, BIT) \
+  asm("{\n\t.reg .pred ph;\n\tsetp.gt.f32 ph, %1, %2;\n\t@ph or.b32 %0, %0, %3;\n\t}" : "+r"(CMSK) : "r"(S), "f"(HI), "n"(BIT))
+template <int J>
+__device__ __forceinline__ void tc_cmp32_one(const uint32_t (&r)[32], float hi, uint32_t& c0, uint32_t& c1) {
+  if constexpr (J < 32) {  // two independent mask chains
+    TC_CMP1(r[J], hi, c0, 1u << J);
+    TC_CMP1(r[J + 1], hi, c1, 1u << (J + 1));
+    tc_cmp32_one<J + 2>(r, hi, c0, c1);
+  }
+}
 template <int J>
 __device__ __forceinline__ void tc_cmp32(const uint32_t (&r)[32], float hi, float lo, uint32_t& c0, uint32_t& c1, uint32_t& m0, uint32_t& m1) {
   if constexpr (J < 32) {  // two independent mask chains
@@ -440,6 +452,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a, const __g
       if (degenerate) scQ = 1.f;
     }
     const float sc = scE * scQ;
+    const bool no_band = a.planes == 1 && !a.l2;   // approximate mode: hi == lo == the target score (warp-uniform)
 
     auto flush = [&]() {
       __syncwarp();
@@ -509,7 +522,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a, const __g
       // one 32-column chunk: counts, undecided mask, padding correction, append of the undecided pairs
       auto process = [&](uint32_t (&r)[32], int jc) {
         uint32_t k0 = 0, k1 = 0, m0 = 0, m1 = 0;
-        tc_cmp32<0>(r, hi, lo, k0, k1, m0, m1);
+        if (no_band) tc_cmp32_one<0>(r, hi, k0, k1); else tc_cmp32<0>(r, hi, lo, k0, k1, m0, m1);
         uint32_t cmask = k0 | k1, mask = m0 | m1;
         const int64_t c0 = n0 + jc;
         const int64_t left = a.n_rows - c0;                     // columns of this chunk that are real entities
