@@ -463,8 +463,23 @@ def sec_train_c2(args, rank, world, dev, barrier, max_over_ranks, timed_passes, 
     plan = eng.rank_plan(tri, ct, ch, row_range=ku.shard_rows(N, world, rank), mode="cuda").capture()
     ms, launches, kms = timed_passes(plan, eng, 3, 10)
     t_ms = max_over_ranks(float(np.sum(ms)))
+    # per-kernel time of the two tile launches (tail, head) from an un-captured pass with the sides serial; the L1 distance needs 2 (tail) /
+    # 3 (head) separately rounded fp32 adds per (query, entity, k): its roofline is the fp32 add pipe, SMs x 128 lanes x the maximum SM clock
+    plan2 = eng.rank_plan(tri, ct, ch, row_range=ku.shard_rows(N, world, rank), mode="cuda")
+    plan2.fork_sides = False
+    _, _, kms2 = timed_passes(plan2, eng, 2, 5)
+    tile_ms = kms2["tile"][0] / max(1, kms2["tile"][1])          # average of the tail and the head launch
+    rows = ku.shard_rows(N, world, rank)
+    lane_adds = 2.5 * nt * (rows[1] - rows[0]) * d                # per launch, averaged over the two sides (2 d and 3 d per pair)
+    add_peak = eng.num_sms * 128 * 1.965e9
     out["eval_c2"] = {"workload": w["name"] + ": filtered 1-N ranking, fp32 CUDA-core tile kernel", "value": rnd(10 * 2 * nt / (t_ms * 1e-3)), "unit": "queries/s",
-                      "queries_per_pass": 2 * nt, "ms_per_pass": rnd(t_ms / 10), "scaling": "strong", "cuda_graph": True}
+                      "queries_per_pass": 2 * nt, "ms_per_pass": rnd(t_ms / 10), "scaling": "strong", "cuda_graph": True,
+                      "sides_as_parallel_graph_branches": bool(plan.fork_sides),
+                      "roofline": {"bound": "fp32 add pipe", "kernel": "k_rank_tile3 (packed FADD2, TMA-fed; tail and head launches averaged)",
+                                   "kernel_ms": rnd(tile_ms), "achieved": rnd(lane_adds / (tile_ms * 1e-3) / 1e12), "peak": rnd(add_peak / 1e12),
+                                   "unit": "T lane-adds/s", "frac": rnd(lane_adds / (tile_ms * 1e-3) / add_peak),
+                                   "peak_source": "SMs x 128 fp32 lanes x clocks.max.sm (1965 MHz); FADD2 occupies the pipe two cycles, so the lane rate is the ceiling"}}
+    del plan2
     del plan, eng
     return out
 

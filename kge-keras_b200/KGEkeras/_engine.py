@@ -133,6 +133,11 @@ class Engine:
 
     # ---- bookkeeping --------------------------------------------------------------------------------------------
     @property
+    def num_sms(self):
+        """SM count of the context's device (kgeb_num_sms)."""
+        return int(self.lib.kgeb_num_sms(self.ctx))
+
+    @property
     def launches(self):
         return int(self.lib.kgeb_launch_count(self.ctx))
 
