@@ -201,18 +201,6 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
       "@pu or.b32 %1, %1, %5;\n\t}"                                                                                       \
       : "+r"(CMSK), "+r"(UMSK)                                                                                            \
       : "r"(S), "f"(HI), "f"(LO), "n"(BIT))
-// approximate mode: no band, so one compare and one predicated OR per accumulator (a score equal to the target's is simply not counted,
-// as in the reference's strict >); half the epilogue's CUDA-core work -- which matters on a power-capped chip
-#define TC_CMP1(S, HI, CMSK, BIT) \
-  asm("{\n\t.reg .pred ph;\n\tsetp.gt.f32 ph, %1, %2;\n\t@ph or.b32 %0, %0, %3;\n\t}" : "+r"(CMSK) : "r"(S), "f"(HI), "n"(BIT))
-template <int J>
-__device__ __forceinline__ void tc_cmp32_one(const uint32_t (&r)[32], float hi, uint32_t& c0, uint32_t& c1) {
-  if constexpr (J < 32) {  // two independent mask chains
-    TC_CMP1(r[J], hi, c0, 1u << J);
-    TC_CMP1(r[J + 1], hi, c1, 1u << (J + 1));
-    tc_cmp32_one<J + 2>(r, hi, c0, c1);
-  }
-}
 template <int J>
 __device__ __forceinline__ void tc_cmp32(const uint32_t (&r)[32], float hi, float lo, uint32_t& c0, uint32_t& c1, uint32_t& m0, uint32_t& m1) {
   if constexpr (J < 32) {  // two independent mask chains
@@ -293,6 +281,11 @@ __device__ __forceinline__ void tc_item(const TcArgs& a, int64_t it, int64_t& ti
   }
 }
 
+// the work unit (CTA, or CTA pair) and their number.  Read from blockIdx / gridDim at every use: hoisting them into 64-bit locals ahead of
+// the role split made ptxas drop the uniform datapath for the single-thread producer / MMA-issue loops (UIADD3 / ULOP3 / USHF 303 -> 11 in
+// SASS) and cost the approximate mode 8-18 % (measured A/B on one box)
+template <int NCTA> __device__ __forceinline__ unsigned tc_unit() { return NCTA == 2 ? blockIdx.x >> 1 : blockIdx.x; }
+template <int NCTA> __device__ __forceinline__ unsigned tc_units() { return NCTA == 2 ? gridDim.x >> 1 : gridDim.x; }
 // NCTA = 1: one CTA per tile (128 queries x 256 entities).  NCTA = 2 (cta_group::2, clusters of two CTAs on the two SMs of a TPC): one MMA
 // covers 256 queries x 256 entities -- each CTA stages its own 128-query tile and only HALF of the entity tile (128 rows), so the
 // shared-memory fill and fetch per MMA flop drop by a third; the accumulator rows of a CTA's queries live in its own TMEM and its
@@ -307,7 +300,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a, const __g
   constexpr uint32_t B_STAGE = TC_B_STAGE / NCTA;
   const uint32_t crank = NCTA == 2 ? tc_cluster_rank() : 0u;
   const bool leader = crank == 0;
-  const int64_t unit = NCTA == 2 ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x, nunits = NCTA == 2 ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
   extern __shared__ unsigned char tc_smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* smA = smem;
@@ -351,7 +343,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a, const __g
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       const size_t a_tile_bytes = (size_t)a.nkc * planes * TC_BM * 16, b_tile_bytes = (size_t)a.nkc * planes * TC_BN * 16;
-      for (int64_t it = unit; it < items; it += nunits) {
+      for (int64_t it = tc_unit<NCTA>(); it < items; it += tc_units<NCTA>()) {
         int64_t tile, qt;
         tc_item(a, it, tile, qt);
         if (NCTA == 2) {   // this CTA's query tile of the pair; an odd last pair re-reads the last tile (its epilogue rows are all q >= Q)
@@ -388,7 +380,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a, const __g
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       const uint32_t lboA = (uint32_t)planes * TC_BM * 16, lboB = (uint32_t)planes * BROWS * 16;
       const uint32_t idesc = NCTA == 2 ? (a.idesc & ~(0x1Fu << 24)) | ((uint32_t)((TC_BM * 2) >> 4) << 24) : a.idesc;   // M = 256 across the pair
-      for (int64_t it = unit; it < items; it += nunits) {
+      for (int64_t it = tc_unit<NCTA>(); it < items; it += tc_units<NCTA>()) {
         tc_mbar_wait(acc_empty + acc, acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * TC_BN;
@@ -452,7 +444,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a, const __g
       if (degenerate) scQ = 1.f;
     }
     const float sc = scE * scQ;
-    const bool no_band = a.planes == 1 && !a.l2;   // approximate mode: hi == lo == the target score (warp-uniform)
 
     auto flush = [&]() {
       __syncwarp();
@@ -465,7 +456,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a, const __g
       wcnt = 0;
     };
 
-    for (int64_t it = unit; it < items; it += nunits) {
+    for (int64_t it = tc_unit<NCTA>(); it < items; it += tc_units<NCTA>()) {
       int64_t tile, qt;
       tc_item(a, it, tile, qt);
       if (NCTA == 2) qt = 2 * qt + crank;   // past the last tile for the second CTA of an odd last pair: every q >= Q below
@@ -522,7 +513,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a, const __g
       // one 32-column chunk: counts, undecided mask, padding correction, append of the undecided pairs
       auto process = [&](uint32_t (&r)[32], int jc) {
         uint32_t k0 = 0, k1 = 0, m0 = 0, m1 = 0;
-        if (no_band) tc_cmp32_one<0>(r, hi, k0, k1); else tc_cmp32<0>(r, hi, lo, k0, k1, m0, m1);
+        tc_cmp32<0>(r, hi, lo, k0, k1, m0, m1);
         uint32_t cmask = k0 | k1, mask = m0 | m1;
         const int64_t c0 = n0 + jc;
         const int64_t left = a.n_rows - c0;                     // columns of this chunk that are real entities
