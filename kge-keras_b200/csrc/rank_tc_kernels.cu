@@ -216,6 +216,9 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
          (1ull << 46);
 }
+// the same descriptor as a variable low word (start address and LBO fields) and the constant high word (SBO = 128 bytes, version bit 46)
+__device__ __forceinline__ uint32_t tc_desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); }
+__device__ __forceinline__ uint64_t tc_desc64(uint32_t lo) { return ((uint64_t)(((128u >> 4) & 0x3FFFu) | (1u << 14)) << 32) | lo; }
 // instruction descriptor: fp32 accumulate, A and B both K-major, N = 256, M = 128; operand format fp16 (0) or bf16 (1)
 constexpr uint32_t TC_IDESC_F16 = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 constexpr uint32_t TC_IDESC_BF16 = TC_IDESC_F16 | (1u << 7) | (1u << 10);
@@ -336,7 +339,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a, const __g
   tc_fence_before();
   if (NCTA == 2) tc_cluster_sync(); else __syncthreads();   // pair: the peer's barriers exist before anything arrives on them
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // The CTA owns all 512 columns of its SM's tensor memory, so the allocation starts at column 0, lane 0.  Checked once; the MMA issuer then
+  // addresses the accumulators with constants -- a base loaded from shared memory is a VECTOR register to the compiler, and every MMA paid
+  // an ELECT / R2UR.BROADCAST / BRA.U.ANY round trip to move it to the uniform datapath (SASS of the previous build).
+  if (*tmem_slot != 0u) __trap();
+  constexpr uint32_t tmem_base = 0u;
 
   if (warp == 0) {
     // ===== producer: one thread streams the packed operand stages =====
@@ -397,21 +404,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a, const __g
             const int nk16 = (a.nkc - c0 < ch_per_stage ? a.nkc - c0 : ch_per_stage) >> 1;  // K=16 steps in this stage
             tc_mbar_wait(full + stage, phase);
             tc_fence_after();
-            const uint32_t sa = tc_smem_u32(smA + stage * TC_A_STAGE), sb = tc_smem_u32(smB + stage * B_STAGE);
-            for (int j = 0; j < nk16; ++j) {
-              // chunk column (2j, plane p) starts at (2j*planes + p) * rows * 16 bytes
-              const uint32_t a0 = sa + (uint32_t)(2 * j * planes) * TC_BM * 16, b0 = sb + (uint32_t)(2 * j * planes) * BROWS * 16;
+            // descriptors of the stage's first K=16 step; the next step / the other plane is a constant added to the 14-bit start-address
+            // field (shared memory ends below 2^18 bytes, so the field never carries): one uniform add per operand per MMA instead of
+            // rebuilding the descriptor
+            // (kept as 32-bit low words + one constant high word so that the arithmetic stays on the uniform datapath)
+            uint32_t la = tc_desc_lo(tc_smem_u32(smA + stage * TC_A_STAGE), lboA), lb = tc_desc_lo(tc_smem_u32(smB + stage * B_STAGE), lboB);
+            const uint32_t stepA = (uint32_t)(2 * planes) * TC_BM, stepB = (uint32_t)(2 * planes) * BROWS;   // (2 chunk columns x planes x rows x 16 B) >> 4
+            for (int j = 0; j < nk16; ++j, la += stepA, lb += stepB) {
               if (NCTA == 2) {
-                tc_mma_bf16_2cta(tmem_d, tc_desc(a0, lboA, 128), tc_desc(b0, lboB, 128), idesc, accumulate);  // qh . eh
+                tc_mma_bf16_2cta(tmem_d, tc_desc64(la), tc_desc64(lb), idesc, accumulate);  // qh . eh
                 if (planes == 2) {
-                  tc_mma_bf16_2cta(tmem_d, tc_desc(a0, lboA, 128), tc_desc(b0 + BROWS * 16, lboB, 128), idesc, 1);  // qh . el
-                  tc_mma_bf16_2cta(tmem_d, tc_desc(a0 + TC_BM * 16, lboA, 128), tc_desc(b0, lboB, 128), idesc, 1);  // ql . eh
+                  tc_mma_bf16_2cta(tmem_d, tc_desc64(la), tc_desc64(lb + BROWS), idesc, 1);  // qh . el  (the other plane: rows x 16 B further)
+                  tc_mma_bf16_2cta(tmem_d, tc_desc64(la + TC_BM), tc_desc64(lb), idesc, 1);  // ql . eh
                 }
               } else {
-                tc_mma_bf16(tmem_d, tc_desc(a0, lboA, 128), tc_desc(b0, lboB, 128), idesc, accumulate);  // qh . eh
+                tc_mma_bf16(tmem_d, tc_desc64(la), tc_desc64(lb), idesc, accumulate);  // qh . eh
                 if (planes == 2) {
-                  tc_mma_bf16(tmem_d, tc_desc(a0, lboA, 128), tc_desc(b0 + BROWS * 16, lboB, 128), idesc, 1);  // qh . el
-                  tc_mma_bf16(tmem_d, tc_desc(a0 + TC_BM * 16, lboA, 128), tc_desc(b0, lboB, 128), idesc, 1);  // ql . eh
+                  tc_mma_bf16(tmem_d, tc_desc64(la), tc_desc64(lb + BROWS), idesc, 1);  // qh . el
+                  tc_mma_bf16(tmem_d, tc_desc64(la + TC_BM), tc_desc64(lb), idesc, 1);  // ql . eh
                 }
               }
               accumulate = 1;
@@ -1310,12 +1320,13 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
   }
   const int64_t items = qt * nt;
   const int grid = (int)(items < ctx->num_sms ? items : ctx->num_sms);
-  // KGEB_TC_2CTA=1: CTA pairs (cta_group::2), one MMA over 256 queries x 256 entities, half of the entity tile staged per CTA
-  static const bool pair = [] { const char* e = getenv("KGEB_TC_2CTA"); return e && e[0] == '1'; }();
+  // CTA pairs (cta_group::2: one MMA over 256 queries x 256 entities, half of the entity tile staged per CTA) are the default: 4-5 % faster than
+  // one CTA per tile in both modes on C5 (profiles/r02_tc_pair.md); KGEB_TC_2CTA=0 selects one CTA per tile
+  static const bool pair = [] { const char* e = getenv("KGEB_TC_2CTA"); return !(e && e[0] == '0'); }();
   a.qtiles_real = (int)qt;
   KGEB_TIME_BEGIN(ctx, KGEB_TIMED_RANK_TC, st);
   if (ts) k_rank_tc_ts<<<grid, TC_THREADS, TS_SMEM_BYTES, st>>>(a);
-  else if (pair && tc_image_map(packedQ, TC_BM, qt * nkc * planes, &tmQ) && tc_image_map(pe, TC_BN, nt * nkc * planes, &tmE)) {
+  else if (pair && ctx->num_sms >= 2 && tc_image_map(packedQ, TC_BM, qt * nkc * planes, &tmQ) && tc_image_map(pe, TC_BN, nt * nkc * planes, &tmE)) {
     const int64_t qpairs = (qt + 1) / 2;
     a.qtiles = (int)qpairs;
     if (a.qgroup > qpairs) a.qgroup = (int)qpairs;

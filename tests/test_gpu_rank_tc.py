@@ -353,3 +353,18 @@ def test_tc_ts_variant_passes_the_approximate_mode_tests():
                        text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "passed" in r.stdout
+
+
+def test_one_cta_per_tile_variant_in_child_process():
+    """CTA pairs (k_rank_tc_t<2>, cta_group::2) are the default since round 2; KGEB_TC_2CTA=0 (read once per process) keeps one CTA per tile
+    (k_rank_tc_t<1>): every test of this file passes on it too."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("KGEB_TC_2CTA") == "0" or os.environ.get("KGEB_TC_TS") == "1":
+        pytest.skip("already inside a child")
+    env = dict(os.environ, KGEB_TC_2CTA="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k", "not variant"], env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "passed" in r.stdout
