@@ -110,16 +110,38 @@ __device__ __forceinline__ void tc_bulk_g2s(void* dst, const void* src, uint32_t
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by ONE thread for the CTA
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// The forms below are executed by ALL lanes of the (converged) issuing warp; elect.sync picks the one lane that performs the operation --
+// always the same lane for the full mask, so the commits track the MMAs.  In a branch of the shape `if (lane == 0)` ptxas wraps every
+// UTCHMMA in an ELECT / PLOP3 / BRA.U.ANY loop (one trip per distinct active thread), which cost more than the instruction itself.
+__device__ __forceinline__ void tc_mma_bf16_w(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
-      ".reg .pred p;\n\t"
+      ".reg .pred p, pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2cta_w(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_w(uint64_t* bar) {
+  asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2cta_w(uint64_t* bar) {
+  asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(tc_smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
 }
 // arrives on `bar` once every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -141,16 +163,6 @@ __device__ __forceinline__ void tc_mbar_arrive_remote(uint64_t* bar, uint32_t ra
       "r"(rank)
       : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // 2-D TMA box into THIS CTA's shared memory whose transaction bytes complete on the barrier at the same offset in the LEADER CTA
 // (cp.async.bulk.tensor ... .cta_group::2: the one copy form whose destination and barrier may sit in different CTAs of the pair)
 __device__ __forceinline__ void tc_tma_2d_pair(void* dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
@@ -162,12 +174,6 @@ __device__ __forceinline__ void tc_tma_2d_pair(void* dst, const CUtensorMap* tma
       "}" ::"r"(tc_smem_u32(dst)),
       "l"(tmap), "r"(c0), "r"(c1), "r"(tc_smem_u32(bar))
       : "memory");
-}
-// arrives on the barrier at this offset in BOTH CTAs of the pair once every MMA issued so far has completed
-__device__ __forceinline__ void tc_commit_2cta(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns of TMEM -> 32 registers per thread (thread = lane = query row).  The load is
 // asynchronous: the registers are valid only after tc_ld_wait, which names them as in/out operands so that no use can
@@ -382,8 +388,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a, const __g
   } else if (warp == 1) {
     if (NCTA == 2 && !leader) {
       // peer CTA: the leader issues the MMAs of the pair
-    } else if (lane == 0) {
-      // ===== MMA issuer: one thread (of the leader CTA in a pair) =====
+    } else {
+      // ===== MMA issuer: the whole warp runs the loop, one elected lane issues (of the leader CTA in a pair) =====
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       const uint32_t lboA = (uint32_t)planes * TC_BM * 16, lboB = (uint32_t)planes * BROWS * 16;
       const uint32_t idesc = NCTA == 2 ? (a.idesc & ~(0x1Fu << 24)) | ((uint32_t)((TC_BM * 2) >> 4) << 24) : a.idesc;   // M = 256 across the pair
@@ -412,16 +418,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a, const __g
             const uint32_t stepA = (uint32_t)(2 * planes) * TC_BM, stepB = (uint32_t)(2 * planes) * BROWS;   // (2 chunk columns x planes x rows x 16 B) >> 4
             for (int j = 0; j < nk16; ++j, la += stepA, lb += stepB) {
               if (NCTA == 2) {
-                tc_mma_bf16_2cta(tmem_d, tc_desc64(la), tc_desc64(lb), idesc, accumulate);  // qh . eh
+                tc_mma_bf16_2cta_w(tmem_d, tc_desc64(la), tc_desc64(lb), idesc, accumulate);  // qh . eh
                 if (planes == 2) {
-                  tc_mma_bf16_2cta(tmem_d, tc_desc64(la), tc_desc64(lb + BROWS), idesc, 1);  // qh . el  (the other plane: rows x 16 B further)
-                  tc_mma_bf16_2cta(tmem_d, tc_desc64(la + TC_BM), tc_desc64(lb), idesc, 1);  // ql . eh
+                  tc_mma_bf16_2cta_w(tmem_d, tc_desc64(la), tc_desc64(lb + BROWS), idesc, 1);  // qh . el  (the other plane: rows x 16 B further)
+                  tc_mma_bf16_2cta_w(tmem_d, tc_desc64(la + TC_BM), tc_desc64(lb), idesc, 1);  // ql . eh
                 }
               } else {
-                tc_mma_bf16(tmem_d, tc_desc64(la), tc_desc64(lb), idesc, accumulate);  // qh . eh
+                tc_mma_bf16_w(tmem_d, tc_desc64(la), tc_desc64(lb), idesc, accumulate);  // qh . eh
                 if (planes == 2) {
-                  tc_mma_bf16(tmem_d, tc_desc64(la), tc_desc64(lb + BROWS), idesc, 1);  // qh . el
-                  tc_mma_bf16(tmem_d, tc_desc64(la + TC_BM), tc_desc64(lb), idesc, 1);  // ql . eh
+                  tc_mma_bf16_w(tmem_d, tc_desc64(la), tc_desc64(lb + BROWS), idesc, 1);  // qh . el
+                  tc_mma_bf16_w(tmem_d, tc_desc64(la + TC_BM), tc_desc64(lb), idesc, 1);  // ql . eh
                 }
               }
               accumulate = 1;
@@ -430,10 +436,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rank_tc_t(TcArgs a, const __g
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
           for (int h = 0; h < nin; ++h) {   // the stages may be overwritten once these MMAs have read them
-            if (NCTA == 2) tc_commit_2cta(empty + st_idx[h]); else tc_commit(empty + st_idx[h]);
+            if (NCTA == 2) tc_commit_2cta_w(empty + st_idx[h]); else tc_commit_w(empty + st_idx[h]);
           }
         }
-        if (NCTA == 2) tc_commit_2cta(acc_full + acc); else tc_commit(acc_full + acc);
+        if (NCTA == 2) tc_commit_2cta_w(acc_full + acc); else tc_commit_w(acc_full + acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
