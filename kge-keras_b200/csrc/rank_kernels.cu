@@ -799,11 +799,8 @@ int launch_tile(kgeb_ctx* ctx, dim3 grid2d, int64_t items, cudaStream_t st, cons
       CUtensorMap tmapE;
       if (!no_t3 && sm3 <= 227 * 1024 && t3_tensor_map(E_shard, n_rows, ctx->we, ctx->ldE, &tmapE)) {
         // the resident query tile fits: decoupled TMA producer / packed consumer kernel, one CTA per SM
-        static size_t set3 = 0;
-        if (set3 < sm3) {
-          KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_rank_tile3<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
-          set3 = sm3;
-        }
+        // (the attribute is per device and per function; setting it on every launch costs ~1 us and stays correct with several devices in one process)
+        KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_rank_tile3<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
         int64_t g3 = ctx->num_sms;
         if (g3 > items) g3 = items;
         k_rank_tile3<OP><<<(unsigned)g3, T3_THREADS, sm3, st>>>(tmapE, n_rows, ctx->we, qvec, qw, tscore, Q, fin, counts);
@@ -811,9 +808,9 @@ int launch_tile(kgeb_ctx* ctx, dim3 grid2d, int64_t items, cudaStream_t st, cons
       }
       auto kern = k_rank_tile2<OP>;
       const size_t tsm = ((size_t)(op_two_part<OP>() ? 4 : 2) * BQ * BKP + 2 * (BN / 2) * BPP) * sizeof(float);
-      static int occ = 0;   // resident CTAs per SM of this instantiation, asked once
+      static int occ = 0;   // resident CTAs per SM of this instantiation, asked once (every device of a box is the same part)
+      KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
       if (occ == 0) {
-        KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
         int o = 0;
         KGEB_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, 256, tsm));
         occ = o < 1 ? 1 : o;

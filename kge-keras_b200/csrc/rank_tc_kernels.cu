@@ -1317,8 +1317,9 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
   }
   CUtensorMap tmQ, tmE;
   memset(&tmQ, 0, sizeof(tmQ)); memset(&tmE, 0, sizeof(tmE));
-  static bool attr_done = false;  // per process; the attribute is per function, setting it again is harmless
-  if (!attr_done) {
+  static bool attr_done_dev[64] = {};  // the attribute is per function AND per device (several devices in one process: each sets it once)
+  bool& attr_done = attr_done_dev[ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0];
+  if (!attr_done || ctx->device >= 64) {
     KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_rank_tc_t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
     KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_rank_tc_t<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
     KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_rank_tc_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM_BYTES));
