@@ -27,45 +27,77 @@ __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y
 
 // ping-pong between x and y: returns the buffer that holds the result.  INV uses conjugated twiddles (no 1/d scale).
 // Radix-4 Stockham autosort stages (each pass reads and writes every element once, so half the shared-memory traffic of
-// radix-2), plus one radix-2 stage when log2(d) is odd.  tw[k] = exp(-2 pi i k / d), k < d.
+// radix-2), plus one radix-2 stage when log2(d) is odd.  tw[k] = exp(-2 pi i k / d), k < d; behind it (tw + d) the compact tables of the
+// radix-4 stages: stage p keeps w_m[k] = exp(-2 pi i m k / (4 p)), m = 1..3, k < p, at tw[d + (p - 1) + (m - 1) p + k] -- the same values
+// the strided reads tw[(m k) << sh] returned, but consecutive in k (the strided reads cost 4-8 wavefronts each at p = 4 and 16).
+// Bank conflicts of the stores: only the p = 4 stage has them (a warp's 32 outputs of one store fall on 8 banks: 8 wavefronts instead
+// of 2), so that stage writes through the permutation hf_swz and the stage after it reads through it; every other stage is conflict free
+// with plain indices (ncu before: 43 % of the shared-memory wavefronts of these kernels were conflicts).
+__device__ __forceinline__ int hf_swz(int j) { return j ^ (((j >> 4) & 3) << 2); }
+
+// one radix-4 Stockham stage.  P > 0: compile-time p (masks, twiddle offsets and the store shape fold away); P == 0: p at run time.
+// RD / WR: read / write through hf_swz (the p = 16 stage reads what the p = 4 stage wrote).
+template <bool INV, int P, bool RD, bool WR>
+__device__ __forceinline__ void hf_stage4(const float2* __restrict__ x, float2* __restrict__ y, const float2* __restrict__ ctw, int d, int p_rt, int lane) {
+  const int p = P > 0 ? P : p_rt, t = d >> 2;
+  for (int i = lane; i < t; i += 32) {
+    const int k = i & (p - 1), j = ((i - k) << 2) + k;
+    float2 w1 = ctw[k], w2 = ctw[p + k], w3 = ctw[2 * p + k];
+    if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+    const float2 u0 = x[RD ? hf_swz(i) : i], u1 = cmul(x[RD ? hf_swz(i + t) : i + t], w1), u2 = cmul(x[RD ? hf_swz(i + 2 * t) : i + 2 * t], w2),
+                 u3 = cmul(x[RD ? hf_swz(i + 3 * t) : i + 3 * t], w3);
+    const float2 v0 = make_float2(u0.x + u2.x, u0.y + u2.y), v1 = make_float2(u0.x - u2.x, u0.y - u2.y);
+    const float2 v2 = make_float2(u1.x + u3.x, u1.y + u3.y);
+    const float2 df = make_float2(u1.x - u3.x, u1.y - u3.y);
+    const float2 v3 = INV ? make_float2(-df.y, df.x) : make_float2(df.y, -df.x);      // (+/-) i * (u1 - u3)
+    const float2 y0 = make_float2(v0.x + v2.x, v0.y + v2.y), y1 = make_float2(v1.x + v3.x, v1.y + v3.y);
+    const float2 y2 = make_float2(v0.x - v2.x, v0.y - v2.y), y3 = make_float2(v1.x - v3.x, v1.y - v3.y);
+    if (P == 1) {                                        // the four outputs are adjacent: two 128-bit stores
+      *reinterpret_cast<float4*>(y + j) = make_float4(y0.x, y0.y, y1.x, y1.y);
+      *reinterpret_cast<float4*>(y + j + 2) = make_float4(y2.x, y2.y, y3.x, y3.y);
+    } else if (WR) {
+      y[hf_swz(j)] = y0; y[hf_swz(j + p)] = y1; y[hf_swz(j + 2 * p)] = y2; y[hf_swz(j + 3 * p)] = y3;
+    } else {
+      y[j] = y0; y[j + p] = y1; y[j + 2 * p] = y2; y[j + 3 * p] = y3;
+    }
+  }
+}
+
+// widths 32 .. 1024 (the launchers check): the p = 1 and p = 4 stages always run and the p = 4 stage is never the last one
 template <bool INV>
 __device__ __forceinline__ float2* warp_fft(float2* x, float2* y, const float2* __restrict__ tw, int d, int logd, int lane) {
-  int p = 1, lp = 0;
-  for (; 4 * p <= d; p <<= 2, lp += 2) {
-    const int t = d >> 2, sh = logd - 2 - lp;          // twiddle index m * k * d / (4 p) = (m * k) << sh
+  const float2* ctw = tw + d;
+  float2* tmp;
+  __syncwarp();
+  hf_stage4<INV, 1, false, false>(x, y, ctw, d, 1, lane);
+  tmp = x; x = y; y = tmp;
+  __syncwarp();
+  hf_stage4<INV, 4, false, true>(x, y, ctw + 3, d, 4, lane);
+  tmp = x; x = y; y = tmp;
+  int p = 16, lp = 4;
+  if (64 <= d) {
     __syncwarp();
-    for (int i = lane; i < t; i += 32) {
-      const int k = i & (p - 1), j = ((i - k) << 2) + k;
-      float2 w1 = tw[k << sh], w2 = tw[(2 * k) << sh], w3 = tw[(3 * k) << sh];
-      if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
-      const float2 u0 = x[i], u1 = cmul(x[i + t], w1), u2 = cmul(x[i + 2 * t], w2), u3 = cmul(x[i + 3 * t], w3);
-      const float2 v0 = make_float2(u0.x + u2.x, u0.y + u2.y), v1 = make_float2(u0.x - u2.x, u0.y - u2.y);
-      const float2 v2 = make_float2(u1.x + u3.x, u1.y + u3.y);
-      const float2 df = make_float2(u1.x - u3.x, u1.y - u3.y);
-      const float2 v3 = INV ? make_float2(-df.y, df.x) : make_float2(df.y, -df.x);      // (+/-) i * (u1 - u3)
-      const float2 y0 = make_float2(v0.x + v2.x, v0.y + v2.y), y1 = make_float2(v1.x + v3.x, v1.y + v3.y);
-      const float2 y2 = make_float2(v0.x - v2.x, v0.y - v2.y), y3 = make_float2(v1.x - v3.x, v1.y - v3.y);
-      if (p == 1) {                                      // the four outputs are adjacent: two 128-bit stores
-        *reinterpret_cast<float4*>(y + j) = make_float4(y0.x, y0.y, y1.x, y1.y);
-        *reinterpret_cast<float4*>(y + j + 2) = make_float4(y2.x, y2.y, y3.x, y3.y);
-      } else {
-        y[j] = y0; y[j + p] = y1; y[j + 2 * p] = y2; y[j + 3 * p] = y3;
-      }
+    hf_stage4<INV, 16, true, false>(x, y, ctw + 15, d, 16, lane);
+    tmp = x; x = y; y = tmp;
+    for (p = 64, lp = 6; 4 * p <= d; p <<= 2, lp += 2) {
+      __syncwarp();
+      hf_stage4<INV, 0, false, false>(x, y, ctw + (p - 1), d, p, lane);
+      tmp = x; x = y; y = tmp;
     }
-    float2* tmp = x; x = y; y = tmp;
   }
   if (p < d) {                                           // log2(d) odd: one radix-2 stage with p = d / 2
     const int t = d >> 1, sh = logd - 1 - lp;
+    const bool rd_swz = p == 16;                         // d == 32: this stage reads what the p = 4 stage wrote
     __syncwarp();
     for (int i = lane; i < t; i += 32) {
       const int k = i & (p - 1), j = ((i - k) << 1) + k;
       float2 w = tw[k << sh];
       if (INV) w.y = -w.y;
-      const float2 u0 = x[i], u1 = cmul(x[i + t], w);
+      const float2 u0 = x[rd_swz ? hf_swz(i) : i], u1 = cmul(x[rd_swz ? hf_swz(i + t) : i + t], w);
       y[j] = make_float2(u0.x + u1.x, u0.y + u1.y);
       y[j + p] = make_float2(u0.x - u1.x, u0.y - u1.y);
     }
-    float2* tmp = x; x = y; y = tmp;
+    tmp = x; x = y; y = tmp;
   }
   __syncwarp();
   return x;
@@ -116,13 +148,20 @@ __device__ __forceinline__ void hf_split(const float2* Z, int f, int d, float2& 
 }
 
 __device__ __forceinline__ void hf_setup(const HoleFftArgs& a, float2* smem, float2*& tw, HfWarp& w) {
-  tw = smem;                                   // d twiddles exp(-2 pi i k / d), shared by the block (radix-4 stages index up to 3d/4)
+  tw = smem;                                   // d twiddles exp(-2 pi i k / d), shared by the block, then the compact radix-4 tables (< d entries)
   for (int k = threadIdx.x; k < a.d; k += blockDim.x) {
     float sn, cs;
     sincospif(-2.f * (float)k / (float)a.d, &sn, &cs);
     tw[k] = make_float2(cs, sn);
   }
-  float2* base = smem + a.d + (size_t)(threadIdx.x >> 5) * 4 * a.d;
+  for (int p = 1; 4 * p <= a.d; p <<= 2)        // w_m[k] = exp(-2 pi i m k / (4 p)): the argument is an exact fp32 ratio, as in tw[]
+    for (int e = threadIdx.x; e < 3 * p; e += blockDim.x) {
+      const int m = e / p + 1, k = e - (m - 1) * p;
+      float sn, cs;
+      sincospif(-2.f * (float)(m * k) / (float)(4 * p), &sn, &cs);
+      tw[a.d + (p - 1) + e] = make_float2(cs, sn);
+    }
+  float2* base = smem + 2 * a.d + (size_t)(threadIdx.x >> 5) * 4 * a.d;
   w.a = base; w.b = base + a.d; w.P = base + 2 * a.d; w.acc = base + 3 * a.d;
   __syncthreads();
 }
@@ -162,7 +201,7 @@ __global__ void __launch_bounds__(HF_WARPS * 32) k_hole_fft_fwd(HoleFftArgs a, c
 }
 
 template <bool DP>
-__global__ void __launch_bounds__(HF_WARPS * 32) k_hole_fft_bwd(HoleFftArgs a, const int32_t* __restrict__ idx, int64_t m, const float* __restrict__ dscore,
+__global__ void __launch_bounds__(HF_WARPS * 32, 6) k_hole_fft_bwd(HoleFftArgs a, const int32_t* __restrict__ idx, int64_t m, const float* __restrict__ dscore,
                                                                 float* gE, float* gR, uint8_t* tE, uint8_t* tR) {
   extern __shared__ __align__(16) float2 hf_smem[];
   float2* tw; HfWarp w;
@@ -245,7 +284,7 @@ struct HoleTrainArgs {
 };
 
 template <bool DP>
-__global__ void __launch_bounds__(HF_WARPS * 32) k_hole_fft_train(HoleFftArgs a, HoleTrainArgs t) {
+__global__ void __launch_bounds__(HF_WARPS * 32, 5) k_hole_fft_train(HoleFftArgs a, HoleTrainArgs t) {
   extern __shared__ __align__(16) float2 hf_smem[];
   float2* tw; HfWarp w;
   hf_setup(a, hf_smem, tw, w);
@@ -361,9 +400,14 @@ bool hf_args(const kgeb_ctx* ctx, const float* E, const float* R, HoleFftArgs* a
   a->stream = ctx->dp_stream;
   return true;
 }
-size_t hf_smem_bytes(int d) { return ((size_t)d + (size_t)HF_WARPS * 4 * d) * sizeof(float2); }
-int hf_grid(const kgeb_ctx* ctx, int64_t m, size_t smem) {
-  int per_sm = (int)((200u * 1024u) / smem);
+size_t hf_smem_bytes(int d) { return ((size_t)2 * d + (size_t)HF_WARPS * 4 * d) * sizeof(float2); }
+// grid = SMs x the blocks of THIS kernel that are really resident per SM (asked from the runtime: registers can bind before shared memory
+// does -- with 125 registers the fused kernel fits 4 blocks where the shared-memory budget alone says 5, and a grid of 5 per SM would run
+// a second wave a quarter full), each block a contiguous range of triples
+template <typename Kern>
+int hf_grid(const kgeb_ctx* ctx, Kern kern, int64_t m, size_t smem) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HF_WARPS * 32, smem) != cudaSuccess) per_sm = (int)((200u * 1024u) / smem);
   if (per_sm > 8) per_sm = 8;
   if (per_sm < 1) per_sm = 1;
   int64_t blocks = (int64_t)ctx->num_sms * per_sm;
@@ -379,13 +423,12 @@ int kgeb_internal_hole_fft_fwd(kgeb_ctx* ctx, const float* E, const float* R, co
   HoleFftArgs a;
   if (!hf_args(ctx, E, R, &a)) return KGEB_ERR_UNSUPPORTED;
   const size_t sm = hf_smem_bytes(a.d);
-  const int grid = hf_grid(ctx, m, sm);
   if (a.dp.thr) {
     KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_hole_fft_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_hole_fft_fwd<true><<<grid, HF_WARPS * 32, sm, st>>>(a, idx, m, scores);
+    k_hole_fft_fwd<true><<<hf_grid(ctx, k_hole_fft_fwd<true>, m, sm), HF_WARPS * 32, sm, st>>>(a, idx, m, scores);
   } else {
     KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_hole_fft_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_hole_fft_fwd<false><<<grid, HF_WARPS * 32, sm, st>>>(a, idx, m, scores);
+    k_hole_fft_fwd<false><<<hf_grid(ctx, k_hole_fft_fwd<false>, m, sm), HF_WARPS * 32, sm, st>>>(a, idx, m, scores);
   }
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
@@ -396,13 +439,12 @@ int kgeb_internal_hole_fft_bwd(kgeb_ctx* ctx, const float* E, const float* R, co
   HoleFftArgs a;
   if (!hf_args(ctx, E, R, &a) || !kgeb_aligned16(gE) || !kgeb_aligned16(gR)) return KGEB_ERR_UNSUPPORTED;
   const size_t sm = hf_smem_bytes(a.d);
-  const int grid = hf_grid(ctx, m, sm);
   if (a.dp.thr) {
     KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_hole_fft_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_hole_fft_bwd<true><<<grid, HF_WARPS * 32, sm, st>>>(a, idx, m, dscore, gE, gR, tE, tR);
+    k_hole_fft_bwd<true><<<hf_grid(ctx, k_hole_fft_bwd<true>, m, sm), HF_WARPS * 32, sm, st>>>(a, idx, m, dscore, gE, gR, tE, tR);
   } else {
     KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_hole_fft_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_hole_fft_bwd<false><<<grid, HF_WARPS * 32, sm, st>>>(a, idx, m, dscore, gE, gR, tE, tR);
+    k_hole_fft_bwd<false><<<hf_grid(ctx, k_hole_fft_bwd<false>, m, sm), HF_WARPS * 32, sm, st>>>(a, idx, m, dscore, gE, gR, tE, tR);
   }
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
@@ -419,13 +461,15 @@ int kgeb_internal_hole_fft_train(kgeb_ctx* ctx, const float* E, const float* R, 
   t.seed = seed; t.offset = offset; t.N = (uint32_t)ctx->N; t.loss = loss; t.pos_scores = pos_scores; t.neg_scores = neg_scores; t.neg_out = neg_out;
   t.gE = gE; t.gR = gR; t.tE = tE; t.tR = tR; t.partials = ctx->d_partials; t.ticket = ctx->d_ticket;
   const size_t sm = hf_smem_bytes(a.d);
-  int grid = hf_grid(ctx, B * (1 + (int64_t)K), sm);
-  if (grid > KGEB_MAX_PARTIAL_BLOCKS) grid = KGEB_MAX_PARTIAL_BLOCKS;
   if (a.dp.thr) {
     KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_hole_fft_train<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    int grid = hf_grid(ctx, k_hole_fft_train<true>, B * (1 + (int64_t)K), sm);
+    if (grid > KGEB_MAX_PARTIAL_BLOCKS) grid = KGEB_MAX_PARTIAL_BLOCKS;
     k_hole_fft_train<true><<<grid, HF_WARPS * 32, sm, st>>>(a, t);
   } else {
     KGEB_CUDA_OK(ctx, cudaFuncSetAttribute(k_hole_fft_train<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    int grid = hf_grid(ctx, k_hole_fft_train<false>, B * (1 + (int64_t)K), sm);
+    if (grid > KGEB_MAX_PARTIAL_BLOCKS) grid = KGEB_MAX_PARTIAL_BLOCKS;
     k_hole_fft_train<false><<<grid, HF_WARPS * 32, sm, st>>>(a, t);
   }
   KGEB_LAUNCH_OK(ctx);
