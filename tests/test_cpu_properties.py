@@ -127,3 +127,74 @@ def test_hole_fourier_identities_used_by_the_fft_kernels(logd, seed):
     np.testing.assert_allclose(g.real, c * ds[0], atol=1e-9 * (1 + np.abs(ds).max()))
     np.testing.assert_allclose(g.imag, c * do[0], atol=1e-9 * (1 + np.abs(do).max()))
     np.testing.assert_allclose(np.fft.ifft(c * np.conj(S) * O).real, c * dp[0], atol=1e-9 * (1 + np.abs(dp).max()))
+
+
+def _hf_swz(j):
+    return j ^ (((j >> 4) & 3) << 2)
+
+
+def _stockham_as_in_hole_fft_kernels(z, inverse=False):
+    """The stage loops of warp_fft (kge-keras_b200/csrc/hole_fft_kernels.cu) restated index for index: radix-4 Stockham autosort stages
+    with the per-stage compact twiddle tables w_m[k] = exp(-2 pi i m k / (4 p)), the p = 4 stage STORING through the bank permutation
+    hf_swz and the stage after it (radix-4 p = 16, or the radix-2 stage when d = 32) LOADING through it, one radix-2 stage for odd log2 d."""
+    d = len(z)
+    logd = d.bit_length() - 1
+    tw = np.exp(-2j * np.pi * np.arange(d) / d)
+    ctw = np.zeros(d, complex)
+    p = 1
+    while 4 * p <= d:
+        for e in range(3 * p):
+            m = e // p + 1
+            ctw[(p - 1) + e] = np.exp(-2j * np.pi * m * (e - (m - 1) * p) / (4 * p))
+        p <<= 2
+    x, y = np.array(z, complex), np.zeros(d, complex)
+    p, lp = 1, 0
+    while 4 * p <= d:
+        t, rd, wr = d >> 2, p == 16, p == 4
+        for i in range(t):
+            k = i & (p - 1)
+            j = ((i - k) << 2) + k
+            w = [ctw[p - 1 + m * p + k] for m in range(3)]
+            if inverse:
+                w = [np.conj(v) for v in w]
+            src = [i + m * t for m in range(4)]
+            if rd:
+                src = [_hf_swz(q) for q in src]
+            u0, u1, u2, u3 = x[src[0]], x[src[1]] * w[0], x[src[2]] * w[1], x[src[3]] * w[2]
+            v0, v1, v2, df = u0 + u2, u0 - u2, u1 + u3, u1 - u3
+            v3 = 1j * df if inverse else -1j * df
+            for m, val in enumerate((v0 + v2, v1 + v3, v0 - v2, v1 - v3)):
+                y[_hf_swz(j + m * p) if wr else j + m * p] = val
+        x, y = y, x
+        p, lp = p << 2, lp + 2
+    if p < d:
+        t, sh, rd = d >> 1, logd - 1 - lp, p == 16
+        for i in range(t):
+            k = i & (p - 1)
+            j = ((i - k) << 1) + k
+            w = np.conj(tw[k << sh]) if inverse else tw[k << sh]
+            a, b = (_hf_swz(i), _hf_swz(i + t)) if rd else (i, i + t)
+            y[j], y[j + p] = x[a] + x[b] * w, x[a] - x[b] * w
+        x, y = y, x
+    return x
+
+
+@pytest.mark.parametrize("d", [32, 64, 128, 256, 512, 1024])
+def test_hole_fft_stage_indexing_with_the_bank_permutation(d):
+    """The index maps of the conflict-free FFT stages (compact twiddle tables, hf_swz between the p = 4 and the following stage) give the
+    DFT for every supported width, forward and inverse; hf_swz is a bijection of every aligned group of 64 indices that keeps the 16-element
+    groups a warp reads in one wavefront intact."""
+    rng = np.random.default_rng(d)
+    z = rng.normal(size=d) + 1j * rng.normal(size=d)
+    assert np.abs(_stockham_as_in_hole_fft_kernels(z) - np.fft.fft(z)).max() < 1e-11
+    assert np.abs(_stockham_as_in_hole_fft_kernels(z, True) - np.fft.ifft(z) * d).max() < 1e-11
+    idx = np.arange(d)
+    img = np.array([_hf_swz(int(j)) for j in idx])
+    assert sorted(img) == list(idx) and np.all(img >> 6 == idx >> 6) and np.all(img >> 4 == idx >> 4)
+    # the store pattern of the p = 4 stage: one store instruction = 32 lanes writing j = 16 a + b + 4 m (a = lane >> 2, b = lane & 3);
+    # through hf_swz the 32 addresses cover every 8-byte bank slot exactly twice (two wavefronts: the minimum for 256 bytes)
+    for m in range(4):
+        slots = [_hf_swz(16 * (lane >> 2) + (lane & 3) + 4 * m) % 16 for lane in range(32)]
+        assert sorted(slots) == sorted(list(range(16)) * 2)
+        plain = [(16 * (lane >> 2) + (lane & 3) + 4 * m) % 16 for lane in range(32)]
+        assert len(set(plain)) == 4          # without it: four slots, eight lanes each
