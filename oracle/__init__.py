@@ -9,11 +9,16 @@ checker (or as the timed CPU baseline), never as the thing shipped.  The product
 (`kge-keras_b200/`) never imports `oracle` and fails loudly without its CUDA library.
 
 Parity pinning status: the reference (`/root/reference`, TensorFlow/Keras) cannot be imported
-in this image (no tensorflow, keras, rdflib, spacy), and its own `tests.py` asserts nothing, so
-the TF-dependent part (score functions, losses, optimizer) is **parity unpinned** by reference
-golden vectors: it is a line-by-line restatement, cross-checked fp32-vs-fp64 and against torch
-autograd.  The NumPy/SciPy part (`generate_negative`, `oversample_data`, `gen_tail_data`,
-`gen_head_data`, `validate`) IS pinned: `oracle/ref_ast.py` executes the reference's own function
-bodies (AST-extracted, unmodified) in this container and `tests/golden/make_golden.py` froze
-their outputs into `tests/golden/*.npz|json`, which the restatement is checked against.
+as it stands in this image (no tensorflow, keras, rdflib, spacy), and its own `tests.py` asserts
+nothing.  Two mechanisms run the reference's OWN code here and freeze its outputs as fixtures:
+  * `oracle/ref_ast.py` executes the NumPy/SciPy function bodies of utils.py (AST-extracted,
+    unmodified): `generate_negative`, `oversample_data`, `gen_tail_data`, `gen_head_data`,
+    `validate`, `mrr`, `hits`, `pad` -> `tests/golden/make_golden.py`, `make_golden_full.py`;
+  * `oracle/ref_tf_exec.py` loads models.py and utils.py unmodified over a torch-backed
+    `tensorflow` stand-in: score functions, losses, regulariser, literal branch and their autodiff
+    gradients, in fp32 and fp64 -> `tests/golden/make_golden_fp.py` -> `tests/golden/fp_ref.npz`.
+The restatement in `kge_oracle.py` is held to both fixture sets (tests/test_cpu_*goldens*.py).
+Not pinned by reference code, because the reference only calls them: the Keras optimizers,
+`binary_crossentropy`, `GlorotUniform`, `Dense` (restated from their published definitions) and
+the rounding of TensorFlow's own kernels (the bars are stated against fp64 runs of the source).
 """

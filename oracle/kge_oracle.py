@@ -5,9 +5,11 @@ Two precisions are offered everywhere: `np.float32` mirrors the reference op by 
 fp32, NumPy broadcasting == TF broadcasting), `np.float64` is the "truth" the fp32 numbers are
 judged against.
 
-Parity status: the TF-dependent functions here are "parity unpinned" (no reference golden vectors
-exist and TF is not installable here); the NumPy functions are pinned by tests/golden/ (made by
-running the reference's own code through oracle/ref_ast.py).
+Parity status: the NumPy functions are pinned by tests/golden/ (made by running the reference's own
+code through oracle/ref_ast.py); the TF-typed functions (scores, losses, regulariser, literal branch,
+gradients) by tests/golden/fp_ref.npz (the reference's models.py / utils.py executed unmodified over
+the torch-backed `tensorflow` stand-in of oracle/ref_tf_exec.py); the optimizer arithmetic is a
+restatement of Keras' published update rules, cross-checked against torch.optim only.
 """
 from __future__ import annotations
 
