@@ -1,10 +1,6 @@
-timeout 600 python -m pytest tests/test_gpu_multi.py tests/test_gpu_peer.py -m gpu -x -q > gpurun_out/r2_pytest54.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2_pytest54.log
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2_bench54_n2.log 2> gpurun_out/r2_bench54_n2.err; echo "bench n2 rc=$?"
-tail -c 300 gpurun_out/r2_bench54_n2.err
-python - <<'PY'
-import json
-d=json.loads([l for l in open('gpurun_out/r2_bench54_n2.log') if l.startswith('{')][-1])
-print('n_gpus', d['n_gpus'], 'value %.4g ms %.4g e2e %.4g approx %.4g' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['approx_bf16']['value']), d['clocks'])
-for k in ('eval_c2','eval_c3','train_sharded_c5'):
-    print(k, json.dumps(d.get(k))[:500])
-PY
+set -x
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
+timeout 150 ncu --set full --clock-control none --import-source on -k regex:k_seqk_pairs -s 1 -c 1 -o gpurun_out/prof_r2_seqk_pairs_c5 \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --skip-secondary > gpurun_out/ncu_r2_seqk.log 2>&1; echo "ncu rc=$?"
+tail -3 gpurun_out/ncu_r2_seqk.log | cut -c1-300
+ls -la gpurun_out/prof_r2_seqk_pairs_c5*
