@@ -261,8 +261,11 @@ KGEB_API int64_t kgeb_rank_tc_packed_bytes(const kgeb_ctx* ctx, int64_t n_rows, 
 KGEB_API int kgeb_rank_tc_pack_entities(kgeb_ctx* ctx, const float* E_shard, int64_t n_rows, int mode, void* packed,
                                int64_t packed_bytes, kgeb_stream stream);
 /* workspace for Q queries (256-byte aligned): 256-byte header {uint32 appended, uint32 capacity, .., uint32 query scale at
- * byte 16}, worklist of capacity (q,c) pairs, packed queries, query norms.  After the stream has run the call, appended > capacity means the worklist overflowed:
- * counts are then incomplete and the call must be repeated with a larger worklist_cap. */
+ * byte 16}, worklist of capacity (q,c) pairs, packed queries, query norms and -- in the exact mode, when Q x num_entities >= 2^30 or
+ * KGEB_PAIRS_GROUPED=1 was set when the context was created -- the scratch of the on-device ordering of the worklist by entity
+ * (bins, slots, the ordered copy: 12 bytes per worklist entry + 4 bytes per entity).  After the stream has run the call,
+ * appended > capacity means the worklist overflowed: counts are then incomplete and the call must be repeated with a larger
+ * worklist_cap. */
 KGEB_API int64_t kgeb_rank_tc_workspace_bytes(const kgeb_ctx* ctx, int64_t Q, int mode, int64_t worklist_cap);
 KGEB_API int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_offset, int64_t n_rows, const void* packedE,
                     const float* qvec, const float* tscore, const int32_t* triples, int64_t Q, int side,

@@ -39,6 +39,8 @@ extern "C" int kgeb_create(kgeb_ctx** out, int device, int64_t num_entities, int
   if (const char* e = getenv("KGEB_TRAIN_KERNEL")) c->env_force_reg = strcmp(e, "reg") == 0;
   if (const char* e = getenv("KGEB_HOLE")) c->hole_fft = strcmp(e, "fft") == 0;
   if (const char* e = getenv("KGEB_ALLPAIRS")) c->env_allpairs_dense = strcmp(e, "dense") == 0;
+  c->env_pairs_grouped = -1;
+  if (const char* e = getenv("KGEB_PAIRS_GROUPED")) c->env_pairs_grouped = atoi(e) != 0;
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) c->ring_cfg[i][j].smem = -1;
   if ((e = cudaMalloc(&c->d_partials, sizeof(double) * 2 * KGEB_MAX_PARTIAL_BLOCKS)) != cudaSuccess ||
       (e = cudaMalloc(&c->d_ticket, sizeof(unsigned int))) != cudaSuccess ||

@@ -36,6 +36,7 @@ struct kgeb_ctx {
   // tuning knobs read from the environment ONCE at kgeb_create (KGEB_RING_CTAS, KGEB_RING_D, KGEB_TRAIN_KERNEL=reg):
   // measurement aids, never consulted on the launch path
   int env_ring_ctas, env_ring_d, env_force_reg, env_allpairs_dense;   // KGEB_ALLPAIRS=dense forces the m x m loss kernel (A/B)
+  int env_pairs_grouped;   // KGEB_PAIRS_GROUPED=0 / 1: never / always order the undecided pairs by entity before re-scoring; -1 (unset) = by size
   // launch configuration of the ring kernel per (negative mode, dropout flavour), filled on first use: the shared-memory
   // opt-in and the occupancy query are per-function driver calls that need not be repeated every step
   struct { int smem, occ; } ring_cfg[3][2];

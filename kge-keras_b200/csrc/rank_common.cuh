@@ -48,4 +48,9 @@ int kgeb_internal_filter_correct(kgeb_ctx* ctx, const float* E_shard, int64_t ro
 // counts[q] += [seq score(q,c) > tscore[q]] for the first min(wl_hdr[0], wl_cap) pairs (q, shard-local c) of the worklist
 int kgeb_internal_refine_worklist(kgeb_ctx* ctx, const float* E_shard, int64_t n_rows, const float* qvec, const float* tscore,
                                   int64_t Q, int side, const uint32_t* wl_hdr, uint32_t wl_cap, const uint2* wl, int32_t* counts,
-                                  cudaStream_t st);
+                                  cudaStream_t st, int grouped);
+// wl_group_kernels.cu: the worklist ordered by entity on the device (counting sort; lengths never reach the host)
+struct KgebWlGroupLayout { size_t bins, slot, out, cub, cub_bytes, total; };
+KgebWlGroupLayout kgeb_internal_wl_group_layout(int64_t n_rows, int64_t cap);
+int kgeb_internal_wl_group(kgeb_ctx* ctx, const uint32_t* hdr, uint32_t cap, const uint2* wl, int64_t n_rows, unsigned char* scratch,
+                           const uint2** ordered, const uint32_t** length, cudaStream_t st);

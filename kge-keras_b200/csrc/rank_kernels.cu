@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) k_query_prep(int kind, int side, int gamm
 // pass), then lane p accumulates ITS pair sequentially over k from shared memory (stride 33: conflict free).  The
 // arithmetic is exactly seq_score's (same order, same roundings), only the loads are cooperative.
 // ---------------------------------------------------------------------------------------------------
-enum { PAIRS_TARGET = 0, PAIRS_WORKLIST = 1, PAIRS_FILTER = 2 };
+enum { PAIRS_TARGET = 0, PAIRS_WORKLIST = 1, PAIRS_FILTER = 2, PAIRS_GROUPED = 3 };   // GROUPED: a worklist ordered by entity (wl_group_kernels.cu)
 #ifndef KGEB_PAIR_WARPS
 #define KGEB_PAIR_WARPS 2
 #endif
@@ -129,6 +129,7 @@ constexpr int PAIR_NBUF = KGEB_PAIR_NBUF;    // k-chunks of 32 floats in flight 
 template <int OP, int SRC>
 __global__ void __launch_bounds__(PAIR_WARPS * 32) k_seqk_pairs(PairArgs a) {
   constexpr bool HEAD = op_two_part<OP>();
+  constexpr bool GROUPED = SRC == PAIRS_GROUPED;   // consecutive pairs share entity rows: a warp stages each DISTINCT row once
   constexpr int LDP = PAIR_LDP, NB = PAIR_NBUF;
   constexpr int ROWS = HEAD ? 3 : 2;            // q, e (and the second query part) per pair
   extern __shared__ __align__(16) float pair_smem[];
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_seqk_pairs(PairArgs a) {
   const int sub = lane >> 3, l8 = lane & 7;  // 8 lanes x 16 bytes cover one 128-byte row segment; 4 pairs per copy instruction
   int64_t n;
   if (SRC == PAIRS_TARGET) n = a.Q;
-  else if (SRC == PAIRS_WORKLIST) n = a.wl_hdr[0] < a.wl_cap ? a.wl_hdr[0] : a.wl_cap;
+  else if (SRC == PAIRS_WORKLIST || GROUPED) n = a.wl_hdr[0] < a.wl_cap ? a.wl_hdr[0] : a.wl_cap;
   else n = a.offs[a.Q];
   const int64_t warp0 = (int64_t)blockIdx.x * PAIR_WARPS + w, nwarps = (int64_t)gridDim.x * PAIR_WARPS;
   const int nkc = (a.W + 31) / 32;
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_seqk_pairs(PairArgs a) {
       if (SRC == PAIRS_TARGET) {
         q = x;
         c = (int64_t)(a.side == KGEB_SIDE_TAIL ? a.triples[3 * q + 2] : a.triples[3 * q]) - a.row_offset;
-      } else if (SRC == PAIRS_WORKLIST) {
+      } else if (SRC == PAIRS_WORKLIST || GROUPED) {
         const uint2 pr = a.wl[x];
         q = pr.x; c = pr.y;
       } else {
@@ -171,6 +172,14 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_seqk_pairs(PairArgs a) {
     }
     // element offsets of the two rows of MY pair; the copy lanes fetch them from the owning lane
     const int64_t qoff = q * a.qw, eoff = c * (int64_t)a.ldE;
+    // GROUPED: lane p opens a new entity row when its candidate differs from lane p-1's; row p is staged into slot
+    // (number of rows opened at or before p) - 1 and every lane reads its slot (same-slot lanes read one address: a broadcast)
+    uint32_t firstmask = 0xffffffffu;
+    if (GROUPED) {
+      const int64_t cprev = __shfl_up_sync(0xffffffffu, c, 1);
+      firstmask = __ballot_sync(0xffffffffu, lane == 0 || c != cprev);
+    }
+    const int eslot = GROUPED ? __popc(firstmask & ((2u << lane) - 1u)) - 1 : lane;
     // issue the asynchronous copies of k-chunk kc (32 floats of every pair's rows) into buffer kc % NB
     auto issue = [&](int kc) {
       const int k = kc * 32 + 4 * l8;
@@ -181,7 +190,8 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_seqk_pairs(PairArgs a) {
         const int p = 4 * i + sub;
         const int64_t qo = __shfl_sync(0xffffffffu, qoff, p), eo = __shfl_sync(0xffffffffu, eoff, p);
         cp_async16(buf(b, 0) + p * LDP + 4 * l8, a.qvec + qo + (kin ? k : 0), kin);
-        cp_async16(buf(b, 1) + p * LDP + 4 * l8, a.Es + eo + (kin ? k : 0), kin);
+        if (!GROUPED) cp_async16(buf(b, 1) + p * LDP + 4 * l8, a.Es + eo + (kin ? k : 0), kin);
+        else if ((firstmask >> p) & 1u) cp_async16(buf(b, 1) + (__popc(firstmask & ((2u << p) - 1u)) - 1) * LDP + 4 * l8, a.Es + eo + (kin ? k : 0), kin);
         if (HEAD) cp_async16(buf(b, 2) + p * LDP + 4 * l8, a.qvec + qo + a.W + (kin ? k : 0), kin);
       }
       cp_async_commit();
@@ -197,7 +207,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_seqk_pairs(PairArgs a) {
       __syncwarp();
       const int b = kc % NB;
       const float* rq = buf(b, 0) + lane * LDP;
-      const float* re = buf(b, 1) + lane * LDP;
+      const float* re = buf(b, 1) + eslot * LDP;
       const float* rq2 = HEAD ? buf(b, 2) + lane * LDP : nullptr;
       const int klim = a.W - kc * 32 < 32 ? a.W - kc * 32 : 32;   // multiple of 4
       for (int kk = 0; kk < klim; kk += 4) {
@@ -218,7 +228,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_seqk_pairs(PairArgs a) {
     if (!valid) continue;
     const float sc = seq_finish<OP>(acc, a.fin);
     if (SRC == PAIRS_TARGET) a.tscore[q] = sc;
-    else if (SRC == PAIRS_WORKLIST) { if (sc > a.tscore[q]) atomicAdd(a.counts + q, 1); }
+    else if (SRC == PAIRS_WORKLIST || GROUPED) { if (sc > a.tscore[q]) atomicAdd(a.counts + q, 1); }
     else { if (sc > a.tscore[q]) atomicSub(a.counts + q, 1); }
   }
 }
@@ -963,14 +973,24 @@ int kgeb_internal_filter_correct(kgeb_ctx* ctx, const float* E_shard, int64_t ro
   return KGEB_OK;
 }
 
+// grouped != 0: `wl` is ordered by entity (kgeb_internal_wl_group) and wl_hdr points at its length; the kinds the tensor-core pass
+// serves have a grouped kernel, any other op takes the plain one (the order of a worklist never changes what is counted)
 int kgeb_internal_refine_worklist(kgeb_ctx* ctx, const float* E_shard, int64_t n_rows, const float* qvec, const float* tscore,
                                   int64_t Q, int side, const uint32_t* wl_hdr, uint32_t wl_cap, const uint2* wl, int32_t* counts,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, int grouped) {
   PairArgs a = {};
   a.Es = E_shard; a.row_offset = 0; a.n_rows = n_rows; a.ldE = ctx->ldE; a.W = ctx->we; a.qvec = qvec;
   a.qw = kgeb_query_width(ctx, side); a.tscore = const_cast<float*>(tscore); a.Q = Q; a.side = side; a.fin = seq_fin(ctx);
   a.wl_hdr = wl_hdr; a.wl_cap = wl_cap; a.wl = wl; a.counts = counts;
-  launch_pairs<PAIRS_WORKLIST>(host_op_for(ctx->kind, side), ctx->num_sms * 16, st, a);
+  const int op = host_op_for(ctx->kind, side), blocks = ctx->num_sms * 16;
+  if (grouped && (op == OP_DOT || op == OP_L2_TAIL || op == OP_L2_HEAD)) {
+    constexpr int SRC = PAIRS_GROUPED;
+    if (op == OP_DOT) KGEB_PAIRS_LAUNCH(OP_DOT)
+    else if (op == OP_L2_TAIL) KGEB_PAIRS_LAUNCH(OP_L2_TAIL)
+    else KGEB_PAIRS_LAUNCH(OP_L2_HEAD)
+  } else {
+    launch_pairs<PAIRS_WORKLIST>(op, blocks, st, a);
+  }
   KGEB_LAUNCH_OK(ctx);
   return KGEB_OK;
 }

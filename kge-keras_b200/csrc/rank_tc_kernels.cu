@@ -1103,7 +1103,14 @@ TcPackedLayout tc_packed_layout(const kgeb_ctx* ctx, int64_t n_rows, int mode) {
   return L;
 }
 // workspace: [header 256 B: appended, capacity, query scale bits at +16][worklist][packed queries][query norms][weighted query norms]
-struct TcWsLayout { size_t wl, packedQ, qnorm, qwnorm, q2, l2q, total; };
+struct TcWsLayout { size_t wl, packedQ, qnorm, qwnorm, q2, l2q, grp, total; };
+// The undecided pairs are ordered by entity before the exact re-scoring (wl_group_kernels.cu) when the pass is large enough for the
+// four extra launches to pay: on the 1M-entity shape the re-scoring is bound by L2 -> SM bandwidth and an entity occurs in ~12
+// pairs.  `rows` = the shard's rows at the call, the table's rows when the workspace is sized (never fewer).
+inline bool tc_pairs_grouped(const kgeb_ctx* ctx, int64_t Q, int64_t rows, int mode) {
+  if (mode != KGEB_TC_BF16X3_EXACT || ctx->env_pairs_grouped == 0) return false;
+  return ctx->env_pairs_grouped == 1 || Q * rows >= ((int64_t)1 << 30);
+}
 TcWsLayout tc_ws_layout(const kgeb_ctx* ctx, int64_t Q, int mode, int64_t worklist_cap) {
   const int64_t qt = tc_tiles(Q, TC_BM);
   TcWsLayout L;
@@ -1113,7 +1120,8 @@ TcWsLayout tc_ws_layout(const kgeb_ctx* ctx, int64_t Q, int mode, int64_t workli
   L.qwnorm = L.qnorm + tc_align((size_t)qt * TC_BM * 4);
   L.q2 = L.qwnorm + tc_align((size_t)qt * TC_BM * 4);                         // L2 mode: q' [qt*128, W] and six per-query arrays
   L.l2q = L.q2 + (tc_l2_kind(ctx) ? tc_align((size_t)qt * TC_BM * ctx->we * 4) : 0);
-  L.total = L.l2q + (tc_l2_kind(ctx) ? tc_align((size_t)6 * qt * TC_BM * 4) : 0);
+  L.grp = L.l2q + (tc_l2_kind(ctx) ? tc_align((size_t)6 * qt * TC_BM * 4) : 0);
+  L.total = L.grp + (tc_pairs_grouped(ctx, Q, ctx->N, mode) ? tc_align(kgeb_internal_wl_group_layout(ctx->N, worklist_cap).total) : 0);
   return L;
 }
 
@@ -1353,7 +1361,16 @@ extern "C" int kgeb_rank_1n_tc(kgeb_ctx* ctx, const float* E_shard, int64_t row_
   KGEB_LAUNCH_OK(ctx);
   KGEB_TIME_BEGIN(ctx, KGEB_TIMED_RANK_REFINE, st);
   // hdr[0] = pairs appended, hdr[1] = capacity (written by the kernel): the host checks hdr[0] <= hdr[1] after the pass
-  const int rc = kgeb_internal_refine_worklist(ctx, E_shard, n_rows, qvec, tscore, Q, side, hdr, (uint32_t)worklist_cap, wl, counts, st);
+  int rc;
+  if (tc_pairs_grouped(ctx, Q, n_rows, mode)) {
+    const uint2* ordered = nullptr;
+    const uint32_t* length = nullptr;
+    rc = kgeb_internal_wl_group(ctx, hdr, (uint32_t)worklist_cap, wl, n_rows, ws + W.grp, &ordered, &length, st);
+    if (rc == KGEB_OK)
+      rc = kgeb_internal_refine_worklist(ctx, E_shard, n_rows, qvec, tscore, Q, side, length, (uint32_t)worklist_cap, ordered, counts, st, 1);
+  } else {
+    rc = kgeb_internal_refine_worklist(ctx, E_shard, n_rows, qvec, tscore, Q, side, hdr, (uint32_t)worklist_cap, wl, counts, st, 0);
+  }
   KGEB_TIME_END(ctx, KGEB_TIMED_RANK_REFINE, st);
   return rc;
 }

@@ -368,3 +368,58 @@ def test_one_cta_per_tile_variant_in_child_process():
                        text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "passed" in r.stdout
+
+
+# ---- the undecided pairs ordered by entity before the exact re-scoring (wl_group_kernels.cu, k_seqk_pairs<OP, PAIRS_GROUPED>) -------
+@pytest.mark.parametrize("case", ["all_ties", "near_ties_complex", "transe_l2_tail", "transe_l2_head", "sharded"])
+def test_tc_exact_with_the_worklist_grouped_by_entity(case, monkeypatch):
+    """KGEB_PAIRS_GROUPED=1 forces the path the large shapes take by themselves: a counting sort of the worklist by entity on the
+    device, then the re-scoring kernel whose warps stage every distinct entity row once.  The integer counts must not change:
+    identical to the CUDA-core kernel with every candidate tied (each entity in Q pairs: long runs), with clustered near-ties
+    (runs of mixed length, many warps that straddle runs), for the L2 operand pairs, and summed over shards."""
+    abi = _abi()
+    from KGEkeras._engine import Engine
+    monkeypatch.setenv("KGEB_PAIRS_GROUPED", "1")        # read once, when the context is created
+    rng = np.random.default_rng(23)
+    if case == "all_ties":
+        N, R, d, Q = 600, 3, 16, 90
+        E = np.repeat(ko.glorot_uniform(rng, 1, d), N, axis=0)
+        Rm = ko.glorot_uniform(rng, R, d)
+        eng = Engine(abi.DISTMULT, N, R, d, d, 12.0, E=E, R=Rm)
+        tri = rand_triples(rng, Q, N, R)
+        stats = {}
+        got = eng.rank_counts_tc(tri, 0, mode=abi.TC_BF16X3_EXACT, stats=stats).cpu().numpy()
+        assert stats["undecided_pairs"] >= Q * (N - 1)
+        np.testing.assert_array_equal(got, eng.rank_counts(tri, 0).cpu().numpy())
+        return
+    if case == "near_ties_complex":
+        N, R, W = 512, 3, 64
+        E = _near_tie_table(rng, N, rng.uniform(-1, 1, W).astype(np.float32))
+        Rm = rng.uniform(-1, 1, (R, W)).astype(np.float32)
+        stats, _, _ = _check_exact_against_cuda_core(E, Rm, kind=ko.COMPLEX, Q=96, seed=5)
+        assert stats["undecided_pairs"] > 0
+        return
+    if case.startswith("transe_l2"):
+        side = case.split("_")[-1]
+        N, d, Q = 700, 28, 129
+        base = ko.glorot_uniform(rng, 1, d) * 3
+        E = (base + rng.normal(size=(N, d)) * 1e-6).astype(np.float32)     # clustered rows: distances agree to ~1e-6
+        Rm = ko.glorot_uniform(rng, 5, d) * 3
+        eng = Engine(abi.TRANSE_L2, N, 5, d, d, 12.0, E=E, R=Rm)
+        tri = rand_triples(rng, Q, N, 5)
+        sd = 0 if side == "tail" else 1
+        stats = {}
+        got = eng.rank_counts_tc(tri, sd, mode=abi.TC_F16X3_EXACT, stats=stats).cpu().numpy()
+        assert stats["undecided_pairs"] > 0
+        np.testing.assert_array_equal(got, eng.rank_counts(tri, sd).cpu().numpy())
+        return
+    # sharded: partial counts over row ranges add up to the whole, filter included
+    eng, E, Rm, tri, fh, ft = _rank_case(ko.COMPLEX, 1500, 5, 40, 300, seed=9, dyadic=False)
+    offs, ids = ko.filter_csr(tri, "tail", ft)
+    whole_f = eng.rank_counts(tri, 0, offs, ids).cpu().numpy()
+    for G in (1, 3):
+        per = -(-1500 // G)
+        acc = torch.zeros(len(tri), dtype=torch.int32, device="cuda")
+        for g in range(G):
+            eng.rank_counts_tc(tri, 0, offs, ids, row_range=(g * per, min(1500, (g + 1) * per)), counts=acc, mode=abi.TC_BF16X3_EXACT)
+        np.testing.assert_array_equal(acc.cpu().numpy(), whole_f)
