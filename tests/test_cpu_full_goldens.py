@@ -50,3 +50,35 @@ def test_trained_tables_rank_far_better_than_chance():
             continue
         chance = (np.log(meta["N"]) + 0.58) / meta["N"]
         assert meta["metrics_f64"]["mrr"] > 2 * chance, (name, meta["metrics_f64"]["mrr"], chance)
+
+
+REFMODEL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "full_refmodel.npz")
+SMALL = [n for n in sorted(ff.CONFIGS) if not ff.CONFIGS[n].get("quant")]
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_reference_model_classes_through_reference_validate_give_the_golden_ranks(name):
+    """tests/golden/full_refmodel.npz (made by tests/golden/make_golden_refmodel.py): the reference's own model class (models.py run
+    unmodified over the stand-in of oracle/ref_tf_exec.py, Keras' 32-row predict batches) handed to the reference's own validate.
+    Every one of the 2 x |test| ranks equals the fixture's golden rank -- the ranks the CUDA path must and does reproduce exactly
+    (tests/test_gpu_full_goldens.py) -- so on these configurations the GPU result IS the reference pipeline's result."""
+    z = np.load(REFMODEL)
+    fx = ff.load(name)
+    np.testing.assert_array_equal(z[name + "/tail_ranks"], fx["tail_ranks"])
+    np.testing.assert_array_equal(z[name + "/head_ranks"], fx["head_ranks"])
+    keys = [str(k) for k in z[name + "/metric_keys"]]
+    assert len(keys) == 15
+    for k, v in zip(keys, z[name + "/metrics"]):
+        assert abs(v - fx["meta"]["metrics_f64"][k]) <= 1e-5 * max(1.0, abs(v)), k     # SciPy >= 1.11 returns fp32 ranks: fp32 means
+
+
+def test_reference_pipeline_regenerates_live():
+    from oracle import ref_ast, ref_tf_exec
+    if not (ref_ast.available() and ref_tf_exec.available()):
+        pytest.skip("/root/reference is only mounted in the build container")
+    import make_golden_refmodel as mg
+    live = mg.generate(["nations_TransE_L2_gammaNeg_d50", "UMLS_HolE_d64"])
+    z = np.load(REFMODEL)
+    for k, v in live.items():
+        if v.dtype.kind in "iu":
+            np.testing.assert_array_equal(v, z[k], err_msg=k)
