@@ -84,7 +84,7 @@ def test_reference_pipeline_regenerates_live():
             np.testing.assert_array_equal(v, z[k], err_msg=k)
 
 
-@pytest.mark.parametrize("name", ["WN18RR_TransE_L1_d200"])
+@pytest.mark.parametrize("name", ["WN18RR_TransE_L1_d200", "FB15k-237_ComplEx_d200"])
 def test_reference_pipeline_on_the_large_config_differs_only_at_near_ties(name):
     """C2 (WN18RR, TransE-L1 d=200, all 3 134 test triples x 40 943 candidates, both sides) through the reference's own model class
     and validate (tests/golden/make_golden_refmodel.py <name>; 13 minutes of CPU).  With 40 943 candidates per query two fp32
@@ -107,7 +107,7 @@ def test_reference_pipeline_on_the_large_config_differs_only_at_near_ties(name):
         diff = np.nonzero(ref_r != gold)[0]
         total_diff += len(diff)
         assert len(diff) <= 0.25 * n, (side, len(diff))
-        for i in diff:
+        for i in diff[:: max(1, len(diff) // 100)]:      # every differing query up to 100 per side, an even sample beyond that
             tri = ds["test"][i:i + 1]
             sc = ko.all_entity_scores(kind, E, R, tri, side, meta["gamma"], np.float64)[0]
             tgt = int(tri[0, 2] if side == "tail" else tri[0, 0])
