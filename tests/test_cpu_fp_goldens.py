@@ -186,4 +186,7 @@ def test_fixture_regenerates_from_the_reference():
         if v.dtype.kind in "iuU":
             assert np.array_equal(v, w), k
         else:
-            np.testing.assert_allclose(v, w, rtol=1e-6 if v.dtype == np.float32 else 1e-12, atol=1e-30, err_msg=k)
+            # same machine, same thread count: bit-identical; another thread count may re-associate a torch reduction, so entries
+            # that cancel to ~0 are held to the array's scale instead of their own
+            tol = 1e-6 if v.dtype == np.float32 else 1e-12
+            np.testing.assert_allclose(v, w, rtol=tol, atol=tol * max(1e-30, float(np.max(np.abs(w)))), err_msg=k)
